@@ -1,0 +1,241 @@
+"""ctypes bindings for the parity oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  Nothing under simpleraytracing_b200/ does.
+
+  Oracle      oracle/liboracle.so       plain-C restatement (srt_oracle.c)
+  Reference   oracle/_ref/libsrt_ref.so the reference's own Ray/Triangle/TriangleMesh
+                                        sources behind the same interface (ref_shim.cpp)
+"""
+import ctypes as C
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+
+
+class Camera(C.Structure):
+    """RayTracerInfo (main-pthreads-lbuffer.cxx:125-135) as plain floats."""
+    _fields_ = [(n, C.c_float * 3) for n in
+                ("detector", "origin", "up", "right", "lower", "upper", "range",
+                 "light_position", "light_direction")]
+
+    def vec(self, name):
+        return np.array(getattr(self, name)[:], dtype=np.float32)
+
+
+def build(force=False):
+    """Compile liboracle.so (and _ref/ when /root/reference is present)."""
+    if force or not (HERE / "liboracle.so").exists() or \
+            (HERE / "srt_oracle.c").stat().st_mtime > (HERE / "liboracle.so").stat().st_mtime:
+        subprocess.run(["make", "-C", str(HERE), str(HERE / "liboracle.so")], check=True,
+                       stdout=subprocess.DEVNULL)
+    if Path("/root/reference/src").is_dir():
+        subprocess.run(["make", "-C", str(HERE), "ref"], check=True, stdout=subprocess.DEVNULL)
+
+
+def _opt(a, dtype):
+    if a is None:
+        return None
+    assert a.dtype == dtype and a.flags.c_contiguous
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """Plain-C restatement."""
+
+    def __init__(self):
+        build()
+        self.lib = C.CDLL(str(HERE / "liboracle.so"))
+        L = self.lib
+        L.oracle_bbox.argtypes = [_f32p, C.c_uint64, _f32p, _f32p]
+        L.oracle_init_camera.argtypes = [_f32p, _f32p, C.POINTER(Camera)]
+        L.oracle_pixel_spacing.argtypes = [C.POINTER(Camera), C.c_uint32, C.c_uint32]
+        L.oracle_pixel_spacing.restype = C.c_float
+        L.oracle_make_ray.argtypes = [C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _f32p, _f32p]
+        L.oracle_intersect.argtypes = [_f32p, _f32p, _f32p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.oracle_ray_direction.argtypes = [_f32p, _f32p]
+        L.oracle_triangle_normal.argtypes = [_f32p, _f32p]
+        L.oracle_triangle_area.argtypes = [_f32p]
+        L.oracle_triangle_area.restype = C.c_float
+        L.oracle_render_lbuffer.argtypes = [_f32p, _u32p, C.c_int, C.POINTER(Camera), C.c_uint32, C.c_uint32,
+                                            C.c_uint64, C.c_uint64, C.c_int, _f32p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]
+        L.oracle_repair.argtypes = [_f32p, C.c_uint32, C.c_uint32, _f32p]
+        L.oracle_render_sort.argtypes = [_f32p, _u32p, C.c_int, C.POINTER(Camera), C.c_uint32, C.c_uint32,
+                                         C.c_uint64, C.c_uint64, _f32p, C.c_void_p]
+        L.oracle_save_text.argtypes = [C.c_char_p, _f32p, C.c_uint32, C.c_uint32]
+        L.oracle_partition.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+
+    # scene ---------------------------------------------------------------
+    def camera(self, tri):
+        tri = np.ascontiguousarray(tri, np.float32).reshape(-1)
+        lo = np.empty(3, np.float32); hi = np.empty(3, np.float32)
+        self.lib.oracle_bbox(tri, tri.size // 9, lo, hi)
+        cam = Camera()
+        self.lib.oracle_init_camera(lo, hi, C.byref(cam))
+        return cam
+
+    def pixel_spacing(self, cam, W, H):
+        return np.float32(self.lib.oracle_pixel_spacing(C.byref(cam), W, H))
+
+    def make_ray(self, cam, W, H, row, col):
+        a = np.empty(3, np.float32); b = np.empty(3, np.float32)
+        self.lib.oracle_make_ray(C.byref(cam), W, H, row, col, a, b)
+        return a, b
+
+    def ray_direction(self, d):
+        out = np.empty(3, np.float32)
+        self.lib.oracle_ray_direction(np.ascontiguousarray(d, np.float32), out)
+        return out
+
+    def intersect(self, o, d, tri9):
+        t = C.c_float(0); st = C.c_int(-1)
+        hit = self.lib.oracle_intersect(np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32),
+                                        np.ascontiguousarray(tri9, np.float32).reshape(-1), C.byref(t), C.byref(st))
+        return bool(hit), np.float32(t.value), st.value
+
+    def triangle_normal(self, tri9):
+        n = np.empty(3, np.float32)
+        self.lib.oracle_triangle_normal(np.ascontiguousarray(tri9, np.float32).reshape(-1), n)
+        return n
+
+    def triangle_area(self, tri9):
+        return np.float32(self.lib.oracle_triangle_area(np.ascontiguousarray(tri9, np.float32).reshape(-1)))
+
+    # renders --------------------------------------------------------------
+    def render_lbuffer(self, tri, mesh_ntris, cam, W, H, pixel_range=None, threads=None, want_stages=False):
+        """-> dict(L, dist, ssum, hits[, stages]); arrays are W*H (only the range is written)."""
+        tri = np.ascontiguousarray(tri, np.float32).reshape(-1)
+        nt = np.ascontiguousarray(mesh_ntris, np.uint32)
+        assert tri.size == 9 * int(nt.sum())
+        n = W * H
+        b, e = (0, n - 1) if pixel_range is None else pixel_range
+        threads = threads or os.cpu_count() or 1
+        out = dict(L=np.zeros(n, np.float32), dist=np.zeros(n, np.float32),
+                   ssum=np.zeros(n, np.int32), hits=np.zeros(n, np.uint32))
+        stages = np.zeros(4, np.uint64)
+        if e >= b:
+            self.lib.oracle_render_lbuffer(tri, nt, len(nt), C.byref(cam), W, H, b, e, threads, out["L"],
+                                           _opt(out["dist"], np.float32), _opt(out["ssum"], np.int32),
+                                           _opt(out["hits"], np.uint32),
+                                           stages.ctypes.data_as(C.c_void_p) if want_stages else None)
+        if want_stages:
+            out["stages"] = stages
+        return out
+
+    def repair(self, L, W, H):
+        img = np.empty(W * H, np.float32)
+        self.lib.oracle_repair(np.ascontiguousarray(L, np.float32).reshape(-1), W, H, img)
+        return img
+
+    def render_sort(self, tri, mesh_ntris, cam, W, H, threads=None):
+        tri = np.ascontiguousarray(tri, np.float32).reshape(-1)
+        nt = np.ascontiguousarray(mesh_ntris, np.uint32)
+        n = W * H
+        img = np.zeros(n, np.float32); hits = np.zeros(n, np.uint32)
+        threads = threads or os.cpu_count() or 1
+        cuts = np.linspace(0, n, threads + 1).astype(np.int64)
+
+        def job(i):
+            if cuts[i + 1] > cuts[i]:
+                self.lib.oracle_render_sort(tri, nt, len(nt), C.byref(cam), W, H, int(cuts[i]), int(cuts[i + 1] - 1),
+                                            img, hits.ctypes.data_as(C.c_void_p))
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(job, range(threads)))
+        return img, hits
+
+    def save_text(self, path, img, W, H):
+        return self.lib.oracle_save_text(str(path).encode(), np.ascontiguousarray(img, np.float32).reshape(-1), W, H)
+
+    def partition(self, total, n):
+        s = np.zeros(n, np.uint64); e = np.zeros(n, np.uint64)
+        self.lib.oracle_partition(total, n, s.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p))
+        return s, e
+
+
+class Reference:
+    """The reference's own classes (oracle/_ref/libsrt_ref.so). May be absent."""
+
+    @staticmethod
+    def available():
+        return (HERE / "_ref" / "libsrt_ref.so").exists()
+
+    def __init__(self):
+        build()
+        self.lib = C.CDLL(str(HERE / "_ref" / "libsrt_ref.so"))
+        L = self.lib
+        L.ref_scene_camera.argtypes = [_f32p, _u32p, C.c_int, C.POINTER(Camera)]
+        L.ref_intersect.argtypes = [_f32p, _f32p, _f32p, C.POINTER(C.c_float)]
+        L.ref_ray_direction.argtypes = [_f32p, _f32p]
+        L.ref_triangle_normal.argtypes = [_f32p, _f32p]
+        L.ref_triangle_area.argtypes = [_f32p]
+        L.ref_triangle_area.restype = C.c_float
+        L.ref_render_lbuffer.argtypes = [_f32p, _u32p, C.c_int, C.POINTER(Camera), C.c_uint32, C.c_uint32,
+                                         C.c_uint64, C.c_uint64, C.c_int, _f32p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_render_sort.argtypes = [_f32p, _u32p, C.c_int, C.POINTER(Camera), C.c_uint32, C.c_uint32,
+                                      C.c_uint64, C.c_uint64, _f32p]
+        L.ref_save_text.argtypes = [C.c_char_p, _f32p, C.c_uint32, C.c_uint32]
+
+    def camera(self, tri, mesh_ntris):
+        tri = np.ascontiguousarray(tri, np.float32).reshape(-1)
+        cam = Camera()
+        self.lib.ref_scene_camera(tri, np.ascontiguousarray(mesh_ntris, np.uint32), len(mesh_ntris), C.byref(cam))
+        return cam
+
+    def intersect(self, o, d, tri9):
+        t = C.c_float(0)
+        hit = self.lib.ref_intersect(np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32),
+                                     np.ascontiguousarray(tri9, np.float32).reshape(-1), C.byref(t))
+        return bool(hit), np.float32(t.value)
+
+    def ray_direction(self, d):
+        out = np.empty(3, np.float32)
+        self.lib.ref_ray_direction(np.ascontiguousarray(d, np.float32), out)
+        return out
+
+    def triangle_normal(self, tri9):
+        n = np.empty(3, np.float32)
+        self.lib.ref_triangle_normal(np.ascontiguousarray(tri9, np.float32).reshape(-1), n)
+        return n
+
+    def triangle_area(self, tri9):
+        return np.float32(self.lib.ref_triangle_area(np.ascontiguousarray(tri9, np.float32).reshape(-1)))
+
+    def render_lbuffer(self, tri, mesh_ntris, cam, W, H, pixel_range=None, threads=None):
+        tri = np.ascontiguousarray(tri, np.float32).reshape(-1)
+        nt = np.ascontiguousarray(mesh_ntris, np.uint32)
+        n = W * H
+        b, e = (0, n - 1) if pixel_range is None else pixel_range
+        threads = threads or os.cpu_count() or 1
+        out = dict(L=np.zeros(n, np.float32), dist=np.zeros(n, np.float32),
+                   ssum=np.zeros(n, np.int32), hits=np.zeros(n, np.uint32))
+        if e >= b:
+            self.lib.ref_render_lbuffer(tri, nt, len(nt), C.byref(cam), W, H, b, e, threads, out["L"],
+                                        _opt(out["dist"], np.float32), _opt(out["ssum"], np.int32),
+                                        _opt(out["hits"], np.uint32))
+        return out
+
+    def render_sort(self, tri, mesh_ntris, cam, W, H, threads=None):
+        tri = np.ascontiguousarray(tri, np.float32).reshape(-1)
+        nt = np.ascontiguousarray(mesh_ntris, np.uint32)
+        n = W * H
+        img = np.zeros(n, np.float32)
+        threads = threads or os.cpu_count() or 1
+        cuts = np.linspace(0, n, threads + 1).astype(np.int64)
+
+        def job(i):
+            if cuts[i + 1] > cuts[i]:
+                self.lib.ref_render_sort(tri, nt, len(nt), C.byref(cam), W, H, int(cuts[i]), int(cuts[i + 1] - 1), img)
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(job, range(threads)))
+        return img
+
+    def save_text(self, path, img, W, H):
+        return self.lib.ref_save_text(str(path).encode(), np.ascontiguousarray(img, np.float32).reshape(-1), W, H)
