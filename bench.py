@@ -1,0 +1,325 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the X-ray L-buffer hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size 2048] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): dragon
+(22 866 triangles) L-buffer + Beer-Lambert attenuation + artefact repair at 2048 x 2048.
+A step is ONE frame: render (row band per rank) -> in-place NCCL all_gather of the bands
+(N > 1) -> repair on the assembled frame.  The frame is a fixed amount of work that is
+sharded over the ranks: scaling = "strong".
+
+Keys of the JSON line (see the task contract):
+  value        whole-job ray-triangle tests/s, scene + frame buffers resident in HBM
+  e2e          the same through the C-ABI with HOST buffers: srt_set_meshes (host vertices),
+               srt_set_camera, band render, all_gather, repair, image back to host memory
+  roofline     FP32-pipe roofline of the render kernel: 19 algorithmic flop per (ray, triangle)
+               test over the FFMA peak measured live on this GPU
+  cpu_baseline the reference's CPU implementation (oracle/_ref, else the oracle port) on a
+               bounded sample of the same frame on the host cores (rank 0, N = 1 only)
+
+--impl reference times that CPU implementation as the bench arm itself.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+F_ALG = 19.0            # algorithmic flop per test
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.45 at 1965 MHz
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def cpu_reference_engine():
+    """(kind, engine): the reference's own classes when oracle/_ref is built, else the oracle port."""
+    from oracle.pyoracle import Oracle, Reference
+    if Reference.available() or Path("/root/reference/src").is_dir():
+        try:
+            return "reference", Reference()
+        except Exception:
+            pass
+    return "port", Oracle()
+
+
+def cpu_sample_rate(engine, kind, tri, W, H, seconds, threads):
+    """Time the CPU L-buffer path on a contiguous pixel range through the frame centre.
+    Brute-force cost is uniform per pixel, so tests/s of the sample is tests/s of the frame."""
+    ntri = len(tri)
+    cam = engine.camera(tri, [ntri]) if kind == "reference" else engine.camera(tri)
+    start = (H // 2) * W
+    probe = max(threads * 4, 64)
+    t0 = time.perf_counter()
+    engine.render_lbuffer(tri, [ntri], cam, W, H, pixel_range=(start, start + probe - 1), threads=threads)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    n_pix = int(min(W * H - start, max(probe, probe * seconds / dt)))
+    t0 = time.perf_counter()
+    engine.render_lbuffer(tri, [ntri], cam, W, H, pixel_range=(start, start + n_pix - 1), threads=threads)
+    dt = time.perf_counter() - t0
+    return n_pix * ntri / dt, n_pix, dt
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    from simpleraytracing_b200 import scene
+    tri = scene.dragon()
+    W = H = args.size
+    kind, eng = cpu_reference_engine()
+    threads = os.cpu_count() or 1
+    per_step = max(0.5, min(8.0, 150.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample_rate(eng, kind, tri, W, H, per_step, threads)
+    rates, pix, secs = [], 0, 0.0
+    for _ in range(args.steps):
+        r, n_pix, dt = cpu_sample_rate(eng, kind, tri, W, H, per_step, threads)
+        rates.append(r); pix += n_pix; secs += dt
+    value = pix * len(tri) / secs
+    frame_ms = W * H * len(tri) / value * 1e3
+    sample = f"{pix // max(1, args.steps)} contiguous pixels of the {W}x{H} frame per step, all {len(tri)} triangles"
+    line = {
+        "impl": "reference", "metric": "ray-triangle tests/s (X-ray L-buffer, dragon)", "value": value,
+        "unit": "tests/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "dragon mesh fixture (tests/golden/dragon_mesh.npz); CPU, no GPU used",
+        "config": {"workload": f"X-ray L-buffer {W}x{H} dragon (BASELINE configs[2])", "triangles": len(tri),
+                   "ms_per_step_note": "full-frame time extrapolated from the sample (uniform cost per pixel)"},
+        "cpu_baseline": {"value": value, "unit": "tests/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from simpleraytracing_b200 import Context, Library, scene
+    from simpleraytracing_b200.bands import BandLayout
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    lib = Library()
+    ctx = Context(local, lib)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    tri = scene.dragon()
+    ntri = len(tri)
+    W = H = args.size
+    lo, hi = lib.scene_bbox([(tri, float(scene.MU_MESH0))])
+    cam = lib.camera_from_bbox(lo, hi, W, H)
+    meshes = [(tri, float(scene.MU_MESH0))]
+    ctx.set_meshes(meshes)
+    ctx.set_camera(cam)
+    params = lib.default_params(kernel=args.kernel, pixels_per_thread=args.ppt)
+
+    lay = BandLayout(H, W, world, rank)
+    frame = lay.new_frame(torch.float32, dev)
+    image = torch.empty(H * W, dtype=torch.float32, device=dev)
+    host_image = torch.empty(H * W, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def step_device():
+        ctx.render_lbuffer_device(params, lay.rows, frame.data_ptr())
+        full = lay.all_gather_(frame)
+        ctx.repair_device(params, full.data_ptr(), image.data_ptr())
+
+    def step_e2e():
+        # the call a user of the reference makes: host meshes + camera in, host image out
+        ctx.set_meshes(meshes)
+        ctx.set_camera(cam)
+        ctx.render_lbuffer_device(params, lay.rows, frame.data_ptr())
+        full = lay.all_gather_(frame)
+        ctx.repair_device(params, full.data_ptr(), image.data_ptr())
+        host_image.copy_(image, non_blocking=True)
+        stream.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sync_each):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        wall = 0.0
+        for a, b in ev:
+            flush.fill_(1)                      # L2 flush between timed iterations (outside the event pair)
+            if sync_each:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            a.record(stream)
+            fn()
+            b.record(stream)
+            if sync_each:
+                torch.cuda.synchronize()
+                wall += time.perf_counter() - t0
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        if sync_each:
+            ms = max(ms, wall * 1e3)            # host work (pre-pack) is part of the end-to-end time
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # --- FP32 peak of this GPU (roofline denominator) before the clocks ramp down
+    peak_tf = ctx.ffma_peak_tflops(3)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step_device, args.steps, args.warmup, sync_each=False)
+    # render-kernel-only time for the roofline: CUDA events around the kernel, on its stream
+    barrier()
+    kern_ms = []
+    for _ in range(max(3, min(args.steps, 10))):
+        flush.fill_(1)
+        ctx.render_lbuffer_device(params, lay.rows, frame.data_ptr())
+        kern_ms.append(ctx.timing().render_ms)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms = timed(step_e2e, max(1, min(args.steps, 10)), max(1, min(args.warmup, 3)), sync_each=True)
+    e2e_steps = max(1, min(args.steps, 10))
+
+    tests_frame = float(W) * H * ntri
+    value = tests_frame * args.steps / (total_ms * 1e-3)
+    e2e_value = tests_frame * e2e_steps / (e2e_ms * 1e-3)
+    kt = float(np.mean(kern_ms)) * 1e-3
+    band_tests = float(lay.rows[1] - lay.rows[0]) * W * ntri
+    achieved_tf = band_tests * F_ALG / kt / 1e12
+    peak, peak_src = (peak_tf, "FFMA probe on this GPU (srt_debug_ffma_peak)") if peak_tf > 1 else \
+        (NOMINAL_FP32_TFLOPS, "nominal 148 SM x 128 lanes x 2 x 1965 MHz")
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            kind, eng = cpu_reference_engine()
+            threads = os.cpu_count() or 1
+            r, n_pix, dt = cpu_sample_rate(eng, kind, tri, W, H, args.cpu_seconds, threads)
+            cpu = {"value": r, "unit": "tests/s", "cores": threads, "kind": kind,
+                   "sample": f"{n_pix} contiguous pixels of the {W}x{H} frame x {ntri} triangles in {dt:.1f} s"}
+        line = {
+            "metric": "ray-triangle tests/s (X-ray L-buffer, dragon)", "value": value, "unit": "tests/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "dragon mesh fixture (reference dragon.ply, 22866 triangles); synthetic camera from its bbox",
+            "config": {"workload": f"X-ray L-buffer {W}x{H} dragon, row bands over {world} GPU(s) (BASELINE configs[2])",
+                       "triangles": ntri, "kernel": ctx.timing().kernel_used, "l2": "256 MiB flush write between steps",
+                       "step": "band render + all_gather + repair"},
+            "e2e": {"value": e2e_value, "unit": "tests/s", "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "h2d_bytes_per_step": int(tri.nbytes + 4 * 16 + 4 * (W + H)) + 0,
+                    "d2h_bytes_per_step": int(H * W * 4)},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "lbuffer_filtered_kernel", "kernel_ms": kt * 1e3,
+                         "flop_per_test": F_ALG, "tests_per_launch": band_tests},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 exact, 2 filtered")
+    ap.add_argument("--ppt", type=int, default=0, help="pixels per thread (0 = auto)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

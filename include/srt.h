@@ -1,0 +1,181 @@
+/*
+ * srt.h -- C ABI of the B200-native SimpleRayTracing hot path.
+ *
+ * The reference (Brandagot/SimpleRayTracing) has no plugin/FFI layer: every
+ * driver inlines its own per-pixel loop.  The replaceable unit is the
+ * driver-level render function, and this header is the boundary a maintainer
+ * binds instead of it (see INTEGRATION.md for the C++ shim):
+ *
+ *   reference interface                                     replaced by
+ *   ------------------------------------------------------  ---------------------------
+ *   renderLoop(Image&, const vector<TriangleMesh>&,         srt_set_meshes + srt_set_camera
+ *              RayTracerInfo&)            src/main.cxx:159-161,626      + srt_render_xray
+ *   void* renderLoopCallBack(void* PThreadData*)            srt_render_lbuffer (row band)
+ *              src/main-pthreads-lbuffer.cxx:186,733-813
+ *   global std::vector<float> L_buffer    ...lbuffer.cxx:254,314        L_out of srt_render_lbuffer
+ *   repair + Image::setPixel loop         ...lbuffer.cxx:329-404        srt_repair
+ *   initialiseRayTracing / getBBox        ...lbuffer.cxx:585-667        srt_scene_bbox + srt_camera_from_bbox
+ *   pthreadWorkLoadAllocation             ...lbuffer.cxx:694-725        srt_partition_rows
+ *   MPI gather of pixel ranges            src/main-mpi.cxx:854-881      row bands + one NCCL allgather
+ *                                                                       on the *_device buffers
+ *   renderLoop(Image&, meshes, detector, origin, up, right, Light)      srt_render_shaded
+ *              src/main-omp.cxx:136-142,588-797
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success
+ * and a negative srt_status on failure (message: srt_last_error); nothing
+ * throws across the boundary; the caller owns every host pointer, the library
+ * owns all device memory except the buffers handed to the *_device entry
+ * points.  One context drives one GPU (one process per GPU); calls on a
+ * context must not be made concurrently.  There is no CPU fallback: without a
+ * usable sm_100 device srt_create fails.
+ */
+#ifndef SRT_H
+#define SRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRT_VERSION 100
+
+typedef enum {
+    SRT_OK = 0,
+    SRT_ERR_INVALID = -1,      /* bad argument (NULL, sizes, order of calls)  ~ std::length_error / out_of_range */
+    SRT_ERR_CUDA = -2,         /* CUDA runtime failure                                                */
+    SRT_ERR_NO_DEVICE = -3,    /* no CUDA device / not an sm_100 part                                 */
+    SRT_ERR_NOMEM = -4
+} srt_status;
+
+typedef struct srt_ctx srt_ctx;
+
+/* Material (include/Material.h:86-124): plain data, shaded variant only. */
+typedef struct {
+    float ambient[3], diffuse[3], specular[3];
+    float shininess;
+} srt_material;
+
+/* One TriangleMesh (include/TriangleMesh.h:106-169) flattened. */
+typedef struct {
+    const float*   vertices;    /* 9 floats per triangle: P1 P2 P3 (Triangle::getP1..P3)             */
+    const float*   normals;     /* 3 per triangle == Triangle::getNormal(); NULL -> computed exactly
+                                   as Triangle::computeNormal (include/Triangle.inl:170-178)          */
+    const float*   texcoords;   /* 9 per triangle (3 x Vec3) or NULL                                  */
+    uint32_t       n_triangles;
+    float          mu;          /* linear attenuation coefficient of this mesh's material (1/cm);
+                                   the reference hard-codes 0.1037f (mesh 0) / 0.3971f (others),
+                                   src/main-pthreads-lbuffer.cxx:798-803                               */
+    srt_material   material;
+    const uint8_t* texture_rgb; /* tex_w*tex_h*3, row-major, or NULL                                  */
+    uint32_t       tex_w, tex_h;
+} srt_mesh_desc;
+
+/* RayTracerInfo (src/main-pthreads-lbuffer.cxx:125-135) + image geometry. */
+typedef struct {
+    float    origin[3];         /* X-ray source == ray origin of every primary ray                    */
+    float    detector[3];       /* detector centre                                                    */
+    float    up[3], right[3];
+    float    pixel_spacing[2];  /* [0]: columns (u), [1]: rows (v); ...lbuffer.cxx:739-741            */
+    uint32_t width, height;
+} srt_camera;
+
+typedef enum {
+    SRT_KERNEL_AUTO = 0,        /* filtered kernel, falling back to exact when it cannot apply        */
+    SRT_KERNEL_EXACT = 1,       /* every (ray, triangle) pair runs the reference op sequence          */
+    SRT_KERNEL_FILTERED = 2,    /* conservative affine reject per pair + exact test for survivors     */
+    SRT_KERNEL_AUDIT = 3        /* diagnostic: exact kernel that also evaluates the filter for every
+                                   pair and counts (filter rejects && exact hits) -- must stay 0      */
+} srt_kernel;
+
+#define SRT_FLAG_ALL_MESHES_CONTRIBUTE 1u  /* default off: only mesh 0 adds path length (lbuffer.cxx:788) */
+
+typedef struct {
+    float    incident;          /* initial L-buffer value, 80.0f (lbuffer.cxx:314)                    */
+    double   length_to_cm;      /* 0.1: mesh units (mm) -> cm (lbuffer.cxx:808)                       */
+    uint32_t repair_depth;      /* 4 (lbuffer.cxx:339)                                                */
+    uint32_t kernel;            /* srt_kernel                                                         */
+    uint32_t flags;
+    uint32_t pixels_per_thread; /* 0 = auto; tuning knob of the filtered kernel (1, 2, 4 or 8)        */
+} srt_params;
+
+typedef struct {
+    float    render_ms;         /* device time of the last render (events on the context's stream)   */
+    float    repair_ms;
+    float    h2d_ms, d2h_ms;
+    uint64_t pair_tests;        /* (ray, triangle) pairs evaluated by the last render                 */
+    uint64_t exact_tests;       /* pairs that ran the exact reference sequence (srt_debug_count_exact) */
+    uint64_t filter_violations; /* SRT_KERNEL_AUDIT only: pairs the filter would have wrongly rejected */
+    uint32_t kernel_used;       /* srt_kernel actually launched                                       */
+    uint32_t launches;          /* kernels launched by the last call                                  */
+} srt_timing;
+
+/* ---- context ------------------------------------------------------------ */
+int  srt_create(srt_ctx** out, int device_id);
+void srt_destroy(srt_ctx* ctx);
+const char* srt_last_error(const srt_ctx* ctx);          /* ctx may be NULL: last create error      */
+int  srt_version(void);
+/* Launch on an existing CUDA stream (cudaStream_t as void*); NULL = the context's own stream. */
+int  srt_set_stream(srt_ctx* ctx, void* cuda_stream);
+int  srt_synchronize(srt_ctx* ctx);
+void srt_default_params(srt_params* p);
+
+/* ---- host-side helpers (pure CPU arithmetic, exact reference op order) --- */
+/* TriangleMesh::computeBoundingBox + getBBox (src/TriangleMesh.cxx:192-228, lbuffer.cxx:585-608). */
+int  srt_scene_bbox(const srt_mesh_desc* meshes, int n_meshes, float lower[3], float upper[3]);
+/* initialiseRayTracing (lbuffer.cxx:611-667) + pixel spacing (:739-741). */
+int  srt_camera_from_bbox(const float lower[3], const float upper[3], uint32_t width, uint32_t height,
+                          srt_camera* out);
+/* Row-band partition with the reference's remainder rule (main-pthreads-rows.cxx:312-334 /
+ * lbuffer.cxx:694-725 applied to rows): part i of n gets rows [begin, end). */
+int  srt_partition_rows(uint32_t height, uint32_t n_parts, uint32_t part, uint32_t* row_begin, uint32_t* row_end);
+/* Triangle::computeNormal for n triangles (9 floats in, 3 out each). */
+int  srt_triangle_normals(const float* vertices, uint32_t n_triangles, float* normals_out);
+
+/* ---- scene upload -------------------------------------------------------- */
+int  srt_set_meshes(srt_ctx* ctx, int n_meshes, const srt_mesh_desc* meshes);
+int  srt_set_camera(srt_ctx* ctx, const srt_camera* cam);
+
+/* ---- X-ray L-buffer path (the hot path) ---------------------------------- */
+/*
+ * Render rows [row_begin, row_end) of the L-buffer (pre-repair attenuated
+ * intensity; -1 marks artefact pixels, lbuffer.cxx:805-809).  All output
+ * pointers address FULL frames (width*height, row-major, index row*W+col as
+ * lbuffer.cxx:254); only the band's rows are written.  path_len_out /
+ * sign_sum_out / hit_count_out (mesh 0: summed signed path length `distance`,
+ * `signSum`, number of accepted intersections) are optional (NULL).
+ * Host-pointer version: synchronous, includes the device->host copy.
+ */
+int  srt_render_lbuffer(srt_ctx* ctx, const srt_params* params, uint32_t row_begin, uint32_t row_end,
+                        float* L_out, float* path_len_out, int32_t* sign_sum_out, uint32_t* hit_count_out);
+/* Device-pointer version: asynchronous on the context's stream (same layout).
+ * Lets the caller run an in-place NCCL allgather over the bands. */
+int  srt_render_lbuffer_device(srt_ctx* ctx, const srt_params* params, uint32_t row_begin, uint32_t row_end,
+                               float* dL, float* d_path_len, int32_t* d_sign_sum, uint32_t* d_hit_count);
+
+/* Artefact repair + image fill over a full frame (lbuffer.cxx:329-404). L_in and image_out must not alias. */
+int  srt_repair(srt_ctx* ctx, const srt_params* params, const float* L_in, float* image_out);
+int  srt_repair_device(srt_ctx* ctx, const srt_params* params, const float* dL_in, float* d_image_out);
+
+/* Whole frame in one call: L-buffer for all rows, repair, image to host
+ * (what renderLoop + the output loop of main() produce; Image::getData layout). */
+int  srt_render_xray(srt_ctx* ctx, const srt_params* params, float* image_out);
+
+/* Last-call timings and counters (waits for the last render on the stream to finish). */
+int  srt_last_timing(srt_ctx* ctx, srt_timing* out);
+/* Diagnostic: make renders count the pairs that reach the exact path (costs one atomic per CTA). */
+int  srt_debug_count_exact(srt_ctx* ctx, int enable);
+/* Diagnostic: measured FP32 FMA throughput of the context's GPU in TFLOP/s (the roofline denominator
+ * bench.py reports against; MEASURED_PEAKS.json has no FP32 figure). */
+int  srt_debug_ffma_peak(srt_ctx* ctx, int repeats, float* tflops_out);
+/* Diagnostic, host only (no GPU needed): the packed per-triangle constants the kernels stream.
+ * exact16: 16 floats / triangle; filt8, filt2_8: 8 floats / padded triangle (padding = multiple of 2);
+ * tile_m: one margin per 512-triangle tile (+1 spare). Any output may be NULL. */
+int  srt_debug_prepack(const float* vertices, uint32_t n_triangles, const srt_camera* cam, float* exact16,
+                       float* filt8, float* filt2_8, float* tile_m, uint32_t* n_padded, uint32_t* n_unfilterable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRT_H */

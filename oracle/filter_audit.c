@@ -1,0 +1,91 @@
+/*
+ * filter_audit.c -- CPU audit of the product's conservative reject filter.
+ *
+ * TEST INFRASTRUCTURE ONLY (see srt_oracle.c).  Takes the packed per-triangle
+ * filter constants produced by the product's host pre-pack (srt_debug_prepack)
+ * and, for every (pixel, triangle) pair of a frame, evaluates the filter with
+ * the same fused-multiply-add sequence the CUDA kernel uses (fmaf == one
+ * rounding, like FFMA) next to the oracle's Ray::intersect restatement.
+ * A "violation" is a pair the filter rejects although the oracle reports a hit;
+ * the filter is only valid if there are none.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    float detector[3], origin[3], up[3], right[3];
+    float lower[3], upper[3], range[3];
+    float light_position[3], light_direction[3];
+} oracle_camera;
+
+extern void oracle_make_ray(const oracle_camera* cam, uint32_t W, uint32_t H, uint32_t row, uint32_t col,
+                            float dirA[3], float dirB[3]);
+extern int oracle_intersect(const float o[3], const float d[3], const float tri9[9], float* t, int* stage);
+
+typedef struct {
+    const float* tri; uint32_t n; const oracle_camera* cam; uint32_t W, H;
+    const float* filt; const float* filt2; const float* tile_m; uint32_t tile_tris;
+    uint64_t p0, p1;
+    /* out: [0] pairs, [1] survive level0 (tile margin), [2] survive level0 (triangle margin),
+     *      [3] survive level1, [4] oracle hits, [5] violations */
+    uint64_t c[6];
+} audit_job;
+
+__attribute__((target("fma"))) static void* audit_worker(void* arg)
+{
+    audit_job* j = (audit_job*)arg;
+    const float xc = (float)(0.5 - (double)j->W / 2.0), yc = (float)(0.5 - (double)j->H / 2.0);
+    for (uint64_t p = j->p0; p < j->p1; ++p) {
+        uint32_t row = (uint32_t)(p / j->W), col = (uint32_t)(p % j->W);
+        float dA[3], dB[3];
+        oracle_make_ray(j->cam, j->W, j->H, row, col, dA, dB);
+        const float x = (float)col + xc, y = (float)row + yc;
+        for (uint32_t k = 0; k < j->n; ++k) {
+            const float* f = j->filt + 8 * (size_t)k;
+            const float* g = j->filt2 + 8 * (size_t)k;
+            const float tm = j->tile_m[k / j->tile_tris];
+            /* kernel: X = fma(bx, x, fma(gx, y, ax)); D = fma(bd, x, fma(gd, y, ad)) */
+            const float X1 = __builtin_fmaf(f[0], x, __builtin_fmaf(f[1], y, f[2]));
+            const float Dd = __builtin_fmaf(f[3], x, __builtin_fmaf(f[4], y, f[5]));
+            const float X2 = __builtin_fmaf(g[0], x, __builtin_fmaf(g[1], y, g[2]));
+            const float X3 = __builtin_fmaf(g[4], x, __builtin_fmaf(g[5], y, g[6]));
+            const int s0t = (fabsf(Dd) - fabsf(X1)) >= -tm;
+            const int s0 = s0t && !(fabsf(X1) > fabsf(Dd) + f[6]);
+            const int s1 = s0 && !((fabsf(X2) > fabsf(Dd) + g[3]) || (fabsf(X3) > fabsf(Dd) + g[7]));
+            float t; int st;
+            const int hit = oracle_intersect(j->cam->origin, dB, j->tri + 9 * (size_t)k, &t, &st);
+            j->c[0]++; j->c[1] += s0t; j->c[2] += s0; j->c[3] += s1; j->c[4] += hit;
+            if (hit && !s1) j->c[5]++;
+        }
+    }
+    return 0;
+}
+
+int oracle_filter_audit(const float* tri, uint32_t n, const oracle_camera* cam, uint32_t W, uint32_t H,
+                        const float* filt, const float* filt2, const float* tile_m, uint32_t tile_tris,
+                        uint64_t pixel_begin, uint64_t pixel_end, int n_threads, uint64_t counts[6])
+{
+    if (!__builtin_cpu_supports("fma")) return -1;
+    if (n_threads < 1) n_threads = 1;
+    audit_job* jobs = (audit_job*)calloc((size_t)n_threads, sizeof(audit_job));
+    pthread_t* tid = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
+    uint64_t total = pixel_end - pixel_begin;
+    for (int i = 0; i < n_threads; ++i) {
+        audit_job* j = &jobs[i];
+        j->tri = tri; j->n = n; j->cam = cam; j->W = W; j->H = H; j->filt = filt; j->filt2 = filt2;
+        j->tile_m = tile_m; j->tile_tris = tile_tris;
+        j->p0 = pixel_begin + total * (uint64_t)i / (uint64_t)n_threads;
+        j->p1 = pixel_begin + total * (uint64_t)(i + 1) / (uint64_t)n_threads;
+        pthread_create(&tid[i], NULL, audit_worker, j);
+    }
+    memset(counts, 0, 6 * sizeof(uint64_t));
+    for (int i = 0; i < n_threads; ++i) {
+        pthread_join(tid[i], NULL);
+        for (int k = 0; k < 6; ++k) counts[k] += jobs[i].c[k];
+    }
+    free(jobs); free(tid);
+    return 0;
+}

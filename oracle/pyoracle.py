@@ -32,10 +32,8 @@ class Camera(C.Structure):
 
 def build(force=False):
     """Compile liboracle.so (and _ref/ when /root/reference is present)."""
-    if force or not (HERE / "liboracle.so").exists() or \
-            (HERE / "srt_oracle.c").stat().st_mtime > (HERE / "liboracle.so").stat().st_mtime:
-        subprocess.run(["make", "-C", str(HERE), str(HERE / "liboracle.so")], check=True,
-                       stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", str(HERE), str(HERE / "liboracle.so")] + (["-B"] if force else []),
+                   check=True, stdout=subprocess.DEVNULL)
     if Path("/root/reference/src").is_dir():
         subprocess.run(["make", "-C", str(HERE), "ref"], check=True, stdout=subprocess.DEVNULL)
 
@@ -72,6 +70,8 @@ class Oracle:
                                          C.c_uint64, C.c_uint64, _f32p, C.c_void_p]
         L.oracle_save_text.argtypes = [C.c_char_p, _f32p, C.c_uint32, C.c_uint32]
         L.oracle_partition.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.oracle_filter_audit.argtypes = [_f32p, C.c_uint32, C.POINTER(Camera), C.c_uint32, C.c_uint32, _f32p, _f32p,
+                                          _f32p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
 
     # scene ---------------------------------------------------------------
     def camera(self, tri):
@@ -153,6 +153,22 @@ class Oracle:
 
     def save_text(self, path, img, W, H):
         return self.lib.oracle_save_text(str(path).encode(), np.ascontiguousarray(img, np.float32).reshape(-1), W, H)
+
+    def filter_audit(self, tri, cam, W, H, packed, pixel_range=None, threads=None, tile_tris=512):
+        """Audit the product's packed filter constants against the oracle's intersect.
+        -> dict(pairs, survive0_tile, survive0, survive1, hits, violations)"""
+        tri = np.ascontiguousarray(tri, np.float32).reshape(-1)
+        n = tri.size // 9
+        b, e = (0, W * H) if pixel_range is None else pixel_range
+        counts = np.zeros(6, np.uint64)
+        rc = self.lib.oracle_filter_audit(tri, n, C.byref(cam), W, H,
+                                          np.ascontiguousarray(packed["filt"], np.float32).reshape(-1),
+                                          np.ascontiguousarray(packed["filt2"], np.float32).reshape(-1),
+                                          np.ascontiguousarray(packed["tile_m"], np.float32), tile_tris, b, e,
+                                          threads or os.cpu_count() or 1, counts.ctypes.data_as(C.c_void_p))
+        if rc:
+            raise RuntimeError("host CPU has no FMA: cannot emulate the kernel's FFMA sequence")
+        return dict(zip(("pairs", "survive0_tile", "survive0", "survive1", "hits", "violations"), map(int, counts)))
 
     def partition(self, total, n):
         s = np.zeros(n, np.uint64); e = np.zeros(n, np.uint64)

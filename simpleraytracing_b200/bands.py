@@ -1,0 +1,52 @@
+"""Row-band sharding of one frame over N ranks and its assembly with ONE all_gather.
+
+The reference's only communication step is a gather of contiguous pixel ranges to rank 0 with
+blocking MPI_Send/MPI_Recv (src/main-mpi.cxx:258-293, 854-881).  Here every rank renders the rows
+`rows` of its band straight into the full-frame buffer and a single in-place all_gather (NCCL over
+NVLink on the GPUs, gloo in the CPU tests) leaves the whole frame on every rank, so the +-4-pixel
+repair stencil (main-pthreads-lbuffer.cxx:329-404) can run after assembly and results do not
+depend on N.
+
+Partition rule: H / N rows each, the first H % N ranks get one more
+(pthreadWorkLoadAllocation, main-pthreads-lbuffer.cxx:694-725; rows variant
+main-pthreads-rows.cxx:312-334).  all_gather needs equal counts, so when N does not divide H the
+frame buffer is padded: bands are gathered in slots of ceil(H/N) rows and compacted afterwards.
+"""
+import torch
+import torch.distributed as dist
+
+
+class BandLayout:
+    def __init__(self, H, W, world, rank):
+        self.H, self.W, self.world, self.rank = H, W, world, rank
+        per, rem = divmod(H, world)
+        self.starts = [i * per + min(i, rem) for i in range(world)]
+        self.counts = [per + (1 if i < rem else 0) for i in range(world)]
+        self.rows = (self.starts[rank], self.starts[rank] + self.counts[rank])
+        self.even = rem == 0
+        self.slot_rows = per + (0 if self.even else 1)
+
+    def new_frame(self, dtype, device):
+        """Buffer a rank renders into: the H*W frame (+ one slot of staging when bands are uneven)."""
+        n = self.H * self.W + (0 if self.even else self.world * self.slot_rows * self.W)
+        return torch.empty(n, dtype=dtype, device=device)
+
+    def all_gather_(self, frame):
+        """Assemble the full frame on every rank. Returns a view of the first H*W elements."""
+        H, W = self.H, self.W
+        out = frame[: H * W]
+        if self.world == 1:
+            return out
+        if self.even:
+            mine = out.view(self.world, -1)[self.rank]
+            dist.all_gather_into_tensor(out, mine)                       # in place: send slot == my band
+            return out
+        slots = frame[H * W:].view(self.world, self.slot_rows * W)
+        rb, re = self.rows
+        send = slots[self.rank]
+        send[: (re - rb) * W].copy_(out[rb * W: re * W])
+        dist.all_gather_into_tensor(slots.view(-1), send.clone())
+        for i in range(self.world):
+            if i != self.rank and self.counts[i]:
+                out[self.starts[i] * W: (self.starts[i] + self.counts[i]) * W].copy_(slots[i][: self.counts[i] * W])
+        return out

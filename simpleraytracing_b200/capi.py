@@ -1,0 +1,267 @@
+"""ctypes binding of include/srt.h (tests and bench only; no computation here)."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libsrt_b200.so"
+
+KERNEL_AUTO, KERNEL_EXACT, KERNEL_FILTERED, KERNEL_AUDIT = 0, 1, 2, 3
+FLAG_ALL_MESHES_CONTRIBUTE = 1
+
+
+class SrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"srt error {code}: {msg}")
+        self.code = code
+
+
+class Material(C.Structure):
+    _fields_ = [("ambient", C.c_float * 3), ("diffuse", C.c_float * 3), ("specular", C.c_float * 3),
+                ("shininess", C.c_float)]
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("normals", C.c_void_p), ("texcoords", C.c_void_p),
+                ("n_triangles", C.c_uint32), ("mu", C.c_float), ("material", Material),
+                ("texture_rgb", C.c_void_p), ("tex_w", C.c_uint32), ("tex_h", C.c_uint32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("detector", C.c_float * 3), ("up", C.c_float * 3),
+                ("right", C.c_float * 3), ("pixel_spacing", C.c_float * 2),
+                ("width", C.c_uint32), ("height", C.c_uint32)]
+
+    def vec(self, name):
+        return np.array(getattr(self, name)[:], dtype=np.float32)
+
+
+class Params(C.Structure):
+    _fields_ = [("incident", C.c_float), ("length_to_cm", C.c_double), ("repair_depth", C.c_uint32),
+                ("kernel", C.c_uint32), ("flags", C.c_uint32), ("pixels_per_thread", C.c_uint32)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("render_ms", C.c_float), ("repair_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("pair_tests", C.c_uint64), ("exact_tests", C.c_uint64), ("filter_violations", C.c_uint64),
+                ("kernel_used", C.c_uint32), ("launches", C.c_uint32)]
+
+
+# every symbol include/srt.h declares (tests/test_abi.py checks the .so exports all of them)
+EXPORTS = [
+    "srt_create", "srt_destroy", "srt_last_error", "srt_version", "srt_set_stream", "srt_synchronize",
+    "srt_default_params", "srt_scene_bbox", "srt_camera_from_bbox", "srt_partition_rows", "srt_triangle_normals",
+    "srt_set_meshes", "srt_set_camera", "srt_render_lbuffer", "srt_render_lbuffer_device", "srt_repair",
+    "srt_repair_device", "srt_render_xray", "srt_last_timing", "srt_debug_count_exact", "srt_debug_prepack", "srt_debug_ffma_peak",
+]
+
+
+def load_library(path=None):
+    path = Path(path) if path else LIB_PATH
+    if not path.exists():
+        raise FileNotFoundError(
+            f"{path} is missing: build it with `make -C simpleraytracing_b200/csrc` "
+            "(or __graft_entry__.build()). There is no CPU fallback.")
+    return C.CDLL(str(path))
+
+
+def _ptr(a, dtype):
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.c_contiguous, (a.dtype, dtype)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Library:
+    """Function table; host-only helpers are usable without a GPU."""
+
+    def __init__(self, path=None):
+        self.lib = L = load_library(path)
+        vp, u32, i32 = C.c_void_p, C.c_uint32, C.c_int
+        L.srt_last_error.restype = C.c_char_p
+        L.srt_last_error.argtypes = [vp]
+        L.srt_create.argtypes = [C.POINTER(vp), i32]
+        L.srt_destroy.argtypes = [vp]
+        L.srt_destroy.restype = None
+        L.srt_set_stream.argtypes = [vp, vp]
+        L.srt_synchronize.argtypes = [vp]
+        L.srt_default_params.argtypes = [C.POINTER(Params)]
+        L.srt_default_params.restype = None
+        L.srt_scene_bbox.argtypes = [C.POINTER(MeshDesc), i32, vp, vp]
+        L.srt_camera_from_bbox.argtypes = [vp, vp, u32, u32, C.POINTER(Camera)]
+        L.srt_partition_rows.argtypes = [u32, u32, u32, C.POINTER(u32), C.POINTER(u32)]
+        L.srt_triangle_normals.argtypes = [vp, u32, vp]
+        L.srt_set_meshes.argtypes = [vp, i32, C.POINTER(MeshDesc)]
+        L.srt_set_camera.argtypes = [vp, C.POINTER(Camera)]
+        L.srt_render_lbuffer.argtypes = [vp, C.POINTER(Params), u32, u32, vp, vp, vp, vp]
+        L.srt_render_lbuffer_device.argtypes = [vp, C.POINTER(Params), u32, u32, vp, vp, vp, vp]
+        L.srt_repair.argtypes = [vp, C.POINTER(Params), vp, vp]
+        L.srt_repair_device.argtypes = [vp, C.POINTER(Params), vp, vp]
+        L.srt_render_xray.argtypes = [vp, C.POINTER(Params), vp]
+        L.srt_last_timing.argtypes = [vp, C.POINTER(Timing)]
+        L.srt_debug_count_exact.argtypes = [vp, i32]
+        L.srt_debug_ffma_peak.argtypes = [vp, i32, C.POINTER(C.c_float)]
+        L.srt_debug_prepack.argtypes = [vp, u32, C.POINTER(Camera), vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32)]
+
+    # ---- host-only helpers ---------------------------------------------------
+    def default_params(self, **kw):
+        p = Params()
+        self.lib.srt_default_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    @staticmethod
+    def mesh_descs(meshes):
+        """meshes: list of (tri[n,9] float32, mu). Returns (ctypes array, keepalive)."""
+        arr = (MeshDesc * len(meshes))()
+        keep = []
+        for i, (tri, mu) in enumerate(meshes):
+            tri = np.ascontiguousarray(tri, np.float32).reshape(-1, 9)
+            keep.append(tri)
+            arr[i].vertices = tri.ctypes.data if len(tri) else None
+            arr[i].n_triangles = len(tri)
+            arr[i].mu = mu
+        return arr, keep
+
+    def scene_bbox(self, meshes):
+        arr, keep = self.mesh_descs(meshes)
+        lo = np.empty(3, np.float32); hi = np.empty(3, np.float32)
+        rc = self.lib.srt_scene_bbox(arr, len(meshes), _ptr(lo, np.float32), _ptr(hi, np.float32))
+        if rc:
+            raise SrtError(rc, "srt_scene_bbox")
+        return lo, hi
+
+    def camera_from_bbox(self, lo, hi, W, H):
+        cam = Camera()
+        lo = np.ascontiguousarray(lo, np.float32); hi = np.ascontiguousarray(hi, np.float32)
+        rc = self.lib.srt_camera_from_bbox(_ptr(lo, np.float32), _ptr(hi, np.float32), W, H, C.byref(cam))
+        if rc:
+            raise SrtError(rc, "srt_camera_from_bbox")
+        return cam
+
+    def partition_rows(self, H, n, i):
+        b = C.c_uint32(); e = C.c_uint32()
+        rc = self.lib.srt_partition_rows(H, n, i, C.byref(b), C.byref(e))
+        if rc:
+            raise SrtError(rc, "srt_partition_rows")
+        return b.value, e.value
+
+    def triangle_normals(self, tri):
+        tri = np.ascontiguousarray(tri, np.float32).reshape(-1, 9)
+        out = np.empty((len(tri), 3), np.float32)
+        rc = self.lib.srt_triangle_normals(_ptr(tri, np.float32), len(tri), _ptr(out, np.float32))
+        if rc:
+            raise SrtError(rc, "srt_triangle_normals")
+        return out
+
+    def debug_prepack(self, tri, cam):
+        tri = np.ascontiguousarray(tri, np.float32).reshape(-1, 9)
+        n = len(tri)
+        npad = (n + 1) // 2 * 2
+        exact = np.zeros((max(n, 1), 16), np.float32)
+        filt = np.zeros((max(npad, 1), 8), np.float32)
+        filt2 = np.zeros((max(npad, 1), 8), np.float32)
+        tile_m = np.zeros((npad + 511) // 512 + 1, np.float32)
+        a = C.c_uint32(); b = C.c_uint32()
+        rc = self.lib.srt_debug_prepack(_ptr(tri, np.float32), n, C.byref(cam), _ptr(exact, np.float32),
+                                        _ptr(filt, np.float32), _ptr(filt2, np.float32), _ptr(tile_m, np.float32),
+                                        C.byref(a), C.byref(b))
+        if rc:
+            raise SrtError(rc, "srt_debug_prepack")
+        assert a.value == npad
+        return dict(exact=exact[:n], filt=filt[:npad], filt2=filt2[:npad], tile_m=tile_m, n_padded=a.value,
+                    unfilterable=b.value)
+
+
+class Context:
+    """One GPU context (srt_ctx). Raises SrtError when no sm_100 device is usable."""
+
+    def __init__(self, device=0, library=None):
+        self.L = library or Library()
+        self.lib = self.L.lib
+        h = C.c_void_p()
+        rc = self.lib.srt_create(C.byref(h), device)
+        if rc:
+            raise SrtError(rc, self.lib.srt_last_error(None).decode())
+        self.h = h
+        self._keep = None
+        self.cam = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.srt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise SrtError(rc, self.lib.srt_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.lib.srt_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._ck(self.lib.srt_synchronize(self.h))
+
+    def set_meshes(self, meshes):
+        arr, keep = Library.mesh_descs(meshes)
+        self._ck(self.lib.srt_set_meshes(self.h, len(meshes), arr))
+
+    def set_camera(self, cam):
+        self.cam = cam
+        self._ck(self.lib.srt_set_camera(self.h, C.byref(cam)))
+
+    def count_exact(self, on=True):
+        self._ck(self.lib.srt_debug_count_exact(self.h, int(on)))
+
+    def render_lbuffer(self, params, rows=None, extras=True, out=None):
+        """Host-buffer render of a row band -> dict(L[, dist, ssum, hits]) as full-frame arrays."""
+        W, H = self.cam.width, self.cam.height
+        rb, re = (0, H) if rows is None else rows
+        n = W * H
+        out = out or {}
+        L = out.get("L"); L = np.zeros(n, np.float32) if L is None else L
+        dist = ssum = hits = None
+        if extras:
+            dist = np.zeros(n, np.float32); ssum = np.zeros(n, np.int32); hits = np.zeros(n, np.uint32)
+        self._ck(self.lib.srt_render_lbuffer(self.h, C.byref(params), rb, re, _ptr(L, np.float32),
+                                             _ptr(dist, np.float32), _ptr(ssum, np.int32), _ptr(hits, np.uint32)))
+        return dict(L=L, dist=dist, ssum=ssum, hits=hits)
+
+    def render_lbuffer_device(self, params, rows, dL, d_dist=0, d_ssum=0, d_hits=0):
+        """Device-pointer render (ints = raw device addresses, e.g. torch.Tensor.data_ptr())."""
+        self._ck(self.lib.srt_render_lbuffer_device(self.h, C.byref(params), rows[0], rows[1], C.c_void_p(dL),
+                                                    C.c_void_p(d_dist or None), C.c_void_p(d_ssum or None),
+                                                    C.c_void_p(d_hits or None)))
+
+    def repair(self, params, L):
+        L = np.ascontiguousarray(L, np.float32).reshape(-1)
+        img = np.empty_like(L)
+        self._ck(self.lib.srt_repair(self.h, C.byref(params), _ptr(L, np.float32), _ptr(img, np.float32)))
+        return img
+
+    def repair_device(self, params, dL, d_img):
+        self._ck(self.lib.srt_repair_device(self.h, C.byref(params), C.c_void_p(dL), C.c_void_p(d_img)))
+
+    def render_xray(self, params, out=None):
+        n = self.cam.width * self.cam.height
+        img = np.empty(n, np.float32) if out is None else out
+        self._ck(self.lib.srt_render_xray(self.h, C.byref(params), _ptr(img, np.float32)))
+        return img
+
+    def ffma_peak_tflops(self, repeats=3):
+        v = C.c_float()
+        self._ck(self.lib.srt_debug_ffma_peak(self.h, repeats, C.byref(v)))
+        return float(v.value)
+
+    def timing(self):
+        t = Timing()
+        self._ck(self.lib.srt_last_timing(self.h, C.byref(t)))
+        return t

@@ -1,0 +1,439 @@
+// kernels.cu -- sm_100a kernels of the X-ray L-buffer path.
+//
+// Reference semantics implemented here (all citations under /root/reference):
+//   ray generation          src/main-pthreads-lbuffer.cxx:753-762, include/Ray.inl:74-85
+//   Ray::intersect          src/Ray.cxx:72-125
+//   accumulation            src/main-pthreads-lbuffer.cxx:780-795
+//   attenuation / flagging  src/main-pthreads-lbuffer.cxx:798-809
+//   artefact repair         src/main-pthreads-lbuffer.cxx:329-404
+//
+// Arithmetic contract: everything that decides a hit or feeds an output value is
+// computed with separately rounded IEEE binary32 operations in the reference's
+// order (__fmul_rn / __fadd_rn / __fsub_rn / __fdiv_rn / __fsqrt_rn are never
+// contracted into FMAs and are unaffected by fast-math flags).  The FMA-contracted
+// arithmetic of the filtered kernel only ever REJECTS pairs that provably miss
+// ("filter proof"); it never decides a hit and never produces a value.
+#include "kernels.h"
+
+#include <cfloat>
+
+namespace srt {
+namespace {
+
+// ------------------------------------------------------------------ helpers
+struct RayDirs { float ax, ay, az, bx, by, bz; };   // dirA: sign test; dirB: Ray::m_direction
+
+__device__ __forceinline__ float dot_rn(float ax, float ay, float az, float bx, float by, float bz)
+{   // Vec3::dotProduct, include/Vec3.inl:313-317: (x*x' + y*y') + z*z'
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+
+__device__ __forceinline__ RayDirs make_ray(const DevCamera& c, uint32_t row, uint32_t col)
+{
+    const float v = __ldg(c.v_off + row), u = __ldg(c.u_off + col);
+    // direction = detector + up * v_offset + right * u_offset - origin          (lbuffer.cxx:760)
+    const float x = __fsub_rn(__fadd_rn(__fadd_rn(c.dx, __fmul_rn(c.ux, v)), __fmul_rn(c.rx, u)), c.ox);
+    const float y = __fsub_rn(__fadd_rn(__fadd_rn(c.dy, __fmul_rn(c.uy, v)), __fmul_rn(c.ry, u)), c.oy);
+    const float z = __fsub_rn(__fadd_rn(__fadd_rn(c.dz, __fmul_rn(c.uz, v)), __fmul_rn(c.rz, u)), c.oz);
+    // direction.normalise(): sqrt + three divides                                (Vec3.inl:461-476)
+    const float len = __fsqrt_rn(dot_rn(x, y, z, x, y, z));
+    RayDirs r;
+    r.ax = __fdiv_rn(x, len); r.ay = __fdiv_rn(y, len); r.az = __fdiv_rn(z, len);
+    // Ray::Ray re-normalises unless the length classifies as zero               (Ray.inl:74-85)
+    const float len2 = __fsqrt_rn(dot_rn(r.ax, r.ay, r.az, r.ax, r.ay, r.az));
+    if (len2 != 0.0f) { r.bx = __fdiv_rn(r.ax, len2); r.by = __fdiv_rn(r.ay, len2); r.bz = __fdiv_rn(r.az, len2); }
+    else { r.bx = 0.0f; r.by = 0.0f; r.bz = 0.0f; }
+    return r;
+}
+
+// Ray::intersect (src/Ray.cxx:72-125) on pre-packed per-triangle constants (prepack.h: ExactTri).
+// A = {e2.xyz, e1.x}  B = {e1.yz, tvec.xy}  C = {tvec.z, qvec.xyz}
+__device__ __forceinline__ bool exact_intersect(const RayDirs& r, const float4 A, const float4 B, const float4 C,
+                                                const float e2q, float& t)
+{
+    const float pvx = __fsub_rn(__fmul_rn(r.by, A.z), __fmul_rn(r.bz, A.y));   // pvec = dir x edge2   (:90)
+    const float pvy = __fsub_rn(__fmul_rn(r.bz, A.x), __fmul_rn(r.bx, A.z));
+    const float pvz = __fsub_rn(__fmul_rn(r.bx, A.y), __fmul_rn(r.by, A.x));
+    const float det = dot_rn(A.w, B.x, B.y, pvx, pvy, pvz);                      // edge1 . pvec        (:93)
+    if (det == 0.0f) return false;                                              // FP_ZERO only        (:94)
+    const float inv = __fdiv_rn(1.0f, det);                                     // float(1.0/det)      (:99)
+    const float u = __fmul_rn(dot_rn(B.z, B.w, C.x, pvx, pvy, pvz), inv);       // (:105)
+    if (u < 0.0f || u > 1.0f) return false;                                     // (:106)
+    const float v = __fmul_rn(dot_rn(r.bx, r.by, r.bz, C.y, C.z, C.w), inv);    // dir . qvec          (:115)
+    if (v < 0.0f || __fadd_rn(u, v) > 1.0f) return false;                       // (:116)
+    t = __fmul_rn(e2q, inv);                                                    // (edge2 . qvec)*inv  (:122)
+    return true;
+}
+
+// lbuffer.cxx:788-793 for one accepted pair
+__device__ __forceinline__ void accumulate_hit(const RayDirs& r, const float4 Dn, float t,
+                                               float& dist, int& ssum, uint32_t& hits)
+{
+    if ((double)t > 0.0000001) {
+        const float dn = dot_rn(r.ax, r.ay, r.az, Dn.y, Dn.z, Dn.w);            // direction . normal
+        const int sign = (0.0f < dn) - (dn < 0.0f);                             // signum            (:729)
+        dist = __fadd_rn(dist, __fmul_rn((float)sign, t));                      // distance += sign*t
+        ssum += sign;
+        ++hits;
+    }
+}
+
+// lbuffer.cxx:798-809
+__device__ __forceinline__ float attenuate(float L, float mu, float dist, int ssum, double length_to_cm)
+{
+    if (L == -1.0f) return L;                                                   // (:772) later meshes skipped
+    if (ssum != 0) return -1.0f;
+    return (float)((double)L * exp(-((double)mu * ((double)dist * length_to_cm))));
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));          // 3-input FMNMX (sm_100+)
+    return d;
+}
+
+// ---- mbarrier / bulk-copy (TMA 1-D) plumbing ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init()
+{ asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ------------------------------------------------------------------ exact kernel
+// One pixel per thread, warp footprint 8 x 4 pixels; triangle constants are read with
+// warp-uniform 128-bit loads (L1/L2 resident).  AUDIT additionally checks the filters.
+template <bool AUDIT>
+__global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constant__ RenderArgs a)
+{
+    const uint32_t col = blockIdx.x * 8 + (threadIdx.x & 7);
+    const uint32_t row = a.row_begin + blockIdx.y * 16 + (threadIdx.x >> 3);
+    const uint32_t W = a.cam.W;
+    if (col >= W || row >= a.row_end) return;
+    const RayDirs r = make_ray(a.cam, row, col);
+    const float x = (float)col + a.cam.xc, y = (float)row + a.cam.yc;
+    float L = a.incident;
+    unsigned long long n_viol = 0;
+    for (int m = 0; m < a.n_meshes; ++m) {
+        const DevMesh M = a.meshes[m];
+        float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
+        if (M.contributes) {
+#pragma unroll 1
+            for (uint32_t j = 0; j < M.n; ++j) {
+                const float4 A = __ldg(M.exact + 4 * (size_t)j);
+                const float4 B = __ldg(M.exact + 4 * (size_t)j + 1);
+                const float4 C = __ldg(M.exact + 4 * (size_t)j + 2);
+                const float4 Dn = __ldg(M.exact + 4 * (size_t)j + 3);
+                float t;
+                const bool hit = exact_intersect(r, A, B, C, Dn.x, t);
+                if (hit) accumulate_hit(r, Dn, t, dist, ssum, hits);
+                if (AUDIT) {
+                    const float4 fa = __ldg(M.filt + 2 * (size_t)j), fb = __ldg(M.filt + 2 * (size_t)j + 1);
+                    const float4 ga = __ldg(M.filt2 + 2 * (size_t)j), gb = __ldg(M.filt2 + 2 * (size_t)j + 1);
+                    const float tm = __ldg(M.tile_m + j / kTileTris);
+                    const float X1 = fmaf(fa.x, x, fmaf(fa.y, y, fa.z));
+                    const float Dd = fmaf(fa.w, x, fmaf(fb.x, y, fb.y));
+                    const float X2 = fmaf(ga.x, x, fmaf(ga.y, y, ga.z));
+                    const float X3 = fmaf(gb.x, x, fmaf(gb.y, y, gb.z));
+                    const bool reject = !(fabsf(Dd) - fabsf(X1) >= -tm) || (fabsf(X1) > fabsf(Dd) + fb.z) ||
+                                        (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);
+                    if (reject && hit) ++n_viol;
+                }
+            }
+        }
+        L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
+        if (m == 0) {
+            const size_t p = (size_t)row * W + col;
+            if (a.dist) a.dist[p] = dist;
+            if (a.ssum) a.ssum[p] = ssum;
+            if (a.hits) a.hits[p] = hits;
+        }
+    }
+    a.L[(size_t)row * W + col] = L;
+    if (AUDIT && a.counters && n_viol) atomicAdd(a.counters + 1, n_viol);
+}
+
+// --------------------------------------------------------------- filtered kernel
+// P pixels (consecutive columns of one row) per thread; lanes 4 x 8 -> warp footprint 4P x 8;
+// 4 warps 2 x 2 -> CTA footprint 8P x 16.  Level-0 filter data is streamed through a
+// kStages-deep shared-memory ring with 1-D bulk copies (TMA) signalled on mbarriers; every
+// thread evaluates the affine strip test for its P pixels against each triangle of the tile.
+// Survivors (rare, spatially coherent) run level 1 and then the exact reference sequence.
+template <int P>
+__global__ void __launch_bounds__(128) lbuffer_filtered_kernel(const __grid_constant__ RenderArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* tiles = reinterpret_cast<float4*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileTris * 32);
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t col0 = (blockIdx.x * 8 + (warp & 1) * 4 + (lane & 3)) * P;
+    const uint32_t row = a.row_begin + blockIdx.y * 16 + (warp >> 1) * 8 + (lane >> 2);
+    const uint32_t W = a.cam.W;
+    const bool row_ok = row < a.row_end;
+
+    float x[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) x[k] = (float)(col0 + k) + a.cam.xc;
+    const float y = (float)row + a.cam.yc;
+
+    if (tid == 0) {
+#pragma unroll
+        for (uint32_t s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    float Lval[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) Lval[k] = a.incident;
+
+    uint32_t issued = 0, consumed = 0;     // tiles issued / consumed by this CTA over all meshes
+    unsigned long long n_exact = 0;
+
+    for (int m = 0; m < a.n_meshes; ++m) {
+        const DevMesh M = a.meshes[m];
+        // accumulators are touched only on the (rare) exact path: dynamically indexed -> local memory
+        float dist[P]; int ssum[P]; uint32_t hits[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) { dist[k] = 0.0f; ssum[k] = 0; hits[k] = 0; }
+
+        if (M.contributes && M.n > 0) {
+            const uint32_t n_tiles = (M.n_padded + kTileTris - 1) / kTileTris;
+            auto issue = [&](uint32_t t) {
+                const uint32_t stage = issued % kStages;
+                const uint32_t cnt = min(kTileTris, M.n_padded - t * kTileTris);
+                if (tid == 0) {
+                    mbar_expect_tx(&full[stage], cnt * 32u);
+                    bulk_g2s(tiles + (size_t)stage * kTileTris * 2, M.filt + (size_t)t * kTileTris * 2, cnt * 32u,
+                             &full[stage]);
+                }
+                ++issued;
+            };
+            for (uint32_t t = 0; t < min(kStages - 1, n_tiles); ++t) issue(t);
+
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                if (t + kStages - 1 < n_tiles) issue(t + kStages - 1);
+                const uint32_t stage = consumed % kStages;
+                mbar_wait(&full[stage], (consumed / kStages) & 1u);
+                const float4* tp = tiles + (size_t)stage * kTileTris * 2;
+                const uint32_t cnt = min(kTileTris, M.n_padded - t * kTileTris);
+                const float negM = -__ldg(M.tile_m + t);
+
+#pragma unroll 1
+                for (uint32_t j = 0; j < cnt; j += kGroupTris) {
+                    const float4 a0 = tp[2 * j], b0 = tp[2 * j + 1], a1 = tp[2 * j + 2], b1 = tp[2 * j + 3];
+                    const float bs0 = fmaf(a0.y, y, a0.z), bd0 = fmaf(b0.x, y, b0.y);
+                    const float bs1 = fmaf(a1.y, y, a1.z), bd1 = fmaf(b1.x, y, b1.y);
+                    float acc = -FLT_MAX;
+#pragma unroll
+                    for (int k = 0; k < P; ++k) {
+                        const float S0 = fmaf(a0.x, x[k], bs0), D0 = fmaf(a0.w, x[k], bd0);
+                        const float S1 = fmaf(a1.x, x[k], bs1), D1 = fmaf(a1.w, x[k], bd1);
+                        acc = fmax3(acc, fabsf(D0) - fabsf(S0), fabsf(D1) - fabsf(S1));
+                    }
+                    if (__any_sync(0xffffffffu, acc >= negM)) {
+                        // ---- slow path: per-triangle margins, level 1, exact test ----
+#pragma unroll 1
+                        for (uint32_t g = 0; g < kGroupTris; ++g) {
+                            const uint32_t jj = t * kTileTris + j + g;          // triangle index in the mesh
+                            if (jj >= M.n) break;                                // padding entry
+                            const float4 fa = tp[2 * (j + g)], fb = tp[2 * (j + g) + 1];
+                            const float bs = fmaf(fa.y, y, fa.z), bd = fmaf(fb.x, y, fb.y);
+                            uint32_t mask = 0;
+#pragma unroll
+                            for (int k = 0; k < P; ++k) {
+                                const float S = fmaf(fa.x, x[k], bs), Dd = fmaf(fa.w, x[k], bd);
+                                if (!(fabsf(S) > fabsf(Dd) + fb.z)) mask |= 1u << k;
+                            }
+                            if (!row_ok) mask = 0;
+                            if (mask == 0) continue;
+                            const float4 ga = __ldg(M.filt2 + 2 * (size_t)jj), gb = __ldg(M.filt2 + 2 * (size_t)jj + 1);
+                            const float b2 = fmaf(ga.y, y, ga.z), b3 = fmaf(gb.y, y, gb.z);
+#pragma unroll
+                            for (int k = 0; k < P; ++k) {
+                                const float Dd = fmaf(fa.w, x[k], bd);
+                                const float X2 = fmaf(ga.x, x[k], b2), X3 = fmaf(gb.x, x[k], b3);
+                                if ((fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w)) mask &= ~(1u << k);
+                            }
+                            if (mask == 0) continue;
+                            const float4 A = __ldg(M.exact + 4 * (size_t)jj), B = __ldg(M.exact + 4 * (size_t)jj + 1);
+                            const float4 C = __ldg(M.exact + 4 * (size_t)jj + 2), Dn = __ldg(M.exact + 4 * (size_t)jj + 3);
+#pragma unroll 1
+                            while (mask) {
+                                const int k = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const uint32_t col = col0 + k;
+                                if (col >= W) break;
+                                const RayDirs r = make_ray(a.cam, row, col);
+                                float tt;
+                                ++n_exact;
+                                if (exact_intersect(r, A, B, C, Dn.x, tt)) accumulate_hit(r, Dn, tt, dist[k], ssum[k], hits[k]);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();      // every warp is done with this stage before it is refilled
+                ++consumed;
+            }
+        }
+
+#pragma unroll
+        for (int k = 0; k < P; ++k) Lval[k] = attenuate(Lval[k], M.mu, dist[k], ssum[k], a.length_to_cm);
+        if (m == 0 && row_ok) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                if (col0 + k < W) {
+                    const size_t p = (size_t)row * W + col0 + k;
+                    if (a.dist) a.dist[p] = dist[k];
+                    if (a.ssum) a.ssum[p] = ssum[k];
+                    if (a.hits) a.hits[p] = hits[k];
+                }
+            }
+        }
+    }
+
+    if (row_ok) {
+        float* out = a.L + (size_t)row * W + col0;
+        if (P >= 4 && (W & 3u) == 0 && col0 + P <= W) {
+#pragma unroll
+            for (int k = 0; k < P; k += 4)
+                *reinterpret_cast<float4*>(out + k) = make_float4(Lval[k], Lval[k + 1 < P ? k + 1 : k],
+                                                                   Lval[k + 2 < P ? k + 2 : k], Lval[k + 3 < P ? k + 3 : k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < P; ++k)
+                if (col0 + k < W) out[k] = Lval[k];
+        }
+    }
+    if (a.counters && n_exact) atomicAdd(a.counters, n_exact);
+}
+
+// ------------------------------------------------------------------ repair kernel
+// lbuffer.cxx:329-404.  Index arithmetic is unsigned 32-bit like the reference's
+// (`col - i`, `row - i` wrap); the reference's `index > size` guard would read one
+// element past the end when index == size, here that case stops the probe.
+__device__ __forceinline__ float repair_probe_dir(const float* __restrict__ L, uint32_t base, int32_t step,
+                                                  uint32_t depth, uint64_t size)
+{
+    float value = 0.0f;
+    for (uint32_t i = 1; i <= depth; ++i) {
+        const uint32_t index = base + (uint32_t)((int32_t)i * step);
+        if ((uint64_t)index >= size) break;
+        const float v = L[index];
+        if (v != -1.0f) { value = v; break; }
+    }
+    return value;
+}
+
+__global__ void __launch_bounds__(256) repair_kernel(const float* __restrict__ L, float* __restrict__ image,
+                                                     uint32_t W, uint32_t H, uint32_t depth)
+{
+    const uint64_t size = (uint64_t)W * H;
+    const uint64_t pixel = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel >= size) return;
+    float out = L[pixel];
+    if (out == -1.0f) {
+        const uint32_t row = (uint32_t)(pixel / W), col = (uint32_t)(pixel % W);
+        const uint32_t base = row * W + col;
+        float sum = 0.0f; uint32_t n = 0;
+        float v;
+        v = repair_probe_dir(L, base, 1, depth, size);               if (v != 0.0f) { sum = __fadd_rn(sum, v); ++n; }   // +col
+        v = repair_probe_dir(L, base, -(int32_t)W, depth, size);     if (v != 0.0f) { sum = __fadd_rn(sum, v); ++n; }   // -row
+        v = repair_probe_dir(L, base, -1, depth, size);              if (v != 0.0f) { sum = __fadd_rn(sum, v); ++n; }   // -col
+        v = repair_probe_dir(L, base, (int32_t)W, depth, size);      if (v != 0.0f) { sum = __fadd_rn(sum, v); ++n; }   // +row
+        out = __fdiv_rn(sum, (float)n);                              // 0/0 -> NaN like the reference
+    }
+    image[pixel] = out;
+}
+
+// ------------------------------------------------------------------ FFMA peak probe
+// 16 independent FFMA chains per thread: the measured FP32 roofline denominator (bench.py).
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b)
+{
+    float r[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) r[k] = (float)(threadIdx.x + k);
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r[k] = fmaf(r[k], a, b);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += r[k];
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+} // namespace
+
+cudaError_t launch_ffma_peak(float* scratch, int blocks, int iters, cudaStream_t s)
+{
+    ffma_peak_kernel<<<blocks, 256, 0, s>>>(scratch, iters, 0.999f, 0.001f);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ launchers
+cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
+{
+    if (a.row_end <= a.row_begin || a.cam.W == 0) return cudaSuccess;
+    dim3 grid((a.cam.W + 7) / 8, (a.row_end - a.row_begin + 15) / 16);
+    if (audit) lbuffer_exact_kernel<true><<<grid, 128, 0, s>>>(a);
+    else lbuffer_exact_kernel<false><<<grid, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int P>
+static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
+{
+    const size_t smem = (size_t)kStages * kTileTris * 32 + kStages * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(lbuffer_filtered_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((a.cam.W + 8 * P - 1) / (8 * P), (a.row_end - a.row_begin + 15) / 16);
+    lbuffer_filtered_kernel<P><<<grid, 128, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s)
+{
+    if (a.row_end <= a.row_begin || a.cam.W == 0) return cudaSuccess;
+    switch (ppt) {
+        case 1: return launch_filtered_t<1>(a, s);
+        case 2: return launch_filtered_t<2>(a, s);
+        case 4: return launch_filtered_t<4>(a, s);
+        case 8: return launch_filtered_t<8>(a, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_repair(const float* L, float* image, uint32_t W, uint32_t H, uint32_t depth, cudaStream_t s)
+{
+    const uint64_t size = (uint64_t)W * H;
+    if (size == 0) return cudaSuccess;
+    repair_kernel<<<(unsigned)((size + 255) / 256), 256, 0, s>>>(L, image, W, H, depth);
+    return cudaGetLastError();
+}
+
+} // namespace srt

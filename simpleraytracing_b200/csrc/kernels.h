@@ -1,0 +1,59 @@
+// kernels.h -- launch interface between the C-ABI layer (srt_api.cpp) and the sm_100a kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace srt {
+
+constexpr uint32_t kTileTris  = 512;   // triangles per shared-memory tile of level-0 filter data (16 KB)
+constexpr uint32_t kGroupTris = 2;     // triangles per vote group in the filtered kernel
+constexpr uint32_t kStages    = 3;     // bulk-copy pipeline depth
+
+// One mesh as the kernels see it (device pointers).
+struct DevMesh {
+    const float4* filt;      // 2 float4 per (padded) triangle   -- FilterTri
+    const float4* filt2;     // 2 float4 per (padded) triangle   -- FilterTri2
+    const float4* exact;     // 4 float4 per triangle            -- ExactTri
+    const float*  tile_m;    // level-0 margin per tile
+    uint32_t n, n_padded;
+    float    mu;             // attenuation coefficient
+    int      contributes;    // 0: mesh adds no path length (reference semantics for meshes > 0)
+};
+
+struct DevCamera {
+    float ox, oy, oz;        // origin
+    float dx, dy, dz;        // detector
+    float ux, uy, uz;        // up
+    float rx, ry, rz;        // right
+    const float* u_off;      // W entries: float(double(spacing)*(0.5 + col - W/2.0)), lbuffer.cxx:757
+    const float* v_off;      // H entries, lbuffer.cxx:756
+    float xc, yc;            // centred pixel coordinate = index + xc (0.5 - W/2)
+    uint32_t W, H;
+};
+
+struct RenderArgs {
+    DevCamera cam;
+    const DevMesh* meshes;   // device array
+    int n_meshes;
+    uint32_t row_begin, row_end;
+    float incident;          // 80.0f
+    double length_to_cm;     // 0.1
+    float* L;                // full-frame outputs (row*W + col); band rows written
+    float* dist;             // optional
+    int32_t* ssum;           // optional
+    uint32_t* hits;          // optional
+    unsigned long long* counters;   // optional: [0] exact tests run, [1] filter violations (audit)
+};
+
+// Exact kernel: every pair runs the reference op sequence. audit != 0 additionally evaluates the
+// filters for every pair and counts (filter says reject) && (exact says hit) into counters[1].
+cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s);
+// Filtered kernel; ppt = pixels per thread (1, 2, 4, 8).
+cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s);
+// Artefact repair + image fill (lbuffer.cxx:329-404).
+cudaError_t launch_repair(const float* L, float* image, uint32_t W, uint32_t H, uint32_t depth, cudaStream_t s);
+
+// FP32 FMA throughput probe: blocks x 256 threads x iters x 16 FFMA.
+cudaError_t launch_ffma_peak(float* scratch, int blocks, int iters, cudaStream_t s);
+
+} // namespace srt

@@ -1,0 +1,590 @@
+// srt_api.cpp -- the extern "C" boundary declared in include/srt.h.
+//
+// Host responsibilities: validate arguments, keep the scene resident on the GPU (packed by
+// prepack.cpp), compute the camera with the reference's exact float operation order, launch
+// the kernels on the context's stream and time them with CUDA events.  No compute happens
+// on the CPU: if CUDA is unavailable every render call fails with SRT_ERR_NO_DEVICE /
+// SRT_ERR_CUDA.  Compile with -ffp-contract=off (camera arithmetic must match the
+// reference bit for bit).
+#include "srt.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "prepack.h"
+
+#if defined(__FMA__) && !defined(SRT_ALLOW_FMA_HOST)
+#error "build srt_api.cpp without -mfma/-march=native"
+#endif
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HostMesh {
+    std::vector<float> vertices;     // 9 per triangle
+    std::vector<float> normals;      // 3 per triangle (always materialised)
+    uint32_t n = 0;
+    float mu = 0.0f;
+};
+
+struct DeviceMeshBuffers {
+    void* filt = nullptr; void* filt2 = nullptr; void* exact = nullptr; void* tile_m = nullptr;
+};
+
+} // namespace
+
+struct srt_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    std::string error;
+
+    std::vector<HostMesh> meshes;
+    bool have_camera = false;
+    srt_camera camera{};
+    bool packed = false;                 // device scene matches meshes + camera
+    bool filterable = false;
+
+    std::vector<DeviceMeshBuffers> dmesh;
+    srt::DevMesh* d_meshes = nullptr;    // device array of descriptors (two variants: default / all contribute)
+    srt::DevMesh* d_meshes_all = nullptr;
+    float* d_u_off = nullptr; float* d_v_off = nullptr;
+    uint64_t total_tris = 0, mesh0_tris = 0;
+
+    // frame scratch for the host-pointer entry points
+    size_t frame_cap = 0;
+    float* d_L = nullptr; float* d_img = nullptr; float* d_dist = nullptr; int32_t* d_ssum = nullptr; uint32_t* d_hits = nullptr;
+    unsigned long long* d_counters = nullptr;
+    bool count_exact = false;
+    bool counters_pending = false, timing_pending = false;
+
+    srt_timing timing{};
+};
+
+namespace {
+
+int fail(srt_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->error = buf; else g_create_error = buf;
+    return code;
+}
+
+#define SRT_CUDA(c, call)                                                                        \
+    do { cudaError_t e__ = (call);                                                               \
+         if (e__ != cudaSuccess) return fail((c), SRT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); } while (0)
+
+void free_scene(srt_ctx* c)
+{
+    for (auto& d : c->dmesh) { cudaFree(d.filt); cudaFree(d.filt2); cudaFree(d.exact); cudaFree(d.tile_m); }
+    c->dmesh.clear();
+    cudaFree(c->d_meshes); c->d_meshes = nullptr;
+    cudaFree(c->d_meshes_all); c->d_meshes_all = nullptr;
+    cudaFree(c->d_u_off); c->d_u_off = nullptr;
+    cudaFree(c->d_v_off); c->d_v_off = nullptr;
+    c->packed = false;
+}
+
+void free_frame(srt_ctx* c)
+{
+    cudaFree(c->d_L); cudaFree(c->d_img); cudaFree(c->d_dist); cudaFree(c->d_ssum); cudaFree(c->d_hits);
+    c->d_L = c->d_img = c->d_dist = nullptr; c->d_ssum = nullptr; c->d_hits = nullptr; c->frame_cap = 0;
+}
+
+int ensure_frame(srt_ctx* c, size_t pixels)
+{
+    if (pixels <= c->frame_cap) return SRT_OK;
+    free_frame(c);
+    SRT_CUDA(c, cudaMalloc(&c->d_L, pixels * 4));
+    SRT_CUDA(c, cudaMalloc(&c->d_img, pixels * 4));
+    SRT_CUDA(c, cudaMalloc(&c->d_dist, pixels * 4));
+    SRT_CUDA(c, cudaMalloc(&c->d_ssum, pixels * 4));
+    SRT_CUDA(c, cudaMalloc(&c->d_hits, pixels * 4));
+    c->frame_cap = pixels;
+    return SRT_OK;
+}
+
+// Upload the packed scene for the current meshes + camera.
+int pack_scene(srt_ctx* c)
+{
+    if (c->packed) return SRT_OK;
+    if (c->meshes.empty()) return fail(c, SRT_ERR_INVALID, "srt_set_meshes has not been called");
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    free_scene(c);
+    const srt_camera& cam = c->camera;
+    const uint32_t W = cam.width, H = cam.height;
+
+    // per-column / per-row offsets exactly as lbuffer.cxx:756-757:
+    //   float v_offset = pixel_spacing[1] * (0.5 + row - H / 2.0)   (double product, narrowed)
+    std::vector<float> u_off(W ? W : 1), v_off(H ? H : 1);
+    for (uint32_t col = 0; col < W; ++col)
+        u_off[col] = (float)((double)cam.pixel_spacing[0] * (0.5 + (double)col - (double)W / 2.0));
+    for (uint32_t row = 0; row < H; ++row)
+        v_off[row] = (float)((double)cam.pixel_spacing[1] * (0.5 + (double)row - (double)H / 2.0));
+    SRT_CUDA(c, cudaMalloc(&c->d_u_off, u_off.size() * 4));
+    SRT_CUDA(c, cudaMalloc(&c->d_v_off, v_off.size() * 4));
+    SRT_CUDA(c, cudaMemcpyAsync(c->d_u_off, u_off.data(), u_off.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    SRT_CUDA(c, cudaMemcpyAsync(c->d_v_off, v_off.data(), v_off.size() * 4, cudaMemcpyHostToDevice, c->stream));
+
+    srt::FrameGeom g = srt::make_frame_geom(cam.origin, cam.detector, cam.up, cam.right,
+                                            cam.pixel_spacing[0], cam.pixel_spacing[1], W, H);
+    c->filterable = g.filterable;
+
+    std::vector<srt::DevMesh> desc(c->meshes.size());
+    c->dmesh.resize(c->meshes.size());
+    c->total_tris = 0;
+    for (size_t m = 0; m < c->meshes.size(); ++m) {
+        const HostMesh& hm = c->meshes[m];
+        srt::PackedMesh pm;
+        srt::prepack_mesh(hm.vertices.data(), hm.normals.data(), hm.n, cam.origin, g, srt::kTileTris, srt::kGroupTris, pm);
+        DeviceMeshBuffers& d = c->dmesh[m];
+        const size_t nf = pm.filt.size() ? pm.filt.size() : 1, ne = pm.exact.size() ? pm.exact.size() : 1;
+        SRT_CUDA(c, cudaMalloc(&d.filt, nf * sizeof(srt::FilterTri)));
+        SRT_CUDA(c, cudaMalloc(&d.filt2, nf * sizeof(srt::FilterTri2)));
+        SRT_CUDA(c, cudaMalloc(&d.exact, ne * sizeof(srt::ExactTri)));
+        SRT_CUDA(c, cudaMalloc(&d.tile_m, pm.tile_m.size() * 4));
+        if (hm.n) {
+            SRT_CUDA(c, cudaMemcpyAsync(d.filt, pm.filt.data(), pm.filt.size() * sizeof(srt::FilterTri), cudaMemcpyHostToDevice, c->stream));
+            SRT_CUDA(c, cudaMemcpyAsync(d.filt2, pm.filt2.data(), pm.filt2.size() * sizeof(srt::FilterTri2), cudaMemcpyHostToDevice, c->stream));
+            SRT_CUDA(c, cudaMemcpyAsync(d.exact, pm.exact.data(), pm.exact.size() * sizeof(srt::ExactTri), cudaMemcpyHostToDevice, c->stream));
+        }
+        SRT_CUDA(c, cudaMemcpyAsync(d.tile_m, pm.tile_m.data(), pm.tile_m.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        SRT_CUDA(c, cudaStreamSynchronize(c->stream));      // pm goes out of scope
+        desc[m].filt = (const float4*)d.filt; desc[m].filt2 = (const float4*)d.filt2;
+        desc[m].exact = (const float4*)d.exact; desc[m].tile_m = (const float*)d.tile_m;
+        desc[m].n = pm.n; desc[m].n_padded = pm.n_padded; desc[m].mu = hm.mu;
+        desc[m].contributes = (m == 0);                     // lbuffer.cxx:788: only meshes[0] adds path length
+        c->total_tris += hm.n;
+    }
+    c->mesh0_tris = c->meshes[0].n;
+    SRT_CUDA(c, cudaMalloc(&c->d_meshes, desc.size() * sizeof(srt::DevMesh)));
+    SRT_CUDA(c, cudaMalloc(&c->d_meshes_all, desc.size() * sizeof(srt::DevMesh)));
+    SRT_CUDA(c, cudaMemcpy(c->d_meshes, desc.data(), desc.size() * sizeof(srt::DevMesh), cudaMemcpyHostToDevice));
+    for (auto& d : desc) d.contributes = 1;
+    SRT_CUDA(c, cudaMemcpy(c->d_meshes_all, desc.data(), desc.size() * sizeof(srt::DevMesh), cudaMemcpyHostToDevice));
+    c->packed = true;
+    return SRT_OK;
+}
+
+int choose_ppt(const srt_ctx* c, const srt_params* p, uint32_t rows)
+{
+    if (p->pixels_per_thread == 1 || p->pixels_per_thread == 2 || p->pixels_per_thread == 4 || p->pixels_per_thread == 8)
+        return (int)p->pixels_per_thread;
+    // largest P that still gives every SM several CTAs (148 SMs; see DESIGN.md "grid sizing")
+    const uint64_t W = c->camera.width;
+    for (int P = 8; P > 1; P >>= 1) {
+        const uint64_t ctas = ((W + 8 * P - 1) / (8 * P)) * ((rows + 15) / 16);
+        if (ctas >= 148ull * 6) return P;
+    }
+    return 1;
+}
+
+int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint32_t row_end,
+                  float* dL, float* d_dist, int32_t* d_ssum, uint32_t* d_hits)
+{
+    if (!params) return fail(c, SRT_ERR_INVALID, "params is NULL");
+    if (!dL) return fail(c, SRT_ERR_INVALID, "L buffer is NULL");
+    int rc = pack_scene(c);
+    if (rc) return rc;
+    const srt_camera& cam = c->camera;
+    if (row_begin > row_end || row_end > cam.height)
+        return fail(c, SRT_ERR_INVALID, "row band [%u, %u) outside the %u-row frame", row_begin, row_end, cam.height);
+
+    srt::RenderArgs a{};
+    a.cam.ox = cam.origin[0]; a.cam.oy = cam.origin[1]; a.cam.oz = cam.origin[2];
+    a.cam.dx = cam.detector[0]; a.cam.dy = cam.detector[1]; a.cam.dz = cam.detector[2];
+    a.cam.ux = cam.up[0]; a.cam.uy = cam.up[1]; a.cam.uz = cam.up[2];
+    a.cam.rx = cam.right[0]; a.cam.ry = cam.right[1]; a.cam.rz = cam.right[2];
+    a.cam.u_off = c->d_u_off; a.cam.v_off = c->d_v_off;
+    a.cam.xc = (float)(0.5 - (double)cam.width / 2.0); a.cam.yc = (float)(0.5 - (double)cam.height / 2.0);
+    a.cam.W = cam.width; a.cam.H = cam.height;
+    const bool all = (params->flags & SRT_FLAG_ALL_MESHES_CONTRIBUTE) != 0;
+    a.meshes = all ? c->d_meshes_all : c->d_meshes;
+    a.n_meshes = (int)c->meshes.size();
+    a.row_begin = row_begin; a.row_end = row_end;
+    a.incident = params->incident; a.length_to_cm = params->length_to_cm;
+    a.L = dL; a.dist = d_dist; a.ssum = d_ssum; a.hits = d_hits;
+    a.counters = nullptr;
+    if (c->count_exact || params->kernel == SRT_KERNEL_AUDIT) {
+        if (!c->d_counters) SRT_CUDA(c, cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)));
+        SRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+        a.counters = c->d_counters;
+    }
+
+    uint32_t kernel = params->kernel;
+    const int audit = (kernel == SRT_KERNEL_AUDIT);
+    if (audit) kernel = SRT_KERNEL_EXACT;
+    if (kernel == SRT_KERNEL_AUTO) kernel = c->filterable ? SRT_KERNEL_FILTERED : SRT_KERNEL_EXACT;
+    if (kernel != SRT_KERNEL_EXACT && kernel != SRT_KERNEL_FILTERED)
+        return fail(c, SRT_ERR_INVALID, "unknown kernel selector %u", params->kernel);
+
+    SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if (kernel == SRT_KERNEL_FILTERED) SRT_CUDA(c, srt::launch_lbuffer_filtered(a, choose_ppt(c, params, row_end - row_begin), c->stream));
+    else SRT_CUDA(c, srt::launch_lbuffer_exact(a, audit, c->stream));
+    SRT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    c->timing.kernel_used = kernel;
+    c->timing.launches = (row_end > row_begin) ? 1 : 0;
+    const uint64_t tris = all ? c->total_tris : c->mesh0_tris;
+    c->timing.pair_tests = (uint64_t)(row_end - row_begin) * cam.width * tris;
+    c->timing.exact_tests = 0; c->timing.filter_violations = 0;
+    c->counters_pending = a.counters != nullptr;
+    c->timing_pending = true;
+    return SRT_OK;
+}
+
+} // namespace
+
+// =============================================================================
+extern "C" {
+
+int srt_version(void) { return SRT_VERSION; }
+
+const char* srt_last_error(const srt_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+void srt_default_params(srt_params* p)
+{
+    if (!p) return;
+    p->incident = 80.000f;          // lbuffer.cxx:314
+    p->length_to_cm = 0.1;          // lbuffer.cxx:808
+    p->repair_depth = 4;            // lbuffer.cxx:339
+    p->kernel = SRT_KERNEL_AUTO;
+    p->flags = 0;
+    p->pixels_per_thread = 0;
+}
+
+int srt_create(srt_ctx** out, int device_id)
+{
+    if (!out) return fail(nullptr, SRT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, SRT_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= n) return fail(nullptr, SRT_ERR_INVALID, "device %d out of range [0, %d)", device_id, n);
+    cudaDeviceProp prop{};
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess)
+        return fail(nullptr, SRT_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, SRT_ERR_NO_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", device_id, prop.major, prop.minor);
+    srt_ctx* c = new (std::nothrow) srt_ctx();
+    if (!c) return fail(nullptr, SRT_ERR_NOMEM, "out of host memory");
+    c->device = device_id;
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c; return fail(nullptr, SRT_ERR_CUDA, "stream creation: %s", cudaGetErrorString(e));
+    }
+    c->stream = c->own_stream;
+    for (auto& ev : c->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) { srt_destroy(c); return fail(nullptr, SRT_ERR_CUDA, "event creation: %s", cudaGetErrorString(e)); }
+    *out = c;
+    return SRT_OK;
+}
+
+void srt_destroy(srt_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_scene(c); free_frame(c);
+    cudaFree(c->d_counters);
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int srt_set_stream(srt_ctx* c, void* s)
+{
+    if (!c) return SRT_ERR_INVALID;
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return SRT_OK;
+}
+
+int srt_synchronize(srt_ctx* c)
+{
+    if (!c) return SRT_ERR_INVALID;
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SRT_OK;
+}
+
+// ---- host helpers -----------------------------------------------------------
+int srt_triangle_normals(const float* vertices, uint32_t n, float* out)
+{
+    if ((!vertices || !out) && n) return SRT_ERR_INVALID;
+    for (uint32_t i = 0; i < n; ++i) srt::compute_normal(vertices + 9 * (size_t)i, out + 3 * (size_t)i);
+    return SRT_OK;
+}
+
+int srt_scene_bbox(const srt_mesh_desc* meshes, int n_meshes, float lo[3], float hi[3])
+{
+    if (!lo || !hi || n_meshes < 0 || (n_meshes && !meshes)) return SRT_ERR_INVALID;
+    const float inf = std::numeric_limits<float>::infinity();
+    for (int k = 0; k < 3; ++k) { lo[k] = inf; hi[k] = -inf; }
+    for (int m = 0; m < n_meshes; ++m) {
+        if (meshes[m].n_triangles && !meshes[m].vertices) return SRT_ERR_INVALID;
+        // TriangleMesh::computeBoundingBox (TriangleMesh.cxx:192-228): std::min / std::max over P1, P2, P3
+        float mlo[3] = { inf, inf, inf }, mhi[3] = { -inf, -inf, -inf };
+        for (size_t i = 0; i < (size_t)meshes[m].n_triangles * 3; ++i)
+            for (int k = 0; k < 3; ++k) {
+                const float v = meshes[m].vertices[i * 3 + k];
+                mlo[k] = (v < mlo[k]) ? v : mlo[k];
+                mhi[k] = (mhi[k] < v) ? v : mhi[k];
+            }
+        for (int k = 0; k < 3; ++k) {       // getBBox (lbuffer.cxx:585-608)
+            lo[k] = (mlo[k] < lo[k]) ? mlo[k] : lo[k];
+            hi[k] = (hi[k] < mhi[k]) ? mhi[k] : hi[k];
+        }
+    }
+    return SRT_OK;
+}
+
+int srt_camera_from_bbox(const float lo[3], const float hi[3], uint32_t W, uint32_t H, srt_camera* out)
+{
+    if (!lo || !hi || !out || W == 0 || H == 0) return SRT_ERR_INVALID;
+    // initialiseRayTracing, lbuffer.cxx:611-667.  Float ops, except where the reference's
+    // Vec3::operator/(double) and `diagonal * 0.6` promote to double.
+    float range[3], centre[3];
+    for (int k = 0; k < 3; ++k) {
+        range[k] = hi[k] - lo[k];                                   // :620
+        centre[k] = lo[k] + (float)((double)range[k] / 2.0);        // :621
+    }
+    const float diagonal = std::sqrt(range[0] * range[0] + range[1] * range[1] + range[2] * range[2]);   // :631
+    const float up[3] = { 0.0f, 0.0f, -1.0f };                      // :633
+    float origin[3] = { centre[0] - diagonal * 1, centre[1] - 0.0f, centre[2] - 0.0f };                     // :635
+    float detector[3] = { centre[0] + (float)((double)diagonal * 0.6), centre[1] + 0.0f, centre[2] + 0.0f }; // :636
+    float d[3] = { detector[0] - origin[0], detector[1] - origin[1], detector[2] - origin[2] };             // :638
+    for (int pass = 0; pass < 2; ++pass) {                          // normalize() :639 and normalise() :648
+        const float len = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        d[0] /= len; d[1] /= len; d[2] /= len;
+    }
+    // right = direction x up, :649 (Vec3::crossProduct)
+    const float right[3] = { d[1] * up[2] - d[2] * up[1], d[2] * up[0] - d[0] * up[2], d[0] * up[1] - d[1] * up[0] };
+    // pixel spacing, :739-741
+    const float res1 = range[2] / (float)W, res2 = range[1] / (float)H;
+    const float spacing = 2 * ((res1 < res2) ? res2 : res1);
+    for (int k = 0; k < 3; ++k) { out->origin[k] = origin[k]; out->detector[k] = detector[k]; out->up[k] = up[k]; out->right[k] = right[k]; }
+    out->pixel_spacing[0] = spacing; out->pixel_spacing[1] = spacing;
+    out->width = W; out->height = H;
+    return SRT_OK;
+}
+
+int srt_partition_rows(uint32_t H, uint32_t n_parts, uint32_t part, uint32_t* rb, uint32_t* re)
+{
+    if (!rb || !re || n_parts == 0 || part >= n_parts) return SRT_ERR_INVALID;
+    // total / n each, the first total % n parts get one more (lbuffer.cxx:701-719, rows variant :312-334)
+    const uint32_t per = H / n_parts, rem = H % n_parts;
+    *rb = part * per + (part < rem ? part : rem);
+    *re = *rb + per + (part < rem ? 1u : 0u);
+    return SRT_OK;
+}
+
+// ---- scene --------------------------------------------------------------------
+int srt_set_meshes(srt_ctx* c, int n_meshes, const srt_mesh_desc* meshes)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (n_meshes <= 0 || !meshes) return fail(c, SRT_ERR_INVALID, "need at least one mesh");
+    std::vector<HostMesh> hm((size_t)n_meshes);
+    for (int m = 0; m < n_meshes; ++m) {
+        const srt_mesh_desc& d = meshes[m];
+        if (d.n_triangles && !d.vertices) return fail(c, SRT_ERR_INVALID, "mesh %d: vertices is NULL (buffer size error)", m);
+        hm[m].n = d.n_triangles; hm[m].mu = d.mu;
+        hm[m].vertices.assign(d.vertices, d.vertices + 9 * (size_t)d.n_triangles);
+        hm[m].normals.resize(3 * (size_t)d.n_triangles);
+        if (d.normals) std::memcpy(hm[m].normals.data(), d.normals, hm[m].normals.size() * 4);
+        else srt_triangle_normals(hm[m].vertices.data(), d.n_triangles, hm[m].normals.data());
+    }
+    c->meshes.swap(hm);
+    c->packed = false;
+    return SRT_OK;
+}
+
+int srt_set_camera(srt_ctx* c, const srt_camera* cam)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (!cam) return fail(c, SRT_ERR_INVALID, "camera is NULL");
+    if (cam->width == 0 || cam->height == 0 || (uint64_t)cam->width * cam->height >= (1ull << 32))
+        return fail(c, SRT_ERR_INVALID, "image size %u x %u not supported", cam->width, cam->height);
+    c->camera = *cam;
+    c->have_camera = true;
+    c->packed = false;
+    return SRT_OK;
+}
+
+// ---- L-buffer -------------------------------------------------------------------
+int srt_render_lbuffer_device(srt_ctx* c, const srt_params* p, uint32_t rb, uint32_t re,
+                              float* dL, float* dd, int32_t* ds, uint32_t* dh)
+{
+    if (!c) return SRT_ERR_INVALID;
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    return render_device(c, p, rb, re, dL, dd, ds, dh);
+}
+
+int srt_render_lbuffer(srt_ctx* c, const srt_params* p, uint32_t rb, uint32_t re,
+                       float* L_out, float* dist_out, int32_t* ssum_out, uint32_t* hits_out)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (!L_out) return fail(c, SRT_ERR_INVALID, "L_out is NULL");
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    const size_t W = c->camera.width, pixels = W * c->camera.height;
+    int rc = ensure_frame(c, pixels);
+    if (rc) return rc;
+    rc = render_device(c, p, rb, re, c->d_L, dist_out ? c->d_dist : nullptr, ssum_out ? c->d_ssum : nullptr,
+                       hits_out ? c->d_hits : nullptr);
+    if (rc) return rc;
+    const size_t off = (size_t)rb * W, cnt = (size_t)(re - rb) * W;
+    if (cnt) {
+        SRT_CUDA(c, cudaMemcpyAsync(L_out + off, c->d_L + off, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (dist_out) SRT_CUDA(c, cudaMemcpyAsync(dist_out + off, c->d_dist + off, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (ssum_out) SRT_CUDA(c, cudaMemcpyAsync(ssum_out + off, c->d_ssum + off, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (hits_out) SRT_CUDA(c, cudaMemcpyAsync(hits_out + off, c->d_hits + off, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    SRT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
+    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.d2h_ms, c->ev[1], c->ev[2]));
+    c->timing.repair_ms = 0.0f; c->timing.h2d_ms = 0.0f;
+    return SRT_OK;
+}
+
+// ---- repair -----------------------------------------------------------------------
+int srt_repair_device(srt_ctx* c, const srt_params* p, const float* dL, float* dimg)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (!p || !dL || !dimg || dL == dimg) return fail(c, SRT_ERR_INVALID, "repair needs distinct non-NULL buffers");
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    SRT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    SRT_CUDA(c, srt::launch_repair(dL, dimg, c->camera.width, c->camera.height, p->repair_depth, c->stream));
+    SRT_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    return SRT_OK;
+}
+
+int srt_repair(srt_ctx* c, const srt_params* p, const float* L_in, float* image_out)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (!p || !L_in || !image_out || L_in == image_out) return fail(c, SRT_ERR_INVALID, "repair needs distinct non-NULL buffers");
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    const size_t pixels = (size_t)c->camera.width * c->camera.height;
+    int rc = ensure_frame(c, pixels);
+    if (rc) return rc;
+    SRT_CUDA(c, cudaMemcpyAsync(c->d_L, L_in, pixels * 4, cudaMemcpyHostToDevice, c->stream));
+    rc = srt_repair_device(c, p, c->d_L, c->d_img);
+    if (rc) return rc;
+    SRT_CUDA(c, cudaMemcpyAsync(image_out, c->d_img, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.repair_ms, c->ev[2], c->ev[3]));
+    c->timing.launches = 1;
+    return SRT_OK;
+}
+
+// ---- whole frame --------------------------------------------------------------------
+int srt_render_xray(srt_ctx* c, const srt_params* p, float* image_out)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (!p || !image_out) return fail(c, SRT_ERR_INVALID, "params / image_out is NULL");
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    const size_t pixels = (size_t)c->camera.width * c->camera.height;
+    int rc = ensure_frame(c, pixels);
+    if (rc) return rc;
+    rc = render_device(c, p, 0, c->camera.height, c->d_L, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    rc = srt_repair_device(c, p, c->d_L, c->d_img);
+    if (rc) return rc;
+    SRT_CUDA(c, cudaMemcpyAsync(image_out, c->d_img, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
+    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.repair_ms, c->ev[2], c->ev[3]));
+    c->timing.launches = 2;
+    return SRT_OK;
+}
+
+int srt_last_timing(srt_ctx* c, srt_timing* out)
+{
+    if (!c || !out) return SRT_ERR_INVALID;
+    if (c->timing_pending) {
+        SRT_CUDA(c, cudaSetDevice(c->device));
+        SRT_CUDA(c, cudaEventSynchronize(c->ev[1]));
+        SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
+        if (c->counters_pending && c->d_counters) {
+            unsigned long long cnts[2] = { 0, 0 };
+            SRT_CUDA(c, cudaMemcpyAsync(cnts, c->d_counters, sizeof cnts, cudaMemcpyDeviceToHost, c->stream));
+            SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+            c->timing.exact_tests = cnts[0]; c->timing.filter_violations = cnts[1];
+        }
+        c->timing_pending = false; c->counters_pending = false;
+    }
+    *out = c->timing;
+    return SRT_OK;
+}
+
+// diagnostic (host only, no GPU): run the pre-pack for one mesh and return the packed arrays.
+// exact16: 16 floats per triangle; filt8 / filt2_8: 8 floats per padded triangle; tile_m: one per tile.
+int srt_debug_prepack(const float* vertices, uint32_t n, const srt_camera* cam, float* exact16, float* filt8,
+                      float* filt2_8, float* tile_m, uint32_t* n_padded, uint32_t* n_unfilterable)
+{
+    if (!vertices || !cam) return SRT_ERR_INVALID;
+    srt::FrameGeom g = srt::make_frame_geom(cam->origin, cam->detector, cam->up, cam->right, cam->pixel_spacing[0],
+                                            cam->pixel_spacing[1], cam->width, cam->height);
+    srt::PackedMesh pm;
+    srt::prepack_mesh(vertices, nullptr, n, cam->origin, g, srt::kTileTris, srt::kGroupTris, pm);
+    if (exact16) std::memcpy(exact16, pm.exact.data(), pm.exact.size() * sizeof(srt::ExactTri));
+    if (filt8) std::memcpy(filt8, pm.filt.data(), pm.filt.size() * sizeof(srt::FilterTri));
+    if (filt2_8) std::memcpy(filt2_8, pm.filt2.data(), pm.filt2.size() * sizeof(srt::FilterTri2));
+    if (tile_m) std::memcpy(tile_m, pm.tile_m.data(), pm.tile_m.size() * sizeof(float));
+    if (n_padded) *n_padded = pm.n_padded;
+    if (n_unfilterable) *n_unfilterable = pm.unfilterable + (g.filterable ? 0u : 0u);
+    return SRT_OK;
+}
+
+// diagnostic: measured FP32 FMA peak of this GPU in TFLOP/s (2 flop per FFMA), best of `repeats` launches
+int srt_debug_ffma_peak(srt_ctx* c, int repeats, float* tflops_out)
+{
+    if (!c || !tflops_out) return SRT_ERR_INVALID;
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    cudaDeviceProp prop{};
+    SRT_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 14;
+    float* scratch = nullptr;
+    SRT_CUDA(c, cudaMalloc(&scratch, (size_t)blocks * 256 * sizeof(float)));
+    float best = 0.0f;
+    for (int r = 0; r < (repeats < 1 ? 1 : repeats) + 1; ++r) {       // first launch is the warm-up
+        SRT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+        SRT_CUDA(c, srt::launch_ffma_peak(scratch, blocks, iters, c->stream));
+        SRT_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+        SRT_CUDA(c, cudaEventSynchronize(c->ev[3]));
+        float ms = 0.0f;
+        SRT_CUDA(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
+        const double flop = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+        const float tf = (float)(flop / (ms * 1e-3) / 1e12);
+        if (r > 0 && tf > best) best = tf;
+    }
+    cudaFree(scratch);
+    *tflops_out = best;
+    return SRT_OK;
+}
+
+// test/diagnostic hook (not part of the reference-facing surface): count exact-path tests
+int srt_debug_count_exact(srt_ctx* c, int enable)
+{
+    if (!c) return SRT_ERR_INVALID;
+    c->count_exact = enable != 0;
+    return SRT_OK;
+}
+
+} // extern "C"

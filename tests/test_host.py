@@ -1,0 +1,132 @@
+"""Host-side logic of the product (camera, bbox, partition, pre-pack, filter margins) against the oracle.
+CPU only: these entry points of libsrt_b200.so do no GPU work."""
+import numpy as np
+import pytest
+
+from conftest import bits
+from simpleraytracing_b200 import scene
+
+
+def test_bbox_and_camera_bit_exact(srtlib, oracle, dragon):
+    lo, hi = srtlib.scene_bbox([(dragon, 0.1037)])
+    cam_o = oracle.camera(dragon)
+    assert (bits(lo) == bits(cam_o.vec("lower"))).all() and (bits(hi) == bits(cam_o.vec("upper"))).all()
+    for W, H in ((128, 128), (1024, 1024), (2048, 2048), (1512, 1512), (640, 480), (3, 7)):
+        cam = srtlib.camera_from_bbox(lo, hi, W, H)
+        for n in ("origin", "detector", "up", "right"):
+            assert (bits(cam.vec(n)) == bits(cam_o.vec(n))).all(), (n, W, H)
+        sp = oracle.pixel_spacing(cam_o, W, H)
+        assert bits(np.float32(cam.pixel_spacing[0])) == bits(sp) and cam.pixel_spacing[1] == cam.pixel_spacing[0]
+
+
+def test_bbox_multi_mesh(srtlib, oracle, dragon):
+    lo, hi = srtlib.scene_bbox([(dragon, 0.1)])
+    quad = scene.logo_quad(lo, hi)
+    lo2, hi2 = srtlib.scene_bbox([(dragon, 0.1), (quad, 0.3)])
+    cam = oracle.camera(np.concatenate([dragon, quad]))
+    assert (bits(lo2) == bits(cam.vec("lower"))).all() and (bits(hi2) == bits(cam.vec("upper"))).all()
+
+
+def test_camera_rejects_bad_arguments(srtlib):
+    from simpleraytracing_b200 import SrtError
+    with pytest.raises(SrtError):
+        srtlib.camera_from_bbox([0, 0, 0], [1, 1, 1], 0, 8)
+
+
+def test_partition_rows_reference_rule(srtlib, oracle):
+    for H, n in ((2048, 8), (2048, 3), (10, 4), (7, 8), (1, 1), (1512, 5)):
+        s, e = oracle.partition(H, n)
+        got = [srtlib.partition_rows(H, n, i) for i in range(n)]
+        for i in range(n):
+            if e[i] + 1 > s[i] or H >= n:       # the reference's [start, end] is inclusive
+                assert got[i] == (int(s[i]), int(e[i]) + 1), (H, n, i)
+        assert got[0][0] == 0 and got[-1][1] == H
+        assert all(got[i][1] == got[i + 1][0] for i in range(n - 1))
+
+
+def test_triangle_normals_bit_exact(srtlib, oracle, dragon):
+    n = srtlib.triangle_normals(dragon[:4000])
+    ref = np.array([oracle.triangle_normal(t) for t in dragon[:4000]])
+    assert (bits(n) == bits(ref)).all()
+
+
+def test_prepack_exact_constants(srtlib, oracle, dragon):
+    """ExactTri must hold the floats Ray::intersect would compute (Ray.cxx:86-122), bit for bit."""
+    lo, hi = srtlib.scene_bbox([(dragon, 0.1)])
+    cam = srtlib.camera_from_bbox(lo, hi, 256, 256)
+    pk = srtlib.debug_prepack(dragon, cam)
+    f = np.float32
+    p1, p2, p3 = dragon[:, 0:3], dragon[:, 3:6], dragon[:, 6:9]
+    o = cam.vec("origin")
+    e1 = p2 - p1; e2 = p3 - p1; tv = o[None, :] - p1
+
+    def cross(a, b):      # Vec3.inl:321-329, float32 ops, one rounding each
+        return np.stack([a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1], a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2],
+                         a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]], 1)
+    qv = cross(tv, e1)
+    e2q = (e2[:, 0] * qv[:, 0] + e2[:, 1] * qv[:, 1]) + e2[:, 2] * qv[:, 2]
+    E = pk["exact"]
+    expect = np.concatenate([e2, e1, tv, qv, e2q[:, None], srtlib.triangle_normals(dragon)], 1).astype(f)
+    assert expect.dtype == f and (bits(E) == bits(expect)).all()
+    assert pk["unfilterable"] == 0 and pk["n_padded"] == len(dragon) + len(dragon) % 2
+
+
+@pytest.mark.parametrize("size", [48, 96])
+def test_filter_never_rejects_a_hit_dragon(srtlib, oracle, dragon, size):
+    """CPU emulation of the kernel's FFMA filter vs the oracle for every (pixel, triangle) pair."""
+    lo, hi = srtlib.scene_bbox([(dragon, 0.1)])
+    cam = srtlib.camera_from_bbox(lo, hi, size, size)
+    pk = srtlib.debug_prepack(dragon, cam)
+    a = oracle.filter_audit(dragon, oracle.camera(dragon), size, size, pk)
+    assert a["pairs"] == size * size * len(dragon)
+    assert a["violations"] == 0
+    assert a["hits"] > 0 and a["survive1"] >= a["hits"]
+    assert a["survive0_tile"] < 0.03 * a["pairs"]          # the filter must actually filter
+    assert a["survive1"] < 10 * a["hits"]
+
+
+def _adversarial_mesh(cam_o, oracle, W, H, rng):
+    """Triangles whose vertices / edges lie exactly on pixel rays (the boundary cases of u, v, u+v)."""
+    o = cam_o.vec("origin").astype(np.float64)
+    tris = []
+    for _ in range(300):
+        pix = rng.integers(0, [H, W], size=(3, 2))
+        ts = rng.uniform(150, 300, size=3)
+        pts = []
+        for (r, c), t in zip(pix, ts):
+            _, db = oracle.make_ray(cam_o, W, H, int(r), int(c))
+            pts.append(o + t * db.astype(np.float64))
+        kind = rng.integers(0, 4)
+        if kind == 1:      # sliver: third vertex on the edge of the first two
+            pts[2] = pts[0] + (pts[1] - pts[0]) * rng.uniform()
+        elif kind == 2:    # tiny triangle around one pixel ray
+            pts[1] = pts[0] + rng.normal(size=3) * 1e-3
+            pts[2] = pts[0] + rng.normal(size=3) * 1e-3
+        elif kind == 3:    # huge triangle
+            pts[1] = pts[0] + rng.normal(size=3) * 500
+            pts[2] = pts[0] + rng.normal(size=3) * 500
+        tris.append(np.concatenate(pts))
+    return np.asarray(tris, np.float32)
+
+
+def test_filter_never_rejects_a_hit_adversarial(srtlib, oracle, dragon):
+    rng = np.random.default_rng(11)
+    cam_o = oracle.camera(dragon)
+    lo, hi = cam_o.vec("lower"), cam_o.vec("upper")
+    W = H = 40
+    tri = _adversarial_mesh(cam_o, oracle, W, H, rng)
+    cam = srtlib.camera_from_bbox(lo, hi, W, H)
+    pk = srtlib.debug_prepack(tri, cam)
+    a = oracle.filter_audit(tri, cam_o, W, H, pk)
+    assert a["violations"] == 0 and a["hits"] > 500
+
+
+def test_unfilterable_triangles_always_survive(srtlib, oracle, dragon):
+    cam_o = oracle.camera(dragon)
+    cam = srtlib.camera_from_bbox(cam_o.vec("lower"), cam_o.vec("upper"), 16, 16)
+    tri = dragon[:6].copy()
+    tri[1, 4] = np.inf; tri[3, 0] = np.nan; tri[4, :] = 3e38
+    pk = srtlib.debug_prepack(tri, cam)
+    assert pk["unfilterable"] == 3
+    for k in (1, 3, 4):
+        assert (pk["filt"][k] == 0).all() and (pk["filt2"][k] == 0).all()
