@@ -113,15 +113,15 @@ def cpu_sample_rate(engine, kind, tri, W, H, seconds, threads):
     ntri = len(tri)
     cam = engine.camera(tri, [ntri]) if kind == "reference" else engine.camera(tri)
     start = (H // 2) * W
-    probe = max(threads * 4, 64)
-    t0 = time.perf_counter()
-    engine.render_lbuffer(tri, [ntri], cam, W, H, pixel_range=(start, start + probe - 1), threads=threads)
-    dt = max(time.perf_counter() - t0, 1e-4)
-    n_pix = int(min(W * H - start, max(probe, probe * seconds / dt)))
-    t0 = time.perf_counter()
-    engine.render_lbuffer(tri, [ntri], cam, W, H, pixel_range=(start, start + n_pix - 1), threads=threads)
-    dt = time.perf_counter() - t0
-    return n_pix * ntri / dt, n_pix, dt
+    n_pix = max(threads * 16, 256)
+    while True:                                   # grow the sample until it takes about `seconds`
+        n_pix = int(min(W * H - start, n_pix))
+        t0 = time.perf_counter()
+        engine.render_lbuffer(tri, [ntri], cam, W, H, pixel_range=(start, start + n_pix - 1), threads=threads)
+        dt = max(time.perf_counter() - t0, 1e-4)
+        if dt >= 0.6 * seconds or n_pix >= W * H - start:
+            return n_pix * ntri / dt, n_pix, dt
+        n_pix = int(n_pix * min(8.0, max(1.5, 1.1 * seconds / dt)))
 
 
 def run_reference_arm(args):
@@ -176,7 +176,10 @@ def run_ours(args):
 
     lib = Library()
     ctx = Context(local, lib)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream shared by torch (events, NCCL, copies) and the library's kernels
+    # (handle 0 would mean "the context's own stream" to srt_set_stream)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     tri = scene.dragon()

@@ -171,7 +171,8 @@ int  srt_debug_count_exact(srt_ctx* ctx, int enable);
 int  srt_debug_ffma_peak(srt_ctx* ctx, int repeats, float* tflops_out);
 /* Diagnostic, host only (no GPU needed): the packed per-triangle constants the kernels stream.
  * exact16: 16 floats / triangle; filt8, filt2_8: 8 floats / padded triangle (padding = multiple of 2);
- * tile_m: one margin per 512-triangle tile (+1 spare). Any output may be NULL. */
+ * tile_m: one margin per tile of srt_debug_tile_triangles() triangles (+1 spare). Any output may be NULL. */
+int  srt_debug_tile_triangles(void);
 int  srt_debug_prepack(const float* vertices, uint32_t n_triangles, const srt_camera* cam, float* exact16,
                        float* filt8, float* filt2_8, float* tile_m, uint32_t* n_padded, uint32_t* n_unfilterable);
 

@@ -154,7 +154,7 @@ class Oracle:
     def save_text(self, path, img, W, H):
         return self.lib.oracle_save_text(str(path).encode(), np.ascontiguousarray(img, np.float32).reshape(-1), W, H)
 
-    def filter_audit(self, tri, cam, W, H, packed, pixel_range=None, threads=None, tile_tris=512):
+    def filter_audit(self, tri, cam, W, H, packed, pixel_range=None, threads=None):
         """Audit the product's packed filter constants against the oracle's intersect.
         -> dict(pairs, survive0_tile, survive0, survive1, hits, violations)"""
         tri = np.ascontiguousarray(tri, np.float32).reshape(-1)
@@ -164,7 +164,7 @@ class Oracle:
         rc = self.lib.oracle_filter_audit(tri, n, C.byref(cam), W, H,
                                           np.ascontiguousarray(packed["filt"], np.float32).reshape(-1),
                                           np.ascontiguousarray(packed["filt2"], np.float32).reshape(-1),
-                                          np.ascontiguousarray(packed["tile_m"], np.float32), tile_tris, b, e,
+                                          np.ascontiguousarray(packed["tile_m"], np.float32), int(packed["tile_tris"]), b, e,
                                           threads or os.cpu_count() or 1, counts.ctypes.data_as(C.c_void_p))
         if rc:
             raise RuntimeError("host CPU has no FMA: cannot emulate the kernel's FFMA sequence")

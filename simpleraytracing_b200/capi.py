@@ -53,7 +53,7 @@ EXPORTS = [
     "srt_create", "srt_destroy", "srt_last_error", "srt_version", "srt_set_stream", "srt_synchronize",
     "srt_default_params", "srt_scene_bbox", "srt_camera_from_bbox", "srt_partition_rows", "srt_triangle_normals",
     "srt_set_meshes", "srt_set_camera", "srt_render_lbuffer", "srt_render_lbuffer_device", "srt_repair",
-    "srt_repair_device", "srt_render_xray", "srt_last_timing", "srt_debug_count_exact", "srt_debug_prepack", "srt_debug_ffma_peak",
+    "srt_repair_device", "srt_render_xray", "srt_last_timing", "srt_debug_count_exact", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_tile_triangles",
 ]
 
 
@@ -163,7 +163,8 @@ class Library:
         exact = np.zeros((max(n, 1), 16), np.float32)
         filt = np.zeros((max(npad, 1), 8), np.float32)
         filt2 = np.zeros((max(npad, 1), 8), np.float32)
-        tile_m = np.zeros((npad + 511) // 512 + 1, np.float32)
+        tt = self.lib.srt_debug_tile_triangles()
+        tile_m = np.zeros((npad + tt - 1) // tt + 1, np.float32)
         a = C.c_uint32(); b = C.c_uint32()
         rc = self.lib.srt_debug_prepack(_ptr(tri, np.float32), n, C.byref(cam), _ptr(exact, np.float32),
                                         _ptr(filt, np.float32), _ptr(filt2, np.float32), _ptr(tile_m, np.float32),
@@ -172,7 +173,7 @@ class Library:
             raise SrtError(rc, "srt_debug_prepack")
         assert a.value == npad
         return dict(exact=exact[:n], filt=filt[:npad], filt2=filt2[:npad], tile_m=tile_m, n_padded=a.value,
-                    unfilterable=b.value)
+                    unfilterable=b.value, tile_tris=tt)
 
 
 class Context:

@@ -177,12 +177,79 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 // kStages-deep shared-memory ring with 1-D bulk copies (TMA) signalled on mbarriers; every
 // thread evaluates the affine strip test for its P pixels against each triangle of the tile.
 // Survivors (rare, spatially coherent) run level 1 and then the exact reference sequence.
+//
+// Loop shape (driven by the ncu source view of the first version, profiles/r01_*):
+//  * the next group's coefficients are prefetched into registers while the current group is
+//    evaluated (no LDS latency on the critical path);
+//  * the vote on a group's survivors is taken one iteration later, when its FMNMX3 chain has
+//    long retired (no FMNMX3 -> FSETP -> VOTE -> BRA stall);
+//  * the slow path is an out-of-line function reading only global memory, so a pending group
+//    can be resolved after its shared-memory stage has been recycled.
+// Triangle order per pixel is preserved: pending groups are resolved strictly in order.
+
+struct SlowArgs {
+    const float4* filt; const float4* filt2; const float4* exact;
+    uint32_t n;                  // triangles in the mesh
+    float y; uint32_t row, col0; int row_ok;
+};
+
 template <int P>
-__global__ void __launch_bounds__(128) lbuffer_filtered_kernel(const __grid_constant__ RenderArgs a)
+__device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const SlowArgs& s, uint32_t jj0, uint32_t pend,
+                                                float* dist, int* ssum, uint32_t* hits, unsigned long long& n_exact)
+{
+#pragma unroll 1
+    for (uint32_t g = 0; g < kGroupTris; ++g) {
+        const uint32_t jj = jj0 + g;                                   // triangle index in the mesh
+        if (jj >= s.n) break;                                          // padding entry
+        if (!__any_sync(0xffffffffu, (pend >> g) & 1u)) continue;      // no lane has a survivor for this triangle
+        const float4 fa = __ldg(s.filt + 2 * (size_t)jj), fb = __ldg(s.filt + 2 * (size_t)jj + 1);
+        const float bs = fmaf(fa.y, s.y, fa.z), bd = fmaf(fb.x, s.y, fb.y);
+        uint32_t mask = 0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            const float xk = (float)(s.col0 + k) + cam.xc;
+            const float S = fmaf(fa.x, xk, bs), Dd = fmaf(fa.w, xk, bd);
+            if (!(fabsf(S) > fabsf(Dd) + fb.z)) mask |= 1u << k;       // per-triangle margin (NaN survives)
+        }
+        if (!s.row_ok) mask = 0;
+        if (mask == 0) continue;
+        const float4 ga = __ldg(s.filt2 + 2 * (size_t)jj), gb = __ldg(s.filt2 + 2 * (size_t)jj + 1);
+        const float b2 = fmaf(ga.y, s.y, ga.z), b3 = fmaf(gb.y, s.y, gb.z);
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            const float xk = (float)(s.col0 + k) + cam.xc;
+            const float Dd = fmaf(fa.w, xk, bd);
+            const float X2 = fmaf(ga.x, xk, b2), X3 = fmaf(gb.x, xk, b3);
+            if ((fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w)) mask &= ~(1u << k);
+        }
+        if (mask == 0) continue;
+        const float4 A = __ldg(s.exact + 4 * (size_t)jj), B = __ldg(s.exact + 4 * (size_t)jj + 1);
+        const float4 C = __ldg(s.exact + 4 * (size_t)jj + 2), Dn = __ldg(s.exact + 4 * (size_t)jj + 3);
+#pragma unroll 1
+        while (mask) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t col = s.col0 + k;
+            if (col >= cam.W) break;
+            const RayDirs r = make_ray(cam, s.row, col);
+            float tt;
+            ++n_exact;
+            if (exact_intersect(r, A, B, C, Dn.x, tt)) accumulate_hit(r, Dn, tt, dist[k], ssum[k], hits[k]);
+        }
+    }
+}
+
+template <int P>
+#ifndef SRT_MIN_CTAS
+#define SRT_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(const __grid_constant__ RenderArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* tiles = reinterpret_cast<float4*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileTris * 32);
+    // 64 B of slack after the last stage: the register prefetch of "the next group" may run one group
+    // past the end of a tile (the values are never used)
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileTris * 32 + 64);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t col0 = (blockIdx.x * 8 + (warp & 1) * 4 + (lane & 3)) * P;
@@ -217,6 +284,9 @@ __global__ void __launch_bounds__(128) lbuffer_filtered_kernel(const __grid_cons
         for (int k = 0; k < P; ++k) { dist[k] = 0.0f; ssum[k] = 0; hits[k] = 0; }
 
         if (M.contributes && M.n > 0) {
+            SlowArgs sa;
+            sa.filt = M.filt; sa.filt2 = M.filt2; sa.exact = M.exact; sa.n = M.n;
+            sa.y = y; sa.row = row; sa.col0 = col0; sa.row_ok = row_ok;
             const uint32_t n_tiles = (M.n_padded + kTileTris - 1) / kTileTris;
             auto issue = [&](uint32_t t) {
                 const uint32_t stage = issued % kStages;
@@ -230,70 +300,48 @@ __global__ void __launch_bounds__(128) lbuffer_filtered_kernel(const __grid_cons
             };
             for (uint32_t t = 0; t < min(kStages - 1, n_tiles); ++t) issue(t);
 
+            uint32_t pend = 0;             // bit g: triangle g of the previous group may survive in this lane
+            uint32_t pend_j = 0;           // its first triangle index
+
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 if (t + kStages - 1 < n_tiles) issue(t + kStages - 1);
                 const uint32_t stage = consumed % kStages;
                 mbar_wait(&full[stage], (consumed / kStages) & 1u);
                 const float4* tp = tiles + (size_t)stage * kTileTris * 2;
-                const uint32_t cnt = min(kTileTris, M.n_padded - t * kTileTris);
+                const uint32_t cnt = min(kTileTris, M.n_padded - t * kTileTris);    // multiple of kGroupTris
                 const float negM = -__ldg(M.tile_m + t);
+                const uint32_t jbase = t * kTileTris;
 
+                float4 a0 = tp[0], b0 = tp[1], a1 = tp[2], b1 = tp[3];
 #pragma unroll 1
                 for (uint32_t j = 0; j < cnt; j += kGroupTris) {
-                    const float4 a0 = tp[2 * j], b0 = tp[2 * j + 1], a1 = tp[2 * j + 2], b1 = tp[2 * j + 3];
+                    // prefetch the next group (after the last group this reads the slack / next stage: unused)
+                    const float4* np = tp + 2 * (j + kGroupTris);
+                    const float4 na0 = np[0], nb0 = np[1], na1 = np[2], nb1 = np[3];
+
                     const float bs0 = fmaf(a0.y, y, a0.z), bd0 = fmaf(b0.x, y, b0.y);
                     const float bs1 = fmaf(a1.y, y, a1.z), bd1 = fmaf(b1.x, y, b1.y);
-                    float acc = -FLT_MAX;
+                    float acc0 = -FLT_MAX, acc1 = -FLT_MAX;        // one survivor accumulator per triangle
 #pragma unroll
-                    for (int k = 0; k < P; ++k) {
+                    for (int k = 0; k < P; k += 2) {
+                        const int k1 = (k + 1 < P) ? k + 1 : k;
                         const float S0 = fmaf(a0.x, x[k], bs0), D0 = fmaf(a0.w, x[k], bd0);
                         const float S1 = fmaf(a1.x, x[k], bs1), D1 = fmaf(a1.w, x[k], bd1);
-                        acc = fmax3(acc, fabsf(D0) - fabsf(S0), fabsf(D1) - fabsf(S1));
+                        const float S2 = fmaf(a0.x, x[k1], bs0), D2 = fmaf(a0.w, x[k1], bd0);
+                        const float S3 = fmaf(a1.x, x[k1], bs1), D3 = fmaf(a1.w, x[k1], bd1);
+                        acc0 = fmax3(acc0, fabsf(D0) - fabsf(S0), fabsf(D2) - fabsf(S2));
+                        acc1 = fmax3(acc1, fabsf(D1) - fabsf(S1), fabsf(D3) - fabsf(S3));
                     }
-                    if (__any_sync(0xffffffffu, acc >= negM)) {
-                        // ---- slow path: per-triangle margins, level 1, exact test ----
-#pragma unroll 1
-                        for (uint32_t g = 0; g < kGroupTris; ++g) {
-                            const uint32_t jj = t * kTileTris + j + g;          // triangle index in the mesh
-                            if (jj >= M.n) break;                                // padding entry
-                            const float4 fa = tp[2 * (j + g)], fb = tp[2 * (j + g) + 1];
-                            const float bs = fmaf(fa.y, y, fa.z), bd = fmaf(fb.x, y, fb.y);
-                            uint32_t mask = 0;
-#pragma unroll
-                            for (int k = 0; k < P; ++k) {
-                                const float S = fmaf(fa.x, x[k], bs), Dd = fmaf(fa.w, x[k], bd);
-                                if (!(fabsf(S) > fabsf(Dd) + fb.z)) mask |= 1u << k;
-                            }
-                            if (!row_ok) mask = 0;
-                            if (mask == 0) continue;
-                            const float4 ga = __ldg(M.filt2 + 2 * (size_t)jj), gb = __ldg(M.filt2 + 2 * (size_t)jj + 1);
-                            const float b2 = fmaf(ga.y, y, ga.z), b3 = fmaf(gb.y, y, gb.z);
-#pragma unroll
-                            for (int k = 0; k < P; ++k) {
-                                const float Dd = fmaf(fa.w, x[k], bd);
-                                const float X2 = fmaf(ga.x, x[k], b2), X3 = fmaf(gb.x, x[k], b3);
-                                if ((fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w)) mask &= ~(1u << k);
-                            }
-                            if (mask == 0) continue;
-                            const float4 A = __ldg(M.exact + 4 * (size_t)jj), B = __ldg(M.exact + 4 * (size_t)jj + 1);
-                            const float4 C = __ldg(M.exact + 4 * (size_t)jj + 2), Dn = __ldg(M.exact + 4 * (size_t)jj + 3);
-#pragma unroll 1
-                            while (mask) {
-                                const int k = __ffs(mask) - 1;
-                                mask &= mask - 1;
-                                const uint32_t col = col0 + k;
-                                if (col >= W) break;
-                                const RayDirs r = make_ray(a.cam, row, col);
-                                float tt;
-                                ++n_exact;
-                                if (exact_intersect(r, A, B, C, Dn.x, tt)) accumulate_hit(r, Dn, tt, dist[k], ssum[k], hits[k]);
-                            }
-                        }
-                    }
+                    // resolve the PREVIOUS group now: its predicates have been ready for a whole iteration
+                    if (__any_sync(0xffffffffu, pend != 0)) filtered_slow_path<P>(a.cam, sa, pend_j, pend, dist, ssum, hits, n_exact);
+                    pend = (acc0 >= negM ? 1u : 0u) | (acc1 >= negM ? 2u : 0u);
+                    pend_j = jbase + j;
+                    a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
                 }
                 __syncthreads();      // every warp is done with this stage before it is refilled
                 ++consumed;
             }
+            if (__any_sync(0xffffffffu, pend != 0)) filtered_slow_path<P>(a.cam, sa, pend_j, pend, dist, ssum, hits, n_exact);
         }
 
 #pragma unroll
@@ -373,9 +421,11 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, f
 #pragma unroll
     for (int k = 0; k < 16; ++k) r[k] = (float)(threadIdx.x + k);
 #pragma unroll 1
-    for (int i = 0; i < iters; ++i) {
+    for (int i = 0; i < iters; i += 8) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) r[k] = fmaf(r[k], a, b);
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) r[k] = fmaf(r[k], a, b);
     }
     float s = 0.0f;
 #pragma unroll
@@ -404,7 +454,7 @@ cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
 template <int P>
 static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
 {
-    const size_t smem = (size_t)kStages * kTileTris * 32 + kStages * sizeof(uint64_t);
+    const size_t smem = (size_t)kStages * kTileTris * 32 + 64 + kStages * sizeof(uint64_t);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(lbuffer_filtered_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -5,7 +5,10 @@
 
 namespace srt {
 
-constexpr uint32_t kTileTris  = 512;   // triangles per shared-memory tile of level-0 filter data (16 KB)
+#ifndef SRT_TILE_TRIS
+#define SRT_TILE_TRIS 256
+#endif
+constexpr uint32_t kTileTris  = SRT_TILE_TRIS;   // triangles per shared-memory tile of level-0 filter data (8 KB)
 constexpr uint32_t kGroupTris = 2;     // triangles per vote group in the filtered kernel
 constexpr uint32_t kStages    = 3;     // bulk-copy pipeline depth
 

@@ -533,6 +533,9 @@ int srt_last_timing(srt_ctx* c, srt_timing* out)
     return SRT_OK;
 }
 
+// diagnostic: triangles per shared-memory tile (granularity of tile_m)
+int srt_debug_tile_triangles(void) { return (int)srt::kTileTris; }
+
 // diagnostic (host only, no GPU): run the pre-pack for one mesh and return the packed arrays.
 // exact16: 16 floats per triangle; filt8 / filt2_8: 8 floats per padded triangle; tile_m: one per tile.
 int srt_debug_prepack(const float* vertices, uint32_t n, const srt_camera* cam, float* exact16, float* filt8,

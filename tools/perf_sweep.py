@@ -12,7 +12,10 @@ from simpleraytracing_b200 import Context, Library, scene, KERNEL_EXACT, KERNEL_
 
 
 def main():
-    lib = Library(); ctx = Context(0, lib)
+    import os
+    lib = Library(os.environ.get("SRT_LIB") or None); ctx = Context(0, lib)
+    only_filtered = bool(os.environ.get("SRT_ONLY_FILTERED"))
+    ppt_list = tuple(int(v) for v in os.environ.get("SRT_PPTS", "1,2,4,8").split(","))
     tri = scene.dragon(); nt = len(tri)
     lo, hi = lib.scene_bbox([(tri, 0.1037)])
     ctx.set_meshes([(tri, 0.1037)])
@@ -21,7 +24,7 @@ def main():
     for size in sizes:
         ctx.set_camera(lib.camera_from_bbox(lo, hi, size, size))
         L = np.zeros(size * size, np.float32)
-        for kernel, ppts in ((KERNEL_FILTERED, (1, 2, 4, 8)), (KERNEL_EXACT, (0,))):
+        for kernel, ppts in ((KERNEL_FILTERED, ppt_list),) + (() if only_filtered else ((KERNEL_EXACT, (0,)),)):
             for ppt in ppts:
                 p = lib.default_params(kernel=kernel, pixels_per_thread=ppt)
                 ms = []
