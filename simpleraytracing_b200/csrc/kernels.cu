@@ -194,14 +194,13 @@ struct SlowArgs {
 };
 
 template <int P>
-__device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const SlowArgs& s, uint32_t jj0, uint32_t pend,
+__device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const SlowArgs& s, uint32_t jj0,
                                                 float* dist, int* ssum, uint32_t* hits, unsigned long long& n_exact)
 {
 #pragma unroll 1
     for (uint32_t g = 0; g < kGroupTris; ++g) {
         const uint32_t jj = jj0 + g;                                   // triangle index in the mesh
         if (jj >= s.n) break;                                          // padding entry
-        if (!__any_sync(0xffffffffu, (pend >> g) & 1u)) continue;      // no lane has a survivor for this triangle
         const float4 fa = __ldg(s.filt + 2 * (size_t)jj), fb = __ldg(s.filt + 2 * (size_t)jj + 1);
         const float bs = fmaf(fa.y, s.y, fa.z), bd = fmaf(fb.x, s.y, fb.y);
         uint32_t mask = 0;
@@ -300,7 +299,7 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
             };
             for (uint32_t t = 0; t < min(kStages - 1, n_tiles); ++t) issue(t);
 
-            uint32_t pend = 0;             // bit g: triangle g of the previous group may survive in this lane
+            bool pend = false;             // may the previous group have a survivor in this lane?
             uint32_t pend_j = 0;           // its first triangle index
 
             for (uint32_t t = 0; t < n_tiles; ++t) {
@@ -333,15 +332,15 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
                         acc1 = fmax3(acc1, fabsf(D1) - fabsf(S1), fabsf(D3) - fabsf(S3));
                     }
                     // resolve the PREVIOUS group now: its predicates have been ready for a whole iteration
-                    if (__any_sync(0xffffffffu, pend != 0)) filtered_slow_path<P>(a.cam, sa, pend_j, pend, dist, ssum, hits, n_exact);
-                    pend = (acc0 >= negM ? 1u : 0u) | (acc1 >= negM ? 2u : 0u);
+                    if (__any_sync(0xffffffffu, pend)) filtered_slow_path<P>(a.cam, sa, pend_j, dist, ssum, hits, n_exact);
+                    pend = fmaxf(acc0, acc1) >= negM;
                     pend_j = jbase + j;
                     a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
                 }
                 __syncthreads();      // every warp is done with this stage before it is refilled
                 ++consumed;
             }
-            if (__any_sync(0xffffffffu, pend != 0)) filtered_slow_path<P>(a.cam, sa, pend_j, pend, dist, ssum, hits, n_exact);
+            if (__any_sync(0xffffffffu, pend)) filtered_slow_path<P>(a.cam, sa, pend_j, dist, ssum, hits, n_exact);
         }
 
 #pragma unroll
