@@ -173,6 +173,8 @@ int  srt_debug_ffma_peak(srt_ctx* ctx, int repeats, float* tflops_out);
  * exact16: 16 floats / triangle; filt8, filt2_8: 8 floats / padded triangle (padding = multiple of 2);
  * tile_m: one margin per tile of srt_debug_tile_triangles() triangles (+1 spare). Any output may be NULL. */
 int  srt_debug_tile_triangles(void);
+/* Diagnostic: the same arrays as computed ON THE GPU for mesh `mesh` of the context's scene. */
+int  srt_debug_download_packed(srt_ctx* ctx, int mesh, float* exact16, float* filt8, float* filt2_8, float* tile_m);
 int  srt_debug_prepack(const float* vertices, uint32_t n_triangles, const srt_camera* cam, float* exact16,
                        float* filt8, float* filt2_8, float* tile_m, uint32_t* n_padded, uint32_t* n_unfilterable);
 

@@ -53,7 +53,7 @@ EXPORTS = [
     "srt_create", "srt_destroy", "srt_last_error", "srt_version", "srt_set_stream", "srt_synchronize",
     "srt_default_params", "srt_scene_bbox", "srt_camera_from_bbox", "srt_partition_rows", "srt_triangle_normals",
     "srt_set_meshes", "srt_set_camera", "srt_render_lbuffer", "srt_render_lbuffer_device", "srt_repair",
-    "srt_repair_device", "srt_render_xray", "srt_last_timing", "srt_debug_count_exact", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_tile_triangles",
+    "srt_repair_device", "srt_render_xray", "srt_last_timing", "srt_debug_count_exact", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_tile_triangles", "srt_debug_download_packed",
 ]
 
 
@@ -101,6 +101,7 @@ class Library:
         L.srt_render_xray.argtypes = [vp, C.POINTER(Params), vp]
         L.srt_last_timing.argtypes = [vp, C.POINTER(Timing)]
         L.srt_debug_count_exact.argtypes = [vp, i32]
+        L.srt_debug_download_packed.argtypes = [vp, i32, vp, vp, vp, vp]
         L.srt_debug_ffma_peak.argtypes = [vp, i32, C.POINTER(C.c_float)]
         L.srt_debug_prepack.argtypes = [vp, u32, C.POINTER(Camera), vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32)]
 
@@ -256,6 +257,15 @@ class Context:
         img = np.empty(n, np.float32) if out is None else out
         self._ck(self.lib.srt_render_xray(self.h, C.byref(params), _ptr(img, np.float32)))
         return img
+
+    def download_packed(self, mesh, n):
+        tt = self.lib.srt_debug_tile_triangles()
+        npad = (n + 1) // 2 * 2
+        exact = np.zeros((max(n, 1), 16), np.float32); filt = np.zeros((max(npad, 1), 8), np.float32)
+        filt2 = np.zeros((max(npad, 1), 8), np.float32); tile_m = np.zeros((npad + tt - 1) // tt + 1, np.float32)
+        self._ck(self.lib.srt_debug_download_packed(self.h, mesh, _ptr(exact, np.float32), _ptr(filt, np.float32),
+                                                    _ptr(filt2, np.float32), _ptr(tile_m, np.float32)))
+        return dict(exact=exact[:n], filt=filt[:npad], filt2=filt2[:npad], tile_m=tile_m, n_padded=npad, tile_tris=tt)
 
     def ffma_peak_tflops(self, repeats=3):
         v = C.c_float()

@@ -17,6 +17,8 @@
 
 #include <cfloat>
 
+#include "prepack_math.h"
+
 namespace srt {
 namespace {
 
@@ -412,6 +414,65 @@ __global__ void __launch_bounds__(256) repair_kernel(const float* __restrict__ L
     image[pixel] = out;
 }
 
+// ------------------------------------------------------------------ scene pre-pack
+// One thread per triangle, one CTA per shared-memory tile of the render kernel (kTileTris), so the
+// tile's level-0 margin is a block-wide max.  Exact constants use round-to-nearest intrinsics
+// (prepack_math.h); the filter coefficients / margins are double precision.
+__global__ void __launch_bounds__(kTileTris) prepack_kernel(const float* __restrict__ vertices,
+                                                            const float* __restrict__ normals, uint32_t n,
+                                                            uint32_t n_padded, float ox, float oy, float oz,
+                                                            const __grid_constant__ FrameGeom g, ExactTri* exact,
+                                                            FilterTri* filt, FilterTri2* filt2, float* tile_m)
+{
+    __shared__ float red[kTileTris / 32];
+    const uint32_t i = blockIdx.x * kTileTris + threadIdx.x;
+    float m = 0.0f;
+    if (i < n) {
+        float v[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = vertices[9 * (size_t)i + k];
+        float nrm[3];
+        const float origin[3] = { ox, oy, oz };
+        if (normals) { nrm[0] = normals[3 * (size_t)i]; nrm[1] = normals[3 * (size_t)i + 1]; nrm[2] = normals[3 * (size_t)i + 2]; }
+        ExactTri E; FilterTri f; FilterTri2 f2;
+        pack_triangle(v, normals ? nrm : nullptr, origin, g, E, f, f2);
+        float4* eo = reinterpret_cast<float4*>(exact + i);
+        eo[0] = make_float4(E.e2x, E.e2y, E.e2z, E.e1x); eo[1] = make_float4(E.e1y, E.e1z, E.tx, E.ty);
+        eo[2] = make_float4(E.tz, E.qx, E.qy, E.qz);     eo[3] = make_float4(E.e2q, E.nx, E.ny, E.nz);
+        float4* fo = reinterpret_cast<float4*>(filt + i);
+        fo[0] = make_float4(f.bx, f.gx, f.ax, f.bd); fo[1] = make_float4(f.gd, f.ad, f.m, f.pad);
+        float4* go = reinterpret_cast<float4*>(filt2 + i);
+        go[0] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2); go[1] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
+        m = f.m;
+    } else if (i < n_padded) {
+        FilterTri f; FilterTri2 f2;
+        pack_padding(f, f2);
+        float4* fo = reinterpret_cast<float4*>(filt + i);
+        fo[0] = make_float4(f.bx, f.gx, f.ax, f.bd); fo[1] = make_float4(f.gd, f.ad, f.m, f.pad);
+        float4* go = reinterpret_cast<float4*>(filt2 + i);
+        go[0] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2); go[1] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < (int)(kTileTris / 32); ++w) t = fmaxf(t, red[w]);
+        tile_m[blockIdx.x] = t;
+    }
+}
+
+// Per-column / per-row detector offsets exactly as lbuffer.cxx:756-757:
+//   float v_offset = pixel_spacing[1] * (0.5 + row - H / 2.0)   (double product, narrowed to float)
+__global__ void offsets_kernel(float* u_off, float* v_off, uint32_t W, uint32_t H, float sp_u, float sp_v)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < W) u_off[i] = (float)__dmul_rn((double)sp_u, (0.5 + (double)i - (double)W / 2.0));
+    if (i < H) v_off[i] = (float)__dmul_rn((double)sp_v, (0.5 + (double)i - (double)H / 2.0));
+}
+
 // ------------------------------------------------------------------ FFMA peak probe
 // 16 independent FFMA chains per thread: the measured FP32 roofline denominator (bench.py).
 __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b)
@@ -433,6 +494,25 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, f
 }
 
 } // namespace
+
+cudaError_t launch_prepack(const float* vertices, const float* normals, uint32_t n, uint32_t n_padded,
+                           const float origin[3], const FrameGeom& g, void* exact, void* filt, void* filt2,
+                           float* tile_m, cudaStream_t s)
+{
+    const uint32_t tiles = (n_padded + kTileTris - 1) / kTileTris;
+    if (tiles == 0) return cudaSuccess;
+    prepack_kernel<<<tiles, kTileTris, 0, s>>>(vertices, normals, n, n_padded, origin[0], origin[1], origin[2], g,
+                                               (ExactTri*)exact, (FilterTri*)filt, (FilterTri2*)filt2, tile_m);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_offsets(float* u_off, float* v_off, uint32_t W, uint32_t H, float sp_u, float sp_v, cudaStream_t s)
+{
+    const uint32_t n = W > H ? W : H;
+    if (n == 0) return cudaSuccess;
+    offsets_kernel<<<(n + 255) / 256, 256, 0, s>>>(u_off, v_off, W, H, sp_u, sp_v);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_ffma_peak(float* scratch, int blocks, int iters, cudaStream_t s)
 {

@@ -56,6 +56,14 @@ cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s
 // Artefact repair + image fill (lbuffer.cxx:329-404).
 cudaError_t launch_repair(const float* L, float* image, uint32_t W, uint32_t H, uint32_t depth, cudaStream_t s);
 
+// Scene pre-pack on the GPU (prepack_math.h): raw vertices -> ExactTri / FilterTri / FilterTri2 / tile margins.
+struct FrameGeom;
+cudaError_t launch_prepack(const float* vertices, const float* normals, uint32_t n, uint32_t n_padded,
+                           const float origin[3], const FrameGeom& g, void* exact, void* filt, void* filt2,
+                           float* tile_m, cudaStream_t s);
+// Detector offset tables u_off[W], v_off[H] (lbuffer.cxx:756-757).
+cudaError_t launch_offsets(float* u_off, float* v_off, uint32_t W, uint32_t H, float sp_u, float sp_v, cudaStream_t s);
+
 // FP32 FMA throughput probe: blocks x 256 threads x iters x 16 FFMA.
 cudaError_t launch_ffma_peak(float* scratch, int blocks, int iters, cudaStream_t s);
 

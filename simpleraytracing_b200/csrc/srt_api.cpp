@@ -29,15 +29,15 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct HostMesh {
-    std::vector<float> vertices;     // 9 per triangle
-    std::vector<float> normals;      // 3 per triangle (always materialised)
-    uint32_t n = 0;
+// One mesh resident on the device: raw geometry as uploaded + the packed arrays the kernels stream.
+struct MeshBuf {
+    float* d_vertices = nullptr;     // 9 per triangle
+    float* d_normals = nullptr;      // 3 per triangle, only when the caller supplied normals
+    void* filt = nullptr; void* filt2 = nullptr; void* exact = nullptr; float* tile_m = nullptr;
+    size_t cap = 0;                  // capacity in triangles of all of the above
+    uint32_t n = 0, n_padded = 0;
+    bool has_normals = false;
     float mu = 0.0f;
-};
-
-struct DeviceMeshBuffers {
-    void* filt = nullptr; void* filt2 = nullptr; void* exact = nullptr; void* tile_m = nullptr;
 };
 
 } // namespace
@@ -49,16 +49,18 @@ struct srt_ctx {
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     std::string error;
 
-    std::vector<HostMesh> meshes;
+    std::vector<MeshBuf> meshes;
+    size_t n_meshes = 0;                 // meshes in use (buffers beyond are kept for reuse)
     bool have_camera = false;
     srt_camera camera{};
-    bool packed = false;                 // device scene matches meshes + camera
+    bool packed = false;                 // packed arrays match meshes + camera
     bool filterable = false;
 
-    std::vector<DeviceMeshBuffers> dmesh;
-    srt::DevMesh* d_meshes = nullptr;    // device array of descriptors (two variants: default / all contribute)
-    srt::DevMesh* d_meshes_all = nullptr;
+    std::vector<srt::DevMesh> h_desc;    // host copy of the descriptor arrays (default | all contribute)
+    srt::DevMesh* d_meshes = nullptr;    // device array: [0, n) default semantics, [n, 2n) all meshes contribute
+    size_t desc_cap = 0;
     float* d_u_off = nullptr; float* d_v_off = nullptr;
+    size_t off_cap_u = 0, off_cap_v = 0;
     uint64_t total_tris = 0, mesh0_tris = 0;
 
     // frame scratch for the host-pointer entry points
@@ -85,14 +87,19 @@ int fail(srt_ctx* c, int code, const char* fmt, ...)
     do { cudaError_t e__ = (call);                                                               \
          if (e__ != cudaSuccess) return fail((c), SRT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); } while (0)
 
+void free_mesh(MeshBuf& m)
+{
+    cudaFree(m.d_vertices); cudaFree(m.d_normals); cudaFree(m.filt); cudaFree(m.filt2); cudaFree(m.exact); cudaFree(m.tile_m);
+    m = MeshBuf{};
+}
+
 void free_scene(srt_ctx* c)
 {
-    for (auto& d : c->dmesh) { cudaFree(d.filt); cudaFree(d.filt2); cudaFree(d.exact); cudaFree(d.tile_m); }
-    c->dmesh.clear();
-    cudaFree(c->d_meshes); c->d_meshes = nullptr;
-    cudaFree(c->d_meshes_all); c->d_meshes_all = nullptr;
-    cudaFree(c->d_u_off); c->d_u_off = nullptr;
-    cudaFree(c->d_v_off); c->d_v_off = nullptr;
+    for (auto& m : c->meshes) free_mesh(m);
+    c->meshes.clear(); c->n_meshes = 0;
+    cudaFree(c->d_meshes); c->d_meshes = nullptr; c->desc_cap = 0;
+    cudaFree(c->d_u_off); c->d_u_off = nullptr; c->off_cap_u = 0;
+    cudaFree(c->d_v_off); c->d_v_off = nullptr; c->off_cap_v = 0;
     c->packed = false;
 }
 
@@ -105,6 +112,7 @@ void free_frame(srt_ctx* c)
 int ensure_frame(srt_ctx* c, size_t pixels)
 {
     if (pixels <= c->frame_cap) return SRT_OK;
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
     free_frame(c);
     SRT_CUDA(c, cudaMalloc(&c->d_L, pixels * 4));
     SRT_CUDA(c, cudaMalloc(&c->d_img, pixels * 4));
@@ -115,66 +123,73 @@ int ensure_frame(srt_ctx* c, size_t pixels)
     return SRT_OK;
 }
 
-// Upload the packed scene for the current meshes + camera.
+// Grow a mesh's device buffers to hold n triangles (only reallocates when growing).
+int ensure_mesh(srt_ctx* c, MeshBuf& m, size_t n, bool want_normals)
+{
+    const size_t pad = (n + srt::kGroupTris - 1) / srt::kGroupTris * srt::kGroupTris;
+    if (pad > m.cap || m.cap == 0) {
+        SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        const bool had_normals = m.d_normals != nullptr;
+        free_mesh(m);
+        const size_t cap = pad + pad / 8 + 64;
+        SRT_CUDA(c, cudaMalloc(&m.d_vertices, cap * 9 * sizeof(float)));
+        SRT_CUDA(c, cudaMalloc(&m.filt, cap * sizeof(srt::FilterTri)));
+        SRT_CUDA(c, cudaMalloc(&m.filt2, cap * sizeof(srt::FilterTri2)));
+        SRT_CUDA(c, cudaMalloc(&m.exact, cap * sizeof(srt::ExactTri)));
+        SRT_CUDA(c, cudaMalloc(&m.tile_m, (cap / srt::kTileTris + 2) * sizeof(float)));
+        if (had_normals || want_normals) SRT_CUDA(c, cudaMalloc(&m.d_normals, cap * 3 * sizeof(float)));
+        m.cap = cap;
+    }
+    if (want_normals && !m.d_normals) SRT_CUDA(c, cudaMalloc(&m.d_normals, m.cap * 3 * sizeof(float)));
+    return SRT_OK;
+}
+
+// (Re)build the packed arrays for the current meshes + camera: all on the GPU, all asynchronous.
 int pack_scene(srt_ctx* c)
 {
     if (c->packed) return SRT_OK;
-    if (c->meshes.empty()) return fail(c, SRT_ERR_INVALID, "srt_set_meshes has not been called");
+    if (c->n_meshes == 0) return fail(c, SRT_ERR_INVALID, "srt_set_meshes has not been called");
     if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
-    SRT_CUDA(c, cudaSetDevice(c->device));
-    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    free_scene(c);
     const srt_camera& cam = c->camera;
     const uint32_t W = cam.width, H = cam.height;
+    if (W > c->off_cap_u) {
+        SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_u_off); c->d_u_off = nullptr;
+        SRT_CUDA(c, cudaMalloc(&c->d_u_off, (size_t)W * 4)); c->off_cap_u = W;
+    }
+    if (H > c->off_cap_v) {
+        SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_v_off); c->d_v_off = nullptr;
+        SRT_CUDA(c, cudaMalloc(&c->d_v_off, (size_t)H * 4)); c->off_cap_v = H;
+    }
+    SRT_CUDA(c, srt::launch_offsets(c->d_u_off, c->d_v_off, W, H, cam.pixel_spacing[0], cam.pixel_spacing[1], c->stream));
 
-    // per-column / per-row offsets exactly as lbuffer.cxx:756-757:
-    //   float v_offset = pixel_spacing[1] * (0.5 + row - H / 2.0)   (double product, narrowed)
-    std::vector<float> u_off(W ? W : 1), v_off(H ? H : 1);
-    for (uint32_t col = 0; col < W; ++col)
-        u_off[col] = (float)((double)cam.pixel_spacing[0] * (0.5 + (double)col - (double)W / 2.0));
-    for (uint32_t row = 0; row < H; ++row)
-        v_off[row] = (float)((double)cam.pixel_spacing[1] * (0.5 + (double)row - (double)H / 2.0));
-    SRT_CUDA(c, cudaMalloc(&c->d_u_off, u_off.size() * 4));
-    SRT_CUDA(c, cudaMalloc(&c->d_v_off, v_off.size() * 4));
-    SRT_CUDA(c, cudaMemcpyAsync(c->d_u_off, u_off.data(), u_off.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    SRT_CUDA(c, cudaMemcpyAsync(c->d_v_off, v_off.data(), v_off.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    const srt::FrameGeom g = srt::make_frame_geom(cam.origin, cam.detector, cam.up, cam.right,
+                                                  cam.pixel_spacing[0], cam.pixel_spacing[1], W, H);
+    c->filterable = g.filterable != 0;
 
-    srt::FrameGeom g = srt::make_frame_geom(cam.origin, cam.detector, cam.up, cam.right,
-                                            cam.pixel_spacing[0], cam.pixel_spacing[1], W, H);
-    c->filterable = g.filterable;
-
-    std::vector<srt::DevMesh> desc(c->meshes.size());
-    c->dmesh.resize(c->meshes.size());
+    const size_t nm = c->n_meshes;
+    c->h_desc.assign(2 * nm, srt::DevMesh{});
     c->total_tris = 0;
-    for (size_t m = 0; m < c->meshes.size(); ++m) {
-        const HostMesh& hm = c->meshes[m];
-        srt::PackedMesh pm;
-        srt::prepack_mesh(hm.vertices.data(), hm.normals.data(), hm.n, cam.origin, g, srt::kTileTris, srt::kGroupTris, pm);
-        DeviceMeshBuffers& d = c->dmesh[m];
-        const size_t nf = pm.filt.size() ? pm.filt.size() : 1, ne = pm.exact.size() ? pm.exact.size() : 1;
-        SRT_CUDA(c, cudaMalloc(&d.filt, nf * sizeof(srt::FilterTri)));
-        SRT_CUDA(c, cudaMalloc(&d.filt2, nf * sizeof(srt::FilterTri2)));
-        SRT_CUDA(c, cudaMalloc(&d.exact, ne * sizeof(srt::ExactTri)));
-        SRT_CUDA(c, cudaMalloc(&d.tile_m, pm.tile_m.size() * 4));
-        if (hm.n) {
-            SRT_CUDA(c, cudaMemcpyAsync(d.filt, pm.filt.data(), pm.filt.size() * sizeof(srt::FilterTri), cudaMemcpyHostToDevice, c->stream));
-            SRT_CUDA(c, cudaMemcpyAsync(d.filt2, pm.filt2.data(), pm.filt2.size() * sizeof(srt::FilterTri2), cudaMemcpyHostToDevice, c->stream));
-            SRT_CUDA(c, cudaMemcpyAsync(d.exact, pm.exact.data(), pm.exact.size() * sizeof(srt::ExactTri), cudaMemcpyHostToDevice, c->stream));
-        }
-        SRT_CUDA(c, cudaMemcpyAsync(d.tile_m, pm.tile_m.data(), pm.tile_m.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        SRT_CUDA(c, cudaStreamSynchronize(c->stream));      // pm goes out of scope
-        desc[m].filt = (const float4*)d.filt; desc[m].filt2 = (const float4*)d.filt2;
-        desc[m].exact = (const float4*)d.exact; desc[m].tile_m = (const float*)d.tile_m;
-        desc[m].n = pm.n; desc[m].n_padded = pm.n_padded; desc[m].mu = hm.mu;
-        desc[m].contributes = (m == 0);                     // lbuffer.cxx:788: only meshes[0] adds path length
-        c->total_tris += hm.n;
+    for (size_t m = 0; m < nm; ++m) {
+        MeshBuf& mb = c->meshes[m];
+        SRT_CUDA(c, srt::launch_prepack(mb.d_vertices, mb.has_normals ? mb.d_normals : nullptr, mb.n, mb.n_padded,
+                                        cam.origin, g, mb.exact, mb.filt, mb.filt2, mb.tile_m, c->stream));
+        srt::DevMesh& d = c->h_desc[m];
+        d.filt = (const float4*)mb.filt; d.filt2 = (const float4*)mb.filt2; d.exact = (const float4*)mb.exact;
+        d.tile_m = mb.tile_m; d.n = mb.n; d.n_padded = mb.n_padded; d.mu = mb.mu;
+        d.contributes = (m == 0);                           // lbuffer.cxx:788: only meshes[0] adds path length
+        c->h_desc[nm + m] = d;
+        c->h_desc[nm + m].contributes = 1;
+        c->total_tris += mb.n;
     }
     c->mesh0_tris = c->meshes[0].n;
-    SRT_CUDA(c, cudaMalloc(&c->d_meshes, desc.size() * sizeof(srt::DevMesh)));
-    SRT_CUDA(c, cudaMalloc(&c->d_meshes_all, desc.size() * sizeof(srt::DevMesh)));
-    SRT_CUDA(c, cudaMemcpy(c->d_meshes, desc.data(), desc.size() * sizeof(srt::DevMesh), cudaMemcpyHostToDevice));
-    for (auto& d : desc) d.contributes = 1;
-    SRT_CUDA(c, cudaMemcpy(c->d_meshes_all, desc.data(), desc.size() * sizeof(srt::DevMesh), cudaMemcpyHostToDevice));
+    if (2 * nm > c->desc_cap) {
+        SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_meshes); c->d_meshes = nullptr;
+        SRT_CUDA(c, cudaMalloc(&c->d_meshes, 2 * nm * sizeof(srt::DevMesh))); c->desc_cap = 2 * nm;
+    }
+    SRT_CUDA(c, cudaMemcpyAsync(c->d_meshes, c->h_desc.data(), 2 * nm * sizeof(srt::DevMesh), cudaMemcpyHostToDevice, c->stream));
     c->packed = true;
     return SRT_OK;
 }
@@ -197,6 +212,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
 {
     if (!params) return fail(c, SRT_ERR_INVALID, "params is NULL");
     if (!dL) return fail(c, SRT_ERR_INVALID, "L buffer is NULL");
+    const bool repack = !c->packed;
     int rc = pack_scene(c);
     if (rc) return rc;
     const srt_camera& cam = c->camera;
@@ -212,8 +228,8 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     a.cam.xc = (float)(0.5 - (double)cam.width / 2.0); a.cam.yc = (float)(0.5 - (double)cam.height / 2.0);
     a.cam.W = cam.width; a.cam.H = cam.height;
     const bool all = (params->flags & SRT_FLAG_ALL_MESHES_CONTRIBUTE) != 0;
-    a.meshes = all ? c->d_meshes_all : c->d_meshes;
-    a.n_meshes = (int)c->meshes.size();
+    a.meshes = c->d_meshes + (all ? c->n_meshes : 0);
+    a.n_meshes = (int)c->n_meshes;
     a.row_begin = row_begin; a.row_end = row_end;
     a.incident = params->incident; a.length_to_cm = params->length_to_cm;
     a.L = dL; a.dist = d_dist; a.ssum = d_ssum; a.hits = d_hits;
@@ -236,7 +252,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     else SRT_CUDA(c, srt::launch_lbuffer_exact(a, audit, c->stream));
     SRT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     c->timing.kernel_used = kernel;
-    c->timing.launches = (row_end > row_begin) ? 1 : 0;
+    c->timing.launches = ((row_end > row_begin) ? 1 : 0) + (repack ? 1 + (uint32_t)c->n_meshes : 0);
     const uint64_t tris = all ? c->total_tris : c->mesh0_tris;
     c->timing.pair_tests = (uint64_t)(row_end - row_begin) * cam.width * tris;
     c->timing.exact_tests = 0; c->timing.filter_violations = 0;
@@ -396,18 +412,32 @@ int srt_set_meshes(srt_ctx* c, int n_meshes, const srt_mesh_desc* meshes)
 {
     if (!c) return SRT_ERR_INVALID;
     if (n_meshes <= 0 || !meshes) return fail(c, SRT_ERR_INVALID, "need at least one mesh");
-    std::vector<HostMesh> hm((size_t)n_meshes);
+    for (int m = 0; m < n_meshes; ++m)
+        if (meshes[m].n_triangles && !meshes[m].vertices)
+            return fail(c, SRT_ERR_INVALID, "mesh %d: vertices is NULL (buffer size error)", m);
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    if (c->meshes.size() < (size_t)n_meshes) c->meshes.resize((size_t)n_meshes);
+    c->packed = false;
+    c->n_meshes = 0;
     for (int m = 0; m < n_meshes; ++m) {
         const srt_mesh_desc& d = meshes[m];
-        if (d.n_triangles && !d.vertices) return fail(c, SRT_ERR_INVALID, "mesh %d: vertices is NULL (buffer size error)", m);
-        hm[m].n = d.n_triangles; hm[m].mu = d.mu;
-        hm[m].vertices.assign(d.vertices, d.vertices + 9 * (size_t)d.n_triangles);
-        hm[m].normals.resize(3 * (size_t)d.n_triangles);
-        if (d.normals) std::memcpy(hm[m].normals.data(), d.normals, hm[m].normals.size() * 4);
-        else srt_triangle_normals(hm[m].vertices.data(), d.n_triangles, hm[m].normals.data());
+        MeshBuf& mb = c->meshes[m];
+        int rc = ensure_mesh(c, mb, d.n_triangles, d.normals != nullptr);
+        if (rc) return rc;
+        mb.n = d.n_triangles;
+        mb.n_padded = (d.n_triangles + srt::kGroupTris - 1) / srt::kGroupTris * srt::kGroupTris;
+        mb.mu = d.mu;
+        mb.has_normals = d.normals != nullptr;
+        // pageable source: the runtime stages the data before returning, the caller's buffer is free again
+        if (d.n_triangles) {
+            SRT_CUDA(c, cudaMemcpyAsync(mb.d_vertices, d.vertices, (size_t)d.n_triangles * 9 * sizeof(float),
+                                        cudaMemcpyHostToDevice, c->stream));
+            if (d.normals)
+                SRT_CUDA(c, cudaMemcpyAsync(mb.d_normals, d.normals, (size_t)d.n_triangles * 3 * sizeof(float),
+                                            cudaMemcpyHostToDevice, c->stream));
+        }
     }
-    c->meshes.swap(hm);
-    c->packed = false;
+    c->n_meshes = (size_t)n_meshes;
     return SRT_OK;
 }
 
@@ -530,6 +560,24 @@ int srt_last_timing(srt_ctx* c, srt_timing* out)
         c->timing_pending = false; c->counters_pending = false;
     }
     *out = c->timing;
+    return SRT_OK;
+}
+
+// diagnostic: download the device-side packed arrays of one mesh (packs the scene first if needed)
+int srt_debug_download_packed(srt_ctx* c, int mesh, float* exact16, float* filt8, float* filt2_8, float* tile_m)
+{
+    if (!c) return SRT_ERR_INVALID;
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    int rc = pack_scene(c);
+    if (rc) return rc;
+    if (mesh < 0 || (size_t)mesh >= c->n_meshes) return fail(c, SRT_ERR_INVALID, "mesh index %d out of range", mesh);
+    const MeshBuf& mb = c->meshes[mesh];
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (exact16 && mb.n) SRT_CUDA(c, cudaMemcpy(exact16, mb.exact, (size_t)mb.n * sizeof(srt::ExactTri), cudaMemcpyDeviceToHost));
+    if (filt8 && mb.n_padded) SRT_CUDA(c, cudaMemcpy(filt8, mb.filt, (size_t)mb.n_padded * sizeof(srt::FilterTri), cudaMemcpyDeviceToHost));
+    if (filt2_8 && mb.n_padded) SRT_CUDA(c, cudaMemcpy(filt2_8, mb.filt2, (size_t)mb.n_padded * sizeof(srt::FilterTri2), cudaMemcpyDeviceToHost));
+    const size_t tiles = (mb.n_padded + srt::kTileTris - 1) / srt::kTileTris;
+    if (tile_m && tiles) SRT_CUDA(c, cudaMemcpy(tile_m, mb.tile_m, tiles * sizeof(float), cudaMemcpyDeviceToHost));
     return SRT_OK;
 }
 
