@@ -1,0 +1,127 @@
+// test_host_api.cpp -- checks of the C++ host classes (include/srt/*.h) against the reference's documented
+// behaviour.  `test_host_api cpu` needs no GPU; `test_host_api gpu <ply> <W> <H> <out.txt>` renders through
+// srt::renderLoop (CUDA) and writes the image with Image::saveTextFile.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "srt/PlyLoader.h"
+#include "srt/RenderLoop.h"
+
+static int failures = 0;
+#define CHECK(cond) do { if (!(cond)) { std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); ++failures; } } while (0)
+template <class E, class F> static bool throws(F f) { try { f(); } catch (const E&) { return true; } catch (...) { return false; } return false; }
+
+static int cpu_tests()
+{
+    using namespace srt;
+    // Vec3: float vs double overloads (Vec3.inl:205-233)
+    Vec3 a(1.0f, 2.0f, 3.0f), b(0.1f, 0.2f, 0.3f);
+    CHECK((a + b).getX() == 1.0f + 0.1f && (a - b).getZ() == 3.0f - 0.3f);
+    CHECK((b * 0.6).getX() == float(double(0.1f) * 0.6));
+    CHECK((b * 0.6f).getX() == 0.1f * 0.6f);
+    CHECK((b / 3.0).getY() == float(double(0.2f) / 3.0) && (b / 3.0f).getY() == 0.2f / 3.0f);
+    CHECK(a.dotProduct(b) == 1.0f * 0.1f + 2.0f * 0.2f + 3.0f * 0.3f);
+    CHECK(a.crossProduct(b).getX() == 2.0f * 0.3f - 3.0f * 0.2f);
+    CHECK(a[2] == 3.0f && throws<std::out_of_range>([&] { (void)a[3]; }));
+    Vec3 n(3, 4, 0); n.normalise();
+    CHECK(n.getX() == 3.0f / 5.0f && n.getY() == 4.0f / 5.0f && Vec3(3, 4, 0).getLength() == 5.0f);
+    CHECK(reflect(Vec3(1, -1, 0), Vec3(0, 1, 0)).getY() == 1.0f);
+    std::ostringstream os; os << Vec3(1, 2.5f, -3);
+    CHECK(os.str() == "1 2.5 -3");
+    // Triangle: cached unit normal, area
+    Triangle t(Vec3(0, 0, 0), Vec3(2, 0, 0), Vec3(0, 2, 0));
+    CHECK(t.getNormal().getZ() == 1.0f && t.getNormal().getX() == 0.0f && t.getArea() == 2.0f);
+    t.setVertices(Vec3(0, 0, 0), Vec3(0, 2, 0), Vec3(2, 0, 0));
+    CHECK(t.getNormal().getZ() == -1.0f);
+    // Ray: constructor renormalises, zero direction stays zero; intersect is two-sided and accepts negative t
+    Ray r(Vec3(0.5f, 0.5f, -1), Vec3(0, 0, 10));
+    CHECK(r.getDirection().getZ() == 1.0f);
+    CHECK(Ray(Vec3(), Vec3()).getDirection().getLength() == 0.0f);
+    float tt = 0;
+    CHECK(r.intersect(t, tt) && tt == 1.0f);
+    CHECK(Ray(Vec3(0.5f, 0.5f, 1), Vec3(0, 0, 1)).intersect(t, tt) && tt == -1.0f);
+    CHECK(!Ray(Vec3(3, 3, -1), Vec3(0, 0, 1)).intersect(t, tt));
+    CHECK(r.getPointAt(2.0f).getZ() == 1.0f);
+    // TriangleMesh: overloads, length errors, bbox, stubbed bbox test
+    std::vector<float> v = { 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 2 };
+    std::vector<unsigned int> idx = { 0, 1, 2, 0, 2, 3 };
+    TriangleMesh m(v, idx);
+    CHECK(m.getNumberOfTriangles() == 2 && m.getUpperBBoxCorner().getZ() == 2.0f && m.getLowerBBoxCorner().getX() == 0.0f);
+    CHECK(m.getTriangle(1).getP3().getZ() == 2.0f && m.intersectBBox(r));
+    CHECK(throws<std::length_error>([&] { TriangleMesh bad(std::vector<float>(10, 0.f)); }));
+    CHECK(throws<std::length_error>([&] { TriangleMesh bad(v, std::vector<unsigned int>{ 0, 1 }); }));
+    CHECK(throws<std::length_error>([&] { TriangleMesh bad(v, idx, std::vector<float>(3, 0.f)); }));
+    TriangleMesh soup(std::vector<float>{ 0, 0, 0, 1, 0, 0, 0, 1, 0 });
+    CHECK(soup.getNumberOfTriangles() == 1 && soup.flatVertices().size() == 9 && soup.flatNormals()[2] == 1.0f);
+    std::vector<float> tc = { 0, 1, 0, 1, 1, 0, 1, 0, 0, 0, 0, 0 };
+    TriangleMesh tex(v, idx, tc);
+    CHECK(tex.getTriangle(1).getTextCoord2().getX() == 1.0f && tex.getTriangle(1).getTextCoord3().getX() == 0.0f);
+    // Image: bounds checks, text format, LUT
+    Image img(3, 2, 80.0f);
+    img.setPixel(1, 0, 11.513f); img.setPixel(2, 1, 0.5f);
+    float px = 0; img.getPixel(1, 0, px);
+    CHECK(px == 11.513f && throws<std::out_of_range>([&] { img.setPixel(3, 0, 1.0f); }) &&
+          throws<std::out_of_range>([&] { img.getPixel(0, 2, px); }));
+    const std::string path = "/tmp/srt_test_image.txt";
+    img.saveTextFile(path);
+    { std::ifstream f(path); std::stringstream ss; ss << f.rdbuf(); CHECK(ss.str() == "80\t11.513\t80\n80\t80\t0.5"); }
+    Image copy = img; copy.setPixel(0, 0, 1.0f); img.getPixel(0, 0, px);
+    CHECK(px == 80.0f);                                                  // deep copy
+    const std::vector<unsigned char> lut = img.applyLUT(0.0f, 80.0f);
+    CHECK(lut.size() == 18 && lut[0] == 255 && lut[3] == (unsigned char)std::lround(255.0 * 11.513f / 80.0) && lut[15] == 2);
+    // host helpers of the C ABI through the C++ shim
+    std::vector<TriangleMesh> set = { m };
+    Vec3 lo, hi; getBBox(set, hi, lo);
+    CHECK(hi.getZ() == 2.0f && lo.getY() == 0.0f);
+    Image out;
+    RayTracerInfo info = initialiseRayTracing(set, hi, lo, 8, 8, out, 0.0f);
+    CHECK(out.getWidth() == 8 && info.up.getZ() == -1.0f && info.right.getY() == 1.0f && info.range.getZ() == 2.0f);
+    CHECK(info.detector_position.getX() > info.origin.getX());
+    // no GPU -> the renderer must fail loudly
+    int ndev = 0;
+    {
+        srt_ctx* c = nullptr;
+        const int rc = srt_create(&c, 0);
+        if (rc == SRT_OK) { srt_destroy(c); ndev = 1; }
+    }
+    if (!ndev) CHECK(throws<std::runtime_error>([&] { renderLoop(out, set, info); }));
+    std::printf(failures ? "%d FAILURES\n" : "OK\n", failures);
+    return failures ? 1 : 0;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc >= 2 && std::strcmp(argv[1], "cpu") == 0) return cpu_tests();
+    if (argc >= 6 && std::strcmp(argv[1], "gpu") == 0) {
+        try {
+            std::vector<srt::TriangleMesh> meshes;
+            srt::loadMeshes(argv[2], meshes);
+            const unsigned W = (unsigned)std::atoi(argv[3]), H = (unsigned)std::atoi(argv[4]);
+            srt::Vec3 lo, hi; srt::getBBox(meshes, hi, lo);
+            srt::Image image;
+            srt::RayTracerInfo info = srt::initialiseRayTracing(meshes, hi, lo, H, W, image, 0.0f);
+            srt::renderLoop(image, meshes, info);
+            image.saveTextFile(argv[5]);
+            std::printf("OK %zu triangles\n", meshes[0].getNumberOfTriangles());
+            return 0;
+        } catch (const std::exception& e) { std::printf("ERROR: %s\n", e.what()); return 1; }
+    }
+    if (argc >= 3 && std::strcmp(argv[1], "ply") == 0) {
+        try {
+            std::vector<srt::TriangleMesh> meshes;
+            srt::loadMeshes(argv[2], meshes);
+            const std::vector<float> v = meshes[0].flatVertices();
+            double sum = 0, wsum = 0;
+            for (size_t i = 0; i < v.size(); ++i) { sum += v[i]; wsum += v[i] * (double)((i % 97) + 1); }
+            std::printf("%zu %.17g %.17g\n", meshes[0].getNumberOfTriangles(), sum, wsum);
+            return 0;
+        } catch (const std::exception& e) { std::printf("ERROR: %s\n", e.what()); return 1; }
+    }
+    std::printf("usage: %s cpu | ply <file> | gpu <ply> <W> <H> <out.txt>\n", argv[0]);
+    return 2;
+}

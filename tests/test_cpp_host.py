@@ -1,0 +1,98 @@
+"""The C++ host side (include/srt/*.h, CLI driver): reference-compatible classes, PLY loader, and -- on a GPU --
+the drop-in renderLoop and the main-pthreads-lbuffer-compatible command line."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, load_golden
+
+BIN = ROOT / "simpleraytracing_b200" / "bin"
+
+
+@pytest.fixture(scope="module")
+def host_bins(srtlib):
+    subprocess.run(["make", "-C", str(ROOT / "simpleraytracing_b200" / "host")], check=True, stdout=subprocess.DEVNULL)
+    return BIN
+
+
+def write_ply(path, vertices, faces, binary=True):
+    v = np.asarray(vertices, "<f4"); f = np.asarray(faces, "<i4")
+    hdr = ("ply\nformat %s 1.0\ncomment test\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+           "element face %d\nproperty list uchar int vertex_indices\nend_header\n") % (
+               "binary_little_endian" if binary else "ascii", len(v), len(f))
+    with open(path, "wb") as fh:
+        fh.write(hdr.encode())
+        if binary:
+            fh.write(v.tobytes())
+            rec = np.zeros(len(f), dtype=[("n", "u1"), ("i", "<i4", 3)])
+            rec["n"] = 3; rec["i"] = f
+            fh.write(rec.tobytes())
+        else:
+            for p in v:
+                fh.write(("%.9g %.9g %.9g\n" % tuple(p)).encode())
+            for t in f:
+                fh.write(("3 %d %d %d\n" % tuple(t)).encode())
+
+
+def expected_sums(vertices, faces):
+    soup = np.asarray(vertices, np.float32)[np.asarray(faces).reshape(-1)].reshape(-1).astype(np.float64)
+    w = (np.arange(soup.size) % 97) + 1.0
+    return len(faces), soup.sum(), (soup * w).sum()
+
+
+def test_host_classes(host_bins):
+    r = subprocess.run([str(host_bins / "test_host_api"), "cpu"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("binary", [True, False])
+def test_ply_loader_matches_fixture(host_bins, tmp_path, binary):
+    d = np.load(GOLDEN / "dragon_mesh.npz")
+    v, f = d["vertices"], d["faces"]
+    if not binary:
+        v, f = v[:3000], f[(f < 3000).all(1)][:4000]
+    p = tmp_path / "mesh.ply"
+    write_ply(p, v, f, binary)
+    r = subprocess.run([str(host_bins / "test_host_api"), "ply", str(p)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    n, s, ws = r.stdout.split()
+    en, es, ews = expected_sums(v, f)
+    assert int(n) == en and float(s) == pytest.approx(es, rel=1e-12) and float(ws) == pytest.approx(ews, rel=1e-12)
+
+
+def test_ply_loader_skips_non_triangles_and_rejects_garbage(host_bins, tmp_path):
+    p = tmp_path / "quad.ply"
+    p.write_text("ply\nformat ascii 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\n"
+                 "element face 2\nproperty list uchar int vertex_indices\nend_header\n"
+                 "0 0 0\n1 0 0\n1 1 0\n0 1 0\n4 0 1 2 3\n3 0 1 2\n")
+    r = subprocess.run([str(host_bins / "test_host_api"), "ply", str(p)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split()[0] == "1"
+    bad = tmp_path / "bad.ply"; bad.write_text("not a ply\n")
+    r = subprocess.run([str(host_bins / "test_host_api"), "ply", str(bad)], capture_output=True, text=True)
+    assert r.returncode == 1 and "ERROR" in r.stdout
+    r = subprocess.run([str(host_bins / "test_host_api"), "ply", str(tmp_path / "missing.ply")], capture_output=True, text=True)
+    assert r.returncode == 1
+
+
+@pytest.mark.gpu
+def test_cli_and_render_loop_reproduce_the_reference_output(host_bins, tmp_path, oracle):
+    """srt_xray (flags of main-pthreads-lbuffer.cxx) and srt::renderLoop write the text image the reference would:
+    oracle repair of the reference-generated golden L-buffer, printed by Image::saveTextFile."""
+    d = np.load(GOLDEN / "dragon_mesh.npz")
+    write_ply(tmp_path / "dragon.ply", d["vertices"], d["faces"])
+    (tmp_path / "out").mkdir()
+    g = load_golden("lbuffer_dragon_128.npz")
+    want = tmp_path / "want.txt"
+    oracle.save_text(want, oracle.repair(g["L"], 128, 128), 128, 128)
+    r = subprocess.run([str(host_bins / "srt_xray"), "-s", "128", "128", "-t", "6", "-f", "cli.txt", "-i", "./dragon.ply"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "out" / "cli.txt").read_text() == want.read_text()
+    r = subprocess.run([str(host_bins / "test_host_api"), "gpu", str(tmp_path / "dragon.ply"), "128", "128",
+                        str(tmp_path / "loop.txt")], capture_output=True, text=True)
+    assert r.returncode == 0 and "22866 triangles" in r.stdout, r.stdout
+    assert (tmp_path / "loop.txt").read_text() == want.read_text()
+    # the classic flag errors keep their exit status
+    assert subprocess.run([str(host_bins / "srt_xray"), "--bogus"], capture_output=True).returncode != 0
