@@ -163,7 +163,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from simpleraytracing_b200 import Context, Library, scene
-    from simpleraytracing_b200.bands import BandLayout
+    from simpleraytracing_b200.bands import BandLayout, InterleavedLayout
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
@@ -194,21 +194,33 @@ def run_ours(args):
 
     lay = BandLayout(H, W, world, rank)
     frame = lay.new_frame(torch.float32, dev)
+    # N > 1: block-cyclic 16-row blocks (contiguous bands are unbalanced: rows through the dragon are slower)
+    il = InterleavedLayout(H, W, world, rank)
+    slots = il.new_slots(torch.float32, dev) if world > 1 else None
+    my_slot_ptr = il.my_slot(slots).data_ptr() if world > 1 else 0
+    my_rows = len(il.rows_of(rank)) if world > 1 else H
     image = torch.empty(H * W, dtype=torch.float32, device=dev)
     host_image = torch.empty(H * W, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
+    def render_and_assemble():
+        if world == 1:
+            ctx.render_lbuffer_device(params, lay.rows, frame.data_ptr())
+            return frame
+        ctx.render_lbuffer_interleaved_device(params, world, rank, my_slot_ptr)
+        il.all_gather_(slots)
+        ctx.deinterleave_device(world, slots.data_ptr(), frame.data_ptr())
+        return frame
+
     def step_device():
-        ctx.render_lbuffer_device(params, lay.rows, frame.data_ptr())
-        full = lay.all_gather_(frame)
+        full = render_and_assemble()
         ctx.repair_device(params, full.data_ptr(), image.data_ptr())
 
     def step_e2e():
         # the call a user of the reference makes: host meshes + camera in, host image out
         ctx.set_meshes(meshes)
         ctx.set_camera(cam)
-        ctx.render_lbuffer_device(params, lay.rows, frame.data_ptr())
-        full = lay.all_gather_(frame)
+        full = render_and_assemble()
         ctx.repair_device(params, full.data_ptr(), image.data_ptr())
         host_image.copy_(image, non_blocking=True)
         stream.synchronize()
@@ -256,7 +268,10 @@ def run_ours(args):
     kern_ms = []
     for _ in range(max(3, min(args.steps, 10))):
         flush.fill_(1)
-        ctx.render_lbuffer_device(params, lay.rows, frame.data_ptr())
+        if world == 1:
+            ctx.render_lbuffer_device(params, lay.rows, frame.data_ptr())
+        else:
+            ctx.render_lbuffer_interleaved_device(params, world, rank, my_slot_ptr)
         kern_ms.append(ctx.timing().render_ms)
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = timed(step_e2e, max(1, min(args.steps, 10)), max(1, min(args.warmup, 3)), sync_each=True)
@@ -266,7 +281,7 @@ def run_ours(args):
     value = tests_frame * args.steps / (total_ms * 1e-3)
     e2e_value = tests_frame * e2e_steps / (e2e_ms * 1e-3)
     kt = float(np.mean(kern_ms)) * 1e-3
-    band_tests = float(lay.rows[1] - lay.rows[0]) * W * ntri
+    band_tests = float(my_rows) * W * ntri
     achieved_tf = band_tests * F_ALG / kt / 1e12
     peak, peak_src = (peak_tf, "FFMA probe on this GPU (srt_debug_ffma_peak)") if peak_tf > 1 else \
         (NOMINAL_FP32_TFLOPS, "nominal 148 SM x 128 lanes x 2 x 1965 MHz")
@@ -286,11 +301,11 @@ def run_ours(args):
             "data": "dragon mesh fixture (reference dragon.ply, 22866 triangles); synthetic camera from its bbox",
             "config": {"workload": f"X-ray L-buffer {W}x{H} dragon, row bands over {world} GPU(s) (BASELINE configs[2])",
                        "triangles": ntri, "kernel": ctx.timing().kernel_used, "l2": "256 MiB flush write between steps",
-                       "step": "band render + all_gather + repair"},
+                       "step": "render (16-row blocks, block-cyclic over ranks) + all_gather + de-interleave + repair"},
             "e2e": {"value": e2e_value, "unit": "tests/s", "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(tri.nbytes + 4 * 16 + 4 * (W + H)) + 0,
                     "d2h_bytes_per_step": int(H * W * 4)},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": (2 if world == 1 else 3) * args.steps,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak, "traffic": None, "peak_source": peak_src,
                          "kernel": "lbuffer_filtered_kernel", "kernel_ms": kt * 1e3,

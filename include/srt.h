@@ -97,7 +97,7 @@ typedef struct {
     uint32_t repair_depth;      /* 4 (lbuffer.cxx:339)                                                */
     uint32_t kernel;            /* srt_kernel                                                         */
     uint32_t flags;
-    uint32_t pixels_per_thread; /* 0 = auto; tuning knob of the filtered kernel (1, 2, 4 or 8)        */
+    uint32_t pixels_per_thread; /* 0 = auto; tuning knob of the filtered kernel (1 ... 8)            */
 } srt_params;
 
 typedef struct {
@@ -153,6 +153,19 @@ int  srt_render_lbuffer(srt_ctx* ctx, const srt_params* params, uint32_t row_beg
  * Lets the caller run an in-place NCCL allgather over the bands. */
 int  srt_render_lbuffer_device(srt_ctx* ctx, const srt_params* params, uint32_t row_begin, uint32_t row_end,
                                float* dL, float* d_path_len, int32_t* d_sign_sum, uint32_t* d_hit_count);
+
+/*
+ * Load-balanced multi-GPU sharding.  Contiguous bands are unbalanced (rows through the object run the exact
+ * path far more often), so N ranks can instead take the 16-row blocks of the frame block-cyclically: rank
+ * `part` renders blocks part, part + n_parts, ... into a DENSE slot buffer of srt_interleave_slot_rows() rows
+ * (local row = (block / n_parts) * 16 + r).  After one all_gather of the slots ([n_parts][slot_rows][W]),
+ * srt_deinterleave_device scatters them back to image order.  Results are bit-identical to a single render.
+ */
+int  srt_interleave_slot_rows(uint32_t height, uint32_t n_parts, uint32_t* slot_rows);
+int  srt_render_lbuffer_interleaved_device(srt_ctx* ctx, const srt_params* params, uint32_t n_parts, uint32_t part,
+                                           float* d_slot_L, float* d_slot_path_len, int32_t* d_slot_sign_sum,
+                                           uint32_t* d_slot_hit_count);
+int  srt_deinterleave_device(srt_ctx* ctx, uint32_t n_parts, const float* d_slots, float* d_frame);
 
 /* Artefact repair + image fill over a full frame (lbuffer.cxx:329-404). L_in and image_out must not alias. */
 int  srt_repair(srt_ctx* ctx, const srt_params* params, const float* L_in, float* image_out);

@@ -50,3 +50,47 @@ class BandLayout:
             if i != self.rank and self.counts[i]:
                 out[self.starts[i] * W: (self.starts[i] + self.counts[i]) * W].copy_(slots[i][: self.counts[i] * W])
         return out
+
+
+class InterleavedLayout:
+    """Block-cyclic sharding of the frame's 16-row blocks over the ranks (load balance: rows through the object
+    take the exact path far more often than empty rows, so contiguous bands finish at very different times).
+
+    Rank r renders blocks r, r + world, ... into its dense slot (`slot_rows` rows, see srt_interleave_slot_rows);
+    one in-place all_gather of the slots leaves `slots[world][slot_rows][W]` on every rank; de-interleaving back
+    to image order is srt_deinterleave_device on the GPU (`deinterleave_torch` is the same mapping in torch for
+    the CPU tests of this host logic).
+    """
+    BLOCK = 16
+
+    def __init__(self, H, W, world, rank):
+        self.H, self.W, self.world, self.rank = H, W, world, rank
+        self.n_blocks = (H + self.BLOCK - 1) // self.BLOCK
+        self.slot_rows = ((self.n_blocks + world - 1) // world) * self.BLOCK
+
+    def new_slots(self, dtype, device):
+        return torch.zeros(self.world * self.slot_rows * self.W, dtype=dtype, device=device)
+
+    def my_slot(self, slots):
+        return slots.view(self.world, self.slot_rows * self.W)[self.rank]
+
+    def rows_of(self, rank):
+        """image rows rendered by `rank`, in slot order"""
+        rows = []
+        for b in range(rank, self.n_blocks, self.world):
+            rows.extend(range(b * self.BLOCK, min((b + 1) * self.BLOCK, self.H)))
+        return rows
+
+    def all_gather_(self, slots):
+        if self.world > 1:
+            dist.all_gather_into_tensor(slots, self.my_slot(slots))          # in place: send slot == my slot
+        return slots
+
+    def deinterleave_torch(self, slots):
+        out = torch.empty(self.H, self.W, dtype=slots.dtype, device=slots.device)
+        s = slots.view(self.world, self.slot_rows, self.W)
+        for r in range(self.world):
+            rows = self.rows_of(r)
+            if rows:
+                out[torch.tensor(rows)] = s[r, : len(rows)]
+        return out.view(-1)

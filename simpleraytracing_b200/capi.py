@@ -53,7 +53,8 @@ EXPORTS = [
     "srt_create", "srt_destroy", "srt_last_error", "srt_version", "srt_set_stream", "srt_synchronize",
     "srt_default_params", "srt_scene_bbox", "srt_camera_from_bbox", "srt_partition_rows", "srt_triangle_normals",
     "srt_set_meshes", "srt_set_camera", "srt_render_lbuffer", "srt_render_lbuffer_device", "srt_repair",
-    "srt_repair_device", "srt_render_xray", "srt_last_timing", "srt_debug_count_exact", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_tile_triangles", "srt_debug_download_packed",
+    "srt_repair_device", "srt_render_xray", "srt_interleave_slot_rows",
+    "srt_render_lbuffer_interleaved_device", "srt_deinterleave_device", "srt_last_timing", "srt_debug_count_exact", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_tile_triangles", "srt_debug_download_packed",
 ]
 
 
@@ -96,6 +97,9 @@ class Library:
         L.srt_set_camera.argtypes = [vp, C.POINTER(Camera)]
         L.srt_render_lbuffer.argtypes = [vp, C.POINTER(Params), u32, u32, vp, vp, vp, vp]
         L.srt_render_lbuffer_device.argtypes = [vp, C.POINTER(Params), u32, u32, vp, vp, vp, vp]
+        L.srt_interleave_slot_rows.argtypes = [u32, u32, C.POINTER(u32)]
+        L.srt_render_lbuffer_interleaved_device.argtypes = [vp, C.POINTER(Params), u32, u32, vp, vp, vp, vp]
+        L.srt_deinterleave_device.argtypes = [vp, u32, vp, vp]
         L.srt_repair.argtypes = [vp, C.POINTER(Params), vp, vp]
         L.srt_repair_device.argtypes = [vp, C.POINTER(Params), vp, vp]
         L.srt_render_xray.argtypes = [vp, C.POINTER(Params), vp]
@@ -148,6 +152,13 @@ class Library:
         if rc:
             raise SrtError(rc, "srt_partition_rows")
         return b.value, e.value
+
+    def interleave_slot_rows(self, H, n_parts):
+        v = C.c_uint32()
+        rc = self.lib.srt_interleave_slot_rows(H, n_parts, C.byref(v))
+        if rc:
+            raise SrtError(rc, "srt_interleave_slot_rows")
+        return v.value
 
     def triangle_normals(self, tri):
         tri = np.ascontiguousarray(tri, np.float32).reshape(-1, 9)
@@ -242,6 +253,14 @@ class Context:
         self._ck(self.lib.srt_render_lbuffer_device(self.h, C.byref(params), rows[0], rows[1], C.c_void_p(dL),
                                                     C.c_void_p(d_dist or None), C.c_void_p(d_ssum or None),
                                                     C.c_void_p(d_hits or None)))
+
+    def render_lbuffer_interleaved_device(self, params, n_parts, part, d_slot, d_dist=0, d_ssum=0, d_hits=0):
+        self._ck(self.lib.srt_render_lbuffer_interleaved_device(self.h, C.byref(params), n_parts, part, C.c_void_p(d_slot),
+                                                                C.c_void_p(d_dist or None), C.c_void_p(d_ssum or None),
+                                                                C.c_void_p(d_hits or None)))
+
+    def deinterleave_device(self, n_parts, d_slots, d_frame):
+        self._ck(self.lib.srt_deinterleave_device(self.h, n_parts, C.c_void_p(d_slots), C.c_void_p(d_frame)))
 
     def repair(self, params, L):
         L = np.ascontiguousarray(L, np.float32).reshape(-1)

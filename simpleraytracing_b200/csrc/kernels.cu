@@ -127,7 +127,9 @@ template <bool AUDIT>
 __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constant__ RenderArgs a)
 {
     const uint32_t col = blockIdx.x * 8 + (threadIdx.x & 7);
-    const uint32_t row = a.row_begin + blockIdx.y * 16 + (threadIdx.x >> 3);
+    const uint32_t lrow = threadIdx.x >> 3;
+    const uint32_t row = a.row_begin + (blockIdx.y * a.blk_stride + a.blk_phase) * 16 + lrow;
+    const uint32_t orow = a.compact ? blockIdx.y * 16 + lrow : row;      // output row (slot-local when compact)
     const uint32_t W = a.cam.W;
     if (col >= W || row >= a.row_end) return;
     const RayDirs r = make_ray(a.cam, row, col);
@@ -155,21 +157,23 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
                     const float Dd = fmaf(fa.w, x, fmaf(fb.x, y, fb.y));
                     const float X2 = fmaf(ga.x, x, fmaf(ga.y, y, ga.z));
                     const float X3 = fmaf(gb.x, x, fmaf(gb.y, y, gb.z));
-                    const bool reject = !(fabsf(Dd) - fabsf(X1) >= -tm) || (fabsf(X1) > fabsf(Dd) + fb.z) ||
-                                        (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);
+                    bool reject = !(fabsf(Dd) - fabsf(X1) >= -tm) || (fabsf(X1) > fabsf(Dd) + fb.z);   // level 0
+                    if (Dd > fb.z) reject = reject || (X1 < -fb.z) || (X2 < -ga.w) || (X3 < -gb.w);       // level 1
+                    else if (Dd < -fb.z) reject = reject || (X1 > fb.z) || (X2 > ga.w) || (X3 > gb.w);
+                    else reject = reject || (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);
                     if (reject && hit) ++n_viol;
                 }
             }
         }
         L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
         if (m == 0) {
-            const size_t p = (size_t)row * W + col;
+            const size_t p = (size_t)orow * W + col;
             if (a.dist) a.dist[p] = dist;
             if (a.ssum) a.ssum[p] = ssum;
             if (a.hits) a.hits[p] = hits;
         }
     }
-    a.L[(size_t)row * W + col] = L;
+    a.L[(size_t)orow * W + col] = L;
     if (AUDIT && a.counters && n_viol) atomicAdd(a.counters + 1, n_viol);
 }
 
@@ -196,7 +200,7 @@ struct SlowArgs {
 };
 
 template <int P>
-__device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const SlowArgs& s, uint32_t jj0,
+__device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const SlowArgs& s, uint32_t jj0, const float* rays,
                                                 float* dist, int* ssum, uint32_t* hits, unsigned long long& n_exact)
 {
 #pragma unroll 1
@@ -205,23 +209,31 @@ __device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const Slow
         if (jj >= s.n) break;                                          // padding entry
         const float4 fa = __ldg(s.filt + 2 * (size_t)jj), fb = __ldg(s.filt + 2 * (size_t)jj + 1);
         const float bs = fmaf(fa.y, s.y, fa.z), bd = fmaf(fb.x, s.y, fb.y);
+        const float m1 = fb.z;
         uint32_t mask = 0;
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             const float xk = (float)(s.col0 + k) + cam.xc;
             const float S = fmaf(fa.x, xk, bs), Dd = fmaf(fa.w, xk, bd);
-            if (!(fabsf(S) > fabsf(Dd) + fb.z)) mask |= 1u << k;       // per-triangle margin (NaN survives)
+            if (!(fabsf(S) > fabsf(Dd) + m1)) mask |= 1u << k;         // per-triangle margin (NaN survives)
         }
         if (!s.row_ok) mask = 0;
         if (mask == 0) continue;
+        // level 1: the conservative footprint of the triangle itself.  With X in {u, v, w = 1-u-v numerators}
+        // a hit needs X * sgn(det) >= -(rounding) for all three; where the sign of det is
+        // certain (|D| > m) that is three one-sided tests, elsewhere the two-sided strips |X| <= |D| + m.
         const float4 ga = __ldg(s.filt2 + 2 * (size_t)jj), gb = __ldg(s.filt2 + 2 * (size_t)jj + 1);
         const float b2 = fmaf(ga.y, s.y, ga.z), b3 = fmaf(gb.y, s.y, gb.z);
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             const float xk = (float)(s.col0 + k) + cam.xc;
-            const float Dd = fmaf(fa.w, xk, bd);
+            const float S = fmaf(fa.x, xk, bs), Dd = fmaf(fa.w, xk, bd);
             const float X2 = fmaf(ga.x, xk, b2), X3 = fmaf(gb.x, xk, b3);
-            if ((fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w)) mask &= ~(1u << k);
+            bool reject;
+            if (Dd > m1) reject = (S < -m1) || (X2 < -ga.w) || (X3 < -gb.w);
+            else if (Dd < -m1) reject = (S > m1) || (X2 > ga.w) || (X3 > gb.w);
+            else reject = (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);
+            if (reject) mask &= ~(1u << k);
         }
         if (mask == 0) continue;
         const float4 A = __ldg(s.exact + 4 * (size_t)jj), B = __ldg(s.exact + 4 * (size_t)jj + 1);
@@ -230,9 +242,10 @@ __device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const Slow
         while (mask) {
             const int k = __ffs(mask) - 1;
             mask &= mask - 1;
-            const uint32_t col = s.col0 + k;
-            if (col >= cam.W) break;
-            const RayDirs r = make_ray(cam, s.row, col);
+            if (s.col0 + k >= cam.W) break;
+            RayDirs r;                                                  // cached per-pixel ray (make_ray at kernel start)
+            r.ax = rays[6 * k]; r.ay = rays[6 * k + 1]; r.az = rays[6 * k + 2];
+            r.bx = rays[6 * k + 3]; r.by = rays[6 * k + 4]; r.bz = rays[6 * k + 5];
             float tt;
             ++n_exact;
             if (exact_intersect(r, A, B, C, Dn.x, tt)) accumulate_hit(r, Dn, tt, dist[k], ssum[k], hits[k]);
@@ -254,7 +267,9 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t col0 = (blockIdx.x * 8 + (warp & 1) * 4 + (lane & 3)) * P;
-    const uint32_t row = a.row_begin + blockIdx.y * 16 + (warp >> 1) * 8 + (lane >> 2);
+    const uint32_t lrow = (warp >> 1) * 8 + (lane >> 2);
+    const uint32_t row = a.row_begin + (blockIdx.y * a.blk_stride + a.blk_phase) * 16 + lrow;
+    const uint32_t orow = a.compact ? blockIdx.y * 16 + lrow : row;      // output row (slot-local when compact)
     const uint32_t W = a.cam.W;
     const bool row_ok = row < a.row_end;
 
@@ -273,6 +288,16 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
     float Lval[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) Lval[k] = a.incident;
+
+    // per-pixel ray directions, generated once with the reference's exact sequence; only the (rare)
+    // exact path reads them, with a dynamic index -> local memory
+    float rays[6 * P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+        RayDirs r = make_ray(a.cam, min(row, a.cam.H - 1), min(col0 + k, W - 1));
+        rays[6 * k] = r.ax; rays[6 * k + 1] = r.ay; rays[6 * k + 2] = r.az;
+        rays[6 * k + 3] = r.bx; rays[6 * k + 4] = r.by; rays[6 * k + 5] = r.bz;
+    }
 
     uint32_t issued = 0, consumed = 0;     // tiles issued / consumed by this CTA over all meshes
     unsigned long long n_exact = 0;
@@ -334,7 +359,7 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
                         acc1 = fmax3(acc1, fabsf(D1) - fabsf(S1), fabsf(D3) - fabsf(S3));
                     }
                     // resolve the PREVIOUS group now: its predicates have been ready for a whole iteration
-                    if (__any_sync(0xffffffffu, pend)) filtered_slow_path<P>(a.cam, sa, pend_j, dist, ssum, hits, n_exact);
+                    if (__any_sync(0xffffffffu, pend)) filtered_slow_path<P>(a.cam, sa, pend_j, rays, dist, ssum, hits, n_exact);
                     pend = fmaxf(acc0, acc1) >= negM;
                     pend_j = jbase + j;
                     a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
@@ -342,7 +367,7 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
                 __syncthreads();      // every warp is done with this stage before it is refilled
                 ++consumed;
             }
-            if (__any_sync(0xffffffffu, pend)) filtered_slow_path<P>(a.cam, sa, pend_j, dist, ssum, hits, n_exact);
+            if (__any_sync(0xffffffffu, pend)) filtered_slow_path<P>(a.cam, sa, pend_j, rays, dist, ssum, hits, n_exact);
         }
 
 #pragma unroll
@@ -351,7 +376,7 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
 #pragma unroll
             for (int k = 0; k < P; ++k) {
                 if (col0 + k < W) {
-                    const size_t p = (size_t)row * W + col0 + k;
+                    const size_t p = (size_t)orow * W + col0 + k;
                     if (a.dist) a.dist[p] = dist[k];
                     if (a.ssum) a.ssum[p] = ssum[k];
                     if (a.hits) a.hits[p] = hits[k];
@@ -361,8 +386,8 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
     }
 
     if (row_ok) {
-        float* out = a.L + (size_t)row * W + col0;
-        if (P >= 4 && (W & 3u) == 0 && col0 + P <= W) {
+        float* out = a.L + (size_t)orow * W + col0;
+        if (P % 4 == 0 && (W & 3u) == 0 && col0 + P <= W) {
 #pragma unroll
             for (int k = 0; k < P; k += 4)
                 *reinterpret_cast<float4*>(out + k) = make_float4(Lval[k], Lval[k + 1 < P ? k + 1 : k],
@@ -374,6 +399,25 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
         }
     }
     if (a.counters && n_exact) atomicAdd(a.counters, n_exact);
+}
+
+// ------------------------------------------------------------------ de-interleave
+// slots[part][local_row][col] with local_row = (block / n_parts) * 16 + r holds image row block * 16 + r of
+// block = local_block * n_parts + part.  float4 copies when W % 4 == 0.
+__global__ void __launch_bounds__(256) deinterleave_kernel(const float* __restrict__ slots, float* __restrict__ frame,
+                                                           uint32_t W, uint32_t H, uint32_t n_parts, uint32_t slot_rows)
+{
+    const uint32_t row = blockIdx.y;
+    const uint32_t blk = row >> 4, r = row & 15u;
+    const uint32_t part = blk % n_parts, lrow = (blk / n_parts) * 16 + r;
+    const float* src = slots + ((size_t)part * slot_rows + lrow) * W;
+    float* dst = frame + (size_t)row * W;
+    if ((W & 3u) == 0) {
+        for (uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) * 4; c < W; c += gridDim.x * blockDim.x * 4)
+            *reinterpret_cast<float4*>(dst + c) = *reinterpret_cast<const float4*>(src + c);
+    } else {
+        for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < W; c += gridDim.x * blockDim.x) dst[c] = src[c];
+    }
 }
 
 // ------------------------------------------------------------------ repair kernel
@@ -523,8 +567,8 @@ cudaError_t launch_ffma_peak(float* scratch, int blocks, int iters, cudaStream_t
 // ------------------------------------------------------------------ launchers
 cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
 {
-    if (a.row_end <= a.row_begin || a.cam.W == 0) return cudaSuccess;
-    dim3 grid((a.cam.W + 7) / 8, (a.row_end - a.row_begin + 15) / 16);
+    if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0) return cudaSuccess;
+    dim3 grid((a.cam.W + 7) / 8, a.n_blocks);
     if (audit) lbuffer_exact_kernel<true><<<grid, 128, 0, s>>>(a);
     else lbuffer_exact_kernel<false><<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
@@ -540,21 +584,34 @@ static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    dim3 grid((a.cam.W + 8 * P - 1) / (8 * P), (a.row_end - a.row_begin + 15) / 16);
+    dim3 grid((a.cam.W + 8 * P - 1) / (8 * P), a.n_blocks);
     lbuffer_filtered_kernel<P><<<grid, 128, smem, s>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s)
 {
-    if (a.row_end <= a.row_begin || a.cam.W == 0) return cudaSuccess;
+    if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0) return cudaSuccess;
     switch (ppt) {
         case 1: return launch_filtered_t<1>(a, s);
         case 2: return launch_filtered_t<2>(a, s);
+        case 3: return launch_filtered_t<3>(a, s);
         case 4: return launch_filtered_t<4>(a, s);
+        case 5: return launch_filtered_t<5>(a, s);
+        case 6: return launch_filtered_t<6>(a, s);
+        case 7: return launch_filtered_t<7>(a, s);
         case 8: return launch_filtered_t<8>(a, s);
         default: return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_deinterleave(const float* slots, float* frame, uint32_t W, uint32_t H, uint32_t n_parts,
+                                uint32_t slot_rows, cudaStream_t s)
+{
+    if (W == 0 || H == 0) return cudaSuccess;
+    dim3 grid((W / 4 + 255) / 256 ? (W / 4 + 255) / 256 : 1, H);
+    deinterleave_kernel<<<grid, 256, 0, s>>>(slots, frame, W, H, n_parts, slot_rows);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_repair(const float* L, float* image, uint32_t W, uint32_t H, uint32_t depth, cudaStream_t s)

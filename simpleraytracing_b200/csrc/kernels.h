@@ -39,6 +39,12 @@ struct RenderArgs {
     const DevMesh* meshes;   // device array
     int n_meshes;
     uint32_t row_begin, row_end;
+    // Row-block interleaving (multi-GPU load balance): CTA row-block `by` of the grid renders the image rows of
+    // block `by * blk_stride + blk_phase` (16 rows each, counted from row_begin).  blk_stride = 1, blk_phase = 0
+    // is a contiguous band.  compact != 0: outputs are addressed by the LOCAL row `by * 16 + r` (a dense slot
+    // buffer for the all_gather) instead of the image row.
+    uint32_t blk_stride, blk_phase, n_blocks;   // n_blocks = grid.y
+    int compact;
     float incident;          // 80.0f
     double length_to_cm;     // 0.1
     float* L;                // full-frame outputs (row*W + col); band rows written
@@ -53,6 +59,9 @@ struct RenderArgs {
 cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s);
 // Filtered kernel; ppt = pixels per thread (1, 2, 4, 8).
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s);
+// Scatter gathered slots [n_parts][slot_rows][W] (block-cyclic 16-row blocks) back to image order [H][W].
+cudaError_t launch_deinterleave(const float* slots, float* frame, uint32_t W, uint32_t H, uint32_t n_parts,
+                                uint32_t slot_rows, cudaStream_t s);
 // Artefact repair + image fill (lbuffer.cxx:329-404).
 cudaError_t launch_repair(const float* L, float* image, uint32_t W, uint32_t H, uint32_t depth, cudaStream_t s);
 

@@ -8,6 +8,7 @@
 // reference bit for bit).
 #include "srt.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -194,21 +195,33 @@ int pack_scene(srt_ctx* c)
     return SRT_OK;
 }
 
+// Pixels per thread for the filtered kernel.  A thread that owns more pixels amortises the per-triangle
+// coefficient loads over more tests (cost per test c(P), measured on B200: profiles/r01_band_sweep.txt), but a
+// launch with few CTAs must also divide evenly over the 148 SMs: the SM that hosts ceil(CTAs/148) of them sets
+// the time, and with fewer than 8 resident CTAs the SM's issue slots are not saturated (eff).
 int choose_ppt(const srt_ctx* c, const srt_params* p, uint32_t rows)
 {
-    if (p->pixels_per_thread == 1 || p->pixels_per_thread == 2 || p->pixels_per_thread == 4 || p->pixels_per_thread == 8)
-        return (int)p->pixels_per_thread;
-    // largest P that still gives every SM several CTAs (148 SMs; see DESIGN.md "grid sizing")
-    const uint64_t W = c->camera.width;
-    for (int P = 8; P > 1; P >>= 1) {
-        const uint64_t ctas = ((W + 8 * P - 1) / (8 * P)) * ((rows + 15) / 16);
-        if (ctas >= 148ull * 6) return P;
+    if (p->pixels_per_thread >= 1 && p->pixels_per_thread <= 8) return (int)p->pixels_per_thread;
+    static const double cost[9] = { 0, 3.17, 2.14, 2.30, 1.71, 1.21, 1.11, 1.03, 1.00 };   // per test, relative to P = 8
+    static const double eff[9] = { 0, 0.35, 0.60, 0.78, 0.88, 0.93, 0.96, 0.98, 1.00 };     // issue efficiency, k resident CTAs
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const double W = c->camera.width, blocks = (rows + 15) / 16;
+    int best = 8; double best_t = 1e300;
+    for (int P = 8; P >= 1; --P) {
+        const double ctas = std::ceil(W / (8.0 * P)) * blocks;
+        const double q = ctas / sms;
+        const int k = (int)std::ceil(q);
+        const double t = (q <= 8.0 ? k / eff[k < 1 ? 1 : k] : q * 1.02) * P * cost[P];
+        if (t < best_t * 0.999) { best_t = t; best = P; }
     }
-    return 1;
+    return best;
 }
 
+// parts == 0: contiguous band [row_begin, row_end) written at image positions.
+// parts >= 1: block-cyclic part `part` of `parts` over the whole frame, written compactly (slot layout).
 int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint32_t row_end,
-                  float* dL, float* d_dist, int32_t* d_ssum, uint32_t* d_hits)
+                  float* dL, float* d_dist, int32_t* d_ssum, uint32_t* d_hits, uint32_t parts = 0, uint32_t part = 0)
 {
     if (!params) return fail(c, SRT_ERR_INVALID, "params is NULL");
     if (!dL) return fail(c, SRT_ERR_INVALID, "L buffer is NULL");
@@ -231,6 +244,15 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     a.meshes = c->d_meshes + (all ? c->n_meshes : 0);
     a.n_meshes = (int)c->n_meshes;
     a.row_begin = row_begin; a.row_end = row_end;
+    const uint32_t total_blocks = (row_end - row_begin + 15) / 16;
+    uint32_t band_rows = row_end - row_begin;
+    if (parts == 0) { a.blk_stride = 1; a.blk_phase = 0; a.n_blocks = total_blocks; a.compact = 0; }
+    else {
+        a.blk_stride = parts; a.blk_phase = part; a.compact = 1;
+        a.n_blocks = total_blocks > part ? (total_blocks - part + parts - 1) / parts : 0;
+        band_rows = 0;
+        for (uint32_t b = part; b < total_blocks; b += parts) band_rows += std::min(16u, row_end - row_begin - b * 16);
+    }
     a.incident = params->incident; a.length_to_cm = params->length_to_cm;
     a.L = dL; a.dist = d_dist; a.ssum = d_ssum; a.hits = d_hits;
     a.counters = nullptr;
@@ -248,13 +270,13 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         return fail(c, SRT_ERR_INVALID, "unknown kernel selector %u", params->kernel);
 
     SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    if (kernel == SRT_KERNEL_FILTERED) SRT_CUDA(c, srt::launch_lbuffer_filtered(a, choose_ppt(c, params, row_end - row_begin), c->stream));
+    if (kernel == SRT_KERNEL_FILTERED) SRT_CUDA(c, srt::launch_lbuffer_filtered(a, choose_ppt(c, params, a.n_blocks * 16), c->stream));
     else SRT_CUDA(c, srt::launch_lbuffer_exact(a, audit, c->stream));
     SRT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     c->timing.kernel_used = kernel;
-    c->timing.launches = ((row_end > row_begin) ? 1 : 0) + (repack ? 1 + (uint32_t)c->n_meshes : 0);
+    c->timing.launches = ((band_rows > 0) ? 1 : 0) + (repack ? 1 + (uint32_t)c->n_meshes : 0);
     const uint64_t tris = all ? c->total_tris : c->mesh0_tris;
-    c->timing.pair_tests = (uint64_t)(row_end - row_begin) * cam.width * tris;
+    c->timing.pair_tests = (uint64_t)band_rows * cam.width * tris;
     c->timing.exact_tests = 0; c->timing.filter_violations = 0;
     c->counters_pending = a.counters != nullptr;
     c->timing_pending = true;
@@ -460,6 +482,36 @@ int srt_render_lbuffer_device(srt_ctx* c, const srt_params* p, uint32_t rb, uint
     if (!c) return SRT_ERR_INVALID;
     SRT_CUDA(c, cudaSetDevice(c->device));
     return render_device(c, p, rb, re, dL, dd, ds, dh);
+}
+
+int srt_interleave_slot_rows(uint32_t height, uint32_t n_parts, uint32_t* slot_rows)
+{
+    if (!slot_rows || n_parts == 0) return SRT_ERR_INVALID;
+    const uint32_t blocks = (height + 15) / 16;
+    *slot_rows = ((blocks + n_parts - 1) / n_parts) * 16;
+    return SRT_OK;
+}
+
+int srt_render_lbuffer_interleaved_device(srt_ctx* c, const srt_params* p, uint32_t n_parts, uint32_t part,
+                                          float* d_slot, float* dd, int32_t* ds, uint32_t* dh)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (n_parts == 0 || part >= n_parts) return fail(c, SRT_ERR_INVALID, "part %u of %u", part, n_parts);
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    return render_device(c, p, 0, c->camera.height, d_slot, dd, ds, dh, n_parts, part);
+}
+
+int srt_deinterleave_device(srt_ctx* c, uint32_t n_parts, const float* d_slots, float* d_frame)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (n_parts == 0 || !d_slots || !d_frame || d_slots == d_frame) return fail(c, SRT_ERR_INVALID, "bad deinterleave arguments");
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    uint32_t slot_rows = 0;
+    srt_interleave_slot_rows(c->camera.height, n_parts, &slot_rows);
+    SRT_CUDA(c, srt::launch_deinterleave(d_slots, d_frame, c->camera.width, c->camera.height, n_parts, slot_rows, c->stream));
+    return SRT_OK;
 }
 
 int srt_render_lbuffer(srt_ctx* c, const srt_params* p, uint32_t rb, uint32_t re,
