@@ -108,16 +108,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
+    uint32_t ok;
     asm volatile("{\n"
                  ".reg .pred p;\n"
-                 "WAIT_%=:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                 "@p bra DONE_%=;\n"
-                 "bra WAIT_%=;\n"
-                 "DONE_%=:\n"
-                 "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 "selp.u32 %0, 1, 0, p;\n"
+                 "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) { }
 }
 
 // ------------------------------------------------------------------ exact kernel
@@ -150,8 +155,8 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
                 const bool hit = exact_intersect(r, A, B, C, Dn.x, t);
                 if (hit) accumulate_hit(r, Dn, t, dist, ssum, hits);
                 if (AUDIT) {
-                    const float4 fa = __ldg(M.filt + 2 * (size_t)j), fb = __ldg(M.filt + 2 * (size_t)j + 1);
-                    const float4 ga = __ldg(M.filt2 + 2 * (size_t)j), gb = __ldg(M.filt2 + 2 * (size_t)j + 1);
+                    const float4 fa = __ldg(M.filt + 4 * (size_t)j), fb = __ldg(M.filt + 4 * (size_t)j + 1);
+                    const float4 ga = __ldg(M.filt + 4 * (size_t)j + 2), gb = __ldg(M.filt + 4 * (size_t)j + 3);
                     const float tm = __ldg(M.tile_m + j / kTileTris);
                     const float X1 = fmaf(fa.x, x, fmaf(fa.y, y, fa.z));
                     const float Dd = fmaf(fa.w, x, fmaf(fb.x, y, fb.y));
@@ -179,61 +184,71 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 
 // --------------------------------------------------------------- filtered kernel
 // P pixels (consecutive columns of one row) per thread; lanes 4 x 8 -> warp footprint 4P x 8;
-// 4 warps 2 x 2 -> CTA footprint 8P x 16.  Level-0 filter data is streamed through a
-// kStages-deep shared-memory ring with 1-D bulk copies (TMA) signalled on mbarriers; every
-// thread evaluates the affine strip test for its P pixels against each triangle of the tile.
-// Survivors (rare, spatially coherent) run level 1 and then the exact reference sequence.
+// 4 warps 2 x 2 -> CTA footprint 8P x 16.  The 64-byte filter records (level 0 + level 1) are
+// streamed through a kStages-deep shared-memory ring of kTileTris-triangle tiles with 1-D bulk
+// copies (TMA) signalled on "full" mbarriers; a warp releases a stage by arriving on its "empty"
+// mbarrier, so warps never wait for each other except through the ring (no __syncthreads in the
+// loop).  Every thread evaluates the level-0 strip test for its P pixels against each triangle;
+// survivors (rare, spatially coherent) run level 1 and then the exact reference sequence.
 //
-// Loop shape (driven by the ncu source view of the first version, profiles/r01_*):
-//  * the next group's coefficients are prefetched into registers while the current group is
+// Loop shape (driven by the ncu source views under profiles/):
+//  * the next group's level-0 coefficients are prefetched into registers while the current group is
 //    evaluated (no LDS latency on the critical path);
-//  * the vote on a group's survivors is taken one iteration later, when its FMNMX3 chain has
-//    long retired (no FMNMX3 -> FSETP -> VOTE -> BRA stall);
-//  * the slow path is an out-of-line function reading only global memory, so a pending group
-//    can be resolved after its shared-memory stage has been recycled.
+//  * the vote on a group's survivors is taken one iteration later, when its FMNMX3 chain has long
+//    retired (no FMNMX3 -> FSETP -> VOTE -> BRA stall); the last group of a tile is resolved before
+//    the stage is released, so the slow path can read its records from shared memory;
+//  * the slow path is an out-of-line function; it first applies the level-1 triangle-footprint test
+//    to the END POINTS of the thread's pixel run (edge functions are affine in x: outside the same
+//    edge at both ends => outside in between).  ~4 % of the groups reach the slow path, almost all
+//    only because a strip crosses the warp far away from the triangle; those leave after ~30
+//    instructions per triangle without touching global memory.
 // Triangle order per pixel is preserved: pending groups are resolved strictly in order.
 
 struct SlowArgs {
-    const float4* filt; const float4* filt2; const float4* exact;
+    const float4* exact;
     uint32_t n;                  // triangles in the mesh
     float y; uint32_t row, col0; int row_ok;
 };
 
 template <int P>
-__device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const SlowArgs& s, uint32_t jj0, const float* rays,
+__device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const SlowArgs& s, const float4* rec, uint32_t jj0,
                                                 float* dist, int* ssum, uint32_t* hits, unsigned long long& n_exact)
 {
+    const float xa = (float)s.col0 + cam.xc, xb = (float)(s.col0 + P - 1) + cam.xc;     // ends of the pixel run
 #pragma unroll 1
     for (uint32_t g = 0; g < kGroupTris; ++g) {
         const uint32_t jj = jj0 + g;                                   // triangle index in the mesh
         if (jj >= s.n) break;                                          // padding entry
-        const float4 fa = __ldg(s.filt + 2 * (size_t)jj), fb = __ldg(s.filt + 2 * (size_t)jj + 1);
+        const float4 fa = rec[4 * g], fb = rec[4 * g + 1], ga = rec[4 * g + 2], gb = rec[4 * g + 3];   // shared memory
         const float bs = fmaf(fa.y, s.y, fa.z), bd = fmaf(fb.x, s.y, fb.y);
-        const float m1 = fb.z;
+        const float b2 = fmaf(ga.y, s.y, ga.z), b3 = fmaf(gb.y, s.y, gb.z);
+        const float m1 = fb.z, m2 = ga.w, m3 = gb.w;
+        // --- run-level level-1 test.  With X in {u, v, w = 1-u-v numerators} a hit needs
+        // X * sgn(det) >= -(rounding) for all three.  X and D are affine in x: where the sign
+        // of D is certain at both ends of the run it is certain inside, and an edge function that is below
+        // -m at both ends is below it inside.
+        {
+            const float Da = fmaf(fa.w, xa, bd), Db = fmaf(fa.w, xb, bd);
+            const float Sa = fmaf(fa.x, xa, bs), Sb = fmaf(fa.x, xb, bs);
+            const float Ua = fmaf(ga.x, xa, b2), Ub = fmaf(ga.x, xb, b2);
+            const float Va = fmaf(gb.x, xa, b3), Vb = fmaf(gb.x, xb, b3);
+            bool out = !s.row_ok;
+            if (Da > m1 && Db > m1) out = out || (fmaxf(Sa, Sb) < -m1) || (fmaxf(Ua, Ub) < -m2) || (fmaxf(Va, Vb) < -m3);
+            else if (Da < -m1 && Db < -m1) out = out || (fminf(Sa, Sb) > m1) || (fminf(Ua, Ub) > m2) || (fminf(Va, Vb) > m3);
+            if (out) continue;
+        }
+        // --- per-pixel level 0 (per-triangle margin) and level 1
         uint32_t mask = 0;
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             const float xk = (float)(s.col0 + k) + cam.xc;
             const float S = fmaf(fa.x, xk, bs), Dd = fmaf(fa.w, xk, bd);
-            if (!(fabsf(S) > fabsf(Dd) + m1)) mask |= 1u << k;         // per-triangle margin (NaN survives)
-        }
-        if (!s.row_ok) mask = 0;
-        if (mask == 0) continue;
-        // level 1: the conservative footprint of the triangle itself.  With X in {u, v, w = 1-u-v numerators}
-        // a hit needs X * sgn(det) >= -(rounding) for all three; where the sign of det is
-        // certain (|D| > m) that is three one-sided tests, elsewhere the two-sided strips |X| <= |D| + m.
-        const float4 ga = __ldg(s.filt2 + 2 * (size_t)jj), gb = __ldg(s.filt2 + 2 * (size_t)jj + 1);
-        const float b2 = fmaf(ga.y, s.y, ga.z), b3 = fmaf(gb.y, s.y, gb.z);
-#pragma unroll
-        for (int k = 0; k < P; ++k) {
-            const float xk = (float)(s.col0 + k) + cam.xc;
-            const float S = fmaf(fa.x, xk, bs), Dd = fmaf(fa.w, xk, bd);
             const float X2 = fmaf(ga.x, xk, b2), X3 = fmaf(gb.x, xk, b3);
-            bool reject;
-            if (Dd > m1) reject = (S < -m1) || (X2 < -ga.w) || (X3 < -gb.w);
-            else if (Dd < -m1) reject = (S > m1) || (X2 > ga.w) || (X3 > gb.w);
-            else reject = (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);
-            if (reject) mask &= ~(1u << k);
+            bool reject = fabsf(S) > fabsf(Dd) + m1;                   // NaN compares false: survives
+            if (Dd > m1) reject = reject || (S < -m1) || (X2 < -m2) || (X3 < -m3);
+            else if (Dd < -m1) reject = reject || (S > m1) || (X2 > m2) || (X3 > m3);
+            else reject = reject || (fabsf(X2) > fabsf(Dd) + m2) || (fabsf(X3) > fabsf(Dd) + m3);
+            if (!reject) mask |= 1u << k;
         }
         if (mask == 0) continue;
         const float4 A = __ldg(s.exact + 4 * (size_t)jj), B = __ldg(s.exact + 4 * (size_t)jj + 1);
@@ -242,10 +257,9 @@ __device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const Slow
         while (mask) {
             const int k = __ffs(mask) - 1;
             mask &= mask - 1;
-            if (s.col0 + k >= cam.W) break;
-            RayDirs r;                                                  // cached per-pixel ray (make_ray at kernel start)
-            r.ax = rays[6 * k]; r.ay = rays[6 * k + 1]; r.az = rays[6 * k + 2];
-            r.bx = rays[6 * k + 3]; r.by = rays[6 * k + 4]; r.bz = rays[6 * k + 5];
+            const uint32_t col = s.col0 + k;
+            if (col >= cam.W) break;
+            const RayDirs r = make_ray(cam, s.row, col);
             float tt;
             ++n_exact;
             if (exact_intersect(r, A, B, C, Dn.x, tt)) accumulate_hit(r, Dn, tt, dist[k], ssum[k], hits[k]);
@@ -255,15 +269,16 @@ __device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const Slow
 
 template <int P>
 #ifndef SRT_MIN_CTAS
-#define SRT_MIN_CTAS 8
+#define SRT_MIN_CTAS 7
 #endif
 __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(const __grid_constant__ RenderArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* tiles = reinterpret_cast<float4*>(smem_raw);
-    // 64 B of slack after the last stage: the register prefetch of "the next group" may run one group
+    // 128 B of slack after the last stage: the register prefetch of "the next group" may run one group
     // past the end of a tile (the values are never used)
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileTris * 32 + 64);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileTris * 64 + 128);
+    uint64_t* empty = full + kStages;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t col0 = (blockIdx.x * 8 + (warp & 1) * 4 + (lane & 3)) * P;
@@ -280,7 +295,7 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
 
     if (tid == 0) {
 #pragma unroll
-        for (uint32_t s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -289,17 +304,7 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
 #pragma unroll
     for (int k = 0; k < P; ++k) Lval[k] = a.incident;
 
-    // per-pixel ray directions, generated once with the reference's exact sequence; only the (rare)
-    // exact path reads them, with a dynamic index -> local memory
-    float rays[6 * P];
-#pragma unroll
-    for (int k = 0; k < P; ++k) {
-        RayDirs r = make_ray(a.cam, min(row, a.cam.H - 1), min(col0 + k, W - 1));
-        rays[6 * k] = r.ax; rays[6 * k + 1] = r.ay; rays[6 * k + 2] = r.az;
-        rays[6 * k + 3] = r.bx; rays[6 * k + 4] = r.by; rays[6 * k + 5] = r.bz;
-    }
-
-    uint32_t issued = 0, consumed = 0;     // tiles issued / consumed by this CTA over all meshes
+    uint32_t issued = 0, consumed = 0;     // tiles issued / consumed by this CTA over all meshes (uniform)
     unsigned long long n_exact = 0;
 
     for (int m = 0; m < a.n_meshes; ++m) {
@@ -311,43 +316,46 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
 
         if (M.contributes && M.n > 0) {
             SlowArgs sa;
-            sa.filt = M.filt; sa.filt2 = M.filt2; sa.exact = M.exact; sa.n = M.n;
+            sa.exact = M.exact; sa.n = M.n;
             sa.y = y; sa.row = row; sa.col0 = col0; sa.row_ok = row_ok;
             const uint32_t n_tiles = (M.n_padded + kTileTris - 1) / kTileTris;
+            // producer side: wait until every warp released the stage, then one thread refills it
             auto issue = [&](uint32_t t) {
                 const uint32_t stage = issued % kStages;
                 const uint32_t cnt = min(kTileTris, M.n_padded - t * kTileTris);
+                // every thread waits (uniform control flow: a spin loop under `if (tid == 0)` would make the compiler
+                // treat the rest of the tile loop as divergent); the wait is for the tile consumed kStages - 1 tiles
+                // ago, so it only blocks a warp that ran a whole tile ahead of the slowest warp of the CTA
+                mbar_wait(&empty[stage], ((issued / kStages) & 1u) ^ 1u);           // first use passes immediately
                 if (tid == 0) {
-                    mbar_expect_tx(&full[stage], cnt * 32u);
-                    bulk_g2s(tiles + (size_t)stage * kTileTris * 2, M.filt + (size_t)t * kTileTris * 2, cnt * 32u,
+                    mbar_expect_tx(&full[stage], cnt * 64u);
+                    bulk_g2s(tiles + (size_t)stage * kTileTris * 4, M.filt + (size_t)t * kTileTris * 4, cnt * 64u,
                              &full[stage]);
                 }
                 ++issued;
             };
             for (uint32_t t = 0; t < min(kStages - 1, n_tiles); ++t) issue(t);
 
-            bool pend = false;             // may the previous group have a survivor in this lane?
-            uint32_t pend_j = 0;           // its first triangle index
-
             for (uint32_t t = 0; t < n_tiles; ++t) {
-                if (t + kStages - 1 < n_tiles) issue(t + kStages - 1);
+                __syncwarp();          // re-converge after the single-lane producer / release code
                 const uint32_t stage = consumed % kStages;
                 mbar_wait(&full[stage], (consumed / kStages) & 1u);
-                const float4* tp = tiles + (size_t)stage * kTileTris * 2;
+                const float4* tp = tiles + (size_t)stage * kTileTris * 4;
                 const uint32_t cnt = min(kTileTris, M.n_padded - t * kTileTris);    // multiple of kGroupTris
                 const float negM = -__ldg(M.tile_m + t);
                 const uint32_t jbase = t * kTileTris;
 
-                float4 a0 = tp[0], b0 = tp[1], a1 = tp[2], b1 = tp[3];
+                bool pend = false;             // may the previous group have a survivor in this lane?
+                float4 a0 = tp[0], b0 = tp[1], a1 = tp[4], b1 = tp[5];
 #pragma unroll 1
                 for (uint32_t j = 0; j < cnt; j += kGroupTris) {
-                    // prefetch the next group (after the last group this reads the slack / next stage: unused)
-                    const float4* np = tp + 2 * (j + kGroupTris);
-                    const float4 na0 = np[0], nb0 = np[1], na1 = np[2], nb1 = np[3];
+                    // prefetch the next group's level-0 coefficients (past the tile end: slack / next stage, unused)
+                    const float4* np = tp + 4 * (j + kGroupTris);
+                    const float4 na0 = np[0], nb0 = np[1], na1 = np[4], nb1 = np[5];
 
                     const float bs0 = fmaf(a0.y, y, a0.z), bd0 = fmaf(b0.x, y, b0.y);
                     const float bs1 = fmaf(a1.y, y, a1.z), bd1 = fmaf(b1.x, y, b1.y);
-                    float acc0 = -FLT_MAX, acc1 = -FLT_MAX;        // one survivor accumulator per triangle
+                    float acc0 = -FLT_MAX, acc1 = -FLT_MAX;
 #pragma unroll
                     for (int k = 0; k < P; k += 2) {
                         const int k1 = (k + 1 < P) ? k + 1 : k;
@@ -358,16 +366,20 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
                         acc0 = fmax3(acc0, fabsf(D0) - fabsf(S0), fabsf(D2) - fabsf(S2));
                         acc1 = fmax3(acc1, fabsf(D1) - fabsf(S1), fabsf(D3) - fabsf(S3));
                     }
-                    // resolve the PREVIOUS group now: its predicates have been ready for a whole iteration
-                    if (__any_sync(0xffffffffu, pend)) filtered_slow_path<P>(a.cam, sa, pend_j, rays, dist, ssum, hits, n_exact);
+                    // resolve the PREVIOUS group now: its predicate has been ready for a whole iteration
+                    if (__any_sync(0xffffffffu, pend))
+                        filtered_slow_path<P>(a.cam, sa, tp + 4 * (j - kGroupTris), jbase + j - kGroupTris, dist, ssum, hits, n_exact);
                     pend = fmaxf(acc0, acc1) >= negM;
-                    pend_j = jbase + j;
                     a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
                 }
-                __syncthreads();      // every warp is done with this stage before it is refilled
+                // last group of the tile, while its records are still in shared memory
+                if (__any_sync(0xffffffffu, pend))
+                    filtered_slow_path<P>(a.cam, sa, tp + 4 * (cnt - kGroupTris), jbase + cnt - kGroupTris, dist, ssum, hits, n_exact);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);        // this warp is done with the stage
                 ++consumed;
+                if (t + kStages - 1 < n_tiles) issue(t + kStages - 1);
             }
-            if (__any_sync(0xffffffffu, pend)) filtered_slow_path<P>(a.cam, sa, pend_j, rays, dist, ssum, hits, n_exact);
         }
 
 #pragma unroll
@@ -466,7 +478,7 @@ __global__ void __launch_bounds__(kTileTris) prepack_kernel(const float* __restr
                                                             const float* __restrict__ normals, uint32_t n,
                                                             uint32_t n_padded, float ox, float oy, float oz,
                                                             const __grid_constant__ FrameGeom g, ExactTri* exact,
-                                                            FilterTri* filt, FilterTri2* filt2, float* tile_m)
+                                                            float4* filt, float* tile_m)
 {
     __shared__ float red[kTileTris / 32];
     const uint32_t i = blockIdx.x * kTileTris + threadIdx.x;
@@ -483,18 +495,16 @@ __global__ void __launch_bounds__(kTileTris) prepack_kernel(const float* __restr
         float4* eo = reinterpret_cast<float4*>(exact + i);
         eo[0] = make_float4(E.e2x, E.e2y, E.e2z, E.e1x); eo[1] = make_float4(E.e1y, E.e1z, E.tx, E.ty);
         eo[2] = make_float4(E.tz, E.qx, E.qy, E.qz);     eo[3] = make_float4(E.e2q, E.nx, E.ny, E.nz);
-        float4* fo = reinterpret_cast<float4*>(filt + i);
+        float4* fo = filt + 4 * (size_t)i;
         fo[0] = make_float4(f.bx, f.gx, f.ax, f.bd); fo[1] = make_float4(f.gd, f.ad, f.m, f.pad);
-        float4* go = reinterpret_cast<float4*>(filt2 + i);
-        go[0] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2); go[1] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
+        fo[2] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2); fo[3] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
         m = f.m;
     } else if (i < n_padded) {
         FilterTri f; FilterTri2 f2;
         pack_padding(f, f2);
-        float4* fo = reinterpret_cast<float4*>(filt + i);
+        float4* fo = filt + 4 * (size_t)i;
         fo[0] = make_float4(f.bx, f.gx, f.ax, f.bd); fo[1] = make_float4(f.gd, f.ad, f.m, f.pad);
-        float4* go = reinterpret_cast<float4*>(filt2 + i);
-        go[0] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2); go[1] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
+        fo[2] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2); fo[3] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -540,13 +550,13 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, f
 } // namespace
 
 cudaError_t launch_prepack(const float* vertices, const float* normals, uint32_t n, uint32_t n_padded,
-                           const float origin[3], const FrameGeom& g, void* exact, void* filt, void* filt2,
+                           const float origin[3], const FrameGeom& g, void* exact, void* filt,
                            float* tile_m, cudaStream_t s)
 {
     const uint32_t tiles = (n_padded + kTileTris - 1) / kTileTris;
     if (tiles == 0) return cudaSuccess;
     prepack_kernel<<<tiles, kTileTris, 0, s>>>(vertices, normals, n, n_padded, origin[0], origin[1], origin[2], g,
-                                               (ExactTri*)exact, (FilterTri*)filt, (FilterTri2*)filt2, tile_m);
+                                               (ExactTri*)exact, (float4*)filt, tile_m);
     return cudaGetLastError();
 }
 
@@ -577,7 +587,7 @@ cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
 template <int P>
 static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
 {
-    const size_t smem = (size_t)kStages * kTileTris * 32 + 64 + kStages * sizeof(uint64_t);
+    const size_t smem = (size_t)kStages * kTileTris * 64 + 128 + 2 * kStages * sizeof(uint64_t);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(lbuffer_filtered_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

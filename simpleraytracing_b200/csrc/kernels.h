@@ -6,16 +6,18 @@
 namespace srt {
 
 #ifndef SRT_TILE_TRIS
-#define SRT_TILE_TRIS 256
+#define SRT_TILE_TRIS 128
 #endif
-constexpr uint32_t kTileTris  = SRT_TILE_TRIS;   // triangles per shared-memory tile of level-0 filter data (8 KB)
+constexpr uint32_t kTileTris  = SRT_TILE_TRIS;   // triangles per shared-memory tile of filter records (64 B each)
 constexpr uint32_t kGroupTris = 2;     // triangles per vote group in the filtered kernel
-constexpr uint32_t kStages    = 3;     // bulk-copy pipeline depth
+#ifndef SRT_STAGES
+#define SRT_STAGES 3
+#endif
+constexpr uint32_t kStages    = SRT_STAGES;     // bulk-copy pipeline depth
 
 // One mesh as the kernels see it (device pointers).
 struct DevMesh {
-    const float4* filt;      // 2 float4 per (padded) triangle   -- FilterTri
-    const float4* filt2;     // 2 float4 per (padded) triangle   -- FilterTri2
+    const float4* filt;      // 4 float4 per (padded) triangle: FilterTri (level 0) followed by FilterTri2 (level 1)
     const float4* exact;     // 4 float4 per triangle            -- ExactTri
     const float*  tile_m;    // level-0 margin per tile
     uint32_t n, n_padded;
@@ -68,7 +70,7 @@ cudaError_t launch_repair(const float* L, float* image, uint32_t W, uint32_t H, 
 // Scene pre-pack on the GPU (prepack_math.h): raw vertices -> ExactTri / FilterTri / FilterTri2 / tile margins.
 struct FrameGeom;
 cudaError_t launch_prepack(const float* vertices, const float* normals, uint32_t n, uint32_t n_padded,
-                           const float origin[3], const FrameGeom& g, void* exact, void* filt, void* filt2,
+                           const float origin[3], const FrameGeom& g, void* exact, void* filt,
                            float* tile_m, cudaStream_t s);
 // Detector offset tables u_off[W], v_off[H] (lbuffer.cxx:756-757).
 cudaError_t launch_offsets(float* u_off, float* v_off, uint32_t W, uint32_t H, float sp_u, float sp_v, cudaStream_t s);

@@ -34,7 +34,7 @@ thread_local std::string g_create_error;
 struct MeshBuf {
     float* d_vertices = nullptr;     // 9 per triangle
     float* d_normals = nullptr;      // 3 per triangle, only when the caller supplied normals
-    void* filt = nullptr; void* filt2 = nullptr; void* exact = nullptr; float* tile_m = nullptr;
+    void* filt = nullptr; void* exact = nullptr; float* tile_m = nullptr;   // filt: 64 B records (level 0 + level 1)
     size_t cap = 0;                  // capacity in triangles of all of the above
     uint32_t n = 0, n_padded = 0;
     bool has_normals = false;
@@ -90,7 +90,7 @@ int fail(srt_ctx* c, int code, const char* fmt, ...)
 
 void free_mesh(MeshBuf& m)
 {
-    cudaFree(m.d_vertices); cudaFree(m.d_normals); cudaFree(m.filt); cudaFree(m.filt2); cudaFree(m.exact); cudaFree(m.tile_m);
+    cudaFree(m.d_vertices); cudaFree(m.d_normals); cudaFree(m.filt); cudaFree(m.exact); cudaFree(m.tile_m);
     m = MeshBuf{};
 }
 
@@ -134,8 +134,7 @@ int ensure_mesh(srt_ctx* c, MeshBuf& m, size_t n, bool want_normals)
         free_mesh(m);
         const size_t cap = pad + pad / 8 + 64;
         SRT_CUDA(c, cudaMalloc(&m.d_vertices, cap * 9 * sizeof(float)));
-        SRT_CUDA(c, cudaMalloc(&m.filt, cap * sizeof(srt::FilterTri)));
-        SRT_CUDA(c, cudaMalloc(&m.filt2, cap * sizeof(srt::FilterTri2)));
+        SRT_CUDA(c, cudaMalloc(&m.filt, cap * (sizeof(srt::FilterTri) + sizeof(srt::FilterTri2))));
         SRT_CUDA(c, cudaMalloc(&m.exact, cap * sizeof(srt::ExactTri)));
         SRT_CUDA(c, cudaMalloc(&m.tile_m, (cap / srt::kTileTris + 2) * sizeof(float)));
         if (had_normals || want_normals) SRT_CUDA(c, cudaMalloc(&m.d_normals, cap * 3 * sizeof(float)));
@@ -175,9 +174,9 @@ int pack_scene(srt_ctx* c)
     for (size_t m = 0; m < nm; ++m) {
         MeshBuf& mb = c->meshes[m];
         SRT_CUDA(c, srt::launch_prepack(mb.d_vertices, mb.has_normals ? mb.d_normals : nullptr, mb.n, mb.n_padded,
-                                        cam.origin, g, mb.exact, mb.filt, mb.filt2, mb.tile_m, c->stream));
+                                        cam.origin, g, mb.exact, mb.filt, mb.tile_m, c->stream));
         srt::DevMesh& d = c->h_desc[m];
-        d.filt = (const float4*)mb.filt; d.filt2 = (const float4*)mb.filt2; d.exact = (const float4*)mb.exact;
+        d.filt = (const float4*)mb.filt; d.exact = (const float4*)mb.exact;
         d.tile_m = mb.tile_m; d.n = mb.n; d.n_padded = mb.n_padded; d.mu = mb.mu;
         d.contributes = (m == 0);                           // lbuffer.cxx:788: only meshes[0] adds path length
         c->h_desc[nm + m] = d;
@@ -626,8 +625,14 @@ int srt_debug_download_packed(srt_ctx* c, int mesh, float* exact16, float* filt8
     const MeshBuf& mb = c->meshes[mesh];
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (exact16 && mb.n) SRT_CUDA(c, cudaMemcpy(exact16, mb.exact, (size_t)mb.n * sizeof(srt::ExactTri), cudaMemcpyDeviceToHost));
-    if (filt8 && mb.n_padded) SRT_CUDA(c, cudaMemcpy(filt8, mb.filt, (size_t)mb.n_padded * sizeof(srt::FilterTri), cudaMemcpyDeviceToHost));
-    if (filt2_8 && mb.n_padded) SRT_CUDA(c, cudaMemcpy(filt2_8, mb.filt2, (size_t)mb.n_padded * sizeof(srt::FilterTri2), cudaMemcpyDeviceToHost));
+    if ((filt8 || filt2_8) && mb.n_padded) {
+        std::vector<float> rec((size_t)mb.n_padded * 16);            // device layout: 64 B records
+        SRT_CUDA(c, cudaMemcpy(rec.data(), mb.filt, rec.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < mb.n_padded; ++i) {
+            if (filt8) std::memcpy(filt8 + 8 * i, rec.data() + 16 * i, 8 * sizeof(float));
+            if (filt2_8) std::memcpy(filt2_8 + 8 * i, rec.data() + 16 * i + 8, 8 * sizeof(float));
+        }
+    }
     const size_t tiles = (mb.n_padded + srt::kTileTris - 1) / srt::kTileTris;
     if (tile_m && tiles) SRT_CUDA(c, cudaMemcpy(tile_m, mb.tile_m, tiles * sizeof(float), cudaMemcpyDeviceToHost));
     return SRT_OK;
