@@ -222,7 +222,8 @@ def run_ours(args):
         ctx.set_camera(cam)
         full = render_and_assemble()
         ctx.repair_device(params, full.data_ptr(), image.data_ptr())
-        host_image.copy_(image, non_blocking=True)
+        if rank == 0:                           # the result is needed on the host once
+            host_image.copy_(image, non_blocking=True)
         stream.synchronize()
 
     def barrier():

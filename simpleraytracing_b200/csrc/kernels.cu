@@ -267,11 +267,10 @@ __device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const Slow
     }
 }
 
-template <int P>
-#ifndef SRT_MIN_CTAS
-#define SRT_MIN_CTAS 7
-#endif
-__global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(const __grid_constant__ RenderArgs a)
+// MINB = resident CTAs per SM the register allocation is tuned for: 7 (72 registers) for grids that fill the GPU,
+// 5 (96 registers, fewer local-memory round trips) for small grids that cannot reach that occupancy anyway.
+template <int P, int MINB>
+__global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __grid_constant__ RenderArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* tiles = reinterpret_cast<float4*>(smem_raw);
@@ -357,14 +356,19 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
                     const float bs1 = fmaf(a1.y, y, a1.z), bd1 = fmaf(b1.x, y, b1.y);
                     float acc0 = -FLT_MAX, acc1 = -FLT_MAX;
 #pragma unroll
-                    for (int k = 0; k < P; k += 2) {
-                        const int k1 = (k + 1 < P) ? k + 1 : k;
+                    for (int k = 0; k + 1 < P; k += 2) {
                         const float S0 = fmaf(a0.x, x[k], bs0), D0 = fmaf(a0.w, x[k], bd0);
                         const float S1 = fmaf(a1.x, x[k], bs1), D1 = fmaf(a1.w, x[k], bd1);
-                        const float S2 = fmaf(a0.x, x[k1], bs0), D2 = fmaf(a0.w, x[k1], bd0);
-                        const float S3 = fmaf(a1.x, x[k1], bs1), D3 = fmaf(a1.w, x[k1], bd1);
+                        const float S2 = fmaf(a0.x, x[k + 1], bs0), D2 = fmaf(a0.w, x[k + 1], bd0);
+                        const float S3 = fmaf(a1.x, x[k + 1], bs1), D3 = fmaf(a1.w, x[k + 1], bd1);
                         acc0 = fmax3(acc0, fabsf(D0) - fabsf(S0), fabsf(D2) - fabsf(S2));
                         acc1 = fmax3(acc1, fabsf(D1) - fabsf(S1), fabsf(D3) - fabsf(S3));
+                    }
+                    if (P & 1) {                                       // odd P: the last pixel on its own
+                        const float S0 = fmaf(a0.x, x[P - 1], bs0), D0 = fmaf(a0.w, x[P - 1], bd0);
+                        const float S1 = fmaf(a1.x, x[P - 1], bs1), D1 = fmaf(a1.w, x[P - 1], bd1);
+                        acc0 = fmaxf(acc0, fabsf(D0) - fabsf(S0));
+                        acc1 = fmaxf(acc1, fabsf(D1) - fabsf(S1));
                     }
                     // resolve the PREVIOUS group now: its predicate has been ready for a whole iteration
                     if (__any_sync(0xffffffffu, pend))
@@ -584,19 +588,36 @@ cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
     return cudaGetLastError();
 }
 
+#ifndef SRT_MIN_CTAS
+#define SRT_MIN_CTAS 7
+#endif
+#ifndef SRT_MIN_CTAS_SMALL
+#define SRT_MIN_CTAS_SMALL 5
+#endif
+
+template <int P, int MINB>
+static cudaError_t launch_filtered_b(const RenderArgs& a, dim3 grid, size_t smem, cudaStream_t s)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(lbuffer_filtered_kernel<P, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    lbuffer_filtered_kernel<P, MINB><<<grid, 128, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 template <int P>
 static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
 {
     const size_t smem = (size_t)kStages * kTileTris * 64 + 128 + 2 * kStages * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(lbuffer_filtered_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
     dim3 grid((a.cam.W + 8 * P - 1) / (8 * P), a.n_blocks);
-    lbuffer_filtered_kernel<P><<<grid, 128, smem, s>>>(a);
-    return cudaGetLastError();
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool small = (size_t)grid.x * grid.y <= (size_t)SRT_MIN_CTAS_SMALL * sms;
+    return small ? launch_filtered_b<P, SRT_MIN_CTAS_SMALL>(a, grid, smem, s) : launch_filtered_b<P, SRT_MIN_CTAS>(a, grid, smem, s);
 }
 
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s)

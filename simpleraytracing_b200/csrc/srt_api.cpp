@@ -201,8 +201,8 @@ int pack_scene(srt_ctx* c)
 int choose_ppt(const srt_ctx* c, const srt_params* p, uint32_t rows)
 {
     if (p->pixels_per_thread >= 1 && p->pixels_per_thread <= 8) return (int)p->pixels_per_thread;
-    static const double cost[9] = { 0, 3.17, 2.14, 2.30, 1.71, 1.21, 1.11, 1.03, 1.00 };   // per test, relative to P = 8
-    static const double eff[9] = { 0, 0.35, 0.60, 0.78, 0.88, 0.93, 0.96, 0.98, 1.00 };     // issue efficiency, k resident CTAs
+    static const double cost[9] = { 0, 3.20, 1.96, 1.77, 1.47, 1.58, 1.51, 1.063, 1.00 };  // per test, relative to P = 8
+    static const double eff[9] = { 0, 0.35, 0.60, 0.78, 0.89, 0.91, 0.92, 0.93, 0.94 };     // issue efficiency, k resident CTAs
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     const double W = c->camera.width, blocks = (rows + 15) / 16;
