@@ -81,6 +81,14 @@ typedef struct {
     uint32_t width, height;
 } srt_camera;
 
+/* Light (include/Light.h:80-111); the shaded drivers use a white light at origin + up * 100.0
+ * (src/main-omp.cxx:235-238).  Only colour and position enter the shading (applyShading, :407-434). */
+typedef struct {
+    float colour[3];
+    float direction[3];
+    float position[3];
+} srt_light;
+
 typedef enum {
     SRT_KERNEL_AUTO = 0,        /* filtered kernel, falling back to exact when it cannot apply        */
     SRT_KERNEL_EXACT = 1,       /* every (ray, triangle) pair runs the reference op sequence          */
@@ -174,6 +182,22 @@ int  srt_repair_device(srt_ctx* ctx, const srt_params* params, const float* dL_i
 /* Whole frame in one call: L-buffer for all rows, repair, image to host
  * (what renderLoop + the output loop of main() produce; Image::getData layout). */
 int  srt_render_xray(srt_ctx* ctx, const srt_params* params, float* image_out);
+
+/* ---- shaded variant (src/main-omp.cxx:588-797; same loop in main-mpi*.cxx / main-pthreads-rows.cxx) ---- */
+/*
+ * Closest hit over ALL meshes (z-buffer, strict `>`, ascending triangle order, negative t accepted), Phong
+ * shading with the hit triangle's cached normal and its mesh's material, shadow ray against every other
+ * triangle (t > 1e-7 => colour * 0.25), area-barycentric nearest-texel lookup for textured meshes, clamp +
+ * int() truncation to 8 bits.  rgb_out: width*height*3 bytes, row-major; pixels without a hit get
+ * background_rgb (the reference's Image(width, height, r, g, b) initial colour).  The camera's
+ * pixel_spacing must be the one of the shaded drivers (from the bbox of all meshes, :594-607).
+ */
+int  srt_render_shaded(srt_ctx* ctx, const srt_params* params, const srt_light* light,
+                       const uint8_t background_rgb[3], uint8_t* rgb_out);
+int  srt_render_shaded_device(srt_ctx* ctx, const srt_params* params, const srt_light* light,
+                              const uint8_t background_rgb[3], uint8_t* d_rgb, uint8_t* d_shadow_or_null);
+/* Diagnostic: z-buffer and scene-wide triangle index per pixel of the last shaded render. */
+int  srt_debug_shaded_buffers(srt_ctx* ctx, float* z_out, int32_t* tri_id_out);
 
 /* Last-call timings and counters (waits for the last render on the stream to finish). */
 int  srt_last_timing(srt_ctx* ctx, srt_timing* out);

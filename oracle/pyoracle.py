@@ -30,6 +30,35 @@ class Camera(C.Structure):
         return np.array(getattr(self, name)[:], dtype=np.float32)
 
 
+class Material(C.Structure):
+    _fields_ = [("ambient", C.c_float * 3), ("diffuse", C.c_float * 3), ("specular", C.c_float * 3),
+                ("shininess", C.c_float)]
+
+
+def _shaded_args(meshes):
+    """meshes: list of dict(tri[n,9], texcoords[n,9] or None, material=(Ka, Kd, Ks, shininess), texture uint8[h,w,3] or None)"""
+    tri = np.ascontiguousarray(np.concatenate([np.asarray(m["tri"], np.float32).reshape(-1, 9) for m in meshes]))
+    have_tc = any(m.get("texcoords") is not None for m in meshes)
+    tc = None
+    if have_tc:
+        tc = np.ascontiguousarray(np.concatenate([
+            np.asarray(m["texcoords"], np.float32).reshape(-1, 9) if m.get("texcoords") is not None
+            else np.zeros((len(m["tri"]), 9), np.float32) for m in meshes]))
+    nt = np.array([len(m["tri"]) for m in meshes], np.uint32)
+    mats = (Material * len(meshes))()
+    texs = (C.c_void_p * len(meshes))()
+    tw = np.zeros(len(meshes), np.uint32); th = np.zeros(len(meshes), np.uint32)
+    keep = []
+    for i, m in enumerate(meshes):
+        ka, kd, ks, sh = m["material"]
+        mats[i].ambient[:] = ka; mats[i].diffuse[:] = kd; mats[i].specular[:] = ks; mats[i].shininess = sh
+        t = m.get("texture")
+        if t is not None:
+            t = np.ascontiguousarray(t, np.uint8); keep.append(t)
+            texs[i] = t.ctypes.data; th[i], tw[i] = t.shape[0], t.shape[1]
+    return tri, tc, nt, mats, texs, tw, th, keep
+
+
 def build(force=False):
     """Compile liboracle.so (and _ref/ when /root/reference is present)."""
     subprocess.run(["make", "-C", str(HERE), str(HERE / "liboracle.so")] + (["-B"] if force else []),
@@ -70,6 +99,9 @@ class Oracle:
                                          C.c_uint64, C.c_uint64, _f32p, C.c_void_p]
         L.oracle_save_text.argtypes = [C.c_char_p, _f32p, C.c_uint32, C.c_uint32]
         L.oracle_partition.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.oracle_render_shaded.argtypes = [_f32p, C.c_void_p, _u32p, C.c_int, C.POINTER(Material), C.c_void_p, _u32p, _u32p,
+                                           C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_filter_audit.argtypes = [_f32p, C.c_uint32, C.POINTER(Camera), C.c_uint32, C.c_uint32, _f32p, _f32p,
                                           _f32p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
 
@@ -129,6 +161,19 @@ class Oracle:
         if want_stages:
             out["stages"] = stages
         return out
+
+    def render_shaded(self, meshes, cam, W, H, background=(128, 128, 128), pixel_range=None, threads=None):
+        """-> dict(rgb uint8[H*W*3], z float32, tri_id int32, shadow uint8). cam = camera WITHOUT the background quad."""
+        tri, tc, nt, mats, texs, tw, th, keep = _shaded_args(meshes)
+        n = W * H
+        b, e = (0, n) if pixel_range is None else pixel_range
+        rgb = np.tile(np.array(background, np.uint8), n)
+        z = np.full(n, np.inf, np.float32); tid = np.full(n, -1, np.int32); sh = np.zeros(n, np.uint8)
+        self.lib.oracle_render_shaded(tri.reshape(-1), tc.ctypes.data_as(C.c_void_p) if tc is not None else None, nt, len(nt),
+                                      mats, C.cast(texs, C.c_void_p), tw, th, C.byref(cam), W, H, b, e,
+                                      threads or os.cpu_count() or 1, rgb.ctypes.data_as(C.c_void_p),
+                                      z.ctypes.data_as(C.c_void_p), tid.ctypes.data_as(C.c_void_p), sh.ctypes.data_as(C.c_void_p))
+        return dict(rgb=rgb, z=z, tri_id=tid, shadow=sh)
 
     def repair(self, L, W, H):
         img = np.empty(W * H, np.float32)
@@ -198,6 +243,24 @@ class Reference:
         L.ref_render_sort.argtypes = [_f32p, _u32p, C.c_int, C.POINTER(Camera), C.c_uint32, C.c_uint32,
                                       C.c_uint64, C.c_uint64, _f32p]
         L.ref_save_text.argtypes = [C.c_char_p, _f32p, C.c_uint32, C.c_uint32]
+        L.ref_render_shaded.argtypes = [_f32p, C.c_void_p, _u32p, C.c_int, C.POINTER(Material), C.c_void_p, _u32p, _u32p,
+                                        C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
+
+    def render_shaded(self, meshes, cam, W, H, background=(128, 128, 128), threads=None):
+        tri, tc, nt, mats, texs, tw, th, keep = _shaded_args(meshes)
+        n = W * H
+        rgb = np.tile(np.array(background, np.uint8), n)
+        threads = threads or os.cpu_count() or 1
+        cuts = np.linspace(0, n, threads + 1).astype(np.int64)
+
+        def job(i):
+            if cuts[i + 1] > cuts[i]:
+                self.lib.ref_render_shaded(tri.reshape(-1), tc.ctypes.data_as(C.c_void_p) if tc is not None else None, nt,
+                                           len(nt), mats, C.cast(texs, C.c_void_p), tw, th, C.byref(cam), W, H,
+                                           int(cuts[i]), int(cuts[i + 1]), rgb.ctypes.data_as(C.c_void_p))
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(job, range(threads)))
+        return rgb
 
     def camera(self, tri, mesh_ntris):
         tri = np.ascontiguousarray(tri, np.float32).reshape(-1)

@@ -31,6 +31,8 @@
 #include "Triangle.h"
 #include "TriangleMesh.h"
 #include "Image.h"
+#include "Material.h"
+#include "Light.h"
 
 /* ---- Image members normally supplied by src/Image.cxx -------------------- */
 Image::Image(const Image& o) : m_p_pixel_data(0), m_width(o.m_width), m_height(o.m_height)
@@ -302,6 +304,126 @@ int ref_render_sort(const float* tri, const uint32_t* ntris, int n_meshes, const
         distance = distance * 0.1;
         float photonOut = 80.000f * exp(-(0.3971f * distance));
         image[pixel] = photonOut;
+    }
+    return 0;
+}
+
+struct ref_material { float ambient[3], diffuse[3], specular[3]; float shininess; };
+
+namespace {
+/* applyShading, src/main-omp.cxx:407-434 -- expressions kept in the reference's form */
+Vec3 applyShading(const Light& aLight, const Material& aMaterial, const Vec3& aNormalVector, const Vec3& aPosition,
+                  const Vec3& aViewPosition)
+{
+    Vec3 ambient, diffuse, specular;
+    ambient = aLight.getColour() * aMaterial.getAmbient();
+    Vec3 lightDir = (aLight.getPosition() - aPosition);
+    lightDir.normalize();
+    float diff = std::max(std::abs(aNormalVector.dotProduct(lightDir)), 0.0f);
+    diffuse = aLight.getColour() * (diff * aMaterial.getDiffuse());
+    Vec3 viewDir(aViewPosition - aPosition);
+    viewDir.normalize();
+    Vec3 reflectDir = reflect(-viewDir, aNormalVector);
+    float spec = std::pow(std::max(dot(viewDir, reflectDir), 0.0f), aMaterial.getShininess());
+    specular = aLight.getColour() * (spec * aMaterial.getSpecular());
+    return ambient + diffuse + specular;
+}
+} // namespace
+
+/* src/main-omp.cxx:588-797 with the reference's classes; textures are raw RGB (the old RGB Image class,
+ * include/oldimage.h, does not build: it includes the wrong .inl). Single-threaded per call. */
+int ref_render_shaded(const float* tri, const float* texcoords, const uint32_t* ntris, int n_meshes,
+                      const ref_material* mats, const uint8_t* const* tex, const uint32_t* tex_w, const uint32_t* tex_h,
+                      const ref_camera* cam, uint32_t W, uint32_t H, uint64_t pixel_begin, uint64_t pixel_end, uint8_t* rgb)
+{
+    using namespace std;
+    vector<TriangleMesh> set;
+    size_t off = 0;
+    for (int m = 0; m < n_meshes; ++m) {
+        vector<float> v(tri + off, tri + off + 9 * (size_t)ntris[m]);
+        TriangleMesh mesh;
+        if (texcoords) { vector<float> tc(texcoords + off, texcoords + off + 9 * (size_t)ntris[m]); mesh.setGeometry(v, tc); }
+        else mesh.setGeometry(v);
+        mesh.setMaterial(Material(get(mats[m].ambient), get(mats[m].diffuse), get(mats[m].specular), mats[m].shininess));
+        set.push_back(mesh);
+        off += 9 * (size_t)ntris[m];
+    }
+    Vec3 aDetectorPosition = get(cam->detector), aRayOrigin = get(cam->origin), anUpVector = get(cam->up), aRightVector = get(cam->right);
+    Vec3 light_position = aRayOrigin + anUpVector * 100.0;
+    Light aLight(Vec3(1, 1, 1), Vec3(1, 0, 0), light_position);
+    Vec3 upper_bbox_corner, lower_bbox_corner;
+    getBBox(set, upper_bbox_corner, lower_bbox_corner);
+    Vec3 range = upper_bbox_corner - lower_bbox_corner;
+    float res1 = range[2] / W;
+    float res2 = range[1] / H;
+    float pixel_spacing[] = { 2 * std::max(res1, res2), 2 * std::max(res1, res2) };
+    float inf = std::numeric_limits<float>::infinity();
+    for (uint64_t pixel = pixel_begin; pixel < pixel_end; ++pixel) {
+        int row = pixel / W, col = pixel % W;
+        float v_offset = pixel_spacing[1] * (0.5 + row - H / 2.0);
+        float u_offset = pixel_spacing[0] * (0.5 + col - W / 2.0);
+        Vec3 direction = aDetectorPosition + anUpVector * v_offset + aRightVector * u_offset - aRayOrigin;
+        direction.normalise();
+        Ray ray(aRayOrigin, direction);
+        const TriangleMesh* p_intersected_object = 0;
+        const Triangle* p_intersected_triangle = 0;
+        int hit_mesh = -1;
+        float zb = inf;
+        for (size_t m = 0; m < set.size(); ++m)
+            for (unsigned int k = 0; k < set[m].getNumberOfTriangles(); ++k) {
+                const Triangle& triangle = set[m].getTriangle(k);
+                float t;
+                if (ray.intersect(triangle, t))
+                    if (zb > t) { zb = t; p_intersected_object = &set[m]; p_intersected_triangle = &triangle; hit_mesh = (int)m; }
+            }
+        if (p_intersected_object && p_intersected_triangle) {
+            float t = zb;
+            Vec3 point_hit = ray.getOrigin() + t * ray.getDirection();
+            Material material = p_intersected_object->getMaterial();
+            Vec3 colour = applyShading(aLight, material, p_intersected_triangle->getNormal(), point_hit, ray.getOrigin());
+            unsigned char r = 0, g = 0, b = 0;
+            Vec3 shadow_ray_direction = aLight.getPosition() - point_hit;
+            shadow_ray_direction.normalise();
+            Ray shadow_ray(point_hit, shadow_ray_direction);
+            bool is_point_in_shadow = false;
+            for (size_t m = 0; m < set.size(); ++m)
+                for (unsigned int k = 0; k < set[m].getNumberOfTriangles(); ++k) {
+                    const Triangle& triangle = set[m].getTriangle(k);
+                    if (&triangle != p_intersected_triangle) {
+                        float ts;
+                        bool intersection = shadow_ray.intersect(triangle, ts);
+                        if (intersection && ts > 0.0000001) { is_point_in_shadow = true; break; }
+                    }
+                }
+            if (is_point_in_shadow) { colour[0] *= 0.25; colour[1] *= 0.25; colour[2] *= 0.25; }
+            const uint8_t* texture = tex ? tex[hit_mesh] : 0;
+            unsigned int tw = texture ? tex_w[hit_mesh] : 0, th = texture ? tex_h[hit_mesh] : 0;
+            if (tw * th) {
+                Vec3 P = aRayOrigin + t * direction;
+                Vec3 A = p_intersected_triangle->getP1(), B = p_intersected_triangle->getP2(), C = p_intersected_triangle->getP3();
+                Triangle ABC(A, B, C), ABP(A, B, P), BCP(B, C, P), CAP(C, A, P);
+                float area_ABC = ABC.getArea();
+                float u = CAP.getArea() / area_ABC;
+                float v = ABP.getArea() / area_ABC;
+                float w = BCP.getArea() / area_ABC;
+                Vec3 texel_coord(w * p_intersected_triangle->getTextCoord1() + u * p_intersected_triangle->getTextCoord2() +
+                                 v * p_intersected_triangle->getTextCoord3());
+                unsigned int ti = texel_coord[0] * (tw - 1), tj = texel_coord[1] * (th - 1);
+                if (ti >= tw) ti = tw - 1;
+                if (tj >= th) tj = th - 1;
+                unsigned char texel_r = texture[(tj * (size_t)tw + ti) * 3], texel_g = texture[(tj * (size_t)tw + ti) * 3 + 1],
+                              texel_b = texture[(tj * (size_t)tw + ti) * 3 + 2];
+                colour[0] *= texel_r; colour[1] *= texel_g; colour[2] *= texel_b;
+                if (colour[0] < 0) r = 0; else if (colour[0] > 255) r = 255; else r = int(colour[0]);
+                if (colour[1] < 0) g = 0; else if (colour[1] > 255) g = 255; else g = int(colour[1]);
+                if (colour[2] < 0) b = 0; else if (colour[2] > 255) b = 255; else b = int(colour[2]);
+            } else {
+                if (255.0 * colour[0] < 0) r = 0; else if (255.0 * colour[0] > 255) r = 255; else r = int(255.0 * colour[0]);
+                if (255.0 * colour[1] < 0) g = 0; else if (255.0 * colour[1] > 255) g = 255; else g = int(255.0 * colour[1]);
+                if (255.0 * colour[2] < 0) b = 0; else if (255.0 * colour[2] > 255) b = 255; else b = int(255.0 * colour[2]);
+            }
+            rgb[pixel * 3] = r; rgb[pixel * 3 + 1] = g; rgb[pixel * 3 + 2] = b;
+        }
     }
     return 0;
 }

@@ -432,3 +432,165 @@ void oracle_partition(uint64_t total, uint32_t n, uint64_t* start, uint64_t* end
         end[i] = (uint64_t)e; last = e;
     }
 }
+
+/* ======================================================================== */
+/* Shaded variant: closest hit, Phong, shadow ray, texture */
+/* restated from src/main-omp.cxx (same loop in main-mpi*.cxx / pthreads-rows) */
+/* ======================================================================== */
+typedef struct {
+    float ambient[3], diffuse[3], specular[3];
+    float shininess;
+} oracle_material;
+
+typedef struct {
+    const float* tri; const float* texcoords; const uint32_t* mesh_ntris; int n_meshes;
+    const oracle_material* mats; const uint8_t* const* tex; const uint32_t* tex_w; const uint32_t* tex_h;
+    const oracle_camera* cam; float light_pos[3]; float light_col[3];
+    uint32_t W, H; float spacing; uint64_t p0, p1;
+    uint8_t* rgb; float* zbuf; int32_t* tri_id; uint8_t* shadow;
+    const float* normals; const uint64_t* mesh_first;
+} shade_job;
+
+static inline v3 v3_mul(v3 a, v3 b) { return v3_make(a.x * b.x, a.y * b.y, a.z * b.z); }     /* Vec3.inl:293-297 */
+static inline v3 v3_neg(v3 a) { return v3_make(-a.x, -a.y, -a.z); }
+/* reflect(I, N) = I - 2.0 * N.dotProduct(I) * N: the scalar is a double, the product narrows per component
+ * (Vec3.inl:120-124 with operator*(double, Vec3) -> Vec3::operator*(double)) */
+static inline v3 v3_reflect(v3 I, v3 N) { return v3_sub(I, v3_muld(N, 2.0 * (double)v3_dot(N, I))); }
+
+/* applyShading, src/main-omp.cxx:407-434 */
+static v3 apply_shading(v3 Lc, v3 Lpos, const oracle_material* m, v3 N, v3 P, v3 view_pos)
+{
+    v3 Ka = ld3(m->ambient), Kd = ld3(m->diffuse), Ks = ld3(m->specular);
+    v3 ambient = v3_mul(Lc, Ka);                                              /* :416 */
+    v3 lightDir = v3_normalise(v3_sub(Lpos, P));                              /* :419-420 */
+    float diff = fabsf(v3_dot(N, lightDir)); if (!(diff > 0.0f)) diff = (diff < 0.0f) ? 0.0f : diff;   /* max(|.|, 0) */
+    v3 diffuse = v3_mul(Lc, v3_mulf(Kd, diff));                               /* :422 */
+    v3 viewDir = v3_normalise(v3_sub(view_pos, P));                           /* :425-426 */
+    v3 reflectDir = v3_reflect(v3_neg(viewDir), N);                           /* :428 */
+    float d = v3_dot(viewDir, reflectDir);
+    float base = (0.0f < d) ? d : 0.0f;                                       /* std::max(d, 0.0f) = (a < b) ? b : a */
+    float spec = powf(base, m->shininess);                                    /* std::pow(float, float) :429 */
+    v3 specular = v3_mul(Lc, v3_mulf(Ks, spec));                              /* :430 */
+    return v3_add(v3_add(ambient, diffuse), specular);                        /* :432 */
+}
+
+static inline uint8_t clamp_trunc_f(float c) { if (c < 0) return 0; if (c > 255) return 255; return (uint8_t)(int)c; }
+static inline uint8_t clamp_trunc_d(double c) { if (c < 0) return 0; if (c > 255) return 255; return (uint8_t)(int)c; }
+
+/* renderLoop, src/main-omp.cxx:588-797, for pixels [p0, p1) */
+static void* shade_worker(void* arg)
+{
+    shade_job* j = (shade_job*)arg;
+    const oracle_camera* cam = j->cam;
+    const uint32_t W = j->W, H = j->H;
+    v3 detector = ld3(cam->detector), origin = ld3(cam->origin), up = ld3(cam->up), right = ld3(cam->right);
+    v3 Lc = ld3(j->light_col), Lpos = ld3(j->light_pos);
+    uint64_t total = 0; for (int m = 0; m < j->n_meshes; ++m) total += j->mesh_ntris[m];
+    for (uint64_t pixel = j->p0; pixel < j->p1; ++pixel) {
+        uint32_t row = (uint32_t)(pixel / W), col = (uint32_t)(pixel % W);
+        float v_offset = (float)((double)j->spacing * (0.5 + (double)row - (double)H / 2.0));     /* :620 */
+        float u_offset = (float)((double)j->spacing * (0.5 + (double)col - (double)W / 2.0));     /* :621 */
+        v3 direction = v3_sub(v3_add(v3_add(detector, v3_mulf(up, v_offset)), v3_mulf(right, u_offset)), origin);
+        direction = v3_normalise(direction);                                                       /* :625 */
+        v3 rdir = ray_ctor_direction(direction);                                                   /* :626 */
+        float z = INFINITY; int64_t hit_tri = -1; int hit_mesh = -1;
+        uint64_t g = 0;
+        for (int m = 0; m < j->n_meshes; ++m)                                                      /* :632 */
+            for (uint32_t k = 0; k < j->mesh_ntris[m]; ++k, ++g) {                                 /* :640 */
+                float t; int st;
+                if (ray_intersect(origin, rdir, ld3(j->tri + 9 * g), ld3(j->tri + 9 * g + 3), ld3(j->tri + 9 * g + 6), &t, &st))
+                    if (z > t) { z = t; hit_tri = (int64_t)g; hit_mesh = m; }                      /* :656-662: strict >, no t > 0 guard */
+            }
+        if (j->zbuf) j->zbuf[pixel] = z;
+        if (j->tri_id) j->tri_id[pixel] = (int32_t)hit_tri;
+        if (hit_tri < 0) continue;                                                                 /* background colour stays */
+        float t = z;
+        v3 point_hit = v3_add(origin, v3_mulf(rdir, t));                                           /* :671 */
+        v3 N = ld3(j->normals + 3 * hit_tri);
+        v3 colour = apply_shading(Lc, Lpos, &j->mats[hit_mesh], N, point_hit, origin);             /* :673 */
+        v3 sdir = v3_normalise(v3_sub(Lpos, point_hit));                                           /* :680-681 */
+        v3 srd = ray_ctor_direction(sdir);                                                         /* :682 */
+        int in_shadow = 0;
+        g = 0;
+        for (int m = 0; m < j->n_meshes; ++m) {                                                    /* :687 */
+            uint64_t g0 = g;
+            for (uint32_t k = 0; k < j->mesh_ntris[m]; ++k) {
+                uint64_t gi = g0 + k;
+                if ((int64_t)gi != hit_tri) {                                                      /* :698 */
+                    float ts; int st;
+                    if (ray_intersect(point_hit, srd, ld3(j->tri + 9 * gi), ld3(j->tri + 9 * gi + 3), ld3(j->tri + 9 * gi + 6), &ts, &st)
+                        && (double)ts > 0.0000001) { in_shadow = 1; break; }                       /* :703-707: inner break only */
+                }
+            }
+            g = g0 + j->mesh_ntris[m];
+        }
+        if (j->shadow) j->shadow[pixel] = (uint8_t)in_shadow;
+        if (in_shadow) {                                                                           /* :715-720 */
+            colour.x = (float)((double)colour.x * 0.25); colour.y = (float)((double)colour.y * 0.25);
+            colour.z = (float)((double)colour.z * 0.25);
+        }
+        uint8_t r, gg, b;
+        const uint8_t* tex = j->tex ? j->tex[hit_mesh] : NULL;
+        uint32_t tw = tex ? j->tex_w[hit_mesh] : 0, th = tex ? j->tex_h[hit_mesh] : 0;
+        if (tex && tw * th) {                                                                      /* :725 */
+            v3 P = v3_add(origin, v3_mulf(direction, t));                                          /* :729: the pre-Ray direction */
+            v3 A = ld3(j->tri + 9 * hit_tri), B = ld3(j->tri + 9 * hit_tri + 3), C = ld3(j->tri + 9 * hit_tri + 6);
+            float area_ABC = tri_area(A, B, C);
+            float u = tri_area(C, A, P) / area_ABC;                                                /* :742-745 */
+            float v = tri_area(A, B, P) / area_ABC;
+            float w = tri_area(B, C, P) / area_ABC;
+            const float* tc = j->texcoords + 9 * hit_tri;
+            v3 texel = v3_add(v3_add(v3_mulf(ld3(tc), w), v3_mulf(ld3(tc + 3), u)), v3_mulf(ld3(tc + 6), v));   /* :748 */
+            uint32_t ti = (uint32_t)(texel.x * (float)(tw - 1)), tj = (uint32_t)(texel.y * (float)(th - 1));     /* :755-756 */
+            if (ti >= tw) ti = tw - 1;      /* the reference would throw std::out_of_range here */
+            if (tj >= th) tj = th - 1;
+            const uint8_t* px = tex + ((size_t)tj * tw + ti) * 3;
+            colour.x *= (float)px[0]; colour.y *= (float)px[1]; colour.z *= (float)px[2];          /* :758-760 */
+            r = clamp_trunc_f(colour.x); gg = clamp_trunc_f(colour.y); b = clamp_trunc_f(colour.z);
+        } else {                                                                                   /* :776-790 */
+            r = clamp_trunc_d(255.0 * (double)colour.x); gg = clamp_trunc_d(255.0 * (double)colour.y);
+            b = clamp_trunc_d(255.0 * (double)colour.z);
+        }
+        j->rgb[pixel * 3] = r; j->rgb[pixel * 3 + 1] = gg; j->rgb[pixel * 3 + 2] = b;              /* :793 */
+    }
+    return 0;
+}
+
+/*
+ * Shaded render of pixels [pixel_begin, pixel_end).  cam = camera of the scene WITHOUT the background quad
+ * (main-omp.cxx:220-241 run before createBackground is appended, :249); the pixel spacing is recomputed inside
+ * from the bbox of ALL meshes (:594-607).  Light: white, at origin + up * 100.0 (:235).  rgb must be pre-filled
+ * with the background colour.  zbuf / tri_id / shadow are optional per-pixel debug outputs.
+ */
+int oracle_render_shaded(const float* tri, const float* texcoords, const uint32_t* mesh_ntris, int n_meshes,
+                         const oracle_material* mats, const uint8_t* const* tex, const uint32_t* tex_w, const uint32_t* tex_h,
+                         const oracle_camera* cam, uint32_t W, uint32_t H, uint64_t pixel_begin, uint64_t pixel_end,
+                         int n_threads, uint8_t* rgb, float* zbuf, int32_t* tri_id, uint8_t* shadow)
+{
+    if (n_threads < 1) n_threads = 1;
+    uint64_t total = 0; for (int m = 0; m < n_meshes; ++m) total += mesh_ntris[m];
+    float* normals = (float*)malloc(sizeof(float) * 3 * (total ? total : 1));
+    for (uint64_t k = 0; k < total; ++k) oracle_triangle_normal(tri + 9 * k, normals + 3 * k);
+    float lo[3], hi[3];
+    oracle_bbox(tri, total, lo, hi);                                     /* getBBox over all meshes, :594 */
+    float res1 = (hi[2] - lo[2]) / (float)W, res2 = (hi[1] - lo[1]) / (float)H;     /* :601-602 */
+    float spacing = 2 * ((res1 < res2) ? res2 : res1);                   /* :603 */
+    v3 lp = v3_add(ld3(cam->origin), v3_muld(ld3(cam->up), 100.0));      /* :235 */
+    shade_job* jobs = (shade_job*)calloc((size_t)n_threads, sizeof(shade_job));
+    pthread_t* tid = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
+    uint64_t n = pixel_end - pixel_begin;
+    for (int i = 0; i < n_threads; ++i) {
+        shade_job* j = &jobs[i];
+        j->tri = tri; j->texcoords = texcoords; j->mesh_ntris = mesh_ntris; j->n_meshes = n_meshes; j->mats = mats;
+        j->tex = tex; j->tex_w = tex_w; j->tex_h = tex_h; j->cam = cam; st3(j->light_pos, lp);
+        j->light_col[0] = j->light_col[1] = j->light_col[2] = 1.0f;
+        j->W = W; j->H = H; j->spacing = spacing; j->rgb = rgb; j->zbuf = zbuf; j->tri_id = tri_id; j->shadow = shadow;
+        j->normals = normals;
+        j->p0 = pixel_begin + n * (uint64_t)i / (uint64_t)n_threads;
+        j->p1 = pixel_begin + n * (uint64_t)(i + 1) / (uint64_t)n_threads;
+        pthread_create(&tid[i], NULL, shade_worker, j);
+    }
+    for (int i = 0; i < n_threads; ++i) pthread_join(tid[i], NULL);
+    free(jobs); free(tid); free(normals);
+    return 0;
+}

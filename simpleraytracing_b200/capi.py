@@ -37,6 +37,10 @@ class Camera(C.Structure):
         return np.array(getattr(self, name)[:], dtype=np.float32)
 
 
+class Light(C.Structure):
+    _fields_ = [("colour", C.c_float * 3), ("direction", C.c_float * 3), ("position", C.c_float * 3)]
+
+
 class Params(C.Structure):
     _fields_ = [("incident", C.c_float), ("length_to_cm", C.c_double), ("repair_depth", C.c_uint32),
                 ("kernel", C.c_uint32), ("flags", C.c_uint32), ("pixels_per_thread", C.c_uint32)]
@@ -54,7 +58,8 @@ EXPORTS = [
     "srt_default_params", "srt_scene_bbox", "srt_camera_from_bbox", "srt_partition_rows", "srt_triangle_normals",
     "srt_set_meshes", "srt_set_camera", "srt_render_lbuffer", "srt_render_lbuffer_device", "srt_repair",
     "srt_repair_device", "srt_render_xray", "srt_interleave_slot_rows",
-    "srt_render_lbuffer_interleaved_device", "srt_deinterleave_device", "srt_last_timing", "srt_debug_count_exact", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_tile_triangles", "srt_debug_download_packed",
+    "srt_render_lbuffer_interleaved_device", "srt_deinterleave_device", "srt_render_shaded",
+    "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_tile_triangles", "srt_debug_download_packed",
 ]
 
 
@@ -100,6 +105,9 @@ class Library:
         L.srt_interleave_slot_rows.argtypes = [u32, u32, C.POINTER(u32)]
         L.srt_render_lbuffer_interleaved_device.argtypes = [vp, C.POINTER(Params), u32, u32, vp, vp, vp, vp]
         L.srt_deinterleave_device.argtypes = [vp, u32, vp, vp]
+        L.srt_render_shaded.argtypes = [vp, C.POINTER(Params), C.POINTER(Light), vp, vp]
+        L.srt_render_shaded_device.argtypes = [vp, C.POINTER(Params), C.POINTER(Light), vp, vp, vp]
+        L.srt_debug_shaded_buffers.argtypes = [vp, vp, vp]
         L.srt_repair.argtypes = [vp, C.POINTER(Params), vp, vp]
         L.srt_repair_device.argtypes = [vp, C.POINTER(Params), vp, vp]
         L.srt_render_xray.argtypes = [vp, C.POINTER(Params), vp]
@@ -119,15 +127,27 @@ class Library:
 
     @staticmethod
     def mesh_descs(meshes):
-        """meshes: list of (tri[n,9] float32, mu). Returns (ctypes array, keepalive)."""
+        """meshes: list of (tri[n,9] float32, mu) or of dicts(tri, mu, texcoords, material=(Ka, Kd, Ks, shininess),
+        texture uint8[h, w, 3]). Returns (ctypes array, keepalive)."""
         arr = (MeshDesc * len(meshes))()
         keep = []
-        for i, (tri, mu) in enumerate(meshes):
-            tri = np.ascontiguousarray(tri, np.float32).reshape(-1, 9)
+        for i, m in enumerate(meshes):
+            if not isinstance(m, dict):
+                m = dict(tri=m[0], mu=m[1])
+            tri = np.ascontiguousarray(m["tri"], np.float32).reshape(-1, 9)
             keep.append(tri)
             arr[i].vertices = tri.ctypes.data if len(tri) else None
             arr[i].n_triangles = len(tri)
-            arr[i].mu = mu
+            arr[i].mu = m.get("mu", 0.0)
+            if m.get("texcoords") is not None:
+                tc = np.ascontiguousarray(m["texcoords"], np.float32).reshape(-1, 9); keep.append(tc)
+                arr[i].texcoords = tc.ctypes.data
+            ka, kd, ks, sh = m.get("material", ((1, 1, 1), (1, 1, 1), (1, 1, 1), 1.0))
+            arr[i].material.ambient[:] = ka; arr[i].material.diffuse[:] = kd; arr[i].material.specular[:] = ks
+            arr[i].material.shininess = sh
+            if m.get("texture") is not None:
+                t = np.ascontiguousarray(m["texture"], np.uint8); keep.append(t)
+                arr[i].texture_rgb = t.ctypes.data; arr[i].tex_h, arr[i].tex_w = t.shape[0], t.shape[1]
         return arr, keep
 
     def scene_bbox(self, meshes):
@@ -261,6 +281,21 @@ class Context:
 
     def deinterleave_device(self, n_parts, d_slots, d_frame):
         self._ck(self.lib.srt_deinterleave_device(self.h, n_parts, C.c_void_p(d_slots), C.c_void_p(d_frame)))
+
+    def render_shaded(self, params, light_position, background=(128, 128, 128), light_colour=(1.0, 1.0, 1.0)):
+        """-> uint8 [H*W*3]"""
+        n = self.cam.width * self.cam.height
+        rgb = np.empty(n * 3, np.uint8)
+        lt = Light(); lt.colour[:] = light_colour; lt.position[:] = [float(v) for v in light_position]
+        bg = np.array(background, np.uint8)
+        self._ck(self.lib.srt_render_shaded(self.h, C.byref(params), C.byref(lt), _ptr(bg, np.uint8), _ptr(rgb, np.uint8)))
+        return rgb
+
+    def shaded_buffers(self):
+        n = self.cam.width * self.cam.height
+        z = np.empty(n, np.float32); tid = np.empty(n, np.int32)
+        self._ck(self.lib.srt_debug_shaded_buffers(self.h, _ptr(z, np.float32), _ptr(tid, np.int32)))
+        return z, tid
 
     def repair(self, params, L):
         L = np.ascontiguousarray(L, np.float32).reshape(-1)

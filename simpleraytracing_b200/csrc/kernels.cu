@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
     const float x = (float)col + a.cam.xc, y = (float)row + a.cam.yc;
     float L = a.incident;
     unsigned long long n_viol = 0;
+    float zbuf = INFINITY; int zid = -1;                                  // mode 1
     for (int m = 0; m < a.n_meshes; ++m) {
         const DevMesh M = a.meshes[m];
         float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
@@ -153,7 +154,10 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
                 const float4 Dn = __ldg(M.exact + 4 * (size_t)j + 3);
                 float t;
                 const bool hit = exact_intersect(r, A, B, C, Dn.x, t);
-                if (hit) accumulate_hit(r, Dn, t, dist, ssum, hits);
+                if (hit) {
+                    if (a.mode == 0) accumulate_hit(r, Dn, t, dist, ssum, hits);
+                    else if (zbuf > t) { zbuf = t; zid = (int)(M.first + j); }     // main-omp.cxx:656-662
+                }
                 if (AUDIT) {
                     const float4 fa = __ldg(M.filt + 4 * (size_t)j), fb = __ldg(M.filt + 4 * (size_t)j + 1);
                     const float4 ga = __ldg(M.filt + 4 * (size_t)j + 2), gb = __ldg(M.filt + 4 * (size_t)j + 3);
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
                 }
             }
         }
+        if (a.mode != 0) continue;
         L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
         if (m == 0) {
             const size_t p = (size_t)orow * W + col;
@@ -178,7 +183,8 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
             if (a.hits) a.hits[p] = hits;
         }
     }
-    a.L[(size_t)orow * W + col] = L;
+    if (a.mode == 0) a.L[(size_t)orow * W + col] = L;
+    else { a.dist[(size_t)orow * W + col] = zbuf; a.ssum[(size_t)orow * W + col] = zid; }
     if (AUDIT && a.counters && n_viol) atomicAdd(a.counters + 1, n_viol);
 }
 
@@ -207,6 +213,7 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 struct SlowArgs {
     const float4* exact;
     uint32_t n;                  // triangles in the mesh
+    uint32_t first; int mode;    // closest-hit mode: scene-wide index of the mesh's first triangle
     float y; uint32_t row, col0; int row_ok;
 };
 
@@ -262,7 +269,10 @@ __device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const Slow
             const RayDirs r = make_ray(cam, s.row, col);
             float tt;
             ++n_exact;
-            if (exact_intersect(r, A, B, C, Dn.x, tt)) accumulate_hit(r, Dn, tt, dist[k], ssum[k], hits[k]);
+            if (exact_intersect(r, A, B, C, Dn.x, tt)) {
+                if (s.mode == 0) accumulate_hit(r, Dn, tt, dist[k], ssum[k], hits[k]);
+                else if (dist[k] > tt) { dist[k] = tt; ssum[k] = (int)(s.first + jj); }   // z-buffer, main-omp.cxx:656-662
+            }
         }
     }
 }
@@ -306,16 +316,22 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
     uint32_t issued = 0, consumed = 0;     // tiles issued / consumed by this CTA over all meshes (uniform)
     unsigned long long n_exact = 0;
 
+    // accumulators are touched only on the (rare) exact path: dynamically indexed -> local memory.
+    // mode 0: path length / signSum / hit count per mesh; mode 1: z-buffer / triangle index over all meshes.
+    float dist[P]; int ssum[P]; uint32_t hits[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) { dist[k] = INFINITY; ssum[k] = -1; hits[k] = 0; }
+
     for (int m = 0; m < a.n_meshes; ++m) {
         const DevMesh M = a.meshes[m];
-        // accumulators are touched only on the (rare) exact path: dynamically indexed -> local memory
-        float dist[P]; int ssum[P]; uint32_t hits[P];
+        if (a.mode == 0) {
 #pragma unroll
-        for (int k = 0; k < P; ++k) { dist[k] = 0.0f; ssum[k] = 0; hits[k] = 0; }
+            for (int k = 0; k < P; ++k) { dist[k] = 0.0f; ssum[k] = 0; hits[k] = 0; }
+        }
 
         if (M.contributes && M.n > 0) {
             SlowArgs sa;
-            sa.exact = M.exact; sa.n = M.n;
+            sa.exact = M.exact; sa.n = M.n; sa.first = M.first; sa.mode = a.mode;
             sa.y = y; sa.row = row; sa.col0 = col0; sa.row_ok = row_ok;
             const uint32_t n_tiles = (M.n_padded + kTileTris - 1) / kTileTris;
             // producer side: wait until every warp released the stage, then one thread refills it
@@ -386,6 +402,7 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
             }
         }
 
+        if (a.mode != 0) continue;
 #pragma unroll
         for (int k = 0; k < P; ++k) Lval[k] = attenuate(Lval[k], M.mu, dist[k], ssum[k], a.length_to_cm);
         if (m == 0 && row_ok) {
@@ -401,7 +418,13 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
         }
     }
 
-    if (row_ok) {
+    if (a.mode != 0) {
+        if (row_ok) {
+#pragma unroll
+            for (int k = 0; k < P; ++k)
+                if (col0 + k < W) { a.dist[(size_t)orow * W + col0 + k] = dist[k]; a.ssum[(size_t)orow * W + col0 + k] = ssum[k]; }
+        }
+    } else if (row_ok) {
         float* out = a.L + (size_t)orow * W + col0;
         if (P % 4 == 0 && (W & 3u) == 0 && col0 + P <= W) {
 #pragma unroll
@@ -415,6 +438,140 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
         }
     }
     if (a.counters && n_exact) atomicAdd(a.counters, n_exact);
+}
+
+// ------------------------------------------------------------------ shade kernel
+// Shaded variant, second pass (src/main-omp.cxx:668-794): Phong shading of the closest hit, shadow ray against
+// every other triangle, area-barycentric texture lookup, clamp + truncation to 8 bits.  One thread per pixel.
+// Shadow rays have per-pixel origins, so the common-origin pre-pack does not apply: the test below is the
+// reference's full sequence on the raw vertices.
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3sub(V3 a, V3 b) { return { __fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z) }; }
+__device__ __forceinline__ V3 v3add(V3 a, V3 b) { return { __fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z) }; }
+__device__ __forceinline__ V3 v3mulf(V3 a, float t) { return { __fmul_rn(a.x, t), __fmul_rn(a.y, t), __fmul_rn(a.z, t) }; }
+__device__ __forceinline__ V3 v3mul(V3 a, V3 b) { return { __fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z) }; }
+__device__ __forceinline__ V3 v3muld(V3 a, double t)       // Vec3::operator*(double): double product, narrowed
+{ return { (float)__dmul_rn((double)a.x, t), (float)__dmul_rn((double)a.y, t), (float)__dmul_rn((double)a.z, t) }; }
+__device__ __forceinline__ float v3dot(V3 a, V3 b) { return dot_rn(a.x, a.y, a.z, b.x, b.y, b.z); }
+__device__ __forceinline__ V3 v3cross(V3 a, V3 b)
+{
+    return { __fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y)), __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z)),
+             __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)) };
+}
+__device__ __forceinline__ V3 v3normalise(V3 a)
+{ const float l = __fsqrt_rn(v3dot(a, a)); return { __fdiv_rn(a.x, l), __fdiv_rn(a.y, l), __fdiv_rn(a.z, l) }; }
+__device__ __forceinline__ V3 ld_v3(const float* p) { return { __ldg(p), __ldg(p + 1), __ldg(p + 2) }; }
+
+// Ray::intersect (src/Ray.cxx:72-125) for an arbitrary origin
+__device__ __forceinline__ bool intersect_generic(V3 o, V3 d, V3 p1, V3 p2, V3 p3, float& t)
+{
+    const V3 e1 = v3sub(p2, p1), e2 = v3sub(p3, p1);
+    const V3 pvec = v3cross(d, e2);
+    const float det = v3dot(e1, pvec);
+    if (det == 0.0f) return false;
+    const float inv = __fdiv_rn(1.0f, det);
+    const V3 tvec = v3sub(o, p1);
+    const float u = __fmul_rn(v3dot(tvec, pvec), inv);
+    if (u < 0.0f || u > 1.0f) return false;
+    const V3 qvec = v3cross(tvec, e1);
+    const float v = __fmul_rn(v3dot(d, qvec), inv);
+    if (v < 0.0f || __fadd_rn(u, v) > 1.0f) return false;
+    t = __fmul_rn(v3dot(e2, qvec), inv);
+    return true;
+}
+
+// Triangle::getArea (include/Triangle.inl:206-216): float cross components, double pow/sqrt, narrowed
+__device__ __forceinline__ float tri_area(V3 a, V3 b, V3 c)
+{
+    const V3 ab = v3sub(b, a), ac = v3sub(c, a);
+    const double x = (double)__fsub_rn(__fmul_rn(ab.y, ac.z), __fmul_rn(ab.z, ac.y));
+    const double y = (double)__fsub_rn(__fmul_rn(ab.z, ac.x), __fmul_rn(ab.x, ac.z));
+    const double z = (double)__fsub_rn(__fmul_rn(ab.x, ac.y), __fmul_rn(ab.y, ac.x));
+    return (float)__dmul_rn(0.5, __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z))));
+}
+
+__device__ __forceinline__ uint8_t clamp_trunc(float c) { return c < 0.0f ? 0 : (c > 255.0f ? 255 : (uint8_t)(int)c); }
+__device__ __forceinline__ uint8_t clamp_trunc(double c) { return c < 0.0 ? 0 : (c > 255.0 ? 255 : (uint8_t)(int)c); }
+
+__global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ ShadeArgs a)
+{
+    const uint32_t col = blockIdx.x * 8 + (threadIdx.x & 7);
+    const uint32_t row = a.row_begin + blockIdx.y * 16 + (threadIdx.x >> 3);
+    const uint32_t W = a.cam.W;
+    if (col >= W || row >= a.row_end) return;
+    const size_t pixel = (size_t)row * W + col;
+    const int id = a.tri_id[pixel];
+    uint8_t* out = a.rgb + 3 * pixel;
+    if (id < 0) { out[0] = a.background[0]; out[1] = a.background[1]; out[2] = a.background[2]; if (a.shadow) a.shadow[pixel] = 0; return; }
+    int hm = 0;
+    while (hm + 1 < a.n_meshes && (uint32_t)id >= a.meshes[hm + 1].first) ++hm;
+    const ShadeMesh M = a.meshes[hm];
+    const uint32_t local = (uint32_t)id - M.first;
+    const RayDirs r = make_ray(a.cam, row, col);
+    const V3 origin = { a.cam.ox, a.cam.oy, a.cam.oz }, rdir = { r.bx, r.by, r.bz }, dirA = { r.ax, r.ay, r.az };
+    const float t = a.z[pixel];
+    const V3 P = v3add(origin, v3mulf(rdir, t));                                       // point_hit (:671)
+    const float4 En = __ldg(M.exact + 4 * (size_t)local + 3);
+    const V3 N = { En.y, En.z, En.w };
+    // ---- applyShading (:407-434)
+    const V3 Lc = { a.light_colour[0], a.light_colour[1], a.light_colour[2] };
+    const V3 Lp = { a.light_position[0], a.light_position[1], a.light_position[2] };
+    const V3 Ka = { M.ka[0], M.ka[1], M.ka[2] }, Kd = { M.kd[0], M.kd[1], M.kd[2] }, Ks = { M.ks[0], M.ks[1], M.ks[2] };
+    const V3 ambient = v3mul(Lc, Ka);
+    const V3 lightDir = v3normalise(v3sub(Lp, P));
+    float diff = fabsf(v3dot(N, lightDir));                                           // max(|N.L|, 0)
+    const V3 diffuse = v3mul(Lc, v3mulf(Kd, diff));
+    const V3 viewDir = v3normalise(v3sub(origin, P));
+    const V3 I = { -viewDir.x, -viewDir.y, -viewDir.z };
+    const V3 reflectDir = v3sub(I, v3muld(N, __dmul_rn(2.0, (double)v3dot(N, I))));    // reflect (Vec3.inl:120-124)
+    const float vd = v3dot(viewDir, reflectDir);
+    const float base = (0.0f < vd) ? vd : 0.0f;
+    const float spec = (M.shininess == 1.0f) ? base : powf(base, M.shininess);        // pow(x, 1) == x exactly
+    const V3 specular = v3mul(Lc, v3mulf(Ks, spec));
+    V3 colour = v3add(v3add(ambient, diffuse), specular);
+    // ---- shadow ray (:680-712)
+    const V3 sdir0 = v3normalise(v3sub(Lp, P));
+    const float sl = __fsqrt_rn(v3dot(sdir0, sdir0));
+    V3 sdir = { 0.0f, 0.0f, 0.0f };
+    if (sl != 0.0f) sdir = { __fdiv_rn(sdir0.x, sl), __fdiv_rn(sdir0.y, sl), __fdiv_rn(sdir0.z, sl) };   // Ray::Ray
+    bool in_shadow = false;
+    for (int m = 0; m < a.n_meshes && !in_shadow; ++m) {
+        const ShadeMesh S = a.meshes[m];
+#pragma unroll 1
+        for (uint32_t k = 0; k < S.n; ++k) {
+            if (S.first + k == (uint32_t)id) continue;                                // &triangle != p_intersected_triangle
+            const float* v = S.vertices + 9 * (size_t)k;
+            float ts;
+            if (intersect_generic(P, sdir, ld_v3(v), ld_v3(v + 3), ld_v3(v + 6), ts) && (double)ts > 0.0000001) { in_shadow = true; break; }
+        }
+    }
+    if (a.shadow) a.shadow[pixel] = in_shadow ? 1 : 0;
+    if (in_shadow) {                                                                   // colour *= 0.25 (double)
+        colour.x = (float)__dmul_rn((double)colour.x, 0.25); colour.y = (float)__dmul_rn((double)colour.y, 0.25);
+        colour.z = (float)__dmul_rn((double)colour.z, 0.25);
+    }
+    // ---- texture (:722-774) or plain conversion (:776-790)
+    if (M.tex && M.tex_w * M.tex_h && M.texcoords) {
+        const V3 Pt = v3add(origin, v3mulf(dirA, t));                                  // uses the pre-Ray direction (:729)
+        const float* v = M.vertices + 9 * (size_t)local;
+        const V3 A = ld_v3(v), B = ld_v3(v + 3), C = ld_v3(v + 6);
+        const float area = tri_area(A, B, C);
+        const float u = __fdiv_rn(tri_area(C, A, Pt), area);
+        const float vv = __fdiv_rn(tri_area(A, B, Pt), area);
+        const float w = __fdiv_rn(tri_area(B, C, Pt), area);
+        const float* tc = M.texcoords + 9 * (size_t)local;
+        const V3 texel = v3add(v3add(v3mulf(ld_v3(tc), w), v3mulf(ld_v3(tc + 3), u)), v3mulf(ld_v3(tc + 6), vv));
+        uint32_t ti = (uint32_t)__fmul_rn(texel.x, (float)(M.tex_w - 1)), tj = (uint32_t)__fmul_rn(texel.y, (float)(M.tex_h - 1));
+        if (ti >= M.tex_w) ti = M.tex_w - 1;                                          // the reference would throw here
+        if (tj >= M.tex_h) tj = M.tex_h - 1;
+        const uint8_t* px = M.tex + ((size_t)tj * M.tex_w + ti) * 3;
+        colour.x = __fmul_rn(colour.x, (float)px[0]); colour.y = __fmul_rn(colour.y, (float)px[1]);
+        colour.z = __fmul_rn(colour.z, (float)px[2]);
+        out[0] = clamp_trunc(colour.x); out[1] = clamp_trunc(colour.y); out[2] = clamp_trunc(colour.z);
+    } else {
+        out[0] = clamp_trunc(__dmul_rn(255.0, (double)colour.x)); out[1] = clamp_trunc(__dmul_rn(255.0, (double)colour.y));
+        out[2] = clamp_trunc(__dmul_rn(255.0, (double)colour.z));
+    }
 }
 
 // ------------------------------------------------------------------ de-interleave
@@ -634,6 +791,14 @@ cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s
         case 8: return launch_filtered_t<8>(a, s);
         default: return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_shade(const ShadeArgs& a, cudaStream_t s)
+{
+    if (a.row_end <= a.row_begin || a.cam.W == 0) return cudaSuccess;
+    dim3 grid((a.cam.W + 7) / 8, (a.row_end - a.row_begin + 15) / 16);
+    shade_kernel<<<grid, 128, 0, s>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_deinterleave(const float* slots, float* frame, uint32_t W, uint32_t H, uint32_t n_parts,

@@ -23,6 +23,7 @@ struct DevMesh {
     uint32_t n, n_padded;
     float    mu;             // attenuation coefficient
     int      contributes;    // 0: mesh adds no path length (reference semantics for meshes > 0)
+    uint32_t first;          // scene-wide index of the mesh's first triangle (closest-hit mode)
 };
 
 struct DevCamera {
@@ -54,7 +55,36 @@ struct RenderArgs {
     int32_t* ssum;           // optional
     uint32_t* hits;          // optional
     unsigned long long* counters;   // optional: [0] exact tests run, [1] filter violations (audit)
+    // mode 0: X-ray L-buffer (above).  mode 1: closest hit over all meshes (shaded variant, main-omp.cxx:632-666):
+    // `dist` receives the z-buffer value t (+inf = no hit), `ssum` the scene-wide triangle index (-1 = none);
+    // strict `z > t` in ascending triangle order => the first of equal t wins, negative t is accepted.
+    int mode;
 };
+
+// ---- shaded variant: Phong + shadow ray + texture for the pixels of a closest-hit pass ------------------
+struct ShadeMesh {
+    const float*   vertices;   // 9 floats per triangle
+    const float4*  exact;      // ExactTri (for the cached normals)
+    const float*   texcoords;  // 9 floats per triangle or nullptr
+    const uint8_t* tex;        // RGB texture or nullptr
+    uint32_t tex_w, tex_h;
+    uint32_t n, first;
+    float ka[3], kd[3], ks[3], shininess;
+};
+
+struct ShadeArgs {
+    DevCamera cam;
+    const ShadeMesh* meshes;   // device array
+    int n_meshes;
+    float light_colour[3], light_position[3];
+    const float* z;            // closest-hit pass outputs (full frame)
+    const int32_t* tri_id;
+    uint8_t* rgb;              // full frame, 3 bytes per pixel
+    uint8_t* shadow;           // optional: 1 where the shadow ray is blocked
+    uint32_t row_begin, row_end;
+    uint8_t background[3];
+};
+cudaError_t launch_shade(const ShadeArgs& a, cudaStream_t s);
 
 // Exact kernel: every pair runs the reference op sequence. audit != 0 additionally evaluates the
 // filters for every pair and counts (filter says reject) && (exact says hit) into counters[1].

@@ -39,6 +39,10 @@ struct MeshBuf {
     uint32_t n = 0, n_padded = 0;
     bool has_normals = false;
     float mu = 0.0f;
+    // shaded variant
+    float* d_texcoords = nullptr; size_t texcoord_cap = 0; bool has_texcoords = false;
+    uint8_t* d_tex = nullptr; size_t tex_cap = 0; uint32_t tex_w = 0, tex_h = 0;
+    srt_material material{};
 };
 
 } // namespace
@@ -57,6 +61,9 @@ struct srt_ctx {
     bool packed = false;                 // packed arrays match meshes + camera
     bool filterable = false;
 
+    std::vector<srt::ShadeMesh> h_shade; // shaded variant: per-mesh descriptors
+    srt::ShadeMesh* d_shade_meshes = nullptr; size_t shade_cap = 0;
+    uint8_t* d_rgb = nullptr; size_t rgb_cap = 0;
     std::vector<srt::DevMesh> h_desc;    // host copy of the descriptor arrays (default | all contribute)
     srt::DevMesh* d_meshes = nullptr;    // device array: [0, n) default semantics, [n, 2n) all meshes contribute
     size_t desc_cap = 0;
@@ -91,12 +98,16 @@ int fail(srt_ctx* c, int code, const char* fmt, ...)
 void free_mesh(MeshBuf& m)
 {
     cudaFree(m.d_vertices); cudaFree(m.d_normals); cudaFree(m.filt); cudaFree(m.exact); cudaFree(m.tile_m);
+    float* tc = m.d_texcoords; size_t tcc = m.texcoord_cap; uint8_t* tx = m.d_tex; size_t txc = m.tex_cap;
     m = MeshBuf{};
+    m.d_texcoords = tc; m.texcoord_cap = tcc; m.d_tex = tx; m.tex_cap = txc;       // kept: sized independently
 }
 
 void free_scene(srt_ctx* c)
 {
-    for (auto& m : c->meshes) free_mesh(m);
+    for (auto& m : c->meshes) { free_mesh(m); cudaFree(m.d_texcoords); cudaFree(m.d_tex); }
+    cudaFree(c->d_shade_meshes); c->d_shade_meshes = nullptr; c->shade_cap = 0;
+    cudaFree(c->d_rgb); c->d_rgb = nullptr; c->rgb_cap = 0;
     c->meshes.clear(); c->n_meshes = 0;
     cudaFree(c->d_meshes); c->d_meshes = nullptr; c->desc_cap = 0;
     cudaFree(c->d_u_off); c->d_u_off = nullptr; c->off_cap_u = 0;
@@ -170,14 +181,23 @@ int pack_scene(srt_ctx* c)
 
     const size_t nm = c->n_meshes;
     c->h_desc.assign(2 * nm, srt::DevMesh{});
+    c->h_shade.assign(nm, srt::ShadeMesh{});
     c->total_tris = 0;
     for (size_t m = 0; m < nm; ++m) {
         MeshBuf& mb = c->meshes[m];
+        srt::ShadeMesh& sm = c->h_shade[m];
+        sm.vertices = mb.d_vertices; sm.exact = (const float4*)mb.exact;
+        sm.texcoords = mb.has_texcoords ? mb.d_texcoords : nullptr;
+        sm.tex = (mb.tex_w && mb.tex_h) ? mb.d_tex : nullptr; sm.tex_w = mb.tex_w; sm.tex_h = mb.tex_h;
+        sm.n = mb.n; sm.first = (uint32_t)c->total_tris;
+        for (int k = 0; k < 3; ++k) { sm.ka[k] = mb.material.ambient[k]; sm.kd[k] = mb.material.diffuse[k]; sm.ks[k] = mb.material.specular[k]; }
+        sm.shininess = mb.material.shininess;
         SRT_CUDA(c, srt::launch_prepack(mb.d_vertices, mb.has_normals ? mb.d_normals : nullptr, mb.n, mb.n_padded,
                                         cam.origin, g, mb.exact, mb.filt, mb.tile_m, c->stream));
         srt::DevMesh& d = c->h_desc[m];
         d.filt = (const float4*)mb.filt; d.exact = (const float4*)mb.exact;
         d.tile_m = mb.tile_m; d.n = mb.n; d.n_padded = mb.n_padded; d.mu = mb.mu;
+        d.first = (uint32_t)c->total_tris;
         d.contributes = (m == 0);                           // lbuffer.cxx:788: only meshes[0] adds path length
         c->h_desc[nm + m] = d;
         c->h_desc[nm + m].contributes = 1;
@@ -190,6 +210,12 @@ int pack_scene(srt_ctx* c)
         SRT_CUDA(c, cudaMalloc(&c->d_meshes, 2 * nm * sizeof(srt::DevMesh))); c->desc_cap = 2 * nm;
     }
     SRT_CUDA(c, cudaMemcpyAsync(c->d_meshes, c->h_desc.data(), 2 * nm * sizeof(srt::DevMesh), cudaMemcpyHostToDevice, c->stream));
+    if (nm > c->shade_cap) {
+        SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_shade_meshes); c->d_shade_meshes = nullptr;
+        SRT_CUDA(c, cudaMalloc(&c->d_shade_meshes, nm * sizeof(srt::ShadeMesh))); c->shade_cap = nm;
+    }
+    SRT_CUDA(c, cudaMemcpyAsync(c->d_shade_meshes, c->h_shade.data(), nm * sizeof(srt::ShadeMesh), cudaMemcpyHostToDevice, c->stream));
     c->packed = true;
     return SRT_OK;
 }
@@ -220,10 +246,12 @@ int choose_ppt(const srt_ctx* c, const srt_params* p, uint32_t rows)
 // parts == 0: contiguous band [row_begin, row_end) written at image positions.
 // parts >= 1: block-cyclic part `part` of `parts` over the whole frame, written compactly (slot layout).
 int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint32_t row_end,
-                  float* dL, float* d_dist, int32_t* d_ssum, uint32_t* d_hits, uint32_t parts = 0, uint32_t part = 0)
+                  float* dL, float* d_dist, int32_t* d_ssum, uint32_t* d_hits, uint32_t parts = 0, uint32_t part = 0,
+                  int mode = 0)
 {
     if (!params) return fail(c, SRT_ERR_INVALID, "params is NULL");
-    if (!dL) return fail(c, SRT_ERR_INVALID, "L buffer is NULL");
+    if (mode == 0 && !dL) return fail(c, SRT_ERR_INVALID, "L buffer is NULL");
+    if (mode == 1 && (!d_dist || !d_ssum)) return fail(c, SRT_ERR_INVALID, "closest-hit pass needs z and id buffers");
     const bool repack = !c->packed;
     int rc = pack_scene(c);
     if (rc) return rc;
@@ -239,7 +267,8 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     a.cam.u_off = c->d_u_off; a.cam.v_off = c->d_v_off;
     a.cam.xc = (float)(0.5 - (double)cam.width / 2.0); a.cam.yc = (float)(0.5 - (double)cam.height / 2.0);
     a.cam.W = cam.width; a.cam.H = cam.height;
-    const bool all = (params->flags & SRT_FLAG_ALL_MESHES_CONTRIBUTE) != 0;
+    const bool all = (params->flags & SRT_FLAG_ALL_MESHES_CONTRIBUTE) != 0 || mode == 1;
+    a.mode = mode;
     a.meshes = c->d_meshes + (all ? c->n_meshes : 0);
     a.n_meshes = (int)c->n_meshes;
     a.row_begin = row_begin; a.row_end = row_end;
@@ -449,6 +478,27 @@ int srt_set_meshes(srt_ctx* c, int n_meshes, const srt_mesh_desc* meshes)
         mb.n_padded = (d.n_triangles + srt::kGroupTris - 1) / srt::kGroupTris * srt::kGroupTris;
         mb.mu = d.mu;
         mb.has_normals = d.normals != nullptr;
+        mb.material = d.material;
+        mb.has_texcoords = d.texcoords != nullptr && d.n_triangles > 0;
+        if (mb.has_texcoords) {
+            if (d.n_triangles > mb.texcoord_cap) {
+                SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+                cudaFree(mb.d_texcoords); mb.d_texcoords = nullptr;
+                SRT_CUDA(c, cudaMalloc(&mb.d_texcoords, (size_t)d.n_triangles * 9 * sizeof(float))); mb.texcoord_cap = d.n_triangles;
+            }
+            SRT_CUDA(c, cudaMemcpyAsync(mb.d_texcoords, d.texcoords, (size_t)d.n_triangles * 9 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        }
+        mb.tex_w = mb.tex_h = 0;
+        if (d.texture_rgb && d.tex_w && d.tex_h) {
+            const size_t bytes = (size_t)d.tex_w * d.tex_h * 3;
+            if (bytes > mb.tex_cap) {
+                SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+                cudaFree(mb.d_tex); mb.d_tex = nullptr;
+                SRT_CUDA(c, cudaMalloc(&mb.d_tex, bytes)); mb.tex_cap = bytes;
+            }
+            SRT_CUDA(c, cudaMemcpyAsync(mb.d_tex, d.texture_rgb, bytes, cudaMemcpyHostToDevice, c->stream));
+            mb.tex_w = d.tex_w; mb.tex_h = d.tex_h;
+        }
         // pageable source: the runtime stages the data before returning, the caller's buffer is free again
         if (d.n_triangles) {
             SRT_CUDA(c, cudaMemcpyAsync(mb.d_vertices, d.vertices, (size_t)d.n_triangles * 9 * sizeof(float),
@@ -592,6 +642,75 @@ int srt_render_xray(srt_ctx* c, const srt_params* p, float* image_out)
     SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
     SRT_CUDA(c, cudaEventElapsedTime(&c->timing.repair_ms, c->ev[2], c->ev[3]));
     c->timing.launches = 2;
+    return SRT_OK;
+}
+
+// ---- shaded variant ------------------------------------------------------------------------
+int srt_render_shaded_device(srt_ctx* c, const srt_params* p, const srt_light* light, const uint8_t background_rgb[3],
+                             uint8_t* d_rgb, uint8_t* d_shadow)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (!p || !light || !background_rgb || !d_rgb) return fail(c, SRT_ERR_INVALID, "params / light / background / rgb is NULL");
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t W = c->camera.width, H = c->camera.height;
+    int rc = ensure_frame(c, (size_t)W * H);
+    if (rc) return rc;
+    // pass 1: closest hit over all meshes (z-buffer + triangle index per pixel)
+    rc = render_device(c, p, 0, H, nullptr, c->d_dist, c->d_ssum, nullptr, 0, 0, /*mode*/ 1);
+    if (rc) return rc;
+    // pass 2: shading, shadow rays, texture
+    srt::ShadeArgs a{};
+    const srt_camera& cam = c->camera;
+    a.cam.ox = cam.origin[0]; a.cam.oy = cam.origin[1]; a.cam.oz = cam.origin[2];
+    a.cam.dx = cam.detector[0]; a.cam.dy = cam.detector[1]; a.cam.dz = cam.detector[2];
+    a.cam.ux = cam.up[0]; a.cam.uy = cam.up[1]; a.cam.uz = cam.up[2];
+    a.cam.rx = cam.right[0]; a.cam.ry = cam.right[1]; a.cam.rz = cam.right[2];
+    a.cam.u_off = c->d_u_off; a.cam.v_off = c->d_v_off;
+    a.cam.xc = (float)(0.5 - (double)W / 2.0); a.cam.yc = (float)(0.5 - (double)H / 2.0);
+    a.cam.W = W; a.cam.H = H;
+    a.meshes = c->d_shade_meshes; a.n_meshes = (int)c->n_meshes;
+    for (int k = 0; k < 3; ++k) { a.light_colour[k] = light->colour[k]; a.light_position[k] = light->position[k]; a.background[k] = background_rgb[k]; }
+    a.z = c->d_dist; a.tri_id = c->d_ssum; a.rgb = d_rgb; a.shadow = d_shadow;
+    a.row_begin = 0; a.row_end = H;
+    SRT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    SRT_CUDA(c, srt::launch_shade(a, c->stream));
+    SRT_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    c->timing.launches += 1;
+    return SRT_OK;
+}
+
+int srt_render_shaded(srt_ctx* c, const srt_params* p, const srt_light* light, const uint8_t background_rgb[3], uint8_t* rgb_out)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (!rgb_out) return fail(c, SRT_ERR_INVALID, "rgb_out is NULL");
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->camera.width * c->camera.height * 3;
+    if (bytes > c->rgb_cap) {
+        SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_rgb); c->d_rgb = nullptr;
+        SRT_CUDA(c, cudaMalloc(&c->d_rgb, bytes)); c->rgb_cap = bytes;
+    }
+    int rc = srt_render_shaded_device(c, p, light, background_rgb, c->d_rgb, nullptr);
+    if (rc) return rc;
+    SRT_CUDA(c, cudaMemcpyAsync(rgb_out, c->d_rgb, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
+    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.repair_ms, c->ev[2], c->ev[3]));     // shade pass time
+    c->timing_pending = false;
+    return SRT_OK;
+}
+
+// diagnostic: z-buffer / triangle index / shadow flag of the last shaded render (host copies; any may be NULL)
+int srt_debug_shaded_buffers(srt_ctx* c, float* z_out, int32_t* tri_id_out)
+{
+    if (!c || !c->have_camera) return SRT_ERR_INVALID;
+    const size_t n = (size_t)c->camera.width * c->camera.height;
+    if (n > c->frame_cap) return fail(c, SRT_ERR_INVALID, "no shaded render yet");
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (z_out) SRT_CUDA(c, cudaMemcpy(z_out, c->d_dist, n * 4, cudaMemcpyDeviceToHost));
+    if (tri_id_out) SRT_CUDA(c, cudaMemcpy(tri_id_out, c->d_ssum, n * 4, cudaMemcpyDeviceToHost));
     return SRT_OK;
 }
 

@@ -64,3 +64,48 @@ def uv_sphere(n_lat=500, n_lon=1000, radius=100.0, centre=(0.0, -670.0, 300.0), 
     south = len(verts) - 1
     faces.append(np.stack([np.full(n_lon, south), idx(nr - 1, j + 1), idx(nr - 1, j)], 1))
     return soup(verts.astype(np.float32), np.concatenate(faces).astype(np.uint32))
+
+
+# ---- shaded variant (src/main-omp.cxx) ---------------------------------------------------------------
+DRAGON_MATERIAL = ((np.float32(np.float64(np.float32(1)) * 0.2), 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0), 1.0)   # :197
+DEFAULT_MATERIAL = ((1.0, 1.0, 1.0), (1.0, 1.0, 1.0), (1.0, 1.0, 1.0), 1.0)                # Material(), Material.inl:76-83
+
+# texture coordinates of the background quad, per vertex (src/main-omp.cxx:537-542), expanded per triangle
+_QUAD_TC = np.array([[0, 1, 0], [1, 1, 0], [1, 0, 0], [0, 0, 0]], np.float32)
+QUAD_TEXCOORDS = np.ascontiguousarray(_QUAD_TC[np.array([0, 1, 2, 0, 2, 3])].reshape(2, 9))
+
+
+def logo_texture():
+    """Bangor_Logo_A1.jpg decoded to raw RGB by tools/make_fixtures.py (1240 x 1754 x 3)."""
+    return np.load(GOLDEN / "logo_texture.npz")["rgb"]
+
+
+def shaded_scene(texture=None):
+    """Config C1: dragon (material of main-omp.cxx:197) + textured background quad derived from the dragon bbox."""
+    tri = dragon()
+    lo = tri.reshape(-1, 3).min(0); hi = tri.reshape(-1, 3).max(0)
+    quad = logo_quad(lo, hi)
+    return [dict(tri=tri, texcoords=None, material=DRAGON_MATERIAL, texture=None),
+            dict(tri=quad, texcoords=QUAD_TEXCOORDS, material=DEFAULT_MATERIAL,
+                 texture=logo_texture() if texture is None else texture)]
+
+
+def shaded_camera(lib, meshes, W, H):
+    """Camera of the shaded drivers: origin/detector/up/right from the bbox of mesh 0 only (main-omp.cxx:208-241
+    runs before the background quad is appended), pixel spacing from the bbox of ALL meshes (renderLoop, :594-607),
+    light at origin + up * 100.0 (:235).  Returns (camera, light_position)."""
+    tri0 = np.asarray(meshes[0]["tri"], np.float32)
+    lo, hi = lib.scene_bbox([(tri0, 0.0)])
+    cam = lib.camera_from_bbox(lo, hi, W, H)
+    lo_all, hi_all = lib.scene_bbox([(np.asarray(m["tri"], np.float32), 0.0) for m in meshes])
+    rng = hi_all - lo_all                                            # float32
+    res1 = rng[2] / np.float32(W); res2 = rng[1] / np.float32(H)
+    sp = np.float32(2) * max(res1, res2)
+    cam.pixel_spacing[0] = cam.pixel_spacing[1] = float(sp)
+    up = cam.vec("up"); origin = cam.vec("origin")
+    light = origin + (up.astype(np.float64) * 100.0).astype(np.float32)   # Vec3::operator*(double), then float add
+    return cam, light
+
+
+def noise_texture(h=64, w=96, seed=1):
+    return np.random.default_rng(seed).integers(0, 256, size=(h, w, 3), dtype=np.uint8)
