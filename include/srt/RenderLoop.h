@@ -17,6 +17,7 @@
 
 #include "../srt.h"
 #include "Image.h"
+#include "ImageRGB.h"
 #include "Light.h"
 #include "TriangleMesh.h"
 #include "Vec3.h"
@@ -41,15 +42,17 @@ inline void check(int rc, const srt_ctx* ctx, const char* what)
     if (rc != SRT_OK) throw std::runtime_error(std::string(what) + ": " + srt_last_error(ctx));
 }
 struct FlatMeshes {
-    std::vector<std::vector<float>> vertices, normals;
+    std::vector<std::vector<float>> vertices, normals, texcoords;
     std::vector<srt_mesh_desc> desc;
 };
 // mu: 0.1037f for mesh 0 ("soft tissue"), 0.3971f for the others ("bone"), lbuffer.cxx:798-803
 inline FlatMeshes flatten(const std::vector<TriangleMesh>& meshes, float mu0 = 0.1037f, float mu_other = 0.3971f)
 {
     FlatMeshes f;
-    f.vertices.reserve(meshes.size()); f.normals.reserve(meshes.size());
-    for (const TriangleMesh& m : meshes) { f.vertices.push_back(m.flatVertices()); f.normals.push_back(m.flatNormals()); }
+    f.vertices.reserve(meshes.size()); f.normals.reserve(meshes.size()); f.texcoords.reserve(meshes.size());
+    for (const TriangleMesh& m : meshes) {
+        f.vertices.push_back(m.flatVertices()); f.normals.push_back(m.flatNormals()); f.texcoords.push_back(m.flatTexCoords());
+    }
     for (size_t i = 0; i < meshes.size(); ++i) {
         srt_mesh_desc d{};
         d.vertices = f.vertices[i].data();
@@ -62,6 +65,11 @@ inline FlatMeshes flatten(const std::vector<TriangleMesh>& meshes, float mu0 = 0
             d.material.specular[k] = mat.getSpecular()[k];
         }
         d.material.shininess = mat.getShininess();
+        const ImageRGB& tex = meshes[i].getTextureRGB();
+        if (tex.getWidth() > 0 && tex.getHeight() > 0) {
+            d.texcoords = f.texcoords[i].data();
+            d.texture_rgb = tex.getData(); d.tex_w = tex.getWidth(); d.tex_h = tex.getHeight();
+        }
         f.desc.push_back(d);
     }
     return f;
@@ -154,6 +162,45 @@ private:
     srt_params params_{};
     srt_camera cam_{};
 };
+
+// createBackground (src/main-omp.cxx:525-555): textured quad behind the scene, built from the scene bbox.
+inline TriangleMesh createBackground(const Vec3& upper, const Vec3& lower, const ImageRGB& texture)
+{
+    const Vec3 range = upper - lower;
+    const float x = upper[0] + range[0] * 0.1f;
+    const float y0 = lower[1] - range[1] * 0.5f, y1 = upper[1] + range[1] * 0.5f;
+    const float z0 = lower[2] - range[2] * 0.5f, z1 = upper[2] + range[2] * 0.5f;
+    const std::vector<float> vertices = { x, y0, z0, x, y1, z0, x, y1, z1, x, y0, z1 };
+    const std::vector<float> text_coords = { 0, 1, 0, 1, 1, 0, 1, 0, 0, 0, 0, 0 };
+    const std::vector<unsigned int> indices = { 0, 1, 2, 0, 2, 3 };
+    TriangleMesh mesh(vertices, indices, text_coords);
+    mesh.setTexture(texture);
+    return mesh;
+}
+
+// Drop-in for the shaded drivers' renderLoop (src/main-omp.cxx:136-142, 588-797): closest hit, Phong shading,
+// shadow rays and texturing on GPU 0. The image keeps its current colour where no triangle is hit, so it must
+// be a uniform background (Image(width, height, r, g, b) as in main-omp.cxx:233).
+inline void renderLoop(ImageRGB& anOutputImage, const std::vector<TriangleMesh>& aTriangleMeshSet,
+                       const Vec3& aDetectorPosition, const Vec3& aRayOrigin, const Vec3& anUpVector,
+                       const Vec3& aRightVector, const Light& aLight)
+{
+    const unsigned int W = anOutputImage.getWidth(), H = anOutputImage.getHeight();
+    if (W == 0 || H == 0) throw std::runtime_error("renderLoop: empty output image");
+    XRayRenderer r(0);
+    r.setMeshes(aTriangleMeshSet);
+    Vec3 upper, lower;
+    getBBox(aTriangleMeshSet, upper, lower);                 // bbox of ALL meshes sets the pixel spacing (:594-607)
+    RayTracerInfo info;
+    info.detector_position = aDetectorPosition; info.origin = aRayOrigin; info.up = anUpVector; info.right = aRightVector;
+    info.range = upper - lower;
+    r.setCamera(info, W, H);
+    srt_light light{};
+    for (int k = 0; k < 3; ++k) { light.colour[k] = aLight.getColour()[k]; light.direction[k] = aLight.getDirection()[k]; light.position[k] = aLight.getPosition()[k]; }
+    unsigned char bg[3];
+    anOutputImage.getPixel(0, 0, bg[0], bg[1], bg[2]);
+    detail::check(srt_render_shaded(r.handle(), &r.params(), &light, bg, anOutputImage.getData()), r.handle(), "srt_render_shaded");
+}
 
 // Drop-in for the reference's renderLoop (src/main.cxx:159-161): X-ray image of the scene on GPU 0.
 inline void renderLoop(Image& anOutputImage, const std::vector<TriangleMesh>& aTriangleMeshSet, RayTracerInfo& rayTracerInfo)

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "Image.h"
+#include "ImageRGB.h"
 #include "Material.h"
 #include "Ray.h"
 #include "Triangle.h"
@@ -62,9 +63,21 @@ public:
     void setMaterial(const Material& m) { material_ = m; }
     Material& getMaterial() { return material_; }
     const Material& getMaterial() const { return material_; }
+    // The shaded drivers texture a mesh with the (older) RGB image class; the float Image overload of the current
+    // reference header (TriangleMesh.h:150-152) is kept for source compatibility.
+    void setTexture(const ImageRGB& img) { texture_rgb_ = img; }
     void setTexture(const Image& img) { texture_ = img; }
     Image& getTexture() { return texture_; }
     const Image& getTexture() const { return texture_; }
+    const ImageRGB& getTextureRGB() const { return texture_rgb_; }
+    // per-triangle texture coordinates, 9 floats each (extension for the C-ABI shim)
+    std::vector<float> flatTexCoords() const
+    {
+        std::vector<float> out; out.reserve(9 * triangles_.size());
+        for (const Triangle& t : triangles_)
+            for (const Vec3* p : { &t.getTextCoord1(), &t.getTextCoord2(), &t.getTextCoord3() }) out.insert(out.end(), p->data(), p->data() + 3);
+        return out;
+    }
 
     size_t getNumberOfTriangles() const { return triangles_.size(); }
     const Triangle& getTriangle(unsigned int i) const { return triangles_[i]; }
@@ -108,6 +121,7 @@ private:
     Material material_;
     Vec3 lower_, upper_;
     Image texture_;
+    ImageRGB texture_rgb_;
 };
 
 inline std::ostream& operator<<(std::ostream& os, const TriangleMesh& m)

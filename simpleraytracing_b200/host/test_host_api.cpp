@@ -74,6 +74,18 @@ static int cpu_tests()
     CHECK(px == 80.0f);                                                  // deep copy
     const std::vector<unsigned char> lut = img.applyLUT(0.0f, 80.0f);
     CHECK(lut.size() == 18 && lut[0] == 255 && lut[3] == (unsigned char)std::lround(255.0 * 11.513f / 80.0) && lut[15] == 2);
+    // ImageRGB (old Image API): RGB pixels, bounds checks, PPM round trip
+    ImageRGB rgb(4, 3, 128, 128, 128);
+    rgb.setPixel(3, 2, 1, 2, 3);
+    unsigned char cr, cg, cb; rgb.getPixel(3, 2, cr, cg, cb);
+    CHECK(cr == 1 && cg == 2 && cb == 3 && rgb.getData()[(2 * 4 + 3) * 3 + 2] == 3);
+    CHECK(throws<std::out_of_range>([&] { rgb.setPixel(4, 0, 0, 0, 0); }));
+    rgb.savePPMFile("/tmp/srt_test_image.ppm");
+    ImageRGB back("/tmp/srt_test_image.ppm"); back.getPixel(3, 2, cr, cg, cb);
+    CHECK(back.getWidth() == 4 && back.getHeight() == 3 && cb == 3);
+    TriangleMesh bgm = createBackground(Vec3(1, 1, 1), Vec3(0, 0, 0), rgb);
+    CHECK(bgm.getNumberOfTriangles() == 2 && bgm.getTextureRGB().getWidth() == 4 && bgm.getTriangle(0).getP1().getX() == 1.0f + 1.0f * 0.1f);
+    CHECK(bgm.getTriangle(1).getTextCoord2().getX() == 1.0f && bgm.flatTexCoords().size() == 18);
     // host helpers of the C ABI through the C++ shim
     std::vector<TriangleMesh> set = { m };
     Vec3 lo, hi; getBBox(set, hi, lo);
@@ -122,6 +134,27 @@ int main(int argc, char** argv)
             return 0;
         } catch (const std::exception& e) { std::printf("ERROR: %s\n", e.what()); return 1; }
     }
-    std::printf("usage: %s cpu | ply <file> | gpu <ply> <W> <H> <out.txt>\n", argv[0]);
+    if (argc >= 7 && std::strcmp(argv[1], "shaded") == 0) {
+        // main-omp.cxx flow: load, material override (:197), bbox, camera, light (:235), background quad, renderLoop
+        try {
+            using namespace srt;
+            std::vector<TriangleMesh> meshes;
+            loadMeshes(argv[2], meshes);
+            meshes[0].setMaterial(Material(0.2 * Vec3(1, 0, 0), Vec3(0, 1, 0), Vec3(0, 0, 1), 1));
+            const unsigned W = (unsigned)std::atoi(argv[3]), H = (unsigned)std::atoi(argv[4]);
+            Vec3 lo, hi; getBBox(meshes, hi, lo);
+            Image unused;
+            RayTracerInfo info = initialiseRayTracing(meshes, hi, lo, H, W, unused, 0.0f);
+            const Vec3 light_position = info.origin + info.up * 100.0;
+            Light light(Vec3(1, 1, 1), (lo + info.range / 2.0) - light_position, light_position);
+            meshes.push_back(createBackground(hi, lo, ImageRGB(argv[5])));
+            ImageRGB out(W, H, 128, 128, 128);
+            renderLoop(out, meshes, info.detector_position, info.origin, info.up, info.right, light);
+            out.savePPMFile(argv[6]);
+            std::printf("OK\n");
+            return 0;
+        } catch (const std::exception& e) { std::printf("ERROR: %s\n", e.what()); return 1; }
+    }
+    std::printf("usage: %s cpu | ply <file> | gpu <ply> <W> <H> <out.txt> | shaded <ply> <W> <H> <tex.ppm> <out.ppm>\n", argv[0]);
     return 2;
 }

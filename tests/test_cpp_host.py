@@ -96,3 +96,22 @@ def test_cli_and_render_loop_reproduce_the_reference_output(host_bins, tmp_path,
     assert (tmp_path / "loop.txt").read_text() == want.read_text()
     # the classic flag errors keep their exit status
     assert subprocess.run([str(host_bins / "srt_xray"), "--bogus"], capture_output=True).returncode != 0
+
+
+@pytest.mark.gpu
+def test_shaded_render_loop_cpp(host_bins, tmp_path):
+    """srt::renderLoop(ImageRGB&, meshes, detector, origin, up, right, light): the main-omp.cxx flow in C++."""
+    from simpleraytracing_b200 import scene
+    d = np.load(GOLDEN / "dragon_mesh.npz")
+    write_ply(tmp_path / "dragon.ply", d["vertices"], d["faces"])
+    tex = scene.noise_texture()
+    with open(tmp_path / "tex.ppm", "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (tex.shape[1], tex.shape[0])); f.write(tex.tobytes())
+    r = subprocess.run([str(host_bins / "test_host_api"), "shaded", str(tmp_path / "dragon.ply"), "128", "128",
+                        str(tmp_path / "tex.ppm"), str(tmp_path / "out.ppm")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = (tmp_path / "out.ppm").read_bytes()
+    got = np.frombuffer(raw[raw.index(b"255\n") + 4:], np.uint8)
+    want = np.load(GOLDEN / "shaded_dragon_logo_128.npz")["rgb_noise"]
+    diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert diff.max() <= 1 and (diff == 0).mean() >= 0.999
