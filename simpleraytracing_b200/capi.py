@@ -59,7 +59,7 @@ EXPORTS = [
     "srt_set_meshes", "srt_set_camera", "srt_render_lbuffer", "srt_render_lbuffer_device", "srt_repair",
     "srt_repair_device", "srt_render_xray", "srt_interleave_slot_rows",
     "srt_render_lbuffer_interleaved_device", "srt_deinterleave_device", "srt_render_shaded",
-    "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_tile_triangles", "srt_debug_download_packed",
+    "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_force_splits", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_tile_triangles", "srt_debug_download_packed",
 ]
 
 
@@ -113,6 +113,7 @@ class Library:
         L.srt_render_xray.argtypes = [vp, C.POINTER(Params), vp]
         L.srt_last_timing.argtypes = [vp, C.POINTER(Timing)]
         L.srt_debug_count_exact.argtypes = [vp, i32]
+        L.srt_debug_force_splits.argtypes = [vp, i32]
         L.srt_debug_download_packed.argtypes = [vp, i32, vp, vp, vp, vp]
         L.srt_debug_ffma_peak.argtypes = [vp, i32, C.POINTER(C.c_float)]
         L.srt_debug_prepack.argtypes = [vp, u32, C.POINTER(Camera), vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32)]
@@ -250,6 +251,9 @@ class Context:
     def set_camera(self, cam):
         self.cam = cam
         self._ck(self.lib.srt_set_camera(self.h, C.byref(cam)))
+
+    def force_splits(self, z):
+        self._ck(self.lib.srt_debug_force_splits(self.h, int(z)))
 
     def count_exact(self, on=True):
         self._ck(self.lib.srt_debug_count_exact(self.h, int(on)))

@@ -213,11 +213,13 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 struct SlowArgs {
     const float4* exact;
     uint32_t n;                  // triangles in the mesh
-    uint32_t first; int mode;    // closest-hit mode: scene-wide index of the mesh's first triangle
+    uint32_t first; int mode;    // scene-wide index of the mesh's first triangle; 0 X-ray, 1 closest hit
+    uint32_t orow, W;            // output row of this thread (hit-list mode)
+    uint2* hit_entries; uint32_t hit_cap, z_splits, z;      // split launch: this slice's sub-lists
     float y; uint32_t row, col0; int row_ok;
 };
 
-template <int P>
+template <int P, bool SPLIT>
 __device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const SlowArgs& s, const float4* rec, uint32_t jj0,
                                                 float* dist, int* ssum, uint32_t* hits, unsigned long long& n_exact)
 {
@@ -270,7 +272,19 @@ __device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const Slow
             float tt;
             ++n_exact;
             if (exact_intersect(r, A, B, C, Dn.x, tt)) {
-                if (s.mode == 0) accumulate_hit(r, Dn, tt, dist[k], ssum[k], hits[k]);
+                if (SPLIT) {                                              // split launch: defer the ordered sum
+                    if ((double)tt > 0.0000001) {                         // lbuffer.cxx:788
+                        const float dn = dot_rn(r.ax, r.ay, r.az, Dn.y, Dn.z, Dn.w);
+                        const int sign = (0.0f < dn) - (dn < 0.0f);
+                        // this thread is the only writer of (pixel, slice): plain stores, ascending triangle order
+                        const uint32_t slot = hits[k]++;
+                        if (slot < s.hit_cap) {
+                            const size_t p = (size_t)s.orow * s.W + col;
+                            s.hit_entries[(p * s.z_splits + s.z) * s.hit_cap + slot] =
+                                make_uint2(s.first + jj, __float_as_uint(__fmul_rn((float)sign, tt)));
+                        }
+                    }
+                } else if (s.mode == 0) accumulate_hit(r, Dn, tt, dist[k], ssum[k], hits[k]);
                 else if (dist[k] > tt) { dist[k] = tt; ssum[k] = (int)(s.first + jj); }   // z-buffer, main-omp.cxx:656-662
             }
         }
@@ -279,7 +293,7 @@ __device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const Slow
 
 // MINB = resident CTAs per SM the register allocation is tuned for: 7 (72 registers) for grids that fill the GPU,
 // 5 (96 registers, fewer local-memory round trips) for small grids that cannot reach that occupancy anyway.
-template <int P, int MINB>
+template <int P, int MINB, bool SPLIT>
 __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __grid_constant__ RenderArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -324,7 +338,7 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
 
     for (int m = 0; m < a.n_meshes; ++m) {
         const DevMesh M = a.meshes[m];
-        if (a.mode == 0) {
+        if (a.mode == 0 && !(SPLIT && m > 0)) {               // split launch: hits[] is the slice-wide append counter
 #pragma unroll
             for (int k = 0; k < P; ++k) { dist[k] = 0.0f; ssum[k] = 0; hits[k] = 0; }
         }
@@ -332,8 +346,11 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
         if (M.contributes && M.n > 0) {
             SlowArgs sa;
             sa.exact = M.exact; sa.n = M.n; sa.first = M.first; sa.mode = a.mode;
+            if (SPLIT) { sa.orow = orow; sa.W = W; sa.hit_entries = a.hit_entries; sa.hit_cap = a.hit_cap; sa.z_splits = a.z_splits; sa.z = blockIdx.z; }
             sa.y = y; sa.row = row; sa.col0 = col0; sa.row_ok = row_ok;
-            const uint32_t n_tiles = (M.n_padded + kTileTris - 1) / kTileTris;
+            const uint32_t all_tiles = (M.n_padded + kTileTris - 1) / kTileTris;
+            const uint32_t t_first = SPLIT ? (uint32_t)((uint64_t)all_tiles * blockIdx.z / a.z_splits) : 0u;
+            const uint32_t n_tiles = SPLIT ? (uint32_t)((uint64_t)all_tiles * (blockIdx.z + 1) / a.z_splits) : all_tiles;   // end of my range
             // producer side: wait until every warp released the stage, then one thread refills it
             auto issue = [&](uint32_t t) {
                 const uint32_t stage = issued % kStages;
@@ -349,9 +366,9 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
                 }
                 ++issued;
             };
-            for (uint32_t t = 0; t < min(kStages - 1, n_tiles); ++t) issue(t);
+            for (uint32_t t = t_first; t < min(t_first + kStages - 1, n_tiles); ++t) issue(t);
 
-            for (uint32_t t = 0; t < n_tiles; ++t) {
+            for (uint32_t t = t_first; t < n_tiles; ++t) {
                 __syncwarp();          // re-converge after the single-lane producer / release code
                 const uint32_t stage = consumed % kStages;
                 mbar_wait(&full[stage], (consumed / kStages) & 1u);
@@ -388,13 +405,13 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
                     }
                     // resolve the PREVIOUS group now: its predicate has been ready for a whole iteration
                     if (__any_sync(0xffffffffu, pend))
-                        filtered_slow_path<P>(a.cam, sa, tp + 4 * (j - kGroupTris), jbase + j - kGroupTris, dist, ssum, hits, n_exact);
+                        filtered_slow_path<P, SPLIT>(a.cam, sa, tp + 4 * (j - kGroupTris), jbase + j - kGroupTris, dist, ssum, hits, n_exact);
                     pend = fmaxf(acc0, acc1) >= negM;
                     a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
                 }
                 // last group of the tile, while its records are still in shared memory
                 if (__any_sync(0xffffffffu, pend))
-                    filtered_slow_path<P>(a.cam, sa, tp + 4 * (cnt - kGroupTris), jbase + cnt - kGroupTris, dist, ssum, hits, n_exact);
+                    filtered_slow_path<P, SPLIT>(a.cam, sa, tp + 4 * (cnt - kGroupTris), jbase + cnt - kGroupTris, dist, ssum, hits, n_exact);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);        // this warp is done with the stage
                 ++consumed;
@@ -402,7 +419,7 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
             }
         }
 
-        if (a.mode != 0) continue;
+        if (a.mode != 0 || SPLIT) continue;             // closest hit / split launch: outputs are written later
 #pragma unroll
         for (int k = 0; k < P; ++k) Lval[k] = attenuate(Lval[k], M.mu, dist[k], ssum[k], a.length_to_cm);
         if (m == 0 && row_ok) {
@@ -418,7 +435,14 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
         }
     }
 
-    if (a.mode != 0) {
+    if (SPLIT) {
+        // split launch: publish how many entries this slice appended per pixel; resolve_hits_kernel writes the outputs
+        if (row_ok) {
+#pragma unroll
+            for (int k = 0; k < P; ++k)
+                if (col0 + k < W) a.hit_counts[((size_t)orow * W + col0 + k) * a.z_splits + blockIdx.z] = hits[k];
+        }
+    } else if (a.mode != 0) {
         if (row_ok) {
 #pragma unroll
             for (int k = 0; k < P; ++k)
@@ -438,6 +462,76 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
         }
     }
     if (a.counters && n_exact) atomicAdd(a.counters, n_exact);
+}
+
+// ------------------------------------------------------------------ hit-list resolve
+// Second pass of a split launch: one thread per output pixel sorts the pixel's hit list by scene-wide triangle
+// index (insertion sort, lists are a handful of entries) and replays the reference's per-mesh accumulation and
+// attenuation (lbuffer.cxx:768-809) in ascending triangle order.  A list that overflowed its capacity is
+// recomputed from scratch with the exact sequence over all triangles (rare; keeps the result exact).
+__global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant__ RenderArgs a)
+{
+    const uint32_t W = a.cam.W;
+    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t by = blockIdx.y >> 4, lrow = blockIdx.y & 15u;
+    const uint32_t row = a.row_begin + (by * a.blk_stride + a.blk_phase) * 16 + lrow;
+    const uint32_t orow = a.compact ? by * 16 + lrow : row;
+    if (col >= W || row >= a.row_end) return;
+    const size_t p = (size_t)orow * W + col;
+    // concatenate the slices' sub-lists (each already ascending; slices cover ascending tile ranges per mesh)
+    constexpr uint32_t kMaxList = 64;
+    uint2 e[kMaxList];
+    uint32_t n = 0; bool overflow = false;
+    for (uint32_t z = 0; z < a.z_splits; ++z) {
+        const uint32_t cnt = a.hit_counts[p * a.z_splits + z];
+        if (cnt > a.hit_cap || n + cnt > kMaxList) { overflow = true; break; }
+        const uint2* src = a.hit_entries + (p * a.z_splits + z) * a.hit_cap;
+        for (uint32_t i = 0; i < cnt; ++i) e[n++] = src[i];
+    }
+    float L = a.incident;
+    float dist0 = 0.0f; int ssum0 = 0; uint32_t hits0 = 0;
+    if (!overflow) {
+        for (uint32_t i = 1; i < n; ++i) {                      // insertion sort by triangle index (multi-mesh scenes)
+            const uint2 key = e[i];
+            uint32_t j = i;
+            while (j > 0 && e[j - 1].x > key.x) { e[j] = e[j - 1]; --j; }
+            e[j] = key;
+        }
+        uint32_t i = 0;
+        for (int m = 0; m < a.n_meshes; ++m) {
+            const DevMesh M = a.meshes[m];
+            float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
+            if (M.contributes) {
+                while (i < n && e[i].x < M.first + M.n) {
+                    const float st = __uint_as_float(e[i].y);
+                    dist = __fadd_rn(dist, st);                  // distance += sign * t, ascending triangle order
+                    ssum += (0.0f < st) - (st < 0.0f);
+                    ++hits; ++i;
+                }
+            }
+            L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
+            if (m == 0) { dist0 = dist; ssum0 = ssum; hits0 = hits; }
+        }
+    } else {
+        const RayDirs r = make_ray(a.cam, row, col);
+        for (int m = 0; m < a.n_meshes; ++m) {
+            const DevMesh M = a.meshes[m];
+            float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
+            if (M.contributes)
+                for (uint32_t j = 0; j < M.n; ++j) {
+                    const float4 A = __ldg(M.exact + 4 * (size_t)j), B = __ldg(M.exact + 4 * (size_t)j + 1);
+                    const float4 C = __ldg(M.exact + 4 * (size_t)j + 2), Dn = __ldg(M.exact + 4 * (size_t)j + 3);
+                    float t;
+                    if (exact_intersect(r, A, B, C, Dn.x, t)) accumulate_hit(r, Dn, t, dist, ssum, hits);
+                }
+            L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
+            if (m == 0) { dist0 = dist; ssum0 = ssum; hits0 = hits; }
+        }
+    }
+    a.L[p] = L;
+    if (a.dist) a.dist[p] = dist0;
+    if (a.ssum) a.ssum[p] = ssum0;
+    if (a.hits) a.hits[p] = hits0;
 }
 
 // ------------------------------------------------------------------ shade kernel
@@ -752,16 +846,16 @@ cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
 #define SRT_MIN_CTAS_SMALL 5
 #endif
 
-template <int P, int MINB>
+template <int P, int MINB, bool SPLIT>
 static cudaError_t launch_filtered_b(const RenderArgs& a, dim3 grid, size_t smem, cudaStream_t s)
 {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(lbuffer_filtered_kernel<P, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(lbuffer_filtered_kernel<P, MINB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    lbuffer_filtered_kernel<P, MINB><<<grid, 128, smem, s>>>(a);
+    lbuffer_filtered_kernel<P, MINB, SPLIT><<<grid, 128, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -769,12 +863,16 @@ template <int P>
 static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
 {
     const size_t smem = (size_t)kStages * kTileTris * 64 + 128 + 2 * kStages * sizeof(uint64_t);
-    dim3 grid((a.cam.W + 8 * P - 1) / (8 * P), a.n_blocks);
+    dim3 grid((a.cam.W + 8 * P - 1) / (8 * P), a.n_blocks, a.z_splits ? a.z_splits : 1);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const bool small = (size_t)grid.x * grid.y <= (size_t)SRT_MIN_CTAS_SMALL * sms;
-    return small ? launch_filtered_b<P, SRT_MIN_CTAS_SMALL>(a, grid, smem, s) : launch_filtered_b<P, SRT_MIN_CTAS>(a, grid, smem, s);
+    const bool small = (size_t)grid.x * grid.y * grid.z <= (size_t)SRT_MIN_CTAS_SMALL * sms;
+    if (a.hit_entries) {                                   // split launches always use P = 8
+        if (P != 8) return cudaErrorInvalidValue;
+        return launch_filtered_b<8, SRT_MIN_CTAS, true>(a, grid, smem, s);
+    }
+    return small ? launch_filtered_b<P, SRT_MIN_CTAS_SMALL, false>(a, grid, smem, s) : launch_filtered_b<P, SRT_MIN_CTAS, false>(a, grid, smem, s);
 }
 
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s)
@@ -791,6 +889,14 @@ cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s
         case 8: return launch_filtered_t<8>(a, s);
         default: return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_resolve_hits(const RenderArgs& a, cudaStream_t s)
+{
+    if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0) return cudaSuccess;
+    dim3 grid((a.cam.W + 255) / 256, a.n_blocks * 16);
+    resolve_hits_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_shade(const ShadeArgs& a, cudaStream_t s)

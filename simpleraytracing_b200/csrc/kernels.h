@@ -59,7 +59,17 @@ struct RenderArgs {
     // `dist` receives the z-buffer value t (+inf = no hit), `ssum` the scene-wide triangle index (-1 = none);
     // strict `z > t` in ascending triangle order => the first of equal t wins, negative t is accepted.
     int mode;
+    // Triangle-range splitting for small grids (mode 0 only).  With z_splits > 1 the CTAs of grid.z slice z stream
+    // only tiles [n_tiles * z / z_splits, n_tiles * (z + 1) / z_splits) of each mesh; accepted intersections are
+    // not accumulated in place (the reference's float sum is order dependent) but appended to a per-(pixel, slice) list
+    // {scene-wide triangle index, sign * t} (no atomics: one owner thread); resolve_hits_kernel concatenates, sorts and replays
+    // lbuffer.cxx:788-809 in the reference's order, so the result is bit-identical to the unsplit kernel.
+    uint32_t z_splits;
+    uint2* hit_entries;      // [pixel][z_splits][hit_cap]: one sub-list per (pixel, slice), written by its only owner
+    uint32_t* hit_counts;    // [pixel][z_splits]: entries appended (may exceed hit_cap: overflow -> exact recompute)
+    uint32_t hit_cap;
 };
+cudaError_t launch_resolve_hits(const RenderArgs& a, cudaStream_t s);
 
 // ---- shaded variant: Phong + shadow ray + texture for the pixels of a closest-hit pass ------------------
 struct ShadeMesh {

@@ -26,6 +26,10 @@
 #error "build srt_api.cpp without -mfma/-march=native"
 #endif
 
+#ifndef SRT_RESIDENT_CTAS
+#define SRT_RESIDENT_CTAS 7      // CTAs of the filtered kernel resident per SM (kernels.cu: SRT_MIN_CTAS)
+#endif
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -76,6 +80,9 @@ struct srt_ctx {
     float* d_L = nullptr; float* d_img = nullptr; float* d_dist = nullptr; int32_t* d_ssum = nullptr; uint32_t* d_hits = nullptr;
     unsigned long long* d_counters = nullptr;
     bool count_exact = false;
+    // hit lists for split launches (small grids)
+    uint2* d_hit_entries = nullptr; uint32_t* d_hit_counts = nullptr; size_t hit_pixels_cap = 0;
+    int force_z_splits = 0;              // diagnostic override: 0 = heuristic
     bool counters_pending = false, timing_pending = false;
 
     srt_timing timing{};
@@ -119,6 +126,8 @@ void free_frame(srt_ctx* c)
 {
     cudaFree(c->d_L); cudaFree(c->d_img); cudaFree(c->d_dist); cudaFree(c->d_ssum); cudaFree(c->d_hits);
     c->d_L = c->d_img = c->d_dist = nullptr; c->d_ssum = nullptr; c->d_hits = nullptr; c->frame_cap = 0;
+    cudaFree(c->d_hit_entries); cudaFree(c->d_hit_counts);
+    c->d_hit_entries = nullptr; c->d_hit_counts = nullptr; c->hit_pixels_cap = 0;
 }
 
 int ensure_frame(srt_ctx* c, size_t pixels)
@@ -297,12 +306,47 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     if (kernel != SRT_KERNEL_EXACT && kernel != SRT_KERNEL_FILTERED)
         return fail(c, SRT_ERR_INVALID, "unknown kernel selector %u", params->kernel);
 
+    // Small grids (a rank's share of a multi-GPU frame): split the triangle range over grid.z and merge through
+    // per-pixel hit lists, so that every SM still gets a full set of resident CTAs.
+    a.z_splits = 1; a.hit_entries = nullptr; a.hit_counts = nullptr; a.hit_cap = 0;
+    int ppt = 0;
+    uint32_t extra_launches = 0;
+    if (kernel == SRT_KERNEL_FILTERED) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        const uint64_t ctas8 = (uint64_t)((cam.width + 63) / 64) * a.n_blocks;
+        // A share of a multi-GPU frame is only a wave or two of CTAs: too few resident warps and no dynamic load
+        // balance (CTA run times vary with their slow-path work).  Aim for ~6 waves of shorter CTAs
+        // (profiles/r01_splits.txt: 512 CTAs x 12 slices 2.18 ms vs 2.53 ms unsplit; ideal 1.93 ms).
+        const uint64_t slots = (uint64_t)sms * SRT_RESIDENT_CTAS;
+        uint32_t zs = 1;
+        if (mode == 0 && params->pixels_per_thread == 0 && ctas8 > 0 && ctas8 < 3 * slots)
+            zs = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(2, (6 * slots + ctas8 / 2) / ctas8));
+        if (c->force_z_splits > 0 && mode == 0) zs = (uint32_t)c->force_z_splits;
+        const uint64_t min_tiles = (c->meshes[0].n_padded + srt::kTileTris - 1) / srt::kTileTris;
+        if (zs > 1 && min_tiles < 4ull * zs) zs = 1;
+        if (zs > 1) {
+            const size_t pixels = (size_t)(parts == 0 ? cam.height : a.n_blocks * 16) * cam.width;   // output index range
+            constexpr uint32_t kHitCap = 12;                  // per (pixel, slice)
+            if (pixels * zs > c->hit_pixels_cap) {
+                SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+                cudaFree(c->d_hit_entries); cudaFree(c->d_hit_counts); c->d_hit_entries = nullptr; c->d_hit_counts = nullptr;
+                SRT_CUDA(c, cudaMalloc(&c->d_hit_entries, pixels * zs * kHitCap * sizeof(uint2)));
+                SRT_CUDA(c, cudaMalloc(&c->d_hit_counts, pixels * zs * sizeof(uint32_t)));
+                c->hit_pixels_cap = pixels * zs;
+            }
+            a.z_splits = zs; a.hit_entries = c->d_hit_entries; a.hit_counts = c->d_hit_counts; a.hit_cap = kHitCap;
+            ppt = 8;
+        } else ppt = choose_ppt(c, params, a.n_blocks * 16);
+    }
     SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    if (kernel == SRT_KERNEL_FILTERED) SRT_CUDA(c, srt::launch_lbuffer_filtered(a, choose_ppt(c, params, a.n_blocks * 16), c->stream));
-    else SRT_CUDA(c, srt::launch_lbuffer_exact(a, audit, c->stream));
+    if (kernel == SRT_KERNEL_FILTERED) {
+        SRT_CUDA(c, srt::launch_lbuffer_filtered(a, ppt, c->stream));
+        if (a.z_splits > 1) { SRT_CUDA(c, srt::launch_resolve_hits(a, c->stream)); extra_launches = 1; }
+    } else SRT_CUDA(c, srt::launch_lbuffer_exact(a, audit, c->stream));
     SRT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     c->timing.kernel_used = kernel;
-    c->timing.launches = ((band_rows > 0) ? 1 : 0) + (repack ? 1 + (uint32_t)c->n_meshes : 0);
+    c->timing.launches = ((band_rows > 0) ? 1 + extra_launches : 0) + (repack ? 1 + (uint32_t)c->n_meshes : 0);
     const uint64_t tris = all ? c->total_tris : c->mesh0_tris;
     c->timing.pair_tests = (uint64_t)band_rows * cam.width * tris;
     c->timing.exact_tests = 0; c->timing.filter_violations = 0;
@@ -803,6 +847,14 @@ int srt_debug_ffma_peak(srt_ctx* c, int repeats, float* tflops_out)
     }
     cudaFree(scratch);
     *tflops_out = best;
+    return SRT_OK;
+}
+
+// diagnostic: force the number of triangle-range splits of the filtered kernel (0 = heuristic)
+int srt_debug_force_splits(srt_ctx* c, int z_splits)
+{
+    if (!c || z_splits < 0 || z_splits > 16) return SRT_ERR_INVALID;
+    c->force_z_splits = z_splits;
     return SRT_OK;
 }
 
