@@ -54,11 +54,8 @@ __attribute__((target("fma"))) static void* audit_worker(void* arg)
             const float X3 = __builtin_fmaf(g[4], x, __builtin_fmaf(g[5], y, g[6]));
             const int s0t = (fabsf(Dd) - fabsf(X1)) >= -tm;
             const int s0 = s0t && !(fabsf(X1) > fabsf(Dd) + f[6]);
-            /* level 1 (slow path): one-sided tests where the sign of D is certain, two-sided strips elsewhere */
-            int rej1;
-            if (Dd > f[6]) rej1 = (X1 < -f[6]) || (X2 < -g[3]) || (X3 < -g[7]);
-            else if (Dd < -f[6]) rej1 = (X1 > f[6]) || (X2 > g[3]) || (X3 > g[7]);
-            else rej1 = (fabsf(X2) > fabsf(Dd) + g[3]) || (fabsf(X3) > fabsf(Dd) + g[7]);
+            /* level 1 (slow path): the two remaining strips */
+            const int rej1 = (fabsf(X2) > fabsf(Dd) + g[3]) || (fabsf(X3) > fabsf(Dd) + g[7]);
             const int s1 = s0 && !rej1;
             float t; int st;
             const int hit = oracle_intersect(j->cam->origin, dB, j->tri + 9 * (size_t)k, &t, &st);

@@ -166,10 +166,8 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
                     const float Dd = fmaf(fa.w, x, fmaf(fb.x, y, fb.y));
                     const float X2 = fmaf(ga.x, x, fmaf(ga.y, y, ga.z));
                     const float X3 = fmaf(gb.x, x, fmaf(gb.y, y, gb.z));
-                    bool reject = !(fabsf(Dd) - fabsf(X1) >= -tm) || (fabsf(X1) > fabsf(Dd) + fb.z);   // level 0
-                    if (Dd > fb.z) reject = reject || (X1 < -fb.z) || (X2 < -ga.w) || (X3 < -gb.w);       // level 1
-                    else if (Dd < -fb.z) reject = reject || (X1 > fb.z) || (X2 > ga.w) || (X3 > gb.w);
-                    else reject = reject || (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);
+                    const bool reject = !(fabsf(Dd) - fabsf(X1) >= -tm) || (fabsf(X1) > fabsf(Dd) + fb.z) ||       // level 0
+                                        (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);       // level 1
                     if (reject && hit) ++n_viol;
                 }
             }
@@ -232,31 +230,29 @@ __device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const Slow
         const float bs = fmaf(fa.y, s.y, fa.z), bd = fmaf(fb.x, s.y, fb.y);
         const float b2 = fmaf(ga.y, s.y, ga.z), b3 = fmaf(gb.y, s.y, gb.z);
         const float m1 = fb.z, m2 = ga.w, m3 = gb.w;
-        // --- run-level level-1 test.  With X in {u, v, w = 1-u-v numerators} a hit needs
-        // X * sgn(det) >= -(rounding) for all three.  X and D are affine in x: where the sign
-        // of D is certain at both ends of the run it is certain inside, and an edge function that is below
-        // -m at both ends is below it inside.
+        // --- run-level test.  Each strip is |Y| <= |D| + m with Y, D affine in x.  Over the thread's pixel run
+        // |D| is convex (max at an end point) and |Y| with the same sign at both ends is minimal at an end point:
+        // min|Y| > max|D| + m at the ends => every pixel of the run is outside that strip.
         {
             const float Da = fmaf(fa.w, xa, bd), Db = fmaf(fa.w, xb, bd);
+            const float dmax = fmaxf(fabsf(Da), fabsf(Db));
             const float Sa = fmaf(fa.x, xa, bs), Sb = fmaf(fa.x, xb, bs);
             const float Ua = fmaf(ga.x, xa, b2), Ub = fmaf(ga.x, xb, b2);
             const float Va = fmaf(gb.x, xa, b3), Vb = fmaf(gb.x, xb, b3);
             bool out = !s.row_ok;
-            if (Da > m1 && Db > m1) out = out || (fmaxf(Sa, Sb) < -m1) || (fmaxf(Ua, Ub) < -m2) || (fmaxf(Va, Vb) < -m3);
-            else if (Da < -m1 && Db < -m1) out = out || (fminf(Sa, Sb) > m1) || (fminf(Ua, Ub) > m2) || (fminf(Va, Vb) > m3);
+            out = out || ((Sa > 0.0f) == (Sb > 0.0f) && fminf(fabsf(Sa), fabsf(Sb)) > dmax + m1);
+            out = out || ((Ua > 0.0f) == (Ub > 0.0f) && fminf(fabsf(Ua), fabsf(Ub)) > dmax + m2);
+            out = out || ((Va > 0.0f) == (Vb > 0.0f) && fminf(fabsf(Va), fabsf(Vb)) > dmax + m3);
             if (out) continue;
         }
-        // --- per-pixel level 0 (per-triangle margin) and level 1
+        // --- per-pixel: the three strips together are the conservative footprint of the triangle
         uint32_t mask = 0;
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             const float xk = (float)(s.col0 + k) + cam.xc;
-            const float S = fmaf(fa.x, xk, bs), Dd = fmaf(fa.w, xk, bd);
-            const float X2 = fmaf(ga.x, xk, b2), X3 = fmaf(gb.x, xk, b3);
-            bool reject = fabsf(S) > fabsf(Dd) + m1;                   // NaN compares false: survives
-            if (Dd > m1) reject = reject || (S < -m1) || (X2 < -m2) || (X3 < -m3);
-            else if (Dd < -m1) reject = reject || (S > m1) || (X2 > m2) || (X3 > m3);
-            else reject = reject || (fabsf(X2) > fabsf(Dd) + m2) || (fabsf(X3) > fabsf(Dd) + m3);
+            const float Dd = fabsf(fmaf(fa.w, xk, bd));
+            const float S = fmaf(fa.x, xk, bs), X2 = fmaf(ga.x, xk, b2), X3 = fmaf(gb.x, xk, b3);
+            const bool reject = (fabsf(S) > Dd + m1) || (fabsf(X2) > Dd + m2) || (fabsf(X3) > Dd + m3);   // NaN survives
             if (!reject) mask |= 1u << k;
         }
         if (mask == 0) continue;

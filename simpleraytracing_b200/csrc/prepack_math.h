@@ -43,8 +43,9 @@ struct ExactTri {
     float e2q, nx, ny, nz;       // e2q = edge2 . qvec (Ray.cxx:122 numerator), n = Triangle::getNormal()
 };
 
-// 32 B: level-0 conservative reject.  X and D are affine in the centred pixel coordinates (x, y):
-// X = bx*x + gx*y + ax, D = bd*x + gd*y + ad.  A pair can only be a hit when |X| <= |D| + m.
+// 32 B: level-0 conservative reject.  Y and D are affine in the centred pixel coordinates (x, y):
+// Y = bx*x + gx*y + ax (Y = 2 X - det for one barycentric numerator X), D = bd*x + gd*y + ad.
+// A pair can only be a hit when |Y| <= |D| + m  (<=> 0 <= X / det <= 1 up to rounding).
 struct FilterTri {
     float bx, gx, ax, bd;
     float gd, ad, m, pad;
@@ -131,10 +132,10 @@ SRT_HD Affine make_affine(d3 N, double r_float_path, const FrameGeom& g)
     return A;
 }
 
-// margin of the strip test |X| <= |D| + m
-SRT_HD double strip_margin(const Affine& X, const Affine& Dn)
+// margin of the strip test |Y| <= |D| + m (Y = 2 X - det): a hit has |2 x_e - det_e| <= |det_e| (1 + 16 eps)
+SRT_HD double strip_margin(const Affine& Y, const Affine& Dn)
 {
-    const double m = X.T + (1.0 + 8.0 * EPS) * Dn.T + 8.0 * EPS * Dn.absmax + 4.0 * EPS * (Dn.absmax + X.absmax);
+    const double m = Y.T + (1.0 + 16.0 * EPS) * Dn.T + 16.0 * EPS * Dn.absmax + 4.0 * EPS * (Dn.absmax + Y.absmax);
     return SAFETY * m + TINY;
 }
 
@@ -182,11 +183,18 @@ SRT_HD bool pack_triangle(const float* v, const float* normal_or_null, const flo
         const double B = a1.x * (a2.y + a2.z) + a1.y * (a2.x + a2.z) + a1.z * (a2.x + a2.y);
         const double Cq = aq.x + aq.y + aq.z;
         const double rS = 6.0 * EPS * A + TINY, rD = 6.0 * EPS * B + TINY, rV = 4.0 * EPS * Cq + TINY;
-        const Affine S = make_affine(Ns, rS, g);
+        // Each barycentric numerator X in {s, q, w = det - s - q} must satisfy 0 <= X / det <= 1 for a hit, i.e.
+        // |2 X - det| <= |det| whatever the sign of det.  Y = 2 X - det is again of the form N . d, so every level of
+        // the filter is the same two-sided strip test |Y| <= |D| + m, and the three strips together are exactly
+        // the (conservative) footprint of the triangle.
         const Affine Dn = make_affine(Nd, rD, g);
-        const Affine Vn = make_affine(QV, rV, g);
+        const d3 Nys = { 2.0 * Ns.x - Nd.x, 2.0 * Ns.y - Nd.y, 2.0 * Ns.z - Nd.z };
+        const d3 Nyv = { 2.0 * QV.x - Nd.x, 2.0 * QV.y - Nd.y, 2.0 * QV.z - Nd.z };
         const d3 Nw = { Nd.x - Ns.x - QV.x, Nd.y - Ns.y - QV.y, Nd.z - Ns.z - QV.z };
-        const Affine Wn = make_affine(Nw, rS + rD + rV, g);
+        const d3 Nyw = { 2.0 * Nw.x - Nd.x, 2.0 * Nw.y - Nd.y, 2.0 * Nw.z - Nd.z };
+        const Affine S = make_affine(Nys, 2.0 * rS + rD, g);
+        const Affine Vn = make_affine(Nyv, 2.0 * rV + rD, g);
+        const Affine Wn = make_affine(Nyw, 2.0 * (rS + rD + rV) + rD, g);
         // narrowest strip first (largest gradient => fewest surviving pixels): sort 3 by grad2, descending
         Affine s0 = S, s1 = Vn, s2 = Wn, t;
         if (s1.grad2 > s0.grad2) { t = s0; s0 = s1; s1 = t; }
