@@ -273,7 +273,9 @@ def run_ours(args):
             ctx.render_lbuffer_device(params, lay.rows, frame.data_ptr())
         else:
             ctx.render_lbuffer_interleaved_device(params, world, rank, my_slot_ptr)
-        kern_ms.append(ctx.timing().render_ms)
+        tm = ctx.timing()
+        kern_ms.append(tm.render_ms)
+        render_launches = tm.launches              # filtered kernel (+ hit-list resolve when the triangle range is split)
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = timed(step_e2e, max(1, min(args.steps, 10)), max(1, min(args.warmup, 3)), sync_each=True)
     e2e_steps = max(1, min(args.steps, 10))
@@ -306,7 +308,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "tests/s", "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(tri.nbytes + 4 * 16 + 4 * (W + H)) + 0,
                     "d2h_bytes_per_step": int(H * W * 4)},
-            "gpu_launches": (2 if world == 1 else 3) * args.steps,
+            "gpu_launches": (render_launches + (1 if world == 1 else 2)) * args.steps,   # + repair (+ de-interleave)
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one full-frame launch, ncu --set full

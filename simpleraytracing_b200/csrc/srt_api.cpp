@@ -315,13 +315,17 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         const uint64_t ctas8 = (uint64_t)((cam.width + 63) / 64) * a.n_blocks;
-        // A share of a multi-GPU frame is only a wave or two of CTAs: too few resident warps and no dynamic load
-        // balance (CTA run times vary with their slow-path work).  Aim for ~6 waves of shorter CTAs
-        // (profiles/r01_splits.txt: 512 CTAs x 12 slices 2.18 ms vs 2.53 ms unsplit; ideal 1.93 ms).
+        // Shorter CTAs in more waves balance the SMs better (CTA run times vary with their slow-path work) and keep
+        // small grids -- a rank's share of a multi-GPU frame is only a wave or two of CTAs -- at full occupancy:
+        // aim for ~12 waves (profiles/r01_splits.txt: N = 8 share 2.00 ms split vs 2.53 ms unsplit, ideal 1.90 ms;
+        // full 2048^2 frame 14.8 ms vs 15.2 ms).  The hit lists cost 96 B per (pixel, slice): capped at 2 GB.
         const uint64_t slots = (uint64_t)sms * SRT_RESIDENT_CTAS;
         uint32_t zs = 1;
-        if (mode == 0 && params->pixels_per_thread == 0 && ctas8 > 0 && ctas8 < 3 * slots)
-            zs = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(2, (6 * slots + ctas8 / 2) / ctas8));
+        if (mode == 0 && params->pixels_per_thread == 0 && ctas8 > 0) {
+            zs = (uint32_t)std::min<uint64_t>(12, std::max<uint64_t>(1, (12 * slots + ctas8 / 2) / ctas8));
+            const uint64_t px = (uint64_t)(parts == 0 ? cam.height : a.n_blocks * 16) * cam.width;
+            while (zs > 1 && px * zs * 96ull > (2ull << 30)) --zs;
+        }
         if (c->force_z_splits > 0 && mode == 0) zs = (uint32_t)c->force_z_splits;
         const uint64_t min_tiles = (c->meshes[0].n_padded + srt::kTileTris - 1) / srt::kTileTris;
         if (zs > 1 && min_tiles < 4ull * zs) zs = 1;
