@@ -36,7 +36,12 @@ with open(out, "w") as f:
             f.write(f"{k:90s} {vals[i]} {units[i]}\n")
     rows = list(csv.reader(io.StringIO(src)))
     if len(rows) > 2:
-        h, body = rows[1], rows[2:]
+        h = rows[1]
+        body = []
+        for r in rows[2:]:                      # first kernel only (a second 'Kernel Name' header starts the next one)
+            if len(r) != len(h):
+                break
+            body.append(r)
         ix = {c: i for i, c in enumerate(h)}
         cols = ["stall_dispatch", "stall_wait", "stall_short_sb", "stall_long_sb", "stall_math", "stall_barrier",
                 "stall_branch_resolving", "stall_no_inst", "stall_not_selected", "stall_selected"]
