@@ -472,58 +472,92 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
     const uint32_t by = blockIdx.y >> 4, lrow = blockIdx.y & 15u;
     const uint32_t row = a.row_begin + (by * a.blk_stride + a.blk_phase) * 16 + lrow;
     const uint32_t orow = a.compact ? by * 16 + lrow : row;
-    if (col >= W || row >= a.row_end) return;
-    const size_t p = (size_t)orow * W + col;
-    // concatenate the slices' sub-lists (each already ascending; slices cover ascending tile ranges per mesh)
-    constexpr uint32_t kMaxList = 64;
-    uint2 e[kMaxList];
-    uint32_t n = 0; bool overflow = false;
-    for (uint32_t z = 0; z < a.z_splits; ++z) {
-        const uint32_t cnt = a.hit_counts[p * a.z_splits + z];
-        if (cnt > a.hit_cap || n + cnt > kMaxList) { overflow = true; break; }
-        const uint2* src = a.hit_entries + (p * a.z_splits + z) * a.hit_cap;
-        for (uint32_t i = 0; i < cnt; ++i) e[n++] = src[i];
-    }
+    const bool valid = col < W && row < a.row_end;          // no early return: the overflow path below is warp-wide
+    const size_t p = (size_t)orow * W + (valid ? col : 0);
     float L = a.incident;
     float dist0 = 0.0f; int ssum0 = 0; uint32_t hits0 = 0;
-    if (!overflow) {
-        for (uint32_t i = 1; i < n; ++i) {                      // insertion sort by triangle index (multi-mesh scenes)
-            const uint2 key = e[i];
-            uint32_t j = i;
-            while (j > 0 && e[j - 1].x > key.x) { e[j] = e[j - 1]; --j; }
-            e[j] = key;
+    bool overflow = false;
+    if (valid) {
+        // concatenate the slices' sub-lists (each already ascending; slices cover ascending tile ranges per mesh)
+        constexpr uint32_t kMaxList = 64;
+        uint2 e[kMaxList];
+        uint32_t n = 0;
+        for (uint32_t z = 0; z < a.z_splits; ++z) {
+            const uint32_t cnt = a.hit_counts[p * a.z_splits + z];
+            if (cnt > a.hit_cap || n + cnt > kMaxList) { overflow = true; break; }
+            const uint2* src = a.hit_entries + (p * a.z_splits + z) * a.hit_cap;
+            for (uint32_t i = 0; i < cnt; ++i) e[n++] = src[i];
         }
-        uint32_t i = 0;
+        if (!overflow) {
+            for (uint32_t i = 1; i < n; ++i) {                  // insertion sort by triangle index (multi-mesh scenes)
+                const uint2 key = e[i];
+                uint32_t j = i;
+                while (j > 0 && e[j - 1].x > key.x) { e[j] = e[j - 1]; --j; }
+                e[j] = key;
+            }
+            uint32_t i = 0;
+            for (int m = 0; m < a.n_meshes; ++m) {
+                const DevMesh M = a.meshes[m];
+                float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
+                if (M.contributes) {
+                    while (i < n && e[i].x < M.first + M.n) {
+                        const float st = __uint_as_float(e[i].y);
+                        dist = __fadd_rn(dist, st);              // distance += sign * t, ascending triangle order
+                        ssum += (0.0f < st) - (st < 0.0f);
+                        ++hits; ++i;
+                    }
+                }
+                L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
+                if (m == 0) { dist0 = dist; ssum0 = ssum; hits0 = hits; }
+            }
+        }
+    }
+    // A sub-list that overflowed its capacity: the WARP recomputes that pixel from scratch with the exact sequence --
+    // 32 triangles at a time (one per lane), hits folded in ascending lane (= triangle) order -- so that one
+    // pathological ray costs tens of microseconds instead of a single thread walking the whole mesh.
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned todo = __ballot_sync(0xffffffffu, valid && overflow);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t prow = __shfl_sync(0xffffffffu, row, src), pcol = __shfl_sync(0xffffffffu, col, src);
+        const RayDirs r = make_ray(a.cam, prow, pcol);
+        float Lc = a.incident, d0 = 0.0f; int s0 = 0; uint32_t h0 = 0;
         for (int m = 0; m < a.n_meshes; ++m) {
             const DevMesh M = a.meshes[m];
             float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
             if (M.contributes) {
-                while (i < n && e[i].x < M.first + M.n) {
-                    const float st = __uint_as_float(e[i].y);
-                    dist = __fadd_rn(dist, st);                  // distance += sign * t, ascending triangle order
-                    ssum += (0.0f < st) - (st < 0.0f);
-                    ++hits; ++i;
+#pragma unroll 1
+                for (uint32_t base = 0; base < M.n; base += 32) {
+                    const uint32_t j = base + lane;
+                    float st = 0.0f; bool got = false;
+                    if (j < M.n) {
+                        const float4 A = __ldg(M.exact + 4 * (size_t)j), B = __ldg(M.exact + 4 * (size_t)j + 1);
+                        const float4 C = __ldg(M.exact + 4 * (size_t)j + 2), Dn = __ldg(M.exact + 4 * (size_t)j + 3);
+                        float t;
+                        if (exact_intersect(r, A, B, C, Dn.x, t) && (double)t > 0.0000001) {
+                            const float dn = dot_rn(r.ax, r.ay, r.az, Dn.y, Dn.z, Dn.w);
+                            st = __fmul_rn((float)((0.0f < dn) - (dn < 0.0f)), t);
+                            got = true;
+                        }
+                    }
+                    unsigned hm = __ballot_sync(0xffffffffu, got);
+                    while (hm) {
+                        const int l = __ffs(hm) - 1;
+                        hm &= hm - 1;
+                        const float v = __shfl_sync(0xffffffffu, st, l);
+                        dist = __fadd_rn(dist, v);
+                        ssum += (0.0f < v) - (v < 0.0f);
+                        ++hits;
+                    }
                 }
             }
-            L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
-            if (m == 0) { dist0 = dist; ssum0 = ssum; hits0 = hits; }
+            Lc = attenuate(Lc, M.mu, dist, ssum, a.length_to_cm);
+            if (m == 0) { d0 = dist; s0 = ssum; h0 = hits; }
         }
-    } else {
-        const RayDirs r = make_ray(a.cam, row, col);
-        for (int m = 0; m < a.n_meshes; ++m) {
-            const DevMesh M = a.meshes[m];
-            float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
-            if (M.contributes)
-                for (uint32_t j = 0; j < M.n; ++j) {
-                    const float4 A = __ldg(M.exact + 4 * (size_t)j), B = __ldg(M.exact + 4 * (size_t)j + 1);
-                    const float4 C = __ldg(M.exact + 4 * (size_t)j + 2), Dn = __ldg(M.exact + 4 * (size_t)j + 3);
-                    float t;
-                    if (exact_intersect(r, A, B, C, Dn.x, t)) accumulate_hit(r, Dn, t, dist, ssum, hits);
-                }
-            L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
-            if (m == 0) { dist0 = dist; ssum0 = ssum; hits0 = hits; }
-        }
+        if ((int)lane == src) { L = Lc; dist0 = d0; ssum0 = s0; hits0 = h0; }
     }
+    if (!valid) return;
     a.L[p] = L;
     if (a.dist) a.dist[p] = dist0;
     if (a.ssum) a.ssum[p] = ssum0;
