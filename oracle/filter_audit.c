@@ -30,8 +30,9 @@ typedef struct {
     const float* filt; const float* filt2; const float* tile_m; uint32_t tile_tris;
     uint64_t p0, p1;
     /* out: [0] pairs, [1] survive level0 (tile margin), [2] survive level0 (triangle margin),
-     *      [3] survive level1, [4] oracle hits, [5] violations */
-    uint64_t c[6];
+     *      [3] survive level1, [4] oracle hits, [5] violations, [6] hits inside a pixel run that the
+     *      run-level test (end points of an aligned 8-pixel run, kernels.cu filtered_slow_path) rejects */
+    uint64_t c[7];
 } audit_job;
 
 __attribute__((target("fma"))) static void* audit_worker(void* arg)
@@ -61,6 +62,23 @@ __attribute__((target("fma"))) static void* audit_worker(void* arg)
             const int hit = oracle_intersect(j->cam->origin, dB, j->tri + 9 * (size_t)k, &t, &st);
             j->c[0]++; j->c[1] += s0t; j->c[2] += s0; j->c[3] += s1; j->c[4] += hit;
             if (hit && !s1) j->c[5]++;
+            if (hit) {
+                /* run-level test of the aligned run of 8 pixels this pixel belongs to */
+                const uint32_t c0 = col & ~7u;
+                const float xa = (float)c0 + xc, xb = (float)(c0 + 7) + xc;
+                const float bs = __builtin_fmaf(f[1], y, f[2]), bd = __builtin_fmaf(f[4], y, f[5]);
+                const float b2 = __builtin_fmaf(g[1], y, g[2]), b3 = __builtin_fmaf(g[5], y, g[6]);
+                const float Da = __builtin_fmaf(f[3], xa, bd), Db = __builtin_fmaf(f[3], xb, bd);
+                const float dmax = fmaxf(fabsf(Da), fabsf(Db));
+                const float Sa = __builtin_fmaf(f[0], xa, bs), Sb = __builtin_fmaf(f[0], xb, bs);
+                const float Ua = __builtin_fmaf(g[0], xa, b2), Ub = __builtin_fmaf(g[0], xb, b2);
+                const float Va = __builtin_fmaf(g[4], xa, b3), Vb = __builtin_fmaf(g[4], xb, b3);
+                int out = 0;
+                out |= ((Sa > 0.0f) == (Sb > 0.0f)) && fminf(fabsf(Sa), fabsf(Sb)) > dmax + f[6];
+                out |= ((Ua > 0.0f) == (Ub > 0.0f)) && fminf(fabsf(Ua), fabsf(Ub)) > dmax + g[3];
+                out |= ((Va > 0.0f) == (Vb > 0.0f)) && fminf(fabsf(Va), fabsf(Vb)) > dmax + g[7];
+                if (out) j->c[6]++;
+            }
         }
     }
     return 0;
@@ -68,7 +86,7 @@ __attribute__((target("fma"))) static void* audit_worker(void* arg)
 
 int oracle_filter_audit(const float* tri, uint32_t n, const oracle_camera* cam, uint32_t W, uint32_t H,
                         const float* filt, const float* filt2, const float* tile_m, uint32_t tile_tris,
-                        uint64_t pixel_begin, uint64_t pixel_end, int n_threads, uint64_t counts[6])
+                        uint64_t pixel_begin, uint64_t pixel_end, int n_threads, uint64_t counts[7])
 {
     if (!__builtin_cpu_supports("fma")) return -1;
     if (n_threads < 1) n_threads = 1;
@@ -83,10 +101,10 @@ int oracle_filter_audit(const float* tri, uint32_t n, const oracle_camera* cam, 
         j->p1 = pixel_begin + total * (uint64_t)(i + 1) / (uint64_t)n_threads;
         pthread_create(&tid[i], NULL, audit_worker, j);
     }
-    memset(counts, 0, 6 * sizeof(uint64_t));
+    memset(counts, 0, 7 * sizeof(uint64_t));
     for (int i = 0; i < n_threads; ++i) {
         pthread_join(tid[i], NULL);
-        for (int k = 0; k < 6; ++k) counts[k] += jobs[i].c[k];
+        for (int k = 0; k < 7; ++k) counts[k] += jobs[i].c[k];
     }
     free(jobs); free(tid);
     return 0;

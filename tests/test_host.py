@@ -79,7 +79,7 @@ def test_filter_never_rejects_a_hit_dragon(srtlib, oracle, dragon, size):
     pk = srtlib.debug_prepack(dragon, cam)
     a = oracle.filter_audit(dragon, oracle.camera(dragon), size, size, pk)
     assert a["pairs"] == size * size * len(dragon)
-    assert a["violations"] == 0
+    assert a["violations"] == 0 and a["run_violations"] == 0
     assert a["hits"] > 0 and a["survive1"] >= a["hits"]
     assert a["survive0_tile"] < 0.03 * a["pairs"]          # the filter must actually filter
     assert a["survive1"] < 10 * a["hits"]
@@ -118,7 +118,7 @@ def test_filter_never_rejects_a_hit_adversarial(srtlib, oracle, dragon):
     cam = srtlib.camera_from_bbox(lo, hi, W, H)
     pk = srtlib.debug_prepack(tri, cam)
     a = oracle.filter_audit(tri, cam_o, W, H, pk)
-    assert a["violations"] == 0 and a["hits"] > 500
+    assert a["violations"] == 0 and a["run_violations"] == 0 and a["hits"] > 500
 
 
 def test_unfilterable_triangles_always_survive(srtlib, oracle, dragon):
