@@ -879,12 +879,8 @@ cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
 template <int P, int MINB, bool SPLIT>
 static cudaError_t launch_filtered_b(const RenderArgs& a, dim3 grid, size_t smem, cudaStream_t s)
 {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(lbuffer_filtered_kernel<P, MINB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static_assert((size_t)kStages * kTileTris * 64 + 128 + 2 * kStages * sizeof(uint64_t) <= 48 * 1024,
+                  "the tile ring must fit the default dynamic shared-memory limit (no per-device opt-in needed)");
     lbuffer_filtered_kernel<P, MINB, SPLIT><<<grid, 128, smem, s>>>(a);
     return cudaGetLastError();
 }
