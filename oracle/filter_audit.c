@@ -5,7 +5,9 @@
  * filter constants produced by the product's host pre-pack (srt_debug_prepack)
  * and, for every (pixel, triangle) pair of a frame, evaluates the filter with
  * the same fused-multiply-add sequence the CUDA kernel uses (fmaf == one
- * rounding, like FFMA) next to the oracle's Ray::intersect restatement.
+ * rounding, like FFMA; the binary16 steps of the level-0 gate are emulated with
+ * _Float16 and an exact long double intermediate == one rounding, like HFMA2)
+ * next to the oracle's Ray::intersect restatement.
  * A "violation" is a pair the filter rejects although the oracle reports a hit;
  * the filter is only valid if there are none.
  */
@@ -35,6 +37,17 @@ typedef struct {
     uint64_t c[7];
 } audit_job;
 
+static _Float16 h_from_bits(uint16_t b) { _Float16 h; memcpy(&h, &b, 2); return h; }
+static _Float16 h_fma(_Float16 a, _Float16 b, _Float16 c) { return (_Float16)((long double)a * (long double)b + (long double)c); }
+static _Float16 h_abs(_Float16 a) { return a < 0 ? -a : a; }
+/* float -> binary16 rounded toward -inf (cvt.rd.f16.f32) */
+static _Float16 h_round_down(float v)
+{
+    _Float16 h = (_Float16)v;
+    if ((float)h > v) { uint16_t b; memcpy(&b, &h, 2); b = (b & 0x8000u) ? (uint16_t)(b + 1) : (b ? (uint16_t)(b - 1) : 0x8001u); memcpy(&h, &b, 2); }
+    return h;
+}
+
 __attribute__((target("fma"))) static void* audit_worker(void* arg)
 {
     audit_job* j = (audit_job*)arg;
@@ -53,7 +66,17 @@ __attribute__((target("fma"))) static void* audit_worker(void* arg)
             const float Dd = __builtin_fmaf(f[3], x, __builtin_fmaf(f[4], y, f[5]));
             const float X2 = __builtin_fmaf(g[0], x, __builtin_fmaf(g[1], y, g[2]));
             const float X3 = __builtin_fmaf(g[4], x, __builtin_fmaf(g[5], y, g[6]));
-            const int s0t = (fabsf(Dd) - fabsf(X1)) >= -tm;
+            /* level-0 gate, even pixels-per-thread (run of 8): binary32 at the run's first pixel, one binary16 step */
+            uint32_t hw; memcpy(&hw, &f[7], 4);
+            const float x0 = (float)(col & ~7u) + xc;
+            const _Float16 hk = (_Float16)(float)(col & 7u);
+            const _Float16 Y16 = h_fma(h_from_bits((uint16_t)(hw & 0xffffu)), hk, (_Float16)__builtin_fmaf(f[0], x0, __builtin_fmaf(f[1], y, f[2])));
+            const _Float16 D16 = h_fma(h_from_bits((uint16_t)(hw >> 16)), hk, (_Float16)__builtin_fmaf(f[3], x0, __builtin_fmaf(f[4], y, f[5])));
+            const _Float16 t16 = (_Float16)((long double)h_abs(D16) - (long double)h_abs(Y16));
+            const int gate16 = !(t16 < h_round_down(-tm));
+            /* odd pixels-per-thread: the binary32 gate */
+            const int gate32 = (fabsf(Dd) - fabsf(X1)) >= -tm;
+            const int s0t = gate16 && gate32;
             const int s0 = s0t && !(fabsf(X1) > fabsf(Dd) + f[6]);
             /* level 1 (slow path): the two remaining strips */
             const int rej1 = (fabsf(X2) > fabsf(Dd) + g[3]) || (fabsf(X3) > fabsf(Dd) + g[7]);

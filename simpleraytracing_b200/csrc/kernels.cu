@@ -16,6 +16,7 @@
 #include "kernels.h"
 
 #include <cfloat>
+#include <cuda_fp16.h>
 
 #include "prepack_math.h"
 
@@ -166,8 +167,16 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
                     const float Dd = fmaf(fa.w, x, fmaf(fb.x, y, fb.y));
                     const float X2 = fmaf(ga.x, x, fmaf(ga.y, y, ga.z));
                     const float X3 = fmaf(gb.x, x, fmaf(gb.y, y, gb.z));
-                    const bool reject = !(fabsf(Dd) - fabsf(X1) >= -tm) || (fabsf(X1) > fabsf(Dd) + fb.z) ||       // level 0
-                                        (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);       // level 1
+                    // level-0 gate of the filtered kernel (8 pixels per thread): binary32 value at the first pixel
+                    // of the aligned run, one binary16 FMA step to this pixel, tile margin rounded up to binary16
+                    const float x0 = (float)(col & ~7u) + a.cam.xc;
+                    const __half hk = __int2half_rn((int)(col & 7u));
+                    const __half2 hs = *reinterpret_cast<const __half2*>(&fb.w);
+                    const __half Y16 = __hfma(__low2half(hs), hk, __float2half_rn(fmaf(fa.x, x0, fmaf(fa.y, y, fa.z))));
+                    const __half D16 = __hfma(__high2half(hs), hk, __float2half_rn(fmaf(fa.w, x0, fmaf(fb.x, y, fb.y))));
+                    const bool gate = __hlt(__hsub(__habs(D16), __habs(Y16)), __float2half_rd(-tm));
+                    const bool reject = gate || !(fabsf(Dd) - fabsf(X1) >= -tm) || (fabsf(X1) > fabsf(Dd) + fb.z) ||  // level 0
+                                        (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);         // level 1
                     if (reject && hit) ++n_viol;
                 }
             }
@@ -212,6 +221,70 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 #define SRT_GROUP_UNROLL 4
 #endif
 constexpr int kGroupUnroll = SRT_GROUP_UNROLL;   // groups per trip of the hot loop: unrolling removes the register rotation of the prefetch and loop overhead (14.8 -> 13.8 ms)
+
+// Level-0 state of one group (kGroupTris = 2 triangles) for one thread's run of P pixels.
+//  * even P: Y and D at the run's first pixel in binary32, rounded to binary16 and stepped along the run with
+//    HFMA2 -- two pixels per instruction; the |D| - |Y| values are folded with 3-input packed max (VHMNMX).
+//    The error of the binary16 steps is part of the record's margin (prepack_math.h, pack_triangle).
+//  * odd P: the binary32 evaluation (2 FFMA + FADD + 1/2 FMNMX3 per pair).
+template <int P>
+struct Level0 {
+    static constexpr bool kHalf = (P & 1) == 0;
+    // kHalf: Y0/D0/Y1/D1 as half2 bits + slope words; else: bx, bd, base-y, base-d per triangle
+    float v[kHalf ? 6 : 8];
+
+    __device__ __forceinline__ void load(const float4* q, float x0, float y)
+    {
+        const float4 a0 = q[0], b0 = q[1], a1 = q[4], b1 = q[5];
+        if constexpr (kHalf) {
+            const float fy0 = fmaf(a0.x, x0, fmaf(a0.y, y, a0.z)), fd0 = fmaf(a0.w, x0, fmaf(b0.x, y, b0.y));
+            const float fy1 = fmaf(a1.x, x0, fmaf(a1.y, y, a1.z)), fd1 = fmaf(a1.w, x0, fmaf(b1.x, y, b1.y));
+            put(0, __floats2half2_rn(fy0, fy0)); put(1, __floats2half2_rn(fd0, fd0));
+            put(2, __floats2half2_rn(fy1, fy1)); put(3, __floats2half2_rn(fd1, fd1));
+            v[4] = b0.w; v[5] = b1.w;
+        } else {
+            v[0] = a0.x; v[1] = a0.w; v[2] = fmaf(a0.y, y, a0.z); v[3] = fmaf(b0.x, y, b0.y);
+            v[4] = a1.x; v[5] = a1.w; v[6] = fmaf(a1.y, y, a1.z); v[7] = fmaf(b1.x, y, b1.y);
+        }
+    }
+    __device__ __forceinline__ void put(int i, __half2 h) { v[i] = *reinterpret_cast<const float*>(&h); }
+    __device__ __forceinline__ __half2 get(int i) const { return *reinterpret_cast<const __half2*>(&v[i]); }
+
+    // may any pixel of the run be inside the level-0 strip of either triangle?
+    __device__ __forceinline__ bool survives(const float (&x)[P], float negM, __half2 negM2) const
+    {
+        if constexpr (kHalf) {
+            const __half2 Y0 = get(0), D0 = get(1), Y1 = get(2), D1 = get(3);
+            const __half2 sy0 = __low2half2(get(4)), sd0 = __high2half2(get(4));
+            const __half2 sy1 = __low2half2(get(5)), sd1 = __high2half2(get(5));
+            __half2 acc = __half2half2(__ushort_as_half((unsigned short)0xfc00u));         // -inf
+#pragma unroll
+            for (int k = 0; k < P; k += 2) {
+                const __half2 dx = __floats2half2_rn((float)k, (float)(k + 1));
+                const __half2 t0 = __hsub2(__habs2(__hfma2(sd0, dx, D0)), __habs2(__hfma2(sy0, dx, Y0)));
+                const __half2 t1 = __hsub2(__habs2(__hfma2(sd1, dx, D1)), __habs2(__hfma2(sy1, dx, Y1)));
+                acc = __hmax2(acc, __hmax2(t0, t1));
+            }
+            return !__hblt2(acc, negM2);                       // some |D| - |Y| >= -margin (a NaN survives)
+        } else {
+            float acc0 = -FLT_MAX, acc1 = -FLT_MAX;
+#pragma unroll
+            for (int k = 0; k + 1 < P; k += 2) {
+                const float S0 = fmaf(v[0], x[k], v[2]), D0 = fmaf(v[1], x[k], v[3]);
+                const float S1 = fmaf(v[4], x[k], v[6]), D1 = fmaf(v[5], x[k], v[7]);
+                const float S2 = fmaf(v[0], x[k + 1], v[2]), D2 = fmaf(v[1], x[k + 1], v[3]);
+                const float S3 = fmaf(v[4], x[k + 1], v[6]), D3 = fmaf(v[5], x[k + 1], v[7]);
+                acc0 = fmax3(acc0, fabsf(D0) - fabsf(S0), fabsf(D2) - fabsf(S2));
+                acc1 = fmax3(acc1, fabsf(D1) - fabsf(S1), fabsf(D3) - fabsf(S3));
+            }
+            const float S0 = fmaf(v[0], x[P - 1], v[2]), D0 = fmaf(v[1], x[P - 1], v[3]);      // the last pixel on its own
+            const float S1 = fmaf(v[4], x[P - 1], v[6]), D1 = fmaf(v[5], x[P - 1], v[7]);
+            acc0 = fmaxf(acc0, fabsf(D0) - fabsf(S0));
+            acc1 = fmaxf(acc1, fabsf(D1) - fabsf(S1));
+            return fmaxf(acc0, acc1) >= negM;
+        }
+    }
+};
 
 struct SlowArgs {
     const float4* exact;
@@ -376,39 +449,24 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
                 const float4* tp = tiles + (size_t)stage * kTileTris * 4;
                 const uint32_t cnt = min(kTileTris, M.n_padded - t * kTileTris);    // multiple of kGroupTris
                 const float negM = -__ldg(M.tile_m + t);
+                const __half2 negM2 = __half2half2(__float2half_rd(negM));     // margin rounded up to binary16
                 const uint32_t jbase = t * kTileTris;
 
                 bool pend = false;             // may the previous group have a survivor in this lane?
-                float4 a0 = tp[0], b0 = tp[1], a1 = tp[4], b1 = tp[5];
+                Level0<P> cur;
+                cur.load(tp, x[0], y);
 #pragma unroll(kGroupUnroll)
                 for (uint32_t j = 0; j < cnt; j += kGroupTris) {
-                    // prefetch the next group's level-0 coefficients (past the tile end: slack / next stage, unused)
-                    const float4* np = tp + 4 * (j + kGroupTris);
-                    const float4 na0 = np[0], nb0 = np[1], na1 = np[4], nb1 = np[5];
-
-                    const float bs0 = fmaf(a0.y, y, a0.z), bd0 = fmaf(b0.x, y, b0.y);
-                    const float bs1 = fmaf(a1.y, y, a1.z), bd1 = fmaf(b1.x, y, b1.y);
-                    float acc0 = -FLT_MAX, acc1 = -FLT_MAX;
-#pragma unroll
-                    for (int k = 0; k + 1 < P; k += 2) {
-                        const float S0 = fmaf(a0.x, x[k], bs0), D0 = fmaf(a0.w, x[k], bd0);
-                        const float S1 = fmaf(a1.x, x[k], bs1), D1 = fmaf(a1.w, x[k], bd1);
-                        const float S2 = fmaf(a0.x, x[k + 1], bs0), D2 = fmaf(a0.w, x[k + 1], bd0);
-                        const float S3 = fmaf(a1.x, x[k + 1], bs1), D3 = fmaf(a1.w, x[k + 1], bd1);
-                        acc0 = fmax3(acc0, fabsf(D0) - fabsf(S0), fabsf(D2) - fabsf(S2));
-                        acc1 = fmax3(acc1, fabsf(D1) - fabsf(S1), fabsf(D3) - fabsf(S3));
-                    }
-                    if (P & 1) {                                       // odd P: the last pixel on its own
-                        const float S0 = fmaf(a0.x, x[P - 1], bs0), D0 = fmaf(a0.w, x[P - 1], bd0);
-                        const float S1 = fmaf(a1.x, x[P - 1], bs1), D1 = fmaf(a1.w, x[P - 1], bd1);
-                        acc0 = fmaxf(acc0, fabsf(D0) - fabsf(S0));
-                        acc1 = fmaxf(acc1, fabsf(D1) - fabsf(S1));
-                    }
+                    // prepare the next group (past the tile end: slack / next stage, values unused): its shared-memory
+                    // loads and per-thread base values are off the critical path of the current group
+                    Level0<P> nxt;
+                    nxt.load(tp + 4 * (j + kGroupTris), x[0], y);
+                    const bool surv = cur.survives(x, negM, negM2);
                     // resolve the PREVIOUS group now: its predicate has been ready for a whole iteration
                     if (__any_sync(0xffffffffu, pend))
                         filtered_slow_path<P, SPLIT>(a.cam, sa, tp + 4 * (j - kGroupTris), jbase + j - kGroupTris, dist, ssum, hits, n_exact);
-                    pend = fmaxf(acc0, acc1) >= negM;
-                    a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
+                    pend = surv;
+                    cur = nxt;
                 }
                 // last group of the tile, while its records are still in shared memory
                 if (__any_sync(0xffffffffu, pend))
@@ -786,14 +844,14 @@ __global__ void __launch_bounds__(kTileTris) prepack_kernel(const float* __restr
         eo[0] = make_float4(E.e2x, E.e2y, E.e2z, E.e1x); eo[1] = make_float4(E.e1y, E.e1z, E.tx, E.ty);
         eo[2] = make_float4(E.tz, E.qx, E.qy, E.qz);     eo[3] = make_float4(E.e2q, E.nx, E.ny, E.nz);
         float4* fo = filt + 4 * (size_t)i;
-        fo[0] = make_float4(f.bx, f.gx, f.ax, f.bd); fo[1] = make_float4(f.gd, f.ad, f.m, f.pad);
+        fo[0] = make_float4(f.bx, f.gx, f.ax, f.bd); fo[1] = make_float4(f.gd, f.ad, f.m, __uint_as_float(f.h));
         fo[2] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2); fo[3] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
         m = f.m;
     } else if (i < n_padded) {
         FilterTri f; FilterTri2 f2;
         pack_padding(f, f2);
         float4* fo = filt + 4 * (size_t)i;
-        fo[0] = make_float4(f.bx, f.gx, f.ax, f.bd); fo[1] = make_float4(f.gd, f.ad, f.m, f.pad);
+        fo[0] = make_float4(f.bx, f.gx, f.ax, f.bd); fo[1] = make_float4(f.gd, f.ad, f.m, __uint_as_float(f.h));
         fo[2] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2); fo[3] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
     }
 #pragma unroll

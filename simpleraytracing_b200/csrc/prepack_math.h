@@ -44,11 +44,15 @@ struct ExactTri {
 };
 
 // 32 B: level-0 conservative reject.  Y and D are affine in the centred pixel coordinates (x, y):
-// Y = bx*x + gx*y + ax (Y = 2 X - det for one barycentric numerator X), D = bd*x + gd*y + ad.
-// A pair can only be a hit when |Y| <= |D| + m  (<=> 0 <= X / det <= 1 up to rounding).
+// Y = bx*x + gx*y + ax (Y = 2 X - det for one barycentric numerator X), D = bd*x + gd*y + ad
+// (D = LAMBDA * det, see pack_triangle).  A pair can only be a hit when |Y| <= |D| + m
+// (<=> 0 <= X / det <= 1 up to rounding).  The record is scaled by a per-triangle power of two so
+// that the render kernel can step Y and D along a pixel run in binary16 (HFMA2, two pixels per
+// instruction) from a binary32 value at the run's first pixel; h holds the binary16 x-slopes.
 struct FilterTri {
     float bx, gx, ax, bd;
-    float gd, ad, m, pad;
+    float gd, ad, m;
+    uint32_t h;                  // binary16(bx) in the low half, binary16(bd) in the high half
 };
 
 // 32 B: level-1 reject, the two remaining strips (slow path only).
@@ -76,6 +80,9 @@ constexpr double SAFETY = 2.0;                   // covers second-order terms of
 constexpr double TINY = 1e-30;                   // absolute slack for gradual underflow
 constexpr double BIG = 1073741824.0;             // 2^30: magnitude precondition
 constexpr double LIM = 1e30;
+constexpr double LAMBDA = 1.00390625;            // 1 + 2^-8: |D| is widened by this factor; pays for the binary16 relative error
+constexpr double H_SLOPE = 14.1 / 2048.0;        // binary16 error per unit x-slope over a run of <= 8 pixels (see pack_triangle)
+constexpr double H_ABS = 9.5367431640625e-07;    // 2^-20: binary16 subnormal roundings
 
 struct f3 { float x, y, z; };
 struct d3 { double x, y, z; };
@@ -97,6 +104,33 @@ SRT_HD double ddot(d3 a, const double b[3]) { return a.x * b[0] + a.y * b[1] + a
 SRT_HD double absdot(d3 a, const double b[3]) { return std::fabs(a.x) * b[0] + std::fabs(a.y) * b[1] + std::fabs(a.z) * b[2]; }
 SRT_HD bool finite3(f3 a) { return std::isfinite(a.x) && std::isfinite(a.y) && std::isfinite(a.z); }
 SRT_HD double maxabs(f3 a) { return std::fmax(std::fabs((double)a.x), std::fmax(std::fabs((double)a.y), std::fabs((double)a.z))); }
+
+// float -> IEEE binary16 bit pattern, round to nearest even (same result as cvt.rn.f16.f32)
+SRT_HD uint32_t f16_bits(float f)
+{
+    uint32_t u;
+#if defined(__CUDA_ARCH__)
+    u = __float_as_uint(f);
+#else
+    static_assert(sizeof(u) == sizeof(f), "binary32 expected");
+    __builtin_memcpy(&u, &f, sizeof(u));
+#endif
+    const uint32_t sign = (u >> 16) & 0x8000u, a = u & 0x7fffffffu;
+    if (a > 0x7f800000u) return sign | 0x7e00u;                 // NaN
+    if (a >= 0x477ff000u) return sign | 0x7c00u;                // >= 65520 (or inf) -> inf
+    if (a < 0x38800000u) {                                      // below 2^-14: binary16 subnormal, spacing 2^-24
+#if defined(__CUDA_ARCH__)
+        const float af = __uint_as_float(a);
+#else
+        float af; __builtin_memcpy(&af, &a, sizeof(af));
+#endif
+        return sign | (uint32_t)std::rint((double)af * 16777216.0);     // exact product, ties to even; 1024 == smallest normal
+    }
+    uint32_t h = (((a >> 23) - 112u) << 10) | ((a & 0x7fffffu) >> 13);
+    const uint32_t rem = a & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;     // a carry moves into the exponent, as it should
+    return sign | h;
+}
 
 SRT_HD float round_up(double v)
 {
@@ -187,7 +221,10 @@ SRT_HD bool pack_triangle(const float* v, const float* normal_or_null, const flo
         // |2 X - det| <= |det| whatever the sign of det.  Y = 2 X - det is again of the form N . d, so every level of
         // the filter is the same two-sided strip test |Y| <= |D| + m, and the three strips together are exactly
         // the (conservative) footprint of the triangle.
-        const Affine Dn = make_affine(Nd, rD, g);
+        // The strips are compared with D = LAMBDA * det, LAMBDA = 1 + 2^-8: |det| <= |LAMBDA det| keeps every bound below
+        // valid as it stands, and the slack (LAMBDA - 1)|det| pays for the RELATIVE error of the binary16 evaluation.
+        const d3 NdT = { LAMBDA * Nd.x, LAMBDA * Nd.y, LAMBDA * Nd.z };
+        const Affine Dn = make_affine(NdT, LAMBDA * rD, g);
         const d3 Nys = { 2.0 * Ns.x - Nd.x, 2.0 * Ns.y - Nd.y, 2.0 * Ns.z - Nd.z };
         const d3 Nyv = { 2.0 * QV.x - Nd.x, 2.0 * QV.y - Nd.y, 2.0 * QV.z - Nd.z };
         const d3 Nw = { Nd.x - Ns.x - QV.x, Nd.y - Ns.y - QV.y, Nd.z - Ns.z - QV.z };
@@ -201,14 +238,45 @@ SRT_HD bool pack_triangle(const float* v, const float* normal_or_null, const flo
         if (s2.grad2 > s1.grad2) { t = s1; s1 = s2; s2 = t; }
         if (s1.grad2 > s0.grad2) { t = s0; s0 = s1; s1 = t; }
         const double m0 = strip_margin(s0, Dn), m1 = strip_margin(s1, Dn), m2 = strip_margin(s2, Dn);
-        ok = std::isfinite(m0) && std::isfinite(m1) && std::isfinite(m2) && m0 < LIM && m1 < LIM && m2 < LIM &&
-             S.absmax < LIM && Dn.absmax < LIM && Vn.absmax < LIM && Wn.absmax < LIM;
+        // --- binary16 stepping of level 0 (render kernel, even pixels-per-thread).  With Yf(k) the binary32 value
+        // fma(bx, x0 + k, fma(gx, y, ax)) the bounds above are about, the kernel evaluates, for pixel k <= 7 of a run,
+        //     Y16(k) = fl16(fl16(bx) * k + fl16(Yf(0)))            (one HFMA2; k is exact in binary16)
+        // |Y16(k) - Yf(k)| <= 7 |fl16(bx) - bx| + |fl16(Yf(0)) - Yf(0)| + 2 eps absmax + 2^-11 |Y16(k)| + subnormal terms
+        //                  <= rho |Yf(k)| + hY,   rho = 1.001 * 2^-10,  hY = (14.1 / 2048) |bx| + 2.1 eps absmax + 2^-21
+        // (|Yf(0)| <= |Yf(k)| + 7 |bx| + ...), and the same for D.  The float-level statement is
+        //     hit  =>  |Yf| <= (1 + 16 eps) / LAMBDA * |Df| + m0,
+        // hence hit => |Y16| <= (1 + rho)(1 + 16 eps) / (LAMBDA (1 - rho)) (|D16| + hD) + (1 + rho) m0 + hY
+        //                    <= |D16| + hD + 1.002 m0 + hY                    [the factor is < 1 for LAMBDA = 1 + 2^-8]
+        // The record is scaled by a power of two `sc` (exact, the tests are scale invariant) so that a hit implies
+        // |D16| + margin <= 2^13 and 7 |bx| <= 7 * 2^12: then no binary16 quantity of a HIT overflows, and an overflowing
+        // Y16 (= +-inf, never NaN: fl16(bx) * k stays finite) is a correct reject because D16 stays finite.
+        const double hY = H_SLOPE * std::fabs(s0.b) + 2.1 * EPS * s0.absmax;
+        const double hD = H_SLOPE * std::fabs(Dn.b) + 2.1 * EPS * Dn.absmax;
+        const double M0 = 1.002 * m0 + hY + hD;
+        double sc = 1.0;
+        {
+            const double U = Dn.absmax + M0, B = std::fabs(s0.b);
+            double lim = 0.0;
+            if (U > 0.0) lim = 8000.0 / U;
+            if (B > 0.0) lim = lim > 0.0 ? std::fmin(lim, 4096.0 / B) : 4096.0 / B;
+            if (lim > 0.0 && std::isfinite(lim)) {
+                int e = (int)std::floor(std::log2(lim));
+                e = e < -100 ? -100 : (e > 100 ? 100 : e);
+                sc = std::ldexp(1.0, e);
+                if (sc > lim) sc *= 0.5;                        // log2 rounding at an exact power of two
+            }
+        }
+        const double M16 = sc * M0 + H_ABS + TINY;
+        ok = std::isfinite(m0) && std::isfinite(m1) && std::isfinite(m2) && sc * m0 < LIM && sc * m1 < LIM && sc * m2 < LIM &&
+             sc * S.absmax < LIM && sc * Dn.absmax < LIM && sc * Vn.absmax < LIM && sc * Wn.absmax < LIM &&
+             sc * (Dn.absmax + M0) <= 8192.0 && sc * std::fabs(s0.b) <= 4100.0;
         if (ok) {
-            f.bx = (float)s0.b; f.gx = (float)s0.g; f.ax = (float)s0.a;
-            f.bd = (float)Dn.b; f.gd = (float)Dn.g; f.ad = (float)Dn.a;
-            f.m = round_up(m0); f.pad = 0.0f;
-            f2.bx2 = (float)s1.b; f2.gx2 = (float)s1.g; f2.ax2 = (float)s1.a; f2.m2 = round_up(m1);
-            f2.bx3 = (float)s2.b; f2.gx3 = (float)s2.g; f2.ax3 = (float)s2.a; f2.m3 = round_up(m2);
+            f.bx = (float)(sc * s0.b); f.gx = (float)(sc * s0.g); f.ax = (float)(sc * s0.a);
+            f.bd = (float)(sc * Dn.b); f.gd = (float)(sc * Dn.g); f.ad = (float)(sc * Dn.a);
+            f.m = round_up(M16);
+            f.h = f16_bits(f.bx) | (f16_bits(f.bd) << 16);
+            f2.bx2 = (float)(sc * s1.b); f2.gx2 = (float)(sc * s1.g); f2.ax2 = (float)(sc * s1.a); f2.m2 = round_up(sc * m1 + TINY);
+            f2.bx3 = (float)(sc * s2.b); f2.gx3 = (float)(sc * s2.g); f2.ax3 = (float)(sc * s2.a); f2.m3 = round_up(sc * m2 + TINY);
         }
     }
     if (!ok) {
@@ -219,7 +287,7 @@ SRT_HD bool pack_triangle(const float* v, const float* normal_or_null, const flo
     return ok;
 }
 
-// Padding entries never survive: X = 3e38, D = 0 -> |D| - |X| = -3e38 < -m for every tile margin (< 1e30).
+// Padding entries never survive: X = 3e38 (binary16: +inf), D = 0 -> |D| - |X| < -m for every tile margin (< 1e30).
 SRT_HD void pack_padding(FilterTri& f, FilterTri2& f2)
 {
     f = FilterTri{ 0, 0, 3.0e38f, 0, 0, 0, 0, 0 };

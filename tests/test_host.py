@@ -71,6 +71,27 @@ def test_prepack_exact_constants(srtlib, oracle, dragon):
     assert pk["unfilterable"] == 0 and pk["n_padded"] == len(dragon) + len(dragon) % 2
 
 
+@pytest.mark.parametrize("size,scale", [(128, 1.0), (2048, 1.0), (640, 3000.0), (640, 1e-4)])
+def test_level0_records_fit_binary16(srtlib, dragon, size, scale):
+    """The level-0 record is scaled by a power of two so the kernel can step it in binary16: |D| + margin <= 2^13 over
+    the frame, 7|bx| stays finite, and word 7 holds the round-to-nearest-even binary16 copies of the x-slopes."""
+    tri = (dragon * np.float32(scale)).astype(np.float32)
+    lo, hi = srtlib.scene_bbox([(tri, 0.1)])
+    cam = srtlib.camera_from_bbox(lo, hi, size, size)
+    pk = srtlib.debug_prepack(tri, cam)
+    assert pk["unfilterable"] == 0
+    f = pk["filt"][:len(tri)].astype(np.float64)
+    half = size / 2.0
+    dmax = np.abs(f[:, 3]) * half + np.abs(f[:, 4]) * half + np.abs(f[:, 5])
+    assert (dmax + f[:, 6] <= 8192.0 * (1 + 1e-6)).all() and (np.abs(f[:, 0]) <= 4100.0).all()
+    assert (dmax + f[:, 6] > 1000.0).mean() > 0.9                  # ... and uses the binary16 range (no needless underflow)
+    w = np.ascontiguousarray(pk["filt"][:len(tri), 7]).view(np.uint32)
+    lo16, hi16 = (w & 0xffff).astype(np.uint16).view(np.float16), (w >> 16).astype(np.uint16).view(np.float16)
+    assert (lo16 == pk["filt"][:len(tri), 0].astype(np.float16)).all()
+    assert (hi16 == pk["filt"][:len(tri), 3].astype(np.float16)).all()
+    assert np.isfinite(lo16.astype(np.float32)).all() and np.isfinite(hi16.astype(np.float32)).all()
+
+
 @pytest.mark.parametrize("size", [48, 96])
 def test_filter_never_rejects_a_hit_dragon(srtlib, oracle, dragon, size):
     """CPU emulation of the kernel's FFMA filter vs the oracle for every (pixel, triangle) pair."""
