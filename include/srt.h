@@ -93,8 +93,11 @@ typedef enum {
     SRT_KERNEL_AUTO = 0,        /* filtered kernel, falling back to exact when it cannot apply        */
     SRT_KERNEL_EXACT = 1,       /* every (ray, triangle) pair runs the reference op sequence          */
     SRT_KERNEL_FILTERED = 2,    /* conservative affine reject per pair + exact test for survivors     */
-    SRT_KERNEL_AUDIT = 3        /* diagnostic: exact kernel that also evaluates the filter for every
+    SRT_KERNEL_AUDIT = 3,       /* diagnostic: exact kernel that also evaluates the filter for every
                                    pair and counts (filter rejects && exact hits) -- must stay 0      */
+    SRT_KERNEL_CULLED = 4       /* the same conservative filter applied hierarchically (image bins, CTA
+                                   tiles, pixel runs) before the per-pair tests: identical hit set and
+                                   summation order, the accelerated path the LBVH option stands for   */
 } srt_kernel;
 
 #define SRT_FLAG_ALL_MESHES_CONTRIBUTE 1u  /* default off: only mesh 0 adds path length (lbuffer.cxx:788) */

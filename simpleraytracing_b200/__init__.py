@@ -8,7 +8,8 @@ by the tests and by ``bench.py``; it performs no computation and has no CPU fall
 the library is missing it raises.
 """
 from .capi import (Library, Context, Camera, MeshDesc, Params, Timing, SrtError, load_library,
-                   KERNEL_AUTO, KERNEL_EXACT, KERNEL_FILTERED, KERNEL_AUDIT, FLAG_ALL_MESHES_CONTRIBUTE)
+                   KERNEL_AUTO, KERNEL_EXACT, KERNEL_FILTERED, KERNEL_AUDIT, KERNEL_CULLED,
+                   FLAG_ALL_MESHES_CONTRIBUTE)
 
 __all__ = ["Library", "Context", "Camera", "MeshDesc", "Params", "Timing", "SrtError", "load_library",
-           "KERNEL_AUTO", "KERNEL_EXACT", "KERNEL_FILTERED", "KERNEL_AUDIT", "FLAG_ALL_MESHES_CONTRIBUTE"]
+           "KERNEL_AUTO", "KERNEL_EXACT", "KERNEL_FILTERED", "KERNEL_AUDIT", "KERNEL_CULLED", "FLAG_ALL_MESHES_CONTRIBUTE"]

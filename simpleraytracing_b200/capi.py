@@ -7,7 +7,7 @@ import numpy as np
 PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "lib" / "libsrt_b200.so"
 
-KERNEL_AUTO, KERNEL_EXACT, KERNEL_FILTERED, KERNEL_AUDIT = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_EXACT, KERNEL_FILTERED, KERNEL_AUDIT, KERNEL_CULLED = 0, 1, 2, 3, 4
 FLAG_ALL_MESHES_CONTRIBUTE = 1
 
 

@@ -627,6 +627,236 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
     if (a.hits) a.hits[p] = hits0;
 }
 
+// ------------------------------------------------------------------ culled kernels
+// SRT_KERNEL_CULLED: the same conservative strip tests, applied hierarchically.  A pixel p inside an axis-aligned box
+// of pixel centres (centre (xc, yc), half extents hx, hy) has |Y(p)| >= |Y(c)| - r_Y and |D(p)| <= |D(c)| + r_D with
+// r = |beta| hx + |gamma| hy, so "no pixel of the box can pass strip i" follows from
+//     |Y_i(c)| - |D(c)| > r_Yi + r_D + 2 m_i
+// (m_i already bounds the float evaluation error at every point of the frame -- twice: once for the pixel, once for
+// the box centre, which is always inside the frame because boxes are clamped to it; the factor kBoxInflate covers the
+// roundings of the radius sum itself).  Three levels use it: bin (256 x 128 pixels, one thread per triangle, ordered
+// compaction into per-bin index lists), CTA tile (64 x 16, one thread per listed triangle, ordered compaction into
+// shared memory) and the thread's run of 8 pixels; survivors of all three take the per-pixel tests and the exact
+// reference sequence exactly like the slow path of the filtered kernel -- in ascending triangle order per pixel, so
+// the float sums are bit-identical.  Every (pixel, triangle) pair is still decided by the same proven-conservative
+// filter or the exact test; none is skipped on a heuristic.
+constexpr float kBoxInflate = 1.0000038f;      // 1 + 2^-18
+
+__device__ __forceinline__ bool box_may_hit(const float4 fa, const float4 fb, const float4 ga, const float4 gb,
+                                            float xc, float yc, float hx, float hy)
+{
+    const float Dc = fabsf(fmaf(fa.w, xc, fmaf(fb.x, yc, fb.y)));
+    const float rD = fmaf(fabsf(fa.w), hx, fabsf(fb.x) * hy);
+    const float Y1 = fabsf(fmaf(fa.x, xc, fmaf(fa.y, yc, fa.z)));
+    const float Y2 = fabsf(fmaf(ga.x, xc, fmaf(ga.y, yc, ga.z)));
+    const float Y3 = fabsf(fmaf(gb.x, xc, fmaf(gb.y, yc, gb.z)));
+    const float s1 = fmaf(fabsf(fa.x), hx, fmaf(fabsf(fa.y), hy, fmaf(2.0f, fb.z, rD))) * kBoxInflate;
+    const float s2 = fmaf(fabsf(ga.x), hx, fmaf(fabsf(ga.y), hy, fmaf(2.0f, ga.w, rD))) * kBoxInflate;
+    const float s3 = fmaf(fabsf(gb.x), hx, fmaf(fabsf(gb.y), hy, fmaf(2.0f, gb.w, rD))) * kBoxInflate;
+    return !(Y1 - Dc > s1) && !(Y2 - Dc > s2) && !(Y3 - Dc > s3);          // NaN survives
+}
+
+// Bin pass: one CTA per (bin, mesh); thread t of iteration i tests triangle 1024 i + t; survivors are appended in
+// ascending triangle order (ballot + warp-count scan).
+constexpr uint32_t kBinThreads = 1024;
+__global__ void __launch_bounds__(kBinThreads) bin_kernel(const __grid_constant__ RenderArgs a)
+{
+    __shared__ uint32_t warp_cnt[kBinThreads / 32];
+    const int m = (int)blockIdx.z;
+    const DevMesh M = a.meshes[m];
+    const uint32_t bin = blockIdx.y * a.bins_x + blockIdx.x;
+    uint32_t* cnt_out = a.bin_counts + (size_t)bin * a.n_meshes + m;
+    if (!M.contributes || M.n == 0) { if (threadIdx.x == 0) *cnt_out = 0; return; }
+    const uint32_t c0 = blockIdx.x * kBinCols, c1 = min(a.cam.W, c0 + kBinCols) - 1;
+    const uint32_t b0 = blockIdx.y * a.bin_blocks, b1 = min(a.n_blocks, b0 + a.bin_blocks) - 1;
+    const uint32_t r0 = a.row_begin + (b0 * a.blk_stride + a.blk_phase) * 16;
+    const uint32_t r1 = min(a.row_end, a.row_begin + (b1 * a.blk_stride + a.blk_phase) * 16 + 16) - 1;
+    const float xc = 0.5f * (float)(c0 + c1) + a.cam.xc, hx = 0.5f * (float)(c1 - c0);
+    const float yc = 0.5f * (float)(r0 + r1) + a.cam.yc, hy = 0.5f * (float)(r1 - r0);
+    uint32_t* out = a.bin_entries + (size_t)bin * a.bin_cap + M.first;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t base = 0;
+    uint32_t j = threadIdx.x;
+    float4 fa, fb, ga, gb;
+    if (j < M.n) { const float4* q = M.filt + 4 * (size_t)j; fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3); }
+    for (uint32_t j0 = 0; j0 < M.n; j0 += kBinThreads) {
+        const bool keep = j < M.n && box_may_hit(fa, fb, ga, gb, xc, yc, hx, hy);
+        const uint32_t jn = j + kBinThreads;                   // prefetch the next iteration's record
+        if (jn < M.n) { const float4* q = M.filt + 4 * (size_t)jn; fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3); }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t v = warp_cnt[lane];                           // kBinThreads / 32 == 32 warps: one count per lane
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, v, o); if ((int)lane >= o) v += u; }
+        const uint32_t total = __shfl_sync(0xffffffffu, v, 31);
+        const uint32_t before = warp ? __shfl_sync(0xffffffffu, v, (int)warp - 1) : 0u;
+        if (keep) out[base + before + __popc(bal & ((1u << lane) - 1u))] = j;
+        base += total;
+        j = jn;
+        __syncthreads();                                       // warp_cnt is rewritten next iteration
+    }
+    if (threadIdx.x == 0) *cnt_out = base;
+}
+
+struct CulledArgs {
+    const float4* exact;
+    uint32_t first; int mode;
+    float y, run_xc, run_hx; uint32_t row, col0;
+};
+
+// One listed triangle for one thread's run of 8 pixels: run-level box test, per-pixel strips, exact sequence.
+__device__ __noinline__ void culled_process(const DevCamera& cam, const CulledArgs& s, const float4* rec, uint32_t jj,
+                                            float* dist, int* ssum, uint32_t* hits, unsigned long long& n_exact)
+{
+    constexpr int P = 8;
+    const float4 fa = rec[0], fb = rec[1], ga = rec[2], gb = rec[3];                        // shared memory
+    if (!box_may_hit(fa, fb, ga, gb, s.run_xc, s.y, s.run_hx, 0.0f)) return;
+    const float bs = fmaf(fa.y, s.y, fa.z), bd = fmaf(fb.x, s.y, fb.y);
+    const float b2 = fmaf(ga.y, s.y, ga.z), b3 = fmaf(gb.y, s.y, gb.z);
+    const float m1 = fb.z, m2 = ga.w, m3 = gb.w;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+        const float xk = (float)(s.col0 + k) + cam.xc;
+        const float Dd = fabsf(fmaf(fa.w, xk, bd));
+        const float S = fmaf(fa.x, xk, bs), X2 = fmaf(ga.x, xk, b2), X3 = fmaf(gb.x, xk, b3);
+        const bool reject = (fabsf(S) > Dd + m1) || (fabsf(X2) > Dd + m2) || (fabsf(X3) > Dd + m3);   // NaN survives
+        if (!reject) mask |= 1u << k;
+    }
+    if (mask == 0) return;
+    const float4 A = __ldg(s.exact + 4 * (size_t)jj), B = __ldg(s.exact + 4 * (size_t)jj + 1);
+    const float4 C = __ldg(s.exact + 4 * (size_t)jj + 2), Dn = __ldg(s.exact + 4 * (size_t)jj + 3);
+#pragma unroll 1
+    while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t col = s.col0 + k;
+        if (col >= cam.W) break;
+        const RayDirs r = make_ray(cam, s.row, col);
+        float tt;
+        ++n_exact;
+        if (exact_intersect(r, A, B, C, Dn.x, tt)) {
+            if (s.mode == 0) accumulate_hit(r, Dn, tt, dist[k], ssum[k], hits[k]);
+            else if (dist[k] > tt) { dist[k] = tt; ssum[k] = (int)(s.first + jj); }       // z-buffer, main-omp.cxx:656-662
+        }
+    }
+}
+
+// Render pass: CTA = 64 x 16 pixels (thread = run of 8 pixels of one row, as in the filtered kernel).
+__global__ void __launch_bounds__(128) lbuffer_culled_kernel(const __grid_constant__ RenderArgs a)
+{
+    constexpr int P = 8;
+    __shared__ float4 s_rec[4][32][4];          // per-warp segments keep the compaction warp-local and ordered
+    __shared__ uint32_t s_idx[4][32];
+    __shared__ uint32_t s_cnt[4];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t col0 = (blockIdx.x * 8 + (warp & 1) * 4 + (lane & 3)) * P;
+    const uint32_t lrow = (warp >> 1) * 8 + (lane >> 2);
+    const uint32_t row0 = a.row_begin + (blockIdx.y * a.blk_stride + a.blk_phase) * 16;
+    const uint32_t row = row0 + lrow;
+    const uint32_t orow = a.compact ? blockIdx.y * 16 + lrow : row;
+    const uint32_t W = a.cam.W;
+    const bool row_ok = row < a.row_end;
+    const bool active = row_ok && col0 < W;
+
+    // CTA tile box and this thread's run box, clamped to the frame
+    const uint32_t tc0 = blockIdx.x * 64, tc1 = min(W, tc0 + 64) - 1;
+    const uint32_t tr1 = min(a.row_end, row0 + 16) - 1;
+    const float txc = 0.5f * (float)(tc0 + tc1) + a.cam.xc, thx = 0.5f * (float)(tc1 - tc0);
+    const float tyc = 0.5f * (float)(row0 + tr1) + a.cam.yc, thy = 0.5f * (float)(tr1 - row0);
+    const uint32_t rc1 = min(W, col0 + P) - 1;
+
+    float Lval[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) Lval[k] = a.incident;
+    unsigned long long n_exact = 0;
+    float dist[P]; int ssum[P]; uint32_t hits[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) { dist[k] = INFINITY; ssum[k] = -1; hits[k] = 0; }
+
+    const uint32_t bin = (blockIdx.y / a.bin_blocks) * a.bins_x + blockIdx.x / (kBinCols / 64);
+    for (int m = 0; m < a.n_meshes; ++m) {
+        const DevMesh M = a.meshes[m];
+        if (a.mode == 0) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) { dist[k] = 0.0f; ssum[k] = 0; hits[k] = 0; }
+        }
+        if (M.contributes && M.n > 0) {
+            CulledArgs sa;
+            sa.exact = M.exact; sa.first = M.first; sa.mode = a.mode;
+            sa.y = (float)row + a.cam.yc; sa.row = row; sa.col0 = col0;
+            sa.run_xc = 0.5f * (float)(col0 + rc1) + a.cam.xc; sa.run_hx = active ? 0.5f * (float)(rc1 - col0) : 0.0f;
+            const uint32_t cnt = __ldg(a.bin_counts + (size_t)bin * a.n_meshes + m);
+            const uint32_t* list = a.bin_entries + (size_t)bin * a.bin_cap + M.first;
+            for (uint32_t i0 = 0; i0 < cnt; i0 += 128) {
+                const uint32_t i = i0 + tid;
+                bool keep = false; uint32_t idx = 0;
+                float4 fa, fb, ga, gb;
+                if (i < cnt) {
+                    idx = __ldg(list + i);
+                    const float4* q = M.filt + 4 * (size_t)idx;
+                    fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3);
+                    keep = box_may_hit(fa, fb, ga, gb, txc, tyc, thx, thy);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                // barrier: the previous chunk's segments have been consumed; OR: does any thread keep a triangle?
+                if (!__syncthreads_or(keep)) continue;
+                if (keep) {
+                    const uint32_t pos = __popc(bal & ((1u << lane) - 1u));
+                    s_rec[warp][pos][0] = fa; s_rec[warp][pos][1] = fb; s_rec[warp][pos][2] = ga; s_rec[warp][pos][3] = gb;
+                    s_idx[warp][pos] = idx;
+                }
+                if (lane == 0) s_cnt[warp] = __popc(bal);
+                __syncthreads();
+                if (active) {
+#pragma unroll 1
+                    for (uint32_t w = 0; w < 4; ++w) {
+                        const uint32_t n_w = s_cnt[w];
+#pragma unroll 1
+                        for (uint32_t q = 0; q < n_w; ++q)
+                            culled_process(a.cam, sa, &s_rec[w][q][0], s_idx[w][q], dist, ssum, hits, n_exact);
+                    }
+                }
+            }
+        }
+        if (a.mode != 0) continue;
+#pragma unroll
+        for (int k = 0; k < P; ++k) Lval[k] = attenuate(Lval[k], M.mu, dist[k], ssum[k], a.length_to_cm);
+        if (m == 0 && row_ok) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                if (col0 + k < W) {
+                    const size_t p = (size_t)orow * W + col0 + k;
+                    if (a.dist) a.dist[p] = dist[k];
+                    if (a.ssum) a.ssum[p] = ssum[k];
+                    if (a.hits) a.hits[p] = hits[k];
+                }
+            }
+        }
+    }
+    if (a.mode != 0) {
+        if (row_ok) {
+#pragma unroll
+            for (int k = 0; k < P; ++k)
+                if (col0 + k < W) { a.dist[(size_t)orow * W + col0 + k] = dist[k]; a.ssum[(size_t)orow * W + col0 + k] = ssum[k]; }
+        }
+    } else if (row_ok) {
+        float* out = a.L + (size_t)orow * W + col0;
+        if ((W & 3u) == 0 && col0 + P <= W) {
+#pragma unroll
+            for (int k = 0; k < P; k += 4)
+                *reinterpret_cast<float4*>(out + k) = make_float4(Lval[k], Lval[k + 1], Lval[k + 2], Lval[k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < P; ++k)
+                if (col0 + k < W) out[k] = Lval[k];
+        }
+    }
+    if (a.counters && n_exact) atomicAdd(a.counters, n_exact);
+}
+
 // ------------------------------------------------------------------ shade kernel
 // Shaded variant, second pass (src/main-omp.cxx:668-794): Phong shading of the closest hit, shadow ray against
 // every other triangle, area-barycentric texture lookup, clamp + truncation to 8 bits.  One thread per pixel.
@@ -978,6 +1208,16 @@ cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s
         case 8: return launch_filtered_t<8>(a, s);
         default: return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_lbuffer_culled(const RenderArgs& a, cudaStream_t s)
+{
+    if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0) return cudaSuccess;
+    bin_kernel<<<dim3(a.bins_x, a.bins_y, (unsigned)a.n_meshes), kBinThreads, 0, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    lbuffer_culled_kernel<<<dim3((a.cam.W + 63) / 64, a.n_blocks), 128, 0, s>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_resolve_hits(const RenderArgs& a, cudaStream_t s)

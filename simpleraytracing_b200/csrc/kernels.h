@@ -68,7 +68,14 @@ struct RenderArgs {
     uint2* hit_entries;      // [pixel][z_splits][hit_cap]: one sub-list per (pixel, slice), written by its only owner
     uint32_t* hit_counts;    // [pixel][z_splits]: entries appended (may exceed hit_cap: overflow -> exact recompute)
     uint32_t hit_cap;
+    // Culled kernel (SRT_KERNEL_CULLED): per-bin triangle lists.  A bin is kBinCols columns x bin_blocks 16-row blocks
+    // of this launch's grid; bin_entries[bin * bin_cap + M.first + i], i < bin_counts[bin * n_meshes + m], are the
+    // indices (within mesh m, ascending) of the triangles whose conservative footprint may touch the bin.
+    uint32_t* bin_entries;
+    uint32_t* bin_counts;
+    uint32_t bin_cap, bin_blocks, bins_x, bins_y;
 };
+constexpr uint32_t kBinCols = 256;     // bin width in pixels (4 CTA tiles of the culled kernel)
 cudaError_t launch_resolve_hits(const RenderArgs& a, cudaStream_t s);
 
 // ---- shaded variant: Phong + shadow ray + texture for the pixels of a closest-hit pass ------------------
@@ -101,6 +108,9 @@ cudaError_t launch_shade(const ShadeArgs& a, cudaStream_t s);
 cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s);
 // Filtered kernel; ppt = pixels per thread (1, 2, 4, 8).
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s);
+// Culled kernel: bin pass (every triangle against every bin of a.bins_x x a.bins_y) + render pass.  Same results
+// as the other kernels: the bins and the per-CTA cull only ever drop pairs the conservative filter proves to miss.
+cudaError_t launch_lbuffer_culled(const RenderArgs& a, cudaStream_t s);
 // Scatter gathered slots [n_parts][slot_rows][W] (block-cyclic 16-row blocks) back to image order [H][W].
 cudaError_t launch_deinterleave(const float* slots, float* frame, uint32_t W, uint32_t H, uint32_t n_parts,
                                 uint32_t slot_rows, cudaStream_t s);

@@ -83,6 +83,8 @@ struct srt_ctx {
     // hit lists for split launches (small grids)
     uint2* d_hit_entries = nullptr; uint32_t* d_hit_counts = nullptr; size_t hit_pixels_cap = 0;
     int force_z_splits = 0;              // diagnostic override: 0 = heuristic
+    // per-bin triangle lists of the culled kernel
+    uint32_t* d_bin_entries = nullptr; uint32_t* d_bin_counts = nullptr; size_t bin_entries_cap = 0, bin_counts_cap = 0;
     bool counters_pending = false, timing_pending = false;
 
     srt_timing timing{};
@@ -128,6 +130,8 @@ void free_frame(srt_ctx* c)
     c->d_L = c->d_img = c->d_dist = nullptr; c->d_ssum = nullptr; c->d_hits = nullptr; c->frame_cap = 0;
     cudaFree(c->d_hit_entries); cudaFree(c->d_hit_counts);
     c->d_hit_entries = nullptr; c->d_hit_counts = nullptr; c->hit_pixels_cap = 0;
+    cudaFree(c->d_bin_entries); cudaFree(c->d_bin_counts);
+    c->d_bin_entries = nullptr; c->d_bin_counts = nullptr; c->bin_entries_cap = 0; c->bin_counts_cap = 0;
 }
 
 int ensure_frame(srt_ctx* c, size_t pixels)
@@ -303,8 +307,35 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     const int audit = (kernel == SRT_KERNEL_AUDIT);
     if (audit) kernel = SRT_KERNEL_EXACT;
     if (kernel == SRT_KERNEL_AUTO) kernel = c->filterable ? SRT_KERNEL_FILTERED : SRT_KERNEL_EXACT;
-    if (kernel != SRT_KERNEL_EXACT && kernel != SRT_KERNEL_FILTERED)
+    if (kernel != SRT_KERNEL_EXACT && kernel != SRT_KERNEL_FILTERED && kernel != SRT_KERNEL_CULLED)
         return fail(c, SRT_ERR_INVALID, "unknown kernel selector %u", params->kernel);
+    if (kernel == SRT_KERNEL_CULLED) {
+        // Bins: 256 columns x 8 row blocks (128 rows) of a contiguous band; with block-cyclic rows the blocks of a rank
+        // are `parts` blocks apart, so a bin is one block tall.  Lists: one slot per scene triangle per bin (worst case
+        // always fits, no counting pass); above 8 GB the per-pair filtered kernel is used instead.
+        a.bin_blocks = a.blk_stride > 1 ? 1u : 8u;
+        a.bins_x = (cam.width + srt::kBinCols - 1) / srt::kBinCols;
+        a.bins_y = (a.n_blocks + a.bin_blocks - 1) / a.bin_blocks;
+        a.bin_cap = (uint32_t)c->total_tris;
+        const size_t bins = (size_t)a.bins_x * a.bins_y;
+        if (!c->filterable) kernel = SRT_KERNEL_EXACT;
+        else if (bins * c->total_tris * 4ull > (8ull << 30) || c->total_tris >= (1ull << 32)) kernel = SRT_KERNEL_FILTERED;
+        else if (bins > 0) {
+            if (bins * c->total_tris > c->bin_entries_cap) {
+                SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+                cudaFree(c->d_bin_entries); c->d_bin_entries = nullptr; c->bin_entries_cap = 0;
+                SRT_CUDA(c, cudaMalloc(&c->d_bin_entries, bins * c->total_tris * 4ull));
+                c->bin_entries_cap = bins * c->total_tris;
+            }
+            if (bins * c->n_meshes > c->bin_counts_cap) {
+                SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+                cudaFree(c->d_bin_counts); c->d_bin_counts = nullptr; c->bin_counts_cap = 0;
+                SRT_CUDA(c, cudaMalloc(&c->d_bin_counts, bins * c->n_meshes * 4ull));
+                c->bin_counts_cap = bins * c->n_meshes;
+            }
+            a.bin_entries = c->d_bin_entries; a.bin_counts = c->d_bin_counts;
+        }
+    }
 
     // Small grids (a rank's share of a multi-GPU frame): split the triangle range over grid.z and merge through
     // per-pixel hit lists, so that every SM still gets a full set of resident CTAs.
@@ -347,6 +378,8 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     if (kernel == SRT_KERNEL_FILTERED) {
         SRT_CUDA(c, srt::launch_lbuffer_filtered(a, ppt, c->stream));
         if (a.z_splits > 1) { SRT_CUDA(c, srt::launch_resolve_hits(a, c->stream)); extra_launches = 1; }
+    } else if (kernel == SRT_KERNEL_CULLED) {
+        SRT_CUDA(c, srt::launch_lbuffer_culled(a, c->stream)); extra_launches = 1;
     } else SRT_CUDA(c, srt::launch_lbuffer_exact(a, audit, c->stream));
     SRT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     c->timing.kernel_used = kernel;

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, bits
-from simpleraytracing_b200 import KERNEL_EXACT, KERNEL_FILTERED, scene
+from simpleraytracing_b200 import KERNEL_EXACT, KERNEL_FILTERED, KERNEL_CULLED, scene
 
 
 @pytest.fixture(scope="module")
@@ -52,7 +52,7 @@ def test_shaded_camera_helper(srtlib, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kernel", [KERNEL_FILTERED, KERNEL_EXACT])
+@pytest.mark.parametrize("kernel", [KERNEL_FILTERED, KERNEL_EXACT, KERNEL_CULLED])
 @pytest.mark.parametrize("name", ["logo", "noise"])
 def test_gpu_shaded_vs_reference_golden(gpu_ctx, srtlib, golden, kernel, name):
     meshes = scene.shaded_scene(texture=None if name == "logo" else scene.noise_texture())
