@@ -702,137 +702,181 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(const __grid_constant_
 struct CulledArgs {
     const float4* exact;
     uint32_t first; int mode;
-    float y, run_xc, run_hx; uint32_t row, col0;
+    float y, x0, run_xc, run_hx; uint32_t col_end;      // x0: centred x of the run's first pixel; col_end = min(W - col0, 8)
+    uint32_t wrow0, wcol0;                              // first row / column of the warp's 32 x 8 pixel tile
+    uint8_t* queue;                                     // this warp's candidate queue (256 entries)
+    float* acc;                                         // this warp's accumulators: [3][256], slot = k * 32 + lane
 };
 
-// One listed triangle for one thread's run of 8 pixels: run-level box test, per-pixel strips, exact sequence.
+// One listed triangle for one WARP (called convergently): every lane applies the run-level box test and the per-pixel
+// strip tests to its run of 8 pixels; the surviving (pixel, triangle) pairs of the whole warp are queued in shared
+// memory and the exact reference sequence is run on them with all lanes busy (a triangle typically covers most of
+// the pixels of two or three lanes: lane-serial execution would leave the warp 90 % idle).  The executing lane
+// regenerates the pixel's ray and folds the result into the pixel's accumulators in shared memory: a triangle
+// contributes at most once per pixel and triangles are processed strictly in ascending order with a warp barrier in
+// between, so every per-pixel float sum keeps the reference's order.
 __device__ __noinline__ void culled_process(const DevCamera& cam, const CulledArgs& s, const float4* rec, uint32_t jj,
-                                            float* dist, int* ssum, uint32_t* hits, unsigned long long& n_exact)
+                                            unsigned long long& n_exact)
 {
     constexpr int P = 8;
+    const uint32_t lane = threadIdx.x & 31u;
     const float4 fa = rec[0], fb = rec[1], ga = rec[2], gb = rec[3];                        // shared memory
-    if (!box_may_hit(fa, fb, ga, gb, s.run_xc, s.y, s.run_hx, 0.0f)) return;
-    const float bs = fmaf(fa.y, s.y, fa.z), bd = fmaf(fb.x, s.y, fb.y);
-    const float b2 = fmaf(ga.y, s.y, ga.z), b3 = fmaf(gb.y, s.y, gb.z);
-    const float m1 = fb.z, m2 = ga.w, m3 = gb.w;
     uint32_t mask = 0;
+    if (s.col_end && box_may_hit(fa, fb, ga, gb, s.run_xc, s.y, s.run_hx, 0.0f)) {
+        const float bs = fmaf(fa.y, s.y, fa.z), bd = fmaf(fb.x, s.y, fb.y);
+        const float b2 = fmaf(ga.y, s.y, ga.z), b3 = fmaf(gb.y, s.y, gb.z);
+        const float m1 = fb.z, m2 = ga.w, m3 = gb.w;
 #pragma unroll
-    for (int k = 0; k < P; ++k) {
-        const float xk = (float)(s.col0 + k) + cam.xc;
-        const float Dd = fabsf(fmaf(fa.w, xk, bd));
-        const float S = fmaf(fa.x, xk, bs), X2 = fmaf(ga.x, xk, b2), X3 = fmaf(gb.x, xk, b3);
-        const bool reject = (fabsf(S) > Dd + m1) || (fabsf(X2) > Dd + m2) || (fabsf(X3) > Dd + m3);   // NaN survives
-        if (!reject) mask |= 1u << k;
+        for (int k = 0; k < P; ++k) {
+            const float xk = s.x0 + (float)k;                              // exact: (half-)integers far below 2^23
+            const float Dd = fabsf(fmaf(fa.w, xk, bd));
+            const float S = fmaf(fa.x, xk, bs), X2 = fmaf(ga.x, xk, b2), X3 = fmaf(gb.x, xk, b3);
+            const bool reject = (fabsf(S) > Dd + m1) || (fabsf(X2) > Dd + m2) || (fabsf(X3) > Dd + m3);   // NaN survives
+            if (!reject) mask |= 1u << k;
+        }
+        mask &= (1u << s.col_end) - 1u;                                    // pixels beyond the last column
     }
-    if (mask == 0) return;
-    const float4 A = __ldg(s.exact + 4 * (size_t)jj), B = __ldg(s.exact + 4 * (size_t)jj + 1);
-    const float4 C = __ldg(s.exact + 4 * (size_t)jj + 2), Dn = __ldg(s.exact + 4 * (size_t)jj + 3);
-#pragma unroll 1
-    while (mask) {
-        const int k = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const uint32_t col = s.col0 + k;
-        if (col >= cam.W) break;
-        const RayDirs r = make_ray(cam, s.row, col);
+    if (!__any_sync(0xffffffffu, mask != 0)) return;
+    // queue positions: exclusive prefix of the per-lane candidate counts
+    const uint32_t mine = __popc(mask);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += u; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    {
+        uint32_t mm = mask, q = incl - mine;
+        while (mm) { const int k = __ffs(mm) - 1; mm &= mm - 1; s.queue[q++] = (uint8_t)(((uint32_t)k << 5) | lane); }
+    }
+    __syncwarp();
+    n_exact += mine;
+    const float4 A = rec[4], B = rec[5], C = rec[6], Dn = rec[7];          // ExactTri, staged with the filter record
+    for (uint32_t q = lane; q < total; q += 32) {
+        const uint32_t e = s.queue[q], owner = e & 31u, k = e >> 5;        // e is also the accumulator slot k * 32 + owner
+        const RayDirs r = make_ray(cam, s.wrow0 + (owner >> 2), s.wcol0 + (owner & 3u) * P + k);
         float tt;
-        ++n_exact;
         if (exact_intersect(r, A, B, C, Dn.x, tt)) {
-            if (s.mode == 0) accumulate_hit(r, Dn, tt, dist[k], ssum[k], hits[k]);
-            else if (dist[k] > tt) { dist[k] = tt; ssum[k] = (int)(s.first + jj); }       // z-buffer, main-omp.cxx:656-662
+            float* acc = s.acc + e;
+            if (s.mode != 0) {                                             // closest hit, strict > (main-omp.cxx:656-662)
+                if (acc[0] > tt) { acc[0] = tt; acc[256] = __int_as_float((int)(s.first + jj)); }
+            } else if ((double)tt > 0.0000001) {                           // lbuffer.cxx:788
+                const float dn = dot_rn(r.ax, r.ay, r.az, Dn.y, Dn.z, Dn.w);
+                const int sign = (0.0f < dn) - (dn < 0.0f);
+                acc[0] = __fadd_rn(acc[0], __fmul_rn((float)sign, tt));    // distance += sign * t
+                acc[256] = __int_as_float(__float_as_int(acc[256]) + sign);
+                acc[512] = __int_as_float(__float_as_int(acc[512]) + 1);
+            }
         }
     }
+    __syncwarp();                                                          // queue and accumulators: next triangle
 }
 
-// Render pass: CTA = 64 x 16 pixels (thread = run of 8 pixels of one row, as in the filtered kernel).
-__global__ void __launch_bounds__(128) lbuffer_culled_kernel(const __grid_constant__ RenderArgs a)
+// Render pass: CTA = 64 x 16 pixels, thread = run of 8 pixels of one row (as in the filtered kernel), but the four
+// warps (32 x 8 pixels each) work independently: each walks the bin's list 32 entries at a time (one listed triangle
+// per lane against the warp's tile), compacts the survivors into its own shared-memory segment and processes them;
+// there is no CTA-wide barrier, so a warp over empty space does not wait for a warp over the object.
+#ifndef SRT_CULLED_MIN_CTAS
+#define SRT_CULLED_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kernel(const __grid_constant__ RenderArgs a)
 {
     constexpr int P = 8;
-    __shared__ float4 s_rec[4][32][4];          // per-warp segments keep the compaction warp-local and ordered
+    __shared__ float4 s_rec[4][32][8];          // per-warp survivors: filter record (4 x float4) + ExactTri (4 x float4)
     __shared__ uint32_t s_idx[4][32];
-    __shared__ uint32_t s_cnt[4];
+    __shared__ float s_acc[4][3 * 256];         // per-warp accumulators: dist | ssum | hits (z | id in closest-hit mode)
+    __shared__ uint8_t s_queue[4][256];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t col0 = (blockIdx.x * 8 + (warp & 1) * 4 + (lane & 3)) * P;
-    const uint32_t lrow = (warp >> 1) * 8 + (lane >> 2);
+    const uint32_t wcol0 = (blockIdx.x * 8 + (warp & 1) * 4) * P;
+    const uint32_t col0 = wcol0 + (lane & 3) * P;
     const uint32_t row0 = a.row_begin + (blockIdx.y * a.blk_stride + a.blk_phase) * 16;
-    const uint32_t row = row0 + lrow;
-    const uint32_t orow = a.compact ? blockIdx.y * 16 + lrow : row;
+    const uint32_t wrow0 = row0 + (warp >> 1) * 8;
+    const uint32_t row = wrow0 + (lane >> 2);
+    const uint32_t orow = a.compact ? blockIdx.y * 16 + (warp >> 1) * 8 + (lane >> 2) : row;
     const uint32_t W = a.cam.W;
     const bool row_ok = row < a.row_end;
     const bool active = row_ok && col0 < W;
+    const bool warp_on = wrow0 < a.row_end && wcol0 < W;       // warp-uniform: the warp's tile has pixels
 
-    // CTA tile box and this thread's run box, clamped to the frame
-    const uint32_t tc0 = blockIdx.x * 64, tc1 = min(W, tc0 + 64) - 1;
-    const uint32_t tr1 = min(a.row_end, row0 + 16) - 1;
-    const float txc = 0.5f * (float)(tc0 + tc1) + a.cam.xc, thx = 0.5f * (float)(tc1 - tc0);
-    const float tyc = 0.5f * (float)(row0 + tr1) + a.cam.yc, thy = 0.5f * (float)(tr1 - row0);
+    // warp tile box and this thread's run box, clamped to the frame
+    const uint32_t tc1 = min(W, wcol0 + 32) - 1, tr1 = min(a.row_end, wrow0 + 8) - 1;
+    const float txc = 0.5f * (float)(wcol0 + tc1) + a.cam.xc, thx = 0.5f * (float)(tc1 - wcol0);
+    const float tyc = 0.5f * (float)(wrow0 + tr1) + a.cam.yc, thy = 0.5f * (float)(tr1 - wrow0);
     const uint32_t rc1 = min(W, col0 + P) - 1;
 
     float Lval[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) Lval[k] = a.incident;
     unsigned long long n_exact = 0;
-    float dist[P]; int ssum[P]; uint32_t hits[P];
+    float* acc = s_acc[warp];
+    if (a.mode != 0) {
 #pragma unroll
-    for (int k = 0; k < P; ++k) { dist[k] = INFINITY; ssum[k] = -1; hits[k] = 0; }
+        for (int k = 0; k < P; ++k) { acc[k * 32 + lane] = INFINITY; acc[256 + k * 32 + lane] = __int_as_float(-1); }
+    }
 
     const uint32_t bin = (blockIdx.y / a.bin_blocks) * a.bins_x + blockIdx.x / (kBinCols / 64);
     for (int m = 0; m < a.n_meshes; ++m) {
         const DevMesh M = a.meshes[m];
         if (a.mode == 0) {
 #pragma unroll
-            for (int k = 0; k < P; ++k) { dist[k] = 0.0f; ssum[k] = 0; hits[k] = 0; }
+            for (int k = 0; k < P; ++k) { acc[k * 32 + lane] = 0.0f; acc[256 + k * 32 + lane] = 0.0f; acc[512 + k * 32 + lane] = 0.0f; }
         }
-        if (M.contributes && M.n > 0) {
+        __syncwarp();
+        if (M.contributes && M.n > 0 && warp_on) {
             CulledArgs sa;
             sa.exact = M.exact; sa.first = M.first; sa.mode = a.mode;
-            sa.y = (float)row + a.cam.yc; sa.row = row; sa.col0 = col0;
+            sa.y = (float)row + a.cam.yc; sa.x0 = (float)col0 + a.cam.xc;
+            sa.queue = s_queue[warp]; sa.acc = acc; sa.wrow0 = wrow0; sa.wcol0 = wcol0;
+            sa.col_end = active ? rc1 - col0 + 1 : 0u;
             sa.run_xc = 0.5f * (float)(col0 + rc1) + a.cam.xc; sa.run_hx = active ? 0.5f * (float)(rc1 - col0) : 0.0f;
             const uint32_t cnt = __ldg(a.bin_counts + (size_t)bin * a.n_meshes + m);
             const uint32_t* list = a.bin_entries + (size_t)bin * a.bin_cap + M.first;
-            for (uint32_t i0 = 0; i0 < cnt; i0 += 128) {
-                const uint32_t i = i0 + tid;
-                bool keep = false; uint32_t idx = 0;
-                float4 fa, fb, ga, gb;
-                if (i < cnt) {
-                    idx = __ldg(list + i);
-                    const float4* q = M.filt + 4 * (size_t)idx;
-                    fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3);
-                    keep = box_may_hit(fa, fb, ga, gb, txc, tyc, thx, thy);
-                }
+            // software pipeline: the next 32 entries' records are in flight while the current ones are processed
+            uint32_t idx = 0; float4 fa, fb, ga, gb;
+            if (lane < cnt) {
+                idx = __ldg(list + lane);
+                const float4* q = M.filt + 4 * (size_t)idx;
+                fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3);
+            }
+            for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
+                const bool keep = i0 + lane < cnt && box_may_hit(fa, fb, ga, gb, txc, tyc, thx, thy);
                 const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                // barrier: the previous chunk's segments have been consumed; OR: does any thread keep a triangle?
-                if (!__syncthreads_or(keep)) continue;
                 if (keep) {
                     const uint32_t pos = __popc(bal & ((1u << lane) - 1u));
-                    s_rec[warp][pos][0] = fa; s_rec[warp][pos][1] = fb; s_rec[warp][pos][2] = ga; s_rec[warp][pos][3] = gb;
+                    const float4* eq = M.exact + 4 * (size_t)idx;          // the exact constants travel with the survivor
+                    const float4 e0 = __ldg(eq), e1 = __ldg(eq + 1), e2 = __ldg(eq + 2), e3 = __ldg(eq + 3);
+                    float4* dst = &s_rec[warp][pos][0];
+                    dst[0] = fa; dst[1] = fb; dst[2] = ga; dst[3] = gb; dst[4] = e0; dst[5] = e1; dst[6] = e2; dst[7] = e3;
                     s_idx[warp][pos] = idx;
                 }
-                if (lane == 0) s_cnt[warp] = __popc(bal);
-                __syncthreads();
-                if (active) {
-#pragma unroll 1
-                    for (uint32_t w = 0; w < 4; ++w) {
-                        const uint32_t n_w = s_cnt[w];
-#pragma unroll 1
-                        for (uint32_t q = 0; q < n_w; ++q)
-                            culled_process(a.cam, sa, &s_rec[w][q][0], s_idx[w][q], dist, ssum, hits, n_exact);
-                    }
+                const uint32_t in = i0 + 32 + lane;
+                if (in < cnt) {
+                    idx = __ldg(list + in);
+                    const float4* q = M.filt + 4 * (size_t)idx;
+                    fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3);
                 }
+                if (bal == 0) continue;
+                __syncwarp();
+                const uint32_t n_w = __popc(bal);
+#pragma unroll 1
+                for (uint32_t q = 0; q < n_w; ++q)
+                    culled_process(a.cam, sa, &s_rec[warp][q][0], s_idx[warp][q], n_exact);
+                __syncwarp();                                  // the segment is rewritten by the next chunk
             }
         }
         if (a.mode != 0) continue;
+        const bool out_ok = m == 0 && row_ok;
+        const bool plain = isfinite(M.mu) && isfinite(a.length_to_cm);     // else 0 * inf = NaN must reach exp()
 #pragma unroll
-        for (int k = 0; k < P; ++k) Lval[k] = attenuate(Lval[k], M.mu, dist[k], ssum[k], a.length_to_cm);
-        if (m == 0 && row_ok) {
-#pragma unroll
-            for (int k = 0; k < P; ++k) {
-                if (col0 + k < W) {
-                    const size_t p = (size_t)orow * W + col0 + k;
-                    if (a.dist) a.dist[p] = dist[k];
-                    if (a.ssum) a.ssum[p] = ssum[k];
-                    if (a.hits) a.hits[p] = hits[k];
-                }
+        for (int k = 0; k < P; ++k) {
+            const float dist = acc[k * 32 + lane];
+            const int ssum = __float_as_int(acc[256 + k * 32 + lane]);
+            // exp(-(mu * (0 * 0.1))) == 1 exactly: pixels the mesh does not touch keep their value bit for bit
+            if (dist != 0.0f || ssum != 0 || !plain) Lval[k] = attenuate(Lval[k], M.mu, dist, ssum, a.length_to_cm);
+            if (out_ok && col0 + k < W) {
+                const size_t p = (size_t)orow * W + col0 + k;
+                if (a.dist) a.dist[p] = dist;
+                if (a.ssum) a.ssum[p] = ssum;
+                if (a.hits) a.hits[p] = (uint32_t)__float_as_int(acc[512 + k * 32 + lane]);
             }
         }
     }
@@ -840,7 +884,10 @@ __global__ void __launch_bounds__(128) lbuffer_culled_kernel(const __grid_consta
         if (row_ok) {
 #pragma unroll
             for (int k = 0; k < P; ++k)
-                if (col0 + k < W) { a.dist[(size_t)orow * W + col0 + k] = dist[k]; a.ssum[(size_t)orow * W + col0 + k] = ssum[k]; }
+                if (col0 + k < W) {
+                    a.dist[(size_t)orow * W + col0 + k] = acc[k * 32 + lane];
+                    a.ssum[(size_t)orow * W + col0 + k] = __float_as_int(acc[256 + k * 32 + lane]);
+                }
         }
     } else if (row_ok) {
         float* out = a.L + (size_t)orow * W + col0;
