@@ -40,14 +40,6 @@ typedef struct {
 static _Float16 h_from_bits(uint16_t b) { _Float16 h; memcpy(&h, &b, 2); return h; }
 static _Float16 h_fma(_Float16 a, _Float16 b, _Float16 c) { return (_Float16)((long double)a * (long double)b + (long double)c); }
 static _Float16 h_abs(_Float16 a) { return a < 0 ? -a : a; }
-/* float -> binary16 rounded toward -inf (cvt.rd.f16.f32) */
-static _Float16 h_round_down(float v)
-{
-    _Float16 h = (_Float16)v;
-    if ((float)h > v) { uint16_t b; memcpy(&b, &h, 2); b = (b & 0x8000u) ? (uint16_t)(b + 1) : (b ? (uint16_t)(b - 1) : 0x8001u); memcpy(&h, &b, 2); }
-    return h;
-}
-
 __attribute__((target("fma"))) static void* audit_worker(void* arg)
 {
     audit_job* j = (audit_job*)arg;
@@ -71,9 +63,10 @@ __attribute__((target("fma"))) static void* audit_worker(void* arg)
             const float x0 = (float)(col & ~7u) + xc;
             const _Float16 hk = (_Float16)(float)(col & 7u);
             const _Float16 Y16 = h_fma(h_from_bits((uint16_t)(hw & 0xffffu)), hk, (_Float16)__builtin_fmaf(f[0], x0, __builtin_fmaf(f[1], y, f[2])));
-            const _Float16 D16 = h_fma(h_from_bits((uint16_t)(hw >> 16)), hk, (_Float16)__builtin_fmaf(f[3], x0, __builtin_fmaf(f[4], y, f[5])));
-            const _Float16 t16 = (_Float16)((long double)h_abs(D16) - (long double)h_abs(Y16));
-            const int gate16 = !(t16 < h_round_down(-tm));
+            /* |D| over the run is bounded by its end-point values; tau = max|D| * (1 + 2^-10) + m, rounded to nearest */
+            const float fd0 = __builtin_fmaf(f[3], x0, __builtin_fmaf(f[4], y, f[5])), fd7 = __builtin_fmaf(f[3], 7.0f, fd0);
+            const _Float16 tau = (_Float16)__builtin_fmaf(fmaxf(fabsf(fd0), fabsf(fd7)), 1.0009765625f, f[6]);
+            const int gate16 = !(h_abs(Y16) > tau);
             /* odd pixels-per-thread: the binary32 gate */
             const int gate32 = (fabsf(Dd) - fabsf(X1)) >= -tm;
             const int s0t = gate16 && gate32;

@@ -24,6 +24,8 @@ namespace srt {
 namespace {
 
 // ------------------------------------------------------------------ helpers
+constexpr float kTauInflate = 1.0009765625f;     // 1 + 2^-10: tau is rounded to NEAREST binary16 (<= 2^-11 down) and must not shrink
+
 struct RayDirs { float ax, ay, az, bx, by, bz; };   // dirA: sign test; dirB: Ray::m_direction
 
 __device__ __forceinline__ float dot_rn(float ax, float ay, float az, float bx, float by, float bz)
@@ -167,14 +169,15 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
                     const float Dd = fmaf(fa.w, x, fmaf(fb.x, y, fb.y));
                     const float X2 = fmaf(ga.x, x, fmaf(ga.y, y, ga.z));
                     const float X3 = fmaf(gb.x, x, fmaf(gb.y, y, gb.z));
-                    // level-0 gate of the filtered kernel (8 pixels per thread): binary32 value at the first pixel
-                    // of the aligned run, one binary16 FMA step to this pixel, tile margin rounded up to binary16
+                    // level-0 gate of the filtered kernel (8 pixels per thread): binary32 Y at the first pixel of the
+                    // aligned run, one binary16 FMA step to this pixel; |D| bounded by its two end-point values
                     const float x0 = (float)(col & ~7u) + a.cam.xc;
                     const __half hk = __int2half_rn((int)(col & 7u));
                     const __half2 hs = *reinterpret_cast<const __half2*>(&fb.w);
                     const __half Y16 = __hfma(__low2half(hs), hk, __float2half_rn(fmaf(fa.x, x0, fmaf(fa.y, y, fa.z))));
-                    const __half D16 = __hfma(__high2half(hs), hk, __float2half_rn(fmaf(fa.w, x0, fmaf(fb.x, y, fb.y))));
-                    const bool gate = __hlt(__hsub(__habs(D16), __habs(Y16)), __float2half_rd(-tm));
+                    const float fd0 = fmaf(fa.w, x0, fmaf(fb.x, y, fb.y)), fd7 = fmaf(fa.w, 7.0f, fd0);
+                    const __half tau = __float2half_rn(fmaf(fmaxf(fabsf(fd0), fabsf(fd7)), kTauInflate, fb.z));
+                    const bool gate = __hgt(__habs(Y16), tau);
                     const bool reject = gate || !(fabsf(Dd) - fabsf(X1) >= -tm) || (fabsf(X1) > fabsf(Dd) + fb.z) ||  // level 0
                                         (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);         // level 1
                     if (reject && hit) ++n_viol;
@@ -223,14 +226,16 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 constexpr int kGroupUnroll = SRT_GROUP_UNROLL;   // groups per trip of the hot loop: unrolling removes the register rotation of the prefetch and loop overhead (14.8 -> 13.8 ms)
 
 // Level-0 state of one group (kGroupTris = 2 triangles) for one thread's run of P pixels.
-//  * even P: Y and D at the run's first pixel in binary32, rounded to binary16 and stepped along the run with
-//    HFMA2 -- two pixels per instruction; the |D| - |Y| values are folded with 3-input packed max (VHMNMX).
-//    The error of the binary16 steps is part of the record's margin (prepack_math.h, pack_triangle).
+//  * even P: Y at the run's first pixel in binary32, rounded to binary16 and stepped along the run with HFMA2 -- two
+//    pixels per instruction; |D| is bounded over the run by its value at the two end points (|affine| is convex), so
+//    the gate is  min_k |Y16(k)| <= tau,  tau = max(|D(x0)|, |D(x_last)|) + m  in binary32, rounded up to binary16:
+//    per triangle 4 HFMA2 + 2 packed min with |.| modifiers + 1 packed compare for 8 pixels.  The error of the
+//    binary16 steps is part of the record's margin (prepack_math.h, pack_triangle).
 //  * odd P: the binary32 evaluation (2 FFMA + FADD + 1/2 FMNMX3 per pair).
 template <int P>
 struct Level0 {
     static constexpr bool kHalf = (P & 1) == 0;
-    // kHalf: Y0/D0/Y1/D1 as half2 bits + slope words; else: bx, bd, base-y, base-d per triangle
+    // kHalf: per triangle {Y0 as half2, tau as half2, slope word}; else: bx, bd, base-y, base-d per triangle
     float v[kHalf ? 6 : 8];
 
     __device__ __forceinline__ void load(const float4* q, float x0, float y)
@@ -239,8 +244,11 @@ struct Level0 {
         if constexpr (kHalf) {
             const float fy0 = fmaf(a0.x, x0, fmaf(a0.y, y, a0.z)), fd0 = fmaf(a0.w, x0, fmaf(b0.x, y, b0.y));
             const float fy1 = fmaf(a1.x, x0, fmaf(a1.y, y, a1.z)), fd1 = fmaf(a1.w, x0, fmaf(b1.x, y, b1.y));
-            put(0, __floats2half2_rn(fy0, fy0)); put(1, __floats2half2_rn(fd0, fd0));
-            put(2, __floats2half2_rn(fy1, fy1)); put(3, __floats2half2_rn(fd1, fd1));
+            const float fe0 = fmaf(a0.w, (float)(P - 1), fd0), fe1 = fmaf(a1.w, (float)(P - 1), fd1);   // D at the last pixel
+            const float t0 = fmaf(fmaxf(fabsf(fd0), fabsf(fe0)), kTauInflate, b0.z);
+            const float t1 = fmaf(fmaxf(fabsf(fd1), fabsf(fe1)), kTauInflate, b1.z);
+            put(0, __floats2half2_rn(fy0, fy0)); put(1, __floats2half2_rn(t0, t0));
+            put(2, __floats2half2_rn(fy1, fy1)); put(3, __floats2half2_rn(t1, t1));
             v[4] = b0.w; v[5] = b1.w;
         } else {
             v[0] = a0.x; v[1] = a0.w; v[2] = fmaf(a0.y, y, a0.z); v[3] = fmaf(b0.x, y, b0.y);
@@ -251,21 +259,21 @@ struct Level0 {
     __device__ __forceinline__ __half2 get(int i) const { return *reinterpret_cast<const __half2*>(&v[i]); }
 
     // may any pixel of the run be inside the level-0 strip of either triangle?
-    __device__ __forceinline__ bool survives(const float (&x)[P], float negM, __half2 negM2) const
+    __device__ __forceinline__ bool survives(const float (&x)[P], float negM) const
     {
         if constexpr (kHalf) {
-            const __half2 Y0 = get(0), D0 = get(1), Y1 = get(2), D1 = get(3);
-            const __half2 sy0 = __low2half2(get(4)), sd0 = __high2half2(get(4));
-            const __half2 sy1 = __low2half2(get(5)), sd1 = __high2half2(get(5));
-            __half2 acc = __half2half2(__ushort_as_half((unsigned short)0xfc00u));         // -inf
+            const __half2 Y0 = get(0), T0 = get(1), Y1 = get(2), T1 = get(3);
+            const __half2 sy0 = __low2half2(get(4)), sy1 = __low2half2(get(5));
+            __half2 m0, m1;
 #pragma unroll
             for (int k = 0; k < P; k += 2) {
                 const __half2 dx = __floats2half2_rn((float)k, (float)(k + 1));
-                const __half2 t0 = __hsub2(__habs2(__hfma2(sd0, dx, D0)), __habs2(__hfma2(sy0, dx, Y0)));
-                const __half2 t1 = __hsub2(__habs2(__hfma2(sd1, dx, D1)), __habs2(__hfma2(sy1, dx, Y1)));
-                acc = __hmax2(acc, __hmax2(t0, t1));
+                const __half2 u0 = __habs2(__hfma2(sy0, dx, Y0)), u1 = __habs2(__hfma2(sy1, dx, Y1));
+                m0 = k ? __hmin2(m0, u0) : u0;
+                m1 = k ? __hmin2(m1, u1) : u1;
             }
-            return !__hblt2(acc, negM2);                       // some |D| - |Y| >= -margin (a NaN survives)
+            // some |Y| <= tau in either triangle; +-inf from a binary16 overflow of Y is a (correct) reject
+            return !__hbgt2(m0, T0) || !__hbgt2(m1, T1);
         } else {
             float acc0 = -FLT_MAX, acc1 = -FLT_MAX;
 #pragma unroll
@@ -449,7 +457,6 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
                 const float4* tp = tiles + (size_t)stage * kTileTris * 4;
                 const uint32_t cnt = min(kTileTris, M.n_padded - t * kTileTris);    // multiple of kGroupTris
                 const float negM = -__ldg(M.tile_m + t);
-                const __half2 negM2 = __half2half2(__float2half_rd(negM));     // margin rounded up to binary16
                 const uint32_t jbase = t * kTileTris;
 
                 bool pend = false;             // may the previous group have a survivor in this lane?
@@ -461,7 +468,7 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
                     // loads and per-thread base values are off the critical path of the current group
                     Level0<P> nxt;
                     nxt.load(tp + 4 * (j + kGroupTris), x[0], y);
-                    const bool surv = cur.survives(x, negM, negM2);
+                    const bool surv = cur.survives(x, negM);
                     // resolve the PREVIOUS group now: its predicate has been ready for a whole iteration
                     if (__any_sync(0xffffffffu, pend))
                         filtered_slow_path<P, SPLIT>(a.cam, sa, tp + 4 * (j - kGroupTris), jbase + j - kGroupTris, dist, ssum, hits, n_exact);

@@ -48,7 +48,8 @@ struct ExactTri {
 // (D = LAMBDA * det, see pack_triangle).  A pair can only be a hit when |Y| <= |D| + m
 // (<=> 0 <= X / det <= 1 up to rounding).  The record is scaled by a per-triangle power of two so
 // that the render kernel can step Y and D along a pixel run in binary16 (HFMA2, two pixels per
-// instruction) from a binary32 value at the run's first pixel; h holds the binary16 x-slopes.
+// instruction) from a binary32 value at the run's first pixel; h holds the binary16 x-slopes (the kernel steps
+// only Y and bounds |D| over the run by its end-point values; the D slope is kept for diagnostics).
 struct FilterTri {
     float bx, gx, ax, bd;
     float gd, ad, m;
@@ -266,7 +267,8 @@ SRT_HD bool pack_triangle(const float* v, const float* normal_or_null, const flo
                 if (sc > lim) sc *= 0.5;                        // log2 rounding at an exact power of two
             }
         }
-        const double M16 = sc * M0 + H_ABS + TINY;
+        // (1 + 2^-9): the kernel forms tau = max|D| * (1 + 2^-10) + m in binary32 and rounds it to NEAREST binary16
+        const double M16 = (sc * M0 + H_ABS + TINY) * 1.001953125;
         ok = std::isfinite(m0) && std::isfinite(m1) && std::isfinite(m2) && sc * m0 < LIM && sc * m1 < LIM && sc * m2 < LIM &&
              sc * S.absmax < LIM && sc * Dn.absmax < LIM && sc * Vn.absmax < LIM && sc * Wn.absmax < LIM &&
              sc * (Dn.absmax + M0) <= 8192.0 && sc * std::fabs(s0.b) <= 4100.0;
