@@ -90,7 +90,7 @@ typedef struct {
 } srt_light;
 
 typedef enum {
-    SRT_KERNEL_AUTO = 0,        /* filtered kernel, falling back to exact when it cannot apply        */
+    SRT_KERNEL_AUTO = 0,        /* fastest applicable: culled, else filtered, else exact (same results) */
     SRT_KERNEL_EXACT = 1,       /* every (ray, triangle) pair runs the reference op sequence          */
     SRT_KERNEL_FILTERED = 2,    /* conservative affine reject per pair + exact test for survivors     */
     SRT_KERNEL_AUDIT = 3,       /* diagnostic: exact kernel that also evaluates the filter for every

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 // Triangle order per pixel is preserved: pending groups are resolved strictly in order.
 
 #ifndef SRT_GROUP_UNROLL
-#define SRT_GROUP_UNROLL 4
+#define SRT_GROUP_UNROLL 2
 #endif
 constexpr int kGroupUnroll = SRT_GROUP_UNROLL;   // groups per trip of the hot loop: unrolling removes the register rotation of the prefetch and loop overhead (14.8 -> 13.8 ms)
 
@@ -235,8 +235,8 @@ constexpr int kGroupUnroll = SRT_GROUP_UNROLL;   // groups per trip of the hot l
 template <int P>
 struct Level0 {
     static constexpr bool kHalf = (P & 1) == 0;
-    // kHalf: per triangle {Y0 as half2, tau as half2, slope word}; else: bx, bd, base-y, base-d per triangle
-    float v[kHalf ? 6 : 8];
+    // kHalf: per triangle {(Y0, tau) as half2, slope word}; else: bx, bd, base-y, base-d per triangle
+    float v[kHalf ? 4 : 8];
 
     __device__ __forceinline__ void load(const float4* q, float x0, float y)
     {
@@ -247,9 +247,8 @@ struct Level0 {
             const float fe0 = fmaf(a0.w, (float)(P - 1), fd0), fe1 = fmaf(a1.w, (float)(P - 1), fd1);   // D at the last pixel
             const float t0 = fmaf(fmaxf(fabsf(fd0), fabsf(fe0)), kTauInflate, b0.z);
             const float t1 = fmaf(fmaxf(fabsf(fd1), fabsf(fe1)), kTauInflate, b1.z);
-            put(0, __floats2half2_rn(fy0, fy0)); put(1, __floats2half2_rn(t0, t0));
-            put(2, __floats2half2_rn(fy1, fy1)); put(3, __floats2half2_rn(t1, t1));
-            v[4] = b0.w; v[5] = b1.w;
+            put(0, __floats2half2_rn(fy0, t0)); put(1, __floats2half2_rn(fy1, t1));      // one pack per triangle: (Y0, tau)
+            v[2] = b0.w; v[3] = b1.w;
         } else {
             v[0] = a0.x; v[1] = a0.w; v[2] = fmaf(a0.y, y, a0.z); v[3] = fmaf(b0.x, y, b0.y);
             v[4] = a1.x; v[5] = a1.w; v[6] = fmaf(a1.y, y, a1.z); v[7] = fmaf(b1.x, y, b1.y);
@@ -262,8 +261,8 @@ struct Level0 {
     __device__ __forceinline__ bool survives(const float (&x)[P], float negM) const
     {
         if constexpr (kHalf) {
-            const __half2 Y0 = get(0), T0 = get(1), Y1 = get(2), T1 = get(3);
-            const __half2 sy0 = __low2half2(get(4)), sy1 = __low2half2(get(5));
+            const __half2 Y0 = __low2half2(get(0)), T0 = __high2half2(get(0)), Y1 = __low2half2(get(1)), T1 = __high2half2(get(1));
+            const __half2 sy0 = __low2half2(get(2)), sy1 = __low2half2(get(3));
             __half2 m0, m1;
 #pragma unroll
             for (int k = 0; k < P; k += 2) {

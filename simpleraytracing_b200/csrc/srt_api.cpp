@@ -306,7 +306,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     uint32_t kernel = params->kernel;
     const int audit = (kernel == SRT_KERNEL_AUDIT);
     if (audit) kernel = SRT_KERNEL_EXACT;
-    if (kernel == SRT_KERNEL_AUTO) kernel = c->filterable ? SRT_KERNEL_FILTERED : SRT_KERNEL_EXACT;
+    if (kernel == SRT_KERNEL_AUTO) kernel = c->filterable ? SRT_KERNEL_CULLED : SRT_KERNEL_EXACT;   // culled falls back to filtered when its lists would not fit
     if (kernel != SRT_KERNEL_EXACT && kernel != SRT_KERNEL_FILTERED && kernel != SRT_KERNEL_CULLED)
         return fail(c, SRT_ERR_INVALID, "unknown kernel selector %u", params->kernel);
     if (kernel == SRT_KERNEL_CULLED) {
