@@ -168,7 +168,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from simpleraytracing_b200 import Context, Library, scene, KERNEL_CULLED
-    from simpleraytracing_b200.bands import BandLayout, InterleavedLayout
+    from simpleraytracing_b200.bands import BandLayout, InterleavedLayout, PeerFrames
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
@@ -205,14 +205,36 @@ def run_ours(args):
     slots = il.new_slots(torch.float32, dev) if world > 1 else None
     my_slot_ptr = il.my_slot(slots).data_ptr() if world > 1 else 0
     my_rows = len(il.rows_of(rank)) if world > 1 else H
+    # N > 1, preferred: fused render + assembly -- the render kernel stores its rows straight into every rank's frame
+    # over NVLink (multicast mapping when the switch offers one); falls back to all_gather + de-interleave
+    peers, assembly = None, "single GPU"
+    if world > 1:
+        assembly = "all_gather of slots + de-interleave kernel"
+        if args.assembly != "allgather":
+            try:
+                # two frame sets used alternately: one barrier per step is enough (a rank can run at most one step ahead)
+                peers = [PeerFrames(H, W, use_multicast=(args.assembly != "p2p")) for _ in range(2)]
+                assembly = ("render kernel stores to the NVSwitch multicast mapping of all frames" if peers[0].multicast_ptr
+                            else "render kernel stores to every peer's frame over NVLink") + " + one device barrier"
+            except Exception as exc:                      # no peer access on this box
+                peers = None
+                assembly += f" (symmetric memory unavailable: {type(exc).__name__})"
     image = torch.empty(H * W, dtype=torch.float32, device=dev)
     host_image = torch.empty(H * W, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    step_no = [0]
 
     def render_and_assemble(p):
         if world == 1:
             ctx.render_lbuffer_device(p, lay.rows, frame.data_ptr())
             return frame
+        if peers is not None:
+            pf = peers[step_no[0] & 1]
+            step_no[0] += 1
+            ctx.render_lbuffer_blocks_device(p, world, rank, pf.pointers())
+            pf.barrier()                                  # every rank's rows have landed in this rank's frame
+            return pf.frame
         ctx.render_lbuffer_interleaved_device(p, world, rank, my_slot_ptr)
         il.all_gather_(slots)
         ctx.deinterleave_device(world, slots.data_ptr(), frame.data_ptr())
@@ -277,6 +299,9 @@ def run_ours(args):
         flush.fill_(1)
         if world == 1:
             ctx.render_lbuffer_device(params, lay.rows, frame.data_ptr())
+        elif peers is not None:
+            barrier()
+            ctx.render_lbuffer_blocks_device(params, world, rank, peers[0].pointers())
         else:
             ctx.render_lbuffer_interleaved_device(params, world, rank, my_slot_ptr)
         tm = ctx.timing()
@@ -290,6 +315,25 @@ def run_ours(args):
     acc_ms = timed(lambda: step_device(params_acc), args.steps, 3, sync_each=False)
     acc_kernel_used = ctx.timing().kernel_used
     acc_e2e_ms = timed(lambda: step_e2e(params_acc), e2e_steps, 2, sync_each=True)
+
+    # correctness of the assembled frame (outside every timed region): the image this rank holds after a sharded
+    # step must equal, bit for bit, the image of one unsharded render on this GPU -- for both kernels
+    verified = True
+    if world > 1:
+        ref_L = torch.empty(H * W, dtype=torch.float32, device=dev)
+        ref_img = torch.empty(H * W, dtype=torch.float32, device=dev)
+        for p_ in (params, params_acc):
+            step_device(p_)
+            ctx.render_lbuffer_device(p_, (0, H), ref_L.data_ptr())
+            ctx.repair_device(p_, ref_L.data_ptr(), ref_img.data_ptr())
+            stream.synchronize()
+            same = torch.equal(image.view(torch.int32), ref_img.view(torch.int32))
+            verified = verified and bool(same)
+        flag = torch.tensor([1 if verified else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        verified = bool(flag.item())
+        if not verified:
+            raise SystemExit(f"bench.py: rank {rank}: the assembled frame differs from the unsharded render")
 
     tests_frame = float(W) * H * ntri
     value = tests_frame * args.steps / (total_ms * 1e-3)
@@ -317,11 +361,12 @@ def run_ours(args):
                        "triangles": ntri, "kernel": kernel_used,
                        "kernel_note": "2 = SRT_KERNEL_FILTERED: the brute-force path, every (ray, triangle) pair evaluated",
                        "l2": "256 MiB flush write between steps",
-                       "step": "render (16-row blocks, block-cyclic over ranks) + all_gather + de-interleave + repair"},
+                       "step": "render (16-row blocks, block-cyclic over ranks) + assembly + repair", "assembly": assembly,
+                       "assembled_frame_equals_unsharded_render": verified},
             "e2e": {"value": e2e_value, "unit": "tests/s", "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(tri.nbytes + 4 * 16 + 4 * (W + H)) + 0,
                     "d2h_bytes_per_step": int(H * W * 4)},
-            "gpu_launches": (render_launches + (1 if world == 1 else 2)) * args.steps,   # + repair (+ de-interleave)
+            "gpu_launches": (render_launches + (1 if (world == 1 or peers is not None) else 2)) * args.steps,   # + repair (+ de-interleave)
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one full-frame launch, ncu --set full
@@ -354,6 +399,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", type=int, default=2, help="headline kernel: 2 filtered (brute force, default), 1 exact, 4 culled, 0 auto")
     ap.add_argument("--ppt", type=int, default=0, help="pixels per thread (0 = auto)")
+    ap.add_argument("--assembly", default="auto", choices=["auto", "p2p", "allgather"],
+                    help="N > 1: auto = fused stores (multicast if available, else per-peer), p2p = per-peer stores, allgather = NCCL")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -177,6 +177,16 @@ int  srt_render_lbuffer_interleaved_device(srt_ctx* ctx, const srt_params* param
                                            float* d_slot_L, float* d_slot_path_len, int32_t* d_slot_sign_sum,
                                            uint32_t* d_slot_hit_count);
 int  srt_deinterleave_device(srt_ctx* ctx, uint32_t n_parts, const float* d_slots, float* d_frame);
+/*
+ * Fused render + assembly: rank `part` renders its 16-row blocks (same block-cyclic split) and the kernel stores
+ * every L value at its IMAGE position (row * W + col) into each of the n_frames (1 ... 8) full-frame buffers in
+ * d_frames -- the rank's own frame plus the peers' frames mapped over NVLink (CUDA IPC / symmetric memory), or a
+ * single NVSwitch multicast mapping that replicates the store to every GPU.  The transfer overlaps the render
+ * tile by tile; no all_gather and no de-interleave pass follow, only a barrier before srt_repair_device.
+ * Replaces the MPI_Send / MPI_Recv gather of src/main-mpi.cxx:854-881.
+ */
+int  srt_render_lbuffer_blocks_device(srt_ctx* ctx, const srt_params* params, uint32_t n_parts, uint32_t part,
+                                      uint32_t n_frames, float* const* d_frames);
 
 /* Artefact repair + image fill over a full frame (lbuffer.cxx:329-404). L_in and image_out must not alias. */
 int  srt_repair(srt_ctx* ctx, const srt_params* params, const float* L_in, float* image_out);

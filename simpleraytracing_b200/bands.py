@@ -94,3 +94,41 @@ class InterleavedLayout:
             if rows:
                 out[torch.tensor(rows)] = s[r, : len(rows)]
         return out.view(-1)
+
+
+class PeerFrames:
+    """Full-frame buffers of all ranks of one node mapped into every rank's address space (NVLink peer memory,
+    `torch.distributed._symmetric_memory`), for the fused render + assembly of srt_render_lbuffer_blocks_device:
+    the render kernel stores each L value into every rank's frame, so the frame is complete on every GPU when the
+    kernels have finished -- no all_gather, no de-interleave pass.
+
+    `pointers()` is what the C ABI takes: [own frame] + [NVSwitch multicast mapping] when the fabric offers one
+    (a single store is replicated to every GPU by the switch), else [own frame] + [each peer's frame].
+    `barrier()` is a device-side barrier over the ranks on the current stream: after it, every rank's stores
+    have landed in this rank's frame.
+    """
+
+    def __init__(self, H, W, group=None, use_multicast=True):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.H, self.W = H, W
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.frame = symm_mem.empty(H * W, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.handle = symm_mem.rendezvous(self.frame, group)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        mc = 0
+        if use_multicast:
+            try:
+                mc = int(self.handle.multicast_ptr)
+            except Exception:
+                mc = 0
+        self.multicast_ptr = mc
+
+    def pointers(self):
+        own = self.peer_ptrs[self.rank]
+        if self.multicast_ptr:
+            return [self.multicast_ptr]          # the switch replicates the store to every GPU, this one included
+        return [own] + [p for r, p in enumerate(self.peer_ptrs) if r != self.rank]
+
+    def barrier(self):
+        self.handle.barrier(channel=0)

@@ -58,7 +58,7 @@ EXPORTS = [
     "srt_default_params", "srt_scene_bbox", "srt_camera_from_bbox", "srt_partition_rows", "srt_triangle_normals",
     "srt_set_meshes", "srt_set_camera", "srt_render_lbuffer", "srt_render_lbuffer_device", "srt_repair",
     "srt_repair_device", "srt_render_xray", "srt_interleave_slot_rows",
-    "srt_render_lbuffer_interleaved_device", "srt_deinterleave_device", "srt_render_shaded",
+    "srt_render_lbuffer_interleaved_device", "srt_deinterleave_device", "srt_render_lbuffer_blocks_device", "srt_render_shaded",
     "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_force_splits", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_tile_triangles", "srt_debug_download_packed",
 ]
 
@@ -104,6 +104,7 @@ class Library:
         L.srt_render_lbuffer_device.argtypes = [vp, C.POINTER(Params), u32, u32, vp, vp, vp, vp]
         L.srt_interleave_slot_rows.argtypes = [u32, u32, C.POINTER(u32)]
         L.srt_render_lbuffer_interleaved_device.argtypes = [vp, C.POINTER(Params), u32, u32, vp, vp, vp, vp]
+        L.srt_render_lbuffer_blocks_device.argtypes = [vp, C.POINTER(Params), u32, u32, u32, C.POINTER(C.c_void_p)]
         L.srt_deinterleave_device.argtypes = [vp, u32, vp, vp]
         L.srt_render_shaded.argtypes = [vp, C.POINTER(Params), C.POINTER(Light), vp, vp]
         L.srt_render_shaded_device.argtypes = [vp, C.POINTER(Params), C.POINTER(Light), vp, vp, vp]
@@ -277,6 +278,12 @@ class Context:
         self._ck(self.lib.srt_render_lbuffer_device(self.h, C.byref(params), rows[0], rows[1], C.c_void_p(dL),
                                                     C.c_void_p(d_dist or None), C.c_void_p(d_ssum or None),
                                                     C.c_void_p(d_hits or None)))
+
+    def render_lbuffer_blocks_device(self, params, n_parts, part, frame_ptrs):
+        """Fused render + assembly: this rank's 16-row blocks, stored at image positions into every frame in
+        `frame_ptrs` (own frame first; peers' NVLink mappings or one multicast mapping after it)."""
+        arr = (C.c_void_p * len(frame_ptrs))(*[C.c_void_p(int(q)) for q in frame_ptrs])
+        self._ck(self.lib.srt_render_lbuffer_blocks_device(self.h, C.byref(params), n_parts, part, len(frame_ptrs), arr))
 
     def render_lbuffer_interleaved_device(self, params, n_parts, part, d_slot, d_dist=0, d_ssum=0, d_hits=0):
         self._ck(self.lib.srt_render_lbuffer_interleaved_device(self.h, C.byref(params), n_parts, part, C.c_void_p(d_slot),

@@ -51,6 +51,12 @@ struct RenderArgs {
     float incident;          // 80.0f
     double length_to_cm;     // 0.1
     float* L;                // full-frame outputs (row*W + col); band rows written
+    // Fused assembly (multi-GPU): with L_image != 0 the L value of a compact (block-cyclic) launch is written at its
+    // IMAGE position instead of the slot position, and additionally into n_L_extra more full-frame buffers -- the
+    // peers' frames mapped over NVLink, or one multicast mapping that the switch replicates to every GPU.
+    int L_image;
+    uint32_t n_L_extra;
+    float* L_extra[7];
     float* dist;             // optional
     int32_t* ssum;           // optional
     uint32_t* hits;          // optional

@@ -260,7 +260,7 @@ int choose_ppt(const srt_ctx* c, const srt_params* p, uint32_t rows)
 // parts >= 1: block-cyclic part `part` of `parts` over the whole frame, written compactly (slot layout).
 int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint32_t row_end,
                   float* dL, float* d_dist, int32_t* d_ssum, uint32_t* d_hits, uint32_t parts = 0, uint32_t part = 0,
-                  int mode = 0)
+                  int mode = 0, float* const* extra_frames = nullptr, uint32_t n_extra = 0)
 {
     if (!params) return fail(c, SRT_ERR_INVALID, "params is NULL");
     if (mode == 0 && !dL) return fail(c, SRT_ERR_INVALID, "L buffer is NULL");
@@ -296,6 +296,9 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     }
     a.incident = params->incident; a.length_to_cm = params->length_to_cm;
     a.L = dL; a.dist = d_dist; a.ssum = d_ssum; a.hits = d_hits;
+    a.L_image = extra_frames != nullptr;                // fused assembly: L goes to image positions of dL + the extra frames
+    a.n_L_extra = n_extra;
+    for (uint32_t i = 0; i < n_extra && i < 7; ++i) a.L_extra[i] = extra_frames[i];
     a.counters = nullptr;
     if (c->count_exact || params->kernel == SRT_KERNEL_AUDIT) {
         if (!c->d_counters) SRT_CUDA(c, cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)));
@@ -630,6 +633,20 @@ int srt_render_lbuffer_interleaved_device(srt_ctx* c, const srt_params* p, uint3
     if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
     SRT_CUDA(c, cudaSetDevice(c->device));
     return render_device(c, p, 0, c->camera.height, d_slot, dd, ds, dh, n_parts, part);
+}
+
+int srt_render_lbuffer_blocks_device(srt_ctx* c, const srt_params* p, uint32_t n_parts, uint32_t part,
+                                     uint32_t n_frames, float* const* d_frames)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (n_parts == 0 || part >= n_parts) return fail(c, SRT_ERR_INVALID, "part %u of %u", part, n_parts);
+    if (n_frames == 0 || n_frames > 8 || !d_frames) return fail(c, SRT_ERR_INVALID, "1 to 8 frame pointers expected");
+    for (uint32_t i = 0; i < n_frames; ++i)
+        if (!d_frames[i]) return fail(c, SRT_ERR_INVALID, "frame pointer %u is NULL", i);
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    return render_device(c, p, 0, c->camera.height, d_frames[0], nullptr, nullptr, nullptr, n_parts, part, 0,
+                         d_frames + 1, n_frames - 1);
 }
 
 int srt_deinterleave_device(srt_ctx* c, uint32_t n_parts, const float* d_slots, float* d_frame)
