@@ -63,9 +63,9 @@ __attribute__((target("fma"))) static void* audit_worker(void* arg)
             const float x0 = (float)(col & ~7u) + xc;
             const _Float16 hk = (_Float16)(float)(col & 7u);
             const _Float16 Y16 = h_fma(h_from_bits((uint16_t)(hw & 0xffffu)), hk, (_Float16)__builtin_fmaf(f[0], x0, __builtin_fmaf(f[1], y, f[2])));
-            /* |D| over the run is bounded by its end-point values; tau = max|D| * (1 + 2^-10) + m, rounded to nearest */
-            const float fd0 = __builtin_fmaf(f[3], x0, __builtin_fmaf(f[4], y, f[5])), fd7 = __builtin_fmaf(f[3], 7.0f, fd0);
-            const _Float16 tau = (_Float16)__builtin_fmaf(fmaxf(fabsf(fd0), fabsf(fd7)), 1.0009765625f, f[6]);
+            /* |D| over the run is bounded by |D16(x0)| + mh (binary16 margin in the high half of word 7); one HADD2 */
+            const _Float16 D16 = (_Float16)__builtin_fmaf(f[3], x0, __builtin_fmaf(f[4], y, f[5]));
+            const _Float16 tau = (_Float16)((long double)h_abs(D16) + (long double)h_from_bits((uint16_t)(hw >> 16)));
             const int gate16 = !(h_abs(Y16) > tau);
             /* odd pixels-per-thread: the binary32 gate */
             const int gate32 = (fabsf(Dd) - fabsf(X1)) >= -tm;

@@ -24,8 +24,6 @@ namespace srt {
 namespace {
 
 // ------------------------------------------------------------------ helpers
-constexpr float kTauInflate = 1.0009765625f;     // 1 + 2^-10: tau is rounded to NEAREST binary16 (<= 2^-11 down) and must not shrink
-
 struct RayDirs { float ax, ay, az, bx, by, bz; };   // dirA: sign test; dirB: Ray::m_direction
 
 __device__ __forceinline__ float dot_rn(float ax, float ay, float az, float bx, float by, float bz)
@@ -205,13 +203,13 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
                     const float X2 = fmaf(ga.x, x, fmaf(ga.y, y, ga.z));
                     const float X3 = fmaf(gb.x, x, fmaf(gb.y, y, gb.z));
                     // level-0 gate of the filtered kernel (8 pixels per thread): binary32 Y at the first pixel of the
-                    // aligned run, one binary16 FMA step to this pixel; |D| bounded by its two end-point values
+                    // aligned run, one binary16 FMA step to this pixel; |D| bounded by |D16(x0)| + the binary16 margin
                     const float x0 = (float)(col & ~7u) + a.cam.xc;
                     const __half hk = __int2half_rn((int)(col & 7u));
                     const __half2 hs = *reinterpret_cast<const __half2*>(&fb.w);
                     const __half Y16 = __hfma(__low2half(hs), hk, __float2half_rn(fmaf(fa.x, x0, fmaf(fa.y, y, fa.z))));
-                    const float fd0 = fmaf(fa.w, x0, fmaf(fb.x, y, fb.y)), fd7 = fmaf(fa.w, 7.0f, fd0);
-                    const __half tau = __float2half_rn(fmaf(fmaxf(fabsf(fd0), fabsf(fd7)), kTauInflate, fb.z));
+                    const __half D16 = __float2half_rn(fmaf(fa.w, x0, fmaf(fb.x, y, fb.y)));
+                    const __half tau = __hadd(__habs(D16), __high2half(hs));
                     const bool gate = __hgt(__habs(Y16), tau);
                     const bool reject = gate || !(fabsf(Dd) - fabsf(X1) >= -tm) || (fabsf(X1) > fabsf(Dd) + fb.z) ||  // level 0
                                         (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);         // level 1
@@ -256,21 +254,21 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 // Triangle order per pixel is preserved: pending groups are resolved strictly in order.
 
 #ifndef SRT_GROUP_UNROLL
-#define SRT_GROUP_UNROLL 2
+#define SRT_GROUP_UNROLL 4
 #endif
-constexpr int kGroupUnroll = SRT_GROUP_UNROLL;   // groups per trip of the hot loop: unrolling removes the register rotation of the prefetch and loop overhead (14.8 -> 13.8 ms)
+constexpr int kGroupUnroll = SRT_GROUP_UNROLL;   // groups per trip of the hot loop (measured: 1 -> 8.59 ms, 2 -> 7.96 ms, 4 -> 7.83 ms per 2048^2 frame)
 
 // Level-0 state of one group (kGroupTris = 2 triangles) for one thread's run of P pixels.
-//  * even P: Y at the run's first pixel in binary32, rounded to binary16 and stepped along the run with HFMA2 -- two
-//    pixels per instruction; |D| is bounded over the run by its value at the two end points (|affine| is convex), so
-//    the gate is  min_k |Y16(k)| <= tau,  tau = max(|D(x0)|, |D(x_last)|) + m  in binary32, rounded up to binary16:
-//    per triangle 4 HFMA2 + 2 packed min with |.| modifiers + 1 packed compare for 8 pixels.  The error of the
-//    binary16 steps is part of the record's margin (prepack_math.h, pack_triangle).
+//  * even P: Y and D at the run's first pixel in binary32, rounded to binary16; Y is stepped along the run with
+//    HFMA2 -- two pixels per instruction -- and |D| is bounded over the run by |D(x0)| + 7 |bd|, so the gate is
+//    min_k |Y16(k)| <= tau,  tau = |D16(x0)| + mh  (one HADD2; mh is the record's binary16 margin):
+//    per triangle 4 FFMA + 1 pack + 4 HFMA2 + 1 HADD2 + 2 packed min with |.| modifiers + 1 packed compare for
+//    8 pixels.  Every rounding of this path is part of mh (prepack_math.h, pack_triangle).
 //  * odd P: the binary32 evaluation (2 FFMA + FADD + 1/2 FMNMX3 per pair).
 template <int P>
 struct Level0 {
     static constexpr bool kHalf = (P & 1) == 0;
-    // kHalf: per triangle {(Y0, tau) as half2, slope word}; else: bx, bd, base-y, base-d per triangle
+    // kHalf: per triangle {(Y, D) at x0 as half2, (slope, margin) word}; else: bx, bd, base-y, base-d per triangle
     float v[kHalf ? 4 : 8];
 
     __device__ __forceinline__ void load(const float4* q, float x0, float y)
@@ -279,10 +277,7 @@ struct Level0 {
         if constexpr (kHalf) {
             const float fy0 = fmaf(a0.x, x0, fmaf(a0.y, y, a0.z)), fd0 = fmaf(a0.w, x0, fmaf(b0.x, y, b0.y));
             const float fy1 = fmaf(a1.x, x0, fmaf(a1.y, y, a1.z)), fd1 = fmaf(a1.w, x0, fmaf(b1.x, y, b1.y));
-            const float fe0 = fmaf(a0.w, (float)(P - 1), fd0), fe1 = fmaf(a1.w, (float)(P - 1), fd1);   // D at the last pixel
-            const float t0 = fmaf(fmaxf(fabsf(fd0), fabsf(fe0)), kTauInflate, b0.z);
-            const float t1 = fmaf(fmaxf(fabsf(fd1), fabsf(fe1)), kTauInflate, b1.z);
-            put(0, __floats2half2_rn(fy0, t0)); put(1, __floats2half2_rn(fy1, t1));      // one pack per triangle: (Y0, tau)
+            put(0, __floats2half2_rn(fy0, fd0)); put(1, __floats2half2_rn(fy1, fd1));      // one pack per triangle: (Y, D) at x0
             v[2] = b0.w; v[3] = b1.w;
         } else {
             v[0] = a0.x; v[1] = a0.w; v[2] = fmaf(a0.y, y, a0.z); v[3] = fmaf(b0.x, y, b0.y);
@@ -296,8 +291,11 @@ struct Level0 {
     __device__ __forceinline__ bool survives(const float (&x)[P], float negM) const
     {
         if constexpr (kHalf) {
-            const __half2 Y0 = __low2half2(get(0)), T0 = __high2half2(get(0)), Y1 = __low2half2(get(1)), T1 = __high2half2(get(1));
+            const __half2 Y0 = __low2half2(get(0)), Y1 = __low2half2(get(1));
             const __half2 sy0 = __low2half2(get(2)), sy1 = __low2half2(get(3));
+            // tau = |D(x0)| + mh in binary16 (mh covers the growth of |D| along the run and both roundings)
+            const __half2 T0 = __hadd2(__habs2(__high2half2(get(0))), __high2half2(get(2)));
+            const __half2 T1 = __hadd2(__habs2(__high2half2(get(1))), __high2half2(get(3)));
             __half2 m0, m1;
 #pragma unroll
             for (int k = 0; k < P; k += 2) {

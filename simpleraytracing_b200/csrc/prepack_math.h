@@ -48,12 +48,12 @@ struct ExactTri {
 // (D = LAMBDA * det, see pack_triangle).  A pair can only be a hit when |Y| <= |D| + m
 // (<=> 0 <= X / det <= 1 up to rounding).  The record is scaled by a per-triangle power of two so
 // that the render kernel can step Y and D along a pixel run in binary16 (HFMA2, two pixels per
-// instruction) from a binary32 value at the run's first pixel; h holds the binary16 x-slopes (the kernel steps
-// only Y and bounds |D| over the run by its end-point values; the D slope is kept for diagnostics).
+// instruction) from a binary32 value at the run's first pixel; h holds the binary16 x-slope of Y and the gate's
+// binary16 margin (the kernel steps only Y and bounds |D| over the run by |D(x0)| + 7 |bd|, folded into that margin).
 struct FilterTri {
     float bx, gx, ax, bd;
     float gd, ad, m;
-    uint32_t h;                  // binary16(bx) in the low half, binary16(bd) in the high half
+    uint32_t h;                  // binary16(bx) in the low half, the gate's binary16 margin mh in the high half
 };
 
 // 32 B: level-1 reject, the two remaining strips (slow path only).
@@ -267,7 +267,6 @@ SRT_HD bool pack_triangle(const float* v, const float* normal_or_null, const flo
                 if (sc > lim) sc *= 0.5;                        // log2 rounding at an exact power of two
             }
         }
-        // (1 + 2^-9): the kernel forms tau = max|D| * (1 + 2^-10) + m in binary32 and rounds it to NEAREST binary16
         const double M16 = (sc * M0 + H_ABS + TINY) * 1.001953125;
         ok = std::isfinite(m0) && std::isfinite(m1) && std::isfinite(m2) && sc * m0 < LIM && sc * m1 < LIM && sc * m2 < LIM &&
              sc * S.absmax < LIM && sc * Dn.absmax < LIM && sc * Vn.absmax < LIM && sc * Wn.absmax < LIM &&
@@ -276,7 +275,12 @@ SRT_HD bool pack_triangle(const float* v, const float* normal_or_null, const flo
             f.bx = (float)(sc * s0.b); f.gx = (float)(sc * s0.g); f.ax = (float)(sc * s0.a);
             f.bd = (float)(sc * Dn.b); f.gd = (float)(sc * Dn.g); f.ad = (float)(sc * Dn.a);
             f.m = round_up(M16);
-            f.h = f16_bits(f.bx) | (f16_bits(f.bd) << 16);
+            // binary16 margin of the kernel's gate  min_k |Y16(k)| <= tau16 = fl16(|fl16(D(x0))| + mh):  |D| over a run of
+            // <= 8 pixels exceeds |D(x0)| by at most 7 |bd| (+ 2 eps absmax, part of M0), fl16(D(x0)) is short by at most
+            // 2^-11 |D| (LAMBDA pays for it, see above) and the final sum is rounded once more (<= 2^-11 (|D| + mh));
+            // (1 + 2^-10) before the round-to-nearest conversion keeps the stored value an upper bound.
+            const double mh = (M16 + 7.0 * std::fabs((double)f.bd) * 1.001 + sc * Dn.absmax / 512.0 + H_ABS) * 1.0009765625;
+            f.h = f16_bits(f.bx) | (f16_bits((float)mh) << 16);
             f2.bx2 = (float)(sc * s1.b); f2.gx2 = (float)(sc * s1.g); f2.ax2 = (float)(sc * s1.a); f2.m2 = round_up(sc * m1 + TINY);
             f2.bx3 = (float)(sc * s2.b); f2.gx3 = (float)(sc * s2.g); f2.ax3 = (float)(sc * s2.a); f2.m3 = round_up(sc * m2 + TINY);
         }
