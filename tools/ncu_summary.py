@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (ncu --set full --import-source on) into a text file for profiles/.
-usage: tools/ncu_summary.py report.ncu-rep out.txt"""
+usage: tools/ncu_summary.py report.ncu-rep out.txt [launch index, default 0]  (the source section covers launch 0 only)"""
 import csv
 import io
 import subprocess
@@ -10,7 +10,9 @@ rep, out = sys.argv[1], sys.argv[2]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # which captured launch (raw page row) to summarise
+vals = rows[2 + which]
 keys = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second",
         "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "launch__waves_per_multiprocessor", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -35,7 +37,7 @@ with open(out, "w") as f:
             i = hdr.index(k)
             f.write(f"{k:90s} {vals[i]} {units[i]}\n")
     rows = list(csv.reader(io.StringIO(src)))
-    if len(rows) > 2:
+    if len(rows) > 2 and which == 0:
         h = rows[1]
         body = []
         for r in rows[2:]:                      # first kernel only (a second 'Kernel Name' header starts the next one)
