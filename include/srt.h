@@ -108,7 +108,7 @@ typedef struct {
     uint32_t repair_depth;      /* 4 (lbuffer.cxx:339)                                                */
     uint32_t kernel;            /* srt_kernel                                                         */
     uint32_t flags;
-    uint32_t pixels_per_thread; /* 0 = auto; tuning knob of the filtered kernel (1 ... 8)            */
+    uint32_t pixels_per_thread; /* 0 = auto; tuning knob of the filtered kernel (1 ... 8, 16)        */
 } srt_params;
 
 typedef struct {

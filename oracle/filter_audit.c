@@ -58,15 +58,20 @@ __attribute__((target("fma"))) static void* audit_worker(void* arg)
             const float Dd = __builtin_fmaf(f[3], x, __builtin_fmaf(f[4], y, f[5]));
             const float X2 = __builtin_fmaf(g[0], x, __builtin_fmaf(g[1], y, g[2]));
             const float X3 = __builtin_fmaf(g[4], x, __builtin_fmaf(g[5], y, g[6]));
-            /* level-0 gate, even pixels-per-thread (run of 8): binary32 at the run's first pixel, one binary16 step */
+            /* level-0 gate for every even run length the kernel is built for: binary32 Y, D at the run's first pixel, one
+             * binary16 step (HFMA2), tau = |D16(x0)| + mh (binary16 margin in the high half of word 7; one HADD2) */
             uint32_t hw; memcpy(&hw, &f[7], 4);
-            const float x0 = (float)(col & ~7u) + xc;
-            const _Float16 hk = (_Float16)(float)(col & 7u);
-            const _Float16 Y16 = h_fma(h_from_bits((uint16_t)(hw & 0xffffu)), hk, (_Float16)__builtin_fmaf(f[0], x0, __builtin_fmaf(f[1], y, f[2])));
-            /* |D| over the run is bounded by |D16(x0)| + mh (binary16 margin in the high half of word 7); one HADD2 */
-            const _Float16 D16 = (_Float16)__builtin_fmaf(f[3], x0, __builtin_fmaf(f[4], y, f[5]));
-            const _Float16 tau = (_Float16)((long double)h_abs(D16) + (long double)h_from_bits((uint16_t)(hw >> 16)));
-            const int gate16 = !(h_abs(Y16) > tau);
+            int gate16 = 1;
+            static const uint32_t runs[5] = { 2, 4, 6, 8, 16 };
+            for (int ri = 0; ri < 5; ++ri) {
+                const uint32_t c0 = col - col % runs[ri];
+                const float x0 = (float)c0 + xc;
+                const _Float16 hk = (_Float16)(float)(col - c0);
+                const _Float16 Y16 = h_fma(h_from_bits((uint16_t)(hw & 0xffffu)), hk, (_Float16)__builtin_fmaf(f[0], x0, __builtin_fmaf(f[1], y, f[2])));
+                const _Float16 D16 = (_Float16)__builtin_fmaf(f[3], x0, __builtin_fmaf(f[4], y, f[5]));
+                const _Float16 tau = (_Float16)((long double)h_abs(D16) + (long double)h_from_bits((uint16_t)(hw >> 16)));
+                if (h_abs(Y16) > tau) gate16 = 0;
+            }
             /* odd pixels-per-thread: the binary32 gate */
             const int gate32 = (fabsf(Dd) - fabsf(X1)) >= -tm;
             const int s0t = gate16 && gate32;

@@ -202,15 +202,18 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
                     const float Dd = fmaf(fa.w, x, fmaf(fb.x, y, fb.y));
                     const float X2 = fmaf(ga.x, x, fmaf(ga.y, y, ga.z));
                     const float X3 = fmaf(gb.x, x, fmaf(gb.y, y, gb.z));
-                    // level-0 gate of the filtered kernel (8 pixels per thread): binary32 Y at the first pixel of the
-                    // aligned run, one binary16 FMA step to this pixel; |D| bounded by |D16(x0)| + the binary16 margin
-                    const float x0 = (float)(col & ~7u) + a.cam.xc;
-                    const __half hk = __int2half_rn((int)(col & 7u));
+                    // level-0 gate of the filtered kernel for every even run length P it is built for: binary32 Y and D at
+                    // the first pixel of the aligned run, one binary16 FMA step to this pixel, tau = |D16(x0)| + mh
                     const __half2 hs = *reinterpret_cast<const __half2*>(&fb.w);
-                    const __half Y16 = __hfma(__low2half(hs), hk, __float2half_rn(fmaf(fa.x, x0, fmaf(fa.y, y, fa.z))));
-                    const __half D16 = __float2half_rn(fmaf(fa.w, x0, fmaf(fb.x, y, fb.y)));
-                    const __half tau = __hadd(__habs(D16), __high2half(hs));
-                    const bool gate = __hgt(__habs(Y16), tau);
+                    bool gate = false;
+                    for (uint32_t P : { 2u, 4u, 6u, 8u, 16u }) {
+                        const uint32_t c0 = col - col % P;
+                        const float x0 = (float)c0 + a.cam.xc;
+                        const __half hk = __int2half_rn((int)(col - c0));
+                        const __half Y16 = __hfma(__low2half(hs), hk, __float2half_rn(fmaf(fa.x, x0, fmaf(fa.y, y, fa.z))));
+                        const __half D16 = __float2half_rn(fmaf(fa.w, x0, fmaf(fb.x, y, fb.y)));
+                        gate = gate || __hgt(__habs(Y16), __hadd(__habs(D16), __high2half(hs)));
+                    }
                     const bool reject = gate || !(fabsf(Dd) - fabsf(X1) >= -tm) || (fabsf(X1) > fabsf(Dd) + fb.z) ||  // level 0
                                         (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);         // level 1
                     if (reject && hit) ++n_viol;
@@ -1275,9 +1278,9 @@ static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const bool small = (size_t)grid.x * grid.y * grid.z <= (size_t)SRT_MIN_CTAS_SMALL * sms;
-    if (a.hit_entries) {                                   // split launches always use P = 8
-        if (P != 8) return cudaErrorInvalidValue;
-        return launch_filtered_b<8, SRT_MIN_CTAS, true>(a, grid, smem, s);
+    if (a.hit_entries) {                                   // split launches always use P = kSplitPixels
+        if (P != kSplitPixels) return cudaErrorInvalidValue;
+        return launch_filtered_b<kSplitPixels, SRT_MIN_CTAS, true>(a, grid, smem, s);
     }
     return small ? launch_filtered_b<P, SRT_MIN_CTAS_SMALL, false>(a, grid, smem, s) : launch_filtered_b<P, SRT_MIN_CTAS, false>(a, grid, smem, s);
 }
@@ -1294,6 +1297,7 @@ cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s
         case 6: return launch_filtered_t<6>(a, s);
         case 7: return launch_filtered_t<7>(a, s);
         case 8: return launch_filtered_t<8>(a, s);
+        case 16: return launch_filtered_t<16>(a, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -10,6 +10,10 @@ namespace srt {
 #endif
 constexpr uint32_t kTileTris  = SRT_TILE_TRIS;   // triangles per shared-memory tile of filter records (64 B each)
 constexpr uint32_t kGroupTris = 2;     // triangles per vote group in the filtered kernel
+#ifndef SRT_SPLIT_PIXELS
+#define SRT_SPLIT_PIXELS 16
+#endif
+constexpr int kSplitPixels = SRT_SPLIT_PIXELS;   // pixels per thread of split (hit-list) launches: 8 or 16
 #ifndef SRT_STAGES
 #define SRT_STAGES 3
 #endif
@@ -112,7 +116,7 @@ cudaError_t launch_shade(const ShadeArgs& a, cudaStream_t s);
 // Exact kernel: every pair runs the reference op sequence. audit != 0 additionally evaluates the
 // filters for every pair and counts (filter says reject) && (exact says hit) into counters[1].
 cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s);
-// Filtered kernel; ppt = pixels per thread (1, 2, 4, 8).
+// Filtered kernel; ppt = pixels per thread (1 ... 8, 16).
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s);
 // Culled kernel: bin pass (every triangle against every bin of a.bins_x x a.bins_y) + render pass.  Same results
 // as the other kernels: the bins and the per-CTA cull only ever drop pairs the conservative filter proves to miss.

@@ -82,7 +82,8 @@ constexpr double TINY = 1e-30;                   // absolute slack for gradual u
 constexpr double BIG = 1073741824.0;             // 2^30: magnitude precondition
 constexpr double LIM = 1e30;
 constexpr double LAMBDA = 1.00390625;            // 1 + 2^-8: |D| is widened by this factor; pays for the binary16 relative error
-constexpr double H_SLOPE = 14.1 / 2048.0;        // binary16 error per unit x-slope over a run of <= 8 pixels (see pack_triangle)
+constexpr int    RUN_MAX = 16;                   // longest pixel run a thread of the filtered kernel steps in binary16
+constexpr double H_SLOPE = (2.0 * (RUN_MAX - 1) + 0.1) / 2048.0;   // binary16 error per unit x-slope over a run of <= RUN_MAX pixels (see pack_triangle)
 constexpr double H_ABS = 9.5367431640625e-07;    // 2^-20: binary16 subnormal roundings
 
 struct f3 { float x, y, z; };
@@ -240,16 +241,16 @@ SRT_HD bool pack_triangle(const float* v, const float* normal_or_null, const flo
         if (s1.grad2 > s0.grad2) { t = s0; s0 = s1; s1 = t; }
         const double m0 = strip_margin(s0, Dn), m1 = strip_margin(s1, Dn), m2 = strip_margin(s2, Dn);
         // --- binary16 stepping of level 0 (render kernel, even pixels-per-thread).  With Yf(k) the binary32 value
-        // fma(bx, x0 + k, fma(gx, y, ax)) the bounds above are about, the kernel evaluates, for pixel k <= 7 of a run,
+        // fma(bx, x0 + k, fma(gx, y, ax)) the bounds above are about, the kernel evaluates, for pixel k < RUN_MAX of a run,
         //     Y16(k) = fl16(fl16(bx) * k + fl16(Yf(0)))            (one HFMA2; k is exact in binary16)
-        // |Y16(k) - Yf(k)| <= 7 |fl16(bx) - bx| + |fl16(Yf(0)) - Yf(0)| + 2 eps absmax + 2^-11 |Y16(k)| + subnormal terms
-        //                  <= rho |Yf(k)| + hY,   rho = 1.001 * 2^-10,  hY = (14.1 / 2048) |bx| + 2.1 eps absmax + 2^-21
-        // (|Yf(0)| <= |Yf(k)| + 7 |bx| + ...), and the same for D.  The float-level statement is
+        // |Y16(k) - Yf(k)| <= k |fl16(bx) - bx| + |fl16(Yf(0)) - Yf(0)| + 2 eps absmax + 2^-11 |Y16(k)| + subnormal terms
+        //                  <= rho |Yf(k)| + hY,   rho = 1.001 * 2^-10,  hY = ((2 k_max + 0.1) / 2048) |bx| + 2.1 eps absmax + 2^-21
+        // (|Yf(0)| <= |Yf(k)| + k_max |bx| + ..., k_max = RUN_MAX - 1 = 15), and the same for D.  The float-level statement is
         //     hit  =>  |Yf| <= (1 + 16 eps) / LAMBDA * |Df| + m0,
         // hence hit => |Y16| <= (1 + rho)(1 + 16 eps) / (LAMBDA (1 - rho)) (|D16| + hD) + (1 + rho) m0 + hY
         //                    <= |D16| + hD + 1.002 m0 + hY                    [the factor is < 1 for LAMBDA = 1 + 2^-8]
         // The record is scaled by a power of two `sc` (exact, the tests are scale invariant) so that a hit implies
-        // |D16| + margin <= 2^13 and 7 |bx| <= 7 * 2^12: then no binary16 quantity of a HIT overflows, and an overflowing
+        // |D16| + margin <= 2^13 and 15 |bx| <= 15 * 2^11: then no binary16 quantity of a HIT overflows, and an overflowing
         // Y16 (= +-inf, never NaN: fl16(bx) * k stays finite) is a correct reject because D16 stays finite.
         const double hY = H_SLOPE * std::fabs(s0.b) + 2.1 * EPS * s0.absmax;
         const double hD = H_SLOPE * std::fabs(Dn.b) + 2.1 * EPS * Dn.absmax;
@@ -259,7 +260,7 @@ SRT_HD bool pack_triangle(const float* v, const float* normal_or_null, const flo
             const double U = Dn.absmax + M0, B = std::fabs(s0.b);
             double lim = 0.0;
             if (U > 0.0) lim = 8000.0 / U;
-            if (B > 0.0) lim = lim > 0.0 ? std::fmin(lim, 4096.0 / B) : 4096.0 / B;
+            if (B > 0.0) lim = lim > 0.0 ? std::fmin(lim, 2048.0 / B) : 2048.0 / B;
             if (lim > 0.0 && std::isfinite(lim)) {
                 int e = (int)std::floor(std::log2(lim));
                 e = e < -100 ? -100 : (e > 100 ? 100 : e);
@@ -270,16 +271,16 @@ SRT_HD bool pack_triangle(const float* v, const float* normal_or_null, const flo
         const double M16 = (sc * M0 + H_ABS + TINY) * 1.001953125;
         ok = std::isfinite(m0) && std::isfinite(m1) && std::isfinite(m2) && sc * m0 < LIM && sc * m1 < LIM && sc * m2 < LIM &&
              sc * S.absmax < LIM && sc * Dn.absmax < LIM && sc * Vn.absmax < LIM && sc * Wn.absmax < LIM &&
-             sc * (Dn.absmax + M0) <= 8192.0 && sc * std::fabs(s0.b) <= 4100.0;
+             sc * (Dn.absmax + M0) <= 8192.0 && sc * std::fabs(s0.b) <= 2050.0;
         if (ok) {
             f.bx = (float)(sc * s0.b); f.gx = (float)(sc * s0.g); f.ax = (float)(sc * s0.a);
             f.bd = (float)(sc * Dn.b); f.gd = (float)(sc * Dn.g); f.ad = (float)(sc * Dn.a);
             f.m = round_up(M16);
             // binary16 margin of the kernel's gate  min_k |Y16(k)| <= tau16 = fl16(|fl16(D(x0))| + mh):  |D| over a run of
-            // <= 8 pixels exceeds |D(x0)| by at most 7 |bd| (+ 2 eps absmax, part of M0), fl16(D(x0)) is short by at most
+            // <= RUN_MAX pixels exceeds |D(x0)| by at most (RUN_MAX - 1) |bd| (+ 2 eps absmax, part of M0), fl16(D(x0)) is short by at most
             // 2^-11 |D| (LAMBDA pays for it, see above) and the final sum is rounded once more (<= 2^-11 (|D| + mh));
             // (1 + 2^-10) before the round-to-nearest conversion keeps the stored value an upper bound.
-            const double mh = (M16 + 7.0 * std::fabs((double)f.bd) * 1.001 + sc * Dn.absmax / 512.0 + H_ABS) * 1.0009765625;
+            const double mh = (M16 + (RUN_MAX - 1) * std::fabs((double)f.bd) * 1.001 + sc * Dn.absmax / 512.0 + H_ABS) * 1.0009765625;
             f.h = f16_bits(f.bx) | (f16_bits((float)mh) << 16);
             f2.bx2 = (float)(sc * s1.b); f2.gx2 = (float)(sc * s1.g); f2.ax2 = (float)(sc * s1.a); f2.m2 = round_up(sc * m1 + TINY);
             f2.bx3 = (float)(sc * s2.b); f2.gx3 = (float)(sc * s2.g); f2.ax3 = (float)(sc * s2.a); f2.m3 = round_up(sc * m2 + TINY);

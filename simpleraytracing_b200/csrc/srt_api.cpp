@@ -27,7 +27,7 @@
 #endif
 
 #ifndef SRT_RESIDENT_CTAS
-#define SRT_RESIDENT_CTAS 7      // CTAs of the filtered kernel resident per SM (kernels.cu: SRT_MIN_CTAS)
+#define SRT_RESIDENT_CTAS 8      // CTAs of the filtered kernel resident per SM (64 registers)
 #endif
 
 namespace {
@@ -239,7 +239,7 @@ int pack_scene(srt_ctx* c)
 // the time, and with fewer than 8 resident CTAs the SM's issue slots are not saturated (eff).
 int choose_ppt(const srt_ctx* c, const srt_params* p, uint32_t rows)
 {
-    if (p->pixels_per_thread >= 1 && p->pixels_per_thread <= 8) return (int)p->pixels_per_thread;
+    if ((p->pixels_per_thread >= 1 && p->pixels_per_thread <= 8) || p->pixels_per_thread == 16) return (int)p->pixels_per_thread;
     static const double cost[9] = { 0, 3.20, 1.96, 1.77, 1.47, 1.58, 1.51, 1.063, 1.00 };  // per test, relative to P = 8
     static const double eff[9] = { 0, 0.35, 0.60, 0.78, 0.89, 0.91, 0.92, 0.93, 0.94 };     // issue efficiency, k resident CTAs
     int sms = 148;
@@ -348,7 +348,8 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     if (kernel == SRT_KERNEL_FILTERED) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-        const uint64_t ctas8 = (uint64_t)((cam.width + 63) / 64) * a.n_blocks;
+        const uint32_t tile_w = 8u * (uint32_t)srt::kSplitPixels;                    // CTA width of a split launch
+        const uint64_t ctas8 = (uint64_t)((cam.width + tile_w - 1) / tile_w) * a.n_blocks;
         // Shorter CTAs in more waves balance the SMs better (CTA run times vary with their slow-path work) and keep
         // small grids -- a rank's share of a multi-GPU frame is only a wave or two of CTAs -- at full occupancy:
         // aim for ~12 waves (profiles/r01_splits.txt: N = 8 share 2.00 ms split vs 2.53 ms unsplit, ideal 1.90 ms;
@@ -356,7 +357,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         const uint64_t slots = (uint64_t)sms * SRT_RESIDENT_CTAS;
         uint32_t zs = 1;
         if (mode == 0 && params->pixels_per_thread == 0 && ctas8 > 0) {
-            zs = (uint32_t)std::min<uint64_t>(12, std::max<uint64_t>(1, (12 * slots + ctas8 / 2) / ctas8));
+            zs = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, (12 * slots + ctas8 / 2) / ctas8));
             const uint64_t px = (uint64_t)(parts == 0 ? cam.height : a.n_blocks * 16) * cam.width;
             while (zs > 1 && px * zs * 96ull > (2ull << 30)) --zs;
         }
@@ -374,7 +375,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
                 c->hit_pixels_cap = pixels * zs;
             }
             a.z_splits = zs; a.hit_entries = c->d_hit_entries; a.hit_counts = c->d_hit_counts; a.hit_cap = kHitCap;
-            ppt = 8;
+            ppt = srt::kSplitPixels;
         } else ppt = choose_ppt(c, params, a.n_blocks * 16);
     }
     SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
@@ -907,7 +908,7 @@ int srt_debug_ffma_peak(srt_ctx* c, int repeats, float* tflops_out)
 // diagnostic: force the number of triangle-range splits of the filtered kernel (0 = heuristic)
 int srt_debug_force_splits(srt_ctx* c, int z_splits)
 {
-    if (!c || z_splits < 0 || z_splits > 16) return SRT_ERR_INVALID;
+    if (!c || z_splits < 0 || z_splits > 64) return SRT_ERR_INVALID;
     c->force_z_splits = z_splits;
     return SRT_OK;
 }

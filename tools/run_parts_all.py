@@ -21,7 +21,7 @@ for part in range(n_parts):
         ctx.render_lbuffer_interleaved_device(p, n_parts, part, slot.data_ptr()); ms.append(ctx.timing().render_ms)
     out.append(round(min(ms[1:]), 4))
 print("parts", n_parts, "per-part ms", out, "sum", round(sum(out), 3), flush=True)
-for zs in (1, 4, 8, 12, 16):
+for zs in (4, 8, 12, 16, 24, 32, 48):
     ctx.force_splits(zs)
     ms = []
     for _ in range(4):
