@@ -259,6 +259,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    per_rank_ms = []          # one list per timed() call: mean ms per step on every rank
+
     def timed(fn, steps, warmup, sync_each):
         for _ in range(warmup):
             fn()
@@ -282,6 +284,9 @@ def run_ours(args):
             ms = max(ms, wall * 1e3)            # host work (pre-pack) is part of the end-to-end time
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
+            every = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            per_rank_ms.append([float(v.item()) / steps for v in every])
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -339,6 +344,12 @@ def run_ours(args):
     value = tests_frame * args.steps / (total_ms * 1e-3)
     e2e_value = tests_frame * e2e_steps / (e2e_ms * 1e-3)
     kt = float(np.mean(kern_ms)) * 1e-3
+    per_rank_kernel = None
+    if world > 1:
+        kt_t = torch.tensor([kt * 1e3], dtype=torch.float64, device=dev)
+        every = [torch.zeros_like(kt_t) for _ in range(world)]
+        dist.all_gather(every, kt_t)
+        per_rank_kernel = [round(float(v.item()), 4) for v in every]
     band_tests = float(my_rows) * W * ntri
     achieved_tf = band_tests * F_ALG / kt / 1e12
     peak, peak_src = (peak_tf, "FFMA probe on this GPU (srt_debug_ffma_peak)") if peak_tf > 1 else \
@@ -377,6 +388,8 @@ def run_ours(args):
                          "flop_per_test": F_ALG, "tests_per_launch": band_tests},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "per_rank": None if world == 1 else {"render_kernel_ms": per_rank_kernel,
+                                                 "step_ms": [round(v, 4) for v in per_rank_ms[0]]},
             "accelerated": {"kernel": acc_kernel_used, "kernel_name": "SRT_KERNEL_CULLED (bins + CTA tiles + pixel runs, identical results)",
                             "ms_per_step": acc_ms / args.steps, "value": tests_frame * args.steps / (acc_ms * 1e-3),
                             "unit": "tests/s (pairs resolved, most of them by a conservative box test)",

@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
         if (row_ok) {
 #pragma unroll
             for (int k = 0; k < P; ++k)
-                if (col0 + k < W) a.hit_counts[((size_t)orow * W + col0 + k) * a.z_splits + cta.z] = hits[k];
+                if (col0 + k < W) a.hit_counts[(size_t)cta.z * a.hit_pixels + (size_t)orow * W + col0 + k] = hits[k];   // [slice][pixel]: coalesced
         }
     } else if (a.mode != 0) {
         if (row_ok) {
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
         uint2 e[kMaxList];
         uint32_t n = 0;
         for (uint32_t z = 0; z < a.z_splits; ++z) {
-            const uint32_t cnt = a.hit_counts[p * a.z_splits + z];
+            const uint32_t cnt = a.hit_counts[(size_t)z * a.hit_pixels + p];
             if (cnt > a.hit_cap || n + cnt > kMaxList) { overflow = true; break; }
             const uint2* src = a.hit_entries + (p * a.z_splits + z) * a.hit_cap;
             for (uint32_t i = 0; i < cnt; ++i) e[n++] = src[i];

@@ -76,7 +76,8 @@ struct RenderArgs {
     // lbuffer.cxx:788-809 in the reference's order, so the result is bit-identical to the unsplit kernel.
     uint32_t z_splits;
     uint2* hit_entries;      // [pixel][z_splits][hit_cap]: one sub-list per (pixel, slice), written by its only owner
-    uint32_t* hit_counts;    // [pixel][z_splits]: entries appended (may exceed hit_cap: overflow -> exact recompute)
+    uint32_t* hit_counts;    // [z_splits][hit_pixels]: entries appended (may exceed hit_cap: overflow -> exact recompute)
+    size_t hit_pixels;       // pixels of the launch's output index range
     uint32_t hit_cap;
     // Culled kernel (SRT_KERNEL_CULLED): per-bin triangle lists.  A bin is kBinCols columns x bin_blocks 16-row blocks
     // of this launch's grid; bin_entries[bin * bin_cap + M.first + i], i < bin_counts[bin * n_meshes + m], are the

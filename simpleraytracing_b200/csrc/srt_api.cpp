@@ -375,6 +375,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
                 c->hit_pixels_cap = pixels * zs;
             }
             a.z_splits = zs; a.hit_entries = c->d_hit_entries; a.hit_counts = c->d_hit_counts; a.hit_cap = kHitCap;
+            a.hit_pixels = pixels;
             ppt = srt::kSplitPixels;
         } else ppt = choose_ppt(c, params, a.n_blocks * 16);
     }
