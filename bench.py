@@ -381,9 +381,9 @@ def run_ours(args):
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one full-frame launch, ncu --set full
-                         # (profiles/r01_ncu_filtered_final_2048.txt: 57 MB read + 106 MB written, mostly hit-list
+                         # (profiles/r01_ncu_filtered_final_2048.txt: 61 MB read + 175 MB written, mostly hit-list
                          # bookkeeping and local-memory accumulators; algorithmic output is 16.8 MB); null for other shapes
-                         "traffic": 1.62e8 if (world == 1 and W == 2048) else None, "peak_source": peak_src,
+                         "traffic": 2.36e8 if (world == 1 and W == 2048) else None, "peak_source": peak_src,
                          "kernel": "lbuffer_filtered_kernel", "kernel_ms": kt * 1e3,
                          "flop_per_test": F_ALG, "tests_per_launch": band_tests},
             "cpu_baseline": cpu,
