@@ -216,7 +216,8 @@ int  srt_debug_shaded_buffers(srt_ctx* ctx, float* z_out, int32_t* tri_id_out);
 int  srt_last_timing(srt_ctx* ctx, srt_timing* out);
 /* Diagnostic: make renders count the pairs that reach the exact path (costs one atomic per CTA). */
 int  srt_debug_count_exact(srt_ctx* ctx, int enable);
-/* Diagnostic: force the filtered kernel's triangle-range split count (hit-list merge); 0 = heuristic. */
+/* Diagnostic: force the filtered kernel's triangle-range split count (hit-list merge); 0 = heuristic.
+ * -1: let srt_params.pixels_per_thread = 8 / 16 choose the run length of split launches (tuning sweeps); -2: off. */
 int  srt_debug_force_splits(srt_ctx* ctx, int z_splits);
 /* Diagnostic: measured FP32 FMA throughput of the context's GPU in TFLOP/s (the roofline denominator
  * bench.py reports against; MEASURED_PEAKS.json has no FP32 figure). */

@@ -1278,9 +1278,9 @@ static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const bool small = (size_t)grid.x * grid.y * grid.z <= (size_t)SRT_MIN_CTAS_SMALL * sms;
-    if (a.hit_entries) {                                   // split launches always use P = kSplitPixels
-        if (P != kSplitPixels) return cudaErrorInvalidValue;
-        return launch_filtered_b<kSplitPixels, SRT_MIN_CTAS, true>(a, grid, smem, s);
+    if (a.hit_entries) {                                   // split launches use runs of 8 or 16 pixels
+        if constexpr (P == 8 || P == 16) return launch_filtered_b<P, SRT_MIN_CTAS, true>(a, grid, smem, s);
+        else return cudaErrorInvalidValue;
     }
     return small ? launch_filtered_b<P, SRT_MIN_CTAS_SMALL, false>(a, grid, smem, s) : launch_filtered_b<P, SRT_MIN_CTAS, false>(a, grid, smem, s);
 }

@@ -26,6 +26,9 @@
 #error "build srt_api.cpp without -mfma/-march=native"
 #endif
 
+#ifndef SRT_SPLIT16_MIN_TILES
+#define SRT_SPLIT16_MIN_TILES 384   // 128 x 16-pixel tiles in a launch from which split launches use 16-pixel runs
+#endif
 #ifndef SRT_RESIDENT_CTAS
 #define SRT_RESIDENT_CTAS 8      // CTAs of the filtered kernel resident per SM (64 registers)
 #endif
@@ -83,6 +86,7 @@ struct srt_ctx {
     // hit lists for split launches (small grids)
     uint2* d_hit_entries = nullptr; uint32_t* d_hit_counts = nullptr; size_t hit_pixels_cap = 0;
     int force_z_splits = 0;              // diagnostic override: 0 = heuristic
+    bool split_forced_ppt = false;       // diagnostic: pixels_per_thread = 8 / 16 selects the run length of SPLIT launches
     // per-bin triangle lists of the culled kernel
     uint32_t* d_bin_entries = nullptr; uint32_t* d_bin_counts = nullptr; size_t bin_entries_cap = 0, bin_counts_cap = 0;
     bool counters_pending = false, timing_pending = false;
@@ -348,15 +352,23 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     if (kernel == SRT_KERNEL_FILTERED) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-        const uint32_t tile_w = 8u * (uint32_t)srt::kSplitPixels;                    // CTA width of a split launch
+        // Pixels per thread of a split launch: runs of 16 halve the per-run overhead (5.7 vs 7.8 ms per 2048^2 frame), but
+        // their CTAs are twice as heavy where the slow path runs, and a grid of only a few hundred tiles cannot average
+        // that out: the 8 shares of the 2048^2 frame took 0.90 ... 1.12 ms with 16-pixel runs against an even 1.03-1.06 ms
+        // with 8-pixel runs, and the frame is done when the slowest rank is.  params->pixels_per_thread = 8 / 16 forces one.
+        const uint64_t tiles16 = (uint64_t)((cam.width + 127) / 128) * a.n_blocks;
+        const int split_p = params->pixels_per_thread == 8 ? 8 : params->pixels_per_thread == 16 ? 16
+                          : (tiles16 >= (uint64_t)SRT_SPLIT16_MIN_TILES ? 16 : 8);
+        const uint32_t tile_w = 8u * (uint32_t)split_p;                              // CTA width of a split launch
         const uint64_t ctas8 = (uint64_t)((cam.width + tile_w - 1) / tile_w) * a.n_blocks;
+        const bool auto_split = params->pixels_per_thread == 0 || (c->split_forced_ppt && (params->pixels_per_thread == 8 || params->pixels_per_thread == 16));
         // Shorter CTAs in more waves balance the SMs better (CTA run times vary with their slow-path work) and keep
         // small grids -- a rank's share of a multi-GPU frame is only a wave or two of CTAs -- at full occupancy:
         // aim for ~12 waves (profiles/r01_splits.txt: N = 8 share 2.00 ms split vs 2.53 ms unsplit, ideal 1.90 ms;
         // full 2048^2 frame 14.8 ms vs 15.2 ms).  The hit lists cost 96 B per (pixel, slice): capped at 2 GB.
         const uint64_t slots = (uint64_t)sms * SRT_RESIDENT_CTAS;
         uint32_t zs = 1;
-        if (mode == 0 && params->pixels_per_thread == 0 && ctas8 > 0) {
+        if (mode == 0 && auto_split && ctas8 > 0) {
             zs = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, (12 * slots + ctas8 / 2) / ctas8));
             const uint64_t px = (uint64_t)(parts == 0 ? cam.height : a.n_blocks * 16) * cam.width;
             while (zs > 1 && px * zs * 96ull > (2ull << 30)) --zs;
@@ -376,7 +388,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
             }
             a.z_splits = zs; a.hit_entries = c->d_hit_entries; a.hit_counts = c->d_hit_counts; a.hit_cap = kHitCap;
             a.hit_pixels = pixels;
-            ppt = srt::kSplitPixels;
+            ppt = split_p;
         } else ppt = choose_ppt(c, params, a.n_blocks * 16);
     }
     SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
@@ -909,7 +921,8 @@ int srt_debug_ffma_peak(srt_ctx* c, int repeats, float* tflops_out)
 // diagnostic: force the number of triangle-range splits of the filtered kernel (0 = heuristic)
 int srt_debug_force_splits(srt_ctx* c, int z_splits)
 {
-    if (!c || z_splits < 0 || z_splits > 64) return SRT_ERR_INVALID;
+    if (!c || z_splits < -2 || z_splits > 64) return SRT_ERR_INVALID;
+    if (z_splits < 0) { c->split_forced_ppt = (z_splits == -1); return SRT_OK; }   // -1: pixels_per_thread 8 / 16 picks the split run length; -2: off
     c->force_z_splits = z_splits;
     return SRT_OK;
 }
