@@ -11,8 +11,14 @@
 // computed with separately rounded IEEE binary32 operations in the reference's
 // order (__fmul_rn / __fadd_rn / __fsub_rn / __fdiv_rn / __fsqrt_rn are never
 // contracted into FMAs and are unaffected by fast-math flags).  The FMA-contracted
-// arithmetic of the filtered kernel only ever REJECTS pairs that provably miss
-// ("filter proof"); it never decides a hit and never produces a value.
+// binary32 / binary16 arithmetic of the filter (filtered kernel, bin pass, culled
+// kernel) only ever REJECTS pairs that provably miss ("filter proof"); it
+// never decides a hit and never produces a value.
+//
+// Kernels: lbuffer_exact_kernel (reference sequence for every pair, + audit of the filter),
+// lbuffer_filtered_kernel (brute force: conservative gate per pair) + resolve_hits_kernel,
+// bin_kernel + lbuffer_culled_kernel (the same gate applied to boxes of pixels first),
+// shade_kernel, repair_kernel, deinterleave_kernel, prepack_kernel, offsets_kernel.
 #include "kernels.h"
 
 #include <cfloat>
@@ -244,10 +250,10 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 // survivors (rare, spatially coherent) run level 1 and then the exact reference sequence.
 //
 // Loop shape (driven by the ncu source views under profiles/):
-//  * the next group's level-0 coefficients are prefetched into registers while the current group is
-//    evaluated (no LDS latency on the critical path);
-//  * the vote on a group's survivors is taken one iteration later, when its FMNMX3 chain has long
-//    retired (no FMNMX3 -> FSETP -> VOTE -> BRA stall); the last group of a tile is resolved before
+//  * the next group's per-thread level-0 state (Level0<P>: 4 registers for even P) is prepared while the
+//    current group is evaluated (no LDS latency on the critical path, no raw coefficients kept live);
+//  * the vote on a group's survivors is taken one iteration later, when its min/compare chain has long
+//    retired (no compare -> VOTE -> BRA stall); the last group of a tile is resolved before
 //    the stage is released, so the slow path can read its records from shared memory;
 //  * the slow path is an out-of-line function; it first applies the level-1 triangle-footprint test
 //    to the END POINTS of the thread's pixel run (edge functions are affine in x: outside the same
