@@ -826,6 +826,10 @@ __device__ __noinline__ void culled_process(const DevCamera& cam, const CulledAr
 #ifndef SRT_CULLED_MIN_CTAS
 #define SRT_CULLED_MIN_CTAS 4
 #endif
+#ifndef SRT_CULLED_CTA_LIST
+#define SRT_CULLED_CTA_LIST 1
+#endif
+constexpr uint32_t kCtaList = 1024;
 __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kernel(const __grid_constant__ RenderArgs a)
 {
     constexpr int P = 8;
@@ -833,6 +837,10 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
     __shared__ uint32_t s_idx[4][32];
     __shared__ float s_acc[4][3 * 256];         // per-warp accumulators: dist | ssum | hits (z | id in closest-hit mode)
     __shared__ uint8_t s_queue[4][256];
+#if SRT_CULLED_CTA_LIST
+    __shared__ uint32_t s_list[kCtaList];       // triangles of the bin that may touch the CTA tile, ascending
+    __shared__ uint32_t s_wcnt[4];
+#endif
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const CtaCoord cta = cta_coord();
@@ -852,6 +860,12 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
     const float txc = 0.5f * (float)(wcol0 + tc1) + a.cam.xc, thx = 0.5f * (float)(tc1 - wcol0);
     const float tyc = 0.5f * (float)(wrow0 + tr1) + a.cam.yc, thy = 0.5f * (float)(tr1 - wrow0);
     const uint32_t rc1 = min(W, col0 + P) - 1;
+#if SRT_CULLED_CTA_LIST
+    // CTA tile box (64 x 16 pixels), clamped to the frame
+    const uint32_t cc0 = cta.x * 64, cc1 = min(W, cc0 + 64) - 1, cr1 = min(a.row_end, row0 + 16) - 1;
+    const float cxc = 0.5f * (float)(cc0 + cc1) + a.cam.xc, chx = 0.5f * (float)(cc1 - cc0);
+    const float cyc = 0.5f * (float)(row0 + cr1) + a.cam.yc, chy = 0.5f * (float)(cr1 - row0);
+#endif
 
     float Lval[P];
 #pragma unroll
@@ -871,7 +885,7 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
             for (int k = 0; k < P; ++k) { acc[k * 32 + lane] = 0.0f; acc[256 + k * 32 + lane] = 0.0f; acc[512 + k * 32 + lane] = 0.0f; }
         }
         __syncwarp();
-        if (M.contributes && M.n > 0 && warp_on) {
+        if (M.contributes && M.n > 0) {
             CulledArgs sa;
             sa.exact = M.exact; sa.first = M.first; sa.mode = a.mode;
             sa.y = (float)row + a.cam.yc; sa.x0 = (float)col0 + a.cam.xc;
@@ -880,6 +894,71 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
             sa.run_xc = 0.5f * (float)(col0 + rc1) + a.cam.xc; sa.run_hx = active ? 0.5f * (float)(rc1 - col0) : 0.0f;
             const uint32_t cnt = __ldg(a.bin_counts + (size_t)bin * a.n_meshes + m);
             const uint32_t* list = a.bin_entries + (size_t)bin * a.bin_cap + M.first;
+#if SRT_CULLED_CTA_LIST
+            // Phase A (whole CTA, equal work per warp): cull the bin's list against the CTA tile, 128 entries per step, into
+            // an ordered index list in shared memory.  Phase B (warps independent): each warp culls that short list against
+            // its own 32 x 8 tile and processes the survivors.  A list longer than kCtaList is handled in rounds.
+            uint32_t idx = 0; float4 fa, fb, ga, gb;
+            if (tid < cnt) {
+                idx = __ldg(list + tid);
+                const float4* q = M.filt + 4 * (size_t)idx;
+                fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3);
+            }
+            uint32_t i0 = 0;
+            while (i0 < cnt) {                                                 // rounds (CTA-uniform)
+                uint32_t n_list = 0;
+                while (i0 < cnt && n_list + 128 <= kCtaList) {
+                    const bool keep = i0 + tid < cnt && box_may_hit(fa, fb, ga, gb, cxc, cyc, chx, chy);
+                    const uint32_t my_idx = idx;
+                    const uint32_t in = i0 + 128 + tid;                       // next step's records in flight
+                    if (in < cnt) {
+                        idx = __ldg(list + in);
+                        const float4* q = M.filt + 4 * (size_t)idx;
+                        fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3);
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                    if (lane == 0) s_wcnt[warp] = __popc(bal);
+                    __syncthreads();
+                    uint32_t off = 0, tot = 0;
+#pragma unroll
+                    for (uint32_t w = 0; w < 4; ++w) { const uint32_t c = s_wcnt[w]; off += w < warp ? c : 0u; tot += c; }
+                    if (keep) s_list[n_list + off + __popc(bal & ((1u << lane) - 1u))] = my_idx;
+                    n_list += tot; i0 += 128;
+                    __syncthreads();                                           // s_wcnt is rewritten; s_list is visible
+                }
+                if (warp_on) {
+                    for (uint32_t j0 = 0; j0 < n_list; j0 += 32) {
+                        const uint32_t j = j0 + lane;
+                        bool keep = false; uint32_t id2 = 0;
+                        float4 ra, rb, rc, rd;
+                        if (j < n_list) {
+                            id2 = s_list[j];
+                            const float4* q = M.filt + 4 * (size_t)id2;     // L1 / L2 hit: phase A has just read it
+                            ra = __ldg(q); rb = __ldg(q + 1); rc = __ldg(q + 2); rd = __ldg(q + 3);
+                            keep = box_may_hit(ra, rb, rc, rd, txc, tyc, thx, thy);
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                        if (bal == 0) continue;
+                        if (keep) {
+                            const uint32_t pos = __popc(bal & ((1u << lane) - 1u));
+                            const float4* eq = M.exact + 4 * (size_t)id2;    // the exact constants travel with the survivor
+                            const float4 e0 = __ldg(eq), e1 = __ldg(eq + 1), e2 = __ldg(eq + 2), e3 = __ldg(eq + 3);
+                            float4* dst = &s_rec[warp][pos][0];
+                            dst[0] = ra; dst[1] = rb; dst[2] = rc; dst[3] = rd; dst[4] = e0; dst[5] = e1; dst[6] = e2; dst[7] = e3;
+                            s_idx[warp][pos] = id2;
+                        }
+                        __syncwarp();
+                        const uint32_t n_w = __popc(bal);
+#pragma unroll 1
+                        for (uint32_t q = 0; q < n_w; ++q)
+                            culled_process(a.cam, sa, &s_rec[warp][q][0], s_idx[warp][q], n_exact);
+                        __syncwarp();                                          // the segment is rewritten by the next chunk
+                    }
+                }
+                __syncthreads();                                               // every warp is done with s_list
+            }
+#else
+            if (warp_on) {
             // software pipeline: the next 32 entries' records are in flight while the current ones are processed
             uint32_t idx = 0; float4 fa, fb, ga, gb;
             if (lane < cnt) {
@@ -912,6 +991,8 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
                     culled_process(a.cam, sa, &s_rec[warp][q][0], s_idx[warp][q], n_exact);
                 __syncwarp();                                  // the segment is rewritten by the next chunk
             }
+            }
+#endif
         }
         if (a.mode != 0) continue;
         const bool out_ok = m == 0 && row_ok;
