@@ -229,6 +229,13 @@ def run_ours(args):
             except Exception as exc:                      # no peer access on this box
                 peers = None
                 assembly += f" (symmetric memory unavailable: {type(exc).__name__})"
+            # every rank must take the same path (the two assemblies synchronise differently): fall back everywhere
+            # if any rank could not map its peers
+            ok = torch.tensor([1 if peers is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0 and peers is not None:
+                peers = None
+                assembly = "all_gather of slots + de-interleave kernel (symmetric memory unavailable on another rank)"
     image = torch.empty(H * W, dtype=torch.float32, device=dev)
     host_image = torch.empty(H * W, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
