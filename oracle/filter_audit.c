@@ -33,13 +33,40 @@ typedef struct {
     uint64_t p0, p1;
     /* out: [0] pairs, [1] survive level0 (tile margin), [2] survive level0 (triangle margin),
      *      [3] survive level1, [4] oracle hits, [5] violations, [6] hits inside a pixel run that the
-     *      run-level test (end points of an aligned 8-pixel run, kernels.cu filtered_slow_path) rejects */
-    uint64_t c[7];
+     *      run-level test (end points of an aligned 8-pixel run, kernels.cu filtered_slow_path) rejects,
+     *      [7] hits inside a box that the box test of the culled kernel rejects (bin 256 x 128, CTA tile
+     *      64 x 16, warp tile 32 x 8, run 8 x 1 of a full-frame launch; kernels.cu box_may_hit) */
+    uint64_t c[8];
 } audit_job;
 
 static _Float16 h_from_bits(uint16_t b) { _Float16 h; memcpy(&h, &b, 2); return h; }
 static _Float16 h_fma(_Float16 a, _Float16 b, _Float16 c) { return (_Float16)((long double)a * (long double)b + (long double)c); }
 static _Float16 h_abs(_Float16 a) { return a < 0 ? -a : a; }
+/* kernels.cu box_may_hit, same operation order (fmaf == FFMA; the plain products and the final scaling are separate
+ * roundings there as well) */
+__attribute__((target("fma"))) static int box_may_hit(const float* f, const float* g, float xc, float yc, float hx, float hy)
+{
+    const float infl = 1.0000038f;
+    const float Dc = fabsf(__builtin_fmaf(f[3], xc, __builtin_fmaf(f[4], yc, f[5])));
+    const float rD = __builtin_fmaf(fabsf(f[3]), hx, fabsf(f[4]) * hy);
+    const float Y1 = fabsf(__builtin_fmaf(f[0], xc, __builtin_fmaf(f[1], yc, f[2])));
+    const float Y2 = fabsf(__builtin_fmaf(g[0], xc, __builtin_fmaf(g[1], yc, g[2])));
+    const float Y3 = fabsf(__builtin_fmaf(g[4], xc, __builtin_fmaf(g[5], yc, g[6])));
+    const float s1 = __builtin_fmaf(fabsf(f[0]), hx, __builtin_fmaf(fabsf(f[1]), hy, __builtin_fmaf(2.0f, f[6], rD))) * infl;
+    const float s2 = __builtin_fmaf(fabsf(g[0]), hx, __builtin_fmaf(fabsf(g[1]), hy, __builtin_fmaf(2.0f, g[3], rD))) * infl;
+    const float s3 = __builtin_fmaf(fabsf(g[4]), hx, __builtin_fmaf(fabsf(g[5]), hy, __builtin_fmaf(2.0f, g[7], rD))) * infl;
+    return !(Y1 - Dc > s1) && !(Y2 - Dc > s2) && !(Y3 - Dc > s3);
+}
+
+/* box [c0, c1] x [r0, r1] of pixel centres, clamped to the frame like the kernels clamp theirs */
+__attribute__((target("fma"))) static int box_level(const float* f, const float* g, uint32_t W, uint32_t H, float xc0, float yc0,
+                                                   uint32_t col, uint32_t row, uint32_t bw, uint32_t bh)
+{
+    uint32_t c0 = col - col % bw, c1 = c0 + bw, r0 = row - row % bh, r1 = r0 + bh;
+    c1 = (c1 < W ? c1 : W) - 1; r1 = (r1 < H ? r1 : H) - 1;
+    return box_may_hit(f, g, 0.5f * (float)(c0 + c1) + xc0, 0.5f * (float)(r0 + r1) + yc0, 0.5f * (float)(c1 - c0), 0.5f * (float)(r1 - r0));
+}
+
 __attribute__((target("fma"))) static void* audit_worker(void* arg)
 {
     audit_job* j = (audit_job*)arg;
@@ -84,6 +111,10 @@ __attribute__((target("fma"))) static void* audit_worker(void* arg)
             j->c[0]++; j->c[1] += s0t; j->c[2] += s0; j->c[3] += s1; j->c[4] += hit;
             if (hit && !s1) j->c[5]++;
             if (hit) {
+                /* culled kernel: every box that contains this pixel must let the triangle through */
+                if (!box_level(f, g, j->W, j->H, xc, yc, col, row, 256, 128) || !box_level(f, g, j->W, j->H, xc, yc, col, row, 64, 16) ||
+                    !box_level(f, g, j->W, j->H, xc, yc, col, row, 32, 8) || !box_level(f, g, j->W, j->H, xc, yc, col, row, 8, 1))
+                    j->c[7]++;
                 /* run-level test of the aligned run of 8 pixels this pixel belongs to */
                 const uint32_t c0 = col & ~7u;
                 const float xa = (float)c0 + xc, xb = (float)(c0 + 7) + xc;
@@ -107,7 +138,7 @@ __attribute__((target("fma"))) static void* audit_worker(void* arg)
 
 int oracle_filter_audit(const float* tri, uint32_t n, const oracle_camera* cam, uint32_t W, uint32_t H,
                         const float* filt, const float* filt2, const float* tile_m, uint32_t tile_tris,
-                        uint64_t pixel_begin, uint64_t pixel_end, int n_threads, uint64_t counts[7])
+                        uint64_t pixel_begin, uint64_t pixel_end, int n_threads, uint64_t counts[8])
 {
     if (!__builtin_cpu_supports("fma")) return -1;
     if (n_threads < 1) n_threads = 1;
@@ -122,10 +153,10 @@ int oracle_filter_audit(const float* tri, uint32_t n, const oracle_camera* cam, 
         j->p1 = pixel_begin + total * (uint64_t)(i + 1) / (uint64_t)n_threads;
         pthread_create(&tid[i], NULL, audit_worker, j);
     }
-    memset(counts, 0, 7 * sizeof(uint64_t));
+    memset(counts, 0, 8 * sizeof(uint64_t));
     for (int i = 0; i < n_threads; ++i) {
         pthread_join(tid[i], NULL);
-        for (int k = 0; k < 7; ++k) counts[k] += jobs[i].c[k];
+        for (int k = 0; k < 8; ++k) counts[k] += jobs[i].c[k];
     }
     free(jobs); free(tid);
     return 0;

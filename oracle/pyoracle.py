@@ -201,11 +201,11 @@ class Oracle:
 
     def filter_audit(self, tri, cam, W, H, packed, pixel_range=None, threads=None):
         """Audit the product's packed filter constants against the oracle's intersect.
-        -> dict(pairs, survive0_tile, survive0, survive1, hits, violations, run_violations)"""
+        -> dict(pairs, survive0_tile, survive0, survive1, hits, violations, run_violations, box_violations)"""
         tri = np.ascontiguousarray(tri, np.float32).reshape(-1)
         n = tri.size // 9
         b, e = (0, W * H) if pixel_range is None else pixel_range
-        counts = np.zeros(7, np.uint64)
+        counts = np.zeros(8, np.uint64)
         rc = self.lib.oracle_filter_audit(tri, n, C.byref(cam), W, H,
                                           np.ascontiguousarray(packed["filt"], np.float32).reshape(-1),
                                           np.ascontiguousarray(packed["filt2"], np.float32).reshape(-1),
@@ -213,7 +213,7 @@ class Oracle:
                                           threads or os.cpu_count() or 1, counts.ctypes.data_as(C.c_void_p))
         if rc:
             raise RuntimeError("host CPU has no FMA: cannot emulate the kernel's FFMA sequence")
-        return dict(zip(("pairs", "survive0_tile", "survive0", "survive1", "hits", "violations", "run_violations"),
+        return dict(zip(("pairs", "survive0_tile", "survive0", "survive1", "hits", "violations", "run_violations", "box_violations"),
                         map(int, counts)))
 
     def partition(self, total, n):

@@ -102,7 +102,7 @@ def test_filter_never_rejects_a_hit_dragon(srtlib, oracle, dragon, size):
     pk = srtlib.debug_prepack(dragon, cam)
     a = oracle.filter_audit(dragon, oracle.camera(dragon), size, size, pk)
     assert a["pairs"] == size * size * len(dragon)
-    assert a["violations"] == 0 and a["run_violations"] == 0
+    assert a["violations"] == 0 and a["run_violations"] == 0 and a["box_violations"] == 0
     assert a["hits"] > 0 and a["survive1"] >= a["hits"]
     assert a["survive0_tile"] < 0.03 * a["pairs"]          # the filter must actually filter
     assert a["survive1"] < 10 * a["hits"]
@@ -132,6 +132,19 @@ def _adversarial_mesh(cam_o, oracle, W, H, rng):
     return np.asarray(tris, np.float32)
 
 
+def test_box_tests_never_reject_a_hit_ragged_frame(srtlib, oracle, dragon):
+    """The culled kernel's box tests (bin 256 x 128, CTA tile 64 x 16, warp tile 32 x 8, run 8 x 1; boxes clamped to the
+    frame) emulated on the CPU against the oracle, on a frame whose size is not a multiple of any box size and which is
+    larger than one bin in both directions."""
+    W, H = 300, 150
+    lo, hi = srtlib.scene_bbox([(dragon, 0.1)])
+    cam = srtlib.camera_from_bbox(lo, hi, W, H)
+    tri = np.ascontiguousarray(dragon[::8])
+    pk = srtlib.debug_prepack(tri, cam)
+    a = oracle.filter_audit(tri, oracle.camera(dragon), W, H, pk)
+    assert a["hits"] > 1500 and a["box_violations"] == 0 and a["violations"] == 0 and a["run_violations"] == 0
+
+
 def test_filter_never_rejects_a_hit_adversarial(srtlib, oracle, dragon):
     rng = np.random.default_rng(11)
     cam_o = oracle.camera(dragon)
@@ -141,7 +154,7 @@ def test_filter_never_rejects_a_hit_adversarial(srtlib, oracle, dragon):
     cam = srtlib.camera_from_bbox(lo, hi, W, H)
     pk = srtlib.debug_prepack(tri, cam)
     a = oracle.filter_audit(tri, cam_o, W, H, pk)
-    assert a["violations"] == 0 and a["run_violations"] == 0 and a["hits"] > 500
+    assert a["violations"] == 0 and a["run_violations"] == 0 and a["box_violations"] == 0 and a["hits"] > 500
 
 
 def test_unfilterable_triangles_always_survive(srtlib, oracle, dragon):
