@@ -108,7 +108,8 @@ typedef struct {
     uint32_t repair_depth;      /* 4 (lbuffer.cxx:339)                                                */
     uint32_t kernel;            /* srt_kernel                                                         */
     uint32_t flags;
-    uint32_t pixels_per_thread; /* 0 = auto; tuning knob of the filtered kernel (1 ... 8, 16)        */
+    uint32_t pixels_per_thread; /* 0 = auto; tuning knob of the filtered kernel: the box of pixels one thread tests per
+                                   triangle, box width | box height << 8 | boxes per thread << 16 (e.g. 0x020110)  */
 } srt_params;
 
 typedef struct {
@@ -216,20 +217,19 @@ int  srt_debug_shaded_buffers(srt_ctx* ctx, float* z_out, int32_t* tri_id_out);
 int  srt_last_timing(srt_ctx* ctx, srt_timing* out);
 /* Diagnostic: make renders count the pairs that reach the exact path (costs one atomic per CTA). */
 int  srt_debug_count_exact(srt_ctx* ctx, int enable);
-/* Diagnostic: force the filtered kernel's triangle-range split count (hit-list merge); 0 = heuristic.
- * -1: let srt_params.pixels_per_thread = 8 / 16 choose the run length of split launches (tuning sweeps); -2: off. */
+/* Diagnostic: force the filtered kernel's triangle-range slice count (grid.z); 0 = heuristic. */
 int  srt_debug_force_splits(srt_ctx* ctx, int z_splits);
-/* Diagnostic: measured FP32 FMA throughput of the context's GPU in TFLOP/s (the roofline denominator
- * bench.py reports against; MEASURED_PEAKS.json has no FP32 figure). */
+/* Diagnostic: measured FP32 FMA throughput of the context's GPU in TFLOP/s. */
 int  srt_debug_ffma_peak(srt_ctx* ctx, int repeats, float* tflops_out);
+/* Diagnostic: padding granularity of packed meshes (triangles) and the default box of the filtered kernel. */
+int  srt_debug_pack_info(uint32_t* pad_to, uint32_t* box_w, uint32_t* box_h);
 /* Diagnostic, host only (no GPU needed): the packed per-triangle constants the kernels stream.
- * exact16: 16 floats / triangle; filt8, filt2_8: 8 floats / padded triangle (padding = multiple of 2);
- * tile_m: one margin per tile of srt_debug_tile_triangles() triangles (+1 spare). Any output may be NULL. */
-int  srt_debug_tile_triangles(void);
+ * exact16: 16 floats / triangle; filt12: 12, filt2_8: 8 floats / padded triangle (filt12[7], [11] = the box bounds R, R2
+ * of the two level-0 strips for a box of box_w x box_h pixels, 0 = default box).  Any output may be NULL. */
+int  srt_debug_prepack(const float* vertices, uint32_t n_triangles, const srt_camera* cam, uint32_t box_w, uint32_t box_h,
+                       float* exact16, float* filt12, float* filt2_8, uint32_t* n_padded, uint32_t* n_unfilterable);
 /* Diagnostic: the same arrays as computed ON THE GPU for mesh `mesh` of the context's scene. */
-int  srt_debug_download_packed(srt_ctx* ctx, int mesh, float* exact16, float* filt8, float* filt2_8, float* tile_m);
-int  srt_debug_prepack(const float* vertices, uint32_t n_triangles, const srt_camera* cam, float* exact16,
-                       float* filt8, float* filt2_8, float* tile_m, uint32_t* n_padded, uint32_t* n_unfilterable);
+int  srt_debug_download_packed(srt_ctx* ctx, int mesh, float* exact16, float* filt12, float* filt2_8);
 
 #ifdef __cplusplus
 }

@@ -4,10 +4,8 @@
  * TEST INFRASTRUCTURE ONLY (see srt_oracle.c).  Takes the packed per-triangle
  * filter constants produced by the product's host pre-pack (srt_debug_prepack)
  * and, for every (pixel, triangle) pair of a frame, evaluates the filter with
- * the same fused-multiply-add sequence the CUDA kernel uses (fmaf == one
- * rounding, like FFMA; the binary16 steps of the level-0 gate are emulated with
- * _Float16 and an exact long double intermediate == one rounding, like HFMA2)
- * next to the oracle's Ray::intersect restatement.
+ * the same fused-multiply-add sequence the CUDA kernels use (fmaf == one
+ * rounding, like FFMA) next to the oracle's Ray::intersect restatement.
  * A "violation" is a pair the filter rejects although the oracle reports a hit;
  * the filter is only valid if there are none.
  */
@@ -29,19 +27,17 @@ extern int oracle_intersect(const float o[3], const float d[3], const float tri9
 
 typedef struct {
     const float* tri; uint32_t n; const oracle_camera* cam; uint32_t W, H;
-    const float* filt; const float* filt2; const float* tile_m; uint32_t tile_tris;
+    const float* filt; const float* filt2; uint32_t box_w, box_h;
     uint64_t p0, p1;
-    /* out: [0] pairs, [1] survive level0 (tile margin), [2] survive level0 (triangle margin),
-     *      [3] survive level1, [4] oracle hits, [5] violations, [6] hits inside a pixel run that the
-     *      run-level test (end points of an aligned 8-pixel run, kernels.cu filtered_slow_path) rejects,
-     *      [7] hits inside a box that the box test of the culled kernel rejects (bin 256 x 128, CTA tile
-     *      64 x 16, warp tile 32 x 8, run 8 x 1 of a full-frame launch; kernels.cu box_may_hit) */
+    /* out: [0] pairs, [1] pairs whose box survives the level-0 box gate of the filtered kernel (|Y(c)| - |D(c)| > R for
+     *      either of its two strips, at the centre of the aligned box_w x box_h box, clamped to the frame; kernels.cu scan_tile), [2] survive the
+     *      per-pixel level-0 strip as well, [3] survive all three per-pixel strips, [4] oracle hits, [5] violations:
+     *      hits that the level-0 box gate or a per-pixel strip rejects, [6] hits that the three-strip test of the
+     *      filtered kernel's box rejects (kernels.cu drain_q1), [7] hits inside a box that the box test of the culled
+     *      kernel rejects (bin 256 x 128, CTA tile 64 x 16, warp tile 32 x 8, run 8 x 1 of a full-frame launch) */
     uint64_t c[8];
 } audit_job;
 
-static _Float16 h_from_bits(uint16_t b) { _Float16 h; memcpy(&h, &b, 2); return h; }
-static _Float16 h_fma(_Float16 a, _Float16 b, _Float16 c) { return (_Float16)((long double)a * (long double)b + (long double)c); }
-static _Float16 h_abs(_Float16 a) { return a < 0 ? -a : a; }
 /* kernels.cu box_may_hit, same operation order (fmaf == FFMA; the plain products and the final scaling are separate
  * roundings there as well) */
 __attribute__((target("fma"))) static int box_may_hit(const float* f, const float* g, float xc, float yc, float hx, float hy)
@@ -76,34 +72,25 @@ __attribute__((target("fma"))) static void* audit_worker(void* arg)
         float dA[3], dB[3];
         oracle_make_ray(j->cam, j->W, j->H, row, col, dA, dB);
         const float x = (float)col + xc, y = (float)row + yc;
+        /* the filtered kernel's box of this pixel: aligned box_w x box_h, clamped to the frame */
+        uint32_t c0 = col - col % j->box_w, c1 = c0 + j->box_w, r0 = row - row % j->box_h, r1 = r0 + j->box_h;
+        c1 = (c1 < j->W ? c1 : j->W) - 1; r1 = (r1 < j->H ? r1 : j->H) - 1;
+        const float bxc = 0.5f * (float)(c0 + c1) + xc, byc = 0.5f * (float)(r0 + r1) + yc;
         for (uint32_t k = 0; k < j->n; ++k) {
-            const float* f = j->filt + 8 * (size_t)k;
+            const float* f = j->filt + 12 * (size_t)k;
             const float* g = j->filt2 + 8 * (size_t)k;
-            const float tm = j->tile_m[k / j->tile_tris];
-            /* kernel: X = fma(bx, x, fma(gx, y, ax)); D = fma(bd, x, fma(gd, y, ad)) */
+            /* kernel: Y = fma(bx, x, fma(gx, y, ax)); D = fma(bd, x, fma(gd, y, ad)) */
             const float X1 = __builtin_fmaf(f[0], x, __builtin_fmaf(f[1], y, f[2]));
             const float Dd = __builtin_fmaf(f[3], x, __builtin_fmaf(f[4], y, f[5]));
             const float X2 = __builtin_fmaf(g[0], x, __builtin_fmaf(g[1], y, g[2]));
             const float X3 = __builtin_fmaf(g[4], x, __builtin_fmaf(g[5], y, g[6]));
-            /* level-0 gate for every even run length the kernel is built for: binary32 Y, D at the run's first pixel, one
-             * binary16 step (HFMA2), tau = |D16(x0)| + mh (binary16 margin in the high half of word 7; one HADD2) */
-            uint32_t hw; memcpy(&hw, &f[7], 4);
-            int gate16 = 1;
-            static const uint32_t runs[5] = { 2, 4, 6, 8, 16 };
-            for (int ri = 0; ri < 5; ++ri) {
-                const uint32_t c0 = col - col % runs[ri];
-                const float x0 = (float)c0 + xc;
-                const _Float16 hk = (_Float16)(float)(col - c0);
-                const _Float16 Y16 = h_fma(h_from_bits((uint16_t)(hw & 0xffffu)), hk, (_Float16)__builtin_fmaf(f[0], x0, __builtin_fmaf(f[1], y, f[2])));
-                const _Float16 D16 = (_Float16)__builtin_fmaf(f[3], x0, __builtin_fmaf(f[4], y, f[5]));
-                const _Float16 tau = (_Float16)((long double)h_abs(D16) + (long double)h_from_bits((uint16_t)(hw >> 16)));
-                if (h_abs(Y16) > tau) gate16 = 0;
-            }
-            /* odd pixels-per-thread: the binary32 gate */
-            const int gate32 = (fabsf(Dd) - fabsf(X1)) >= -tm;
-            const int s0t = gate16 && gate32;
+            /* level-0 box gate (scan_tile): row part first, then the column part, |Y| - |D| against the packed R */
+            const float Yc = __builtin_fmaf(f[0], bxc, __builtin_fmaf(f[1], byc, f[2]));
+            const float Dc = __builtin_fmaf(f[3], bxc, __builtin_fmaf(f[4], byc, f[5]));
+            const float Yc2 = __builtin_fmaf(f[8], bxc, __builtin_fmaf(f[9], byc, f[10]));
+            const int s0t = !((fabsf(Yc) - fabsf(Dc) > f[7]) || (fabsf(Yc2) - fabsf(Dc) > f[11]));
             const int s0 = s0t && !(fabsf(X1) > fabsf(Dd) + f[6]);
-            /* level 1 (slow path): the two remaining strips */
+            /* level 1: the two remaining strips */
             const int rej1 = (fabsf(X2) > fabsf(Dd) + g[3]) || (fabsf(X3) > fabsf(Dd) + g[7]);
             const int s1 = s0 && !rej1;
             float t; int st;
@@ -111,25 +98,12 @@ __attribute__((target("fma"))) static void* audit_worker(void* arg)
             j->c[0]++; j->c[1] += s0t; j->c[2] += s0; j->c[3] += s1; j->c[4] += hit;
             if (hit && !s1) j->c[5]++;
             if (hit) {
+                /* filtered kernel, queue stage (drain_q1): three-strip test of the same box */
+                if (!box_may_hit(f, g, bxc, byc, 0.5f * (float)(c1 - c0), 0.5f * (float)(r1 - r0))) j->c[6]++;
                 /* culled kernel: every box that contains this pixel must let the triangle through */
                 if (!box_level(f, g, j->W, j->H, xc, yc, col, row, 256, 128) || !box_level(f, g, j->W, j->H, xc, yc, col, row, 64, 16) ||
                     !box_level(f, g, j->W, j->H, xc, yc, col, row, 32, 8) || !box_level(f, g, j->W, j->H, xc, yc, col, row, 8, 1))
                     j->c[7]++;
-                /* run-level test of the aligned run of 8 pixels this pixel belongs to */
-                const uint32_t c0 = col & ~7u;
-                const float xa = (float)c0 + xc, xb = (float)(c0 + 7) + xc;
-                const float bs = __builtin_fmaf(f[1], y, f[2]), bd = __builtin_fmaf(f[4], y, f[5]);
-                const float b2 = __builtin_fmaf(g[1], y, g[2]), b3 = __builtin_fmaf(g[5], y, g[6]);
-                const float Da = __builtin_fmaf(f[3], xa, bd), Db = __builtin_fmaf(f[3], xb, bd);
-                const float dmax = fmaxf(fabsf(Da), fabsf(Db));
-                const float Sa = __builtin_fmaf(f[0], xa, bs), Sb = __builtin_fmaf(f[0], xb, bs);
-                const float Ua = __builtin_fmaf(g[0], xa, b2), Ub = __builtin_fmaf(g[0], xb, b2);
-                const float Va = __builtin_fmaf(g[4], xa, b3), Vb = __builtin_fmaf(g[4], xb, b3);
-                int out = 0;
-                out |= ((Sa > 0.0f) == (Sb > 0.0f)) && fminf(fabsf(Sa), fabsf(Sb)) > dmax + f[6];
-                out |= ((Ua > 0.0f) == (Ub > 0.0f)) && fminf(fabsf(Ua), fabsf(Ub)) > dmax + g[3];
-                out |= ((Va > 0.0f) == (Vb > 0.0f)) && fminf(fabsf(Va), fabsf(Vb)) > dmax + g[7];
-                if (out) j->c[6]++;
             }
         }
     }
@@ -137,7 +111,7 @@ __attribute__((target("fma"))) static void* audit_worker(void* arg)
 }
 
 int oracle_filter_audit(const float* tri, uint32_t n, const oracle_camera* cam, uint32_t W, uint32_t H,
-                        const float* filt, const float* filt2, const float* tile_m, uint32_t tile_tris,
+                        const float* filt, const float* filt2, uint32_t box_w, uint32_t box_h,
                         uint64_t pixel_begin, uint64_t pixel_end, int n_threads, uint64_t counts[8])
 {
     if (!__builtin_cpu_supports("fma")) return -1;
@@ -148,7 +122,7 @@ int oracle_filter_audit(const float* tri, uint32_t n, const oracle_camera* cam, 
     for (int i = 0; i < n_threads; ++i) {
         audit_job* j = &jobs[i];
         j->tri = tri; j->n = n; j->cam = cam; j->W = W; j->H = H; j->filt = filt; j->filt2 = filt2;
-        j->tile_m = tile_m; j->tile_tris = tile_tris;
+        j->box_w = box_w ? box_w : 1; j->box_h = box_h ? box_h : 1;
         j->p0 = pixel_begin + total * (uint64_t)i / (uint64_t)n_threads;
         j->p1 = pixel_begin + total * (uint64_t)(i + 1) / (uint64_t)n_threads;
         pthread_create(&tid[i], NULL, audit_worker, j);

@@ -103,7 +103,7 @@ class Oracle:
                                            C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_filter_audit.argtypes = [_f32p, C.c_uint32, C.POINTER(Camera), C.c_uint32, C.c_uint32, _f32p, _f32p,
-                                          _f32p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+                                          C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
 
     # scene ---------------------------------------------------------------
     def camera(self, tri):
@@ -201,7 +201,7 @@ class Oracle:
 
     def filter_audit(self, tri, cam, W, H, packed, pixel_range=None, threads=None):
         """Audit the product's packed filter constants against the oracle's intersect.
-        -> dict(pairs, survive0_tile, survive0, survive1, hits, violations, run_violations, box_violations)"""
+        -> dict(pairs, survive0_box, survive0, survive1, hits, violations, box3_violations, box_violations)"""
         tri = np.ascontiguousarray(tri, np.float32).reshape(-1)
         n = tri.size // 9
         b, e = (0, W * H) if pixel_range is None else pixel_range
@@ -209,11 +209,11 @@ class Oracle:
         rc = self.lib.oracle_filter_audit(tri, n, C.byref(cam), W, H,
                                           np.ascontiguousarray(packed["filt"], np.float32).reshape(-1),
                                           np.ascontiguousarray(packed["filt2"], np.float32).reshape(-1),
-                                          np.ascontiguousarray(packed["tile_m"], np.float32), int(packed["tile_tris"]), b, e,
+                                          int(packed["box"][0]), int(packed["box"][1]), b, e,
                                           threads or os.cpu_count() or 1, counts.ctypes.data_as(C.c_void_p))
         if rc:
             raise RuntimeError("host CPU has no FMA: cannot emulate the kernel's FFMA sequence")
-        return dict(zip(("pairs", "survive0_tile", "survive0", "survive1", "hits", "violations", "run_violations", "box_violations"),
+        return dict(zip(("pairs", "survive0_box", "survive0", "survive1", "hits", "violations", "box3_violations", "box_violations"),
                         map(int, counts)))
 
     def partition(self, total, n):

@@ -59,7 +59,7 @@ EXPORTS = [
     "srt_set_meshes", "srt_set_camera", "srt_render_lbuffer", "srt_render_lbuffer_device", "srt_repair",
     "srt_repair_device", "srt_render_xray", "srt_interleave_slot_rows",
     "srt_render_lbuffer_interleaved_device", "srt_deinterleave_device", "srt_render_lbuffer_blocks_device", "srt_render_shaded",
-    "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_force_splits", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_tile_triangles", "srt_debug_download_packed",
+    "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_force_splits", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_pack_info", "srt_debug_download_packed",
 ]
 
 
@@ -115,9 +115,10 @@ class Library:
         L.srt_last_timing.argtypes = [vp, C.POINTER(Timing)]
         L.srt_debug_count_exact.argtypes = [vp, i32]
         L.srt_debug_force_splits.argtypes = [vp, i32]
-        L.srt_debug_download_packed.argtypes = [vp, i32, vp, vp, vp, vp]
+        L.srt_debug_download_packed.argtypes = [vp, i32, vp, vp, vp]
+        L.srt_debug_pack_info.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
         L.srt_debug_ffma_peak.argtypes = [vp, i32, C.POINTER(C.c_float)]
-        L.srt_debug_prepack.argtypes = [vp, u32, C.POINTER(Camera), vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32)]
+        L.srt_debug_prepack.argtypes = [vp, u32, C.POINTER(Camera), u32, u32, vp, vp, vp, C.POINTER(u32), C.POINTER(u32)]
 
     # ---- host-only helpers ---------------------------------------------------
     def default_params(self, **kw):
@@ -190,24 +191,36 @@ class Library:
             raise SrtError(rc, "srt_triangle_normals")
         return out
 
-    def debug_prepack(self, tri, cam):
+    def pack_info(self):
+        """-> (padding granularity in triangles, default box width, default box height) of the filtered kernel"""
+        p, w, h = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self.lib.srt_debug_pack_info(C.byref(p), C.byref(w), C.byref(h))
+        return p.value, w.value, h.value
+
+    def debug_prepack(self, tri, cam, box=None):
+        """Host pre-pack of one mesh; `box` = (width, height) of the filtered kernel's box (None = default)."""
         tri = np.ascontiguousarray(tri, np.float32).reshape(-1, 9)
         n = len(tri)
-        npad = (n + 1) // 2 * 2
+        pad, bw, bh = self.pack_info()
+        if box is not None:
+            bw, bh = box
+        npad = (n + pad - 1) // pad * pad
         exact = np.zeros((max(n, 1), 16), np.float32)
-        filt = np.zeros((max(npad, 1), 8), np.float32)
+        filt = np.zeros((max(npad, 1), 12), np.float32)
         filt2 = np.zeros((max(npad, 1), 8), np.float32)
-        tt = self.lib.srt_debug_tile_triangles()
-        tile_m = np.zeros((npad + tt - 1) // tt + 1, np.float32)
         a = C.c_uint32(); b = C.c_uint32()
-        rc = self.lib.srt_debug_prepack(_ptr(tri, np.float32), n, C.byref(cam), _ptr(exact, np.float32),
-                                        _ptr(filt, np.float32), _ptr(filt2, np.float32), _ptr(tile_m, np.float32),
-                                        C.byref(a), C.byref(b))
+        rc = self.lib.srt_debug_prepack(_ptr(tri, np.float32), n, C.byref(cam), bw, bh, _ptr(exact, np.float32),
+                                        _ptr(filt, np.float32), _ptr(filt2, np.float32), C.byref(a), C.byref(b))
         if rc:
             raise SrtError(rc, "srt_debug_prepack")
         assert a.value == npad
-        return dict(exact=exact[:n], filt=filt[:npad], filt2=filt2[:npad], tile_m=tile_m, n_padded=a.value,
-                    unfilterable=b.value, tile_tris=tt)
+        return dict(exact=exact[:n], filt=filt[:npad], filt2=filt2[:npad], n_padded=a.value, unfilterable=b.value,
+                    box=(bw, bh))
+
+
+def box_shape(px, py=1, nb=1):
+    """srt_params.pixels_per_thread encoding of a box shape of the filtered kernel."""
+    return px | (py << 8) | (nb << 16)
 
 
 class Context:
@@ -324,13 +337,13 @@ class Context:
         return img
 
     def download_packed(self, mesh, n):
-        tt = self.lib.srt_debug_tile_triangles()
-        npad = (n + 1) // 2 * 2
-        exact = np.zeros((max(n, 1), 16), np.float32); filt = np.zeros((max(npad, 1), 8), np.float32)
-        filt2 = np.zeros((max(npad, 1), 8), np.float32); tile_m = np.zeros((npad + tt - 1) // tt + 1, np.float32)
+        pad = self.L.pack_info()[0]
+        npad = (n + pad - 1) // pad * pad
+        exact = np.zeros((max(n, 1), 16), np.float32); filt = np.zeros((max(npad, 1), 12), np.float32)
+        filt2 = np.zeros((max(npad, 1), 8), np.float32)
         self._ck(self.lib.srt_debug_download_packed(self.h, mesh, _ptr(exact, np.float32), _ptr(filt, np.float32),
-                                                    _ptr(filt2, np.float32), _ptr(tile_m, np.float32)))
-        return dict(exact=exact[:n], filt=filt[:npad], filt2=filt2[:npad], tile_m=tile_m, n_padded=npad, tile_tris=tt)
+                                                    _ptr(filt2, np.float32)))
+        return dict(exact=exact[:n], filt=filt[:npad], filt2=filt2[:npad], n_padded=npad)
 
     def ffma_peak_tflops(self, repeats=3):
         v = C.c_float()

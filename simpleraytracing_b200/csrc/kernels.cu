@@ -11,9 +11,9 @@
 // computed with separately rounded IEEE binary32 operations in the reference's
 // order (__fmul_rn / __fadd_rn / __fsub_rn / __fdiv_rn / __fsqrt_rn are never
 // contracted into FMAs and are unaffected by fast-math flags).  The FMA-contracted
-// binary32 / binary16 arithmetic of the filter (filtered kernel, bin pass, culled
-// kernel) only ever REJECTS pairs that provably miss ("filter proof"); it
-// never decides a hit and never produces a value.
+// binary32 arithmetic of the filter (filtered kernel, bin pass, culled kernel) only ever
+// REJECTS pairs that provably miss ("filter proof"); it never decides a hit
+// and never produces a value.
 //
 // Kernels: lbuffer_exact_kernel (reference sequence for every pair, + audit of the filter),
 // lbuffer_filtered_kernel (brute force: conservative gate per pair) + resolve_hits_kernel,
@@ -22,7 +22,6 @@
 #include "kernels.h"
 
 #include <cfloat>
-#include <cuda_fp16.h>
 
 #include "prepack_math.h"
 
@@ -95,13 +94,6 @@ __device__ __forceinline__ float attenuate(float L, float mu, float dist, int ss
     return (float)((double)L * exp(-((double)mu * ((double)dist * length_to_cm))));
 }
 
-__device__ __forceinline__ float fmax3(float a, float b, float c)
-{
-    float d;
-    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));          // 3-input FMNMX (sm_100+)
-    return d;
-}
-
 // ---- mbarrier / bulk-copy (TMA 1-D) plumbing ---------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
@@ -155,16 +147,37 @@ __device__ __forceinline__ CtaCoord cta_coord()
     return c;
 }
 
-// L output: the launch's own frame plus the extra (peer / multicast) frames of a fused multi-GPU assembly
+// L output: the launch's own frame plus the extra (peer) frames of a fused multi-GPU assembly.  When L is an NVSwitch
+// multicast mapping the store must be a multimem.st: the switch replicates it into every GPU's frame.
 __device__ __forceinline__ void store_L(const RenderArgs& a, size_t p, float v)
 {
-    a.L[p] = v;
+    if (a.L_multicast) asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(a.L + p), "f"(v) : "memory");
+    else a.L[p] = v;
     for (uint32_t i = 0; i < a.n_L_extra; ++i) a.L_extra[i][p] = v;
 }
-__device__ __forceinline__ void store_L4(const RenderArgs& a, size_t p, float4 v)
+__device__ __forceinline__ void store_L4(const RenderArgs& a, size_t p, float4 v)      // p % 4 == 0, frames 16-byte aligned
 {
-    *reinterpret_cast<float4*>(a.L + p) = v;
+    if (a.L_multicast)
+        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.L + p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    else *reinterpret_cast<float4*>(a.L + p) = v;
     for (uint32_t i = 0; i < a.n_L_extra; ++i) *reinterpret_cast<float4*>(a.L_extra[i] + p) = v;
+}
+
+// Three-strip box test (filter proof item 7): may any pixel centre of the box hit the triangle?
+constexpr float kBoxInflate = 1.0000038f;      // 1 + 2^-18
+
+__device__ __forceinline__ bool box_may_hit(const float4 fa, const float4 fb, const float4 ga, const float4 gb,
+                                            float xc, float yc, float hx, float hy)
+{
+    const float Dc = fabsf(fmaf(fa.w, xc, fmaf(fb.x, yc, fb.y)));
+    const float rD = fmaf(fabsf(fa.w), hx, fabsf(fb.x) * hy);
+    const float Y1 = fabsf(fmaf(fa.x, xc, fmaf(fa.y, yc, fa.z)));
+    const float Y2 = fabsf(fmaf(ga.x, xc, fmaf(ga.y, yc, ga.z)));
+    const float Y3 = fabsf(fmaf(gb.x, xc, fmaf(gb.y, yc, gb.z)));
+    const float s1 = fmaf(fabsf(fa.x), hx, fmaf(fabsf(fa.y), hy, fmaf(2.0f, fb.z, rD))) * kBoxInflate;
+    const float s2 = fmaf(fabsf(ga.x), hx, fmaf(fabsf(ga.y), hy, fmaf(2.0f, ga.w, rD))) * kBoxInflate;
+    const float s3 = fmaf(fabsf(gb.x), hx, fmaf(fabsf(gb.y), hy, fmaf(2.0f, gb.w, rD))) * kBoxInflate;
+    return !(Y1 - Dc > s1) && !(Y2 - Dc > s2) && !(Y3 - Dc > s3);          // NaN survives
 }
 
 // ------------------------------------------------------------------ exact kernel
@@ -201,26 +214,23 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
                     else if (zbuf > t) { zbuf = t; zid = (int)(M.first + j); }     // main-omp.cxx:656-662
                 }
                 if (AUDIT) {
-                    const float4 fa = __ldg(M.filt + 4 * (size_t)j), fb = __ldg(M.filt + 4 * (size_t)j + 1);
-                    const float4 ga = __ldg(M.filt + 4 * (size_t)j + 2), gb = __ldg(M.filt + 4 * (size_t)j + 3);
-                    const float tm = __ldg(M.tile_m + j / kTileTris);
+                    const float4 fa = __ldg(M.filt0 + 3 * (size_t)j), fb = __ldg(M.filt0 + 3 * (size_t)j + 1);
+                    const float4 ga = __ldg(M.filt1 + 2 * (size_t)j), gb = __ldg(M.filt1 + 2 * (size_t)j + 1);
                     const float X1 = fmaf(fa.x, x, fmaf(fa.y, y, fa.z));
                     const float Dd = fmaf(fa.w, x, fmaf(fb.x, y, fb.y));
                     const float X2 = fmaf(ga.x, x, fmaf(ga.y, y, ga.z));
                     const float X3 = fmaf(gb.x, x, fmaf(gb.y, y, gb.z));
-                    // level-0 gate of the filtered kernel for every even run length P it is built for: binary32 Y and D at
-                    // the first pixel of the aligned run, one binary16 FMA step to this pixel, tau = |D16(x0)| + mh
-                    const __half2 hs = *reinterpret_cast<const __half2*>(&fb.w);
-                    bool gate = false;
-                    for (uint32_t P : { 2u, 4u, 6u, 8u, 16u }) {
-                        const uint32_t c0 = col - col % P;
-                        const float x0 = (float)c0 + a.cam.xc;
-                        const __half hk = __int2half_rn((int)(col - c0));
-                        const __half Y16 = __hfma(__low2half(hs), hk, __float2half_rn(fmaf(fa.x, x0, fmaf(fa.y, y, fa.z))));
-                        const __half D16 = __float2half_rn(fmaf(fa.w, x0, fmaf(fb.x, y, fb.y)));
-                        gate = gate || __hgt(__habs(Y16), __hadd(__habs(D16), __high2half(hs)));
-                    }
-                    const bool reject = gate || !(fabsf(Dd) - fabsf(X1) >= -tm) || (fabsf(X1) > fabsf(Dd) + fb.z) ||  // level 0
+                    // the filtered kernel's box of this pixel (aligned box_px x box_py box of the launch, clamped to the
+                    // frame): level-0 gate at the box centre against the packed R, and the three-strip box test
+                    const uint32_t c0 = col - col % a.box_px, r0 = row - lrow % a.box_py;
+                    const uint32_t c1 = min(W, c0 + a.box_px) - 1, r1 = min(a.row_end, r0 + a.box_py) - 1;
+                    const float bxc = 0.5f * (float)(c0 + c1) + a.cam.xc, byc = 0.5f * (float)(r0 + r1) + a.cam.yc;
+                    const float Yc = fmaf(fa.x, bxc, fmaf(fa.y, byc, fa.z)), Dc = fmaf(fa.w, bxc, fmaf(fb.x, byc, fb.y));
+                    const float4 fc = __ldg(M.filt0 + 3 * (size_t)j + 2);
+                    const float Yc2 = fmaf(fc.x, bxc, fmaf(fc.y, byc, fc.z));
+                    const bool gate = (fabsf(Yc) - fabsf(Dc) > fb.w) || (fabsf(Yc2) - fabsf(Dc) > fc.w) ||
+                                      !box_may_hit(fa, fb, ga, gb, bxc, byc, 0.5f * (float)(c1 - c0), 0.5f * (float)(r1 - r0));
+                    const bool reject = gate || (fabsf(X1) > fabsf(Dd) + fb.z) ||                                 // level 0
                                         (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);         // level 1
                     if (reject && hit) ++n_viol;
                 }
@@ -241,205 +251,284 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 }
 
 // --------------------------------------------------------------- filtered kernel
-// P pixels (consecutive columns of one row) per thread; lanes 4 x 8 -> warp footprint 4P x 8;
-// 4 warps 2 x 2 -> CTA footprint 8P x 16.  The 64-byte filter records (level 0 + level 1) are
-// streamed through a kStages-deep shared-memory ring of kTileTris-triangle tiles with 1-D bulk
-// copies (TMA) signalled on "full" mbarriers; a warp releases a stage by arriving on its "empty"
-// mbarrier, so warps never wait for each other except through the ring (no __syncthreads in the
-// loop).  Every thread evaluates the level-0 strip test for its P pixels against each triangle;
-// survivors (rare, spatially coherent) run level 1 and then the exact reference sequence.
+// Brute force over triangles: every thread visits every triangle of its slice, and every (pixel, triangle) pair is
+// decided either by a proven-conservative reject or by the reference's exact sequence.
 //
-// Loop shape (driven by the ncu source views under profiles/):
-//  * the next group's per-thread level-0 state (Level0<P>: 4 registers for even P) is prepared while the
-//    current group is evaluated (no LDS latency on the critical path, no raw coefficients kept live);
-//  * the vote on a group's survivors is taken one iteration later, when its min/compare chain has long
-//    retired (no compare -> VOTE -> BRA stall); the last group of a tile is resolved before
-//    the stage is released, so the slow path can read its records from shared memory;
-//  * the slow path is an out-of-line function; it first applies the level-1 triangle-footprint test
-//    to the END POINTS of the thread's pixel run (edge functions are affine in x: outside the same
-//    edge at both ends => outside in between).  ~4 % of the groups reach the slow path, almost all
-//    only because a strip crosses the warp far away from the triangle; those leave after ~30
-//    instructions per triangle without touching global memory.
-// Triangle order per pixel is preserved: pending groups are resolved strictly in order.
+// Mapping.  A thread owns NB boxes of PX x PY pixels side by side in a row band; lanes 4 x 8 -> warp footprint
+// (4 NB PX) x (8 PY) pixels; a CTA covers 16 image rows (the block-cyclic unit of the multi-GPU split).
+//
+// Level 0 (the hot loop).  The 48-byte level-0 records are streamed through a kStages-deep shared-memory ring of
+// kTileTris-triangle tiles with 1-D bulk copies (TMA) signalled on "full" mbarriers; a warp releases a stage by
+// arriving on its "empty" mbarrier (no __syncthreads in the loop).  Per (box, triangle): Y and D -- affine in the
+// pixel coordinates -- are evaluated at the box CENTRE and the box is rejected when |Y(c)| - |D(c)| > R, R being the
+// record's pre-packed bound r_Y + r_D + 2 m for this box size (filter proof item 7): 2 FFMA for the row
+// part (shared by the thread's boxes) + 2 FFMA + 1 FADD + 1 FSETP per box, votes once per group of kGroupTris
+// triangles, one iteration late so that the compare -> VOTE -> BRA chain never stalls the loop.
+//
+// Survivors (a strip of the triangle's level-0 test crosses the box; ~1 % of the box tests) are not processed where
+// they are found -- that would leave 31 lanes idle behind one.  They go through two per-warp queues in shared memory:
+//   Q1 {box, triangle}: appended by ballot in the loop; drained 32 entries at a time, one entry per lane: the
+//      full three-strip box test (the triangle's conservative footprint), then, for the few boxes that pass, the
+//      per-pixel three-strip tests with one lane per pixel of the box;
+//   Q2 {pixel, triangle}: the candidates of the exact test (1.005 x the true hits); drained with one candidate per
+//      lane: ray generation (both normalisations), Ray::intersect's exact sequence, sign test.
+// Accepted intersections are appended to the pixel's hit list through an atomic slot counter; the ordered float sum
+// of the reference is replayed by resolve_hits_kernel, which sorts each list by triangle index first -- so the
+// result does not depend on which lane, warp or z-slice found a hit, and it is bit-identical to the serial loop.
+constexpr uint32_t kQ2Cap = 96;
 
-#ifndef SRT_GROUP_UNROLL
-#define SRT_GROUP_UNROLL 4
-#endif
-constexpr int kGroupUnroll = SRT_GROUP_UNROLL;   // groups per trip of the hot loop (measured: 1 -> 8.59 ms, 2 -> 7.96 ms, 4 -> 7.83 ms per 2048^2 frame)
-
-// Level-0 state of one group (kGroupTris = 2 triangles) for one thread's run of P pixels.
-//  * even P: Y and D at the run's first pixel in binary32, rounded to binary16; Y is stepped along the run with
-//    HFMA2 -- two pixels per instruction -- and |D| is bounded over the run by |D(x0)| + 7 |bd|, so the gate is
-//    min_k |Y16(k)| <= tau,  tau = |D16(x0)| + mh  (one HADD2; mh is the record's binary16 margin):
-//    per triangle 4 FFMA + 1 pack + 4 HFMA2 + 1 HADD2 + 2 packed min with |.| modifiers + 1 packed compare for
-//    8 pixels.  Every rounding of this path is part of mh (prepack_math.h, pack_triangle).
-//  * odd P: the binary32 evaluation (2 FFMA + FADD + 1/2 FMNMX3 per pair).
-template <int P>
-struct Level0 {
-    static constexpr bool kHalf = (P & 1) == 0;
-    // kHalf: per triangle {(Y, D) at x0 as half2, (slope, margin) word}; else: bx, bd, base-y, base-d per triangle
-    float v[kHalf ? 4 : 8];
-
-    __device__ __forceinline__ void load(const float4* q, float x0, float y)
-    {
-        const float4 a0 = q[0], b0 = q[1], a1 = q[4], b1 = q[5];
-        if constexpr (kHalf) {
-            const float fy0 = fmaf(a0.x, x0, fmaf(a0.y, y, a0.z)), fd0 = fmaf(a0.w, x0, fmaf(b0.x, y, b0.y));
-            const float fy1 = fmaf(a1.x, x0, fmaf(a1.y, y, a1.z)), fd1 = fmaf(a1.w, x0, fmaf(b1.x, y, b1.y));
-            put(0, __floats2half2_rn(fy0, fd0)); put(1, __floats2half2_rn(fy1, fd1));      // one pack per triangle: (Y, D) at x0
-            v[2] = b0.w; v[3] = b1.w;
-        } else {
-            v[0] = a0.x; v[1] = a0.w; v[2] = fmaf(a0.y, y, a0.z); v[3] = fmaf(b0.x, y, b0.y);
-            v[4] = a1.x; v[5] = a1.w; v[6] = fmaf(a1.y, y, a1.z); v[7] = fmaf(b1.x, y, b1.y);
-        }
-    }
-    __device__ __forceinline__ void put(int i, __half2 h) { v[i] = *reinterpret_cast<const float*>(&h); }
-    __device__ __forceinline__ __half2 get(int i) const { return *reinterpret_cast<const __half2*>(&v[i]); }
-
-    // may any pixel of the run be inside the level-0 strip of either triangle?
-    __device__ __forceinline__ bool survives(const float (&x)[P], float negM) const
-    {
-        if constexpr (kHalf) {
-            const __half2 Y0 = __low2half2(get(0)), Y1 = __low2half2(get(1));
-            const __half2 sy0 = __low2half2(get(2)), sy1 = __low2half2(get(3));
-            // tau = |D(x0)| + mh in binary16 (mh covers the growth of |D| along the run and both roundings)
-            const __half2 T0 = __hadd2(__habs2(__high2half2(get(0))), __high2half2(get(2)));
-            const __half2 T1 = __hadd2(__habs2(__high2half2(get(1))), __high2half2(get(3)));
-            __half2 m0, m1;
-#pragma unroll
-            for (int k = 0; k < P; k += 2) {
-                const __half2 dx = __floats2half2_rn((float)k, (float)(k + 1));
-                const __half2 u0 = __habs2(__hfma2(sy0, dx, Y0)), u1 = __habs2(__hfma2(sy1, dx, Y1));
-                m0 = k ? __hmin2(m0, u0) : u0;
-                m1 = k ? __hmin2(m1, u1) : u1;
-            }
-            // some |Y| <= tau in either triangle; +-inf from a binary16 overflow of Y is a (correct) reject
-            return !__hbgt2(m0, T0) || !__hbgt2(m1, T1);
-        } else {
-            float acc0 = -FLT_MAX, acc1 = -FLT_MAX;
-#pragma unroll
-            for (int k = 0; k + 1 < P; k += 2) {
-                const float S0 = fmaf(v[0], x[k], v[2]), D0 = fmaf(v[1], x[k], v[3]);
-                const float S1 = fmaf(v[4], x[k], v[6]), D1 = fmaf(v[5], x[k], v[7]);
-                const float S2 = fmaf(v[0], x[k + 1], v[2]), D2 = fmaf(v[1], x[k + 1], v[3]);
-                const float S3 = fmaf(v[4], x[k + 1], v[6]), D3 = fmaf(v[5], x[k + 1], v[7]);
-                acc0 = fmax3(acc0, fabsf(D0) - fabsf(S0), fabsf(D2) - fabsf(S2));
-                acc1 = fmax3(acc1, fabsf(D1) - fabsf(S1), fabsf(D3) - fabsf(S3));
-            }
-            const float S0 = fmaf(v[0], x[P - 1], v[2]), D0 = fmaf(v[1], x[P - 1], v[3]);      // the last pixel on its own
-            const float S1 = fmaf(v[4], x[P - 1], v[6]), D1 = fmaf(v[5], x[P - 1], v[7]);
-            acc0 = fmaxf(acc0, fabsf(D0) - fabsf(S0));
-            acc1 = fmaxf(acc1, fabsf(D1) - fabsf(S1));
-            return fmaxf(acc0, acc1) >= negM;
-        }
-    }
+template <int PX, int PY, int NB>
+struct BoxGeom {
+    static_assert(PY == 1 || PY == 2, "a CTA covers one 16-row block");
+    static_assert(PX * PY <= 32, "the per-pixel stage maps one lane to one pixel of a box");
+    static_assert(NB >= 1 && NB <= 4, "box index is 7 bits");
+    static constexpr uint32_t kWarpW = 4 * NB * PX, kWarpH = 8 * PY;
+    static constexpr uint32_t kWarpsY = 16 / kWarpH, kWarpsX = 4 / kWarpsY;
+    static constexpr uint32_t kCtaW = kWarpsX * kWarpW;
+    static constexpr uint32_t kQ1Cap = 32 * NB + 96;         // room for one triangle's survivors above the drain level
 };
 
-struct SlowArgs {
-    const float4* exact;
-    uint32_t n;                  // triangles in the mesh
-    uint32_t first; int mode;    // scene-wide index of the mesh's first triangle; 0 X-ray, 1 closest hit
-    uint32_t orow, W;            // output row of this thread (hit-list mode)
-    uint2* hit_entries; uint32_t hit_cap, z_splits, z;      // split launch: this slice's sub-lists
-    float y; uint32_t row, col0; int row_ok;
+struct WarpCtx {                  // per warp, in shared memory: everything only the (rare) queue paths touch
+    const float4* filt0; const float4* filt1; const float4* exact;     // current mesh
+    uint32_t n_tris, first;       // triangles in the mesh; scene-wide index of its first triangle
+    uint32_t wrow0, wcol0;        // first image row / column of the warp's footprint
+    uint32_t orow0;               // output row of wrow0 (slot-local when compact)
+    uint32_t n1, n2;              // fill levels of the queues
+    uint32_t* q1; uint2* q2;
+    uint8_t q0[kTileTris / kGroupTris];   // first triangle (within the tile) of the groups of the current tile that have survivors
 };
+static_assert(kTileTris <= 256, "q0 entries are bytes");
 
-template <int P, bool SPLIT>
-__device__ __noinline__ void filtered_slow_path(const DevCamera& cam, const SlowArgs& s, const float4* rec, uint32_t jj0,
-                                                float* dist, int* ssum, uint32_t* hits, unsigned long long& n_exact)
+// Q2 -> exact tests, one candidate per lane
+template <int PX, int PY, int NB>
+__device__ __noinline__ void drain_q2(const RenderArgs& a, WarpCtx* w)
 {
-    const float xa = (float)s.col0 + cam.xc, xb = (float)(s.col0 + P - 1) + cam.xc;     // ends of the pixel run
-#pragma unroll 1
-    for (uint32_t g = 0; g < kGroupTris; ++g) {
-        const uint32_t jj = jj0 + g;                                   // triangle index in the mesh
-        if (jj >= s.n) break;                                          // padding entry
-        const float4 fa = rec[4 * g], fb = rec[4 * g + 1], ga = rec[4 * g + 2], gb = rec[4 * g + 3];   // shared memory
-        const float bs = fmaf(fa.y, s.y, fa.z), bd = fmaf(fb.x, s.y, fb.y);
-        const float b2 = fmaf(ga.y, s.y, ga.z), b3 = fmaf(gb.y, s.y, gb.z);
-        const float m1 = fb.z, m2 = ga.w, m3 = gb.w;
-        // --- run-level test.  Each strip is |Y| <= |D| + m with Y, D affine in x.  Over the thread's pixel run
-        // |D| is convex (max at an end point) and |Y| with the same sign at both ends is minimal at an end point:
-        // min|Y| > max|D| + m at the ends => every pixel of the run is outside that strip.
-        {
-            const float Da = fmaf(fa.w, xa, bd), Db = fmaf(fa.w, xb, bd);
-            const float dmax = fmaxf(fabsf(Da), fabsf(Db));
-            const float Sa = fmaf(fa.x, xa, bs), Sb = fmaf(fa.x, xb, bs);
-            const float Ua = fmaf(ga.x, xa, b2), Ub = fmaf(ga.x, xb, b2);
-            const float Va = fmaf(gb.x, xa, b3), Vb = fmaf(gb.x, xb, b3);
-            bool out = !s.row_ok;
-            out = out || ((Sa > 0.0f) == (Sb > 0.0f) && fminf(fabsf(Sa), fabsf(Sb)) > dmax + m1);
-            out = out || ((Ua > 0.0f) == (Ub > 0.0f) && fminf(fabsf(Ua), fabsf(Ub)) > dmax + m2);
-            out = out || ((Va > 0.0f) == (Vb > 0.0f) && fminf(fabsf(Va), fabsf(Vb)) > dmax + m3);
-            if (out) continue;
+    const uint32_t lane = threadIdx.x & 31u;
+    __syncwarp();
+    const uint32_t n2 = w->n2;
+    const float4* exact = w->exact;
+    for (uint32_t e = lane; e < n2; e += 32) {
+        const uint2 ent = w->q2[e];
+        const uint32_t tri = ent.y, k = ent.x & 31u, bi = ent.x >> 5, bl = bi / NB, b = bi - bl * NB;
+        const uint32_t col = w->wcol0 + ((bl & 3u) * NB + b) * PX + k % PX;
+        const uint32_t dr = (bl >> 2) * PY + k / PX;
+        const RayDirs r = make_ray(a.cam, w->wrow0 + dr, col);
+        const float4 A = __ldg(exact + 4 * (size_t)tri), B = __ldg(exact + 4 * (size_t)tri + 1);
+        const float4 C = __ldg(exact + 4 * (size_t)tri + 2), Dn = __ldg(exact + 4 * (size_t)tri + 3);
+        float tt;
+        if (!exact_intersect(r, A, B, C, Dn.x, tt)) continue;
+        float val = tt;                                                   // mode 1: z-buffer candidate (any sign of t)
+        if (a.mode == 0) {
+            if (!((double)tt > 0.0000001)) continue;                       // lbuffer.cxx:788
+            const float dn = dot_rn(r.ax, r.ay, r.az, Dn.y, Dn.z, Dn.w);   // direction . normal, pre-Ray direction
+            val = __fmul_rn((float)((0.0f < dn) - (dn < 0.0f)), tt);       // sign * t
         }
-        // --- per-pixel: the three strips together are the conservative footprint of the triangle
-        uint32_t mask = 0;
-#pragma unroll
-        for (int k = 0; k < P; ++k) {
-            const float xk = (float)(s.col0 + k) + cam.xc;
-            const float Dd = fabsf(fmaf(fa.w, xk, bd));
-            const float S = fmaf(fa.x, xk, bs), X2 = fmaf(ga.x, xk, b2), X3 = fmaf(gb.x, xk, b3);
-            const bool reject = (fabsf(S) > Dd + m1) || (fabsf(X2) > Dd + m2) || (fabsf(X3) > Dd + m3);   // NaN survives
-            if (!reject) mask |= 1u << k;
-        }
-        if (mask == 0) continue;
-        const float4 A = __ldg(s.exact + 4 * (size_t)jj), B = __ldg(s.exact + 4 * (size_t)jj + 1);
-        const float4 C = __ldg(s.exact + 4 * (size_t)jj + 2), Dn = __ldg(s.exact + 4 * (size_t)jj + 3);
-#pragma unroll 1
-        while (mask) {
-            const int k = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const uint32_t col = s.col0 + k;
-            if (col >= cam.W) break;
-            const RayDirs r = make_ray(cam, s.row, col);
-            float tt;
-            ++n_exact;
-            if (exact_intersect(r, A, B, C, Dn.x, tt)) {
-                if (SPLIT) {                                              // split launch: defer the ordered sum
-                    if ((double)tt > 0.0000001) {                         // lbuffer.cxx:788
-                        const float dn = dot_rn(r.ax, r.ay, r.az, Dn.y, Dn.z, Dn.w);
-                        const int sign = (0.0f < dn) - (dn < 0.0f);
-                        // this thread is the only writer of (pixel, slice): plain stores, ascending triangle order
-                        const uint32_t slot = hits[k]++;
-                        if (slot < s.hit_cap) {
-                            const size_t p = (size_t)s.orow * s.W + col;
-                            s.hit_entries[(p * s.z_splits + s.z) * s.hit_cap + slot] =
-                                make_uint2(s.first + jj, __float_as_uint(__fmul_rn((float)sign, tt)));
-                        }
-                    }
-                } else if (s.mode == 0) accumulate_hit(r, Dn, tt, dist[k], ssum[k], hits[k]);
-                else if (dist[k] > tt) { dist[k] = tt; ssum[k] = (int)(s.first + jj); }   // z-buffer, main-omp.cxx:656-662
-            }
-        }
+        const size_t p = (size_t)(w->orow0 + dr) * a.cam.W + col;
+        const uint32_t slot = atomicAdd(a.hit_counts + p, 1u);
+        if (slot < a.hit_cap) a.hit_entries[p * a.hit_cap + slot] = make_uint2(w->first + tri, __float_as_uint(val));
     }
+    if (a.counters && lane == 0 && n2) atomicAdd(a.counters, (unsigned long long)n2);
+    __syncwarp();
+    if (lane == 0) w->n2 = 0;
+    __syncwarp();
 }
 
-// MINB = resident CTAs per SM the register allocation is tuned for: 7 (72 registers) for grids that fill the GPU,
-// 5 (96 registers, fewer local-memory round trips) for small grids that cannot reach that occupancy anyway.
-template <int P, int MINB, bool SPLIT>
-__global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __grid_constant__ RenderArgs a)
+// Q1 -> three-strip box test per entry, per-pixel tests for the boxes that pass, candidates into Q2
+template <int PX, int PY, int NB>
+__device__ __noinline__ void drain_q1(const RenderArgs& a, WarpCtx* w)
 {
+    const uint32_t lane = threadIdx.x & 31u, W = a.cam.W;
+    __syncwarp();
+    const uint32_t n1 = w->n1;
+    uint32_t n2 = w->n2;
+    const float4* filt0 = w->filt0; const float4* filt1 = w->filt1;
+    for (uint32_t base = 0; base < n1; base += 32) {
+        const uint32_t e = base + lane;
+        uint32_t tri = 0, bi = 0, col0 = 0, row0 = 0;
+        bool pass = false;
+        if (e < n1) {
+            const uint32_t ent = w->q1[e];
+            tri = ent >> 7; bi = ent & 127u;
+            const uint32_t bl = bi / NB, b = bi - bl * NB;
+            col0 = w->wcol0 + ((bl & 3u) * NB + b) * PX; row0 = w->wrow0 + (bl >> 2) * PY;
+            const uint32_t c1 = min(W, col0 + PX) - 1, r1 = min(a.row_end, row0 + PY) - 1;      // queued boxes hold pixels
+            const float4 fa = __ldg(filt0 + 3 * (size_t)tri), fb = __ldg(filt0 + 3 * (size_t)tri + 1);
+            const float4 ga = __ldg(filt1 + 2 * (size_t)tri), gb = __ldg(filt1 + 2 * (size_t)tri + 1);
+            pass = box_may_hit(fa, fb, ga, gb, 0.5f * (float)(col0 + c1) + a.cam.xc, 0.5f * (float)(row0 + r1) + a.cam.yc,
+                               0.5f * (float)(c1 - col0), 0.5f * (float)(r1 - row0));
+        }
+        unsigned pm = __ballot_sync(0xffffffffu, pass);
+        while (pm) {                                                       // warp-uniform: one passing box at a time
+            const int src = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const uint32_t s_tri = __shfl_sync(0xffffffffu, tri, src), s_bi = __shfl_sync(0xffffffffu, bi, src);
+            const uint32_t s_col0 = __shfl_sync(0xffffffffu, col0, src), s_row0 = __shfl_sync(0xffffffffu, row0, src);
+            const uint32_t col = s_col0 + lane % PX, row = s_row0 + lane / PX;             // one lane per pixel of the box
+            bool cand = false;
+            if (lane < PX * PY && col < W && row < a.row_end) {
+                const float4 fa = __ldg(filt0 + 3 * (size_t)s_tri), fb = __ldg(filt0 + 3 * (size_t)s_tri + 1);   // L1 hits
+                const float4 ga = __ldg(filt1 + 2 * (size_t)s_tri), gb = __ldg(filt1 + 2 * (size_t)s_tri + 1);
+                const float x = (float)col + a.cam.xc, y = (float)row + a.cam.yc;
+                const float Dd = fabsf(fmaf(fa.w, x, fmaf(fb.x, y, fb.y)));
+                const float Y1 = fmaf(fa.x, x, fmaf(fa.y, y, fa.z)), Y2 = fmaf(ga.x, x, fmaf(ga.y, y, ga.z));
+                const float Y3 = fmaf(gb.x, x, fmaf(gb.y, y, gb.z));
+                cand = !((fabsf(Y1) > Dd + fb.z) || (fabsf(Y2) > Dd + ga.w) || (fabsf(Y3) > Dd + gb.w));   // NaN survives
+            }
+            const unsigned cm = __ballot_sync(0xffffffffu, cand);
+            if (cm == 0) continue;
+            const uint32_t nc = __popc(cm);
+            if (n2 + nc > kQ2Cap) {
+                if (lane == 0) w->n2 = n2;
+                drain_q2<PX, PY, NB>(a, w);
+                n2 = 0;
+            }
+            if (cand) w->q2[n2 + __popc(cm & ((1u << lane) - 1u))] = make_uint2((s_bi << 5) | lane, s_tri);
+            n2 += nc;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) { w->n1 = 0; w->n2 = n2; }
+    __syncwarp();
+}
+
+template <int NB> struct BoxX { float v[NB]; };
+
+// Queue the survivors of one vote group (records at `tp`, first triangle jj): re-evaluates the group's box tests per
+// box.  Out of line and fed from shared memory so that the hot loop keeps none of this state in registers.
+template <int PX, int PY, int NB>
+__device__ __noinline__ void push_group(const RenderArgs& a, WarpCtx* w, const float4* tp, uint32_t jj, float yc,
+                                        BoxX<NB> xc, uint32_t alive)
+{
+    using G = BoxGeom<PX, PY, NB>;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t n1 = w->n1;
+    const uint32_t n_tris = w->n_tris;
+#pragma unroll 1
+    for (uint32_t g = 0; g < kGroupTris; ++g) {
+        const float4 fa = tp[3 * g], fb = tp[3 * g + 1], fc = tp[3 * g + 2];
+        const float by = fmaf(fa.y, yc, fa.z), dy = fmaf(fb.x, yc, fb.y), by2 = fmaf(fc.y, yc, fc.z);
+        uint32_t mine = 0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const float D = fabsf(fmaf(fa.w, xc.v[b], dy));
+            const float Y = fmaf(fa.x, xc.v[b], by), Y2 = fmaf(fc.x, xc.v[b], by2);
+            if (!((fabsf(Y) - D > fb.w) || (fabsf(Y2) - D > fc.w))) mine |= 1u << b;
+        }
+        mine &= alive;
+        if (jj + g >= n_tris) mine = 0;                                    // padding entry
+        if (!__any_sync(0xffffffffu, mine != 0)) continue;
+        if (n1 + 32 * NB > G::kQ1Cap) {
+            if (lane == 0) w->n1 = n1;
+            drain_q1<PX, PY, NB>(a, w);
+            n1 = 0;
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const unsigned bal = __ballot_sync(0xffffffffu, (mine >> b) & 1u);
+            if ((mine >> b) & 1u) w->q1[n1 + __popc(bal & ((1u << lane) - 1u))] = ((jj + g) << 7) | (lane * NB + b);
+            n1 += __popc(bal);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) w->n1 = n1;
+    __syncwarp();
+}
+
+#ifndef SRT_GROUP_UNROLL
+#define SRT_GROUP_UNROLL 1
+#endif
+constexpr int kGroupUnroll = SRT_GROUP_UNROLL;   // groups per trip of the hot loop
+
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// THE HOT LOOP: level-0 box tests of one thread's NB boxes against the `cnt` triangles of one shared-memory tile.
+// Its own function (own register allocation: the surrounding pipeline code and the queue paths made ptxas spill the
+// loop's three live values at 64 registers); called once per tile.  The groups in which some lane has a survivor are
+// only noted here -- one byte per group in q0, warp-uniform -- and queued by the caller.  The vote on a group is
+// taken one iteration late (its predicate has been ready for a whole iteration: no compare -> VOTE -> BRA stall).
+// Returns the number of groups noted.
+template <int NB>
+__device__ __noinline__ uint32_t scan_tile(uint32_t tile, uint32_t cnt, float yc, BoxX<NB> xc, uint32_t q0)
+{
+    bool pend = false;             // may the previous group have a survivor in this lane?
+    uint32_t n0 = 0;
+#pragma unroll(kGroupUnroll)
+    for (uint32_t j = 0; j < cnt; j += kGroupTris) {
+        bool surv = false;
+#pragma unroll
+        for (uint32_t g = 0; g < kGroupTris; ++g) {
+            const float4 fa = lds128(tile + 48 * (j + g)), fb = lds128(tile + 48 * (j + g) + 16), fc = lds128(tile + 48 * (j + g) + 32);
+            const float by = fmaf(fa.y, yc, fa.z), dy = fmaf(fb.x, yc, fb.y), by2 = fmaf(fc.y, yc, fc.z);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const float D = fabsf(fmaf(fa.w, xc.v[b], dy));
+                const float Y = fmaf(fa.x, xc.v[b], by), Y2 = fmaf(fc.x, xc.v[b], by2);
+                const bool r1 = fabsf(Y) - D > fb.w, r2 = fabsf(Y2) - D > fc.w;            // NaN survives
+                surv |= !(r1 | r2);                                              // bitwise: no short-circuit branches
+            }
+        }
+        if (__any_sync(0xffffffffu, pend)) {                            // the PREVIOUS group
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(q0 + n0), "r"(j - kGroupTris) : "memory");
+            ++n0;
+        }
+        pend = surv;
+    }
+    if (__any_sync(0xffffffffu, pend)) {
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(q0 + n0), "r"(cnt - kGroupTris) : "memory");
+        ++n0;
+    }
+    return n0;
+}
+
+#ifndef SRT_MIN_CTAS
+#define SRT_MIN_CTAS 8
+#endif
+template <int PX, int PY, int NB>
+__global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(const __grid_constant__ RenderArgs a)
+{
+    using G = BoxGeom<PX, PY, NB>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* tiles = reinterpret_cast<float4*>(smem_raw);
-    // 128 B of slack after the last stage: the register prefetch of "the next group" may run one group
-    // past the end of a tile (the values are never used)
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileTris * 64 + 128);
+    float4* tiles = reinterpret_cast<float4*>(smem_raw);                       // kStages x kTileTris x 3 float4
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileTris * 48);
     uint64_t* empty = full + kStages;
+    WarpCtx* wctx = reinterpret_cast<WarpCtx*>(empty + kStages);
+    uint2* q2_all = reinterpret_cast<uint2*>(wctx + 4);
+    uint32_t* q1_all = reinterpret_cast<uint32_t*>(q2_all + 4 * kQ2Cap);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const CtaCoord cta = cta_coord();
-    const uint32_t col0 = (cta.x * 8 + (warp & 1) * 4 + (lane & 3)) * P;
-    const uint32_t lrow = (warp >> 1) * 8 + (lane >> 2);
-    const uint32_t row = a.row_begin + (cta.y * a.blk_stride + a.blk_phase) * 16 + lrow;
-    const uint32_t orow = a.compact ? cta.y * 16 + lrow : row;      // output row (slot-local when compact)
     const uint32_t W = a.cam.W;
-    const bool row_ok = row < a.row_end;
-
-    float x[P];
+    WarpCtx* w = wctx + warp;
+    float yc; BoxX<NB> xc; uint32_t alive = 0;
+    {
+        const uint32_t row0 = a.row_begin + (cta.y * a.blk_stride + a.blk_phase) * 16;      // the CTA's 16-row block
+        const uint32_t wrow0 = row0 + (warp / G::kWarpsX) * G::kWarpH;
+        const uint32_t wcol0 = cta.x * G::kCtaW + (warp % G::kWarpsX) * G::kWarpW;
+        const uint32_t trow0 = wrow0 + (lane >> 2) * PY;                                     // this thread's boxes
+        const uint32_t tcol0 = wcol0 + (lane & 3u) * NB * PX;
+        // Box centres.  Boxes are clamped to the frame (the proof needs the centre inside it); a box without pixels is
+        // evaluated at a clamped position as well and masked out when survivors are queued.
+        const uint32_t last_row = a.row_end - 1;
+        const uint32_t r0c = min(trow0, last_row), r1c = min(trow0 + PY - 1, last_row);
+        yc = 0.5f * (float)(r0c + r1c) + a.cam.yc;
 #pragma unroll
-    for (int k = 0; k < P; ++k) x[k] = (float)(col0 + k) + a.cam.xc;
-    const float y = (float)row + a.cam.yc;
-
+        for (int b = 0; b < NB; ++b) {
+            const uint32_t c0 = tcol0 + b * PX;
+            const uint32_t c0c = min(c0, W - 1), c1c = min(c0 + PX - 1, W - 1);
+            xc.v[b] = 0.5f * (float)(c0c + c1c) + a.cam.xc;
+            if (c0 < W && trow0 < a.row_end) alive |= 1u << b;
+        }
+        if (lane == 0) {
+            w->wrow0 = wrow0; w->wcol0 = wcol0; w->orow0 = a.compact ? cta.y * 16 + (wrow0 - row0) : wrow0;
+            w->n1 = 0; w->n2 = 0;
+            w->q1 = q1_all + warp * G::kQ1Cap; w->q2 = q2_all + warp * kQ2Cap;
+        }
+    }
     if (tid == 0) {
 #pragma unroll
         for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
@@ -447,136 +536,70 @@ __global__ void __launch_bounds__(128, MINB) lbuffer_filtered_kernel(const __gri
     }
     __syncthreads();
 
-    float Lval[P];
-#pragma unroll
-    for (int k = 0; k < P; ++k) Lval[k] = a.incident;
-
     uint32_t issued = 0, consumed = 0;     // tiles issued / consumed by this CTA over all meshes (uniform)
-    unsigned long long n_exact = 0;
-
-    // accumulators are touched only on the (rare) exact path: dynamically indexed -> local memory.
-    // mode 0: path length / signSum / hit count per mesh; mode 1: z-buffer / triangle index over all meshes.
-    float dist[P]; int ssum[P]; uint32_t hits[P];
-#pragma unroll
-    for (int k = 0; k < P; ++k) { dist[k] = INFINITY; ssum[k] = -1; hits[k] = 0; }
 
     for (int m = 0; m < a.n_meshes; ++m) {
-        const DevMesh M = a.meshes[m];
-        if (a.mode == 0 && !(SPLIT && m > 0)) {               // split launch: hits[] is the slice-wide append counter
-#pragma unroll
-            for (int k = 0; k < P; ++k) { dist[k] = 0.0f; ssum[k] = 0; hits[k] = 0; }
-        }
+        const DevMesh* Mp = a.meshes + m;
+        const uint32_t n_padded = Mp->n_padded;
+        if (!Mp->contributes || Mp->n == 0) continue;
+        const float4* filt0 = Mp->filt0;
+        if (lane == 0) { w->filt0 = filt0; w->filt1 = Mp->filt1; w->exact = Mp->exact; w->n_tris = Mp->n; w->first = Mp->first; }
+        __syncwarp();
 
-        if (M.contributes && M.n > 0) {
-            SlowArgs sa;
-            sa.exact = M.exact; sa.n = M.n; sa.first = M.first; sa.mode = a.mode;
-            if (SPLIT) { sa.orow = orow; sa.W = W; sa.hit_entries = a.hit_entries; sa.hit_cap = a.hit_cap; sa.z_splits = a.z_splits; sa.z = cta.z; }
-            sa.y = y; sa.row = row; sa.col0 = col0; sa.row_ok = row_ok;
-            const uint32_t all_tiles = (M.n_padded + kTileTris - 1) / kTileTris;
-            const uint32_t t_first = SPLIT ? (uint32_t)((uint64_t)all_tiles * cta.z / a.z_splits) : 0u;
-            const uint32_t n_tiles = SPLIT ? (uint32_t)((uint64_t)all_tiles * (cta.z + 1) / a.z_splits) : all_tiles;   // end of my range
-            // producer side: wait until every warp released the stage, then one thread refills it
-            auto issue = [&](uint32_t t) {
-                const uint32_t stage = issued % kStages;
-                const uint32_t cnt = min(kTileTris, M.n_padded - t * kTileTris);
-                // every thread waits (uniform control flow: a spin loop under `if (tid == 0)` would make the compiler
-                // treat the rest of the tile loop as divergent); the wait is for the tile consumed kStages - 1 tiles
-                // ago, so it only blocks a warp that ran a whole tile ahead of the slowest warp of the CTA
-                mbar_wait(&empty[stage], ((issued / kStages) & 1u) ^ 1u);           // first use passes immediately
-                if (tid == 0) {
-                    mbar_expect_tx(&full[stage], cnt * 64u);
-                    bulk_g2s(tiles + (size_t)stage * kTileTris * 4, M.filt + (size_t)t * kTileTris * 4, cnt * 64u,
-                             &full[stage]);
-                }
-                ++issued;
-            };
-            for (uint32_t t = t_first; t < min(t_first + kStages - 1, n_tiles); ++t) issue(t);
+        const uint32_t all_tiles = (n_padded + kTileTris - 1) / kTileTris;
+        const uint32_t t_first = (uint32_t)((uint64_t)all_tiles * cta.z / a.z_splits);
+        const uint32_t t_end = (uint32_t)((uint64_t)all_tiles * (cta.z + 1) / a.z_splits);
+        // producer side: wait until every warp released the stage, then one thread refills it
+        auto issue = [&](uint32_t t) {
+            const uint32_t stage = issued % kStages;
+            const uint32_t cnt = min(kTileTris, n_padded - t * kTileTris);
+            // every thread waits (uniform control flow: a spin loop under `if (tid == 0)` would make the compiler treat
+            // the rest of the tile loop as divergent); the wait is for the tile consumed kStages - 1 tiles ago, so it
+            // only blocks a warp that ran a whole tile ahead of the slowest warp of the CTA
+            mbar_wait(&empty[stage], ((issued / kStages) & 1u) ^ 1u);           // first use passes immediately
+            if (tid == 0) {
+                mbar_expect_tx(&full[stage], cnt * 48u);
+                bulk_g2s(tiles + (size_t)stage * kTileTris * 3, filt0 + (size_t)t * kTileTris * 3, cnt * 48u, &full[stage]);
+            }
+            ++issued;
+        };
 
-            for (uint32_t t = t_first; t < n_tiles; ++t) {
-                __syncwarp();          // re-converge after the single-lane producer / release code
-                const uint32_t stage = consumed % kStages;
-                mbar_wait(&full[stage], (consumed / kStages) & 1u);
-                const float4* tp = tiles + (size_t)stage * kTileTris * 4;
-                const uint32_t cnt = min(kTileTris, M.n_padded - t * kTileTris);    // multiple of kGroupTris
-                const float negM = -__ldg(M.tile_m + t);
-                const uint32_t jbase = t * kTileTris;
+        for (uint32_t t = t_first; t < min(t_first + kStages - 1, t_end); ++t) issue(t);
+        for (uint32_t t = t_first; t < t_end; ++t) {
+            __syncwarp();          // re-converge after the single-lane producer / release code
+            const uint32_t stage = consumed % kStages;
+            mbar_wait(&full[stage], (consumed / kStages) & 1u);
+            const float4* tp = tiles + (size_t)stage * kTileTris * 3;
+            const uint32_t cnt = min(kTileTris, n_padded - t * kTileTris);      // multiple of kGroupTris
+            const uint32_t jbase = t * kTileTris;
 
-                bool pend = false;             // may the previous group have a survivor in this lane?
-                Level0<P> cur;
-                cur.load(tp, x[0], y);
-#pragma unroll(kGroupUnroll)
-                for (uint32_t j = 0; j < cnt; j += kGroupTris) {
-                    // prepare the next group (past the tile end: slack / next stage, values unused): its shared-memory
-                    // loads and per-thread base values are off the critical path of the current group
-                    Level0<P> nxt;
-                    nxt.load(tp + 4 * (j + kGroupTris), x[0], y);
-                    const bool surv = cur.survives(x, negM);
-                    // resolve the PREVIOUS group now: its predicate has been ready for a whole iteration
-                    if (__any_sync(0xffffffffu, pend))
-                        filtered_slow_path<P, SPLIT>(a.cam, sa, tp + 4 * (j - kGroupTris), jbase + j - kGroupTris, dist, ssum, hits, n_exact);
-                    pend = surv;
-                    cur = nxt;
-                }
-                // last group of the tile, while its records are still in shared memory
-                if (__any_sync(0xffffffffu, pend))
-                    filtered_slow_path<P, SPLIT>(a.cam, sa, tp + 4 * (cnt - kGroupTris), jbase + cnt - kGroupTris, dist, ssum, hits, n_exact);
+            const uint32_t n0 = scan_tile<NB>(smem_u32(tp), cnt, yc, xc, smem_u32(w->q0));
+            if (n0) {                      // while the tile's records are still in shared memory
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[stage]);        // this warp is done with the stage
-                ++consumed;
-                if (t + kStages - 1 < n_tiles) issue(t + kStages - 1);
-            }
-        }
-
-        if (a.mode != 0 || SPLIT) continue;             // closest hit / split launch: outputs are written later
-#pragma unroll
-        for (int k = 0; k < P; ++k) Lval[k] = attenuate(Lval[k], M.mu, dist[k], ssum[k], a.length_to_cm);
-        if (m == 0 && row_ok) {
-#pragma unroll
-            for (int k = 0; k < P; ++k) {
-                if (col0 + k < W) {
-                    const size_t p = (size_t)orow * W + col0 + k;
-                    if (a.dist) a.dist[p] = dist[k];
-                    if (a.ssum) a.ssum[p] = ssum[k];
-                    if (a.hits) a.hits[p] = hits[k];
+                for (uint32_t i = 0; i < n0; ++i) {
+                    const uint32_t jg = w->q0[i];
+                    push_group<PX, PY, NB>(a, w, tp + 3 * jg, jbase + jg, yc, xc, alive);
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);        // this warp is done with the stage
+            ++consumed;
+            if (t + kStages - 1 < t_end) issue(t + kStages - 1);
         }
+        // the queues hold mesh-local triangle indices: empty them before the next mesh
+        __syncwarp();
+        if (w->n1) drain_q1<PX, PY, NB>(a, w);
+        if (w->n2) drain_q2<PX, PY, NB>(a, w);
     }
-
-    if (SPLIT) {
-        // split launch: publish how many entries this slice appended per pixel; resolve_hits_kernel writes the outputs
-        if (row_ok) {
-#pragma unroll
-            for (int k = 0; k < P; ++k)
-                if (col0 + k < W) a.hit_counts[(size_t)cta.z * a.hit_pixels + (size_t)orow * W + col0 + k] = hits[k];   // [slice][pixel]: coalesced
-        }
-    } else if (a.mode != 0) {
-        if (row_ok) {
-#pragma unroll
-            for (int k = 0; k < P; ++k)
-                if (col0 + k < W) { a.dist[(size_t)orow * W + col0 + k] = dist[k]; a.ssum[(size_t)orow * W + col0 + k] = ssum[k]; }
-        }
-    } else if (row_ok) {
-        const size_t out = (size_t)(a.L_image ? row : orow) * W + col0;
-        if (P % 4 == 0 && (W & 3u) == 0 && col0 + P <= W) {
-#pragma unroll
-            for (int k = 0; k < P; k += 4)
-                store_L4(a, out + k, make_float4(Lval[k], Lval[k + 1 < P ? k + 1 : k],
-                                                 Lval[k + 2 < P ? k + 2 : k], Lval[k + 3 < P ? k + 3 : k]));
-        } else {
-#pragma unroll
-            for (int k = 0; k < P; ++k)
-                if (col0 + k < W) store_L(a, out + k, Lval[k]);
-        }
-    }
-    if (a.counters && n_exact) atomicAdd(a.counters, n_exact);
 }
 
 // ------------------------------------------------------------------ hit-list resolve
-// Second pass of a split launch: one thread per output pixel sorts the pixel's hit list by scene-wide triangle
+// Second pass of the filtered kernel: one thread per output pixel sorts the pixel's hit list by scene-wide triangle
 // index (insertion sort, lists are a handful of entries) and replays the reference's per-mesh accumulation and
-// attenuation (lbuffer.cxx:768-809) in ascending triangle order.  A list that overflowed its capacity is
+// attenuation (lbuffer.cxx:768-809), or the z-buffer update of the shaded drivers (main-omp.cxx:656-662), in ascending
+// triangle order.  It also resets the pixel's slot counter for the next render.  A list that overflowed its capacity is
 // recomputed from scratch with the exact sequence over all triangles (rare; keeps the result exact).
+constexpr uint32_t kMaxHitCap = 16;
 __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant__ RenderArgs a)
 {
     const uint32_t W = a.cam.W;
@@ -587,44 +610,53 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
     const bool valid = col < W && row < a.row_end;          // no early return: the overflow path below is warp-wide
     const size_t p = (size_t)orow * W + (valid ? col : 0);
     float L = a.incident;
-    float dist0 = 0.0f; int ssum0 = 0; uint32_t hits0 = 0;
+    float dist0 = 0.0f; int ssum0 = 0; uint32_t hits0 = 0;   // mode 1: z-buffer value / triangle index
+    if (a.mode != 0) { dist0 = INFINITY; ssum0 = -1; }
     bool overflow = false;
     if (valid) {
-        // concatenate the slices' sub-lists (each already ascending; slices cover ascending tile ranges per mesh)
-        constexpr uint32_t kMaxList = 64;
-        uint2 e[kMaxList];
-        uint32_t n = 0;
-        for (uint32_t z = 0; z < a.z_splits; ++z) {
-            const uint32_t cnt = a.hit_counts[(size_t)z * a.hit_pixels + p];
-            if (cnt > a.hit_cap || n + cnt > kMaxList) { overflow = true; break; }
-            const uint2* src = a.hit_entries + (p * a.z_splits + z) * a.hit_cap;
-            for (uint32_t i = 0; i < cnt; ++i) e[n++] = src[i];
-        }
-        if (!overflow) {
-            for (uint32_t i = 1; i < n; ++i) {                  // insertion sort by triangle index (multi-mesh scenes)
-                const uint2 key = e[i];
+        const uint32_t n = a.hit_counts[p];
+        if (n) a.hit_counts[p] = 0;                          // ready for the next render
+        overflow = n > a.hit_cap;
+        if (n && !overflow) {
+            uint2 e[kMaxHitCap];
+            const uint2* src = a.hit_entries + p * a.hit_cap;
+            for (uint32_t i = 0; i < n; ++i) {               // insertion sort by triangle index while loading
+                const uint2 key = src[i];
                 uint32_t j = i;
                 while (j > 0 && e[j - 1].x > key.x) { e[j] = e[j - 1]; --j; }
                 e[j] = key;
             }
-            uint32_t i = 0;
-            for (int m = 0; m < a.n_meshes; ++m) {
-                const DevMesh M = a.meshes[m];
-                float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
-                if (M.contributes) {
-                    while (i < n && e[i].x < M.first + M.n) {
-                        const float st = __uint_as_float(e[i].y);
-                        dist = __fadd_rn(dist, st);              // distance += sign * t, ascending triangle order
-                        ssum += (0.0f < st) - (st < 0.0f);
-                        ++hits; ++i;
-                    }
+            if (a.mode != 0) {
+                for (uint32_t i = 0; i < n; ++i) {
+                    const float t = __uint_as_float(e[i].y);
+                    if (dist0 > t) { dist0 = t; ssum0 = (int)e[i].x; }      // strict >: the first of equal t wins
                 }
-                L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
-                if (m == 0) { dist0 = dist; ssum0 = ssum; hits0 = hits; }
+            } else {
+                uint32_t i = 0;
+                for (int m = 0; m < a.n_meshes; ++m) {
+                    const DevMesh M = a.meshes[m];
+                    float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
+                    if (M.contributes) {
+                        while (i < n && e[i].x < M.first + M.n) {
+                            const float st = __uint_as_float(e[i].y);
+                            dist = __fadd_rn(dist, st);              // distance += sign * t, ascending triangle order
+                            ssum += (0.0f < st) - (st < 0.0f);
+                            ++hits; ++i;
+                        }
+                    }
+                    L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
+                    if (m == 0) { dist0 = dist; ssum0 = ssum; hits0 = hits; }
+                }
+            }
+        } else if (a.mode == 0 && !overflow) {
+            // no hit in any mesh: L *= exp(-(mu * (0 * 0.1))) == L exactly, unless mu or the unit factor is not finite
+            for (int m = 0; m < a.n_meshes; ++m) {
+                const float mu = a.meshes[m].mu;
+                if (!(isfinite(mu) && isfinite(a.length_to_cm))) L = attenuate(L, mu, 0.0f, 0, a.length_to_cm);
             }
         }
     }
-    // A sub-list that overflowed its capacity: the WARP recomputes that pixel from scratch with the exact sequence --
+    // A list that overflowed its capacity: the WARP recomputes that pixel from scratch with the exact sequence --
     // 32 triangles at a time (one per lane), hits folded in ascending lane (= triangle) order -- so that one
     // pathological ray costs tens of microseconds instead of a single thread walking the whole mesh.
     const uint32_t lane = threadIdx.x & 31u;
@@ -634,7 +666,7 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
         todo &= todo - 1;
         const uint32_t prow = __shfl_sync(0xffffffffu, row, src), pcol = __shfl_sync(0xffffffffu, col, src);
         const RayDirs r = make_ray(a.cam, prow, pcol);
-        float Lc = a.incident, d0 = 0.0f; int s0 = 0; uint32_t h0 = 0;
+        float Lc = a.incident, d0 = a.mode ? INFINITY : 0.0f; int s0 = a.mode ? -1 : 0; uint32_t h0 = 0;
         for (int m = 0; m < a.n_meshes; ++m) {
             const DevMesh M = a.meshes[m];
             float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
@@ -647,10 +679,13 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
                         const float4 A = __ldg(M.exact + 4 * (size_t)j), B = __ldg(M.exact + 4 * (size_t)j + 1);
                         const float4 C = __ldg(M.exact + 4 * (size_t)j + 2), Dn = __ldg(M.exact + 4 * (size_t)j + 3);
                         float t;
-                        if (exact_intersect(r, A, B, C, Dn.x, t) && (double)t > 0.0000001) {
-                            const float dn = dot_rn(r.ax, r.ay, r.az, Dn.y, Dn.z, Dn.w);
-                            st = __fmul_rn((float)((0.0f < dn) - (dn < 0.0f)), t);
-                            got = true;
+                        if (exact_intersect(r, A, B, C, Dn.x, t)) {
+                            if (a.mode != 0) { st = t; got = true; }
+                            else if ((double)t > 0.0000001) {
+                                const float dn = dot_rn(r.ax, r.ay, r.az, Dn.y, Dn.z, Dn.w);
+                                st = __fmul_rn((float)((0.0f < dn) - (dn < 0.0f)), t);
+                                got = true;
+                            }
                         }
                     }
                     unsigned hm = __ballot_sync(0xffffffffu, got);
@@ -658,19 +693,19 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
                         const int l = __ffs(hm) - 1;
                         hm &= hm - 1;
                         const float v = __shfl_sync(0xffffffffu, st, l);
-                        dist = __fadd_rn(dist, v);
-                        ssum += (0.0f < v) - (v < 0.0f);
-                        ++hits;
+                        if (a.mode != 0) { if (d0 > v) { d0 = v; s0 = (int)(M.first + base + (uint32_t)l); } }
+                        else { dist = __fadd_rn(dist, v); ssum += (0.0f < v) - (v < 0.0f); ++hits; }
                     }
                 }
             }
+            if (a.mode != 0) continue;
             Lc = attenuate(Lc, M.mu, dist, ssum, a.length_to_cm);
             if (m == 0) { d0 = dist; s0 = ssum; h0 = hits; }
         }
         if ((int)lane == src) { L = Lc; dist0 = d0; ssum0 = s0; hits0 = h0; }
     }
     if (!valid) return;
-    store_L(a, a.L_image ? (size_t)row * W + col : p, L);
+    if (a.mode == 0) store_L(a, a.L_image ? (size_t)row * W + col : p, L);
     if (a.dist) a.dist[p] = dist0;
     if (a.ssum) a.ssum[p] = ssum0;
     if (a.hits) a.hits[p] = hits0;
@@ -689,22 +724,6 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
 // reference sequence exactly like the slow path of the filtered kernel -- in ascending triangle order per pixel, so
 // the float sums are bit-identical.  Every (pixel, triangle) pair is still decided by the same proven-conservative
 // filter or the exact test; none is skipped on a heuristic.
-constexpr float kBoxInflate = 1.0000038f;      // 1 + 2^-18
-
-__device__ __forceinline__ bool box_may_hit(const float4 fa, const float4 fb, const float4 ga, const float4 gb,
-                                            float xc, float yc, float hx, float hy)
-{
-    const float Dc = fabsf(fmaf(fa.w, xc, fmaf(fb.x, yc, fb.y)));
-    const float rD = fmaf(fabsf(fa.w), hx, fabsf(fb.x) * hy);
-    const float Y1 = fabsf(fmaf(fa.x, xc, fmaf(fa.y, yc, fa.z)));
-    const float Y2 = fabsf(fmaf(ga.x, xc, fmaf(ga.y, yc, ga.z)));
-    const float Y3 = fabsf(fmaf(gb.x, xc, fmaf(gb.y, yc, gb.z)));
-    const float s1 = fmaf(fabsf(fa.x), hx, fmaf(fabsf(fa.y), hy, fmaf(2.0f, fb.z, rD))) * kBoxInflate;
-    const float s2 = fmaf(fabsf(ga.x), hx, fmaf(fabsf(ga.y), hy, fmaf(2.0f, ga.w, rD))) * kBoxInflate;
-    const float s3 = fmaf(fabsf(gb.x), hx, fmaf(fabsf(gb.y), hy, fmaf(2.0f, gb.w, rD))) * kBoxInflate;
-    return !(Y1 - Dc > s1) && !(Y2 - Dc > s2) && !(Y3 - Dc > s3);          // NaN survives
-}
-
 // Bin pass: one CTA per (bin, mesh); thread t of iteration i tests triangle 1024 i + t; survivors are appended in
 // ascending triangle order (ballot + warp-count scan).
 constexpr uint32_t kBinThreads = 1024;
@@ -727,11 +746,15 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(const __grid_constant_
     uint32_t base = 0;
     uint32_t j = threadIdx.x;
     float4 fa, fb, ga, gb;
-    if (j < M.n) { const float4* q = M.filt + 4 * (size_t)j; fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3); }
+    auto load_rec = [&](uint32_t i) {
+        const float4* q0 = M.filt0 + 3 * (size_t)i; const float4* q1 = M.filt1 + 2 * (size_t)i;
+        fa = __ldg(q0); fb = __ldg(q0 + 1); ga = __ldg(q1); gb = __ldg(q1 + 1);
+    };
+    if (j < M.n) load_rec(j);
     for (uint32_t j0 = 0; j0 < M.n; j0 += kBinThreads) {
         const bool keep = j < M.n && box_may_hit(fa, fb, ga, gb, xc, yc, hx, hy);
         const uint32_t jn = j + kBinThreads;                   // prefetch the next iteration's record
-        if (jn < M.n) { const float4* q = M.filt + 4 * (size_t)jn; fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3); }
+        if (jn < M.n) load_rec(jn);
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) warp_cnt[warp] = __popc(bal);
         __syncthreads();
@@ -901,8 +924,8 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
             uint32_t idx = 0; float4 fa, fb, ga, gb;
             if (tid < cnt) {
                 idx = __ldg(list + tid);
-                const float4* q = M.filt + 4 * (size_t)idx;
-                fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3);
+                const float4* q0 = M.filt0 + 3 * (size_t)idx; const float4* q1 = M.filt1 + 2 * (size_t)idx;
+                fa = __ldg(q0); fb = __ldg(q0 + 1); ga = __ldg(q1); gb = __ldg(q1 + 1);
             }
             uint32_t i0 = 0;
             while (i0 < cnt) {                                                 // rounds (CTA-uniform)
@@ -913,8 +936,8 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
                     const uint32_t in = i0 + 128 + tid;                       // next step's records in flight
                     if (in < cnt) {
                         idx = __ldg(list + in);
-                        const float4* q = M.filt + 4 * (size_t)idx;
-                        fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3);
+                        const float4* q0 = M.filt0 + 3 * (size_t)idx; const float4* q1 = M.filt1 + 2 * (size_t)idx;
+                        fa = __ldg(q0); fb = __ldg(q0 + 1); ga = __ldg(q1); gb = __ldg(q1 + 1);
                     }
                     const unsigned bal = __ballot_sync(0xffffffffu, keep);
                     if (lane == 0) s_wcnt[warp] = __popc(bal);
@@ -933,8 +956,8 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
                         float4 ra, rb, rc, rd;
                         if (j < n_list) {
                             id2 = s_list[j];
-                            const float4* q = M.filt + 4 * (size_t)id2;     // L1 / L2 hit: phase A has just read it
-                            ra = __ldg(q); rb = __ldg(q + 1); rc = __ldg(q + 2); rd = __ldg(q + 3);
+                            const float4* q0 = M.filt0 + 3 * (size_t)id2; const float4* q1 = M.filt1 + 2 * (size_t)id2;     // L1 / L2 hit: phase A has just read it
+                            ra = __ldg(q0); rb = __ldg(q0 + 1); rc = __ldg(q1); rd = __ldg(q1 + 1);
                             keep = box_may_hit(ra, rb, rc, rd, txc, tyc, thx, thy);
                         }
                         const unsigned bal = __ballot_sync(0xffffffffu, keep);
@@ -963,8 +986,8 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
             uint32_t idx = 0; float4 fa, fb, ga, gb;
             if (lane < cnt) {
                 idx = __ldg(list + lane);
-                const float4* q = M.filt + 4 * (size_t)idx;
-                fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3);
+                const float4* q0 = M.filt0 + 3 * (size_t)idx; const float4* q1 = M.filt1 + 2 * (size_t)idx;
+                fa = __ldg(q0); fb = __ldg(q0 + 1); ga = __ldg(q1); gb = __ldg(q1 + 1);
             }
             for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
                 const bool keep = i0 + lane < cnt && box_may_hit(fa, fb, ga, gb, txc, tyc, thx, thy);
@@ -980,8 +1003,8 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
                 const uint32_t in = i0 + 32 + lane;
                 if (in < cnt) {
                     idx = __ldg(list + in);
-                    const float4* q = M.filt + 4 * (size_t)idx;
-                    fa = __ldg(q); fb = __ldg(q + 1); ga = __ldg(q + 2); gb = __ldg(q + 3);
+                    const float4* q0 = M.filt0 + 3 * (size_t)idx; const float4* q1 = M.filt1 + 2 * (size_t)idx;
+                    fa = __ldg(q0); fb = __ldg(q0 + 1); ga = __ldg(q1); gb = __ldg(q1 + 1);
                 }
                 if (bal == 0) continue;
                 __syncwarp();
@@ -1022,7 +1045,7 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
         }
     } else if (row_ok) {
         const size_t out = (size_t)(a.L_image ? row : orow) * W + col0;
-        if ((W & 3u) == 0 && col0 + P <= W) {
+        if (a.L_vec4 && col0 + P <= W) {
 #pragma unroll
             for (int k = 0; k < P; k += 4)
                 store_L4(a, out + k, make_float4(Lval[k], Lval[k + 1], Lval[k + 2], Lval[k + 3]));
@@ -1227,18 +1250,16 @@ __global__ void __launch_bounds__(256) repair_kernel(const float* __restrict__ L
 }
 
 // ------------------------------------------------------------------ scene pre-pack
-// One thread per triangle, one CTA per shared-memory tile of the render kernel (kTileTris), so the
-// tile's level-0 margin is a block-wide max.  Exact constants use round-to-nearest intrinsics
-// (prepack_math.h); the filter coefficients / margins are double precision.
-__global__ void __launch_bounds__(kTileTris) prepack_kernel(const float* __restrict__ vertices,
-                                                            const float* __restrict__ normals, uint32_t n,
-                                                            uint32_t n_padded, float ox, float oy, float oz,
-                                                            const __grid_constant__ FrameGeom g, ExactTri* exact,
-                                                            float4* filt, float* tile_m)
+// One thread per triangle.  Exact constants use round-to-nearest intrinsics (prepack_math.h); the filter
+// coefficients / margins are double precision.
+__global__ void __launch_bounds__(128) prepack_kernel(const float* __restrict__ vertices, const float* __restrict__ normals,
+                                                      uint32_t n, uint32_t n_padded, float ox, float oy, float oz,
+                                                      const __grid_constant__ FrameGeom g, ExactTri* exact,
+                                                      float4* filt0, float4* filt1)
 {
-    __shared__ float red[kTileTris / 32];
-    const uint32_t i = blockIdx.x * kTileTris + threadIdx.x;
-    float m = 0.0f;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_padded) return;
+    FilterTri f; FilterTri2 f2;
     if (i < n) {
         float v[9];
 #pragma unroll
@@ -1246,32 +1267,15 @@ __global__ void __launch_bounds__(kTileTris) prepack_kernel(const float* __restr
         float nrm[3];
         const float origin[3] = { ox, oy, oz };
         if (normals) { nrm[0] = normals[3 * (size_t)i]; nrm[1] = normals[3 * (size_t)i + 1]; nrm[2] = normals[3 * (size_t)i + 2]; }
-        ExactTri E; FilterTri f; FilterTri2 f2;
+        ExactTri E;
         pack_triangle(v, normals ? nrm : nullptr, origin, g, E, f, f2);
         float4* eo = reinterpret_cast<float4*>(exact + i);
         eo[0] = make_float4(E.e2x, E.e2y, E.e2z, E.e1x); eo[1] = make_float4(E.e1y, E.e1z, E.tx, E.ty);
         eo[2] = make_float4(E.tz, E.qx, E.qy, E.qz);     eo[3] = make_float4(E.e2q, E.nx, E.ny, E.nz);
-        float4* fo = filt + 4 * (size_t)i;
-        fo[0] = make_float4(f.bx, f.gx, f.ax, f.bd); fo[1] = make_float4(f.gd, f.ad, f.m, __uint_as_float(f.h));
-        fo[2] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2); fo[3] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
-        m = f.m;
-    } else if (i < n_padded) {
-        FilterTri f; FilterTri2 f2;
-        pack_padding(f, f2);
-        float4* fo = filt + 4 * (size_t)i;
-        fo[0] = make_float4(f.bx, f.gx, f.ax, f.bd); fo[1] = make_float4(f.gd, f.ad, f.m, __uint_as_float(f.h));
-        fo[2] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2); fo[3] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.0f;
-#pragma unroll
-        for (int w = 0; w < (int)(kTileTris / 32); ++w) t = fmaxf(t, red[w]);
-        tile_m[blockIdx.x] = t;
-    }
+    } else pack_padding(f, f2);
+    filt0[3 * (size_t)i] = make_float4(f.bx, f.gx, f.ax, f.bd);         filt0[3 * (size_t)i + 1] = make_float4(f.gd, f.ad, f.m, f.R);
+    filt0[3 * (size_t)i + 2] = make_float4(f.bx2, f.gx2, f.ax2, f.R2);
+    filt1[2 * (size_t)i] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2);  filt1[2 * (size_t)i + 1] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
 }
 
 // Per-column / per-row detector offsets exactly as lbuffer.cxx:756-757:
@@ -1306,13 +1310,12 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, f
 } // namespace
 
 cudaError_t launch_prepack(const float* vertices, const float* normals, uint32_t n, uint32_t n_padded,
-                           const float origin[3], const FrameGeom& g, void* exact, void* filt,
-                           float* tile_m, cudaStream_t s)
+                           const float origin[3], const FrameGeom& g, void* exact, void* filt0, void* filt1,
+                           cudaStream_t s)
 {
-    const uint32_t tiles = (n_padded + kTileTris - 1) / kTileTris;
-    if (tiles == 0) return cudaSuccess;
-    prepack_kernel<<<tiles, kTileTris, 0, s>>>(vertices, normals, n, n_padded, origin[0], origin[1], origin[2], g,
-                                               (ExactTri*)exact, (float4*)filt, tile_m);
+    if (n_padded == 0) return cudaSuccess;
+    prepack_kernel<<<(n_padded + 127) / 128, 128, 0, s>>>(vertices, normals, n, n_padded, origin[0], origin[1], origin[2], g,
+                                                          (ExactTri*)exact, (float4*)filt0, (float4*)filt1);
     return cudaGetLastError();
 }
 
@@ -1340,53 +1343,45 @@ cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
     return cudaGetLastError();
 }
 
-#ifndef SRT_MIN_CTAS
-#define SRT_MIN_CTAS 7
-#endif
-#ifndef SRT_MIN_CTAS_SMALL
-#define SRT_MIN_CTAS_SMALL 5
-#endif
-
-template <int P, int MINB, bool SPLIT>
-static cudaError_t launch_filtered_b(const RenderArgs& a, dim3 grid, size_t smem, cudaStream_t s)
+// box shapes the filtered kernel is built for: {box width, box height, boxes per thread}
+template <int PX, int PY, int NB>
+static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
 {
-    static_assert((size_t)kStages * kTileTris * 64 + 128 + 2 * kStages * sizeof(uint64_t) <= 48 * 1024,
-                  "the tile ring must fit the default dynamic shared-memory limit (no per-device opt-in needed)");
-    lbuffer_filtered_kernel<P, MINB, SPLIT><<<grid, 128, smem, s>>>(a);
+    using G = BoxGeom<PX, PY, NB>;
+    constexpr size_t smem = (size_t)kStages * kTileTris * 48 + 2 * kStages * sizeof(uint64_t) + 4 * sizeof(WarpCtx) +
+                            4 * kQ2Cap * sizeof(uint2) + 4 * G::kQ1Cap * sizeof(uint32_t);
+    static_assert(smem <= 48 * 1024, "the tile ring and the queues must fit the default dynamic shared-memory limit");
+    dim3 grid((a.cam.W + G::kCtaW - 1) / G::kCtaW, a.n_blocks, a.z_splits ? a.z_splits : 1);
+    lbuffer_filtered_kernel<PX, PY, NB><<<grid, 128, smem, s>>>(a);
     return cudaGetLastError();
 }
 
-template <int P>
-static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
+#define SRT_BOX_SHAPES(X) X(16, 1, 1) X(16, 1, 2) X(32, 1, 1) X(16, 2, 1) X(8, 2, 2) X(8, 1, 2) X(16, 2, 2) X(8, 1, 1)
+
+bool filtered_box_supported(uint32_t px, uint32_t py)
 {
-    const size_t smem = (size_t)kStages * kTileTris * 64 + 128 + 2 * kStages * sizeof(uint64_t);
-    dim3 grid((a.cam.W + 8 * P - 1) / (8 * P), a.n_blocks, a.z_splits ? a.z_splits : 1);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const bool small = (size_t)grid.x * grid.y * grid.z <= (size_t)SRT_MIN_CTAS_SMALL * sms;
-    if (a.hit_entries) {                                   // split launches use runs of 8 or 16 pixels
-        if constexpr (P == 8 || P == 16) return launch_filtered_b<P, SRT_MIN_CTAS, true>(a, grid, smem, s);
-        else return cudaErrorInvalidValue;
-    }
-    return small ? launch_filtered_b<P, SRT_MIN_CTAS_SMALL, false>(a, grid, smem, s) : launch_filtered_b<P, SRT_MIN_CTAS, false>(a, grid, smem, s);
+#define X(PX, PY, NB) if (px == PX && py == PY) return true;
+    SRT_BOX_SHAPES(X)
+#undef X
+    return false;
 }
 
-cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s)
+uint32_t filtered_cta_width(uint32_t px, uint32_t py, uint32_t nb)
+{
+#define X(PX, PY, NB) if (px == PX && py == PY && nb == NB) return BoxGeom<PX, PY, NB>::kCtaW;
+    SRT_BOX_SHAPES(X)
+#undef X
+    return 0;
+}
+
+cudaError_t launch_lbuffer_filtered(const RenderArgs& a, cudaStream_t s)
 {
     if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0) return cudaSuccess;
-    switch (ppt) {
-        case 1: return launch_filtered_t<1>(a, s);
-        case 2: return launch_filtered_t<2>(a, s);
-        case 3: return launch_filtered_t<3>(a, s);
-        case 4: return launch_filtered_t<4>(a, s);
-        case 5: return launch_filtered_t<5>(a, s);
-        case 6: return launch_filtered_t<6>(a, s);
-        case 7: return launch_filtered_t<7>(a, s);
-        case 8: return launch_filtered_t<8>(a, s);
-        case 16: return launch_filtered_t<16>(a, s);
-        default: return cudaErrorInvalidValue;
-    }
+    if (!a.hit_entries || !a.hit_counts || a.hit_cap == 0 || a.hit_cap > kMaxHitCap) return cudaErrorInvalidValue;
+#define X(PX, PY, NB) if (a.box_px == PX && a.box_py == PY && a.box_nb == NB) return launch_filtered_t<PX, PY, NB>(a, s);
+    SRT_BOX_SHAPES(X)
+#undef X
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_lbuffer_culled(const RenderArgs& a, cudaStream_t s)

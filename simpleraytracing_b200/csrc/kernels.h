@@ -8,22 +8,21 @@ namespace srt {
 #ifndef SRT_TILE_TRIS
 #define SRT_TILE_TRIS 128
 #endif
-constexpr uint32_t kTileTris  = SRT_TILE_TRIS;   // triangles per shared-memory tile of filter records (64 B each)
-constexpr uint32_t kGroupTris = 2;     // triangles per vote group in the filtered kernel
-#ifndef SRT_SPLIT_PIXELS
-#define SRT_SPLIT_PIXELS 16
+constexpr uint32_t kTileTris  = SRT_TILE_TRIS;   // triangles per shared-memory tile of level-0 filter records (48 B each)
+#ifndef SRT_GROUP_TRIS
+#define SRT_GROUP_TRIS 4
 #endif
-constexpr int kSplitPixels = SRT_SPLIT_PIXELS;   // pixels per thread of split (hit-list) launches: 8 or 16
+constexpr uint32_t kGroupTris = SRT_GROUP_TRIS;  // triangles per vote group in the filtered kernel; meshes are padded to a multiple
 #ifndef SRT_STAGES
-#define SRT_STAGES 3
+#define SRT_STAGES 4
 #endif
 constexpr uint32_t kStages    = SRT_STAGES;     // bulk-copy pipeline depth
 
 // One mesh as the kernels see it (device pointers).
 struct DevMesh {
-    const float4* filt;      // 4 float4 per (padded) triangle: FilterTri (level 0) followed by FilterTri2 (level 1)
+    const float4* filt0;     // 3 float4 per (padded) triangle: FilterTri  (level 0; the tiles the filtered kernel streams)
+    const float4* filt1;     // 2 float4 per (padded) triangle: FilterTri2 (level 1: the two other strips)
     const float4* exact;     // 4 float4 per triangle            -- ExactTri
-    const float*  tile_m;    // level-0 margin per tile
     uint32_t n, n_padded;
     float    mu;             // attenuation coefficient
     int      contributes;    // 0: mesh adds no path length (reference semantics for meshes > 0)
@@ -59,6 +58,8 @@ struct RenderArgs {
     // IMAGE position instead of the slot position, and additionally into n_L_extra more full-frame buffers -- the
     // peers' frames mapped over NVLink, or one multicast mapping that the switch replicates to every GPU.
     int L_image;
+    int L_vec4;              // every L frame is 16-byte aligned and W % 4 == 0: 128-bit stores allowed
+    int L_multicast;         // L is an NVSwitch multicast mapping: stored with multimem.st (plain st to such an address is undefined)
     uint32_t n_L_extra;
     float* L_extra[7];
     float* dist;             // optional
@@ -69,15 +70,17 @@ struct RenderArgs {
     // `dist` receives the z-buffer value t (+inf = no hit), `ssum` the scene-wide triangle index (-1 = none);
     // strict `z > t` in ascending triangle order => the first of equal t wins, negative t is accepted.
     int mode;
-    // Triangle-range splitting for small grids (mode 0 only).  With z_splits > 1 the CTAs of grid.z slice z stream
-    // only tiles [n_tiles * z / z_splits, n_tiles * (z + 1) / z_splits) of each mesh; accepted intersections are
-    // not accumulated in place (the reference's float sum is order dependent) but appended to a per-(pixel, slice) list
-    // {scene-wide triangle index, sign * t} (no atomics: one owner thread); resolve_hits_kernel concatenates, sorts and replays
-    // lbuffer.cxx:788-809 in the reference's order, so the result is bit-identical to the unsplit kernel.
+    // Filtered kernel.  One thread tests a BOX of box_px x box_py pixels per triangle (FilterTri::R is packed for that
+    // box); accepted intersections are not accumulated in place (the reference's float sum is order dependent and the
+    // exact tests of a warp run wherever a lane is free) but appended to the pixel's hit list {scene-wide triangle
+    // index, value} -- value = sign * t (mode 0) or t (mode 1) -- through an atomic slot counter; resolve_hits_kernel
+    // sorts each list by triangle index and replays lbuffer.cxx:788-809 (or the z-buffer update, main-omp.cxx:656-662)
+    // in the reference's order.  With z_splits > 1 the CTAs of grid.z slice z stream only tiles
+    // [n_tiles * z / z_splits, n_tiles * (z + 1) / z_splits) of each mesh (small grids still fill the GPU).
+    uint32_t box_px, box_py, box_nb;   // box size (pixels) and boxes per thread (side by side along x)
     uint32_t z_splits;
-    uint2* hit_entries;      // [pixel][z_splits][hit_cap]: one sub-list per (pixel, slice), written by its only owner
-    uint32_t* hit_counts;    // [z_splits][hit_pixels]: entries appended (may exceed hit_cap: overflow -> exact recompute)
-    size_t hit_pixels;       // pixels of the launch's output index range
+    uint2* hit_entries;      // [pixel][hit_cap]
+    uint32_t* hit_counts;    // [pixel]: entries appended (may exceed hit_cap: overflow -> exact recompute); zero between renders
     uint32_t hit_cap;
     // Culled kernel (SRT_KERNEL_CULLED): per-bin triangle lists.  A bin is kBinCols columns x bin_blocks 16-row blocks
     // of this launch's grid; bin_entries[bin * bin_cap + M.first + i], i < bin_counts[bin * n_meshes + m], are the
@@ -117,8 +120,11 @@ cudaError_t launch_shade(const ShadeArgs& a, cudaStream_t s);
 // Exact kernel: every pair runs the reference op sequence. audit != 0 additionally evaluates the
 // filters for every pair and counts (filter says reject) && (exact says hit) into counters[1].
 cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s);
-// Filtered kernel; ppt = pixels per thread (1 ... 8, 16).
-cudaError_t launch_lbuffer_filtered(const RenderArgs& a, int ppt, cudaStream_t s);
+// Filtered kernel for the box shape a.box_px x a.box_py (one of filtered_box_shapes()); launch_resolve_hits must follow.
+cudaError_t launch_lbuffer_filtered(const RenderArgs& a, cudaStream_t s);
+constexpr uint32_t kMaxHitCapacity = 16;
+bool filtered_box_supported(uint32_t box_px, uint32_t box_py);
+uint32_t filtered_cta_width(uint32_t box_px, uint32_t box_py, uint32_t box_nb);   // 0: shape not built
 // Culled kernel: bin pass (every triangle against every bin of a.bins_x x a.bins_y) + render pass.  Same results
 // as the other kernels: the bins and the per-CTA cull only ever drop pairs the conservative filter proves to miss.
 cudaError_t launch_lbuffer_culled(const RenderArgs& a, cudaStream_t s);
@@ -128,11 +134,11 @@ cudaError_t launch_deinterleave(const float* slots, float* frame, uint32_t W, ui
 // Artefact repair + image fill (lbuffer.cxx:329-404).
 cudaError_t launch_repair(const float* L, float* image, uint32_t W, uint32_t H, uint32_t depth, cudaStream_t s);
 
-// Scene pre-pack on the GPU (prepack_math.h): raw vertices -> ExactTri / FilterTri / FilterTri2 / tile margins.
+// Scene pre-pack on the GPU (prepack_math.h): raw vertices -> ExactTri / FilterTri / FilterTri2.
 struct FrameGeom;
 cudaError_t launch_prepack(const float* vertices, const float* normals, uint32_t n, uint32_t n_padded,
-                           const float origin[3], const FrameGeom& g, void* exact, void* filt,
-                           float* tile_m, cudaStream_t s);
+                           const float origin[3], const FrameGeom& g, void* exact, void* filt0, void* filt1,
+                           cudaStream_t s);
 // Detector offset tables u_off[W], v_off[H] (lbuffer.cxx:756-757).
 cudaError_t launch_offsets(float* u_off, float* v_off, uint32_t W, uint32_t H, float sp_u, float sp_v, cudaStream_t s);
 

@@ -12,11 +12,12 @@
 namespace srt {
 
 FrameGeom make_frame_geom(const float origin[3], const float detector[3], const float up[3], const float right[3],
-                          float sp_u, float sp_v, uint32_t W, uint32_t H)
+                          float sp_u, float sp_v, uint32_t W, uint32_t H, uint32_t box_w, uint32_t box_h)
 {
     using namespace pm;
     FrameGeom g{};
     g.sp_u = sp_u; g.sp_v = sp_v;
+    g.box_hx = 0.5 * (double)(box_w ? box_w - 1 : 0); g.box_hy = 0.5 * (double)(box_h ? box_h - 1 : 0);
     g.xmax = 0.5 * (double)W; g.ymax = 0.5 * (double)H;
     const double U = std::fabs(g.sp_u) * g.xmax, V = std::fabs(g.sp_v) * g.ymax;
     bool ok = std::isfinite(g.sp_u) && std::isfinite(g.sp_v);
@@ -44,21 +45,18 @@ FrameGeom make_frame_geom(const float origin[3], const float detector[3], const 
 }
 
 void prepack_mesh(const float* vertices, const float* normals, uint32_t n, const float origin[3],
-                  const FrameGeom& g, uint32_t tile_tris, uint32_t pad_to, PackedMesh& out)
+                  const FrameGeom& g, uint32_t pad_to, PackedMesh& out)
 {
     out.n = n;
     out.n_padded = (n + pad_to - 1) / pad_to * pad_to;
     out.exact.resize(n);
     out.filt.resize(out.n_padded);
     out.filt2.resize(out.n_padded);
-    out.tile_m.assign((out.n_padded + tile_tris - 1) / tile_tris + 1, 0.0f);
     out.unfilterable = 0;
     for (uint32_t i = 0; i < n; ++i) {
         const bool ok = pack_triangle(vertices + 9 * (size_t)i, normals ? normals + 3 * (size_t)i : nullptr, origin, g,
                                       out.exact[i], out.filt[i], out.filt2[i]);
         if (!ok) ++out.unfilterable;
-        float& tm = out.tile_m[i / tile_tris];
-        tm = std::max(tm, out.filt[i].m);
     }
     for (uint32_t i = n; i < out.n_padded; ++i) pack_padding(out.filt[i], out.filt2[i]);
 }

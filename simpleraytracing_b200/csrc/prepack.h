@@ -13,20 +13,20 @@
 
 namespace srt {
 
+// box_w x box_h: the box of pixels one thread of the filtered kernel tests per triangle (FilterTri::R is packed for it)
 FrameGeom make_frame_geom(const float origin[3], const float detector[3], const float up[3], const float right[3],
-                          float sp_u, float sp_v, uint32_t W, uint32_t H);
+                          float sp_u, float sp_v, uint32_t W, uint32_t H, uint32_t box_w, uint32_t box_h);
 
 struct PackedMesh {
     std::vector<ExactTri>   exact;    // n
     std::vector<FilterTri>  filt;     // n padded to a multiple of `pad_to` with never-surviving entries
     std::vector<FilterTri2> filt2;    // n padded likewise
-    std::vector<float>      tile_m;   // max level-0 margin per tile of `tile_tris` triangles
     uint32_t n = 0, n_padded = 0;
     uint32_t unfilterable = 0;        // triangles that always take the exact path
 };
 
 // vertices: 9 floats per triangle; normals: 3 per triangle or nullptr.
 void prepack_mesh(const float* vertices, const float* normals, uint32_t n, const float origin[3],
-                  const FrameGeom& g, uint32_t tile_tris, uint32_t pad_to, PackedMesh& out);
+                  const FrameGeom& g, uint32_t pad_to, PackedMesh& out);
 
 } // namespace srt

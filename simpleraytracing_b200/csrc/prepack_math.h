@@ -43,20 +43,20 @@ struct ExactTri {
     float e2q, nx, ny, nz;       // e2q = edge2 . qvec (Ray.cxx:122 numerator), n = Triangle::getNormal()
 };
 
-// 32 B: level-0 conservative reject.  Y and D are affine in the centred pixel coordinates (x, y):
-// Y = bx*x + gx*y + ax (Y = 2 X - det for one barycentric numerator X), D = bd*x + gd*y + ad
-// (D = LAMBDA * det, see pack_triangle).  A pair can only be a hit when |Y| <= |D| + m
-// (<=> 0 <= X / det <= 1 up to rounding).  The record is scaled by a per-triangle power of two so
-// that the render kernel can step Y and D along a pixel run in binary16 (HFMA2, two pixels per
-// instruction) from a binary32 value at the run's first pixel; h holds the binary16 x-slope of Y and the gate's
-// binary16 margin (the kernel steps only Y and bounds |D| over the run by |D(x0)| + 7 |bd|, folded into that margin).
+// 48 B: level-0 conservative reject.  Y and D are affine in the centred pixel coordinates (x, y):
+// Y = bx*x + gx*y + ax (Y = 2 X - det for one barycentric numerator X), D = bd*x + gd*y + ad (D = det).
+// A pair can only be a hit when |Y| <= |D| + m (<=> 0 <= X / det <= 1 up to rounding).  R is the same test for
+// a whole BOX of pixel centres of the filtered kernel (half extents FrameGeom::box_hx / box_hy): no pixel of a box
+// with centre c can hit when |Y(c)| - |D(c)| > R,  R = (hx (|bx| + |bd|) + hy (|gx| + |gd|) + 2 m)(1 + 2^-18).
+// (bx2, gx2, ax2, R2) is the box test of a SECOND strip (a copy of FilterTri2's first strip): one strip is an infinite
+// band across the image, two strips intersect in a parallelogram around the triangle, so boxes that pass both are rare.
 struct FilterTri {
     float bx, gx, ax, bd;
-    float gd, ad, m;
-    uint32_t h;                  // binary16(bx) in the low half, the gate's binary16 margin mh in the high half
+    float gd, ad, m, R;
+    float bx2, gx2, ax2, R2;
 };
 
-// 32 B: level-1 reject, the two remaining strips (slow path only).
+// 32 B: level-1 reject, the two remaining strips (queue stages of the filtered kernel, bin pass, culled kernel).
 struct FilterTri2 {
     float bx2, gx2, ax2, m2;
     float bx3, gx3, ax3, m3;
@@ -71,6 +71,7 @@ struct FrameGeom {
     double delta[3];             // abs. error bound of the reference's float ray direction before normalising
     double G[3];                 // component-wise bound of that direction
     double Kmax;                 // bound of |d1| * |dirA|
+    double box_hx, box_hy;       // half extents (pixels) of the box one thread of the filtered kernel tests per triangle
     int    filterable;           // camera passes the sanity preconditions of the proof
 };
 
@@ -81,10 +82,7 @@ constexpr double SAFETY = 2.0;                   // covers second-order terms of
 constexpr double TINY = 1e-30;                   // absolute slack for gradual underflow
 constexpr double BIG = 1073741824.0;             // 2^30: magnitude precondition
 constexpr double LIM = 1e30;
-constexpr double LAMBDA = 1.00390625;            // 1 + 2^-8: |D| is widened by this factor; pays for the binary16 relative error
-constexpr int    RUN_MAX = 16;                   // longest pixel run a thread of the filtered kernel steps in binary16
-constexpr double H_SLOPE = (2.0 * (RUN_MAX - 1) + 0.1) / 2048.0;   // binary16 error per unit x-slope over a run of <= RUN_MAX pixels (see pack_triangle)
-constexpr double H_ABS = 9.5367431640625e-07;    // 2^-20: binary16 subnormal roundings
+constexpr double BOX_INFLATE = 1.000003814697265625;   // 1 + 2^-18: roundings of the box test's own float arithmetic
 
 struct f3 { float x, y, z; };
 struct d3 { double x, y, z; };
@@ -106,33 +104,6 @@ SRT_HD double ddot(d3 a, const double b[3]) { return a.x * b[0] + a.y * b[1] + a
 SRT_HD double absdot(d3 a, const double b[3]) { return std::fabs(a.x) * b[0] + std::fabs(a.y) * b[1] + std::fabs(a.z) * b[2]; }
 SRT_HD bool finite3(f3 a) { return std::isfinite(a.x) && std::isfinite(a.y) && std::isfinite(a.z); }
 SRT_HD double maxabs(f3 a) { return std::fmax(std::fabs((double)a.x), std::fmax(std::fabs((double)a.y), std::fabs((double)a.z))); }
-
-// float -> IEEE binary16 bit pattern, round to nearest even (same result as cvt.rn.f16.f32)
-SRT_HD uint32_t f16_bits(float f)
-{
-    uint32_t u;
-#if defined(__CUDA_ARCH__)
-    u = __float_as_uint(f);
-#else
-    static_assert(sizeof(u) == sizeof(f), "binary32 expected");
-    __builtin_memcpy(&u, &f, sizeof(u));
-#endif
-    const uint32_t sign = (u >> 16) & 0x8000u, a = u & 0x7fffffffu;
-    if (a > 0x7f800000u) return sign | 0x7e00u;                 // NaN
-    if (a >= 0x477ff000u) return sign | 0x7c00u;                // >= 65520 (or inf) -> inf
-    if (a < 0x38800000u) {                                      // below 2^-14: binary16 subnormal, spacing 2^-24
-#if defined(__CUDA_ARCH__)
-        const float af = __uint_as_float(a);
-#else
-        float af; __builtin_memcpy(&af, &a, sizeof(af));
-#endif
-        return sign | (uint32_t)std::rint((double)af * 16777216.0);     // exact product, ties to even; 1024 == smallest normal
-    }
-    uint32_t h = (((a >> 23) - 112u) << 10) | ((a & 0x7fffffu) >> 13);
-    const uint32_t rem = a & 0x1fffu;
-    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;     // a carry moves into the exponent, as it should
-    return sign | h;
-}
 
 SRT_HD float round_up(double v)
 {
@@ -223,81 +194,63 @@ SRT_HD bool pack_triangle(const float* v, const float* normal_or_null, const flo
         // |2 X - det| <= |det| whatever the sign of det.  Y = 2 X - det is again of the form N . d, so every level of
         // the filter is the same two-sided strip test |Y| <= |D| + m, and the three strips together are exactly
         // the (conservative) footprint of the triangle.
-        // The strips are compared with D = LAMBDA * det, LAMBDA = 1 + 2^-8: |det| <= |LAMBDA det| keeps every bound below
-        // valid as it stands, and the slack (LAMBDA - 1)|det| pays for the RELATIVE error of the binary16 evaluation.
-        const d3 NdT = { LAMBDA * Nd.x, LAMBDA * Nd.y, LAMBDA * Nd.z };
-        const Affine Dn = make_affine(NdT, LAMBDA * rD, g);
+        const Affine Dn = make_affine(Nd, rD, g);
         const d3 Nys = { 2.0 * Ns.x - Nd.x, 2.0 * Ns.y - Nd.y, 2.0 * Ns.z - Nd.z };
         const d3 Nyv = { 2.0 * QV.x - Nd.x, 2.0 * QV.y - Nd.y, 2.0 * QV.z - Nd.z };
         const d3 Nw = { Nd.x - Ns.x - QV.x, Nd.y - Ns.y - QV.y, Nd.z - Ns.z - QV.z };
         const d3 Nyw = { 2.0 * Nw.x - Nd.x, 2.0 * Nw.y - Nd.y, 2.0 * Nw.z - Nd.z };
-        const Affine S = make_affine(Nys, 2.0 * rS + rD, g);
-        const Affine Vn = make_affine(Nyv, 2.0 * rV + rD, g);
-        const Affine Wn = make_affine(Nyw, 2.0 * (rS + rD + rV) + rD, g);
-        // narrowest strip first (largest gradient => fewest surviving pixels): sort 3 by grad2, descending
-        Affine s0 = S, s1 = Vn, s2 = Wn, t;
-        if (s1.grad2 > s0.grad2) { t = s0; s0 = s1; s1 = t; }
-        if (s2.grad2 > s1.grad2) { t = s1; s1 = s2; s2 = t; }
-        if (s1.grad2 > s0.grad2) { t = s0; s0 = s1; s1 = t; }
-        const double m0 = strip_margin(s0, Dn), m1 = strip_margin(s1, Dn), m2 = strip_margin(s2, Dn);
-        // --- binary16 stepping of level 0 (render kernel, even pixels-per-thread).  With Yf(k) the binary32 value
-        // fma(bx, x0 + k, fma(gx, y, ax)) the bounds above are about, the kernel evaluates, for pixel k < RUN_MAX of a run,
-        //     Y16(k) = fl16(fl16(bx) * k + fl16(Yf(0)))            (one HFMA2; k is exact in binary16)
-        // |Y16(k) - Yf(k)| <= k |fl16(bx) - bx| + |fl16(Yf(0)) - Yf(0)| + 2 eps absmax + 2^-11 |Y16(k)| + subnormal terms
-        //                  <= rho |Yf(k)| + hY,   rho = 1.001 * 2^-10,  hY = ((2 k_max + 0.1) / 2048) |bx| + 2.1 eps absmax + 2^-21
-        // (|Yf(0)| <= |Yf(k)| + k_max |bx| + ..., k_max = RUN_MAX - 1 = 15), and the same for D.  The float-level statement is
-        //     hit  =>  |Yf| <= (1 + 16 eps) / LAMBDA * |Df| + m0,
-        // hence hit => |Y16| <= (1 + rho)(1 + 16 eps) / (LAMBDA (1 - rho)) (|D16| + hD) + (1 + rho) m0 + hY
-        //                    <= |D16| + hD + 1.002 m0 + hY                    [the factor is < 1 for LAMBDA = 1 + 2^-8]
-        // The record is scaled by a power of two `sc` (exact, the tests are scale invariant) so that a hit implies
-        // |D16| + margin <= 2^13 and 15 |bx| <= 15 * 2^11: then no binary16 quantity of a HIT overflows, and an overflowing
-        // Y16 (= +-inf, never NaN: fl16(bx) * k stays finite) is a correct reject because D16 stays finite.
-        const double hY = H_SLOPE * std::fabs(s0.b) + 2.1 * EPS * s0.absmax;
-        const double hD = H_SLOPE * std::fabs(Dn.b) + 2.1 * EPS * Dn.absmax;
-        const double M0 = 1.002 * m0 + hY + hD;
-        double sc = 1.0;
-        {
-            const double U = Dn.absmax + M0, B = std::fabs(s0.b);
-            double lim = 0.0;
-            if (U > 0.0) lim = 8000.0 / U;
-            if (B > 0.0) lim = lim > 0.0 ? std::fmin(lim, 2048.0 / B) : 2048.0 / B;
-            if (lim > 0.0 && std::isfinite(lim)) {
-                int e = (int)std::floor(std::log2(lim));
-                e = e < -100 ? -100 : (e > 100 ? 100 : e);
-                sc = std::ldexp(1.0, e);
-                if (sc > lim) sc *= 0.5;                        // log2 rounding at an exact power of two
-            }
+        Affine st[3] = { make_affine(Nys, 2.0 * rS + rD, g), make_affine(Nyv, 2.0 * rV + rD, g),
+                         make_affine(Nyw, 2.0 * (rS + rD + rV) + rD, g) };
+        const float bd = (float)Dn.b, gd = (float)Dn.g, ad = (float)Dn.a;
+        float mf[3]; double R[3], score[3];
+        ok = std::isfinite(Dn.absmax) && Dn.absmax < LIM;
+        for (int i = 0; i < 3; ++i) {
+            const double m = strip_margin(st[i], Dn);
+            ok = ok && std::isfinite(m) && m < LIM && st[i].absmax < LIM;
+            mf[i] = round_up(m);
+            // Box test of the filtered kernel (filter proof item 7): for every pixel centre p of a box with
+            // centre c and half extents (hx, hy), |Y(p)| >= |Y(c)| - r_Y and |D(p)| <= |D(c)| + r_D with r = |beta| hx +
+            // |gamma| hy (the float coefficients the kernel evaluates), so no pixel of the box can hit when
+            // |Y(c)| - |D(c)| > r_Y + r_D + 2 m: one m for the pixel, one for the float evaluation at the centre.
+            R[i] = (g.box_hx * (std::fabs((double)(float)st[i].b) + std::fabs((double)bd)) +
+                    g.box_hy * (std::fabs((double)(float)st[i].g) + std::fabs((double)gd)) + 2.0 * (double)mf[i]) * BOX_INFLATE;
+            // half width (pixels) of the set of box centres this strip lets through, |D| taken at the image centre
+            score[i] = st[i].grad2 > 0.0 ? (std::fabs(Dn.a) + R[i]) / std::sqrt(st[i].grad2) : INFINITY;
         }
-        const double M16 = (sc * M0 + H_ABS + TINY) * 1.001953125;
-        ok = std::isfinite(m0) && std::isfinite(m1) && std::isfinite(m2) && sc * m0 < LIM && sc * m1 < LIM && sc * m2 < LIM &&
-             sc * S.absmax < LIM && sc * Dn.absmax < LIM && sc * Vn.absmax < LIM && sc * Wn.absmax < LIM &&
-             sc * (Dn.absmax + M0) <= 8192.0 && sc * std::fabs(s0.b) <= 2050.0;
+        // The filtered kernel tests two strips per box: the pair whose parallelogram of surviving box centres is the
+        // smallest (area = 4 h_i h_j / |n_i x n_j| with unit normals n; a heuristic that only affects speed).  The
+        // narrower of the two is level 0.
+        int i0 = 0, i1 = 1; double best = INFINITY;
+        for (int i = 0; i < 3; ++i)
+            for (int j = i + 1; j < 3; ++j) {
+                const double cr = std::fabs(st[i].b * st[j].g - st[i].g * st[j].b);        // |grad_i x grad_j|
+                const double area = cr > 0.0 ? score[i] * score[j] * std::sqrt(st[i].grad2 * st[j].grad2) / cr : INFINITY;
+                if (area < best || (i == 0 && j == 1)) { best = area; i0 = i; i1 = j; }
+            }
+        if (score[i1] < score[i0]) { const int t = i0; i0 = i1; i1 = t; }
+        const int i2 = 3 - i0 - i1;
+        ok = ok && std::isfinite(R[i0]) && R[i0] < LIM && std::isfinite(R[i1]) && R[i1] < LIM;
         if (ok) {
-            f.bx = (float)(sc * s0.b); f.gx = (float)(sc * s0.g); f.ax = (float)(sc * s0.a);
-            f.bd = (float)(sc * Dn.b); f.gd = (float)(sc * Dn.g); f.ad = (float)(sc * Dn.a);
-            f.m = round_up(M16);
-            // binary16 margin of the kernel's gate  min_k |Y16(k)| <= tau16 = fl16(|fl16(D(x0))| + mh):  |D| over a run of
-            // <= RUN_MAX pixels exceeds |D(x0)| by at most (RUN_MAX - 1) |bd| (+ 2 eps absmax, part of M0), fl16(D(x0)) is short by at most
-            // 2^-11 |D| (LAMBDA pays for it, see above) and the final sum is rounded once more (<= 2^-11 (|D| + mh));
-            // (1 + 2^-10) before the round-to-nearest conversion keeps the stored value an upper bound.
-            const double mh = (M16 + (RUN_MAX - 1) * std::fabs((double)f.bd) * 1.001 + sc * Dn.absmax / 512.0 + H_ABS) * 1.0009765625;
-            f.h = f16_bits(f.bx) | (f16_bits((float)mh) << 16);
-            f2.bx2 = (float)(sc * s1.b); f2.gx2 = (float)(sc * s1.g); f2.ax2 = (float)(sc * s1.a); f2.m2 = round_up(sc * m1 + TINY);
-            f2.bx3 = (float)(sc * s2.b); f2.gx3 = (float)(sc * s2.g); f2.ax3 = (float)(sc * s2.a); f2.m3 = round_up(sc * m2 + TINY);
+            f.bx = (float)st[i0].b; f.gx = (float)st[i0].g; f.ax = (float)st[i0].a;
+            f.bd = bd; f.gd = gd; f.ad = ad;
+            f.m = mf[i0]; f.R = round_up(R[i0]);
+            f.bx2 = (float)st[i1].b; f.gx2 = (float)st[i1].g; f.ax2 = (float)st[i1].a; f.R2 = round_up(R[i1]);
+            f2.bx2 = f.bx2; f2.gx2 = f.gx2; f2.ax2 = f.ax2; f2.m2 = mf[i1];
+            f2.bx3 = (float)st[i2].b; f2.gx3 = (float)st[i2].g; f2.ax3 = (float)st[i2].a; f2.m3 = mf[i2];
         }
     }
     if (!ok) {
-        // always survives: X == D == 0 -> |D| - |X| = 0 >= -m
-        f = FilterTri{ 0, 0, 0, 0, 0, 0, 0, 0 };
+        // always survives: Y == D == 0 -> |Y| - |D| = 0 is never > m or > R
+        f = FilterTri{ 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
         f2 = FilterTri2{ 0, 0, 0, 0, 0, 0, 0, 0 };
     }
     return ok;
 }
 
-// Padding entries never survive: X = 3e38 (binary16: +inf), D = 0 -> |D| - |X| < -m for every tile margin (< 1e30).
+// Padding entries never survive: Y = 3e38, D = 0 -> |Y| - |D| > R = 0.
 SRT_HD void pack_padding(FilterTri& f, FilterTri2& f2)
 {
-    f = FilterTri{ 0, 0, 3.0e38f, 0, 0, 0, 0, 0 };
+    f = FilterTri{ 0, 0, 3.0e38f, 0, 0, 0, 0, 0, 0, 0, 3.0e38f, 0 };
     f2 = FilterTri2{ 0, 0, 3.0e38f, 0, 0, 0, 3.0e38f, 0 };
 }
 

@@ -26,11 +26,20 @@
 #error "build srt_api.cpp without -mfma/-march=native"
 #endif
 
-#ifndef SRT_SPLIT16_MIN_TILES
-#define SRT_SPLIT16_MIN_TILES 384   // 128 x 16-pixel tiles in a launch from which split launches use 16-pixel runs
-#endif
 #ifndef SRT_RESIDENT_CTAS
 #define SRT_RESIDENT_CTAS 8      // CTAs of the filtered kernel resident per SM (64 registers)
+#endif
+#ifndef SRT_BOX_PX
+#define SRT_BOX_PX 16            // default box of the filtered kernel: SRT_BOX_PX x SRT_BOX_PY pixels, SRT_BOX_NB boxes per thread
+#endif
+#ifndef SRT_BOX_PY
+#define SRT_BOX_PY 1
+#endif
+#ifndef SRT_BOX_NB
+#define SRT_BOX_NB 2
+#endif
+#ifndef SRT_TARGET_WAVES
+#define SRT_TARGET_WAVES 12      // waves of CTAs a launch of the filtered kernel is split into (triangle-range slices)
 #endif
 
 namespace {
@@ -41,7 +50,9 @@ thread_local std::string g_create_error;
 struct MeshBuf {
     float* d_vertices = nullptr;     // 9 per triangle
     float* d_normals = nullptr;      // 3 per triangle, only when the caller supplied normals
-    void* filt = nullptr; void* exact = nullptr; float* tile_m = nullptr;   // filt: 64 B records (level 0 + level 1)
+    void* filt = nullptr; void* exact = nullptr;   // filt: cap level-0 records (48 B) followed by cap level-1 records (32 B)
+    const float4* filt0() const { return (const float4*)filt; }
+    const float4* filt1() const { return (const float4*)((const char*)filt + cap * sizeof(srt::FilterTri)); }
     size_t cap = 0;                  // capacity in triangles of all of the above
     uint32_t n = 0, n_padded = 0;
     bool has_normals = false;
@@ -65,7 +76,8 @@ struct srt_ctx {
     size_t n_meshes = 0;                 // meshes in use (buffers beyond are kept for reuse)
     bool have_camera = false;
     srt_camera camera{};
-    bool packed = false;                 // packed arrays match meshes + camera
+    bool packed = false;                 // packed arrays match meshes + camera + box shape
+    uint32_t box_px = 0, box_py = 0;     // box of the filtered kernel the packed level-0 bounds (FilterTri::R) are for
     bool filterable = false;
 
     std::vector<srt::ShadeMesh> h_shade; // shaded variant: per-mesh descriptors
@@ -83,10 +95,9 @@ struct srt_ctx {
     float* d_L = nullptr; float* d_img = nullptr; float* d_dist = nullptr; int32_t* d_ssum = nullptr; uint32_t* d_hits = nullptr;
     unsigned long long* d_counters = nullptr;
     bool count_exact = false;
-    // hit lists for split launches (small grids)
-    uint2* d_hit_entries = nullptr; uint32_t* d_hit_counts = nullptr; size_t hit_pixels_cap = 0;
+    // per-pixel hit lists of the filtered kernel (counts are zero between renders: resolve_hits_kernel resets them)
+    uint2* d_hit_entries = nullptr; uint32_t* d_hit_counts = nullptr; size_t hit_pixels_cap = 0; uint32_t hit_cap = 0;
     int force_z_splits = 0;              // diagnostic override: 0 = heuristic
-    bool split_forced_ppt = false;       // diagnostic: pixels_per_thread = 8 / 16 selects the run length of SPLIT launches
     // per-bin triangle lists of the culled kernel
     uint32_t* d_bin_entries = nullptr; uint32_t* d_bin_counts = nullptr; size_t bin_entries_cap = 0, bin_counts_cap = 0;
     bool counters_pending = false, timing_pending = false;
@@ -110,7 +121,7 @@ int fail(srt_ctx* c, int code, const char* fmt, ...)
 
 void free_mesh(MeshBuf& m)
 {
-    cudaFree(m.d_vertices); cudaFree(m.d_normals); cudaFree(m.filt); cudaFree(m.exact); cudaFree(m.tile_m);
+    cudaFree(m.d_vertices); cudaFree(m.d_normals); cudaFree(m.filt); cudaFree(m.exact);
     float* tc = m.d_texcoords; size_t tcc = m.texcoord_cap; uint8_t* tx = m.d_tex; size_t txc = m.tex_cap;
     m = MeshBuf{};
     m.d_texcoords = tc; m.texcoord_cap = tcc; m.d_tex = tx; m.tex_cap = txc;       // kept: sized independently
@@ -133,7 +144,7 @@ void free_frame(srt_ctx* c)
     cudaFree(c->d_L); cudaFree(c->d_img); cudaFree(c->d_dist); cudaFree(c->d_ssum); cudaFree(c->d_hits);
     c->d_L = c->d_img = c->d_dist = nullptr; c->d_ssum = nullptr; c->d_hits = nullptr; c->frame_cap = 0;
     cudaFree(c->d_hit_entries); cudaFree(c->d_hit_counts);
-    c->d_hit_entries = nullptr; c->d_hit_counts = nullptr; c->hit_pixels_cap = 0;
+    c->d_hit_entries = nullptr; c->d_hit_counts = nullptr; c->hit_pixels_cap = 0; c->hit_cap = 0;
     cudaFree(c->d_bin_entries); cudaFree(c->d_bin_counts);
     c->d_bin_entries = nullptr; c->d_bin_counts = nullptr; c->bin_entries_cap = 0; c->bin_counts_cap = 0;
 }
@@ -164,7 +175,6 @@ int ensure_mesh(srt_ctx* c, MeshBuf& m, size_t n, bool want_normals)
         SRT_CUDA(c, cudaMalloc(&m.d_vertices, cap * 9 * sizeof(float)));
         SRT_CUDA(c, cudaMalloc(&m.filt, cap * (sizeof(srt::FilterTri) + sizeof(srt::FilterTri2))));
         SRT_CUDA(c, cudaMalloc(&m.exact, cap * sizeof(srt::ExactTri)));
-        SRT_CUDA(c, cudaMalloc(&m.tile_m, (cap / srt::kTileTris + 2) * sizeof(float)));
         if (had_normals || want_normals) SRT_CUDA(c, cudaMalloc(&m.d_normals, cap * 3 * sizeof(float)));
         m.cap = cap;
     }
@@ -172,10 +182,11 @@ int ensure_mesh(srt_ctx* c, MeshBuf& m, size_t n, bool want_normals)
     return SRT_OK;
 }
 
-// (Re)build the packed arrays for the current meshes + camera: all on the GPU, all asynchronous.
-int pack_scene(srt_ctx* c)
+// (Re)build the packed arrays for the current meshes + camera + box shape of the filtered kernel: all on the GPU,
+// all asynchronous.
+int pack_scene(srt_ctx* c, uint32_t box_px = SRT_BOX_PX, uint32_t box_py = SRT_BOX_PY)
 {
-    if (c->packed) return SRT_OK;
+    if (c->packed && c->box_px == box_px && c->box_py == box_py) return SRT_OK;
     if (c->n_meshes == 0) return fail(c, SRT_ERR_INVALID, "srt_set_meshes has not been called");
     if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
     const srt_camera& cam = c->camera;
@@ -193,7 +204,7 @@ int pack_scene(srt_ctx* c)
     SRT_CUDA(c, srt::launch_offsets(c->d_u_off, c->d_v_off, W, H, cam.pixel_spacing[0], cam.pixel_spacing[1], c->stream));
 
     const srt::FrameGeom g = srt::make_frame_geom(cam.origin, cam.detector, cam.up, cam.right,
-                                                  cam.pixel_spacing[0], cam.pixel_spacing[1], W, H);
+                                                  cam.pixel_spacing[0], cam.pixel_spacing[1], W, H, box_px, box_py);
     c->filterable = g.filterable != 0;
 
     const size_t nm = c->n_meshes;
@@ -210,10 +221,10 @@ int pack_scene(srt_ctx* c)
         for (int k = 0; k < 3; ++k) { sm.ka[k] = mb.material.ambient[k]; sm.kd[k] = mb.material.diffuse[k]; sm.ks[k] = mb.material.specular[k]; }
         sm.shininess = mb.material.shininess;
         SRT_CUDA(c, srt::launch_prepack(mb.d_vertices, mb.has_normals ? mb.d_normals : nullptr, mb.n, mb.n_padded,
-                                        cam.origin, g, mb.exact, mb.filt, mb.tile_m, c->stream));
+                                        cam.origin, g, mb.exact, (void*)mb.filt0(), (void*)mb.filt1(), c->stream));
         srt::DevMesh& d = c->h_desc[m];
-        d.filt = (const float4*)mb.filt; d.exact = (const float4*)mb.exact;
-        d.tile_m = mb.tile_m; d.n = mb.n; d.n_padded = mb.n_padded; d.mu = mb.mu;
+        d.filt0 = mb.filt0(); d.filt1 = mb.filt1(); d.exact = (const float4*)mb.exact;
+        d.n = mb.n; d.n_padded = mb.n_padded; d.mu = mb.mu;
         d.first = (uint32_t)c->total_tris;
         d.contributes = (m == 0);                           // lbuffer.cxx:788: only meshes[0] adds path length
         c->h_desc[nm + m] = d;
@@ -233,44 +244,45 @@ int pack_scene(srt_ctx* c)
         SRT_CUDA(c, cudaMalloc(&c->d_shade_meshes, nm * sizeof(srt::ShadeMesh))); c->shade_cap = nm;
     }
     SRT_CUDA(c, cudaMemcpyAsync(c->d_shade_meshes, c->h_shade.data(), nm * sizeof(srt::ShadeMesh), cudaMemcpyHostToDevice, c->stream));
-    c->packed = true;
+    c->packed = true; c->box_px = box_px; c->box_py = box_py;
     return SRT_OK;
 }
 
-// Pixels per thread for the filtered kernel.  A thread that owns more pixels amortises the per-triangle
-// coefficient loads over more tests (cost per test c(P), measured on B200: profiles/r01_band_sweep.txt), but a
-// launch with few CTAs must also divide evenly over the 148 SMs: the SM that hosts ceil(CTAs/148) of them sets
-// the time, and with fewer than 8 resident CTAs the SM's issue slots are not saturated (eff).
-int choose_ppt(const srt_ctx* c, const srt_params* p, uint32_t rows)
+// Box shape of the filtered kernel: srt_params::pixels_per_thread = box width | box height << 8 | boxes per thread << 16
+// (0 in a field = default).
+bool decode_box(uint32_t v, uint32_t& px, uint32_t& py, uint32_t& nb)
 {
-    if ((p->pixels_per_thread >= 1 && p->pixels_per_thread <= 8) || p->pixels_per_thread == 16) return (int)p->pixels_per_thread;
-    static const double cost[9] = { 0, 3.20, 1.96, 1.77, 1.47, 1.58, 1.51, 1.063, 1.00 };  // per test, relative to P = 8
-    static const double eff[9] = { 0, 0.35, 0.60, 0.78, 0.89, 0.91, 0.92, 0.93, 0.94 };     // issue efficiency, k resident CTAs
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const double W = c->camera.width, blocks = (rows + 15) / 16;
-    int best = 8; double best_t = 1e300;
-    for (int P = 8; P >= 1; --P) {
-        const double ctas = std::ceil(W / (8.0 * P)) * blocks;
-        const double q = ctas / sms;
-        const int k = (int)std::ceil(q);
-        const double t = (q <= 8.0 ? k / eff[k < 1 ? 1 : k] : q * 1.02) * P * cost[P];
-        if (t < best_t * 0.999) { best_t = t; best = P; }
-    }
-    return best;
+    px = v & 0xffu; py = (v >> 8) & 0xffu; nb = (v >> 16) & 0xffu;
+    if (px == 0) { px = SRT_BOX_PX; if (py == 0) py = SRT_BOX_PY; if (nb == 0) nb = SRT_BOX_NB; }
+    if (py == 0) py = 1;
+    if (nb == 0) nb = 1;
+    return srt::filtered_cta_width(px, py, nb) != 0;
 }
 
 // parts == 0: contiguous band [row_begin, row_end) written at image positions.
 // parts >= 1: block-cyclic part `part` of `parts` over the whole frame, written compactly (slot layout).
+// extra_frames != nullptr: fused assembly, L goes to the image positions of dL and of the n_extra extra frames;
+// multicast: dL is an NVSwitch multicast mapping (multimem.st).
 int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint32_t row_end,
                   float* dL, float* d_dist, int32_t* d_ssum, uint32_t* d_hits, uint32_t parts = 0, uint32_t part = 0,
-                  int mode = 0, float* const* extra_frames = nullptr, uint32_t n_extra = 0)
+                  int mode = 0, float* const* extra_frames = nullptr, uint32_t n_extra = 0, bool image_positions = false,
+                  bool multicast = false)
 {
     if (!params) return fail(c, SRT_ERR_INVALID, "params is NULL");
     if (mode == 0 && !dL) return fail(c, SRT_ERR_INVALID, "L buffer is NULL");
     if (mode == 1 && (!d_dist || !d_ssum)) return fail(c, SRT_ERR_INVALID, "closest-hit pass needs z and id buffers");
-    const bool repack = !c->packed;
-    int rc = pack_scene(c);
+    if (n_extra > 7 || (n_extra && !extra_frames)) return fail(c, SRT_ERR_INVALID, "at most 7 extra frames");
+    uint32_t kernel = params->kernel;
+    const int audit = (kernel == SRT_KERNEL_AUDIT);
+    if (audit) kernel = SRT_KERNEL_EXACT;
+    if (kernel != SRT_KERNEL_AUTO && kernel != SRT_KERNEL_EXACT && kernel != SRT_KERNEL_FILTERED && kernel != SRT_KERNEL_CULLED)
+        return fail(c, SRT_ERR_INVALID, "unknown kernel selector %u", params->kernel);
+    uint32_t box_px, box_py, box_nb;
+    if (!decode_box(params->pixels_per_thread, box_px, box_py, box_nb))
+        return fail(c, SRT_ERR_INVALID, "box shape %u x %u x %u (pixels_per_thread = 0x%x) is not built", box_px, box_py, box_nb,
+                    params->pixels_per_thread);
+    const bool repack = !(c->packed && c->box_px == box_px && c->box_py == box_py);
+    int rc = pack_scene(c, box_px, box_py);
     if (rc) return rc;
     const srt_camera& cam = c->camera;
     if (row_begin > row_end || row_end > cam.height)
@@ -300,22 +312,26 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     }
     a.incident = params->incident; a.length_to_cm = params->length_to_cm;
     a.L = dL; a.dist = d_dist; a.ssum = d_ssum; a.hits = d_hits;
-    a.L_image = extra_frames != nullptr;                // fused assembly: L goes to image positions of dL + the extra frames
+    a.L_image = image_positions ? 1 : 0;
+    a.L_multicast = multicast ? 1 : 0;
     a.n_L_extra = n_extra;
-    for (uint32_t i = 0; i < n_extra && i < 7; ++i) a.L_extra[i] = extra_frames[i];
+    bool aligned = ((uintptr_t)dL & 15u) == 0 && (cam.width & 3u) == 0;
+    for (uint32_t i = 0; i < n_extra; ++i) {
+        if (!extra_frames[i]) return fail(c, SRT_ERR_INVALID, "extra frame %u is NULL", i);
+        a.L_extra[i] = extra_frames[i];
+        aligned = aligned && ((uintptr_t)extra_frames[i] & 15u) == 0;
+    }
+    a.L_vec4 = aligned ? 1 : 0;                         // 128-bit stores only into 16-byte aligned frames
+    a.box_px = box_px; a.box_py = box_py; a.box_nb = box_nb;
     a.counters = nullptr;
-    if (c->count_exact || params->kernel == SRT_KERNEL_AUDIT) {
+    if (c->count_exact || audit) {
         if (!c->d_counters) SRT_CUDA(c, cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)));
         SRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
         a.counters = c->d_counters;
     }
 
-    uint32_t kernel = params->kernel;
-    const int audit = (kernel == SRT_KERNEL_AUDIT);
-    if (audit) kernel = SRT_KERNEL_EXACT;
-    if (kernel == SRT_KERNEL_AUTO) kernel = c->filterable ? SRT_KERNEL_CULLED : SRT_KERNEL_EXACT;   // culled falls back to filtered when its lists would not fit
-    if (kernel != SRT_KERNEL_EXACT && kernel != SRT_KERNEL_FILTERED && kernel != SRT_KERNEL_CULLED)
-        return fail(c, SRT_ERR_INVALID, "unknown kernel selector %u", params->kernel);
+    if (kernel == SRT_KERNEL_AUTO) kernel = SRT_KERNEL_CULLED;          // falls back below when it does not apply
+    if (!c->filterable) kernel = SRT_KERNEL_EXACT;                        // camera outside the filter's preconditions
     if (kernel == SRT_KERNEL_CULLED) {
         // Bins: 256 columns x 8 row blocks (128 rows) of a contiguous band; with block-cyclic rows the blocks of a rank
         // are `parts` blocks apart, so a bin is one block tall.  Lists: one slot per scene triangle per bin (worst case
@@ -325,8 +341,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         a.bins_y = (a.n_blocks + a.bin_blocks - 1) / a.bin_blocks;
         a.bin_cap = (uint32_t)c->total_tris;
         const size_t bins = (size_t)a.bins_x * a.bins_y;
-        if (!c->filterable) kernel = SRT_KERNEL_EXACT;
-        else if (bins * c->total_tris * 4ull > (8ull << 30) || c->total_tris >= (1ull << 32)) kernel = SRT_KERNEL_FILTERED;
+        if (bins * c->total_tris * 4ull > (8ull << 30) || c->total_tris >= (1ull << 32)) kernel = SRT_KERNEL_FILTERED;
         else if (bins > 0) {
             if (bins * c->total_tris > c->bin_entries_cap) {
                 SRT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -344,57 +359,44 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         }
     }
 
-    // Small grids (a rank's share of a multi-GPU frame): split the triangle range over grid.z and merge through
-    // per-pixel hit lists, so that every SM still gets a full set of resident CTAs.
     a.z_splits = 1; a.hit_entries = nullptr; a.hit_counts = nullptr; a.hit_cap = 0;
-    int ppt = 0;
     uint32_t extra_launches = 0;
     if (kernel == SRT_KERNEL_FILTERED) {
+        if (c->total_tris >= (1ull << 25)) kernel = SRT_KERNEL_EXACT;   // queue entries hold 25-bit triangle indices
+    }
+    if (kernel == SRT_KERNEL_FILTERED) {
+        // Triangle-range slices (grid.z): shorter CTAs in more waves balance the SMs better (CTA run times vary with
+        // their queue work) and keep small grids -- a rank's share of a multi-GPU frame -- at full occupancy.
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-        // Pixels per thread of a split launch: runs of 16 halve the per-run overhead (5.7 vs 7.8 ms per 2048^2 frame), but
-        // their CTAs are twice as heavy where the slow path runs, and a grid of only a few hundred tiles cannot average
-        // that out: the 8 shares of the 2048^2 frame took 0.90 ... 1.12 ms with 16-pixel runs against an even 1.03-1.06 ms
-        // with 8-pixel runs, and the frame is done when the slowest rank is.  params->pixels_per_thread = 8 / 16 forces one.
-        const uint64_t tiles16 = (uint64_t)((cam.width + 127) / 128) * a.n_blocks;
-        const int split_p = params->pixels_per_thread == 8 ? 8 : params->pixels_per_thread == 16 ? 16
-                          : (tiles16 >= (uint64_t)SRT_SPLIT16_MIN_TILES ? 16 : 8);
-        const uint32_t tile_w = 8u * (uint32_t)split_p;                              // CTA width of a split launch
-        const uint64_t ctas8 = (uint64_t)((cam.width + tile_w - 1) / tile_w) * a.n_blocks;
-        const bool auto_split = params->pixels_per_thread == 0 || (c->split_forced_ppt && (params->pixels_per_thread == 8 || params->pixels_per_thread == 16));
-        // Shorter CTAs in more waves balance the SMs better (CTA run times vary with their slow-path work) and keep
-        // small grids -- a rank's share of a multi-GPU frame is only a wave or two of CTAs -- at full occupancy:
-        // aim for ~12 waves (profiles/r01_splits.txt: N = 8 share 2.00 ms split vs 2.53 ms unsplit, ideal 1.90 ms;
-        // full 2048^2 frame 14.8 ms vs 15.2 ms).  The hit lists cost 96 B per (pixel, slice): capped at 2 GB.
+        const uint32_t cta_w = srt::filtered_cta_width(box_px, box_py, box_nb);
+        const uint64_t ctas = (uint64_t)((cam.width + cta_w - 1) / cta_w) * a.n_blocks;
         const uint64_t slots = (uint64_t)sms * SRT_RESIDENT_CTAS;
         uint32_t zs = 1;
-        if (mode == 0 && auto_split && ctas8 > 0) {
-            zs = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, (12 * slots + ctas8 / 2) / ctas8));
-            const uint64_t px = (uint64_t)(parts == 0 ? cam.height : a.n_blocks * 16) * cam.width;
-            while (zs > 1 && px * zs * 96ull > (2ull << 30)) --zs;
+        if (ctas > 0) zs = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, ((uint64_t)SRT_TARGET_WAVES * slots + ctas / 2) / ctas));
+        if (c->force_z_splits > 0) zs = (uint32_t)c->force_z_splits;
+        uint64_t max_tiles = 1;
+        for (size_t m = 0; m < c->n_meshes; ++m)
+            max_tiles = std::max<uint64_t>(max_tiles, (c->meshes[m].n_padded + srt::kTileTris - 1) / srt::kTileTris);
+        zs = (uint32_t)std::min<uint64_t>(zs, std::max<uint64_t>(1, max_tiles / 2));     // at least two tiles per slice
+        // per-pixel hit lists: 4 + 8 * cap bytes per pixel of the launch's output index range
+        const size_t pixels = (size_t)(parts == 0 ? cam.height : a.n_blocks * 16) * cam.width;
+        const uint32_t cap = pixels <= ((size_t)1 << 24) ? 12u : 8u;
+        if (pixels > c->hit_pixels_cap || cap != c->hit_cap) {
+            SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_hit_entries); cudaFree(c->d_hit_counts); c->d_hit_entries = nullptr; c->d_hit_counts = nullptr;
+            c->hit_pixels_cap = 0;
+            SRT_CUDA(c, cudaMalloc(&c->d_hit_entries, pixels * cap * sizeof(uint2)));
+            SRT_CUDA(c, cudaMalloc(&c->d_hit_counts, pixels * sizeof(uint32_t)));
+            SRT_CUDA(c, cudaMemsetAsync(c->d_hit_counts, 0, pixels * sizeof(uint32_t), c->stream));
+            c->hit_pixels_cap = pixels; c->hit_cap = cap;
         }
-        if (c->force_z_splits > 0 && mode == 0) zs = (uint32_t)c->force_z_splits;
-        const uint64_t min_tiles = (c->meshes[0].n_padded + srt::kTileTris - 1) / srt::kTileTris;
-        if (zs > 1 && min_tiles < 4ull * zs) zs = 1;
-        if (zs > 1) {
-            const size_t pixels = (size_t)(parts == 0 ? cam.height : a.n_blocks * 16) * cam.width;   // output index range
-            constexpr uint32_t kHitCap = 12;                  // per (pixel, slice)
-            if (pixels * zs > c->hit_pixels_cap) {
-                SRT_CUDA(c, cudaStreamSynchronize(c->stream));
-                cudaFree(c->d_hit_entries); cudaFree(c->d_hit_counts); c->d_hit_entries = nullptr; c->d_hit_counts = nullptr;
-                SRT_CUDA(c, cudaMalloc(&c->d_hit_entries, pixels * zs * kHitCap * sizeof(uint2)));
-                SRT_CUDA(c, cudaMalloc(&c->d_hit_counts, pixels * zs * sizeof(uint32_t)));
-                c->hit_pixels_cap = pixels * zs;
-            }
-            a.z_splits = zs; a.hit_entries = c->d_hit_entries; a.hit_counts = c->d_hit_counts; a.hit_cap = kHitCap;
-            a.hit_pixels = pixels;
-            ppt = split_p;
-        } else ppt = choose_ppt(c, params, a.n_blocks * 16);
+        a.z_splits = zs; a.hit_entries = c->d_hit_entries; a.hit_counts = c->d_hit_counts; a.hit_cap = cap;
     }
     SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     if (kernel == SRT_KERNEL_FILTERED) {
-        SRT_CUDA(c, srt::launch_lbuffer_filtered(a, ppt, c->stream));
-        if (a.z_splits > 1) { SRT_CUDA(c, srt::launch_resolve_hits(a, c->stream)); extra_launches = 1; }
+        SRT_CUDA(c, srt::launch_lbuffer_filtered(a, c->stream));
+        SRT_CUDA(c, srt::launch_resolve_hits(a, c->stream)); extra_launches = 1;
     } else if (kernel == SRT_KERNEL_CULLED) {
         SRT_CUDA(c, srt::launch_lbuffer_culled(a, c->stream)); extra_launches = 1;
     } else SRT_CUDA(c, srt::launch_lbuffer_exact(a, audit, c->stream));
@@ -660,7 +662,7 @@ int srt_render_lbuffer_blocks_device(srt_ctx* c, const srt_params* p, uint32_t n
     if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
     SRT_CUDA(c, cudaSetDevice(c->device));
     return render_device(c, p, 0, c->camera.height, d_frames[0], nullptr, nullptr, nullptr, n_parts, part, 0,
-                         d_frames + 1, n_frames - 1);
+                         d_frames + 1, n_frames - 1, /*image_positions*/ true, /*multicast*/ false);
 }
 
 int srt_deinterleave_device(srt_ctx* c, uint32_t n_parts, const float* d_slots, float* d_frame)
@@ -845,49 +847,50 @@ int srt_last_timing(srt_ctx* c, srt_timing* out)
     return SRT_OK;
 }
 
-// diagnostic: download the device-side packed arrays of one mesh (packs the scene first if needed)
-int srt_debug_download_packed(srt_ctx* c, int mesh, float* exact16, float* filt8, float* filt2_8, float* tile_m)
+// diagnostic: download the device-side packed arrays of one mesh (packs the scene first if needed, for the
+// default box shape unless a render has packed another one)
+int srt_debug_download_packed(srt_ctx* c, int mesh, float* exact16, float* filt12, float* filt2_8)
 {
     if (!c) return SRT_ERR_INVALID;
     SRT_CUDA(c, cudaSetDevice(c->device));
-    int rc = pack_scene(c);
+    int rc = c->packed ? SRT_OK : pack_scene(c);
     if (rc) return rc;
     if (mesh < 0 || (size_t)mesh >= c->n_meshes) return fail(c, SRT_ERR_INVALID, "mesh index %d out of range", mesh);
     const MeshBuf& mb = c->meshes[mesh];
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (exact16 && mb.n) SRT_CUDA(c, cudaMemcpy(exact16, mb.exact, (size_t)mb.n * sizeof(srt::ExactTri), cudaMemcpyDeviceToHost));
-    if ((filt8 || filt2_8) && mb.n_padded) {
-        std::vector<float> rec((size_t)mb.n_padded * 16);            // device layout: 64 B records
-        SRT_CUDA(c, cudaMemcpy(rec.data(), mb.filt, rec.size() * sizeof(float), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < mb.n_padded; ++i) {
-            if (filt8) std::memcpy(filt8 + 8 * i, rec.data() + 16 * i, 8 * sizeof(float));
-            if (filt2_8) std::memcpy(filt2_8 + 8 * i, rec.data() + 16 * i + 8, 8 * sizeof(float));
-        }
-    }
-    const size_t tiles = (mb.n_padded + srt::kTileTris - 1) / srt::kTileTris;
-    if (tile_m && tiles) SRT_CUDA(c, cudaMemcpy(tile_m, mb.tile_m, tiles * sizeof(float), cudaMemcpyDeviceToHost));
+    if (filt12 && mb.n_padded) SRT_CUDA(c, cudaMemcpy(filt12, mb.filt0(), (size_t)mb.n_padded * sizeof(srt::FilterTri), cudaMemcpyDeviceToHost));
+    if (filt2_8 && mb.n_padded) SRT_CUDA(c, cudaMemcpy(filt2_8, mb.filt1(), (size_t)mb.n_padded * sizeof(srt::FilterTri2), cudaMemcpyDeviceToHost));
     return SRT_OK;
 }
 
-// diagnostic: triangles per shared-memory tile (granularity of tile_m)
-int srt_debug_tile_triangles(void) { return (int)srt::kTileTris; }
+// diagnostic: how meshes are packed -- padding granularity (triangles) and the default box of the filtered kernel
+int srt_debug_pack_info(uint32_t* pad_to, uint32_t* box_w, uint32_t* box_h)
+{
+    if (pad_to) *pad_to = srt::kGroupTris;
+    if (box_w) *box_w = SRT_BOX_PX;
+    if (box_h) *box_h = SRT_BOX_PY;
+    return SRT_OK;
+}
 
 // diagnostic (host only, no GPU): run the pre-pack for one mesh and return the packed arrays.
-// exact16: 16 floats per triangle; filt8 / filt2_8: 8 floats per padded triangle; tile_m: one per tile.
-int srt_debug_prepack(const float* vertices, uint32_t n, const srt_camera* cam, float* exact16, float* filt8,
-                      float* filt2_8, float* tile_m, uint32_t* n_padded, uint32_t* n_unfilterable)
+// exact16: 16 floats per triangle; filt12: 12, filt2_8: 8 floats per padded triangle.  box_w x box_h: the box the
+// level-0 bounds FilterTri::R / R2 (filt12[7], [11]) are packed for (0 = the default).
+int srt_debug_prepack(const float* vertices, uint32_t n, const srt_camera* cam, uint32_t box_w, uint32_t box_h,
+                      float* exact16, float* filt12, float* filt2_8, uint32_t* n_padded, uint32_t* n_unfilterable)
 {
     if (!vertices || !cam) return SRT_ERR_INVALID;
+    if (box_w == 0) { box_w = SRT_BOX_PX; box_h = SRT_BOX_PY; }
+    if (box_h == 0) box_h = 1;
     srt::FrameGeom g = srt::make_frame_geom(cam->origin, cam->detector, cam->up, cam->right, cam->pixel_spacing[0],
-                                            cam->pixel_spacing[1], cam->width, cam->height);
+                                            cam->pixel_spacing[1], cam->width, cam->height, box_w, box_h);
     srt::PackedMesh pm;
-    srt::prepack_mesh(vertices, nullptr, n, cam->origin, g, srt::kTileTris, srt::kGroupTris, pm);
+    srt::prepack_mesh(vertices, nullptr, n, cam->origin, g, srt::kGroupTris, pm);
     if (exact16) std::memcpy(exact16, pm.exact.data(), pm.exact.size() * sizeof(srt::ExactTri));
-    if (filt8) std::memcpy(filt8, pm.filt.data(), pm.filt.size() * sizeof(srt::FilterTri));
+    if (filt12) std::memcpy(filt12, pm.filt.data(), pm.filt.size() * sizeof(srt::FilterTri));
     if (filt2_8) std::memcpy(filt2_8, pm.filt2.data(), pm.filt2.size() * sizeof(srt::FilterTri2));
-    if (tile_m) std::memcpy(tile_m, pm.tile_m.data(), pm.tile_m.size() * sizeof(float));
     if (n_padded) *n_padded = pm.n_padded;
-    if (n_unfilterable) *n_unfilterable = pm.unfilterable + (g.filterable ? 0u : 0u);
+    if (n_unfilterable) *n_unfilterable = pm.unfilterable;
     return SRT_OK;
 }
 
@@ -921,8 +924,7 @@ int srt_debug_ffma_peak(srt_ctx* c, int repeats, float* tflops_out)
 // diagnostic: force the number of triangle-range splits of the filtered kernel (0 = heuristic)
 int srt_debug_force_splits(srt_ctx* c, int z_splits)
 {
-    if (!c || z_splits < -2 || z_splits > 64) return SRT_ERR_INVALID;
-    if (z_splits < 0) { c->split_forced_ppt = (z_splits == -1); return SRT_OK; }   // -1: pixels_per_thread 8 / 16 picks the split run length; -2: off
+    if (!c || z_splits < 0 || z_splits > 64) return SRT_ERR_INVALID;
     c->force_z_splits = z_splits;
     return SRT_OK;
 }

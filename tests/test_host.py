@@ -68,44 +68,50 @@ def test_prepack_exact_constants(srtlib, oracle, dragon):
     E = pk["exact"]
     expect = np.concatenate([e2, e1, tv, qv, e2q[:, None], srtlib.triangle_normals(dragon)], 1).astype(f)
     assert expect.dtype == f and (bits(E) == bits(expect)).all()
-    assert pk["unfilterable"] == 0 and pk["n_padded"] == len(dragon) + len(dragon) % 2
+    pad = srtlib.pack_info()[0]
+    assert pk["unfilterable"] == 0 and pk["n_padded"] == (len(dragon) + pad - 1) // pad * pad
+
+
+BOXES = [(16, 1), (32, 1), (16, 2), (8, 2), (8, 1)]          # box shapes the filtered kernel is built for
 
 
 @pytest.mark.parametrize("size,scale", [(128, 1.0), (2048, 1.0), (640, 3000.0), (640, 1e-4)])
-def test_level0_records_fit_binary16(srtlib, dragon, size, scale):
-    """The level-0 record is scaled by a power of two so the kernel can step it in binary16: |D| + margin <= 2^13 over
-    the frame, 15|bx| stays finite, and word 7 holds the binary16 x-slope of Y and the gate's binary16 margin."""
+def test_level0_box_bound(srtlib, dragon, size, scale):
+    """Word 7 of the level-0 record is the box bound R of the filtered kernel's gate |Y(c)| - |D(c)| > R: it must
+    cover the box radius of Y and D plus twice the strip margin (filter proof item 7), whatever the scene scale."""
     tri = (dragon * np.float32(scale)).astype(np.float32)
     lo, hi = srtlib.scene_bbox([(tri, 0.1)])
     cam = srtlib.camera_from_bbox(lo, hi, size, size)
-    pk = srtlib.debug_prepack(tri, cam)
-    assert pk["unfilterable"] == 0
-    f = pk["filt"][:len(tri)].astype(np.float64)
-    half = size / 2.0
-    dmax = np.abs(f[:, 3]) * half + np.abs(f[:, 4]) * half + np.abs(f[:, 5])
-    assert (dmax + f[:, 6] <= 8192.0 * (1 + 1e-6)).all() and (np.abs(f[:, 0]) <= 2050.0).all()
-    assert (dmax + f[:, 6] > 16.0).mean() > 0.99                   # ... and stays far above the binary16 subnormal range
-    w = np.ascontiguousarray(pk["filt"][:len(tri), 7]).view(np.uint32)
-    lo16, hi16 = (w & 0xffff).astype(np.uint16).view(np.float16), (w >> 16).astype(np.uint16).view(np.float16)
-    assert (lo16 == pk["filt"][:len(tri), 0].astype(np.float16)).all()
-    # high half: the gate's binary16 margin, an upper bound of m + 15 |bd| (growth of |D| along a run of 16 pixels)
-    mh = hi16.astype(np.float64)
-    assert (mh >= f[:, 6] + 15.0 * np.abs(f[:, 3])).all() and (mh <= 1.05 * (f[:, 6] + 15.0 * np.abs(f[:, 3]) + dmax / 512.0) + 1e-3).all()
-    assert np.isfinite(lo16.astype(np.float32)).all() and np.isfinite(hi16.astype(np.float32)).all()
+    for bw, bh in BOXES:
+        pk = srtlib.debug_prepack(tri, cam, box=(bw, bh))
+        assert pk["unfilterable"] == 0
+        f = pk["filt"][:len(tri)].astype(np.float64)
+        hx, hy = (bw - 1) / 2.0, (bh - 1) / 2.0
+        need = hx * (np.abs(f[:, 0]) + np.abs(f[:, 3])) + hy * (np.abs(f[:, 1]) + np.abs(f[:, 4])) + 2.0 * f[:, 6]
+        assert (f[:, 7] >= need).all() and (f[:, 7] <= need * (1 + 1e-5) + 1e-30).all()
+        g = pk["filt2"][:len(tri)].astype(np.float64)          # second strip: same coefficients as the level-1 record
+        assert (pk["filt"][:len(tri), 8:11] == pk["filt2"][:len(tri), 0:3]).all()
+        need2 = hx * (np.abs(f[:, 8]) + np.abs(f[:, 3])) + hy * (np.abs(f[:, 9]) + np.abs(f[:, 4])) + 2.0 * g[:, 3]
+        assert (f[:, 11] >= need2).all() and (f[:, 11] <= need2 * (1 + 1e-5) + 1e-30).all()
+        assert np.isfinite(pk["filt"]).all() and np.isfinite(pk["filt2"]).all() and (f[:, 6] > 0).all()
+    # padding records never survive: Y = 3e38, D = 0, R = 0
+    pad = pk["filt"][len(tri):]
+    assert len(pad) == pk["n_padded"] - len(tri) and (pad[:, 2] > 1e38).all() and (pad[:, 7] == 0).all() and (pad[:, 11] == 0).all()
 
 
 @pytest.mark.parametrize("size", [48, 96])
 def test_filter_never_rejects_a_hit_dragon(srtlib, oracle, dragon, size):
-    """CPU emulation of the kernel's FFMA filter vs the oracle for every (pixel, triangle) pair."""
+    """CPU emulation of the kernels' FFMA filter vs the oracle for every (pixel, triangle) pair, every box shape."""
     lo, hi = srtlib.scene_bbox([(dragon, 0.1)])
     cam = srtlib.camera_from_bbox(lo, hi, size, size)
-    pk = srtlib.debug_prepack(dragon, cam)
-    a = oracle.filter_audit(dragon, oracle.camera(dragon), size, size, pk)
-    assert a["pairs"] == size * size * len(dragon)
-    assert a["violations"] == 0 and a["run_violations"] == 0 and a["box_violations"] == 0
-    assert a["hits"] > 0 and a["survive1"] >= a["hits"]
-    assert a["survive0_tile"] < 0.03 * a["pairs"]          # the filter must actually filter
-    assert a["survive1"] < 10 * a["hits"]
+    for box in BOXES if size == 48 else BOXES[:1]:
+        pk = srtlib.debug_prepack(dragon, cam, box=box)
+        a = oracle.filter_audit(dragon, oracle.camera(dragon), size, size, pk)
+        assert a["pairs"] == size * size * len(dragon)
+        assert a["violations"] == 0 and a["box3_violations"] == 0 and a["box_violations"] == 0, (box, a)
+        assert a["hits"] > 0 and a["survive1"] >= a["hits"]
+        assert a["survive0_box"] < (0.25 if size == 48 else 0.02) * a["pairs"]     # the gate must actually filter (a box is up to 2/3 of a 48-pixel frame wide)
+        assert a["survive1"] < 10 * a["hits"]
 
 
 def _adversarial_mesh(cam_o, oracle, W, H, rng):
@@ -133,16 +139,17 @@ def _adversarial_mesh(cam_o, oracle, W, H, rng):
 
 
 def test_box_tests_never_reject_a_hit_ragged_frame(srtlib, oracle, dragon):
-    """The culled kernel's box tests (bin 256 x 128, CTA tile 64 x 16, warp tile 32 x 8, run 8 x 1; boxes clamped to the
-    frame) emulated on the CPU against the oracle, on a frame whose size is not a multiple of any box size and which is
-    larger than one bin in both directions."""
+    """The box tests of the filtered kernel (every box shape) and of the culled kernel (bin 256 x 128, CTA tile 64 x 16,
+    warp tile 32 x 8, run 8 x 1; boxes clamped to the frame) emulated on the CPU against the oracle, on a frame whose
+    size is not a multiple of any box size and which is larger than one bin in both directions."""
     W, H = 300, 150
     lo, hi = srtlib.scene_bbox([(dragon, 0.1)])
     cam = srtlib.camera_from_bbox(lo, hi, W, H)
     tri = np.ascontiguousarray(dragon[::8])
-    pk = srtlib.debug_prepack(tri, cam)
-    a = oracle.filter_audit(tri, oracle.camera(dragon), W, H, pk)
-    assert a["hits"] > 1500 and a["box_violations"] == 0 and a["violations"] == 0 and a["run_violations"] == 0
+    for box in BOXES:
+        pk = srtlib.debug_prepack(tri, cam, box=box)
+        a = oracle.filter_audit(tri, oracle.camera(dragon), W, H, pk)
+        assert a["hits"] > 1500 and a["box_violations"] == 0 and a["violations"] == 0 and a["box3_violations"] == 0, (box, a)
 
 
 def test_filter_never_rejects_a_hit_adversarial(srtlib, oracle, dragon):
@@ -152,9 +159,10 @@ def test_filter_never_rejects_a_hit_adversarial(srtlib, oracle, dragon):
     W = H = 40
     tri = _adversarial_mesh(cam_o, oracle, W, H, rng)
     cam = srtlib.camera_from_bbox(lo, hi, W, H)
-    pk = srtlib.debug_prepack(tri, cam)
-    a = oracle.filter_audit(tri, cam_o, W, H, pk)
-    assert a["violations"] == 0 and a["run_violations"] == 0 and a["box_violations"] == 0 and a["hits"] > 500
+    for box in BOXES:
+        pk = srtlib.debug_prepack(tri, cam, box=box)
+        a = oracle.filter_audit(tri, cam_o, W, H, pk)
+        assert a["violations"] == 0 and a["box3_violations"] == 0 and a["box_violations"] == 0 and a["hits"] > 500, (box, a)
 
 
 def test_unfilterable_triangles_always_survive(srtlib, oracle, dragon):
