@@ -1,27 +1,31 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the X-ray L-buffer hot path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--size 2048] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5] [--impl ours|reference]
 
-Workload (BASELINE.json configs[2], the configuration the metric is quoted on): dragon
-(22 866 triangles) L-buffer + Beer-Lambert attenuation + artefact repair at 2048 x 2048.
-A step is ONE frame: render (row band per rank) -> in-place NCCL all_gather of the bands
-(N > 1) -> repair on the assembled frame.  The frame is a fixed amount of work that is
-sharded over the ranks: scaling = "strong".
+Workloads (BASELINE.json configs):
+  c3 (default, the configuration the metric is quoted on): dragon (22 866 triangles), 2048 x 2048
+  c2: dragon, 1024 x 1024       c4: logo quad only (2 triangles), 1512 x 1512 (latency / memory bound)
+  c5: synthetic 998 000-triangle sphere, 8192 x 8192
+A step is ONE frame: L-buffer render + Beer-Lambert attenuation (block-cyclic 16-row blocks over the ranks at N > 1,
+each rank's kernels storing straight into every rank's frame over NVLink) -> artefact repair on the assembled frame.
+The frame is a fixed amount of work sharded over the ranks: scaling = "strong".
 
 Keys of the JSON line (see the task contract):
-  value        whole-job ray-triangle tests/s, scene + frame buffers resident in HBM
-  e2e          the same through the C-ABI with HOST buffers: srt_set_meshes (host vertices),
-               srt_set_camera, band render, all_gather, repair, image back to host memory
-  roofline     FP32-pipe roofline of the render kernel: 19 algorithmic flop per (ray, triangle)
-               test over the FFMA peak measured live on this GPU
-  cpu_baseline the reference's CPU implementation (oracle/_ref, else the oracle port) on a
-               bounded sample of the same frame on the host cores (rank 0, N = 1 only)
-  accelerated  the same frame through SRT_KERNEL_CULLED (hierarchical conservative culling, the
-               accelerated path the north star's "optional LBVH" stands for; identical results):
-               ms per step device-resident and end to end.  The headline keys above stay on the
-               brute-force path -- every (ray, triangle) pair evaluated -- that BASELINE.json's
-               metric, roofline and scaling targets are defined for.
+  value        whole-job ray-triangle tests/s, scene + frame buffers resident in HBM, brute-force kernel
+               (SRT_KERNEL_FILTERED: every thread visits every triangle, every (ray, triangle) pair is decided
+               by a proven-conservative reject or the reference's exact sequence)
+  e2e          N = 1: the same frame through the host-pointer plugin call a reference user makes --
+               srt_set_meshes(host vertices) + srt_set_camera + srt_render_xray(ordinary host image buffer) --
+               timed by the wall clock around the synchronous calls; `pinned` repeats it with srt_host_alloc
+               buffers.  N > 1 (one process per GPU): upload + sharded render + assembly + repair + image to host.
+  roofline     the dominant kernel is bound by the SM's instruction issue rate (no tensor-core or HBM roof applies:
+               0.3 % of the HBM roof): achieved = warp instructions / s (instructions per test from the committed
+               ncu capture x tests of the launch / kernel time by CUDA events), peak = 4 issue slots x SMs x the
+               SM clock sampled under load.  The FP32 figure SURVEY 8d asks for is kept as `fp32_equivalent`.
+  cpu_baseline the reference's CPU implementation (oracle/_ref, else the oracle port) on a bounded sample of the same
+               frame on the host cores (rank 0, N = 1 only)
+  accelerated  the same frame through SRT_KERNEL_CULLED (hierarchical conservative culling; identical results)
 
 --impl reference times that CPU implementation as the bench arm itself.
 """
@@ -40,7 +44,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 F_ALG = 19.0            # algorithmic flop per test
-NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.45 at 1965 MHz
+COUNTERS = ROOT / "profiles" / "r02_kernel_counters.json"      # ncu-derived per-kernel counters (tools/ncu_counters.py)
 
 
 def env_int(name, default):
@@ -110,6 +114,33 @@ def cpu_model():
     return "unknown"
 
 
+# ----------------------------------------------------------------------------- workloads
+def workload(args):
+    """-> dict(name, meshes [(tri, mu)], cam_tri (mesh the camera is derived from), W, H, tests per frame)."""
+    from simpleraytracing_b200 import scene
+    mu = float(scene.MU_MESH0)
+    cfg = args.config
+    if args.size:                                         # legacy: dragon at an arbitrary size
+        tri = scene.dragon(); W = H = args.size
+        name = f"X-ray L-buffer {W}x{H} dragon"
+        return dict(name=name, meshes=[(tri, mu)], cam_tri=tri, W=W, H=H)
+    if cfg in ("c2", "c3"):
+        tri = scene.dragon(); W = H = 1024 if cfg == "c2" else 2048
+        name = f"X-ray L-buffer {W}x{H} dragon (BASELINE configs[{1 if cfg == 'c2' else 2}])"
+        return dict(name=name, meshes=[(tri, mu)], cam_tri=tri, W=W, H=H)
+    if cfg == "c4":
+        d = scene.dragon()
+        lo = d.reshape(-1, 3).min(0); hi = d.reshape(-1, 3).max(0)
+        quad = scene.logo_quad(lo, hi)
+        return dict(name="logo-only attenuation 1512x1512, 2 triangles, camera of the dragon scene (BASELINE configs[3])",
+                    meshes=[(quad, mu)], cam_tri=d, W=1512, H=1512)
+    if cfg == "c5":
+        tri = scene.uv_sphere()
+        return dict(name="X-ray L-buffer 8192x8192 synthetic 998000-triangle sphere (BASELINE configs[4])",
+                    meshes=[(tri, mu)], cam_tri=tri, W=8192, H=8192)
+    raise SystemExit(f"unknown config {cfg}")
+
+
 # ----------------------------------------------------------------------------- CPU arms
 def cpu_reference_engine():
     """(kind, engine): the reference's own classes when oracle/_ref is built, else the oracle port."""
@@ -122,11 +153,13 @@ def cpu_reference_engine():
     return "port", Oracle()
 
 
-def cpu_sample_rate(engine, kind, tri, W, H, seconds, threads):
+def cpu_sample_rate(engine, kind, wl, seconds, threads):
     """Time the CPU L-buffer path on a contiguous pixel range through the frame centre.
     Brute-force cost is uniform per pixel, so tests/s of the sample is tests/s of the frame."""
+    tri = wl["meshes"][0][0]
+    W, H = wl["W"], wl["H"]
     ntri = len(tri)
-    cam = engine.camera(tri, [ntri]) if kind == "reference" else engine.camera(tri)
+    cam = engine.camera(wl["cam_tri"], [len(wl["cam_tri"])]) if kind == "reference" else engine.camera(wl["cam_tri"])
     start = (H // 2) * W
     n_pix = max(threads * 16, 256)
     while True:                                   # grow the sample until it takes about `seconds`
@@ -143,27 +176,27 @@ def run_reference_arm(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
-    from simpleraytracing_b200 import scene
-    tri = scene.dragon()
-    W = H = args.size
+    wl = workload(args)
+    tri = wl["meshes"][0][0]
+    W, H = wl["W"], wl["H"]
     kind, eng = cpu_reference_engine()
     threads = os.cpu_count() or 1
     per_step = max(0.5, min(8.0, 150.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
-        cpu_sample_rate(eng, kind, tri, W, H, per_step, threads)
-    rates, pix, secs = [], 0, 0.0
+        cpu_sample_rate(eng, kind, wl, per_step, threads)
+    pix, secs = 0, 0.0
     for _ in range(args.steps):
-        r, n_pix, dt = cpu_sample_rate(eng, kind, tri, W, H, per_step, threads)
-        rates.append(r); pix += n_pix; secs += dt
+        r, n_pix, dt = cpu_sample_rate(eng, kind, wl, per_step, threads)
+        pix += n_pix; secs += dt
     value = pix * len(tri) / secs
     frame_ms = W * H * len(tri) / value * 1e3
     sample = f"{pix // max(1, args.steps)} contiguous pixels of the {W}x{H} frame per step, all {len(tri)} triangles"
     line = {
-        "impl": "reference", "metric": "ray-triangle tests/s (X-ray L-buffer, dragon)", "value": value,
+        "impl": "reference", "metric": "ray-triangle tests/s (X-ray L-buffer)", "value": value,
         "unit": "tests/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "dragon mesh fixture (tests/golden/dragon_mesh.npz); CPU, no GPU used",
-        "config": {"workload": f"X-ray L-buffer {W}x{H} dragon (BASELINE configs[2])", "triangles": len(tri),
+        "dtype": "f32", "data": "dragon mesh fixture (tests/golden/dragon_mesh.npz) / synthetic; CPU, no GPU used",
+        "config": {"workload": wl["name"], "triangles": len(tri),
                    "ms_per_step_note": "full-frame time extrapolated from the sample (uniform cost per pixel)"},
         "cpu_baseline": {"value": value, "unit": "tests/s", "cores": threads, "cpu_model": cpu_model(), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -174,11 +207,31 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- our arm
+def load_counters(kernel_name, shape, W, world):
+    """Per-test instruction count and per-launch DRAM traffic of the dominant kernel from the committed ncu capture
+    (profiles/r02_kernel_counters.json, written by tools/ncu_counters.py from an `ncu --set full` report)."""
+    try:
+        doc = json.loads(COUNTERS.read_text())
+    except Exception:
+        return None
+    best = None
+    for e in doc.get("captures", []):
+        if e.get("kernel") != kernel_name:
+            continue
+        if shape is not None and e.get("box") not in (None, list(shape)):
+            continue
+        best = e
+        if e.get("width") == W and e.get("n_gpus", 1) == world:
+            break
+    return best
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from simpleraytracing_b200 import Context, Library, scene, KERNEL_CULLED
+    from simpleraytracing_b200 import Context, Library, PinnedArray, KERNEL_CULLED, KERNEL_FILTERED
     from simpleraytracing_b200.bands import BandLayout, InterleavedLayout, PeerFrames
+    from simpleraytracing_b200.capi import Camera
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
@@ -197,25 +250,28 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
-    tri = scene.dragon()
-    ntri = len(tri)
-    W = H = args.size
-    lo, hi = lib.scene_bbox([(tri, float(scene.MU_MESH0))])
+    wl = workload(args)
+    meshes, W, H = wl["meshes"], wl["W"], wl["H"]
+    ntri = sum(len(m[0]) for m in meshes[:1])                     # only mesh 0 is traversed (lbuffer.cxx:788)
+    lo, hi = lib.scene_bbox([(wl["cam_tri"], 0.0)])
     cam = lib.camera_from_bbox(lo, hi, W, H)
-    meshes = [(tri, float(scene.MU_MESH0))]
+    # a second camera for the multi-GPU check: detector moved and pixel spacing changed, same frame size
+    cam_b = Camera.from_buffer_copy(cam)
+    cam_b.detector[1] = cam.detector[1] + 7.5; cam_b.detector[2] = cam.detector[2] - 4.25
+    cam_b.pixel_spacing[0] = cam.pixel_spacing[0] * 0.9; cam_b.pixel_spacing[1] = cam.pixel_spacing[1] * 0.9
     ctx.set_meshes(meshes)
     ctx.set_camera(cam)
-    params = lib.default_params(kernel=args.kernel, pixels_per_thread=args.ppt)
+    params = lib.default_params(kernel=args.kernel, pixels_per_thread=args.box)
     params_acc = lib.default_params(kernel=KERNEL_CULLED)
 
     lay = BandLayout(H, W, world, rank)
     frame = lay.new_frame(torch.float32, dev)
-    # N > 1: block-cyclic 16-row blocks (contiguous bands are unbalanced: rows through the dragon are slower)
+    # N > 1: block-cyclic 16-row blocks (contiguous bands are unbalanced: rows through the object cost more)
     il = InterleavedLayout(H, W, world, rank)
     slots = il.new_slots(torch.float32, dev) if world > 1 else None
     my_slot_ptr = il.my_slot(slots).data_ptr() if world > 1 else 0
     my_rows = len(il.rows_of(rank)) if world > 1 else H
-    # N > 1, preferred: fused render + assembly -- the render kernel stores its rows straight into every rank's frame
+    # N > 1, preferred: fused render + assembly -- the render kernels store their rows straight into every rank's frame
     # over NVLink (multicast mapping when the switch offers one); falls back to all_gather + de-interleave
     peers, assembly = None, "single GPU"
     if world > 1:
@@ -224,8 +280,8 @@ def run_ours(args):
             try:
                 # two frame sets used alternately: one barrier per step is enough (a rank can run at most one step ahead)
                 peers = [PeerFrames(H, W, use_multicast=(args.assembly != "p2p")) for _ in range(2)]
-                assembly = ("render kernel stores to the NVSwitch multicast mapping of all frames" if peers[0].multicast_ptr
-                            else "render kernel stores to every peer's frame over NVLink") + " + one device barrier"
+                assembly = ("render kernels store (multimem.st) to the NVSwitch multicast mapping of all frames" if peers[0].multicast_ptr
+                            else "render kernels store to every peer's frame over NVLink") + " + one device barrier"
             except Exception as exc:                      # no peer access on this box
                 peers = None
                 assembly += f" (symmetric memory unavailable: {type(exc).__name__})"
@@ -237,7 +293,7 @@ def run_ours(args):
                 peers = None
                 assembly = "all_gather of slots + de-interleave kernel (symmetric memory unavailable on another rank)"
     image = torch.empty(H * W, dtype=torch.float32, device=dev)
-    host_image = torch.empty(H * W, dtype=torch.float32).pin_memory()
+    host_image_t = torch.empty(H * W, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     step_no = [0]
@@ -249,7 +305,8 @@ def run_ours(args):
         if peers is not None:
             pf = peers[step_no[0] & 1]
             step_no[0] += 1
-            ctx.render_lbuffer_blocks_device(p, world, rank, pf.pointers())
+            ptrs, mc = pf.pointers()
+            ctx.render_lbuffer_blocks_device(p, world, rank, ptrs, multicast=mc)
             pf.barrier()                                  # every rank's rows have landed in this rank's frame
             return pf.frame
         ctx.render_lbuffer_interleaved_device(p, world, rank, my_slot_ptr)
@@ -261,14 +318,14 @@ def run_ours(args):
         full = render_and_assemble(p)
         ctx.repair_device(p, full.data_ptr(), image.data_ptr())
 
-    def step_e2e(p=params):
-        # the call a user of the reference makes: host meshes + camera in, host image out
+    def step_e2e_sharded(p=params):
+        # one process per GPU: host meshes + camera in, sharded render, assembly, repair, image to host memory
         ctx.set_meshes(meshes)
         ctx.set_camera(cam)
         full = render_and_assemble(p)
         ctx.repair_device(p, full.data_ptr(), image.data_ptr())
         if rank == 0:                           # the result is needed on the host once
-            host_image.copy_(image, non_blocking=True)
+            host_image_t.copy_(image, non_blocking=True)
         stream.synchronize()
 
     def barrier():
@@ -298,7 +355,7 @@ def run_ours(args):
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in ev)
         if sync_each:
-            ms = max(ms, wall * 1e3)            # host work (pre-pack) is part of the end-to-end time
+            ms = max(ms, wall * 1e3)            # host work (upload, pre-pack launch) is part of the end-to-end time
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             every = [torch.zeros_like(t) for _ in range(world)]
@@ -307,50 +364,108 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # --- FP32 peak of this GPU (roofline denominator) before the clocks ramp down
-    peak_tf = ctx.ffma_peak_tflops(3)
+    def wall_timed(fn, steps, warmup):
+        """Synchronous host-pointer calls: wall clock around each call (L2 flushed before, outside the clock)."""
+        for _ in range(warmup):
+            fn()
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            total += time.perf_counter() - t0
+        return total * 1e3
 
+    peak_tf = ctx.ffma_peak_tflops(3)                     # FP32 FFMA peak of this GPU (secondary figure)
+    steps = args.steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    total_ms = timed(step_device, args.steps, args.warmup, sync_each=False)
-    # render-kernel-only time for the roofline: CUDA events around the kernel, on its stream
+    total_ms = timed(step_device, steps, args.warmup, sync_each=False)
+    # the dominant kernel alone: CUDA events around it on its stream (srt_timing.main_kernel_ms)
     barrier()
-    kern_ms = []
-    for _ in range(max(3, min(args.steps, 10))):
+    kern_ms, pass_ms = [], []
+    for _ in range(max(3, min(steps, 10))):
         flush.fill_(1)
         if world == 1:
             ctx.render_lbuffer_device(params, lay.rows, frame.data_ptr())
         elif peers is not None:
             barrier()
-            ctx.render_lbuffer_blocks_device(params, world, rank, peers[0].pointers())
+            ptrs, mc = peers[0].pointers()
+            ctx.render_lbuffer_blocks_device(params, world, rank, ptrs, multicast=mc)
         else:
             ctx.render_lbuffer_interleaved_device(params, world, rank, my_slot_ptr)
         tm = ctx.timing()
-        kern_ms.append(tm.render_ms)
-        render_launches = tm.launches              # filtered kernel (+ hit-list resolve when the triangle range is split)
+        kern_ms.append(tm.main_kernel_ms); pass_ms.append(tm.render_ms)
+        render_launches = tm.launches              # dominant kernel + hit-list resolve (resp. bin pass)
+        z_slices = tm.z_slices
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ms = timed(step_e2e, max(1, min(args.steps, 10)), max(1, min(args.warmup, 3)), sync_each=True)
-    e2e_steps = max(1, min(args.steps, 10))
     kernel_used = ctx.timing().kernel_used
-    # the accelerated path (not the headline): same frame, same step, SRT_KERNEL_CULLED
-    acc_ms = timed(lambda: step_device(params_acc), args.steps, 3, sync_each=False)
-    acc_kernel_used = ctx.timing().kernel_used
-    acc_e2e_ms = timed(lambda: step_e2e(params_acc), e2e_steps, 2, sync_each=True)
+    e2e_steps = max(1, min(steps, 10))
 
-    # correctness of the assembled frame (outside every timed region): the image this rank holds after a sharded
-    # step must equal, bit for bit, the image of one unsharded render on this GPU -- for both kernels
-    verified = True
+    # ---- end to end
+    e2e = {}
+    if world == 1:
+        host_image = np.empty(H * W, np.float32)                      # an ordinary (pageable) host buffer
+        host_meshes = [(np.array(m[0], np.float32, copy=True), m[1]) for m in meshes]
+
+        def plugin_call(img, ms_):
+            ctx.set_meshes(ms_)
+            ctx.set_camera(cam)
+            ctx.render_xray(params, out=img)                          # synchronous: returns with the image in host memory
+
+        e2e_ms = wall_timed(lambda: plugin_call(host_image, host_meshes), e2e_steps, 2)
+        pin_img = PinnedArray(lib, (H * W,), np.float32)
+        pin_tri = [PinnedArray(lib, m[0].shape, np.float32) for m in meshes]
+        for pa, m in zip(pin_tri, meshes):
+            pa.array[...] = m[0]
+        pinned_meshes = [(pa.array, m[1]) for pa, m in zip(pin_tri, meshes)]
+        e2e_pin_ms = wall_timed(lambda: plugin_call(pin_img.array, pinned_meshes), e2e_steps, 2)
+        e2e_same = bool(np.array_equal(pin_img.array.view(np.uint32), host_image.view(np.uint32)))
+        acc_e2e_ms = wall_timed(lambda: (ctx.set_meshes(pinned_meshes), ctx.set_camera(cam),
+                                         ctx.render_xray(params_acc, out=pin_img.array)), e2e_steps, 2)
+        e2e_path = "srt_set_meshes + srt_set_camera + srt_render_xray, ordinary host buffers, wall clock"
+        e2e.update({"pinned": {"ms_per_step": e2e_pin_ms / e2e_steps, "value": float(W) * H * ntri * e2e_steps / (e2e_pin_ms * 1e-3),
+                               "note": "same calls with srt_host_alloc (page-locked) vertex and image buffers",
+                               "image_equals_pageable_run": e2e_same}})
+        ctx.set_stream(stream.cuda_stream)
+    else:
+        e2e_ms = timed(step_e2e_sharded, e2e_steps, max(1, min(args.warmup, 3)), sync_each=True)
+        acc_e2e_ms = timed(lambda: step_e2e_sharded(params_acc), e2e_steps, 2, sync_each=True)
+        e2e_path = "per rank: srt_set_meshes + srt_set_camera + sharded render + assembly + repair; image to pinned host memory on rank 0"
+
+    # the accelerated path (not the headline): same frame, same step, SRT_KERNEL_CULLED
+    ctx.set_meshes(meshes); ctx.set_camera(cam)
+    acc_ms = timed(lambda: step_device(params_acc), steps, 3, sync_each=False)
+    acc_kernel_used = ctx.timing().kernel_used
+
+    # ---- correctness of the assembled frame (outside every timed region).  The frame a rank holds after a sharded
+    # step must equal, bit for bit, the image of one unsharded render on this GPU.  The check alternates between two
+    # cameras and poisons every rank's frame buffers with NaN before each sharded step, so a lost or late peer store
+    # (a missing barrier) cannot hide behind bytes left by an earlier step.
+    verified, checks = True, 0
     if world > 1:
         ref_L = torch.empty(H * W, dtype=torch.float32, device=dev)
         ref_img = torch.empty(H * W, dtype=torch.float32, device=dev)
-        for p_ in (params, params_acc):
+        nan = float("nan")
+        for it in range(args.verify_iters):
+            c_ = cam_b if (it & 1) else cam
+            p_ = params_acc if (it % 3 == 2) else params
+            ctx.set_camera(c_)
+            if peers is not None:
+                peers[step_no[0] & 1].frame.fill_(nan)
+            else:
+                slots.fill_(nan); frame.fill_(nan)
+            barrier()                                           # every rank has poisoned its buffers
             step_device(p_)
             ctx.render_lbuffer_device(p_, (0, H), ref_L.data_ptr())
             ctx.repair_device(p_, ref_L.data_ptr(), ref_img.data_ptr())
             stream.synchronize()
             same = torch.equal(image.view(torch.int32), ref_img.view(torch.int32))
             verified = verified and bool(same)
+            checks += 1
+        ctx.set_camera(cam)
         flag = torch.tensor([1 if verified else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         verified = bool(flag.item())
@@ -370,60 +485,71 @@ def run_ours(args):
         ctx.count_exact(False)
 
     tests_frame = float(W) * H * ntri
-    value = tests_frame * args.steps / (total_ms * 1e-3)
+    value = tests_frame * steps / (total_ms * 1e-3)
     e2e_value = tests_frame * e2e_steps / (e2e_ms * 1e-3)
     kt = float(np.mean(kern_ms)) * 1e-3
     per_rank_kernel = None
     if world > 1:
-        kt_t = torch.tensor([kt * 1e3], dtype=torch.float64, device=dev)
+        kt_t = torch.tensor([float(np.mean(pass_ms))], dtype=torch.float64, device=dev)
         every = [torch.zeros_like(kt_t) for _ in range(world)]
         dist.all_gather(every, kt_t)
         per_rank_kernel = [round(float(v.item()), 4) for v in every]
     band_tests = float(my_rows) * W * ntri
-    achieved_tf = band_tests * F_ALG / kt / 1e12
-    peak, peak_src = (peak_tf, "FFMA probe on this GPU (srt_debug_ffma_peak)") if peak_tf > 1 else \
-        (NOMINAL_FP32_TFLOPS, "nominal 148 SM x 128 lanes x 2 x 1965 MHz")
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
             kind, eng = cpu_reference_engine()
             threads = os.cpu_count() or 1
-            r, n_pix, dt = cpu_sample_rate(eng, kind, tri, W, H, args.cpu_seconds, threads)
+            r, n_pix, dt = cpu_sample_rate(eng, kind, wl, args.cpu_seconds, threads)
             cpu = {"value": r, "unit": "tests/s", "cores": threads, "cpu_model": cpu_model(), "kind": kind,
                    "sample": f"{n_pix} contiguous pixels of the {W}x{H} frame x {ntri} triangles in {dt:.1f} s"}
+        # ---- roofline of the dominant kernel: instruction-issue bound
+        kname = {KERNEL_FILTERED: "lbuffer_filtered_kernel", KERNEL_CULLED: "lbuffer_culled_kernel"}.get(kernel_used, "lbuffer_exact_kernel")
+        cnt = load_counters(kname, None, W, world)
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_peak = 4.0 * sms * sm_mhz * 1e6 / 1e9                      # G warp-instructions / s
+        roof = {"bound": "issue", "unit": "Gwarp-inst/s", "peak": issue_peak,
+                "peak_source": f"4 issue slots x {sms} SMs x {sm_mhz:.0f} MHz (SM clock sampled under load)",
+                "kernel": kname, "kernel_ms": kt * 1e3, "pass_ms": float(np.mean(pass_ms)), "z_slices": int(z_slices),
+                "tests_per_launch": band_tests, "exact_sequence_tests_per_launch": exact_counts.get("headline"),
+                "achieved": None, "frac": None, "traffic": None}
+        if cnt:
+            ipt = float(cnt["warp_inst_per_test"])
+            roof["achieved"] = ipt * band_tests / kt / 1e9
+            roof["frac"] = roof["achieved"] / issue_peak
+            roof["warp_inst_per_test"] = ipt
+            roof["counters_source"] = f"profiles/{COUNTERS.name}: {cnt.get('source', '')}"
+            if cnt.get("width") == W and cnt.get("n_gpus", 1) == world:
+                roof["traffic"] = cnt.get("dram_bytes")              # dram__bytes_read.sum + dram__bytes_write.sum, this launch shape
+            roof["algorithmic_bytes"] = 4.0 * my_rows * W             # the L-buffer rows this launch produces
+        # secondary: the reference's u-stage costed at 19 flop per test against the measured FFMA peak; the
+        # kernel decides that stage with far fewer instructions, so this is an equivalence figure, not a fraction of peak
+        roof["fp32_equivalent"] = {"flop_per_test": F_ALG, "equivalent_tflops": band_tests * F_ALG / kt / 1e12,
+                                   "ffma_peak_tflops": peak_tf, "note": "equivalent rate / FFMA peak is NOT a utilisation"}
+        h2d = int(sum(m[0].nbytes for m in meshes) + 4 * 16)
         line = {
-            "metric": "ray-triangle tests/s (X-ray L-buffer, dragon)", "value": value, "unit": "tests/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "metric": "ray-triangle tests/s (X-ray L-buffer)", "value": value, "unit": "tests/s",
+            "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": total_ms / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "dragon mesh fixture (reference dragon.ply, 22866 triangles); synthetic camera from its bbox",
-            "config": {"workload": f"X-ray L-buffer {W}x{H} dragon, row bands over {world} GPU(s) (BASELINE configs[2])",
-                       "triangles": ntri, "kernel": kernel_used,
-                       "kernel_note": "2 = SRT_KERNEL_FILTERED: the brute-force path, every (ray, triangle) pair evaluated",
+            "data": "dragon mesh fixture (reference dragon.ply, 22866 triangles) / synthetic sphere; camera from the scene bbox",
+            "config": {"workload": wl["name"], "triangles": ntri, "kernel": kernel_used,
+                       "kernel_note": "2 = SRT_KERNEL_FILTERED: the brute-force path, every thread visits every triangle",
                        "l2": "256 MiB flush write between steps",
                        "step": "render (16-row blocks, block-cyclic over ranks) + assembly + repair", "assembly": assembly,
-                       "assembled_frame_equals_unsharded_render": verified},
+                       "assembled_frame_equals_unsharded_render": verified,
+                       "assembly_check": None if world == 1 else f"{checks} sharded frames, two cameras alternating, frames poisoned with NaN before each"},
             "e2e": {"value": e2e_value, "unit": "tests/s", "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "h2d_bytes_per_step": int(tri.nbytes + 4 * 16 + 4 * (W + H)) + 0,
-                    "d2h_bytes_per_step": int(H * W * 4)},
-            "gpu_launches": (render_launches + (1 if (world == 1 or peers is not None) else 2)) * args.steps,   # + repair (+ de-interleave)
-            "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one full-frame launch, ncu --set full
-                         # (profiles/r01_ncu_filtered_final_2048.txt: 61 MB read + 175 MB written, mostly hit-list
-                         # bookkeeping and local-memory accumulators; algorithmic output is 16.8 MB); null for other shapes
-                         "traffic": 2.36e8 if (world == 1 and W == 2048) else None, "peak_source": peak_src,
-                         "kernel": "lbuffer_filtered_kernel", "kernel_ms": kt * 1e3,
-                         "flop_per_test": F_ALG, "tests_per_launch": band_tests,
-                         # secondary figure: the reference's literal 30.1 flop per test, scene weighted
-                         "achieved_literal_30p1_flop": band_tests * 30.1 / kt / 1e12,
-                         "exact_sequence_tests_per_launch": exact_counts.get("headline")},
+                    "path": e2e_path, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(H * W * 4), **e2e},
+            "gpu_launches": (render_launches + (1 if (world == 1 or peers is not None) else 2)) * steps,   # + repair (+ de-interleave)
+            "roofline": roof,
             "cpu_baseline": cpu,
             "clocks": clocks,
-            "per_rank": None if world == 1 else {"render_kernel_ms": per_rank_kernel,
+            "per_rank": None if world == 1 else {"render_pass_ms": per_rank_kernel,
                                                  "step_ms": [round(v, 4) for v in per_rank_ms[0]]},
             "accelerated": {"kernel": acc_kernel_used, "kernel_name": "SRT_KERNEL_CULLED (bins + CTA tiles + pixel runs, identical results)",
-                            "ms_per_step": acc_ms / args.steps, "value": tests_frame * args.steps / (acc_ms * 1e-3),
+                            "ms_per_step": acc_ms / steps, "value": tests_frame * steps / (acc_ms * 1e-3),
                             "unit": "tests/s (pairs resolved, most of them by a conservative box test)",
                             "e2e_ms_per_step": acc_e2e_ms / e2e_steps,
                             "exact_sequence_tests_per_launch": exact_counts.get("accelerated")},
@@ -441,16 +567,21 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--size", type=int, default=0, help="dragon at SIZE x SIZE instead of a named config")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", type=int, default=2, help="headline kernel: 2 filtered (brute force, default), 1 exact, 4 culled, 0 auto")
-    ap.add_argument("--ppt", type=int, default=0, help="pixels per thread (0 = auto)")
+    ap.add_argument("--box", type=lambda v: int(v, 0), default=0,
+                    help="box shape of the filtered kernel: width | height << 8 | boxes per thread << 16 (0 = default)")
     ap.add_argument("--assembly", default="auto", choices=["auto", "p2p", "allgather"],
                     help="N > 1: auto = fused stores (multicast if available, else per-peer), p2p = per-peer stores, allgather = NCCL")
+    ap.add_argument("--verify-iters", type=int, default=50, help="N > 1: sharded frames checked against unsharded renders")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.config == "c5" and args.steps > 5 and "--steps" not in " ".join(sys.argv):
+        args.steps = 3                                           # seconds per frame in the brute-force kernel
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)

@@ -16,8 +16,11 @@
  *   repair + Image::setPixel loop         ...lbuffer.cxx:329-404        srt_repair
  *   initialiseRayTracing / getBBox        ...lbuffer.cxx:585-667        srt_scene_bbox + srt_camera_from_bbox
  *   pthreadWorkLoadAllocation             ...lbuffer.cxx:694-725        srt_partition_rows
- *   MPI gather of pixel ranges            src/main-mpi.cxx:854-881      row bands + one NCCL allgather
- *                                                                       on the *_device buffers
+ *   MPI gather of pixel ranges            src/main-mpi.cxx:854-881      srt_multi_* (one process, N GPUs: the render
+ *                                                                       kernels store into every GPU's frame over
+ *                                                                       NVLink) or, one process per GPU,
+ *                                                                       srt_render_lbuffer_blocks_device on
+ *                                                                       peer-mapped frames
  *   renderLoop(Image&, meshes, detector, origin, up, right, Light)      srt_render_shaded
  *              src/main-omp.cxx:136-142,588-797
  *
@@ -101,6 +104,8 @@ typedef enum {
 } srt_kernel;
 
 #define SRT_FLAG_ALL_MESHES_CONTRIBUTE 1u  /* default off: only mesh 0 adds path length (lbuffer.cxx:788) */
+#define SRT_FLAG_FRAME0_MULTICAST 2u       /* srt_render_lbuffer_blocks_device: d_frames[0] is an NVSwitch multicast
+                                              mapping of every GPU's frame (written with multimem.st)             */
 
 typedef struct {
     float    incident;          /* initial L-buffer value, 80.0f (lbuffer.cxx:314)                    */
@@ -121,6 +126,10 @@ typedef struct {
     uint64_t filter_violations; /* SRT_KERNEL_AUDIT only: pairs the filter would have wrongly rejected */
     uint32_t kernel_used;       /* srt_kernel actually launched                                       */
     uint32_t launches;          /* kernels launched by the last call                                  */
+    float    main_kernel_ms;    /* the dominant kernel of the last render alone: lbuffer_filtered_kernel /
+                                   lbuffer_culled_kernel / lbuffer_exact_kernel (render_ms also covers the
+                                   second kernel of the pass: hit-list resolve, resp. the bin pass)   */
+    uint32_t z_slices;          /* filtered kernel: triangle slices (grid.z) of the last render       */
 } srt_timing;
 
 /* ---- context ------------------------------------------------------------ */
@@ -145,7 +154,15 @@ int  srt_partition_rows(uint32_t height, uint32_t n_parts, uint32_t part, uint32
 /* Triangle::computeNormal for n triangles (9 floats in, 3 out each). */
 int  srt_triangle_normals(const float* vertices, uint32_t n_triangles, float* normals_out);
 
+/* Page-locked host memory for images / vertex arrays the caller transfers every frame (cudaHostAlloc): host-pointer
+ * entry points accept any host pointer, pinned ones skip the staging copy of the driver. */
+int  srt_host_alloc(void** out, size_t bytes);
+void srt_host_free(void* p);
+
 /* ---- scene upload -------------------------------------------------------- */
+/* The arrays are copied to the GPU asynchronously on the context's stream.  Pageable arrays are staged before the call
+ * returns; PINNED arrays (srt_host_alloc, cudaHostAlloc) must stay valid and unmodified until srt_synchronize or the
+ * next synchronous (host-pointer) call on the context returns. */
 int  srt_set_meshes(srt_ctx* ctx, int n_meshes, const srt_mesh_desc* meshes);
 int  srt_set_camera(srt_ctx* ctx, const srt_camera* cam);
 
@@ -182,8 +199,9 @@ int  srt_deinterleave_device(srt_ctx* ctx, uint32_t n_parts, const float* d_slot
  * Fused render + assembly: rank `part` renders its 16-row blocks (same block-cyclic split) and the kernel stores
  * every L value at its IMAGE position (row * W + col) into each of the n_frames (1 ... 8) full-frame buffers in
  * d_frames -- the rank's own frame plus the peers' frames mapped over NVLink (CUDA IPC / symmetric memory), or a
- * single NVSwitch multicast mapping that replicates the store to every GPU.  The transfer overlaps the render
- * tile by tile; no all_gather and no de-interleave pass follow, only a barrier before srt_repair_device.
+ * single NVSwitch multicast mapping that replicates the store to every GPU (n_frames = 1 and
+ * SRT_FLAG_FRAME0_MULTICAST in params->flags).  The transfer overlaps the render tile by tile; no all_gather and
+ * no de-interleave pass follow, only a barrier before srt_repair_device.
  * Replaces the MPI_Send / MPI_Recv gather of src/main-mpi.cxx:854-881.
  */
 int  srt_render_lbuffer_blocks_device(srt_ctx* ctx, const srt_params* params, uint32_t n_parts, uint32_t part,
@@ -196,6 +214,32 @@ int  srt_repair_device(srt_ctx* ctx, const srt_params* params, const float* dL_i
 /* Whole frame in one call: L-buffer for all rows, repair, image to host
  * (what renderLoop + the output loop of main() produce; Image::getData layout). */
 int  srt_render_xray(srt_ctx* ctx, const srt_params* params, float* image_out);
+
+/* ---- one process, N GPUs (replaces the MPI driver, src/main-mpi.cxx:258-293 partition + :854-881 gather) ----
+ *
+ * srt_multi owns one context per device.  A frame is rendered in block-cyclic 16-row blocks (device i renders blocks
+ * i, i + N, ...); every render kernel stores its L values straight into the frame of EVERY device over NVLink peer
+ * mappings (cudaDeviceEnablePeerAccess), cross-device events order the renders before the repair passes, and each
+ * device ends up with the complete, repaired image -- bit-identical to a single-GPU render.  Scene and camera are
+ * replicated.  Requires peer access between all the devices (an NVLink / NVSwitch box); 1 <= n_devices <= 8.
+ */
+typedef struct srt_multi srt_multi;
+int  srt_multi_create(srt_multi** out, const int* device_ids, int n_devices);
+void srt_multi_destroy(srt_multi* m);
+const char* srt_multi_last_error(const srt_multi* m);     /* m may be NULL: last create error */
+int  srt_multi_device_count(const srt_multi* m);
+int  srt_multi_set_meshes(srt_multi* m, int n_meshes, const srt_mesh_desc* meshes);
+int  srt_multi_set_camera(srt_multi* m, const srt_camera* cam);
+/* Render + assemble + repair on all devices; asynchronous.  After srt_multi_synchronize the device pointers returned
+ * by srt_multi_frame hold the pre-repair L-buffer and the repaired image of the LAST render on every device. */
+int  srt_multi_render_xray_device(srt_multi* m, const srt_params* params);
+int  srt_multi_synchronize(srt_multi* m);
+int  srt_multi_frame(srt_multi* m, int index, float** d_L, float** d_image);
+/* The same, synchronous, image copied to host memory from the first device (what renderLoop + the gather leave on
+ * rank 0). */
+int  srt_multi_render_xray(srt_multi* m, const srt_params* params, float* image_out);
+/* Device time of the last render per device: render kernels (index i) and the whole step of the slowest device. */
+int  srt_multi_last_timing(srt_multi* m, float* render_ms_per_device, float* step_ms);
 
 /* ---- shaded variant (src/main-omp.cxx:588-797; same loop in main-mpi*.cxx / main-pthreads-rows.cxx) ---- */
 /*

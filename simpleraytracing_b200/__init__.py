@@ -7,9 +7,9 @@ classes under ``include/srt/``.  This Python package is only the thin ctypes bin
 by the tests and by ``bench.py``; it performs no computation and has no CPU fallback: if
 the library is missing it raises.
 """
-from .capi import (Library, Context, Camera, MeshDesc, Params, Timing, SrtError, load_library,
+from .capi import (Library, Context, MultiContext, PinnedArray, Camera, MeshDesc, Params, Timing, SrtError, load_library,
                    KERNEL_AUTO, KERNEL_EXACT, KERNEL_FILTERED, KERNEL_AUDIT, KERNEL_CULLED,
                    FLAG_ALL_MESHES_CONTRIBUTE)
 
-__all__ = ["Library", "Context", "Camera", "MeshDesc", "Params", "Timing", "SrtError", "load_library",
+__all__ = ["Library", "Context", "MultiContext", "PinnedArray", "Camera", "MeshDesc", "Params", "Timing", "SrtError", "load_library",
            "KERNEL_AUTO", "KERNEL_EXACT", "KERNEL_FILTERED", "KERNEL_AUDIT", "KERNEL_CULLED", "FLAG_ALL_MESHES_CONTRIBUTE"]

@@ -125,10 +125,11 @@ class PeerFrames:
         self.multicast_ptr = mc
 
     def pointers(self):
+        """-> (frame pointers for srt_render_lbuffer_blocks_device, is_multicast)"""
         own = self.peer_ptrs[self.rank]
         if self.multicast_ptr:
-            return [self.multicast_ptr]          # the switch replicates the store to every GPU, this one included
-        return [own] + [p for r, p in enumerate(self.peer_ptrs) if r != self.rank]
+            return [self.multicast_ptr], True    # the switch replicates the (multimem) store to every GPU, this one included
+        return [own] + [p for r, p in enumerate(self.peer_ptrs) if r != self.rank], False
 
     def barrier(self):
         self.handle.barrier(channel=0)

@@ -9,6 +9,7 @@ LIB_PATH = PKG / "lib" / "libsrt_b200.so"
 
 KERNEL_AUTO, KERNEL_EXACT, KERNEL_FILTERED, KERNEL_AUDIT, KERNEL_CULLED = 0, 1, 2, 3, 4
 FLAG_ALL_MESHES_CONTRIBUTE = 1
+FLAG_FRAME0_MULTICAST = 2
 
 
 class SrtError(RuntimeError):
@@ -49,7 +50,8 @@ class Params(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("render_ms", C.c_float), ("repair_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("pair_tests", C.c_uint64), ("exact_tests", C.c_uint64), ("filter_violations", C.c_uint64),
-                ("kernel_used", C.c_uint32), ("launches", C.c_uint32)]
+                ("kernel_used", C.c_uint32), ("launches", C.c_uint32), ("main_kernel_ms", C.c_float),
+                ("z_slices", C.c_uint32)]
 
 
 # every symbol include/srt.h declares (tests/test_abi.py checks the .so exports all of them)
@@ -60,6 +62,10 @@ EXPORTS = [
     "srt_repair_device", "srt_render_xray", "srt_interleave_slot_rows",
     "srt_render_lbuffer_interleaved_device", "srt_deinterleave_device", "srt_render_lbuffer_blocks_device", "srt_render_shaded",
     "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_force_splits", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_pack_info", "srt_debug_download_packed",
+    "srt_host_alloc", "srt_host_free",
+    "srt_multi_create", "srt_multi_destroy", "srt_multi_last_error", "srt_multi_device_count", "srt_multi_set_meshes",
+    "srt_multi_set_camera", "srt_multi_render_xray_device", "srt_multi_synchronize", "srt_multi_frame",
+    "srt_multi_render_xray", "srt_multi_last_timing",
 ]
 
 
@@ -119,6 +125,22 @@ class Library:
         L.srt_debug_pack_info.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
         L.srt_debug_ffma_peak.argtypes = [vp, i32, C.POINTER(C.c_float)]
         L.srt_debug_prepack.argtypes = [vp, u32, C.POINTER(Camera), u32, u32, vp, vp, vp, C.POINTER(u32), C.POINTER(u32)]
+        L.srt_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+        L.srt_host_free.argtypes = [vp]
+        L.srt_host_free.restype = None
+        L.srt_multi_create.argtypes = [C.POINTER(vp), C.POINTER(i32), i32]
+        L.srt_multi_destroy.argtypes = [vp]
+        L.srt_multi_destroy.restype = None
+        L.srt_multi_last_error.argtypes = [vp]
+        L.srt_multi_last_error.restype = C.c_char_p
+        L.srt_multi_device_count.argtypes = [vp]
+        L.srt_multi_set_meshes.argtypes = [vp, i32, C.POINTER(MeshDesc)]
+        L.srt_multi_set_camera.argtypes = [vp, C.POINTER(Camera)]
+        L.srt_multi_render_xray_device.argtypes = [vp, C.POINTER(Params)]
+        L.srt_multi_synchronize.argtypes = [vp]
+        L.srt_multi_frame.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
+        L.srt_multi_render_xray.argtypes = [vp, C.POINTER(Params), vp]
+        L.srt_multi_last_timing.argtypes = [vp, vp, C.POINTER(C.c_float)]
 
     # ---- host-only helpers ---------------------------------------------------
     def default_params(self, **kw):
@@ -292,10 +314,15 @@ class Context:
                                                     C.c_void_p(d_dist or None), C.c_void_p(d_ssum or None),
                                                     C.c_void_p(d_hits or None)))
 
-    def render_lbuffer_blocks_device(self, params, n_parts, part, frame_ptrs):
+    def render_lbuffer_blocks_device(self, params, n_parts, part, frame_ptrs, multicast=False):
         """Fused render + assembly: this rank's 16-row blocks, stored at image positions into every frame in
-        `frame_ptrs` (own frame first; peers' NVLink mappings or one multicast mapping after it)."""
+        `frame_ptrs` (own frame first, then the peers' NVLink mappings) -- or, with multicast=True, into the single
+        NVSwitch multicast mapping frame_ptrs[0]."""
         arr = (C.c_void_p * len(frame_ptrs))(*[C.c_void_p(int(q)) for q in frame_ptrs])
+        if multicast:
+            q = Params.from_buffer_copy(params)
+            q.flags |= FLAG_FRAME0_MULTICAST
+            params = q
         self._ck(self.lib.srt_render_lbuffer_blocks_device(self.h, C.byref(params), n_parts, part, len(frame_ptrs), arr))
 
     def render_lbuffer_interleaved_device(self, params, n_parts, part, d_slot, d_dist=0, d_ssum=0, d_hits=0):
@@ -354,3 +381,93 @@ class Context:
         t = Timing()
         self._ck(self.lib.srt_last_timing(self.h, C.byref(t)))
         return t
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory from srt_host_alloc (freed with the object)."""
+
+    def __init__(self, library, shape, dtype):
+        self.lib = library.lib
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        rc = self.lib.srt_host_alloc(C.byref(p), self.nbytes)
+        if rc:
+            raise SrtError(rc, self.lib.srt_last_error(None).decode())
+        self.ptr = p
+        buf = (C.c_char * self.nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self.lib.srt_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiContext:
+    """srt_multi: one process driving N GPUs (render kernels store into every GPU's frame over NVLink peer mappings)."""
+
+    def __init__(self, devices, library=None):
+        self.L = library or Library()
+        self.lib = self.L.lib
+        ids = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.srt_multi_create(C.byref(h), ids, len(devices))
+        if rc:
+            raise SrtError(rc, self.lib.srt_multi_last_error(None).decode())
+        self.h = h
+        self.n = len(devices)
+        self.cam = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.srt_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise SrtError(rc, self.lib.srt_multi_last_error(self.h).decode())
+
+    def set_meshes(self, meshes):
+        arr, keep = Library.mesh_descs(meshes)
+        self._ck(self.lib.srt_multi_set_meshes(self.h, len(meshes), arr))
+
+    def set_camera(self, cam):
+        self.cam = cam
+        self._ck(self.lib.srt_multi_set_camera(self.h, C.byref(cam)))
+
+    def render_xray(self, params, out=None):
+        n = self.cam.width * self.cam.height
+        img = np.empty(n, np.float32) if out is None else out
+        self._ck(self.lib.srt_multi_render_xray(self.h, C.byref(params), _ptr(img, np.float32)))
+        return img
+
+    def render_xray_device(self, params):
+        self._ck(self.lib.srt_multi_render_xray_device(self.h, C.byref(params)))
+
+    def synchronize(self):
+        self._ck(self.lib.srt_multi_synchronize(self.h))
+
+    def frame(self, index):
+        """-> (device pointer of the pre-repair L-buffer, device pointer of the repaired image) on device `index`"""
+        a = C.c_void_p(); b = C.c_void_p()
+        self._ck(self.lib.srt_multi_frame(self.h, index, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def timing(self):
+        """-> (render kernel ms per device, step ms of the slowest device)"""
+        per = np.zeros(self.n, np.float32); step = C.c_float()
+        self._ck(self.lib.srt_multi_last_timing(self.h, _ptr(per, np.float32), C.byref(step)))
+        return per, float(step.value)

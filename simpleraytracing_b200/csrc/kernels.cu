@@ -546,9 +546,12 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
         if (lane == 0) { w->filt0 = filt0; w->filt1 = Mp->filt1; w->exact = Mp->exact; w->n_tris = Mp->n; w->first = Mp->first; }
         __syncwarp();
 
+        // Slice z of z_splits streams tiles z, z + z_splits, ...: interleaved, because consecutive triangles of a mesh lie
+        // next to each other in the image -- a contiguous range would hand all the queue work (exact tests) of an image
+        // region to the one CTA whose pixels AND triangles are there, and the launch would wait for it.
         const uint32_t all_tiles = (n_padded + kTileTris - 1) / kTileTris;
-        const uint32_t t_first = (uint32_t)((uint64_t)all_tiles * cta.z / a.z_splits);
-        const uint32_t t_end = (uint32_t)((uint64_t)all_tiles * (cta.z + 1) / a.z_splits);
+        const uint32_t t_first = cta.z, t_step = a.z_splits;
+        const uint32_t t_end = all_tiles;
         // producer side: wait until every warp released the stage, then one thread refills it
         auto issue = [&](uint32_t t) {
             const uint32_t stage = issued % kStages;
@@ -564,8 +567,8 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
             ++issued;
         };
 
-        for (uint32_t t = t_first; t < min(t_first + kStages - 1, t_end); ++t) issue(t);
-        for (uint32_t t = t_first; t < t_end; ++t) {
+        for (uint32_t i = 0, t = t_first; i < kStages - 1 && t < t_end; ++i, t += t_step) issue(t);
+        for (uint32_t t = t_first; t < t_end; t += t_step) {
             __syncwarp();          // re-converge after the single-lane producer / release code
             const uint32_t stage = consumed % kStages;
             mbar_wait(&full[stage], (consumed / kStages) & 1u);
@@ -584,7 +587,7 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);        // this warp is done with the stage
             ++consumed;
-            if (t + kStages - 1 < t_end) issue(t + kStages - 1);
+            if (t + (kStages - 1) * t_step < t_end) issue(t + (kStages - 1) * t_step);
         }
         // the queues hold mesh-local triangle indices: empty them before the next mesh
         __syncwarp();
@@ -1374,6 +1377,25 @@ uint32_t filtered_cta_width(uint32_t px, uint32_t py, uint32_t nb)
     return 0;
 }
 
+template <int PX, int PY, int NB>
+static int filtered_occupancy_t()
+{
+    using G = BoxGeom<PX, PY, NB>;
+    constexpr size_t smem = (size_t)kStages * kTileTris * 48 + 2 * kStages * sizeof(uint64_t) + 4 * sizeof(WarpCtx) +
+                            4 * kQ2Cap * sizeof(uint2) + 4 * G::kQ1Cap * sizeof(uint32_t);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lbuffer_filtered_kernel<PX, PY, NB>, 128, smem) != cudaSuccess) n = 0;
+    return n;
+}
+
+int filtered_resident_ctas(uint32_t px, uint32_t py, uint32_t nb)
+{
+#define X(PX, PY, NB) if (px == PX && py == PY && nb == NB) return filtered_occupancy_t<PX, PY, NB>();
+    SRT_BOX_SHAPES(X)
+#undef X
+    return 0;
+}
+
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, cudaStream_t s)
 {
     if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0) return cudaSuccess;
@@ -1384,12 +1406,16 @@ cudaError_t launch_lbuffer_filtered(const RenderArgs& a, cudaStream_t s)
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_lbuffer_culled(const RenderArgs& a, cudaStream_t s)
+cudaError_t launch_lbuffer_bins(const RenderArgs& a, cudaStream_t s)
 {
     if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0) return cudaSuccess;
     bin_kernel<<<dim3(a.bins_x, a.bins_y, (unsigned)a.n_meshes), kBinThreads, 0, s>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lbuffer_culled(const RenderArgs& a, cudaStream_t s)
+{
+    if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0) return cudaSuccess;
     lbuffer_culled_kernel<<<dim3((a.cam.W + 63) / 64, a.n_blocks), 128, 0, s>>>(a);
     return cudaGetLastError();
 }

@@ -75,8 +75,8 @@ struct RenderArgs {
     // exact tests of a warp run wherever a lane is free) but appended to the pixel's hit list {scene-wide triangle
     // index, value} -- value = sign * t (mode 0) or t (mode 1) -- through an atomic slot counter; resolve_hits_kernel
     // sorts each list by triangle index and replays lbuffer.cxx:788-809 (or the z-buffer update, main-omp.cxx:656-662)
-    // in the reference's order.  With z_splits > 1 the CTAs of grid.z slice z stream only tiles
-    // [n_tiles * z / z_splits, n_tiles * (z + 1) / z_splits) of each mesh (small grids still fill the GPU).
+    // in the reference's order.  With z_splits > 1 the CTAs of grid.z slice z stream only tiles z, z + z_splits, ...
+    // of each mesh (small grids still fill the GPU).
     uint32_t box_px, box_py, box_nb;   // box size (pixels) and boxes per thread (side by side along x)
     uint32_t z_splits;
     uint2* hit_entries;      // [pixel][hit_cap]
@@ -125,8 +125,10 @@ cudaError_t launch_lbuffer_filtered(const RenderArgs& a, cudaStream_t s);
 constexpr uint32_t kMaxHitCapacity = 16;
 bool filtered_box_supported(uint32_t box_px, uint32_t box_py);
 uint32_t filtered_cta_width(uint32_t box_px, uint32_t box_py, uint32_t box_nb);   // 0: shape not built
-// Culled kernel: bin pass (every triangle against every bin of a.bins_x x a.bins_y) + render pass.  Same results
+int filtered_resident_ctas(uint32_t box_px, uint32_t box_py, uint32_t box_nb);      // CTAs resident per SM on the current device
+// Culled kernel: bin pass (every triangle against every bin of a.bins_x x a.bins_y), then the render pass.  Same results
 // as the other kernels: the bins and the per-CTA cull only ever drop pairs the conservative filter proves to miss.
+cudaError_t launch_lbuffer_bins(const RenderArgs& a, cudaStream_t s);
 cudaError_t launch_lbuffer_culled(const RenderArgs& a, cudaStream_t s);
 // Scatter gathered slots [n_parts][slot_rows][W] (block-cyclic 16-row blocks) back to image order [H][W].
 cudaError_t launch_deinterleave(const float* slots, float* frame, uint32_t W, uint32_t H, uint32_t n_parts,

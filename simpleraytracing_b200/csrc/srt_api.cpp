@@ -38,9 +38,6 @@
 #ifndef SRT_BOX_NB
 #define SRT_BOX_NB 2
 #endif
-#ifndef SRT_TARGET_WAVES
-#define SRT_TARGET_WAVES 12      // waves of CTAs a launch of the filtered kernel is split into (triangle-range slices)
-#endif
 
 namespace {
 
@@ -69,7 +66,7 @@ struct srt_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // render begin / end, repair begin / end, main kernel begin / end
     std::string error;
 
     std::vector<MeshBuf> meshes;
@@ -365,20 +362,31 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         if (c->total_tris >= (1ull << 25)) kernel = SRT_KERNEL_EXACT;   // queue entries hold 25-bit triangle indices
     }
     if (kernel == SRT_KERNEL_FILTERED) {
-        // Triangle-range slices (grid.z): shorter CTAs in more waves balance the SMs better (CTA run times vary with
-        // their queue work) and keep small grids -- a rank's share of a multi-GPU frame -- at full occupancy.
+        // Triangle slices (grid.z): CTA (x, y, z) streams every z_splits-th tile of the mesh, so that a grid of few
+        // pixel tiles -- a rank's share of a multi-GPU frame -- still fills the GPU.  The scan work of a CTA is uniform
+        // (tiles per slice), so the launch time is ~ waves x (tiles per slice + a fixed per-CTA cost of about half a
+        // tile): the slice count minimises that, i.e. it avoids both a mostly empty last wave and a ragged tile count.
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         const uint32_t cta_w = srt::filtered_cta_width(box_px, box_py, box_nb);
         const uint64_t ctas = (uint64_t)((cam.width + cta_w - 1) / cta_w) * a.n_blocks;
-        const uint64_t slots = (uint64_t)sms * SRT_RESIDENT_CTAS;
-        uint32_t zs = 1;
-        if (ctas > 0) zs = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, ((uint64_t)SRT_TARGET_WAVES * slots + ctas / 2) / ctas));
-        if (c->force_z_splits > 0) zs = (uint32_t)c->force_z_splits;
+        int resident = srt::filtered_resident_ctas(box_px, box_py, box_nb);
+        if (resident <= 0) resident = SRT_RESIDENT_CTAS;
+        const uint64_t slots = (uint64_t)sms * (uint64_t)resident;
         uint64_t max_tiles = 1;
         for (size_t m = 0; m < c->n_meshes; ++m)
             max_tiles = std::max<uint64_t>(max_tiles, (c->meshes[m].n_padded + srt::kTileTris - 1) / srt::kTileTris);
-        zs = (uint32_t)std::min<uint64_t>(zs, std::max<uint64_t>(1, max_tiles / 2));     // at least two tiles per slice
+        uint32_t zs = 1;
+        if (ctas > 0) {
+            const uint32_t zmax = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, max_tiles / 2));   // >= 2 tiles per slice
+            double best = 1e300;
+            for (uint32_t z = 1; z <= zmax; ++z) {
+                const double waves = (double)((ctas * z + slots - 1) / slots);
+                const double cost = waves * ((double)((max_tiles + z - 1) / z) + 0.5);
+                if (cost <= best * 1.0001) { best = cost; zs = z; }                 // ties: more, shorter CTAs
+            }
+        }
+        if (c->force_z_splits > 0) zs = (uint32_t)std::min<uint64_t>((uint64_t)c->force_z_splits, max_tiles);
         // per-pixel hit lists: 4 + 8 * cap bytes per pixel of the launch's output index range
         const size_t pixels = (size_t)(parts == 0 ? cam.height : a.n_blocks * 16) * cam.width;
         const uint32_t cap = pixels <= ((size_t)1 << 24) ? 12u : 8u;
@@ -395,13 +403,23 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     }
     SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     if (kernel == SRT_KERNEL_FILTERED) {
+        SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
         SRT_CUDA(c, srt::launch_lbuffer_filtered(a, c->stream));
+        SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
         SRT_CUDA(c, srt::launch_resolve_hits(a, c->stream)); extra_launches = 1;
     } else if (kernel == SRT_KERNEL_CULLED) {
-        SRT_CUDA(c, srt::launch_lbuffer_culled(a, c->stream)); extra_launches = 1;
-    } else SRT_CUDA(c, srt::launch_lbuffer_exact(a, audit, c->stream));
+        SRT_CUDA(c, srt::launch_lbuffer_bins(a, c->stream)); extra_launches = 1;
+        SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+        SRT_CUDA(c, srt::launch_lbuffer_culled(a, c->stream));
+        SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+    } else {
+        SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+        SRT_CUDA(c, srt::launch_lbuffer_exact(a, audit, c->stream));
+        SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+    }
     SRT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     c->timing.kernel_used = kernel;
+    c->timing.z_slices = a.z_splits;
     c->timing.launches = ((band_rows > 0) ? 1 + extra_launches : 0) + (repack ? 1 + (uint32_t)c->n_meshes : 0);
     const uint64_t tris = all ? c->total_tris : c->mesh0_tris;
     c->timing.pair_tests = (uint64_t)band_rows * cam.width * tris;
@@ -557,6 +575,18 @@ int srt_partition_rows(uint32_t H, uint32_t n_parts, uint32_t part, uint32_t* rb
     return SRT_OK;
 }
 
+int srt_host_alloc(void** out, size_t bytes)
+{
+    if (!out) return SRT_ERR_INVALID;
+    *out = nullptr;
+    if (bytes == 0) return SRT_OK;
+    const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { *out = nullptr; return fail(nullptr, e == cudaErrorMemoryAllocation ? SRT_ERR_NOMEM : SRT_ERR_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
+    return SRT_OK;
+}
+
+void srt_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 // ---- scene --------------------------------------------------------------------
 int srt_set_meshes(srt_ctx* c, int n_meshes, const srt_mesh_desc* meshes)
 {
@@ -661,8 +691,10 @@ int srt_render_lbuffer_blocks_device(srt_ctx* c, const srt_params* p, uint32_t n
         if (!d_frames[i]) return fail(c, SRT_ERR_INVALID, "frame pointer %u is NULL", i);
     if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
     SRT_CUDA(c, cudaSetDevice(c->device));
+    const bool multicast = (p && (p->flags & SRT_FLAG_FRAME0_MULTICAST) != 0);
+    if (multicast && n_frames != 1) return fail(c, SRT_ERR_INVALID, "a multicast mapping is the only frame of the call");
     return render_device(c, p, 0, c->camera.height, d_frames[0], nullptr, nullptr, nullptr, n_parts, part, 0,
-                         d_frames + 1, n_frames - 1, /*image_positions*/ true, /*multicast*/ false);
+                         d_frames + 1, n_frames - 1, /*image_positions*/ true, multicast);
 }
 
 int srt_deinterleave_device(srt_ctx* c, uint32_t n_parts, const float* d_slots, float* d_frame)
@@ -835,6 +867,7 @@ int srt_last_timing(srt_ctx* c, srt_timing* out)
         SRT_CUDA(c, cudaSetDevice(c->device));
         SRT_CUDA(c, cudaEventSynchronize(c->ev[1]));
         SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
+        SRT_CUDA(c, cudaEventElapsedTime(&c->timing.main_kernel_ms, c->ev[4], c->ev[5]));
         if (c->counters_pending && c->d_counters) {
             unsigned long long cnts[2] = { 0, 0 };
             SRT_CUDA(c, cudaMemcpyAsync(cnts, c->d_counters, sizeof cnts, cudaMemcpyDeviceToHost, c->stream));
@@ -934,6 +967,244 @@ int srt_debug_count_exact(srt_ctx* c, int enable)
 {
     if (!c) return SRT_ERR_INVALID;
     c->count_exact = enable != 0;
+    return SRT_OK;
+}
+
+
+// ---- one process, N GPUs -------------------------------------------------------------------------
+} // extern "C"
+
+struct srt_multi {
+    int n = 0;
+    std::vector<int> dev;
+    std::vector<srt_ctx*> ctx;
+    std::vector<float*> L[2];            // two frame sets used alternately (one cross-device barrier per step suffices)
+    std::vector<float*> img;
+    std::vector<cudaEvent_t> ev_start, ev_rendered, ev_end;
+    size_t frame_cap = 0;
+    unsigned step = 0;
+    bool have_camera = false; uint32_t W = 0, H = 0;
+    std::string error;
+};
+
+namespace {
+
+int mfail(srt_multi* m, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (m) m->error = buf; else g_create_error = buf;
+    return code;
+}
+
+#define SRT_MCUDA(m, call)                                                                       \
+    do { cudaError_t e__ = (call);                                                               \
+         if (e__ != cudaSuccess) return mfail((m), SRT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); } while (0)
+
+void multi_free_frames(srt_multi* m)
+{
+    for (int i = 0; i < m->n; ++i) {
+        cudaSetDevice(m->dev[i]);
+        for (int s = 0; s < 2; ++s) { if (i < (int)m->L[s].size()) cudaFree(m->L[s][i]); }
+        if (i < (int)m->img.size()) cudaFree(m->img[i]);
+    }
+    m->L[0].assign(m->n, nullptr); m->L[1].assign(m->n, nullptr); m->img.assign(m->n, nullptr);
+    m->frame_cap = 0;
+}
+
+int multi_ensure_frames(srt_multi* m, size_t pixels)
+{
+    if (pixels <= m->frame_cap) return SRT_OK;
+    int rc = srt_multi_synchronize(m);
+    if (rc) return rc;
+    multi_free_frames(m);
+    for (int i = 0; i < m->n; ++i) {
+        SRT_MCUDA(m, cudaSetDevice(m->dev[i]));
+        for (int s = 0; s < 2; ++s) SRT_MCUDA(m, cudaMalloc(&m->L[s][i], pixels * sizeof(float)));
+        SRT_MCUDA(m, cudaMalloc(&m->img[i], pixels * sizeof(float)));
+    }
+    m->frame_cap = pixels;
+    return SRT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int srt_multi_create(srt_multi** out, const int* device_ids, int n_devices)
+{
+    if (!out) return mfail(nullptr, SRT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!device_ids || n_devices < 1 || n_devices > 8) return mfail(nullptr, SRT_ERR_INVALID, "1 to 8 device ids expected");
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (device_ids[i] == device_ids[j]) return mfail(nullptr, SRT_ERR_INVALID, "device %d listed twice", device_ids[i]);
+    srt_multi* m = new (std::nothrow) srt_multi();
+    if (!m) return mfail(nullptr, SRT_ERR_NOMEM, "out of host memory");
+    m->n = n_devices;
+    m->dev.assign(device_ids, device_ids + n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        srt_ctx* c = nullptr;
+        const int rc = srt_create(&c, device_ids[i]);
+        if (rc) { srt_multi_destroy(m); return rc; }              // message already in the create-error slot
+        m->ctx.push_back(c);
+    }
+    // every device maps every other device's memory: the render kernels store into the peers' frames
+    for (int i = 0; i < n_devices; ++i) {
+        cudaSetDevice(device_ids[i]);
+        for (int j = 0; j < n_devices; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, device_ids[i], device_ids[j]);
+            if (!can) {
+                srt_multi_destroy(m);
+                return mfail(nullptr, SRT_ERR_NO_DEVICE, "device %d cannot access device %d's memory (peer access is required)",
+                             device_ids[i], device_ids[j]);
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                srt_multi_destroy(m);
+                return mfail(nullptr, SRT_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", device_ids[i], device_ids[j], cudaGetErrorString(e));
+            }
+            cudaGetLastError();                                    // clear "already enabled"
+        }
+    }
+    m->ev_start.assign(n_devices, nullptr); m->ev_rendered.assign(n_devices, nullptr); m->ev_end.assign(n_devices, nullptr);
+    m->L[0].assign(n_devices, nullptr); m->L[1].assign(n_devices, nullptr); m->img.assign(n_devices, nullptr);
+    for (int i = 0; i < n_devices; ++i) {
+        cudaSetDevice(device_ids[i]);
+        if (cudaEventCreate(&m->ev_start[i]) != cudaSuccess || cudaEventCreate(&m->ev_end[i]) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_rendered[i], cudaEventDisableTiming) != cudaSuccess) {
+            srt_multi_destroy(m);
+            return mfail(nullptr, SRT_ERR_CUDA, "event creation failed on device %d", device_ids[i]);
+        }
+    }
+    *out = m;
+    return SRT_OK;
+}
+
+void srt_multi_destroy(srt_multi* m)
+{
+    if (!m) return;
+    for (size_t i = 0; i < m->ctx.size(); ++i) { cudaSetDevice(m->dev[i]); cudaStreamSynchronize(m->ctx[i]->stream); }
+    if (!m->img.empty()) multi_free_frames(m);
+    for (size_t i = 0; i < m->ev_start.size(); ++i) {
+        cudaSetDevice(m->dev[i]);
+        if (m->ev_start[i]) cudaEventDestroy(m->ev_start[i]);
+        if (m->ev_rendered[i]) cudaEventDestroy(m->ev_rendered[i]);
+        if (m->ev_end[i]) cudaEventDestroy(m->ev_end[i]);
+    }
+    for (srt_ctx* c : m->ctx) srt_destroy(c);
+    delete m;
+}
+
+const char* srt_multi_last_error(const srt_multi* m) { return m ? m->error.c_str() : g_create_error.c_str(); }
+
+int srt_multi_device_count(const srt_multi* m) { return m ? m->n : 0; }
+
+int srt_multi_set_meshes(srt_multi* m, int n_meshes, const srt_mesh_desc* meshes)
+{
+    if (!m) return SRT_ERR_INVALID;
+    for (int i = 0; i < m->n; ++i) {
+        const int rc = srt_set_meshes(m->ctx[i], n_meshes, meshes);
+        if (rc) return mfail(m, rc, "device %d: %s", m->dev[i], m->ctx[i]->error.c_str());
+    }
+    return SRT_OK;
+}
+
+int srt_multi_set_camera(srt_multi* m, const srt_camera* cam)
+{
+    if (!m) return SRT_ERR_INVALID;
+    for (int i = 0; i < m->n; ++i) {
+        const int rc = srt_set_camera(m->ctx[i], cam);
+        if (rc) return mfail(m, rc, "device %d: %s", m->dev[i], m->ctx[i]->error.c_str());
+    }
+    m->have_camera = true; m->W = cam->width; m->H = cam->height;
+    return SRT_OK;
+}
+
+int srt_multi_synchronize(srt_multi* m)
+{
+    if (!m) return SRT_ERR_INVALID;
+    for (int i = 0; i < m->n; ++i) {
+        SRT_MCUDA(m, cudaSetDevice(m->dev[i]));
+        SRT_MCUDA(m, cudaStreamSynchronize(m->ctx[i]->stream));
+    }
+    return SRT_OK;
+}
+
+int srt_multi_render_xray_device(srt_multi* m, const srt_params* params)
+{
+    if (!m) return SRT_ERR_INVALID;
+    if (!params) return mfail(m, SRT_ERR_INVALID, "params is NULL");
+    if (!m->have_camera) return mfail(m, SRT_ERR_INVALID, "srt_multi_set_camera has not been called");
+    int rc = multi_ensure_frames(m, (size_t)m->W * m->H);
+    if (rc) return rc;
+    const unsigned set = m->step & 1u;
+    // 1. every device renders its blocks into the frame of every device
+    for (int i = 0; i < m->n; ++i) {
+        srt_ctx* c = m->ctx[i];
+        SRT_MCUDA(m, cudaSetDevice(m->dev[i]));
+        SRT_MCUDA(m, cudaEventRecord(m->ev_start[i], c->stream));
+        float* peers[7]; uint32_t np = 0;
+        for (int j = 0; j < m->n; ++j) if (j != i) peers[np++] = m->L[set][j];
+        rc = render_device(c, params, 0, m->H, m->L[set][i], nullptr, nullptr, nullptr, (uint32_t)m->n, (uint32_t)i, 0,
+                           np ? peers : nullptr, np, /*image_positions*/ true, /*multicast*/ false);
+        if (rc) return mfail(m, rc, "device %d: %s", m->dev[i], c->error.c_str());
+        SRT_MCUDA(m, cudaEventRecord(m->ev_rendered[i], c->stream));
+    }
+    // 2. cross-device barrier (events), then the repair pass on every device's own, now complete, frame
+    for (int i = 0; i < m->n; ++i) {
+        srt_ctx* c = m->ctx[i];
+        SRT_MCUDA(m, cudaSetDevice(m->dev[i]));
+        for (int j = 0; j < m->n; ++j) if (j != i) SRT_MCUDA(m, cudaStreamWaitEvent(c->stream, m->ev_rendered[j], 0));
+        rc = srt_repair_device(c, params, m->L[set][i], m->img[i]);
+        if (rc) return mfail(m, rc, "device %d: %s", m->dev[i], c->error.c_str());
+        SRT_MCUDA(m, cudaEventRecord(m->ev_end[i], c->stream));
+    }
+    ++m->step;
+    return SRT_OK;
+}
+
+int srt_multi_frame(srt_multi* m, int index, float** d_L, float** d_image)
+{
+    if (!m || index < 0 || index >= m->n) return SRT_ERR_INVALID;
+    if (m->step == 0 || m->frame_cap == 0) return mfail(m, SRT_ERR_INVALID, "no frame has been rendered yet");
+    const unsigned set = (m->step - 1) & 1u;
+    if (d_L) *d_L = m->L[set][index];
+    if (d_image) *d_image = m->img[index];
+    return SRT_OK;
+}
+
+int srt_multi_render_xray(srt_multi* m, const srt_params* params, float* image_out)
+{
+    if (!m) return SRT_ERR_INVALID;
+    if (!image_out) return mfail(m, SRT_ERR_INVALID, "image_out is NULL");
+    int rc = srt_multi_render_xray_device(m, params);
+    if (rc) return rc;
+    SRT_MCUDA(m, cudaSetDevice(m->dev[0]));
+    SRT_MCUDA(m, cudaMemcpyAsync(image_out, m->img[0], (size_t)m->W * m->H * sizeof(float), cudaMemcpyDeviceToHost, m->ctx[0]->stream));
+    return srt_multi_synchronize(m);
+}
+
+int srt_multi_last_timing(srt_multi* m, float* render_ms_per_device, float* step_ms)
+{
+    if (!m) return SRT_ERR_INVALID;
+    if (m->step == 0) return mfail(m, SRT_ERR_INVALID, "no frame has been rendered yet");
+    int rc = srt_multi_synchronize(m);
+    if (rc) return rc;
+    float worst = 0.0f;
+    for (int i = 0; i < m->n; ++i) {
+        SRT_MCUDA(m, cudaSetDevice(m->dev[i]));
+        srt_timing t{};
+        rc = srt_last_timing(m->ctx[i], &t);
+        if (rc) return mfail(m, rc, "device %d: %s", m->dev[i], m->ctx[i]->error.c_str());
+        if (render_ms_per_device) render_ms_per_device[i] = t.render_ms;
+        float ms = 0.0f;
+        SRT_MCUDA(m, cudaEventElapsedTime(&ms, m->ev_start[i], m->ev_end[i]));
+        worst = std::max(worst, ms);
+    }
+    if (step_ms) *step_ms = worst;
     return SRT_OK;
 }
 
