@@ -399,7 +399,7 @@ def run_ours(args):
         tm = ctx.timing()
         kern_ms.append(tm.main_kernel_ms); pass_ms.append(tm.render_ms)
         render_launches = tm.launches              # dominant kernel + hit-list resolve (resp. bin pass)
-        z_slices = tm.z_slices
+        scan_cols = tm.scan_cols
     clocks = sampler.stop() if rank == 0 else None
     kernel_used = ctx.timing().kernel_used
     e2e_steps = max(1, min(steps, 10))
@@ -512,7 +512,7 @@ def run_ours(args):
         issue_peak = 4.0 * sms * sm_mhz * 1e6 / 1e9                      # G warp-instructions / s
         roof = {"bound": "issue", "unit": "Gwarp-inst/s", "peak": issue_peak,
                 "peak_source": f"4 issue slots x {sms} SMs x {sm_mhz:.0f} MHz (SM clock sampled under load)",
-                "kernel": kname, "kernel_ms": kt * 1e3, "pass_ms": float(np.mean(pass_ms)), "z_slices": int(z_slices),
+                "kernel": kname, "kernel_ms": kt * 1e3, "pass_ms": float(np.mean(pass_ms)), "scan_cols": int(scan_cols),
                 "tests_per_launch": band_tests, "exact_sequence_tests_per_launch": exact_counts.get("headline"),
                 "achieved": None, "frac": None, "traffic": None}
         if cnt:

@@ -113,8 +113,9 @@ typedef struct {
     uint32_t repair_depth;      /* 4 (lbuffer.cxx:339)                                                */
     uint32_t kernel;            /* srt_kernel                                                         */
     uint32_t flags;
-    uint32_t pixels_per_thread; /* 0 = auto; tuning knob of the filtered kernel: the box of pixels one thread tests per
-                                   triangle, box width | box height << 8 | boxes per thread << 16 (e.g. 0x020110)  */
+    uint32_t pixels_per_thread; /* 0 = auto; tuning knob of the filtered kernel: the box of pixels tested per triangle
+                                   and the triangles a thread holds, box width | box height << 8 | triangles << 16
+                                   (e.g. 0x040210 = 16 x 2 pixels, 4 triangles)                                  */
 } srt_params;
 
 typedef struct {
@@ -129,7 +130,7 @@ typedef struct {
     float    main_kernel_ms;    /* the dominant kernel of the last render alone: lbuffer_filtered_kernel /
                                    lbuffer_culled_kernel / lbuffer_exact_kernel (render_ms also covers the
                                    second kernel of the pass: hit-list resolve, resp. the bin pass)   */
-    uint32_t z_slices;          /* filtered kernel: triangle slices (grid.z) of the last render       */
+    uint32_t scan_cols;         /* filtered kernel: box columns per CTA of the last render            */
 } srt_timing;
 
 /* ---- context ------------------------------------------------------------ */
@@ -261,8 +262,8 @@ int  srt_debug_shaded_buffers(srt_ctx* ctx, float* z_out, int32_t* tri_id_out);
 int  srt_last_timing(srt_ctx* ctx, srt_timing* out);
 /* Diagnostic: make renders count the pairs that reach the exact path (costs one atomic per CTA). */
 int  srt_debug_count_exact(srt_ctx* ctx, int enable);
-/* Diagnostic: force the filtered kernel's triangle-range slice count (grid.z); 0 = heuristic. */
-int  srt_debug_force_splits(srt_ctx* ctx, int z_splits);
+/* Diagnostic: force the number of box columns a CTA of the filtered kernel covers (grid.x granularity); 0 = heuristic. */
+int  srt_debug_force_scan_cols(srt_ctx* ctx, int cols);
 /* Diagnostic: measured FP32 FMA throughput of the context's GPU in TFLOP/s. */
 int  srt_debug_ffma_peak(srt_ctx* ctx, int repeats, float* tflops_out);
 /* Diagnostic: padding granularity of packed meshes (triangles) and the default box of the filtered kernel. */

@@ -51,7 +51,7 @@ class Timing(C.Structure):
     _fields_ = [("render_ms", C.c_float), ("repair_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("pair_tests", C.c_uint64), ("exact_tests", C.c_uint64), ("filter_violations", C.c_uint64),
                 ("kernel_used", C.c_uint32), ("launches", C.c_uint32), ("main_kernel_ms", C.c_float),
-                ("z_slices", C.c_uint32)]
+                ("scan_cols", C.c_uint32)]
 
 
 # every symbol include/srt.h declares (tests/test_abi.py checks the .so exports all of them)
@@ -61,7 +61,7 @@ EXPORTS = [
     "srt_set_meshes", "srt_set_camera", "srt_render_lbuffer", "srt_render_lbuffer_device", "srt_repair",
     "srt_repair_device", "srt_render_xray", "srt_interleave_slot_rows",
     "srt_render_lbuffer_interleaved_device", "srt_deinterleave_device", "srt_render_lbuffer_blocks_device", "srt_render_shaded",
-    "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_force_splits", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_pack_info", "srt_debug_download_packed",
+    "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_force_scan_cols", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_pack_info", "srt_debug_download_packed",
     "srt_host_alloc", "srt_host_free",
     "srt_multi_create", "srt_multi_destroy", "srt_multi_last_error", "srt_multi_device_count", "srt_multi_set_meshes",
     "srt_multi_set_camera", "srt_multi_render_xray_device", "srt_multi_synchronize", "srt_multi_frame",
@@ -120,7 +120,7 @@ class Library:
         L.srt_render_xray.argtypes = [vp, C.POINTER(Params), vp]
         L.srt_last_timing.argtypes = [vp, C.POINTER(Timing)]
         L.srt_debug_count_exact.argtypes = [vp, i32]
-        L.srt_debug_force_splits.argtypes = [vp, i32]
+        L.srt_debug_force_scan_cols.argtypes = [vp, i32]
         L.srt_debug_download_packed.argtypes = [vp, i32, vp, vp, vp]
         L.srt_debug_pack_info.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
         L.srt_debug_ffma_peak.argtypes = [vp, i32, C.POINTER(C.c_float)]
@@ -240,9 +240,10 @@ class Library:
                     box=(bw, bh))
 
 
-def box_shape(px, py=1, nb=1):
-    """srt_params.pixels_per_thread encoding of a box shape of the filtered kernel."""
-    return px | (py << 8) | (nb << 16)
+def box_shape(px, py=1, k=0):
+    """srt_params.pixels_per_thread encoding of a shape of the filtered kernel: box of px x py pixels, k triangles per
+    thread (0 = default)."""
+    return px | (py << 8) | (k << 16)
 
 
 class Context:
@@ -288,8 +289,8 @@ class Context:
         self.cam = cam
         self._ck(self.lib.srt_set_camera(self.h, C.byref(cam)))
 
-    def force_splits(self, z):
-        self._ck(self.lib.srt_debug_force_splits(self.h, int(z)))
+    def force_scan_cols(self, cols):
+        self._ck(self.lib.srt_debug_force_scan_cols(self.h, int(cols)))
 
     def count_exact(self, on=True):
         self._ck(self.lib.srt_debug_count_exact(self.h, int(on)))

@@ -107,8 +107,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok;
@@ -251,70 +249,262 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 }
 
 // --------------------------------------------------------------- filtered kernel
-// Brute force over triangles: every thread visits every triangle of its slice, and every (pixel, triangle) pair is
-// decided either by a proven-conservative reject or by the reference's exact sequence.
+// Brute force: every triangle meets every box of pixels, and every (pixel, triangle) pair is decided either by a
+// proven-conservative reject or by the reference's exact sequence.  Four kernels:
 //
-// Mapping.  A thread owns NB boxes of PX x PY pixels side by side in a row band; lanes 4 x 8 -> warp footprint
-// (4 NB PX) x (8 PY) pixels; a CTA covers 16 image rows (the block-cyclic unit of the multi-GPU split).
-//
-// Level 0 (the hot loop).  The 48-byte level-0 records are streamed through a kStages-deep shared-memory ring of
-// kTileTris-triangle tiles with 1-D bulk copies (TMA) signalled on "full" mbarriers; a warp releases a stage by
-// arriving on its "empty" mbarrier (no __syncthreads in the loop).  Per (box, triangle): Y and D -- affine in the
-// pixel coordinates -- are evaluated at the box CENTRE and the box is rejected when |Y(c)| - |D(c)| > R, R being the
-// record's pre-packed bound r_Y + r_D + 2 m for this box size (filter proof item 7): 2 FFMA for the row
-// part (shared by the thread's boxes) + 2 FFMA + 1 FADD + 1 FSETP per box, votes once per group of kGroupTris
-// triangles, one iteration late so that the compare -> VOTE -> BRA chain never stalls the loop.
-//
-// Survivors (a strip of the triangle's level-0 test crosses the box; ~1 % of the box tests) are not processed where
-// they are found -- that would leave 31 lanes idle behind one.  They go through two per-warp queues in shared memory:
-//   Q1 {box, triangle}: appended by ballot in the loop; drained 32 entries at a time, one entry per lane: the
-//      full three-strip box test (the triangle's conservative footprint), then, for the few boxes that pass, the
-//      per-pixel three-strip tests with one lane per pixel of the box;
-//   Q2 {pixel, triangle}: the candidates of the exact test (1.005 x the true hits); drained with one candidate per
-//      lane: ray generation (both normalisations), Ray::intersect's exact sequence, sign test.
-// Accepted intersections are appended to the pixel's hit list through an atomic slot counter; the ordered float sum
-// of the reference is replayed by resolve_hits_kernel, which sorts each list by triangle index first -- so the
-// result does not depend on which lane, warp or z-slice found a hit, and it is bit-identical to the serial loop.
-constexpr uint32_t kQ2Cap = 96;
+// 1. lbuffer_filtered_kernel (the scan: > 90 % of the time).  Triangle-stationary: a thread holds the level-0 records of
+//    K triangles; a CTA (128 threads, 128 K triangles: "chunk" z of the mesh, a strided sample -- triangle
+//    (k 128 + t) n_chunks + z) walks the boxes of PX x PY pixels of its image region: the 16 / PY box rows of one 16-row
+//    block (the block-cyclic unit of the multi-GPU split) x a range of box columns.  Box centres are warp-uniform
+//    scalars computed from the loop counters, so the hot loop touches NO memory at all.
+//    (The first version of this round streamed triangle tiles through shared memory with each thread owning boxes: a
+//    broadcast LDS.128 still moves 512 B into the register file, 4 LSU cycles per warp, and the 3 loads per
+//    (warp, triangle) bounded that kernel at 12 cycles per warp-triangle -- measured 13.7 -- with the issue slots half
+//    idle: profiles/r02_sweep_tile_streaming_*.txt.)
+//    Per (box, triangle): Y, Y2 (two of the triangle's three strips) and D are affine in the pixel coordinates; they are
+//    evaluated at the box CENTRE and the box is rejected when |Y(c)| - |D(c)| > R or |Y2(c)| - |D(c)| > R2, R being the
+//    record's pre-packed bound r_Y + r_D + 2 m for this box size (filter proof item 7).  One strip is an
+//    infinite band across the image; two strips intersect in a parallelogram around the triangle, so survivors are rare
+//    (3e-4 of the box tests at 2048^2).  3 FFMA + 2 FADD + 2 FSETP per test, one vote per two boxes.
+//    Survivors {box, triangle} are staged in a per-warp shared-memory buffer and appended, 128 at a time, to a global
+//    candidate list (one atomic per flush).  Nothing latency-bound runs in this kernel: when the exact tests ran here
+//    too (a warp draining its own queue), the dependent L2 round trips of ~100 000 drain passes held warp slots for
+//    0.5 ms of a 1.4 ms frame and, worse, 0.2 ms of every 0.33 ms share of an 8-GPU frame
+//    (profiles/r02_sweep_scan_inline_drains.txt).
+// 2. candidates_kernel, one list entry per thread: the full three-strip box test (the triangle's conservative
+//    footprint), then the per-pixel three-strip tests over the pixels of the box; the surviving {pixel, triangle} pairs
+//    (1.005 x the true hits) go to a second global list.
+// 3. exact_tests_kernel, one pair per thread: ray generation with both normalisations, Ray::intersect's exact
+//    sequence, sign test; accepted intersections are appended to the pixel's hit list through an atomic slot counter.
+//    (2 and 3 are latency-bound chains of dependent L2 accesses: one item per thread and tens of thousands of threads
+//    in flight hide what a per-warp queue inside the scan kernel could not.)
+// 4. resolve_hits_kernel: sorts each pixel's list by triangle index and replays the reference's ordered float sum --
+//    so the result does not depend on which thread or chunk found a hit: bit-identical to the serial loop.
+// If a candidate list overflows (adversarial scenes; the host grows it for the next frame), resolve recomputes every
+// pixel with the exact sequence: slow, never wrong.
+constexpr uint32_t kStageCap = 256, kStageFlush = 128;
 
-template <int PX, int PY, int NB>
-struct BoxGeom {
-    static_assert(PY == 1 || PY == 2, "a CTA covers one 16-row block");
-    static_assert(PX * PY <= 32, "the per-pixel stage maps one lane to one pixel of a box");
-    static_assert(NB >= 1 && NB <= 4, "box index is 7 bits");
-    static constexpr uint32_t kWarpW = 4 * NB * PX, kWarpH = 8 * PY;
-    static constexpr uint32_t kWarpsY = 16 / kWarpH, kWarpsX = 4 / kWarpsY;
-    static constexpr uint32_t kCtaW = kWarpsX * kWarpW;
-    static constexpr uint32_t kQ1Cap = 32 * NB + 96;         // room for one triangle's survivors above the drain level
+// candidate entry: x = box row j (4 bits) | 16-row block of the launch (14) | box column i (14), y = triangle (27) | mesh (5)
+__device__ __forceinline__ uint2 cand_pack(uint32_t j, uint32_t block, uint32_t i, uint32_t tri, uint32_t mesh)
+{ return make_uint2(j | (block << 4) | (i << 18), tri | (mesh << 27)); }
+
+#ifndef SRT_MIN_CTAS
+#define SRT_MIN_CTAS 4
+#endif
+
+template <int PX, int PY, int K>
+struct ScanGeom {
+    static_assert(16 % PY == 0 && PX * PY <= 64 && PX <= 32, "box rows tile a 16-row block; the per-entry pixel mask is 64 bits");
+    static constexpr uint32_t kBoxRows = 16 / PY;
+    static constexpr size_t kSmem = (size_t)K * 3 * 128 * sizeof(float4) + 16 + 4 * kStageCap * sizeof(uint2);
 };
 
-struct WarpCtx {                  // per warp, in shared memory: everything only the (rare) queue paths touch
-    const float4* filt0; const float4* filt1; const float4* exact;     // current mesh
-    uint32_t n_tris, first;       // triangles in the mesh; scene-wide index of its first triangle
-    uint32_t wrow0, wcol0;        // first image row / column of the warp's footprint
-    uint32_t orow0;               // output row of wrow0 (slot-local when compact)
-    uint32_t n1, n2;              // fill levels of the queues
-    uint32_t* q1; uint2* q2;
-    uint8_t q0[kTileTris / kGroupTris];   // first triangle (within the tile) of the groups of the current tile that have survivors
-};
-static_assert(kTileTris <= 256, "q0 entries are bytes");
-
-// Q2 -> exact tests, one candidate per lane
-template <int PX, int PY, int NB>
-__device__ __noinline__ void drain_q2(const RenderArgs& a, WarpCtx* w)
+template <int PX, int PY, int K>
+__global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(const __grid_constant__ RenderArgs a)
 {
-    const uint32_t lane = threadIdx.x & 31u;
-    __syncwarp();
-    const uint32_t n2 = w->n2;
-    const float4* exact = w->exact;
-    for (uint32_t e = lane; e < n2; e += 32) {
-        const uint2 ent = w->q2[e];
-        const uint32_t tri = ent.y, k = ent.x & 31u, bi = ent.x >> 5, bl = bi / NB, b = bi - bl * NB;
-        const uint32_t col = w->wcol0 + ((bl & 3u) * NB + b) * PX + k % PX;
-        const uint32_t dr = (bl >> 2) * PY + k / PX;
-        const RayDirs r = make_ray(a.cam, w->wrow0 + dr, col);
-        const float4 A = __ldg(exact + 4 * (size_t)tri), B = __ldg(exact + 4 * (size_t)tri + 1);
-        const float4 C = __ldg(exact + 4 * (size_t)tri + 2), Dn = __ldg(exact + 4 * (size_t)tri + 3);
+    using G = ScanGeom<PX, PY, K>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* recs = reinterpret_cast<float4*>(smem_raw);                        // [K][3][128]: the CTA's chunk, SoA
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)K * 3 * 128 * sizeof(float4));
+    uint2* stage = reinterpret_cast<uint2*>(bar + 2) + (threadIdx.x >> 5) * kStageCap;       // this warp's survivors
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const CtaCoord cta = cta_coord();
+    const uint32_t W = a.cam.W;
+    const uint32_t row0 = a.row_begin + (cta.y * a.blk_stride + a.blk_phase) * 16;          // the CTA's 16-row block
+    const uint32_t n_cols = (W + PX - 1) / PX;                                               // box columns of the frame
+    const uint32_t c_begin = cta.x * a.scan_cols, c_end = min(n_cols, c_begin + a.scan_cols);
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    uint32_t phase = 0, n1 = 0;              // n1: survivors staged by this warp (warp-uniform)
+    const float x_first = 0.5f * (float)(PX - 1) + a.cam.xc;                                 // centre of box column 0
+
+    // append the warp's staged survivors to the global candidate list: one atomic, coalesced 8-byte stores
+    auto flush = [&]() {
+        __syncwarp();
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.cand_count, n1);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t e = lane; e < n1; e += 32)
+            if (base + e < a.cand_cap) a.cand[base + e] = stage[e];                         // overflow: resolve falls back to the exact sequence
+        __syncwarp();
+        n1 = 0;
+    };
+
+    for (int m = 0; m < a.n_meshes; ++m) {
+        const DevMesh* Mp = a.meshes + m;
+        const uint32_t n_chunks = Mp->n_chunks;
+        if (!Mp->contributes || Mp->n == 0 || cta.z >= n_chunks) continue;                   // CTA-uniform
+        // the CTA's chunk of level-0 records: one bulk copy (TMA) into shared memory, then K records per thread into
+        // registers per box row (SoA in the chunk: consecutive lanes read consecutive float4)
+        __syncthreads();                                                                     // recs of the previous mesh are consumed
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)(K * 3 * 128 * sizeof(float4)));
+            bulk_g2s(recs, Mp->scan + (size_t)cta.z * K * 3 * 128, (uint32_t)(K * 3 * 128 * sizeof(float4)), bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+#pragma unroll 1
+        for (uint32_t j = 0; j < G::kBoxRows; ++j) {
+            const uint32_t br0 = row0 + j * PY;
+            if (br0 >= a.row_end) break;
+            const uint32_t br1 = min(a.row_end, br0 + PY) - 1;                                // boxes are clamped to the frame
+            const float yc = 0.5f * (float)(br0 + br1) + a.cam.yc;
+            // The thread's K records are re-read from shared memory at every box row (12 LDS per ~100 boxes) instead of
+            // being held across rows: the inner loop then lives on 8 values per triangle -- x slopes and bounds, and the
+            // row parts of Y, Y2, D folded with yc.
+            float bx[K], bd[K], R[K], bx2[K], R2[K], by[K], dy[K], by2[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float4 fa = recs[(k * 3 + 0) * 128 + tid], fb = recs[(k * 3 + 1) * 128 + tid], fc = recs[(k * 3 + 2) * 128 + tid];
+                bx[k] = fa.x; bd[k] = fa.w; R[k] = fb.w; bx2[k] = fc.x; R2[k] = fc.w;
+                by[k] = fmaf(fa.y, yc, fa.z); dy[k] = fmaf(fb.x, yc, fb.y); by2[k] = fmaf(fc.y, yc, fc.z);
+            }
+            // level-0 test of the thread's K triangles against the box with centre xc: may any of them touch it?
+            auto scan = [&](float xc) {
+                bool surv = false;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float D = fabsf(fmaf(bd[k], xc, dy[k]));
+                    const float Y = fmaf(bx[k], xc, by[k]), Y2 = fmaf(bx2[k], xc, by2[k]);
+                    const bool r1 = fabsf(Y) - D > R[k], r2 = fabsf(Y2) - D > R2[k];          // NaN survives
+                    surv |= !(r1 | r2);                                                      // bitwise: no short-circuit branches
+                }
+                return surv;
+            };
+            // stage the survivors of box (j, i) -- rare: one ballot per k.  The tests are re-evaluated on an opaque copy
+            // of xc so that the compiler does not carry the K predicates of every box through the hot loop.
+            auto push = [&](uint32_t i, float xc) {
+                asm volatile("" : "+f"(xc));
+                if (n1 + 32 * K > kStageCap) flush();
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float D = fabsf(fmaf(bd[k], xc, dy[k]));
+                    const float Y = fmaf(bx[k], xc, by[k]), Y2 = fmaf(bx2[k], xc, by2[k]);
+                    const bool sv = !((fabsf(Y) - D > R[k]) | (fabsf(Y2) - D > R2[k]));
+                    const unsigned bal = __ballot_sync(0xffffffffu, sv);
+                    if (sv) stage[n1 + __popc(bal & ((1u << lane) - 1u))] =
+                        cand_pack(j, cta.y, i, ((uint32_t)k * 128 + tid) * n_chunks + cta.z, (uint32_t)m);
+                    n1 += __popc(bal);
+                }
+                if (n1 >= kStageFlush) flush();
+            };
+            // full boxes: the centre advances by PX (exact in binary32: half-integers far below 2^23)
+            const uint32_t c_full = min(c_end, W / PX);
+            float xc = fmaf((float)c_begin, (float)PX, x_first);
+            // two boxes per vote: 2 K independent chains per warp, half the vote / branch overhead
+            uint32_t i = c_begin;
+#pragma unroll 1
+            for (; i + 1 < c_full; i += 2, xc += (float)(2 * PX)) {
+                const float xd = xc + (float)PX;
+                const bool s0 = scan(xc), s1 = scan(xd);
+                if (__any_sync(0xffffffffu, s0 | s1)) {
+                    if (__any_sync(0xffffffffu, s0)) push(i, xc);
+                    if (__any_sync(0xffffffffu, s1)) push(i + 1, xd);
+                }
+            }
+            if (i < c_full && __any_sync(0xffffffffu, scan(xc))) push(i, xc);
+            if (c_full < c_end) {                               // the last box of the row is clamped to the frame
+                const float xl = 0.5f * (float)(c_full * PX + W - 1) + a.cam.xc;
+                if (__any_sync(0xffffffffu, scan(xl))) push(c_full, xl);
+            }
+        }
+    }
+    if (n1) flush();
+}
+
+// ------------------------------------------------------------------ candidates kernel
+// image row -> output row (slot-local when the launch is compact)
+__device__ __forceinline__ uint32_t out_row(const RenderArgs& a, uint32_t row)
+{
+    if (!a.compact) return row;
+    const uint32_t rel = row - a.row_begin;
+    return ((rel >> 4) - a.blk_phase) / a.blk_stride * 16 + (rel & 15u);
+}
+
+// Stage 2 of the filtered path, one list entry {box, triangle} per thread (grid-stride): records from L2, the
+// three-strip box test (the triangle's conservative footprint), then the per-pixel three-strip tests over the pixels
+// of the box with the records in registers.  The surviving {pixel, triangle} pairs -- the candidates of the exact test,
+// 1.005 x the true hits -- are appended to a second global list (one atomic per warp).
+template <int PX, int PY>
+__global__ void __launch_bounds__(128) candidates_kernel(const __grid_constant__ RenderArgs a)
+{
+    static_assert(PX * PY <= 64, "the per-entry pixel mask is 64 bits");
+    const uint32_t lane = threadIdx.x & 31u, W = a.cam.W;
+    const uint32_t n = min(a.cand_count[0], a.cand_cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {      // warp-uniform trip count
+        const uint32_t e = base + lane;
+        unsigned long long mask = 0;
+        uint32_t tm = 0, row0 = 0, col0 = 0;
+        if (e < n) {
+            const uint2 ent = a.cand[e];
+            const uint32_t box_x = ent.x;
+            tm = ent.y;
+            const uint32_t tri = tm & 0x7ffffffu;
+            const DevMesh* Mp = a.meshes + (tm >> 27);
+            row0 = a.row_begin + ((((box_x >> 4) & 0x3fffu) * a.blk_stride + a.blk_phase) * 16) + (box_x & 15u) * PY;
+            col0 = (box_x >> 18) * PX;
+            const uint32_t c1 = min(W, col0 + PX) - 1, r1 = min(a.row_end, row0 + PY) - 1;      // listed boxes hold pixels
+            const float4* f0 = Mp->filt0 + 3 * (size_t)tri; const float4* f1 = Mp->filt1 + 2 * (size_t)tri;
+            const float4 fa = __ldg(f0), fb = __ldg(f0 + 1), ga = __ldg(f1), gb = __ldg(f1 + 1);
+            if (box_may_hit(fa, fb, ga, gb, 0.5f * (float)(col0 + c1) + a.cam.xc, 0.5f * (float)(row0 + r1) + a.cam.yc,
+                            0.5f * (float)(c1 - col0), 0.5f * (float)(r1 - row0))) {
+                const float x0 = (float)col0 + a.cam.xc;
+#pragma unroll
+                for (int ky = 0; ky < PY; ++ky) {
+                    const float y = (float)(row0 + ky) + a.cam.yc;
+                    const float bd = fmaf(fb.x, y, fb.y), b1 = fmaf(fa.y, y, fa.z), b2 = fmaf(ga.y, y, ga.z), b3 = fmaf(gb.y, y, gb.z);
+                    unsigned rowmask = 0;
+#pragma unroll
+                    for (int kx = 0; kx < PX; ++kx) {
+                        const float x = x0 + (float)kx;                                 // exact: (half-)integers far below 2^23
+                        const float Dd = fabsf(fmaf(fa.w, x, bd));
+                        const float Y1 = fmaf(fa.x, x, b1), Y2 = fmaf(ga.x, x, b2), Y3 = fmaf(gb.x, x, b3);
+                        const bool rej = (fabsf(Y1) > Dd + fb.z) | (fabsf(Y2) > Dd + ga.w) | (fabsf(Y3) > Dd + gb.w);   // NaN survives
+                        rowmask |= rej ? 0u : (1u << kx);
+                    }
+                    if (col0 + PX > W) rowmask &= (1u << (W - col0)) - 1u;              // pixels beyond the last column
+                    if (row0 + ky < a.row_end) mask |= (unsigned long long)rowmask << (ky * PX);
+                }
+            }
+        }
+        // append the warp's candidates: one atomic, each lane writes its own pixels
+        const uint32_t mine = (uint32_t)__popcll(mask);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += u; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        uint32_t at = 0;
+        if (lane == 31) at = atomicAdd(a.cand_count + 1, total);
+        at = __shfl_sync(0xffffffffu, at, 31) + incl - mine;
+        while (mask) {
+            const uint32_t k = (uint32_t)__ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            if (at < a.pix_cap) a.pix[at] = make_uint2((row0 + k / PX) * W + col0 + k % PX, tm);   // overflow: resolve falls back
+            ++at;
+        }
+    }
+}
+
+// Stage 3, one candidate {pixel, triangle} per thread (grid-stride): ray generation with both normalisations,
+// Ray::intersect's exact sequence, sign test; accepted intersections are appended to the pixel's hit list through an
+// atomic slot counter.
+__global__ void __launch_bounds__(128) exact_tests_kernel(const __grid_constant__ RenderArgs a)
+{
+    const uint32_t W = a.cam.W;
+    const uint32_t n = min(a.cand_count[1], a.pix_cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    if (a.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.counters, (unsigned long long)n);   // pairs that run the exact sequence
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const uint2 ent = a.pix[e];
+        const uint32_t tri = ent.y & 0x7ffffffu;
+        const DevMesh* Mp = a.meshes + (ent.y >> 27);
+        const float4* exact = Mp->exact + 4 * (size_t)tri;
+        const float4 A = __ldg(exact), B = __ldg(exact + 1), C = __ldg(exact + 2), Dn = __ldg(exact + 3);
+        const uint32_t row = ent.x / W, col = ent.x - row * W;
+        const RayDirs r = make_ray(a.cam, row, col);
         float tt;
         if (!exact_intersect(r, A, B, C, Dn.x, tt)) continue;
         float val = tt;                                                   // mode 1: z-buffer candidate (any sign of t)
@@ -323,276 +513,9 @@ __device__ __noinline__ void drain_q2(const RenderArgs& a, WarpCtx* w)
             const float dn = dot_rn(r.ax, r.ay, r.az, Dn.y, Dn.z, Dn.w);   // direction . normal, pre-Ray direction
             val = __fmul_rn((float)((0.0f < dn) - (dn < 0.0f)), tt);       // sign * t
         }
-        const size_t p = (size_t)(w->orow0 + dr) * a.cam.W + col;
+        const size_t p = (size_t)out_row(a, row) * W + col;
         const uint32_t slot = atomicAdd(a.hit_counts + p, 1u);
-        if (slot < a.hit_cap) a.hit_entries[p * a.hit_cap + slot] = make_uint2(w->first + tri, __float_as_uint(val));
-    }
-    if (a.counters && lane == 0 && n2) atomicAdd(a.counters, (unsigned long long)n2);
-    __syncwarp();
-    if (lane == 0) w->n2 = 0;
-    __syncwarp();
-}
-
-// Q1 -> three-strip box test per entry, per-pixel tests for the boxes that pass, candidates into Q2
-template <int PX, int PY, int NB>
-__device__ __noinline__ void drain_q1(const RenderArgs& a, WarpCtx* w)
-{
-    const uint32_t lane = threadIdx.x & 31u, W = a.cam.W;
-    __syncwarp();
-    const uint32_t n1 = w->n1;
-    uint32_t n2 = w->n2;
-    const float4* filt0 = w->filt0; const float4* filt1 = w->filt1;
-    for (uint32_t base = 0; base < n1; base += 32) {
-        const uint32_t e = base + lane;
-        uint32_t tri = 0, bi = 0, col0 = 0, row0 = 0;
-        bool pass = false;
-        if (e < n1) {
-            const uint32_t ent = w->q1[e];
-            tri = ent >> 7; bi = ent & 127u;
-            const uint32_t bl = bi / NB, b = bi - bl * NB;
-            col0 = w->wcol0 + ((bl & 3u) * NB + b) * PX; row0 = w->wrow0 + (bl >> 2) * PY;
-            const uint32_t c1 = min(W, col0 + PX) - 1, r1 = min(a.row_end, row0 + PY) - 1;      // queued boxes hold pixels
-            const float4 fa = __ldg(filt0 + 3 * (size_t)tri), fb = __ldg(filt0 + 3 * (size_t)tri + 1);
-            const float4 ga = __ldg(filt1 + 2 * (size_t)tri), gb = __ldg(filt1 + 2 * (size_t)tri + 1);
-            pass = box_may_hit(fa, fb, ga, gb, 0.5f * (float)(col0 + c1) + a.cam.xc, 0.5f * (float)(row0 + r1) + a.cam.yc,
-                               0.5f * (float)(c1 - col0), 0.5f * (float)(r1 - row0));
-        }
-        unsigned pm = __ballot_sync(0xffffffffu, pass);
-        while (pm) {                                                       // warp-uniform: one passing box at a time
-            const int src = __ffs(pm) - 1;
-            pm &= pm - 1;
-            const uint32_t s_tri = __shfl_sync(0xffffffffu, tri, src), s_bi = __shfl_sync(0xffffffffu, bi, src);
-            const uint32_t s_col0 = __shfl_sync(0xffffffffu, col0, src), s_row0 = __shfl_sync(0xffffffffu, row0, src);
-            const uint32_t col = s_col0 + lane % PX, row = s_row0 + lane / PX;             // one lane per pixel of the box
-            bool cand = false;
-            if (lane < PX * PY && col < W && row < a.row_end) {
-                const float4 fa = __ldg(filt0 + 3 * (size_t)s_tri), fb = __ldg(filt0 + 3 * (size_t)s_tri + 1);   // L1 hits
-                const float4 ga = __ldg(filt1 + 2 * (size_t)s_tri), gb = __ldg(filt1 + 2 * (size_t)s_tri + 1);
-                const float x = (float)col + a.cam.xc, y = (float)row + a.cam.yc;
-                const float Dd = fabsf(fmaf(fa.w, x, fmaf(fb.x, y, fb.y)));
-                const float Y1 = fmaf(fa.x, x, fmaf(fa.y, y, fa.z)), Y2 = fmaf(ga.x, x, fmaf(ga.y, y, ga.z));
-                const float Y3 = fmaf(gb.x, x, fmaf(gb.y, y, gb.z));
-                cand = !((fabsf(Y1) > Dd + fb.z) || (fabsf(Y2) > Dd + ga.w) || (fabsf(Y3) > Dd + gb.w));   // NaN survives
-            }
-            const unsigned cm = __ballot_sync(0xffffffffu, cand);
-            if (cm == 0) continue;
-            const uint32_t nc = __popc(cm);
-            if (n2 + nc > kQ2Cap) {
-                if (lane == 0) w->n2 = n2;
-                drain_q2<PX, PY, NB>(a, w);
-                n2 = 0;
-            }
-            if (cand) w->q2[n2 + __popc(cm & ((1u << lane) - 1u))] = make_uint2((s_bi << 5) | lane, s_tri);
-            n2 += nc;
-        }
-    }
-    __syncwarp();
-    if (lane == 0) { w->n1 = 0; w->n2 = n2; }
-    __syncwarp();
-}
-
-template <int NB> struct BoxX { float v[NB]; };
-
-// Queue the survivors of one vote group (records at `tp`, first triangle jj): re-evaluates the group's box tests per
-// box.  Out of line and fed from shared memory so that the hot loop keeps none of this state in registers.
-template <int PX, int PY, int NB>
-__device__ __noinline__ void push_group(const RenderArgs& a, WarpCtx* w, const float4* tp, uint32_t jj, float yc,
-                                        BoxX<NB> xc, uint32_t alive)
-{
-    using G = BoxGeom<PX, PY, NB>;
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t n1 = w->n1;
-    const uint32_t n_tris = w->n_tris;
-#pragma unroll 1
-    for (uint32_t g = 0; g < kGroupTris; ++g) {
-        const float4 fa = tp[3 * g], fb = tp[3 * g + 1], fc = tp[3 * g + 2];
-        const float by = fmaf(fa.y, yc, fa.z), dy = fmaf(fb.x, yc, fb.y), by2 = fmaf(fc.y, yc, fc.z);
-        uint32_t mine = 0;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const float D = fabsf(fmaf(fa.w, xc.v[b], dy));
-            const float Y = fmaf(fa.x, xc.v[b], by), Y2 = fmaf(fc.x, xc.v[b], by2);
-            if (!((fabsf(Y) - D > fb.w) || (fabsf(Y2) - D > fc.w))) mine |= 1u << b;
-        }
-        mine &= alive;
-        if (jj + g >= n_tris) mine = 0;                                    // padding entry
-        if (!__any_sync(0xffffffffu, mine != 0)) continue;
-        if (n1 + 32 * NB > G::kQ1Cap) {
-            if (lane == 0) w->n1 = n1;
-            drain_q1<PX, PY, NB>(a, w);
-            n1 = 0;
-        }
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const unsigned bal = __ballot_sync(0xffffffffu, (mine >> b) & 1u);
-            if ((mine >> b) & 1u) w->q1[n1 + __popc(bal & ((1u << lane) - 1u))] = ((jj + g) << 7) | (lane * NB + b);
-            n1 += __popc(bal);
-        }
-    }
-    __syncwarp();
-    if (lane == 0) w->n1 = n1;
-    __syncwarp();
-}
-
-#ifndef SRT_GROUP_UNROLL
-#define SRT_GROUP_UNROLL 1
-#endif
-constexpr int kGroupUnroll = SRT_GROUP_UNROLL;   // groups per trip of the hot loop
-
-__device__ __forceinline__ float4 lds128(uint32_t addr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-
-// THE HOT LOOP: level-0 box tests of one thread's NB boxes against the `cnt` triangles of one shared-memory tile.
-// Its own function (own register allocation: the surrounding pipeline code and the queue paths made ptxas spill the
-// loop's three live values at 64 registers); called once per tile.  The groups in which some lane has a survivor are
-// only noted here -- one byte per group in q0, warp-uniform -- and queued by the caller.  The vote on a group is
-// taken one iteration late (its predicate has been ready for a whole iteration: no compare -> VOTE -> BRA stall).
-// Returns the number of groups noted.
-template <int NB>
-__device__ __noinline__ uint32_t scan_tile(uint32_t tile, uint32_t cnt, float yc, BoxX<NB> xc, uint32_t q0)
-{
-    bool pend = false;             // may the previous group have a survivor in this lane?
-    uint32_t n0 = 0;
-#pragma unroll(kGroupUnroll)
-    for (uint32_t j = 0; j < cnt; j += kGroupTris) {
-        bool surv = false;
-#pragma unroll
-        for (uint32_t g = 0; g < kGroupTris; ++g) {
-            const float4 fa = lds128(tile + 48 * (j + g)), fb = lds128(tile + 48 * (j + g) + 16), fc = lds128(tile + 48 * (j + g) + 32);
-            const float by = fmaf(fa.y, yc, fa.z), dy = fmaf(fb.x, yc, fb.y), by2 = fmaf(fc.y, yc, fc.z);
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const float D = fabsf(fmaf(fa.w, xc.v[b], dy));
-                const float Y = fmaf(fa.x, xc.v[b], by), Y2 = fmaf(fc.x, xc.v[b], by2);
-                const bool r1 = fabsf(Y) - D > fb.w, r2 = fabsf(Y2) - D > fc.w;            // NaN survives
-                surv |= !(r1 | r2);                                              // bitwise: no short-circuit branches
-            }
-        }
-        if (__any_sync(0xffffffffu, pend)) {                            // the PREVIOUS group
-            asm volatile("st.shared.u8 [%0], %1;" ::"r"(q0 + n0), "r"(j - kGroupTris) : "memory");
-            ++n0;
-        }
-        pend = surv;
-    }
-    if (__any_sync(0xffffffffu, pend)) {
-        asm volatile("st.shared.u8 [%0], %1;" ::"r"(q0 + n0), "r"(cnt - kGroupTris) : "memory");
-        ++n0;
-    }
-    return n0;
-}
-
-#ifndef SRT_MIN_CTAS
-#define SRT_MIN_CTAS 8
-#endif
-template <int PX, int PY, int NB>
-__global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(const __grid_constant__ RenderArgs a)
-{
-    using G = BoxGeom<PX, PY, NB>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* tiles = reinterpret_cast<float4*>(smem_raw);                       // kStages x kTileTris x 3 float4
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileTris * 48);
-    uint64_t* empty = full + kStages;
-    WarpCtx* wctx = reinterpret_cast<WarpCtx*>(empty + kStages);
-    uint2* q2_all = reinterpret_cast<uint2*>(wctx + 4);
-    uint32_t* q1_all = reinterpret_cast<uint32_t*>(q2_all + 4 * kQ2Cap);
-
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const CtaCoord cta = cta_coord();
-    const uint32_t W = a.cam.W;
-    WarpCtx* w = wctx + warp;
-    float yc; BoxX<NB> xc; uint32_t alive = 0;
-    {
-        const uint32_t row0 = a.row_begin + (cta.y * a.blk_stride + a.blk_phase) * 16;      // the CTA's 16-row block
-        const uint32_t wrow0 = row0 + (warp / G::kWarpsX) * G::kWarpH;
-        const uint32_t wcol0 = cta.x * G::kCtaW + (warp % G::kWarpsX) * G::kWarpW;
-        const uint32_t trow0 = wrow0 + (lane >> 2) * PY;                                     // this thread's boxes
-        const uint32_t tcol0 = wcol0 + (lane & 3u) * NB * PX;
-        // Box centres.  Boxes are clamped to the frame (the proof needs the centre inside it); a box without pixels is
-        // evaluated at a clamped position as well and masked out when survivors are queued.
-        const uint32_t last_row = a.row_end - 1;
-        const uint32_t r0c = min(trow0, last_row), r1c = min(trow0 + PY - 1, last_row);
-        yc = 0.5f * (float)(r0c + r1c) + a.cam.yc;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const uint32_t c0 = tcol0 + b * PX;
-            const uint32_t c0c = min(c0, W - 1), c1c = min(c0 + PX - 1, W - 1);
-            xc.v[b] = 0.5f * (float)(c0c + c1c) + a.cam.xc;
-            if (c0 < W && trow0 < a.row_end) alive |= 1u << b;
-        }
-        if (lane == 0) {
-            w->wrow0 = wrow0; w->wcol0 = wcol0; w->orow0 = a.compact ? cta.y * 16 + (wrow0 - row0) : wrow0;
-            w->n1 = 0; w->n2 = 0;
-            w->q1 = q1_all + warp * G::kQ1Cap; w->q2 = q2_all + warp * kQ2Cap;
-        }
-    }
-    if (tid == 0) {
-#pragma unroll
-        for (uint32_t s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    uint32_t issued = 0, consumed = 0;     // tiles issued / consumed by this CTA over all meshes (uniform)
-
-    for (int m = 0; m < a.n_meshes; ++m) {
-        const DevMesh* Mp = a.meshes + m;
-        const uint32_t n_padded = Mp->n_padded;
-        if (!Mp->contributes || Mp->n == 0) continue;
-        const float4* filt0 = Mp->filt0;
-        if (lane == 0) { w->filt0 = filt0; w->filt1 = Mp->filt1; w->exact = Mp->exact; w->n_tris = Mp->n; w->first = Mp->first; }
-        __syncwarp();
-
-        // Slice z of z_splits streams tiles z, z + z_splits, ...: interleaved, because consecutive triangles of a mesh lie
-        // next to each other in the image -- a contiguous range would hand all the queue work (exact tests) of an image
-        // region to the one CTA whose pixels AND triangles are there, and the launch would wait for it.
-        const uint32_t all_tiles = (n_padded + kTileTris - 1) / kTileTris;
-        const uint32_t t_first = cta.z, t_step = a.z_splits;
-        const uint32_t t_end = all_tiles;
-        // producer side: wait until every warp released the stage, then one thread refills it
-        auto issue = [&](uint32_t t) {
-            const uint32_t stage = issued % kStages;
-            const uint32_t cnt = min(kTileTris, n_padded - t * kTileTris);
-            // every thread waits (uniform control flow: a spin loop under `if (tid == 0)` would make the compiler treat
-            // the rest of the tile loop as divergent); the wait is for the tile consumed kStages - 1 tiles ago, so it
-            // only blocks a warp that ran a whole tile ahead of the slowest warp of the CTA
-            mbar_wait(&empty[stage], ((issued / kStages) & 1u) ^ 1u);           // first use passes immediately
-            if (tid == 0) {
-                mbar_expect_tx(&full[stage], cnt * 48u);
-                bulk_g2s(tiles + (size_t)stage * kTileTris * 3, filt0 + (size_t)t * kTileTris * 3, cnt * 48u, &full[stage]);
-            }
-            ++issued;
-        };
-
-        for (uint32_t i = 0, t = t_first; i < kStages - 1 && t < t_end; ++i, t += t_step) issue(t);
-        for (uint32_t t = t_first; t < t_end; t += t_step) {
-            __syncwarp();          // re-converge after the single-lane producer / release code
-            const uint32_t stage = consumed % kStages;
-            mbar_wait(&full[stage], (consumed / kStages) & 1u);
-            const float4* tp = tiles + (size_t)stage * kTileTris * 3;
-            const uint32_t cnt = min(kTileTris, n_padded - t * kTileTris);      // multiple of kGroupTris
-            const uint32_t jbase = t * kTileTris;
-
-            const uint32_t n0 = scan_tile<NB>(smem_u32(tp), cnt, yc, xc, smem_u32(w->q0));
-            if (n0) {                      // while the tile's records are still in shared memory
-                __syncwarp();
-                for (uint32_t i = 0; i < n0; ++i) {
-                    const uint32_t jg = w->q0[i];
-                    push_group<PX, PY, NB>(a, w, tp + 3 * jg, jbase + jg, yc, xc, alive);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);        // this warp is done with the stage
-            ++consumed;
-            if (t + (kStages - 1) * t_step < t_end) issue(t + (kStages - 1) * t_step);
-        }
-        // the queues hold mesh-local triangle indices: empty them before the next mesh
-        __syncwarp();
-        if (w->n1) drain_q1<PX, PY, NB>(a, w);
-        if (w->n2) drain_q2<PX, PY, NB>(a, w);
+        if (slot < a.hit_cap) a.hit_entries[p * a.hit_cap + slot] = make_uint2(Mp->first + tri, __float_as_uint(val));
     }
 }
 
@@ -615,11 +538,12 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
     float L = a.incident;
     float dist0 = 0.0f; int ssum0 = 0; uint32_t hits0 = 0;   // mode 1: z-buffer value / triangle index
     if (a.mode != 0) { dist0 = INFINITY; ssum0 = -1; }
+    const bool list_lost = a.cand_count[0] > a.cand_cap || a.cand_count[1] > a.pix_cap;   // a candidate list overflowed: no hit list can be trusted
     bool overflow = false;
     if (valid) {
         const uint32_t n = a.hit_counts[p];
         if (n) a.hit_counts[p] = 0;                          // ready for the next render
-        overflow = n > a.hit_cap;
+        overflow = n > a.hit_cap || list_lost;
         if (n && !overflow) {
             uint2 e[kMaxHitCap];
             const uint2* src = a.hit_entries + p * a.hit_cap;
@@ -1253,15 +1177,18 @@ __global__ void __launch_bounds__(256) repair_kernel(const float* __restrict__ L
 }
 
 // ------------------------------------------------------------------ scene pre-pack
-// One thread per triangle.  Exact constants use round-to-nearest intrinsics (prepack_math.h); the filter
-// coefficients / margins are double precision.
+// One thread per slot of the chunk-major scan array (>= the padded triangle count).  Exact constants use
+// round-to-nearest intrinsics (prepack_math.h); the filter coefficients / margins are double precision.  The level-0
+// record is written twice: in natural triangle order (filt0: queue stages, bin pass, culled kernel) and into the
+// chunk-major SoA array the filtered kernel bulk-copies: slot i = (k 128 + t) n_chunks + c  ->  scan[c][k][j][t].
 __global__ void __launch_bounds__(128) prepack_kernel(const float* __restrict__ vertices, const float* __restrict__ normals,
-                                                      uint32_t n, uint32_t n_padded, float ox, float oy, float oz,
+                                                      uint32_t n, uint32_t n_padded, uint32_t n_chunks, uint32_t scan_k,
+                                                      float ox, float oy, float oz,
                                                       const __grid_constant__ FrameGeom g, ExactTri* exact,
-                                                      float4* filt0, float4* filt1)
+                                                      float4* filt0, float4* filt1, float4* scan)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_padded) return;
+    if (i >= n_chunks * scan_k * 128) return;
     FilterTri f; FilterTri2 f2;
     if (i < n) {
         float v[9];
@@ -1276,9 +1203,14 @@ __global__ void __launch_bounds__(128) prepack_kernel(const float* __restrict__ 
         eo[0] = make_float4(E.e2x, E.e2y, E.e2z, E.e1x); eo[1] = make_float4(E.e1y, E.e1z, E.tx, E.ty);
         eo[2] = make_float4(E.tz, E.qx, E.qy, E.qz);     eo[3] = make_float4(E.e2q, E.nx, E.ny, E.nz);
     } else pack_padding(f, f2);
-    filt0[3 * (size_t)i] = make_float4(f.bx, f.gx, f.ax, f.bd);         filt0[3 * (size_t)i + 1] = make_float4(f.gd, f.ad, f.m, f.R);
-    filt0[3 * (size_t)i + 2] = make_float4(f.bx2, f.gx2, f.ax2, f.R2);
-    filt1[2 * (size_t)i] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2);  filt1[2 * (size_t)i + 1] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
+    const float4 r0 = make_float4(f.bx, f.gx, f.ax, f.bd), r1 = make_float4(f.gd, f.ad, f.m, f.R), r2 = make_float4(f.bx2, f.gx2, f.ax2, f.R2);
+    if (i < n_padded) {
+        filt0[3 * (size_t)i] = r0; filt0[3 * (size_t)i + 1] = r1; filt0[3 * (size_t)i + 2] = r2;
+        filt1[2 * (size_t)i] = make_float4(f2.bx2, f2.gx2, f2.ax2, f2.m2);  filt1[2 * (size_t)i + 1] = make_float4(f2.bx3, f2.gx3, f2.ax3, f2.m3);
+    }
+    const uint32_t c = i % n_chunks, q = i / n_chunks, k = q / 128, t = q % 128;
+    float4* dst = scan + ((size_t)(c * scan_k + k) * 3) * 128 + t;
+    dst[0] = r0; dst[128] = r1; dst[256] = r2;
 }
 
 // Per-column / per-row detector offsets exactly as lbuffer.cxx:756-757:
@@ -1312,13 +1244,14 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, f
 
 } // namespace
 
-cudaError_t launch_prepack(const float* vertices, const float* normals, uint32_t n, uint32_t n_padded,
-                           const float origin[3], const FrameGeom& g, void* exact, void* filt0, void* filt1,
-                           cudaStream_t s)
+cudaError_t launch_prepack(const float* vertices, const float* normals, uint32_t n, uint32_t n_padded, uint32_t n_chunks,
+                           uint32_t scan_k, const float origin[3], const FrameGeom& g, void* exact, void* filt0, void* filt1,
+                           void* scan, cudaStream_t s)
 {
-    if (n_padded == 0) return cudaSuccess;
-    prepack_kernel<<<(n_padded + 127) / 128, 128, 0, s>>>(vertices, normals, n, n_padded, origin[0], origin[1], origin[2], g,
-                                                          (ExactTri*)exact, (float4*)filt0, (float4*)filt1);
+    const uint32_t slots = n_chunks * scan_k * 128;
+    if (slots == 0) return cudaSuccess;
+    prepack_kernel<<<(slots + 127) / 128, 128, 0, s>>>(vertices, normals, n, n_padded, n_chunks, scan_k, origin[0], origin[1],
+                                                       origin[2], g, (ExactTri*)exact, (float4*)filt0, (float4*)filt1, (float4*)scan);
     return cudaGetLastError();
 }
 
@@ -1346,62 +1279,74 @@ cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
     return cudaGetLastError();
 }
 
-// box shapes the filtered kernel is built for: {box width, box height, boxes per thread}
-template <int PX, int PY, int NB>
+// shapes the filtered kernel is built for: {box width, box height, triangles per thread}
+#define SRT_SCAN_SHAPES(X) X(16, 2, 4) X(16, 1, 4) X(32, 1, 4) X(8, 4, 4) X(8, 1, 4) X(32, 2, 4) X(16, 4, 4) X(8, 8, 4) X(16, 2, 2) X(16, 2, 6) X(32, 2, 6)
+
+template <int PX, int PY, int K>
 static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
 {
-    using G = BoxGeom<PX, PY, NB>;
-    constexpr size_t smem = (size_t)kStages * kTileTris * 48 + 2 * kStages * sizeof(uint64_t) + 4 * sizeof(WarpCtx) +
-                            4 * kQ2Cap * sizeof(uint2) + 4 * G::kQ1Cap * sizeof(uint32_t);
-    static_assert(smem <= 48 * 1024, "the tile ring and the queues must fit the default dynamic shared-memory limit");
-    dim3 grid((a.cam.W + G::kCtaW - 1) / G::kCtaW, a.n_blocks, a.z_splits ? a.z_splits : 1);
-    lbuffer_filtered_kernel<PX, PY, NB><<<grid, 128, smem, s>>>(a);
+    using G = ScanGeom<PX, PY, K>;
+    static_assert(G::kSmem <= 48 * 1024, "the chunk and the queues must fit the default dynamic shared-memory limit");
+    const uint32_t n_cols = (a.cam.W + PX - 1) / PX;
+    dim3 grid((n_cols + a.scan_cols - 1) / a.scan_cols, a.n_blocks, a.scan_chunks);
+    lbuffer_filtered_kernel<PX, PY, K><<<grid, 128, G::kSmem, s>>>(a);
     return cudaGetLastError();
 }
 
-#define SRT_BOX_SHAPES(X) X(16, 1, 1) X(16, 1, 2) X(32, 1, 1) X(16, 2, 1) X(8, 2, 2) X(8, 1, 2) X(16, 2, 2) X(8, 1, 1)
-
-bool filtered_box_supported(uint32_t px, uint32_t py)
+template <int PX, int PY>
+static cudaError_t launch_candidates_t(const RenderArgs& a, cudaStream_t s)
 {
-#define X(PX, PY, NB) if (px == PX && py == PY) return true;
-    SRT_BOX_SHAPES(X)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    candidates_kernel<PX, PY><<<sms * 32, 128, 0, s>>>(a);                // grid-stride over the box list
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    exact_tests_kernel<<<sms * 32, 128, 0, s>>>(a);                       // grid-stride over the pixel list
+    return cudaGetLastError();
+}
+
+bool filtered_shape_supported(uint32_t px, uint32_t py, uint32_t k)
+{
+#define X(PX, PY, K) if (px == PX && py == PY && k == K) return true;
+    SRT_SCAN_SHAPES(X)
 #undef X
     return false;
 }
 
-uint32_t filtered_cta_width(uint32_t px, uint32_t py, uint32_t nb)
-{
-#define X(PX, PY, NB) if (px == PX && py == PY && nb == NB) return BoxGeom<PX, PY, NB>::kCtaW;
-    SRT_BOX_SHAPES(X)
-#undef X
-    return 0;
-}
-
-template <int PX, int PY, int NB>
+template <int PX, int PY, int K>
 static int filtered_occupancy_t()
 {
-    using G = BoxGeom<PX, PY, NB>;
-    constexpr size_t smem = (size_t)kStages * kTileTris * 48 + 2 * kStages * sizeof(uint64_t) + 4 * sizeof(WarpCtx) +
-                            4 * kQ2Cap * sizeof(uint2) + 4 * G::kQ1Cap * sizeof(uint32_t);
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lbuffer_filtered_kernel<PX, PY, NB>, 128, smem) != cudaSuccess) n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lbuffer_filtered_kernel<PX, PY, K>, 128, ScanGeom<PX, PY, K>::kSmem) != cudaSuccess) n = 0;
     return n;
 }
 
-int filtered_resident_ctas(uint32_t px, uint32_t py, uint32_t nb)
+int filtered_resident_ctas(uint32_t px, uint32_t py, uint32_t k)
 {
-#define X(PX, PY, NB) if (px == PX && py == PY && nb == NB) return filtered_occupancy_t<PX, PY, NB>();
-    SRT_BOX_SHAPES(X)
+#define X(PX, PY, K) if (px == PX && py == PY && k == K) return filtered_occupancy_t<PX, PY, K>();
+    SRT_SCAN_SHAPES(X)
 #undef X
     return 0;
+}
+
+cudaError_t launch_filtered_candidates(const RenderArgs& a, cudaStream_t s)
+{
+    if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0 || a.scan_chunks == 0) return cudaSuccess;
+#define X(PX, PY, K) if (a.box_px == PX && a.box_py == PY && a.scan_k == K) return launch_candidates_t<PX, PY>(a, s);
+    SRT_SCAN_SHAPES(X)
+#undef X
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, cudaStream_t s)
 {
-    if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0) return cudaSuccess;
-    if (!a.hit_entries || !a.hit_counts || a.hit_cap == 0 || a.hit_cap > kMaxHitCap) return cudaErrorInvalidValue;
-#define X(PX, PY, NB) if (a.box_px == PX && a.box_py == PY && a.box_nb == NB) return launch_filtered_t<PX, PY, NB>(a, s);
-    SRT_BOX_SHAPES(X)
+    if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0 || a.scan_chunks == 0) return cudaSuccess;
+    if (!a.hit_entries || !a.hit_counts || a.hit_cap == 0 || a.hit_cap > kMaxHitCap || a.scan_cols == 0 || !a.cand || !a.cand_count ||
+        !a.pix || a.n_meshes > 32)
+        return cudaErrorInvalidValue;
+#define X(PX, PY, K) if (a.box_px == PX && a.box_py == PY && a.scan_k == K) return launch_filtered_t<PX, PY, K>(a, s);
+    SRT_SCAN_SHAPES(X)
 #undef X
     return cudaErrorInvalidValue;
 }

@@ -5,22 +5,13 @@
 
 namespace srt {
 
-#ifndef SRT_TILE_TRIS
-#define SRT_TILE_TRIS 128
-#endif
-constexpr uint32_t kTileTris  = SRT_TILE_TRIS;   // triangles per shared-memory tile of level-0 filter records (48 B each)
-#ifndef SRT_GROUP_TRIS
-#define SRT_GROUP_TRIS 4
-#endif
-constexpr uint32_t kGroupTris = SRT_GROUP_TRIS;  // triangles per vote group in the filtered kernel; meshes are padded to a multiple
-#ifndef SRT_STAGES
-#define SRT_STAGES 4
-#endif
-constexpr uint32_t kStages    = SRT_STAGES;     // bulk-copy pipeline depth
+constexpr uint32_t kPadTris = 4;       // meshes are padded to a multiple (never-surviving records)
 
 // One mesh as the kernels see it (device pointers).
 struct DevMesh {
-    const float4* filt0;     // 3 float4 per (padded) triangle: FilterTri  (level 0; the tiles the filtered kernel streams)
+    const float4* filt0;     // 3 float4 per (padded) triangle: FilterTri  (level 0), natural triangle order
+    const float4* scan;      // the same records, chunk-major SoA for the filtered kernel: [n_chunks][scan_k][3][128]
+    uint32_t n_chunks;       // chunks of 128 * scan_k triangles (a strided sample of the mesh each)
     const float4* filt1;     // 2 float4 per (padded) triangle: FilterTri2 (level 1: the two other strips)
     const float4* exact;     // 4 float4 per triangle            -- ExactTri
     uint32_t n, n_padded;
@@ -70,15 +61,19 @@ struct RenderArgs {
     // `dist` receives the z-buffer value t (+inf = no hit), `ssum` the scene-wide triangle index (-1 = none);
     // strict `z > t` in ascending triangle order => the first of equal t wins, negative t is accepted.
     int mode;
-    // Filtered kernel.  One thread tests a BOX of box_px x box_py pixels per triangle (FilterTri::R is packed for that
-    // box); accepted intersections are not accumulated in place (the reference's float sum is order dependent and the
-    // exact tests of a warp run wherever a lane is free) but appended to the pixel's hit list {scene-wide triangle
-    // index, value} -- value = sign * t (mode 0) or t (mode 1) -- through an atomic slot counter; resolve_hits_kernel
-    // sorts each list by triangle index and replays lbuffer.cxx:788-809 (or the z-buffer update, main-omp.cxx:656-662)
-    // in the reference's order.  With z_splits > 1 the CTAs of grid.z slice z stream only tiles z, z + z_splits, ...
-    // of each mesh (small grids still fill the GPU).
-    uint32_t box_px, box_py, box_nb;   // box size (pixels) and boxes per thread (side by side along x)
-    uint32_t z_splits;
+    // Filtered kernel.  A thread holds scan_k triangles and tests them against boxes of box_px x box_py pixels
+    // (FilterTri::R / R2 are packed for that box); a CTA covers the box rows of one 16-row block x scan_cols box columns
+    // x one chunk of 128 * scan_k triangles (grid.z = scan_chunks = the largest chunk count of a contributing mesh).
+    // Accepted intersections are not accumulated in place (the reference's float sum is order dependent and the exact
+    // tests of a warp run wherever a lane is free) but appended to the pixel's hit list {scene-wide triangle index,
+    // value} -- value = sign * t (mode 0) or t (mode 1) -- through an atomic slot counter; resolve_hits_kernel sorts each
+    // list by triangle index and replays lbuffer.cxx:788-809 (or the z-buffer update, main-omp.cxx:656-662) in the
+    // reference's order.
+    uint32_t box_px, box_py, scan_k, scan_cols, scan_chunks;
+    // survivors of the scan {box, triangle} (cand) and of the per-pixel strip tests {pixel, triangle} (pix).
+    // cand_count[0] / [1] count them: zero when the scan starts; they may exceed the capacities (entries beyond are
+    // dropped and resolve_hits_kernel recomputes every pixel with the exact sequence).
+    uint2* cand; uint2* pix; uint32_t* cand_count; uint32_t cand_cap, pix_cap;
     uint2* hit_entries;      // [pixel][hit_cap]
     uint32_t* hit_counts;    // [pixel]: entries appended (may exceed hit_cap: overflow -> exact recompute); zero between renders
     uint32_t hit_cap;
@@ -120,12 +115,13 @@ cudaError_t launch_shade(const ShadeArgs& a, cudaStream_t s);
 // Exact kernel: every pair runs the reference op sequence. audit != 0 additionally evaluates the
 // filters for every pair and counts (filter says reject) && (exact says hit) into counters[1].
 cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s);
-// Filtered kernel for the box shape a.box_px x a.box_py (one of filtered_box_shapes()); launch_resolve_hits must follow.
+// Filtered path for the shape (a.box_px, a.box_py, a.scan_k): the scan (a.cand_count[0..1] must be zero), then the
+// candidate stages (per-pixel strip tests, exact tests), then launch_resolve_hits.
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, cudaStream_t s);
+cudaError_t launch_filtered_candidates(const RenderArgs& a, cudaStream_t s);
 constexpr uint32_t kMaxHitCapacity = 16;
-bool filtered_box_supported(uint32_t box_px, uint32_t box_py);
-uint32_t filtered_cta_width(uint32_t box_px, uint32_t box_py, uint32_t box_nb);   // 0: shape not built
-int filtered_resident_ctas(uint32_t box_px, uint32_t box_py, uint32_t box_nb);      // CTAs resident per SM on the current device
+bool filtered_shape_supported(uint32_t box_px, uint32_t box_py, uint32_t scan_k);
+int filtered_resident_ctas(uint32_t box_px, uint32_t box_py, uint32_t scan_k);     // CTAs resident per SM on the current device
 // Culled kernel: bin pass (every triangle against every bin of a.bins_x x a.bins_y), then the render pass.  Same results
 // as the other kernels: the bins and the per-CTA cull only ever drop pairs the conservative filter proves to miss.
 cudaError_t launch_lbuffer_bins(const RenderArgs& a, cudaStream_t s);
@@ -138,9 +134,9 @@ cudaError_t launch_repair(const float* L, float* image, uint32_t W, uint32_t H, 
 
 // Scene pre-pack on the GPU (prepack_math.h): raw vertices -> ExactTri / FilterTri / FilterTri2.
 struct FrameGeom;
-cudaError_t launch_prepack(const float* vertices, const float* normals, uint32_t n, uint32_t n_padded,
-                           const float origin[3], const FrameGeom& g, void* exact, void* filt0, void* filt1,
-                           cudaStream_t s);
+cudaError_t launch_prepack(const float* vertices, const float* normals, uint32_t n, uint32_t n_padded, uint32_t n_chunks,
+                           uint32_t scan_k, const float origin[3], const FrameGeom& g, void* exact, void* filt0, void* filt1,
+                           void* scan, cudaStream_t s);
 // Detector offset tables u_off[W], v_off[H] (lbuffer.cxx:756-757).
 cudaError_t launch_offsets(float* u_off, float* v_off, uint32_t W, uint32_t H, float sp_u, float sp_v, cudaStream_t s);
 

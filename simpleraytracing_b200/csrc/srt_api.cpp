@@ -27,19 +27,23 @@
 #endif
 
 #ifndef SRT_RESIDENT_CTAS
-#define SRT_RESIDENT_CTAS 8      // CTAs of the filtered kernel resident per SM (64 registers)
+#define SRT_RESIDENT_CTAS 4      // CTAs of the filtered kernel resident per SM if the occupancy query fails
 #endif
 #ifndef SRT_BOX_PX
 #define SRT_BOX_PX 16            // default box of the filtered kernel: SRT_BOX_PX x SRT_BOX_PY pixels, SRT_BOX_NB boxes per thread
 #endif
 #ifndef SRT_BOX_PY
-#define SRT_BOX_PY 1
+#define SRT_BOX_PY 4
 #endif
-#ifndef SRT_BOX_NB
-#define SRT_BOX_NB 2
+#ifndef SRT_SCAN_K
+#define SRT_SCAN_K 4             // triangles a thread of the filtered kernel holds in registers
 #endif
 
+
 namespace {
+
+constexpr uint32_t kMaxScanK = 8;
+constexpr size_t kScanSlack = 128 * kMaxScanK;   // the chunk-major scan array is padded to whole chunks
 
 thread_local std::string g_create_error;
 
@@ -48,6 +52,8 @@ struct MeshBuf {
     float* d_vertices = nullptr;     // 9 per triangle
     float* d_normals = nullptr;      // 3 per triangle, only when the caller supplied normals
     void* filt = nullptr; void* exact = nullptr;   // filt: cap level-0 records (48 B) followed by cap level-1 records (32 B)
+    void* scan = nullptr;            // chunk-major copy of the level-0 records for the filtered kernel (cap + kScanSlack slots)
+    uint32_t n_chunks = 0;           // chunks of 128 * scan_k triangles of the current packing
     const float4* filt0() const { return (const float4*)filt; }
     const float4* filt1() const { return (const float4*)((const char*)filt + cap * sizeof(srt::FilterTri)); }
     size_t cap = 0;                  // capacity in triangles of all of the above
@@ -75,6 +81,7 @@ struct srt_ctx {
     srt_camera camera{};
     bool packed = false;                 // packed arrays match meshes + camera + box shape
     uint32_t box_px = 0, box_py = 0;     // box of the filtered kernel the packed level-0 bounds (FilterTri::R) are for
+    uint32_t scan_k = 0;                 // triangles per thread the chunk-major scan arrays are laid out for
     bool filterable = false;
 
     std::vector<srt::ShadeMesh> h_shade; // shaded variant: per-mesh descriptors
@@ -94,7 +101,11 @@ struct srt_ctx {
     bool count_exact = false;
     // per-pixel hit lists of the filtered kernel (counts are zero between renders: resolve_hits_kernel resets them)
     uint2* d_hit_entries = nullptr; uint32_t* d_hit_counts = nullptr; size_t hit_pixels_cap = 0; uint32_t hit_cap = 0;
-    int force_z_splits = 0;              // diagnostic override: 0 = heuristic
+    // candidate list of the filtered kernel: survivors of the scan.  h_cand_count (pinned) receives the count of every
+    // render asynchronously; a later render grows the list when the last known count came close to the capacity.
+    uint2* d_cand = nullptr; uint2* d_pix = nullptr; uint32_t* d_cand_count = nullptr; uint32_t cand_cap = 0, pix_cap = 0;
+    uint32_t* h_cand_count = nullptr;    // [0] box list, [1] pixel list
+    int force_scan_cols = 0;             // diagnostic override of the box columns per CTA: 0 = heuristic
     // per-bin triangle lists of the culled kernel
     uint32_t* d_bin_entries = nullptr; uint32_t* d_bin_counts = nullptr; size_t bin_entries_cap = 0, bin_counts_cap = 0;
     bool counters_pending = false, timing_pending = false;
@@ -118,7 +129,7 @@ int fail(srt_ctx* c, int code, const char* fmt, ...)
 
 void free_mesh(MeshBuf& m)
 {
-    cudaFree(m.d_vertices); cudaFree(m.d_normals); cudaFree(m.filt); cudaFree(m.exact);
+    cudaFree(m.d_vertices); cudaFree(m.d_normals); cudaFree(m.filt); cudaFree(m.exact); cudaFree(m.scan);
     float* tc = m.d_texcoords; size_t tcc = m.texcoord_cap; uint8_t* tx = m.d_tex; size_t txc = m.tex_cap;
     m = MeshBuf{};
     m.d_texcoords = tc; m.texcoord_cap = tcc; m.d_tex = tx; m.tex_cap = txc;       // kept: sized independently
@@ -142,6 +153,8 @@ void free_frame(srt_ctx* c)
     c->d_L = c->d_img = c->d_dist = nullptr; c->d_ssum = nullptr; c->d_hits = nullptr; c->frame_cap = 0;
     cudaFree(c->d_hit_entries); cudaFree(c->d_hit_counts);
     c->d_hit_entries = nullptr; c->d_hit_counts = nullptr; c->hit_pixels_cap = 0; c->hit_cap = 0;
+    cudaFree(c->d_cand); cudaFree(c->d_pix); cudaFree(c->d_cand_count); if (c->h_cand_count) cudaFreeHost(c->h_cand_count);
+    c->d_cand = nullptr; c->d_pix = nullptr; c->d_cand_count = nullptr; c->h_cand_count = nullptr; c->cand_cap = 0; c->pix_cap = 0;
     cudaFree(c->d_bin_entries); cudaFree(c->d_bin_counts);
     c->d_bin_entries = nullptr; c->d_bin_counts = nullptr; c->bin_entries_cap = 0; c->bin_counts_cap = 0;
 }
@@ -163,7 +176,7 @@ int ensure_frame(srt_ctx* c, size_t pixels)
 // Grow a mesh's device buffers to hold n triangles (only reallocates when growing).
 int ensure_mesh(srt_ctx* c, MeshBuf& m, size_t n, bool want_normals)
 {
-    const size_t pad = (n + srt::kGroupTris - 1) / srt::kGroupTris * srt::kGroupTris;
+    const size_t pad = (n + srt::kPadTris - 1) / srt::kPadTris * srt::kPadTris;
     if (pad > m.cap || m.cap == 0) {
         SRT_CUDA(c, cudaStreamSynchronize(c->stream));
         const bool had_normals = m.d_normals != nullptr;
@@ -172,6 +185,7 @@ int ensure_mesh(srt_ctx* c, MeshBuf& m, size_t n, bool want_normals)
         SRT_CUDA(c, cudaMalloc(&m.d_vertices, cap * 9 * sizeof(float)));
         SRT_CUDA(c, cudaMalloc(&m.filt, cap * (sizeof(srt::FilterTri) + sizeof(srt::FilterTri2))));
         SRT_CUDA(c, cudaMalloc(&m.exact, cap * sizeof(srt::ExactTri)));
+        SRT_CUDA(c, cudaMalloc(&m.scan, (cap + kScanSlack) * sizeof(srt::FilterTri)));
         if (had_normals || want_normals) SRT_CUDA(c, cudaMalloc(&m.d_normals, cap * 3 * sizeof(float)));
         m.cap = cap;
     }
@@ -179,11 +193,12 @@ int ensure_mesh(srt_ctx* c, MeshBuf& m, size_t n, bool want_normals)
     return SRT_OK;
 }
 
-// (Re)build the packed arrays for the current meshes + camera + box shape of the filtered kernel: all on the GPU,
+// (Re)build the packed arrays for the current meshes + camera + shape of the filtered kernel: all on the GPU,
 // all asynchronous.
-int pack_scene(srt_ctx* c, uint32_t box_px = SRT_BOX_PX, uint32_t box_py = SRT_BOX_PY)
+int pack_scene(srt_ctx* c, uint32_t box_px = SRT_BOX_PX, uint32_t box_py = SRT_BOX_PY, uint32_t scan_k = SRT_SCAN_K)
 {
-    if (c->packed && c->box_px == box_px && c->box_py == box_py) return SRT_OK;
+    if (c->packed && c->box_px == box_px && c->box_py == box_py && c->scan_k == scan_k) return SRT_OK;
+    if (scan_k == 0 || scan_k > kMaxScanK) return fail(c, SRT_ERR_INVALID, "triangles per thread %u out of range", scan_k);
     if (c->n_meshes == 0) return fail(c, SRT_ERR_INVALID, "srt_set_meshes has not been called");
     if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
     const srt_camera& cam = c->camera;
@@ -217,10 +232,12 @@ int pack_scene(srt_ctx* c, uint32_t box_px = SRT_BOX_PX, uint32_t box_py = SRT_B
         sm.n = mb.n; sm.first = (uint32_t)c->total_tris;
         for (int k = 0; k < 3; ++k) { sm.ka[k] = mb.material.ambient[k]; sm.kd[k] = mb.material.diffuse[k]; sm.ks[k] = mb.material.specular[k]; }
         sm.shininess = mb.material.shininess;
-        SRT_CUDA(c, srt::launch_prepack(mb.d_vertices, mb.has_normals ? mb.d_normals : nullptr, mb.n, mb.n_padded,
-                                        cam.origin, g, mb.exact, (void*)mb.filt0(), (void*)mb.filt1(), c->stream));
+        mb.n_chunks = (mb.n_padded + 128 * scan_k - 1) / (128 * scan_k);
+        SRT_CUDA(c, srt::launch_prepack(mb.d_vertices, mb.has_normals ? mb.d_normals : nullptr, mb.n, mb.n_padded, mb.n_chunks,
+                                        scan_k, cam.origin, g, mb.exact, (void*)mb.filt0(), (void*)mb.filt1(), mb.scan, c->stream));
         srt::DevMesh& d = c->h_desc[m];
         d.filt0 = mb.filt0(); d.filt1 = mb.filt1(); d.exact = (const float4*)mb.exact;
+        d.scan = (const float4*)mb.scan; d.n_chunks = mb.n_chunks;
         d.n = mb.n; d.n_padded = mb.n_padded; d.mu = mb.mu;
         d.first = (uint32_t)c->total_tris;
         d.contributes = (m == 0);                           // lbuffer.cxx:788: only meshes[0] adds path length
@@ -241,19 +258,19 @@ int pack_scene(srt_ctx* c, uint32_t box_px = SRT_BOX_PX, uint32_t box_py = SRT_B
         SRT_CUDA(c, cudaMalloc(&c->d_shade_meshes, nm * sizeof(srt::ShadeMesh))); c->shade_cap = nm;
     }
     SRT_CUDA(c, cudaMemcpyAsync(c->d_shade_meshes, c->h_shade.data(), nm * sizeof(srt::ShadeMesh), cudaMemcpyHostToDevice, c->stream));
-    c->packed = true; c->box_px = box_px; c->box_py = box_py;
+    c->packed = true; c->box_px = box_px; c->box_py = box_py; c->scan_k = scan_k;
     return SRT_OK;
 }
 
-// Box shape of the filtered kernel: srt_params::pixels_per_thread = box width | box height << 8 | boxes per thread << 16
+// Shape of the filtered kernel: srt_params::pixels_per_thread = box width | box height << 8 | triangles per thread << 16
 // (0 in a field = default).
-bool decode_box(uint32_t v, uint32_t& px, uint32_t& py, uint32_t& nb)
+bool decode_box(uint32_t v, uint32_t& px, uint32_t& py, uint32_t& k)
 {
-    px = v & 0xffu; py = (v >> 8) & 0xffu; nb = (v >> 16) & 0xffu;
-    if (px == 0) { px = SRT_BOX_PX; if (py == 0) py = SRT_BOX_PY; if (nb == 0) nb = SRT_BOX_NB; }
+    px = v & 0xffu; py = (v >> 8) & 0xffu; k = (v >> 16) & 0xffu;
+    if (px == 0) { px = SRT_BOX_PX; if (py == 0) py = SRT_BOX_PY; }
     if (py == 0) py = 1;
-    if (nb == 0) nb = 1;
-    return srt::filtered_cta_width(px, py, nb) != 0;
+    if (k == 0) k = SRT_SCAN_K;
+    return srt::filtered_shape_supported(px, py, k);
 }
 
 // parts == 0: contiguous band [row_begin, row_end) written at image positions.
@@ -274,12 +291,12 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     if (audit) kernel = SRT_KERNEL_EXACT;
     if (kernel != SRT_KERNEL_AUTO && kernel != SRT_KERNEL_EXACT && kernel != SRT_KERNEL_FILTERED && kernel != SRT_KERNEL_CULLED)
         return fail(c, SRT_ERR_INVALID, "unknown kernel selector %u", params->kernel);
-    uint32_t box_px, box_py, box_nb;
-    if (!decode_box(params->pixels_per_thread, box_px, box_py, box_nb))
-        return fail(c, SRT_ERR_INVALID, "box shape %u x %u x %u (pixels_per_thread = 0x%x) is not built", box_px, box_py, box_nb,
-                    params->pixels_per_thread);
-    const bool repack = !(c->packed && c->box_px == box_px && c->box_py == box_py);
-    int rc = pack_scene(c, box_px, box_py);
+    uint32_t box_px, box_py, scan_k;
+    if (!decode_box(params->pixels_per_thread, box_px, box_py, scan_k))
+        return fail(c, SRT_ERR_INVALID, "shape %u x %u pixels, %u triangles per thread (pixels_per_thread = 0x%x) is not built", box_px,
+                    box_py, scan_k, params->pixels_per_thread);
+    const bool repack = !(c->packed && c->box_px == box_px && c->box_py == box_py && c->scan_k == scan_k);
+    int rc = pack_scene(c, box_px, box_py, scan_k);
     if (rc) return rc;
     const srt_camera& cam = c->camera;
     if (row_begin > row_end || row_end > cam.height)
@@ -319,7 +336,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         aligned = aligned && ((uintptr_t)extra_frames[i] & 15u) == 0;
     }
     a.L_vec4 = aligned ? 1 : 0;                         // 128-bit stores only into 16-byte aligned frames
-    a.box_px = box_px; a.box_py = box_py; a.box_nb = box_nb;
+    a.box_px = box_px; a.box_py = box_py; a.scan_k = scan_k;
     a.counters = nullptr;
     if (c->count_exact || audit) {
         if (!c->d_counters) SRT_CUDA(c, cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)));
@@ -356,37 +373,33 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         }
     }
 
-    a.z_splits = 1; a.hit_entries = nullptr; a.hit_counts = nullptr; a.hit_cap = 0;
+    a.scan_cols = 0; a.scan_chunks = 0; a.hit_entries = nullptr; a.hit_counts = nullptr; a.hit_cap = 0;
     uint32_t extra_launches = 0;
     if (kernel == SRT_KERNEL_FILTERED) {
-        if (c->total_tris >= (1ull << 25)) kernel = SRT_KERNEL_EXACT;   // queue entries hold 25-bit triangle indices
-    }
-    if (kernel == SRT_KERNEL_FILTERED) {
-        // Triangle slices (grid.z): CTA (x, y, z) streams every z_splits-th tile of the mesh, so that a grid of few
-        // pixel tiles -- a rank's share of a multi-GPU frame -- still fills the GPU.  The scan work of a CTA is uniform
-        // (tiles per slice), so the launch time is ~ waves x (tiles per slice + a fixed per-CTA cost of about half a
-        // tile): the slice count minimises that, i.e. it avoids both a mostly empty last wave and a ragged tile count.
+        // CTA = (one 16-row block) x (scan_cols box columns) x (one chunk of 128 K triangles).  The work of a CTA is
+        // uniform: a fixed prologue (chunk load: ~16 boxes' worth, measured) + its boxes, so the launch takes
+        // waves x (16 + boxes per CTA): the column range is the one that minimises that -- it avoids both a mostly empty
+        // last wave and many tiny CTAs.
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-        const uint32_t cta_w = srt::filtered_cta_width(box_px, box_py, box_nb);
-        const uint64_t ctas = (uint64_t)((cam.width + cta_w - 1) / cta_w) * a.n_blocks;
-        int resident = srt::filtered_resident_ctas(box_px, box_py, box_nb);
+        int resident = srt::filtered_resident_ctas(box_px, box_py, scan_k);
         if (resident <= 0) resident = SRT_RESIDENT_CTAS;
-        const uint64_t slots = (uint64_t)sms * (uint64_t)resident;
-        uint64_t max_tiles = 1;
+        uint32_t chunks = 0;
         for (size_t m = 0; m < c->n_meshes; ++m)
-            max_tiles = std::max<uint64_t>(max_tiles, (c->meshes[m].n_padded + srt::kTileTris - 1) / srt::kTileTris);
-        uint32_t zs = 1;
-        if (ctas > 0) {
-            const uint32_t zmax = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, max_tiles / 2));   // >= 2 tiles per slice
-            double best = 1e300;
-            for (uint32_t z = 1; z <= zmax; ++z) {
-                const double waves = (double)((ctas * z + slots - 1) / slots);
-                const double cost = waves * ((double)((max_tiles + z - 1) / z) + 0.5);
-                if (cost <= best * 1.0001) { best = cost; zs = z; }                 // ties: more, shorter CTAs
-            }
+            if (all || m == 0) chunks = std::max(chunks, c->meshes[m].n_chunks);
+        const uint32_t n_cols = (cam.width + box_px - 1) / box_px;
+        const uint64_t slots = (uint64_t)sms * (uint64_t)resident;
+        uint32_t cols = n_cols;
+        double best = 1e300;
+        for (uint32_t parts_x = 1; parts_x <= n_cols; ++parts_x) {
+            const uint32_t cw = (n_cols + parts_x - 1) / parts_x;
+            if (cw < 4 && parts_x > 1) break;
+            const uint64_t ctas = (uint64_t)((n_cols + cw - 1) / cw) * a.n_blocks * chunks;
+            const double cost = (double)((ctas + slots - 1) / slots) * (16.0 + (double)cw * (16 / box_py));
+            if (cost < best * 0.999) { best = cost; cols = cw; }
         }
-        if (c->force_z_splits > 0) zs = (uint32_t)std::min<uint64_t>((uint64_t)c->force_z_splits, max_tiles);
+        if (c->force_scan_cols > 0) cols = std::min<uint32_t>((uint32_t)c->force_scan_cols, n_cols);
+        a.scan_cols = cols; a.scan_chunks = chunks;
         // per-pixel hit lists: 4 + 8 * cap bytes per pixel of the launch's output index range
         const size_t pixels = (size_t)(parts == 0 ? cam.height : a.n_blocks * 16) * cam.width;
         const uint32_t cap = pixels <= ((size_t)1 << 24) ? 12u : 8u;
@@ -399,14 +412,38 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
             SRT_CUDA(c, cudaMemsetAsync(c->d_hit_counts, 0, pixels * sizeof(uint32_t), c->stream));
             c->hit_pixels_cap = pixels; c->hit_cap = cap;
         }
-        a.z_splits = zs; a.hit_entries = c->d_hit_entries; a.hit_counts = c->d_hit_counts; a.hit_cap = cap;
+        a.hit_entries = c->d_hit_entries; a.hit_counts = c->d_hit_counts; a.hit_cap = cap;
+        // candidate lists: 8 bytes per survivor of the scan {box, triangle} (3e-4 of the box tests on the dragon) and per
+        // survivor of the per-pixel strip tests {pixel, triangle} (~ the hits).  Sized from the scene, grown when the
+        // counts of an earlier render (read back asynchronously) came within a factor 2 of the capacity.
+        if (!c->h_cand_count) {
+            SRT_CUDA(c, cudaHostAlloc(&c->h_cand_count, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+            c->h_cand_count[0] = c->h_cand_count[1] = 0;
+        }
+        uint64_t want_cap = std::max<uint64_t>(4ull << 20, 32ull * c->total_tris);
+        uint64_t want_pix = std::max<uint64_t>(16ull << 20, 128ull * c->total_tris);
+        want_cap = std::min<uint64_t>(std::max<uint64_t>(want_cap, 2ull * c->h_cand_count[0]), 0xffffffffull);
+        want_pix = std::min<uint64_t>(std::max<uint64_t>(want_pix, 2ull * c->h_cand_count[1]), 0xffffffffull);
+        if (want_cap > c->cand_cap || want_pix > c->pix_cap) {
+            SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_cand); cudaFree(c->d_pix); c->d_cand = nullptr; c->d_pix = nullptr; c->cand_cap = 0; c->pix_cap = 0;
+            SRT_CUDA(c, cudaMalloc(&c->d_cand, want_cap * sizeof(uint2)));
+            SRT_CUDA(c, cudaMalloc(&c->d_pix, want_pix * sizeof(uint2)));
+            c->cand_cap = (uint32_t)want_cap; c->pix_cap = (uint32_t)want_pix;
+        }
+        if (!c->d_cand_count) SRT_CUDA(c, cudaMalloc(&c->d_cand_count, 2 * sizeof(uint32_t)));
+        SRT_CUDA(c, cudaMemsetAsync(c->d_cand_count, 0, 2 * sizeof(uint32_t), c->stream));
+        a.cand = c->d_cand; a.pix = c->d_pix; a.cand_count = c->d_cand_count; a.cand_cap = c->cand_cap; a.pix_cap = c->pix_cap;
+        if (c->n_meshes > 32 || c->total_tris >= (1ull << 27)) kernel = SRT_KERNEL_EXACT;     // candidate entries: 5-bit mesh, 27-bit triangle
     }
     SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     if (kernel == SRT_KERNEL_FILTERED) {
         SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
         SRT_CUDA(c, srt::launch_lbuffer_filtered(a, c->stream));
         SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
-        SRT_CUDA(c, srt::launch_resolve_hits(a, c->stream)); extra_launches = 1;
+        SRT_CUDA(c, srt::launch_filtered_candidates(a, c->stream));
+        SRT_CUDA(c, srt::launch_resolve_hits(a, c->stream)); extra_launches = 3;          // + candidates, exact tests
+        SRT_CUDA(c, cudaMemcpyAsync(c->h_cand_count, c->d_cand_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     } else if (kernel == SRT_KERNEL_CULLED) {
         SRT_CUDA(c, srt::launch_lbuffer_bins(a, c->stream)); extra_launches = 1;
         SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
@@ -419,7 +456,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     }
     SRT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     c->timing.kernel_used = kernel;
-    c->timing.z_slices = a.z_splits;
+    c->timing.scan_cols = a.scan_cols;
     c->timing.launches = ((band_rows > 0) ? 1 + extra_launches : 0) + (repack ? 1 + (uint32_t)c->n_meshes : 0);
     const uint64_t tris = all ? c->total_tris : c->mesh0_tris;
     c->timing.pair_tests = (uint64_t)band_rows * cam.width * tris;
@@ -605,7 +642,7 @@ int srt_set_meshes(srt_ctx* c, int n_meshes, const srt_mesh_desc* meshes)
         int rc = ensure_mesh(c, mb, d.n_triangles, d.normals != nullptr);
         if (rc) return rc;
         mb.n = d.n_triangles;
-        mb.n_padded = (d.n_triangles + srt::kGroupTris - 1) / srt::kGroupTris * srt::kGroupTris;
+        mb.n_padded = (d.n_triangles + srt::kPadTris - 1) / srt::kPadTris * srt::kPadTris;
         mb.mu = d.mu;
         mb.has_normals = d.normals != nullptr;
         mb.material = d.material;
@@ -900,7 +937,7 @@ int srt_debug_download_packed(srt_ctx* c, int mesh, float* exact16, float* filt1
 // diagnostic: how meshes are packed -- padding granularity (triangles) and the default box of the filtered kernel
 int srt_debug_pack_info(uint32_t* pad_to, uint32_t* box_w, uint32_t* box_h)
 {
-    if (pad_to) *pad_to = srt::kGroupTris;
+    if (pad_to) *pad_to = srt::kPadTris;
     if (box_w) *box_w = SRT_BOX_PX;
     if (box_h) *box_h = SRT_BOX_PY;
     return SRT_OK;
@@ -918,7 +955,7 @@ int srt_debug_prepack(const float* vertices, uint32_t n, const srt_camera* cam, 
     srt::FrameGeom g = srt::make_frame_geom(cam->origin, cam->detector, cam->up, cam->right, cam->pixel_spacing[0],
                                             cam->pixel_spacing[1], cam->width, cam->height, box_w, box_h);
     srt::PackedMesh pm;
-    srt::prepack_mesh(vertices, nullptr, n, cam->origin, g, srt::kGroupTris, pm);
+    srt::prepack_mesh(vertices, nullptr, n, cam->origin, g, srt::kPadTris, pm);
     if (exact16) std::memcpy(exact16, pm.exact.data(), pm.exact.size() * sizeof(srt::ExactTri));
     if (filt12) std::memcpy(filt12, pm.filt.data(), pm.filt.size() * sizeof(srt::FilterTri));
     if (filt2_8) std::memcpy(filt2_8, pm.filt2.data(), pm.filt2.size() * sizeof(srt::FilterTri2));
@@ -955,10 +992,10 @@ int srt_debug_ffma_peak(srt_ctx* c, int repeats, float* tflops_out)
 }
 
 // diagnostic: force the number of triangle-range splits of the filtered kernel (0 = heuristic)
-int srt_debug_force_splits(srt_ctx* c, int z_splits)
+int srt_debug_force_scan_cols(srt_ctx* c, int cols)
 {
-    if (!c || z_splits < 0 || z_splits > 64) return SRT_ERR_INVALID;
-    c->force_z_splits = z_splits;
+    if (!c || cols < 0) return SRT_ERR_INVALID;
+    c->force_scan_cols = cols;
     return SRT_OK;
 }
 

@@ -72,7 +72,7 @@ def test_prepack_exact_constants(srtlib, oracle, dragon):
     assert pk["unfilterable"] == 0 and pk["n_padded"] == (len(dragon) + pad - 1) // pad * pad
 
 
-BOXES = [(16, 1), (32, 1), (16, 2), (8, 2), (8, 1)]          # box shapes the filtered kernel is built for
+BOXES = [(16, 2), (16, 1), (32, 1), (8, 4), (8, 1), (32, 2), (16, 4), (8, 8)]          # box shapes the filtered kernel is built for
 
 
 @pytest.mark.parametrize("size,scale", [(128, 1.0), (2048, 1.0), (640, 3000.0), (640, 1e-4)])

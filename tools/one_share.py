@@ -7,7 +7,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from simpleraytracing_b200 import Context, Library, scene, KERNEL_FILTERED  # noqa: E402
 from simpleraytracing_b200.capi import box_shape  # noqa: E402
-sh = tuple(int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "16x1x2").split("x"))
+sh = tuple(int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "16x2x4").split("x"))
 size = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 lib = Library(os.environ.get("SRT_LIB")); ctx = Context(0, lib)
 tri = scene.dragon(); lo, hi = lib.scene_bbox([(tri, 0.1037)])

@@ -2,11 +2,11 @@
 """Development sweeps on ONE GPU (device time from the library's CUDA events, best of N after a warm-up).
 
   python tools/sweep.py boxes  [size]          every box shape of the filtered kernel: full frame + the 8 block-cyclic shares
-  python tools/sweep.py splits [size] [shape]  full frame and share 0 of 8 with forced triangle-range slice counts
+  python tools/sweep.py splits [size] [shape]  full frame and share 0 of 8 with forced box-column counts per CTA
   python tools/sweep.py parts  [size] [shape]  per-share kernel time for N = 2, 4, 8 (load balance across ranks)
   python tools/sweep.py kernels [size] [scene] one frame with every kernel selector (+ exact-test counts)
 
-shape = PXxPYxNB, e.g. 16x1x2.  Output: one line per measurement; copy what matters into profiles/.
+shape = PXxPYxNB, e.g. 16x2x4 (box width x box height x triangles per thread).  Output: one line per measurement; copy what matters into profiles/.
 """
 import os
 import sys
@@ -19,7 +19,7 @@ sys.path.insert(0, str(ROOT))
 from simpleraytracing_b200 import Context, Library, scene, KERNEL_FILTERED, KERNEL_CULLED, KERNEL_EXACT  # noqa: E402
 from simpleraytracing_b200.capi import box_shape  # noqa: E402
 
-SHAPES = [(16, 1, 1), (16, 1, 2), (32, 1, 1), (16, 2, 1), (8, 2, 2), (8, 1, 2), (16, 2, 2), (8, 1, 1)]
+SHAPES = [(16, 2, 4), (16, 1, 4), (32, 1, 4), (8, 4, 4), (8, 1, 4), (32, 2, 4), (16, 4, 4), (8, 8, 4), (16, 2, 2), (16, 2, 6), (32, 2, 6)]
 
 
 def parse_shape(s):
@@ -58,14 +58,14 @@ def main():
             print(f"box {sh} {size}^2: full {f:.4f} ms | shares of 8: {parts} sum {sum(parts):.3f} max {max(parts):.4f} "
                   f"-> efficiency bound {f / 8 / max(parts):.3f}", flush=True)
     elif mode == "splits":
-        sh = parse_shape(sys.argv[3]) if len(sys.argv) > 3 else (16, 1, 2)
+        sh = parse_shape(sys.argv[3]) if len(sys.argv) > 3 else (16, 2, 4)
         p = lib.default_params(kernel=KERNEL_FILTERED, pixels_per_thread=box_shape(*sh))
-        for zs in (0, 1, 2, 4, 6, 8, 12, 16, 24, 32, 48, 64):
-            ctx.force_splits(zs)
-            print(f"box {sh} slices {zs}: full {full(p):.4f} ms, share 0/8 {share(p, 8, 0):.4f} ms, share 0/4 {share(p, 4, 0):.4f} ms", flush=True)
-        ctx.force_splits(0)
+        for zs in (0, 4, 8, 16, 32, 64, 128):
+            ctx.force_scan_cols(zs)
+            print(f"box {sh} box columns per CTA {zs}: full {full(p):.4f} ms, share 0/8 {share(p, 8, 0):.4f} ms, share 0/4 {share(p, 4, 0):.4f} ms", flush=True)
+        ctx.force_scan_cols(0)
     elif mode == "parts":
-        sh = parse_shape(sys.argv[3]) if len(sys.argv) > 3 else (16, 1, 2)
+        sh = parse_shape(sys.argv[3]) if len(sys.argv) > 3 else (16, 2, 4)
         for kern in (KERNEL_FILTERED, KERNEL_CULLED):
             p = lib.default_params(kernel=kern, pixels_per_thread=box_shape(*sh))
             f = full(p)
