@@ -6,6 +6,7 @@
 //   renderLoop(Image&, meshes, info)    main.cxx:626-743          srt::renderLoop         -> GPU L-buffer + repair
 //   renderLoopCallBack(PThreadData*)    lbuffer.cxx:733-813       srt::XRayRenderer::renderRows (row band)
 //   repair + setPixel loop in main()    lbuffer.cxx:329-404       srt::XRayRenderer::repair
+//   MPI partition + gather              main-mpi.cxx:258-293,854-881   srt::MultiGpuXRayRenderer (one process, N GPUs)
 //
 // All rendering happens in the CUDA kernels of libsrt_b200.so. Failures (no GPU, CUDA errors, bad
 // arguments) throw std::runtime_error carrying srt_last_error(); nothing here computes a frame on the CPU.
@@ -123,6 +124,7 @@ public:
     {
         const detail::FlatMeshes f = detail::flatten(meshes);
         detail::check(srt_set_meshes(ctx_, (int)f.desc.size(), f.desc.data()), ctx_, "srt_set_meshes");
+        detail::check(srt_synchronize(ctx_), ctx_, "srt_synchronize");     // the flattened arrays die with this scope
     }
 
     void setCamera(const RayTracerInfo& info, unsigned int width, unsigned int height)
@@ -159,6 +161,64 @@ public:
 
 private:
     srt_ctx* ctx_ = nullptr;
+    srt_params params_{};
+    srt_camera cam_{};
+};
+
+// One process, several GPUs: the role of the MPI driver (src/main-mpi.cxx:258-293 partition, :854-881 gather).  Every
+// GPU renders its share of 16-row blocks and stores it into the frame of every GPU over NVLink; render() returns the
+// repaired image of the first device, bit-identical to XRayRenderer::render.
+class MultiGpuXRayRenderer {
+public:
+    explicit MultiGpuXRayRenderer(const std::vector<int>& devices)
+    {
+        if (srt_multi_create(&m_, devices.data(), (int)devices.size()) != SRT_OK)
+            throw std::runtime_error(std::string("srt_multi_create: ") + srt_multi_last_error(nullptr));
+        srt_default_params(&params_);
+    }
+    ~MultiGpuXRayRenderer() { srt_multi_destroy(m_); }
+    MultiGpuXRayRenderer(const MultiGpuXRayRenderer&) = delete;
+    MultiGpuXRayRenderer& operator=(const MultiGpuXRayRenderer&) = delete;
+
+    srt_params& params() { return params_; }
+    int deviceCount() const { return srt_multi_device_count(m_); }
+
+    void setMeshes(const std::vector<TriangleMesh>& meshes)
+    {
+        const detail::FlatMeshes f = detail::flatten(meshes);
+        check(srt_multi_set_meshes(m_, (int)f.desc.size(), f.desc.data()), "srt_multi_set_meshes");
+        check(srt_multi_synchronize(m_), "srt_multi_synchronize");           // the flattened arrays die with this scope
+    }
+    void setCamera(const RayTracerInfo& info, unsigned int width, unsigned int height)
+    {
+        for (int k = 0; k < 3; ++k) {
+            cam_.origin[k] = info.origin[k]; cam_.detector[k] = info.detector_position[k];
+            cam_.up[k] = info.up[k]; cam_.right[k] = info.right[k];
+        }
+        const float res1 = info.range[2] / width, res2 = info.range[1] / height;      // lbuffer.cxx:739-741
+        cam_.pixel_spacing[0] = cam_.pixel_spacing[1] = 2 * std::max(res1, res2);
+        cam_.width = width; cam_.height = height;
+        check(srt_multi_set_camera(m_, &cam_), "srt_multi_set_camera");
+    }
+    void render(Image& out)
+    {
+        out.setSize(cam_.width, cam_.height);
+        check(srt_multi_render_xray(m_, &params_, out.getData()), "srt_multi_render_xray");
+    }
+    // device time of the last render: the slowest device's whole step (render + assembly wait + repair), in ms
+    float stepMilliseconds()
+    {
+        float ms = 0.0f;
+        check(srt_multi_last_timing(m_, nullptr, &ms), "srt_multi_last_timing");
+        return ms;
+    }
+
+private:
+    void check(int rc, const char* what) const
+    {
+        if (rc != SRT_OK) throw std::runtime_error(std::string(what) + ": " + srt_multi_last_error(m_));
+    }
+    srt_multi* m_ = nullptr;
     srt_params params_{};
     srt_camera cam_{};
 };

@@ -1,6 +1,8 @@
 // test_host_api.cpp -- checks of the C++ host classes (include/srt/*.h) against the reference's documented
 // behaviour.  `test_host_api cpu` needs no GPU; `test_host_api gpu <ply> <W> <H> <out.txt>` renders through
-// srt::renderLoop (CUDA) and writes the image with Image::saveTextFile.
+// srt::renderLoop (CUDA) and writes the image with Image::saveTextFile; `test_host_api gpu-multi <ply> <W> <H> <out.txt>
+// [n_gpus]` does the same on all (or the first n) visible GPUs through srt::MultiGpuXRayRenderer and checks that the image
+// equals the single-GPU one bit for bit.
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -121,6 +123,34 @@ int main(int argc, char** argv)
             image.saveTextFile(argv[5]);
             std::printf("OK %zu triangles\n", meshes[0].getNumberOfTriangles());
             return 0;
+        } catch (const std::exception& e) { std::printf("ERROR: %s\n", e.what()); return 1; }
+    }
+    if (argc >= 6 && std::strcmp(argv[1], "gpu-multi") == 0) {
+        try {
+            std::vector<srt::TriangleMesh> meshes;
+            srt::loadMeshes(argv[2], meshes);
+            const unsigned W = (unsigned)std::atoi(argv[3]), H = (unsigned)std::atoi(argv[4]);
+            srt::Vec3 lo, hi; srt::getBBox(meshes, hi, lo);
+            srt::Image single, multi;
+            srt::RayTracerInfo info = srt::initialiseRayTracing(meshes, hi, lo, H, W, single, 0.0f);
+            srt::renderLoop(single, meshes, info);                               // GPU 0 alone
+            int n = 0;
+            while (n < 8) { srt_ctx* c = nullptr; if (srt_create(&c, n) != SRT_OK) break; srt_destroy(c); ++n; }
+            if (argc >= 7) n = std::min(n, std::atoi(argv[6]));
+            if (n < 1) { std::printf("ERROR: no GPU\n"); return 1; }
+            std::vector<int> devices(n);
+            for (int i = 0; i < n; ++i) devices[i] = i;
+            srt::MultiGpuXRayRenderer r(devices);
+            r.setMeshes(meshes);
+            r.setCamera(info, W, H);
+            for (int rep = 0; rep < 3; ++rep) r.render(multi);                   // both frame sets get used
+            const float ms = r.stepMilliseconds();
+            size_t diff = 0;
+            for (size_t i = 0; i < (size_t)W * H; ++i)
+                diff += std::memcmp(single.getData() + i, multi.getData() + i, sizeof(float)) != 0;
+            multi.saveTextFile(argv[5]);
+            std::printf("%s %d GPUs, %zu differing pixels, step %.3f ms\n", diff ? "MISMATCH" : "OK", n, diff, ms);
+            return diff ? 1 : 0;
         } catch (const std::exception& e) { std::printf("ERROR: %s\n", e.what()); return 1; }
     }
     if (argc >= 3 && std::strcmp(argv[1], "ply") == 0) {
