@@ -9,7 +9,9 @@
  *   reference interface                                     replaced by
  *   ------------------------------------------------------  ---------------------------
  *   renderLoop(Image&, const vector<TriangleMesh>&,         srt_set_meshes + srt_set_camera
- *              RayTracerInfo&)            src/main.cxx:159-161,626      + srt_render_xray
+ *              RayTracerInfo&)            src/main.cxx:159-161,626      + srt_render_xray_sorted (the driver's own
+ *                                                                       sort-based image) or srt_render_xray (the
+ *                                                                       L-buffer image of main-pthreads-lbuffer)
  *   void* renderLoopCallBack(void* PThreadData*)            srt_render_lbuffer (row band)
  *              src/main-pthreads-lbuffer.cxx:186,733-813
  *   global std::vector<float> L_buffer    ...lbuffer.cxx:254,314        L_out of srt_render_lbuffer
@@ -216,6 +218,15 @@ int  srt_repair_device(srt_ctx* ctx, const srt_params* params, const float* dL_i
  * (what renderLoop + the output loop of main() produce; Image::getData layout). */
 int  srt_render_xray(srt_ctx* ctx, const srt_params* params, float* image_out);
 
+/* ---- sort-based X-ray (the serial driver, src/main.cxx:626-743; what produced out/dragon-128x128-serial.txt) ----
+ * Per ray: the intersection distances t > 1e-7 with mesh 0 are sorted, exit - entry pairs summed (an odd count counts
+ * as no path, :714-718), image = incident * exp(-(mu0 * (d * length_to_cm))) in the reference's float / double mix
+ * (mu0 = meshes[0].mu: the driver hard-codes 0.3971f).  No artefact flag, no repair pass.  Runs on the filtered path
+ * (srt_params.kernel AUTO / FILTERED / CULLED are all served by it). */
+int  srt_render_xray_sorted(srt_ctx* ctx, const srt_params* params, float* image_out);
+int  srt_render_xray_sorted_device(srt_ctx* ctx, const srt_params* params, float* d_image, float* d_path_len_or_null,
+                                   uint32_t* d_hit_count_or_null);
+
 /* ---- one process, N GPUs (replaces the MPI driver, src/main-mpi.cxx:258-293 partition + :854-881 gather) ----
  *
  * srt_multi owns one context per device.  A frame is rendered in block-cyclic 16-row blocks (device i renders blocks
@@ -264,6 +275,9 @@ int  srt_last_timing(srt_ctx* ctx, srt_timing* out);
 int  srt_debug_count_exact(srt_ctx* ctx, int enable);
 /* Diagnostic: force the number of box columns a CTA of the filtered kernel covers (grid.x granularity); 0 = heuristic. */
 int  srt_debug_force_scan_cols(srt_ctx* ctx, int cols);
+/* Diagnostic: cap the per-bin triangle lists of the culled kernel and the two candidate lists of the filtered path
+ * (entries; 0 = no cap).  Overflowing lists fall back to exact but slow paths; tests use this to exercise them. */
+int  srt_debug_force_list_caps(srt_ctx* ctx, uint32_t bin_cap, uint32_t cand_cap, uint32_t pix_cap);
 /* Diagnostic: measured FP32 FMA throughput of the context's GPU in TFLOP/s. */
 int  srt_debug_ffma_peak(srt_ctx* ctx, int repeats, float* tflops_out);
 /* Diagnostic: padding granularity of packed meshes (triangles) and the default box of the filtered kernel. */

@@ -3,7 +3,8 @@
 //   reference                                                     here
 //   getBBox(meshes, upper, lower)       lbuffer.cxx:585-608       srt::getBBox            -> srt_scene_bbox
 //   initialiseRayTracing(...)           lbuffer.cxx:611-667       srt::initialiseRayTracing -> srt_camera_from_bbox
-//   renderLoop(Image&, meshes, info)    main.cxx:626-743          srt::renderLoop         -> GPU L-buffer + repair
+//   renderLoop(Image&, meshes, info)    main.cxx:626-743          srt::renderLoop         -> srt_render_xray_sorted
+//   main() of the L-buffer driver       lbuffer.cxx:258-423       srt::renderLoopLBuffer  -> srt_render_xray (L-buffer + repair)
 //   renderLoopCallBack(PThreadData*)    lbuffer.cxx:733-813       srt::XRayRenderer::renderRows (row band)
 //   repair + setPixel loop in main()    lbuffer.cxx:329-404       srt::XRayRenderer::repair
 //   MPI partition + gather              main-mpi.cxx:258-293,854-881   srt::MultiGpuXRayRenderer (one process, N GPUs)
@@ -262,8 +263,21 @@ inline void renderLoop(ImageRGB& anOutputImage, const std::vector<TriangleMesh>&
     detail::check(srt_render_shaded(r.handle(), &r.params(), &light, bg, anOutputImage.getData()), r.handle(), "srt_render_shaded");
 }
 
-// Drop-in for the reference's renderLoop (src/main.cxx:159-161): X-ray image of the scene on GPU 0.
+// Drop-in for the serial driver's renderLoop (src/main.cxx:159-161, 626-743): the SORT-based X-ray image of the scene on
+// GPU 0 -- per ray the intersections with mesh 0 are sorted and exit - entry pairs summed, 80 exp(-(0.3971 d / 10)).
+// This is the function that produced out/dragon-128x128-serial.txt.
 inline void renderLoop(Image& anOutputImage, const std::vector<TriangleMesh>& aTriangleMeshSet, RayTracerInfo& rayTracerInfo)
+{
+    XRayRenderer r(0);
+    const detail::FlatMeshes f = detail::flatten(aTriangleMeshSet, /*mu0: main.cxx:739*/ 0.3971f, 0.3971f);
+    detail::check(srt_set_meshes(r.handle(), (int)f.desc.size(), f.desc.data()), r.handle(), "srt_set_meshes");
+    r.setCamera(rayTracerInfo, anOutputImage.getWidth(), anOutputImage.getHeight());
+    detail::check(srt_render_xray_sorted(r.handle(), &r.params(), anOutputImage.getData()), r.handle(), "srt_render_xray_sorted");
+}
+
+// The flow of main-pthreads-lbuffer.cxx (render callback :733-813 over all pixels + repair / image fill :329-404): the
+// L-buffer X-ray image (signed path-length sum, artefact flag, Beer-Lambert with mu = 0.1037 / 0.3971, repair).
+inline void renderLoopLBuffer(Image& anOutputImage, const std::vector<TriangleMesh>& aTriangleMeshSet, RayTracerInfo& rayTracerInfo)
 {
     XRayRenderer r(0);
     r.setMeshes(aTriangleMeshSet);

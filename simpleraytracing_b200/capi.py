@@ -61,8 +61,8 @@ EXPORTS = [
     "srt_set_meshes", "srt_set_camera", "srt_render_lbuffer", "srt_render_lbuffer_device", "srt_repair",
     "srt_repair_device", "srt_render_xray", "srt_interleave_slot_rows",
     "srt_render_lbuffer_interleaved_device", "srt_deinterleave_device", "srt_render_lbuffer_blocks_device", "srt_render_shaded",
-    "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_force_scan_cols", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_pack_info", "srt_debug_download_packed",
-    "srt_host_alloc", "srt_host_free",
+    "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_force_scan_cols", "srt_debug_force_list_caps", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_pack_info", "srt_debug_download_packed",
+    "srt_host_alloc", "srt_host_free", "srt_render_xray_sorted", "srt_render_xray_sorted_device",
     "srt_multi_create", "srt_multi_destroy", "srt_multi_last_error", "srt_multi_device_count", "srt_multi_set_meshes",
     "srt_multi_set_camera", "srt_multi_render_xray_device", "srt_multi_synchronize", "srt_multi_frame",
     "srt_multi_render_xray", "srt_multi_last_timing",
@@ -121,10 +121,13 @@ class Library:
         L.srt_last_timing.argtypes = [vp, C.POINTER(Timing)]
         L.srt_debug_count_exact.argtypes = [vp, i32]
         L.srt_debug_force_scan_cols.argtypes = [vp, i32]
+        L.srt_debug_force_list_caps.argtypes = [vp, u32, u32, u32]
         L.srt_debug_download_packed.argtypes = [vp, i32, vp, vp, vp]
         L.srt_debug_pack_info.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
         L.srt_debug_ffma_peak.argtypes = [vp, i32, C.POINTER(C.c_float)]
         L.srt_debug_prepack.argtypes = [vp, u32, C.POINTER(Camera), u32, u32, vp, vp, vp, C.POINTER(u32), C.POINTER(u32)]
+        L.srt_render_xray_sorted.argtypes = [vp, C.POINTER(Params), vp]
+        L.srt_render_xray_sorted_device.argtypes = [vp, C.POINTER(Params), vp, vp, vp]
         L.srt_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         L.srt_host_free.argtypes = [vp]
         L.srt_host_free.restype = None
@@ -292,6 +295,9 @@ class Context:
     def force_scan_cols(self, cols):
         self._ck(self.lib.srt_debug_force_scan_cols(self.h, int(cols)))
 
+    def force_list_caps(self, bin_cap=0, cand_cap=0, pix_cap=0):
+        self._ck(self.lib.srt_debug_force_list_caps(self.h, bin_cap, cand_cap, pix_cap))
+
     def count_exact(self, on=True):
         self._ck(self.lib.srt_debug_count_exact(self.h, int(on)))
 
@@ -363,6 +369,17 @@ class Context:
         img = np.empty(n, np.float32) if out is None else out
         self._ck(self.lib.srt_render_xray(self.h, C.byref(params), _ptr(img, np.float32)))
         return img
+
+    def render_xray_sorted(self, params, out=None):
+        """Sort-based X-ray image of src/main.cxx (no repair pass) -> float32 [H*W]"""
+        n = self.cam.width * self.cam.height
+        img = np.empty(n, np.float32) if out is None else out
+        self._ck(self.lib.srt_render_xray_sorted(self.h, C.byref(params), _ptr(img, np.float32)))
+        return img
+
+    def render_xray_sorted_device(self, params, d_image, d_path=0, d_hits=0):
+        self._ck(self.lib.srt_render_xray_sorted_device(self.h, C.byref(params), C.c_void_p(d_image), C.c_void_p(d_path or None),
+                                                        C.c_void_p(d_hits or None)))
 
     def download_packed(self, mesh, n):
         pad = self.L.pack_info()[0]

@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(128) exact_tests_kernel(const __grid_constant_
             if (!((double)tt > 0.0000001)) continue;                       // lbuffer.cxx:788
             const float dn = dot_rn(r.ax, r.ay, r.az, Dn.y, Dn.z, Dn.w);   // direction . normal, pre-Ray direction
             val = __fmul_rn((float)((0.0f < dn) - (dn < 0.0f)), tt);       // sign * t
-        }
+        } else if (a.mode == 2 && !((double)tt > 0.0000001)) continue;     // sort mode keeps t itself (main.cxx:687)
         const size_t p = (size_t)out_row(a, row) * W + col;
         const uint32_t slot = atomicAdd(a.hit_counts + p, 1u);
         if (slot < a.hit_cap) a.hit_entries[p * a.hit_cap + slot] = make_uint2(Mp->first + tri, __float_as_uint(val));
@@ -525,9 +525,75 @@ __global__ void __launch_bounds__(128) exact_tests_kernel(const __grid_constant_
 // attenuation (lbuffer.cxx:768-809), or the z-buffer update of the shaded drivers (main-omp.cxx:656-662), in ascending
 // triangle order.  It also resets the pixel's slot counter for the next render.  A list that overflowed its capacity is
 // recomputed from scratch with the exact sequence over all triangles (rare; keeps the result exact).
+// std::exp(float) of the reference's build == glibc's expf (sysdeps/ieee754/flt-32/e_expf.c; the exp2f algorithm of the
+// ARM optimized routines): x N / ln2 = k + r in double, 2^(k/N) from a 32-entry table, a cubic in r, one narrowing.  Its
+// result is the correctly rounded float in all but ~0.06 % of the arguments; restating the algorithm (table entry i =
+// bits(2^(i/32)) - (i << 47), coefficients as published) reproduces those too -- checked against the libm of the build
+// container on 200 000 arguments (tools/check_expf.py).
+__device__ const unsigned long long kExp2fTab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull,
+};
+
+__device__ __forceinline__ float expf_glibc(float x)
+{
+    const uint32_t abstop = (__float_as_uint(x) >> 20) & 0x7ffu;
+    if (abstop >= 0x42bu) {                                   // |x| >= 88 or NaN
+        if (__float_as_uint(x) == 0xff800000u) return 0.0f;
+        if (abstop >= 0x7f8u) return x + x;
+        if (x > 88.72283172607421875f) return INFINITY;       // 0x1.62e42ep6f
+        if (x < -103.972076416015625f) return 0.0f;           // -0x1.9fe368p6f
+    }
+    const double N = 32.0;
+    const double z = __dmul_rn(0x1.71547652b82fep+0 * N, (double)x);
+    double kd = __dadd_rn(z, 0x1.8p+52);
+    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    kd = __dsub_rn(kd, 0x1.8p+52);
+    const double r = __dsub_rn(z, kd);
+    const unsigned long long t = kExp2fTab[ki % 32] + (ki << 47);
+    const double s = __longlong_as_double((long long)t);
+    const double c0 = 0x1.c6af84b912394p-5 / N / N / N, c1 = 0x1.ebfce50fac4f3p-3 / N / N, c2 = 0x1.62e42ff0c52d6p-1 / N;
+    const double p = __dadd_rn(__dmul_rn(c0, r), c1);
+    const double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(c2, r), 1.0);
+    y = __dadd_rn(__dmul_rn(p, r2), y);
+    y = __dmul_rn(y, s);
+    return (float)y;
+}
+
 constexpr uint32_t kMaxHitCap = 16;
+constexpr uint32_t kSortOverflowCap = 256;     // sort mode: intersections of one ray the overflow path can order
+
+// Sort-based X-ray value of one pixel (src/main.cxx:700-741): the ray's intersection distances t (mesh 0, t > 1e-7) are
+// sorted, exit - entry pairs are summed in float, an odd count counts as no path (:714-718), then
+// `distance = distance * 0.1` (double product, narrowed) and `80.000f * exp(-(0.3971f * distance))` with std::exp(float)
+// (expf_glibc above).
+__device__ float sorted_xray_value(float* t, uint32_t n, float incident, float mu, double length_to_cm, float& path)
+{
+    float distance = 0.0f;
+    if (n > 0 && (n & 1u) == 0) {
+        for (uint32_t i = 1; i < n; ++i) {                  // std::sort: ascending; ties are interchangeable values
+            const float key = t[i];
+            uint32_t j = i;
+            while (j > 0 && t[j - 1] > key) { t[j] = t[j - 1]; --j; }
+            t[j] = key;
+        }
+        for (uint32_t i = 0; i < n; i += 2) distance = __fadd_rn(distance, __fsub_rn(t[i + 1], t[i]));    // :706-708
+    }
+    path = distance;
+    distance = (float)((double)distance * length_to_cm);                                              // :725
+    return __fmul_rn(incident, expf_glibc(-__fmul_rn(mu, distance)));                                  // :739
+}
+
 __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant__ RenderArgs a)
 {
+    __shared__ float s_sort[8][kSortOverflowCap];
     const uint32_t W = a.cam.W;
     const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t by = blockIdx.y >> 4, lrow = blockIdx.y & 15u;
@@ -537,7 +603,7 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
     const size_t p = (size_t)orow * W + (valid ? col : 0);
     float L = a.incident;
     float dist0 = 0.0f; int ssum0 = 0; uint32_t hits0 = 0;   // mode 1: z-buffer value / triangle index
-    if (a.mode != 0) { dist0 = INFINITY; ssum0 = -1; }
+    if (a.mode == 1) { dist0 = INFINITY; ssum0 = -1; }
     const bool list_lost = a.cand_count[0] > a.cand_cap || a.cand_count[1] > a.pix_cap;   // a candidate list overflowed: no hit list can be trusted
     bool overflow = false;
     if (valid) {
@@ -553,7 +619,12 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
                 while (j > 0 && e[j - 1].x > key.x) { e[j] = e[j - 1]; --j; }
                 e[j] = key;
             }
-            if (a.mode != 0) {
+            if (a.mode == 2) {
+                float t[kMaxHitCap];
+                for (uint32_t i = 0; i < n; ++i) t[i] = __uint_as_float(e[i].y);
+                L = sorted_xray_value(t, n, a.incident, a.meshes[0].mu, a.length_to_cm, dist0);
+                ssum0 = 0; hits0 = n;
+            } else if (a.mode != 0) {
                 for (uint32_t i = 0; i < n; ++i) {
                     const float t = __uint_as_float(e[i].y);
                     if (dist0 > t) { dist0 = t; ssum0 = (int)e[i].x; }      // strict >: the first of equal t wins
@@ -575,6 +646,10 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
                     if (m == 0) { dist0 = dist; ssum0 = ssum; hits0 = hits; }
                 }
             }
+        } else if (a.mode == 2 && !overflow) {
+            float none[1];
+            L = sorted_xray_value(none, 0, a.incident, a.meshes[0].mu, a.length_to_cm, dist0);
+            ssum0 = 0;
         } else if (a.mode == 0 && !overflow) {
             // no hit in any mesh: L *= exp(-(mu * (0 * 0.1))) == L exactly, unless mu or the unit factor is not finite
             for (int m = 0; m < a.n_meshes; ++m) {
@@ -593,7 +668,9 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
         todo &= todo - 1;
         const uint32_t prow = __shfl_sync(0xffffffffu, row, src), pcol = __shfl_sync(0xffffffffu, col, src);
         const RayDirs r = make_ray(a.cam, prow, pcol);
-        float Lc = a.incident, d0 = a.mode ? INFINITY : 0.0f; int s0 = a.mode ? -1 : 0; uint32_t h0 = 0;
+        float Lc = a.incident, d0 = a.mode == 1 ? INFINITY : 0.0f; int s0 = a.mode == 1 ? -1 : 0; uint32_t h0 = 0;
+        float* ts = s_sort[threadIdx.x >> 5];               // sort mode: the ray's distances, in the warp's scratch
+        uint32_t n_sort = 0;
         for (int m = 0; m < a.n_meshes; ++m) {
             const DevMesh M = a.meshes[m];
             float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
@@ -607,7 +684,8 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
                         const float4 C = __ldg(M.exact + 4 * (size_t)j + 2), Dn = __ldg(M.exact + 4 * (size_t)j + 3);
                         float t;
                         if (exact_intersect(r, A, B, C, Dn.x, t)) {
-                            if (a.mode != 0) { st = t; got = true; }
+                            if (a.mode == 1) { st = t; got = true; }
+                            else if (a.mode == 2) { st = t; got = (double)t > 0.0000001; }
                             else if ((double)t > 0.0000001) {
                                 const float dn = dot_rn(r.ax, r.ay, r.az, Dn.y, Dn.z, Dn.w);
                                 st = __fmul_rn((float)((0.0f < dn) - (dn < 0.0f)), t);
@@ -620,7 +698,8 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
                         const int l = __ffs(hm) - 1;
                         hm &= hm - 1;
                         const float v = __shfl_sync(0xffffffffu, st, l);
-                        if (a.mode != 0) { if (d0 > v) { d0 = v; s0 = (int)(M.first + base + (uint32_t)l); } }
+                        if (a.mode == 1) { if (d0 > v) { d0 = v; s0 = (int)(M.first + base + (uint32_t)l); } }
+                        else if (a.mode == 2) { if (n_sort < kSortOverflowCap && lane == 0) ts[n_sort] = v; ++n_sort; }
                         else { dist = __fadd_rn(dist, v); ssum += (0.0f < v) - (v < 0.0f); ++hits; }
                     }
                 }
@@ -629,10 +708,21 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
             Lc = attenuate(Lc, M.mu, dist, ssum, a.length_to_cm);
             if (m == 0) { d0 = dist; s0 = ssum; h0 = hits; }
         }
+        if (a.mode == 2) {
+            __syncwarp();
+            if ((int)lane == src) {
+                // more intersections on one ray than the scratch holds: not representable here (NaN, never a wrong number)
+                if (n_sort > kSortOverflowCap) { L = NAN; dist0 = NAN; }
+                else L = sorted_xray_value(ts, n_sort, a.incident, a.meshes[0].mu, a.length_to_cm, dist0);
+                ssum0 = 0; hits0 = n_sort;
+            }
+            __syncwarp();
+            continue;
+        }
         if ((int)lane == src) { L = Lc; dist0 = d0; ssum0 = s0; hits0 = h0; }
     }
     if (!valid) return;
-    if (a.mode == 0) store_L(a, a.L_image ? (size_t)row * W + col : p, L);
+    if (a.mode != 1) store_L(a, a.L_image ? (size_t)row * W + col : p, L);
     if (a.dist) a.dist[p] = dist0;
     if (a.ssum) a.ssum[p] = ssum0;
     if (a.hits) a.hits[p] = hits0;
@@ -668,7 +758,11 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(const __grid_constant_
     const uint32_t r1 = min(a.row_end, a.row_begin + (b1 * a.blk_stride + a.blk_phase) * 16 + 16) - 1;
     const float xc = 0.5f * (float)(c0 + c1) + a.cam.xc, hx = 0.5f * (float)(c1 - c0);
     const float yc = 0.5f * (float)(r0 + r1) + a.cam.yc, hy = 0.5f * (float)(r1 - r0);
-    uint32_t* out = a.bin_entries + (size_t)bin * a.bin_cap + M.first;
+    // the mesh's share of the bin's list: proportional to its triangle count; survivors beyond it are counted but not
+    // stored, and the render pass then walks the whole mesh for this bin (count > capacity)
+    const uint32_t off_m = (uint32_t)((uint64_t)M.first * a.bin_cap / a.total_tris);
+    const uint32_t cap_m = (uint32_t)((uint64_t)(M.first + M.n) * a.bin_cap / a.total_tris) - off_m;
+    uint32_t* out = a.bin_entries + (size_t)bin * a.bin_cap + off_m;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t base = 0;
     uint32_t j = threadIdx.x;
@@ -690,7 +784,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_kernel(const __grid_constant_
         for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, v, o); if ((int)lane >= o) v += u; }
         const uint32_t total = __shfl_sync(0xffffffffu, v, 31);
         const uint32_t before = warp ? __shfl_sync(0xffffffffu, v, (int)warp - 1) : 0u;
-        if (keep) out[base + before + __popc(bal & ((1u << lane) - 1u))] = j;
+        if (keep) { const uint32_t pos = base + before + __popc(bal & ((1u << lane) - 1u)); if (pos < cap_m) out[pos] = j; }
         base += total;
         j = jn;
         __syncthreads();                                       // warp_cnt is rewritten next iteration
@@ -842,15 +936,19 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
             sa.queue = s_queue[warp]; sa.acc = acc; sa.wrow0 = wrow0; sa.wcol0 = wcol0;
             sa.col_end = active ? rc1 - col0 + 1 : 0u;
             sa.run_xc = 0.5f * (float)(col0 + rc1) + a.cam.xc; sa.run_hx = active ? 0.5f * (float)(rc1 - col0) : 0.0f;
-            const uint32_t cnt = __ldg(a.bin_counts + (size_t)bin * a.n_meshes + m);
-            const uint32_t* list = a.bin_entries + (size_t)bin * a.bin_cap + M.first;
+            const uint32_t off_m = (uint32_t)((uint64_t)M.first * a.bin_cap / a.total_tris);
+            const uint32_t cap_m = (uint32_t)((uint64_t)(M.first + M.n) * a.bin_cap / a.total_tris) - off_m;
+            const uint32_t listed = __ldg(a.bin_counts + (size_t)bin * a.n_meshes + m);
+            const bool whole_mesh = listed > cap_m;                  // the bin's list overflowed: every triangle is a candidate
+            const uint32_t cnt = whole_mesh ? M.n : listed;
+            const uint32_t* list = a.bin_entries + (size_t)bin * a.bin_cap + off_m;
 #if SRT_CULLED_CTA_LIST
             // Phase A (whole CTA, equal work per warp): cull the bin's list against the CTA tile, 128 entries per step, into
             // an ordered index list in shared memory.  Phase B (warps independent): each warp culls that short list against
             // its own 32 x 8 tile and processes the survivors.  A list longer than kCtaList is handled in rounds.
             uint32_t idx = 0; float4 fa, fb, ga, gb;
             if (tid < cnt) {
-                idx = __ldg(list + tid);
+                idx = (whole_mesh ? tid : __ldg(list + tid));
                 const float4* q0 = M.filt0 + 3 * (size_t)idx; const float4* q1 = M.filt1 + 2 * (size_t)idx;
                 fa = __ldg(q0); fb = __ldg(q0 + 1); ga = __ldg(q1); gb = __ldg(q1 + 1);
             }
@@ -862,7 +960,7 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
                     const uint32_t my_idx = idx;
                     const uint32_t in = i0 + 128 + tid;                       // next step's records in flight
                     if (in < cnt) {
-                        idx = __ldg(list + in);
+                        idx = (whole_mesh ? in : __ldg(list + in));
                         const float4* q0 = M.filt0 + 3 * (size_t)idx; const float4* q1 = M.filt1 + 2 * (size_t)idx;
                         fa = __ldg(q0); fb = __ldg(q0 + 1); ga = __ldg(q1); gb = __ldg(q1 + 1);
                     }
@@ -912,7 +1010,7 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
             // software pipeline: the next 32 entries' records are in flight while the current ones are processed
             uint32_t idx = 0; float4 fa, fb, ga, gb;
             if (lane < cnt) {
-                idx = __ldg(list + lane);
+                idx = (whole_mesh ? lane : __ldg(list + lane));
                 const float4* q0 = M.filt0 + 3 * (size_t)idx; const float4* q1 = M.filt1 + 2 * (size_t)idx;
                 fa = __ldg(q0); fb = __ldg(q0 + 1); ga = __ldg(q1); gb = __ldg(q1 + 1);
             }
@@ -929,7 +1027,7 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
                 }
                 const uint32_t in = i0 + 32 + lane;
                 if (in < cnt) {
-                    idx = __ldg(list + in);
+                    idx = (whole_mesh ? in : __ldg(list + in));
                     const float4* q0 = M.filt0 + 3 * (size_t)idx; const float4* q1 = M.filt1 + 2 * (size_t)idx;
                     fa = __ldg(q0); fb = __ldg(q0 + 1); ga = __ldg(q1); gb = __ldg(q1 + 1);
                 }

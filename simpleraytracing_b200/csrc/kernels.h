@@ -60,6 +60,8 @@ struct RenderArgs {
     // mode 0: X-ray L-buffer (above).  mode 1: closest hit over all meshes (shaded variant, main-omp.cxx:632-666):
     // `dist` receives the z-buffer value t (+inf = no hit), `ssum` the scene-wide triangle index (-1 = none);
     // strict `z > t` in ascending triangle order => the first of equal t wins, negative t is accepted.
+    // mode 2 (filtered path only): sort-based X-ray of src/main.cxx:626-743: the ray's t > 1e-7 of the contributing meshes
+    // are sorted and exit - entry pairs summed; `L` receives 80 exp(-(mu0 d / 10)), `dist` the path length d, `hits` the count.
     int mode;
     // Filtered kernel.  A thread holds scan_k triangles and tests them against boxes of box_px x box_py pixels
     // (FilterTri::R / R2 are packed for that box); a CTA covers the box rows of one 16-row block x scan_cols box columns
@@ -78,11 +80,12 @@ struct RenderArgs {
     uint32_t* hit_counts;    // [pixel]: entries appended (may exceed hit_cap: overflow -> exact recompute); zero between renders
     uint32_t hit_cap;
     // Culled kernel (SRT_KERNEL_CULLED): per-bin triangle lists.  A bin is kBinCols columns x bin_blocks 16-row blocks
-    // of this launch's grid; bin_entries[bin * bin_cap + M.first + i], i < bin_counts[bin * n_meshes + m], are the
+    // of this launch's grid; bin_entries[bin * bin_cap + off_m + i], i < bin_counts[bin * n_meshes + m] (off_m: the mesh's
+    // proportional share of the bin_cap entries of a bin; a count above the share = "walk the whole mesh"), are the
     // indices (within mesh m, ascending) of the triangles whose conservative footprint may touch the bin.
     uint32_t* bin_entries;
     uint32_t* bin_counts;
-    uint32_t bin_cap, bin_blocks, bins_x, bins_y;
+    uint32_t bin_cap, bin_blocks, bins_x, bins_y, total_tris;
 };
 constexpr uint32_t kBinCols = 256;     // bin width in pixels (4 CTA tiles of the culled kernel)
 cudaError_t launch_resolve_hits(const RenderArgs& a, cudaStream_t s);

@@ -106,6 +106,7 @@ struct srt_ctx {
     uint2* d_cand = nullptr; uint2* d_pix = nullptr; uint32_t* d_cand_count = nullptr; uint32_t cand_cap = 0, pix_cap = 0;
     uint32_t* h_cand_count = nullptr;    // [0] box list, [1] pixel list
     int force_scan_cols = 0;             // diagnostic override of the box columns per CTA: 0 = heuristic
+    uint32_t force_bin_cap = 0, force_cand_cap = 0, force_pix_cap = 0;    // diagnostic: shrink the lists to exercise the overflow paths
     // per-bin triangle lists of the culled kernel
     uint32_t* d_bin_entries = nullptr; uint32_t* d_bin_counts = nullptr; size_t bin_entries_cap = 0, bin_counts_cap = 0;
     bool counters_pending = false, timing_pending = false;
@@ -283,7 +284,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
                   bool multicast = false)
 {
     if (!params) return fail(c, SRT_ERR_INVALID, "params is NULL");
-    if (mode == 0 && !dL) return fail(c, SRT_ERR_INVALID, "L buffer is NULL");
+    if (mode != 1 && !dL) return fail(c, SRT_ERR_INVALID, "L buffer is NULL");
     if (mode == 1 && (!d_dist || !d_ssum)) return fail(c, SRT_ERR_INVALID, "closest-hit pass needs z and id buffers");
     if (n_extra > 7 || (n_extra && !extra_frames)) return fail(c, SRT_ERR_INVALID, "at most 7 extra frames");
     uint32_t kernel = params->kernel;
@@ -346,22 +347,32 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
 
     if (kernel == SRT_KERNEL_AUTO) kernel = SRT_KERNEL_CULLED;          // falls back below when it does not apply
     if (!c->filterable) kernel = SRT_KERNEL_EXACT;                        // camera outside the filter's preconditions
+    if (mode == 2) {
+        // the sort mode lives on the hit lists of the filtered path (an unfilterable camera lets every box through:
+        // the lists overflow and the resolve pass orders each ray's intersections itself -- slow, still exact)
+        if (params->kernel == SRT_KERNEL_EXACT || audit) return fail(c, SRT_ERR_INVALID, "the sort-based X-ray runs on SRT_KERNEL_FILTERED");
+        kernel = SRT_KERNEL_FILTERED;
+    }
     if (kernel == SRT_KERNEL_CULLED) {
         // Bins: 256 columns x 8 row blocks (128 rows) of a contiguous band; with block-cyclic rows the blocks of a rank
-        // are `parts` blocks apart, so a bin is one block tall.  Lists: one slot per scene triangle per bin (worst case
-        // always fits, no counting pass); above 8 GB the per-pair filtered kernel is used instead.
+        // are `parts` blocks apart, so a bin is one block tall.  Lists: up to one slot per scene triangle per bin, capped
+        // so that all lists together stay within 1 GiB (the 998 000-triangle sphere at 8192^2 has 2 048 bins: 131 072
+        // slots each, ~15 000 used); a bin whose list overflows its share is rendered from the whole mesh instead.
         a.bin_blocks = a.blk_stride > 1 ? 1u : 8u;
         a.bins_x = (cam.width + srt::kBinCols - 1) / srt::kBinCols;
         a.bins_y = (a.n_blocks + a.bin_blocks - 1) / a.bin_blocks;
-        a.bin_cap = (uint32_t)c->total_tris;
         const size_t bins = (size_t)a.bins_x * a.bins_y;
-        if (bins * c->total_tris * 4ull > (8ull << 30) || c->total_tris >= (1ull << 32)) kernel = SRT_KERNEL_FILTERED;
+        if (c->total_tris >= (1ull << 32) || c->total_tris == 0) kernel = SRT_KERNEL_FILTERED;
         else if (bins > 0) {
-            if (bins * c->total_tris > c->bin_entries_cap) {
+            const uint64_t budget = (1ull << 30) / 4;                                      // entries
+            const uint64_t per_bin = std::max<uint64_t>(std::min<uint64_t>(c->total_tris, budget / bins), std::min<uint64_t>(c->total_tris, 4096));
+            a.bin_cap = (uint32_t)per_bin; a.total_tris = (uint32_t)c->total_tris;
+            if (c->force_bin_cap) a.bin_cap = std::min<uint32_t>(a.bin_cap, c->force_bin_cap);
+            if (bins * per_bin > c->bin_entries_cap) {
                 SRT_CUDA(c, cudaStreamSynchronize(c->stream));
                 cudaFree(c->d_bin_entries); c->d_bin_entries = nullptr; c->bin_entries_cap = 0;
-                SRT_CUDA(c, cudaMalloc(&c->d_bin_entries, bins * c->total_tris * 4ull));
-                c->bin_entries_cap = bins * c->total_tris;
+                SRT_CUDA(c, cudaMalloc(&c->d_bin_entries, bins * per_bin * 4ull));
+                c->bin_entries_cap = bins * per_bin;
             }
             if (bins * c->n_meshes > c->bin_counts_cap) {
                 SRT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -434,6 +445,8 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         if (!c->d_cand_count) SRT_CUDA(c, cudaMalloc(&c->d_cand_count, 2 * sizeof(uint32_t)));
         SRT_CUDA(c, cudaMemsetAsync(c->d_cand_count, 0, 2 * sizeof(uint32_t), c->stream));
         a.cand = c->d_cand; a.pix = c->d_pix; a.cand_count = c->d_cand_count; a.cand_cap = c->cand_cap; a.pix_cap = c->pix_cap;
+        if (c->force_cand_cap) a.cand_cap = std::min(a.cand_cap, c->force_cand_cap);
+        if (c->force_pix_cap) a.pix_cap = std::min(a.pix_cap, c->force_pix_cap);
         if (c->n_meshes > 32 || c->total_tris >= (1ull << 27)) kernel = SRT_KERNEL_EXACT;     // candidate entries: 5-bit mesh, 27-bit triangle
     }
     SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
@@ -828,6 +841,34 @@ int srt_render_xray(srt_ctx* c, const srt_params* p, float* image_out)
     return SRT_OK;
 }
 
+// ---- sort-based X-ray (src/main.cxx:626-743) -------------------------------------------------
+int srt_render_xray_sorted_device(srt_ctx* c, const srt_params* p, float* d_image, float* d_path_len, uint32_t* d_hit_count)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (!p || !d_image) return fail(c, SRT_ERR_INVALID, "params / image is NULL");
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    return render_device(c, p, 0, c->camera.height, d_image, d_path_len, nullptr, d_hit_count, 0, 0, /*mode*/ 2);
+}
+
+int srt_render_xray_sorted(srt_ctx* c, const srt_params* p, float* image_out)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (!p || !image_out) return fail(c, SRT_ERR_INVALID, "params / image_out is NULL");
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    const size_t pixels = (size_t)c->camera.width * c->camera.height;
+    int rc = ensure_frame(c, pixels);
+    if (rc) return rc;
+    rc = render_device(c, p, 0, c->camera.height, c->d_img, nullptr, nullptr, nullptr, 0, 0, /*mode*/ 2);
+    if (rc) return rc;
+    SRT_CUDA(c, cudaMemcpyAsync(image_out, c->d_img, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
+    c->timing.repair_ms = 0.0f;
+    return SRT_OK;
+}
+
 // ---- shaded variant ------------------------------------------------------------------------
 int srt_render_shaded_device(srt_ctx* c, const srt_params* p, const srt_light* light, const uint8_t background_rgb[3],
                              uint8_t* d_rgb, uint8_t* d_shadow)
@@ -996,6 +1037,15 @@ int srt_debug_force_scan_cols(srt_ctx* c, int cols)
 {
     if (!c || cols < 0) return SRT_ERR_INVALID;
     c->force_scan_cols = cols;
+    return SRT_OK;
+}
+
+// diagnostic: cap the culled kernel's per-bin lists and the filtered path's candidate lists (0 = no cap) so that tests
+// can exercise the overflow fallbacks
+int srt_debug_force_list_caps(srt_ctx* c, uint32_t bin_cap, uint32_t cand_cap, uint32_t pix_cap)
+{
+    if (!c) return SRT_ERR_INVALID;
+    c->force_bin_cap = bin_cap; c->force_cand_cap = cand_cap; c->force_pix_cap = pix_cap;
     return SRT_OK;
 }
 

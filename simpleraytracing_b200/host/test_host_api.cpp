@@ -1,6 +1,7 @@
 // test_host_api.cpp -- checks of the C++ host classes (include/srt/*.h) against the reference's documented
 // behaviour.  `test_host_api cpu` needs no GPU; `test_host_api gpu <ply> <W> <H> <out.txt>` renders through
-// srt::renderLoop (CUDA) and writes the image with Image::saveTextFile; `test_host_api gpu-multi <ply> <W> <H> <out.txt>
+// srt::renderLoop (CUDA; main.cxx's sort-based image, or the L-buffer flow with a trailing "lbuffer") and writes the image
+// with Image::saveTextFile; `test_host_api gpu-multi <ply> <W> <H> <out.txt>
 // [n_gpus]` does the same on all (or the first n) visible GPUs through srt::MultiGpuXRayRenderer and checks that the image
 // equals the single-GPU one bit for bit.
 #include <cmath>
@@ -104,6 +105,7 @@ static int cpu_tests()
         if (rc == SRT_OK) { srt_destroy(c); ndev = 1; }
     }
     if (!ndev) CHECK(throws<std::runtime_error>([&] { renderLoop(out, set, info); }));
+    if (!ndev) CHECK(throws<std::runtime_error>([&] { renderLoopLBuffer(out, set, info); }));
     std::printf(failures ? "%d FAILURES\n" : "OK\n", failures);
     return failures ? 1 : 0;
 }
@@ -119,7 +121,9 @@ int main(int argc, char** argv)
             srt::Vec3 lo, hi; srt::getBBox(meshes, hi, lo);
             srt::Image image;
             srt::RayTracerInfo info = srt::initialiseRayTracing(meshes, hi, lo, H, W, image, 0.0f);
-            srt::renderLoop(image, meshes, info);
+            // argv[6] == "lbuffer": the main-pthreads-lbuffer flow; default: main.cxx's sort-based renderLoop
+            if (argc >= 7 && std::strcmp(argv[6], "lbuffer") == 0) srt::renderLoopLBuffer(image, meshes, info);
+            else srt::renderLoop(image, meshes, info);
             image.saveTextFile(argv[5]);
             std::printf("OK %zu triangles\n", meshes[0].getNumberOfTriangles());
             return 0;
@@ -133,7 +137,7 @@ int main(int argc, char** argv)
             srt::Vec3 lo, hi; srt::getBBox(meshes, hi, lo);
             srt::Image single, multi;
             srt::RayTracerInfo info = srt::initialiseRayTracing(meshes, hi, lo, H, W, single, 0.0f);
-            srt::renderLoop(single, meshes, info);                               // GPU 0 alone
+            srt::renderLoopLBuffer(single, meshes, info);                        // GPU 0 alone
             int n = 0;
             while (n < 8) { srt_ctx* c = nullptr; if (srt_create(&c, n) != SRT_OK) break; srt_destroy(c); ++n; }
             if (argc >= 7) n = std::min(n, std::atoi(argv[6]));

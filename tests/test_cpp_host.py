@@ -91,9 +91,26 @@ def test_cli_and_render_loop_reproduce_the_reference_output(host_bins, tmp_path,
     assert r.returncode == 0, r.stdout + r.stderr
     assert (tmp_path / "out" / "cli.txt").read_text() == want.read_text()
     r = subprocess.run([str(host_bins / "test_host_api"), "gpu", str(tmp_path / "dragon.ply"), "128", "128",
-                        str(tmp_path / "loop.txt")], capture_output=True, text=True)
+                        str(tmp_path / "loop.txt"), "lbuffer"], capture_output=True, text=True)
     assert r.returncode == 0 and "22866 triangles" in r.stdout, r.stdout
     assert (tmp_path / "loop.txt").read_text() == want.read_text()
+    # srt::renderLoop(Image&, meshes, info) is main.cxx's renderLoop: its text output must be the reference's own golden
+    # file out/dragon-128x128-serial.txt, character for character (fixture: the file's values, printed with %g like
+    # Image::saveTextFile prints them)
+    r = subprocess.run([str(host_bins / "test_host_api"), "gpu", str(tmp_path / "dragon.ply"), "128", "128",
+                        str(tmp_path / "serial.txt")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    gold = np.load(GOLDEN / "dragon_128_serial.npy")
+    gold_text = "\n".join("\t".join("%.6g" % v for v in row) for row in gold)
+    assert (tmp_path / "serial.txt").read_text() == gold_text
+    # CLI: -b is accepted like the reference's, --csv appends a row in the batch scripts' format
+    r = subprocess.run([str(host_bins / "srt_xray"), "-s", "64", "64", "-b", "10", "20", "30", "-f", "b.txt", "-i", "./dragon.ply",
+                        "--csv", "timing.csv"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = (tmp_path / "timing.csv").read_text().strip().split("\n")
+    assert rows[0] == "CPU,Parallelisation,Number of threads,Number of nodes,Compiler,Image size,Runtime in sec"
+    assert len(rows) == 2 and rows[1].split(",")[1:4] == ["CUDA", "1", "1"] and rows[1].split(",")[5] == "64x64"
+    assert subprocess.run([str(host_bins / "srt_xray"), "-b", "300", "0", "0"], cwd=tmp_path, capture_output=True).returncode != 0
     # the classic flag errors keep their exit status
     assert subprocess.run([str(host_bins / "srt_xray"), "--bogus"], capture_output=True).returncode != 0
 
