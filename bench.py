@@ -47,6 +47,16 @@ F_ALG = 19.0            # algorithmic flop per test
 COUNTERS = ROOT / "profiles" / "r02_kernel_counters.json"      # ncu-derived per-kernel counters (tools/ncu_counters.py)
 
 
+VERBOSE = bool(os.environ.get("SRT_BENCH_VERBOSE"))
+T0 = time.time()
+
+
+def note(msg):
+    """progress marker on stderr (SRT_BENCH_VERBOSE=1): rank 0 only"""
+    if VERBOSE and os.environ.get("RANK", "0") == "0":
+        print(f"[bench {time.time() - T0:7.2f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -259,6 +269,7 @@ def run_ours(args):
     cam_b = Camera.from_buffer_copy(cam)
     cam_b.detector[1] = cam.detector[1] + 7.5; cam_b.detector[2] = cam.detector[2] - 4.25
     cam_b.pixel_spacing[0] = cam.pixel_spacing[0] * 0.9; cam_b.pixel_spacing[1] = cam.pixel_spacing[1] * 0.9
+    note("scene built")
     ctx.set_meshes(meshes)
     ctx.set_camera(cam)
     params = lib.default_params(kernel=args.kernel, pixels_per_thread=args.box)
@@ -336,8 +347,12 @@ def run_ours(args):
     per_rank_ms = []          # one list per timed() call: mean ms per step on every rank
 
     def timed(fn, steps, warmup, sync_each):
-        for _ in range(warmup):
+        for i in range(warmup):
             fn()
+            if VERBOSE:
+                stream.synchronize()
+                tm_ = ctx.timing()
+                note(f"warm-up step {i}: pass {tm_.render_ms:.3f} ms, main kernel {tm_.main_kernel_ms:.3f} ms, kernel {tm_.kernel_used}")
         barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         wall = 0.0
@@ -382,7 +397,9 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    note("timing the device-resident steps")
     total_ms = timed(step_device, steps, args.warmup, sync_each=False)
+    note(f"{total_ms / steps:.4f} ms per step")
     # the dominant kernel alone: CUDA events around it on its stream (srt_timing.main_kernel_ms)
     barrier()
     kern_ms, pass_ms = [], []
@@ -405,6 +422,7 @@ def run_ours(args):
     e2e_steps = max(1, min(steps, 10))
 
     # ---- end to end
+    note("end to end")
     e2e = {}
     if world == 1:
         host_image = np.empty(H * W, np.float32)                      # an ordinary (pageable) host buffer
@@ -436,6 +454,7 @@ def run_ours(args):
         e2e_path = "per rank: srt_set_meshes + srt_set_camera + sharded render + assembly + repair; image to pinned host memory on rank 0"
 
     # the accelerated path (not the headline): same frame, same step, SRT_KERNEL_CULLED
+    note("accelerated path")
     ctx.set_meshes(meshes); ctx.set_camera(cam)
     acc_ms = timed(lambda: step_device(params_acc), steps, 3, sync_each=False)
     acc_kernel_used = ctx.timing().kernel_used
@@ -472,6 +491,7 @@ def run_ours(args):
         if not verified:
             raise SystemExit(f"bench.py: rank {rank}: the assembled frame differs from the unsharded render")
 
+    note("exact-test counts")
     # actual work behind the "tests": pairs that reach the exact reference sequence (this rank's share), both kernels
     exact_counts = {}
     try:
@@ -498,6 +518,7 @@ def run_ours(args):
 
     if rank == 0:
         cpu = None
+        note("cpu baseline")
         if world == 1 and not args.no_cpu:
             kind, eng = cpu_reference_engine()
             threads = os.cpu_count() or 1

@@ -133,6 +133,11 @@ typedef struct {
                                    lbuffer_culled_kernel / lbuffer_exact_kernel (render_ms also covers the
                                    second kernel of the pass: hit-list resolve, resp. the bin pass)   */
     uint32_t scan_cols;         /* filtered kernel: box columns per CTA of the last render            */
+    float    min_strip_slack;   /* SRT_KERNEL_AUDIT: smallest head-room of a strip bound on a HIT, in units of the
+                                   bound's margin: (|D| + m - |Y|) / m (3.4e38 if there was no hit)        */
+    float    min_box_slack;     /* the same for the level-0 box bounds: (R - (|Y(c)| - |D(c)|)) / 2m; the box radii
+                                   in R are exact geometry, so 0.5 is the geometric worst case (a hit on the
+                                   strip's edge at a box corner)                                       */
 } srt_timing;
 
 /* ---- context ------------------------------------------------------------ */
@@ -161,6 +166,11 @@ int  srt_triangle_normals(const float* vertices, uint32_t n_triangles, float* no
  * entry points accept any host pointer, pinned ones skip the staging copy of the driver. */
 int  srt_host_alloc(void** out, size_t bytes);
 void srt_host_free(void* p);
+
+/* JPEG writer (nvJPEG encoder on the context's GPU): 8-bit interleaved RGB, quality 1 ... 100, no chroma subsampling.
+ * Replaces the libjpeg writers Image::saveJPEGFile (src/Image.cxx:85-146: quality 100, 3 components) and the old
+ * RGB Image's (src/Image.bakk.cxx:170-226). */
+int  srt_write_jpeg(srt_ctx* ctx, const char* path, const uint8_t* rgb, uint32_t width, uint32_t height, int quality);
 
 /* ---- scene upload -------------------------------------------------------- */
 /* The arrays are copied to the GPU asynchronously on the context's stream.  Pageable arrays are staged before the call

@@ -11,6 +11,7 @@
 // replicated to RGB; saveTGAFile writes that as an uncompressed 24-bit TGA with the reference's
 // header layout (src/Image.cxx:148-206); savePGMFile is an extra 8-bit writer.
 #pragma once
+#include "../srt.h"
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -82,6 +83,15 @@ public:
                 std::fwrite(bgr, 1, 3, f);
             }
         std::fclose(f);
+    }
+
+    // Image::saveJPEGFile (src/Image.cxx:85-146): LUT to 8 bits, 3 components, quality 100 -- encoded by nvJPEG on the
+    // GPU of `ctx` (srt_write_jpeg); the LUT is the intended one (see applyLUT above)
+    void saveJPEGFile(srt_ctx* ctx, const std::string& name, float vmin = 0.0f, float vmax = 1.0f) const
+    {
+        const std::vector<unsigned char> rgb = applyLUT(vmin, vmax);
+        if (srt_write_jpeg(ctx, name.c_str(), rgb.data(), width_, height_, 100) != SRT_OK)
+            throw std::runtime_error(std::string("saveJPEGFile: ") + srt_last_error(ctx));
     }
 
     void savePGMFile(const std::string& name, float vmin = 0.0f, float vmax = 1.0f) const

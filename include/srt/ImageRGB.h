@@ -3,6 +3,7 @@
 // (main-omp / main-mpi / main-pthreads-rows) render into and which TriangleMesh uses as a texture.
 // libjpeg is not available here, so files are read/written as binary PPM (P6) or TGA instead of JPEG.
 #pragma once
+#include "../srt.h"
 #include <cstdio>
 #include <fstream>
 #include <sstream>
@@ -56,6 +57,13 @@ public:
         if (!f) throw std::runtime_error("Truncated PPM file " + name);
     }
     // uncompressed 24-bit TGA, header layout of src/Image.bakk.cxx:230-290
+    // old Image::saveJPEGFile (src/Image.bakk.cxx:170-226): quality 100 -- encoded by nvJPEG on the GPU of `ctx`
+    void saveJPEGFile(srt_ctx* ctx, const std::string& name) const
+    {
+        if (srt_write_jpeg(ctx, name.c_str(), getData(), getWidth(), getHeight(), 100) != SRT_OK)
+            throw std::runtime_error(std::string("saveJPEGFile: ") + srt_last_error(ctx));
+    }
+
     void saveTGAFile(const std::string& name) const
     {
         std::FILE* f = std::fopen(name.c_str(), "wb");

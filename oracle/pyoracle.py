@@ -91,6 +91,8 @@ class Oracle:
         L.oracle_triangle_normal.argtypes = [_f32p, _f32p]
         L.oracle_triangle_area.argtypes = [_f32p]
         L.oracle_triangle_area.restype = C.c_float
+        L.oracle_render_lbuffer_pixels.argtypes = [_f32p, _u32p, C.c_int, C.POINTER(Camera), C.c_uint32, C.c_uint32,
+                                                   C.c_void_p, C.c_uint64, C.c_int, _f32p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_render_lbuffer.argtypes = [_f32p, _u32p, C.c_int, C.POINTER(Camera), C.c_uint32, C.c_uint32,
                                             C.c_uint64, C.c_uint64, C.c_int, _f32p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
@@ -161,6 +163,19 @@ class Oracle:
         if want_stages:
             out["stages"] = stages
         return out
+
+    def render_lbuffer_pixels(self, tri, mesh_ntris, cam, W, H, pixels, threads=None):
+        """L-buffer values of a LIST of pixel indices -> dict(L, dist, ssum, hits), one entry per listed pixel."""
+        tri = np.ascontiguousarray(tri, np.float32).reshape(-1)
+        nt = np.ascontiguousarray(mesh_ntris, np.uint32)
+        pix = np.ascontiguousarray(pixels, np.uint64)
+        n = W * H
+        full = dict(L=np.zeros(n, np.float32), dist=np.zeros(n, np.float32), ssum=np.zeros(n, np.int32), hits=np.zeros(n, np.uint32))
+        self.lib.oracle_render_lbuffer_pixels(tri, nt, len(nt), C.byref(cam), W, H, pix.ctypes.data_as(C.c_void_p), len(pix),
+                                              threads or os.cpu_count() or 1, full["L"], full["dist"].ctypes.data_as(C.c_void_p),
+                                              full["ssum"].ctypes.data_as(C.c_void_p), full["hits"].ctypes.data_as(C.c_void_p))
+        idx = pix.astype(np.int64)
+        return {k: v[idx] for k, v in full.items()}
 
     def render_shaded(self, meshes, cam, W, H, background=(128, 128, 128), pixel_range=None, threads=None):
         """-> dict(rgb uint8[H*W*3], z float32, tri_id int32, shadow uint8). cam = camera WITHOUT the background quad."""

@@ -309,6 +309,49 @@ int oracle_render_lbuffer(const float* tri, const uint32_t* mesh_ntris, int n_me
     return 0;
 }
 
+/* The same render for an arbitrary LIST of pixels (strided subsets of very large frames: SURVEY 8d evaluates the
+ * 8192 x 8192 configuration on every 64th row and column).  Outputs are written at the pixels' own indices of the
+ * full-frame arrays; triangle normals are computed once, the list is cut into n_threads contiguous pieces. */
+typedef struct { lbuf_job job; const uint64_t* pixels; uint64_t first, last; } lbuf_list_job;
+
+static void* lbuffer_list_callback(void* arg)
+{
+    lbuf_list_job* lj = (lbuf_list_job*)arg;
+    for (uint64_t i = lj->first; i < lj->last; ++i) {
+        lbuf_job one = lj->job;
+        one.start_pixel = one.end_pixel = lj->pixels[i];
+        lbuffer_callback(&one);
+    }
+    return 0;
+}
+
+int oracle_render_lbuffer_pixels(const float* tri, const uint32_t* mesh_ntris, int n_meshes,
+                                 const oracle_camera* cam, uint32_t W, uint32_t H,
+                                 const uint64_t* pixels, uint64_t n_pixels, int n_threads,
+                                 float* L, float* dist, int32_t* ssum, uint32_t* hits)
+{
+    if (n_threads < 1) n_threads = 1;
+    uint64_t total_tris = 0;
+    for (int m = 0; m < n_meshes; ++m) total_tris += mesh_ntris[m];
+    float* normals = (float*)malloc(sizeof(float) * 3 * (total_tris ? total_tris : 1));
+    for (uint64_t k = 0; k < total_tris; ++k) oracle_triangle_normal(tri + 9 * k, normals + 3 * k);
+    for (uint64_t i = 0; i < n_pixels; ++i) L[pixels[i]] = 80.000f;        /* :314 */
+    lbuf_list_job* jobs = (lbuf_list_job*)calloc((size_t)n_threads, sizeof(lbuf_list_job));
+    pthread_t* tid = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
+    for (int i = 0; i < n_threads; ++i) {
+        lbuf_job* j = &jobs[i].job;
+        j->tri = tri; j->mesh_ntris = mesh_ntris; j->n_meshes = n_meshes; j->normals = normals;
+        j->cam = cam; j->W = W; j->H = H; j->L = L; j->dist = dist; j->ssum = ssum; j->hits = hits;
+        jobs[i].pixels = pixels;
+        jobs[i].first = n_pixels * (uint64_t)i / (uint64_t)n_threads;
+        jobs[i].last = n_pixels * (uint64_t)(i + 1) / (uint64_t)n_threads;
+        pthread_create(&tid[i], NULL, lbuffer_list_callback, &jobs[i]);
+    }
+    for (int i = 0; i < n_threads; ++i) pthread_join(tid[i], NULL);
+    free(jobs); free(tid); free(normals);
+    return 0;
+}
+
 /* ---- artefact repair + image fill (main-pthreads-lbuffer.cxx:329-404) ----- */
 /* All index arithmetic is unsigned 32-bit as in the reference (row/col are
  * `unsigned int`, so `col - i` and `row - i` wrap).  The reference's guard is

@@ -51,7 +51,7 @@ class Timing(C.Structure):
     _fields_ = [("render_ms", C.c_float), ("repair_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("pair_tests", C.c_uint64), ("exact_tests", C.c_uint64), ("filter_violations", C.c_uint64),
                 ("kernel_used", C.c_uint32), ("launches", C.c_uint32), ("main_kernel_ms", C.c_float),
-                ("scan_cols", C.c_uint32)]
+                ("scan_cols", C.c_uint32), ("min_strip_slack", C.c_float), ("min_box_slack", C.c_float)]
 
 
 # every symbol include/srt.h declares (tests/test_abi.py checks the .so exports all of them)
@@ -62,7 +62,7 @@ EXPORTS = [
     "srt_repair_device", "srt_render_xray", "srt_interleave_slot_rows",
     "srt_render_lbuffer_interleaved_device", "srt_deinterleave_device", "srt_render_lbuffer_blocks_device", "srt_render_shaded",
     "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_force_scan_cols", "srt_debug_force_list_caps", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_pack_info", "srt_debug_download_packed",
-    "srt_host_alloc", "srt_host_free", "srt_render_xray_sorted", "srt_render_xray_sorted_device",
+    "srt_host_alloc", "srt_host_free", "srt_write_jpeg", "srt_render_xray_sorted", "srt_render_xray_sorted_device",
     "srt_multi_create", "srt_multi_destroy", "srt_multi_last_error", "srt_multi_device_count", "srt_multi_set_meshes",
     "srt_multi_set_camera", "srt_multi_render_xray_device", "srt_multi_synchronize", "srt_multi_frame",
     "srt_multi_render_xray", "srt_multi_last_timing",
@@ -128,6 +128,7 @@ class Library:
         L.srt_debug_prepack.argtypes = [vp, u32, C.POINTER(Camera), u32, u32, vp, vp, vp, C.POINTER(u32), C.POINTER(u32)]
         L.srt_render_xray_sorted.argtypes = [vp, C.POINTER(Params), vp]
         L.srt_render_xray_sorted_device.argtypes = [vp, C.POINTER(Params), vp, vp, vp]
+        L.srt_write_jpeg.argtypes = [vp, C.c_char_p, vp, u32, u32, i32]
         L.srt_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         L.srt_host_free.argtypes = [vp]
         L.srt_host_free.restype = None
@@ -380,6 +381,11 @@ class Context:
     def render_xray_sorted_device(self, params, d_image, d_path=0, d_hits=0):
         self._ck(self.lib.srt_render_xray_sorted_device(self.h, C.byref(params), C.c_void_p(d_image), C.c_void_p(d_path or None),
                                                         C.c_void_p(d_hits or None)))
+
+    def write_jpeg(self, path, rgb, quality=100):
+        """rgb: uint8 [H, W, 3] -> JPEG file (nvJPEG encoder on this context's GPU)"""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        self._ck(self.lib.srt_write_jpeg(self.h, str(path).encode(), _ptr(rgb, np.uint8), rgb.shape[1], rgb.shape[0], quality))
 
     def download_packed(self, mesh, n):
         pad = self.L.pack_info()[0]

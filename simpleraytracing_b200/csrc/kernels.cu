@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
     const float x = (float)col + a.cam.xc, y = (float)row + a.cam.yc;
     float L = a.incident;
     unsigned long long n_viol = 0;
+    float min_strip = INFINITY, min_box = INFINITY;                       // audit: smallest head-room seen on a hit
     float zbuf = INFINITY; int zid = -1;                                  // mode 1
     for (int m = 0; m < a.n_meshes; ++m) {
         const DevMesh M = a.meshes[m];
@@ -231,6 +232,15 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
                     const bool reject = gate || (fabsf(X1) > fabsf(Dd) + fb.z) ||                                 // level 0
                                         (fabsf(X2) > fabsf(Dd) + ga.w) || (fabsf(X3) > fabsf(Dd) + gb.w);         // level 1
                     if (reject && hit) ++n_viol;
+                    if (hit && fb.z > 0.0f) {
+                        // head-room of the bounds on this HIT, in units of the rounding-error margin m: (|D| + m - |Y|) / m per
+                        // strip (1 = the margin is untouched) and (R - (|Y(c)| - |D(c)|)) / 2m per level-0 box test (the box radii
+                        // in R are exact geometry, 2m is its error budget; a hit on the strip's edge at a box corner gives 0.5)
+                        const float aD = fabsf(Dd);
+                        const float sp = fminf(fminf((aD + fb.z - fabsf(X1)) / fb.z, (aD + ga.w - fabsf(X2)) / ga.w), (aD + gb.w - fabsf(X3)) / gb.w);
+                        const float sb = fminf((fb.w - (fabsf(Yc) - fabsf(Dc))) / (2.0f * fb.z), (fc.w - (fabsf(Yc2) - fabsf(Dc))) / (2.0f * ga.w));
+                        min_strip = fminf(min_strip, sp); min_box = fminf(min_box, sb);
+                    }
                 }
             }
         }
@@ -245,7 +255,12 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
     }
     if (a.mode == 0) store_L(a, (size_t)(a.L_image ? row : orow) * W + col, L);
     else { a.dist[(size_t)orow * W + col] = zbuf; a.ssum[(size_t)orow * W + col] = zid; }
-    if (AUDIT && a.counters && n_viol) atomicAdd(a.counters + 1, n_viol);
+    if (AUDIT && a.counters) {
+        if (n_viol) atomicAdd(a.counters + 1, n_viol);
+        // non-negative floats order like their bit patterns; negative head-room is a violation and counted above
+        if (min_strip < INFINITY) atomicMin(reinterpret_cast<unsigned int*>(a.counters + 2), __float_as_uint(fmaxf(min_strip, 0.0f)));
+        if (min_box < INFINITY) atomicMin(reinterpret_cast<unsigned int*>(a.counters + 2) + 1, __float_as_uint(fmaxf(min_box, 0.0f)));
+    }
 }
 
 // --------------------------------------------------------------- filtered kernel
@@ -513,9 +528,11 @@ __global__ void __launch_bounds__(128) exact_tests_kernel(const __grid_constant_
             const float dn = dot_rn(r.ax, r.ay, r.az, Dn.y, Dn.z, Dn.w);   // direction . normal, pre-Ray direction
             val = __fmul_rn((float)((0.0f < dn) - (dn < 0.0f)), tt);       // sign * t
         } else if (a.mode == 2 && !((double)tt > 0.0000001)) continue;     // sort mode keeps t itself (main.cxx:687)
+        // push onto the pixel's list: the candidate's own slot e becomes the list node {triangle, value} (the pixel index
+        // it held is no longer needed), linked through hit_next; one atomic exchange on the pixel's head
         const size_t p = (size_t)out_row(a, row) * W + col;
-        const uint32_t slot = atomicAdd(a.hit_counts + p, 1u);
-        if (slot < a.hit_cap) a.hit_entries[p * a.hit_cap + slot] = make_uint2(Mp->first + tri, __float_as_uint(val));
+        a.pix[e] = make_uint2(Mp->first + tri, __float_as_uint(val));
+        a.hit_next[e] = atomicExch(a.hit_head + p, e);
     }
 }
 
@@ -567,7 +584,8 @@ __device__ __forceinline__ float expf_glibc(float x)
     return (float)y;
 }
 
-constexpr uint32_t kMaxHitCap = 16;
+constexpr uint32_t kNoHit = 0xffffffffu;       // empty list head / end of a pixel's hit list
+constexpr uint32_t kLocalHits = 32;            // hits of one pixel the resolve pass sorts in a local array
 constexpr uint32_t kSortOverflowCap = 256;     // sort mode: intersections of one ray the overflow path can order
 
 // Sort-based X-ray value of one pixel (src/main.cxx:700-741): the ray's intersection distances t (mesh 0, t > 1e-7) are
@@ -604,63 +622,88 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
     float L = a.incident;
     float dist0 = 0.0f; int ssum0 = 0; uint32_t hits0 = 0;   // mode 1: z-buffer value / triangle index
     if (a.mode == 1) { dist0 = INFINITY; ssum0 = -1; }
-    const bool list_lost = a.cand_count[0] > a.cand_cap || a.cand_count[1] > a.pix_cap;   // a candidate list overflowed: no hit list can be trusted
-    bool overflow = false;
+    // a candidate list overflowed: no hit list can be trusted, every pixel is recomputed below
+    const bool overflow = a.cand_count[0] > a.cand_cap || a.cand_count[1] > a.pix_cap;
     if (valid) {
-        const uint32_t n = a.hit_counts[p];
-        if (n) a.hit_counts[p] = 0;                          // ready for the next render
-        overflow = n > a.hit_cap || list_lost;
-        if (n && !overflow) {
-            uint2 e[kMaxHitCap];
-            const uint2* src = a.hit_entries + p * a.hit_cap;
-            for (uint32_t i = 0; i < n; ++i) {               // insertion sort by triangle index while loading
-                const uint2 key = src[i];
-                uint32_t j = i;
-                while (j > 0 && e[j - 1].x > key.x) { e[j] = e[j - 1]; --j; }
+        const uint32_t head = a.hit_head[p];
+        if (head != kNoHit) a.hit_head[p] = kNoHit;         // ready for the next render
+        if (overflow) { /* recomputed by the warp below */ }
+        else if (a.mode == 1) {
+            // closest hit: strict `z > t` in ascending triangle order == smallest t, lowest triangle index among equals
+            for (uint32_t i = head; i != kNoHit; i = a.hit_next[i]) {
+                const uint2 e = a.pix[i];
+                const float t = __uint_as_float(e.y);
+                if (dist0 > t || (dist0 == t && (int)e.x < ssum0)) { dist0 = t; ssum0 = (int)e.x; }
+            }
+        } else {
+            // The pixel's hits in the reference's order: ascending triangle index (mode 0: the float sum is order
+            // dependent) resp. ascending t (mode 2).  Lists of up to kLocalHits entries are insertion-sorted into a
+            // local array while the chain is walked; longer ones (rays grazing a bumpy silhouette) are replayed by
+            // selection -- one walk of the chain per entry, no storage -- which is slow but rare and exact.
+            uint2 e[kLocalHits];
+            uint32_t n = 0;
+            for (uint32_t i = head; i != kNoHit; i = a.hit_next[i], ++n) {
+                if (n >= kLocalHits) continue;
+                const uint2 key = a.pix[i];
+                const uint32_t kk = a.mode == 2 ? key.y : key.x;            // positive floats order like their bits
+                uint32_t j = n;
+                while (j > 0 && (a.mode == 2 ? e[j - 1].y : e[j - 1].x) > kk) { e[j] = e[j - 1]; --j; }
                 e[j] = key;
             }
+            // visit entry number `i` (0-based, in order): from the array, or by selection over the chain
+            unsigned long long last = 0;                                    // long lists: (key, node) + 1 of the last visited entry
+            auto entry = [&](uint32_t i) -> uint2 {
+                if (n <= kLocalHits) return e[i];
+                unsigned long long best = ~0ull; uint2 bv = make_uint2(0, 0);
+                for (uint32_t c = head; c != kNoHit; c = a.hit_next[c]) {
+                    const uint2 v = a.pix[c];
+                    const unsigned long long k = (((unsigned long long)(a.mode == 2 ? v.y : v.x)) << 32 | c) + 1;
+                    if (k > last && k < best) { best = k; bv = v; }
+                }
+                last = best;
+                return bv;
+            };
             if (a.mode == 2) {
-                float t[kMaxHitCap];
-                for (uint32_t i = 0; i < n; ++i) t[i] = __uint_as_float(e[i].y);
-                L = sorted_xray_value(t, n, a.incident, a.meshes[0].mu, a.length_to_cm, dist0);
+                // main.cxx:700-741 (sorted_xray_value), streamed: pairs (t[i], t[i + 1]) in ascending order
+                float distance = 0.0f;
+                if (n > 0 && (n & 1u) == 0)
+                    for (uint32_t i = 0; i < n; i += 2) {
+                        const float t0 = __uint_as_float(entry(i).y), t1 = __uint_as_float(entry(i + 1).y);
+                        distance = __fadd_rn(distance, __fsub_rn(t1, t0));
+                    }
+                dist0 = distance;
+                distance = (float)((double)distance * a.length_to_cm);
+                L = __fmul_rn(a.incident, expf_glibc(-__fmul_rn(a.meshes[0].mu, distance)));
                 ssum0 = 0; hits0 = n;
-            } else if (a.mode != 0) {
-                for (uint32_t i = 0; i < n; ++i) {
-                    const float t = __uint_as_float(e[i].y);
-                    if (dist0 > t) { dist0 = t; ssum0 = (int)e[i].x; }      // strict >: the first of equal t wins
+            } else if (n == 0) {
+                // no hit in any mesh: L *= exp(-(mu * (0 * 0.1))) == L exactly, unless mu or the unit factor is not finite
+                for (int m = 0; m < a.n_meshes; ++m) {
+                    const float mu = a.meshes[m].mu;
+                    if (!(isfinite(mu) && isfinite(a.length_to_cm))) L = attenuate(L, mu, 0.0f, 0, a.length_to_cm);
                 }
             } else {
                 uint32_t i = 0;
+                uint2 cur = entry(0);
                 for (int m = 0; m < a.n_meshes; ++m) {
                     const DevMesh M = a.meshes[m];
                     float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
                     if (M.contributes) {
-                        while (i < n && e[i].x < M.first + M.n) {
-                            const float st = __uint_as_float(e[i].y);
+                        while (i < n && cur.x < M.first + M.n) {
+                            const float st = __uint_as_float(cur.y);
                             dist = __fadd_rn(dist, st);              // distance += sign * t, ascending triangle order
                             ssum += (0.0f < st) - (st < 0.0f);
                             ++hits; ++i;
+                            if (i < n) cur = entry(i);
                         }
                     }
                     L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
                     if (m == 0) { dist0 = dist; ssum0 = ssum; hits0 = hits; }
                 }
             }
-        } else if (a.mode == 2 && !overflow) {
-            float none[1];
-            L = sorted_xray_value(none, 0, a.incident, a.meshes[0].mu, a.length_to_cm, dist0);
-            ssum0 = 0;
-        } else if (a.mode == 0 && !overflow) {
-            // no hit in any mesh: L *= exp(-(mu * (0 * 0.1))) == L exactly, unless mu or the unit factor is not finite
-            for (int m = 0; m < a.n_meshes; ++m) {
-                const float mu = a.meshes[m].mu;
-                if (!(isfinite(mu) && isfinite(a.length_to_cm))) L = attenuate(L, mu, 0.0f, 0, a.length_to_cm);
-            }
         }
     }
-    // A list that overflowed its capacity: the WARP recomputes that pixel from scratch with the exact sequence --
-    // 32 triangles at a time (one per lane), hits folded in ascending lane (= triangle) order -- so that one
-    // pathological ray costs tens of microseconds instead of a single thread walking the whole mesh.
+    // The candidate lists overflowed: the WARP recomputes each of its pixels from scratch with the exact sequence --
+    // 32 triangles at a time (one per lane), hits folded in ascending lane (= triangle) order.
     const uint32_t lane = threadIdx.x & 31u;
     unsigned todo = __ballot_sync(0xffffffffu, valid && overflow);
     while (todo) {
@@ -1440,8 +1483,7 @@ cudaError_t launch_filtered_candidates(const RenderArgs& a, cudaStream_t s)
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, cudaStream_t s)
 {
     if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0 || a.scan_chunks == 0) return cudaSuccess;
-    if (!a.hit_entries || !a.hit_counts || a.hit_cap == 0 || a.hit_cap > kMaxHitCap || a.scan_cols == 0 || !a.cand || !a.cand_count ||
-        !a.pix || a.n_meshes > 32)
+    if (!a.hit_head || !a.hit_next || a.scan_cols == 0 || !a.cand || !a.cand_count || !a.pix || a.n_meshes > 32)
         return cudaErrorInvalidValue;
 #define X(PX, PY, K) if (a.box_px == PX && a.box_py == PY && a.scan_k == K) return launch_filtered_t<PX, PY, K>(a, s);
     SRT_SCAN_SHAPES(X)

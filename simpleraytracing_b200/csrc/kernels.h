@@ -56,7 +56,8 @@ struct RenderArgs {
     float* dist;             // optional
     int32_t* ssum;           // optional
     uint32_t* hits;          // optional
-    unsigned long long* counters;   // optional: [0] exact tests run, [1] filter violations (audit)
+    unsigned long long* counters;   // optional: [0] exact tests run, [1] filter violations (audit), [2] two floats: the smallest
+                                    // head-room of the strip bounds and of the level-0 box bounds over all hits (audit)
     // mode 0: X-ray L-buffer (above).  mode 1: closest hit over all meshes (shaded variant, main-omp.cxx:632-666):
     // `dist` receives the z-buffer value t (+inf = no hit), `ssum` the scene-wide triangle index (-1 = none);
     // strict `z > t` in ascending triangle order => the first of equal t wins, negative t is accepted.
@@ -68,17 +69,17 @@ struct RenderArgs {
     // x one chunk of 128 * scan_k triangles (grid.z = scan_chunks = the largest chunk count of a contributing mesh).
     // Accepted intersections are not accumulated in place (the reference's float sum is order dependent and the exact
     // tests of a warp run wherever a lane is free) but appended to the pixel's hit list {scene-wide triangle index,
-    // value} -- value = sign * t (mode 0) or t (mode 1) -- through an atomic slot counter; resolve_hits_kernel sorts each
-    // list by triangle index and replays lbuffer.cxx:788-809 (or the z-buffer update, main-omp.cxx:656-662) in the
+    // value} -- value = sign * t (mode 0) or t (modes 1, 2) -- a linked list with an atomic head; resolve_hits_kernel
+    // sorts each list by triangle index and replays lbuffer.cxx:788-809 (or the z-buffer update, main-omp.cxx:656-662) in the
     // reference's order.
     uint32_t box_px, box_py, scan_k, scan_cols, scan_chunks;
     // survivors of the scan {box, triangle} (cand) and of the per-pixel strip tests {pixel, triangle} (pix).
     // cand_count[0] / [1] count them: zero when the scan starts; they may exceed the capacities (entries beyond are
     // dropped and resolve_hits_kernel recomputes every pixel with the exact sequence).
     uint2* cand; uint2* pix; uint32_t* cand_count; uint32_t cand_cap, pix_cap;
-    uint2* hit_entries;      // [pixel][hit_cap]
-    uint32_t* hit_counts;    // [pixel]: entries appended (may exceed hit_cap: overflow -> exact recompute); zero between renders
-    uint32_t hit_cap;
+    uint32_t* hit_head;      // [pixel]: the pixel's hit list (index into pix / hit_next; 0xffffffff = empty, also between renders)
+    uint32_t* hit_next;      // [pix_cap]: next node of the list; node e = candidate e of the pix list, which exact_tests_kernel
+                             // overwrites in place with {scene-wide triangle index, value}
     // Culled kernel (SRT_KERNEL_CULLED): per-bin triangle lists.  A bin is kBinCols columns x bin_blocks 16-row blocks
     // of this launch's grid; bin_entries[bin * bin_cap + off_m + i], i < bin_counts[bin * n_meshes + m] (off_m: the mesh's
     // proportional share of the bin_cap entries of a bin; a count above the share = "walk the whole mesh"), are the
@@ -122,7 +123,6 @@ cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
 // candidate stages (per-pixel strip tests, exact tests), then launch_resolve_hits.
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, cudaStream_t s);
 cudaError_t launch_filtered_candidates(const RenderArgs& a, cudaStream_t s);
-constexpr uint32_t kMaxHitCapacity = 16;
 bool filtered_shape_supported(uint32_t box_px, uint32_t box_py, uint32_t scan_k);
 int filtered_resident_ctas(uint32_t box_px, uint32_t box_py, uint32_t scan_k);     // CTAs resident per SM on the current device
 // Culled kernel: bin pass (every triangle against every bin of a.bins_x x a.bins_y), then the render pass.  Same results

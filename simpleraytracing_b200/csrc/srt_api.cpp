@@ -18,6 +18,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <nvjpeg.h>
 
 #include "kernels.h"
 #include "prepack.h"
@@ -100,11 +101,12 @@ struct srt_ctx {
     unsigned long long* d_counters = nullptr;
     bool count_exact = false;
     // per-pixel hit lists of the filtered kernel (counts are zero between renders: resolve_hits_kernel resets them)
-    uint2* d_hit_entries = nullptr; uint32_t* d_hit_counts = nullptr; size_t hit_pixels_cap = 0; uint32_t hit_cap = 0;
+    uint32_t* d_hit_head = nullptr; uint32_t* d_hit_next = nullptr; size_t hit_pixels_cap = 0;
     // candidate list of the filtered kernel: survivors of the scan.  h_cand_count (pinned) receives the count of every
     // render asynchronously; a later render grows the list when the last known count came close to the capacity.
     uint2* d_cand = nullptr; uint2* d_pix = nullptr; uint32_t* d_cand_count = nullptr; uint32_t cand_cap = 0, pix_cap = 0;
     uint32_t* h_cand_count = nullptr;    // [0] box list, [1] pixel list
+    uint64_t lists_key = 0;              // launch geometry whose list sizes have been verified (0 = none)
     int force_scan_cols = 0;             // diagnostic override of the box columns per CTA: 0 = heuristic
     uint32_t force_bin_cap = 0, force_cand_cap = 0, force_pix_cap = 0;    // diagnostic: shrink the lists to exercise the overflow paths
     // per-bin triangle lists of the culled kernel
@@ -152,8 +154,8 @@ void free_frame(srt_ctx* c)
 {
     cudaFree(c->d_L); cudaFree(c->d_img); cudaFree(c->d_dist); cudaFree(c->d_ssum); cudaFree(c->d_hits);
     c->d_L = c->d_img = c->d_dist = nullptr; c->d_ssum = nullptr; c->d_hits = nullptr; c->frame_cap = 0;
-    cudaFree(c->d_hit_entries); cudaFree(c->d_hit_counts);
-    c->d_hit_entries = nullptr; c->d_hit_counts = nullptr; c->hit_pixels_cap = 0; c->hit_cap = 0;
+    cudaFree(c->d_hit_head); cudaFree(c->d_hit_next);
+    c->d_hit_head = nullptr; c->d_hit_next = nullptr; c->hit_pixels_cap = 0;
     cudaFree(c->d_cand); cudaFree(c->d_pix); cudaFree(c->d_cand_count); if (c->h_cand_count) cudaFreeHost(c->h_cand_count);
     c->d_cand = nullptr; c->d_pix = nullptr; c->d_cand_count = nullptr; c->h_cand_count = nullptr; c->cand_cap = 0; c->pix_cap = 0;
     cudaFree(c->d_bin_entries); cudaFree(c->d_bin_counts);
@@ -191,6 +193,31 @@ int ensure_mesh(srt_ctx* c, MeshBuf& m, size_t n, bool want_normals)
         m.cap = cap;
     }
     if (want_normals && !m.d_normals) SRT_CUDA(c, cudaMalloc(&m.d_normals, m.cap * 3 * sizeof(float)));
+    return SRT_OK;
+}
+
+// Work lists of the filtered path: at least `cand` {box, triangle} and `pix` {pixel, triangle} entries (only ever grows).
+int ensure_lists(srt_ctx* c, uint64_t cand, uint64_t pix)
+{
+    cand = std::min<uint64_t>(cand, 0xffffffffull); pix = std::min<uint64_t>(pix, 0xffffffffull);
+    if (!c->h_cand_count) {
+        SRT_CUDA(c, cudaHostAlloc(&c->h_cand_count, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+        c->h_cand_count[0] = c->h_cand_count[1] = 0;
+    }
+    if (!c->d_cand_count) SRT_CUDA(c, cudaMalloc(&c->d_cand_count, 2 * sizeof(uint32_t)));
+    if (cand > c->cand_cap) {
+        SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_cand); c->d_cand = nullptr; c->cand_cap = 0;
+        SRT_CUDA(c, cudaMalloc(&c->d_cand, cand * sizeof(uint2)));
+        c->cand_cap = (uint32_t)cand;
+    }
+    if (pix > c->pix_cap) {
+        SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_pix); cudaFree(c->d_hit_next); c->d_pix = nullptr; c->d_hit_next = nullptr; c->pix_cap = 0;
+        SRT_CUDA(c, cudaMalloc(&c->d_pix, pix * sizeof(uint2)));
+        SRT_CUDA(c, cudaMalloc(&c->d_hit_next, pix * sizeof(uint32_t)));
+        c->pix_cap = (uint32_t)pix;
+    }
     return SRT_OK;
 }
 
@@ -260,6 +287,7 @@ int pack_scene(srt_ctx* c, uint32_t box_px = SRT_BOX_PX, uint32_t box_py = SRT_B
     }
     SRT_CUDA(c, cudaMemcpyAsync(c->d_shade_meshes, c->h_shade.data(), nm * sizeof(srt::ShadeMesh), cudaMemcpyHostToDevice, c->stream));
     c->packed = true; c->box_px = box_px; c->box_py = box_py; c->scan_k = scan_k;
+    c->lists_key = 0;                                       // new scene / camera: the work-list sizes are unverified again
     return SRT_OK;
 }
 
@@ -340,8 +368,9 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     a.box_px = box_px; a.box_py = box_py; a.scan_k = scan_k;
     a.counters = nullptr;
     if (c->count_exact || audit) {
-        if (!c->d_counters) SRT_CUDA(c, cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)));
+        if (!c->d_counters) SRT_CUDA(c, cudaMalloc(&c->d_counters, 3 * sizeof(unsigned long long)));
         SRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+        SRT_CUDA(c, cudaMemsetAsync(c->d_counters + 2, 0x7f, sizeof(unsigned long long), c->stream));      // two large floats (3.4e38)
         a.counters = c->d_counters;
     }
 
@@ -384,7 +413,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         }
     }
 
-    a.scan_cols = 0; a.scan_chunks = 0; a.hit_entries = nullptr; a.hit_counts = nullptr; a.hit_cap = 0;
+    a.scan_cols = 0; a.scan_chunks = 0; a.hit_head = nullptr; a.hit_next = nullptr;
     uint32_t extra_launches = 0;
     if (kernel == SRT_KERNEL_FILTERED) {
         // CTA = (one 16-row block) x (scan_cols box columns) x (one chunk of 128 K triangles).  The work of a CTA is
@@ -411,52 +440,65 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         }
         if (c->force_scan_cols > 0) cols = std::min<uint32_t>((uint32_t)c->force_scan_cols, n_cols);
         a.scan_cols = cols; a.scan_chunks = chunks;
-        // per-pixel hit lists: 4 + 8 * cap bytes per pixel of the launch's output index range
+        // per-pixel hit lists: a 4-byte head per pixel of the launch's output index range (0xffffffff = empty; the
+        // resolve pass leaves them empty again), nodes in the pix list below
         const size_t pixels = (size_t)(parts == 0 ? cam.height : a.n_blocks * 16) * cam.width;
-        const uint32_t cap = pixels <= ((size_t)1 << 24) ? 12u : 8u;
-        if (pixels > c->hit_pixels_cap || cap != c->hit_cap) {
+        if (pixels > c->hit_pixels_cap) {
             SRT_CUDA(c, cudaStreamSynchronize(c->stream));
-            cudaFree(c->d_hit_entries); cudaFree(c->d_hit_counts); c->d_hit_entries = nullptr; c->d_hit_counts = nullptr;
-            c->hit_pixels_cap = 0;
-            SRT_CUDA(c, cudaMalloc(&c->d_hit_entries, pixels * cap * sizeof(uint2)));
-            SRT_CUDA(c, cudaMalloc(&c->d_hit_counts, pixels * sizeof(uint32_t)));
-            SRT_CUDA(c, cudaMemsetAsync(c->d_hit_counts, 0, pixels * sizeof(uint32_t), c->stream));
-            c->hit_pixels_cap = pixels; c->hit_cap = cap;
+            cudaFree(c->d_hit_head); c->d_hit_head = nullptr; c->hit_pixels_cap = 0;
+            SRT_CUDA(c, cudaMalloc(&c->d_hit_head, pixels * sizeof(uint32_t)));
+            SRT_CUDA(c, cudaMemsetAsync(c->d_hit_head, 0xff, pixels * sizeof(uint32_t), c->stream));
+            c->hit_pixels_cap = pixels;
         }
-        a.hit_entries = c->d_hit_entries; a.hit_counts = c->d_hit_counts; a.hit_cap = cap;
-        // candidate lists: 8 bytes per survivor of the scan {box, triangle} (3e-4 of the box tests on the dragon) and per
-        // survivor of the per-pixel strip tests {pixel, triangle} (~ the hits).  Sized from the scene, grown when the
-        // counts of an earlier render (read back asynchronously) came within a factor 2 of the capacity.
-        if (!c->h_cand_count) {
-            SRT_CUDA(c, cudaHostAlloc(&c->h_cand_count, 2 * sizeof(uint32_t), cudaHostAllocDefault));
-            c->h_cand_count[0] = c->h_cand_count[1] = 0;
-        }
-        uint64_t want_cap = std::max<uint64_t>(4ull << 20, 32ull * c->total_tris);
-        uint64_t want_pix = std::max<uint64_t>(16ull << 20, 128ull * c->total_tris);
-        want_cap = std::min<uint64_t>(std::max<uint64_t>(want_cap, 2ull * c->h_cand_count[0]), 0xffffffffull);
-        want_pix = std::min<uint64_t>(std::max<uint64_t>(want_pix, 2ull * c->h_cand_count[1]), 0xffffffffull);
-        if (want_cap > c->cand_cap || want_pix > c->pix_cap) {
-            SRT_CUDA(c, cudaStreamSynchronize(c->stream));
-            cudaFree(c->d_cand); cudaFree(c->d_pix); c->d_cand = nullptr; c->d_pix = nullptr; c->cand_cap = 0; c->pix_cap = 0;
-            SRT_CUDA(c, cudaMalloc(&c->d_cand, want_cap * sizeof(uint2)));
-            SRT_CUDA(c, cudaMalloc(&c->d_pix, want_pix * sizeof(uint2)));
-            c->cand_cap = (uint32_t)want_cap; c->pix_cap = (uint32_t)want_pix;
-        }
-        if (!c->d_cand_count) SRT_CUDA(c, cudaMalloc(&c->d_cand_count, 2 * sizeof(uint32_t)));
-        SRT_CUDA(c, cudaMemsetAsync(c->d_cand_count, 0, 2 * sizeof(uint32_t), c->stream));
-        a.cand = c->d_cand; a.pix = c->d_pix; a.cand_count = c->d_cand_count; a.cand_cap = c->cand_cap; a.pix_cap = c->pix_cap;
+        a.hit_head = c->d_hit_head;
+        // candidate lists: 8 bytes per survivor of the scan {box, triangle} (3e-4 of the box tests on the dragon) and 12 per
+        // survivor of the per-pixel strip tests {pixel, triangle} (~ the hits).  First sized from the scene; the first
+        // render of a launch geometry then CHECKS the counts (one synchronisation, below) and grows the lists to twice
+        // what that frame needed -- the counts of a scene / camera / launch geometry never change afterwards.
+        rc = ensure_lists(c, std::max<uint64_t>(4ull << 20, 32ull * c->total_tris), std::max<uint64_t>(16ull << 20, 64ull * c->total_tris));
+        if (rc) return rc;
+        a.cand = c->d_cand; a.pix = c->d_pix; a.hit_next = c->d_hit_next; a.cand_count = c->d_cand_count;
+        a.cand_cap = c->cand_cap; a.pix_cap = c->pix_cap;
         if (c->force_cand_cap) a.cand_cap = std::min(a.cand_cap, c->force_cand_cap);
         if (c->force_pix_cap) a.pix_cap = std::min(a.pix_cap, c->force_pix_cap);
         if (c->n_meshes > 32 || c->total_tris >= (1ull << 27)) kernel = SRT_KERNEL_EXACT;     // candidate entries: 5-bit mesh, 27-bit triangle
     }
     SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     if (kernel == SRT_KERNEL_FILTERED) {
-        SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
-        SRT_CUDA(c, srt::launch_lbuffer_filtered(a, c->stream));
-        SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
-        SRT_CUDA(c, srt::launch_filtered_candidates(a, c->stream));
+        // launch geometry the list sizes were verified for (scene / camera changes reset it through `packed`)
+        const uint64_t key = ((uint64_t)row_begin << 40) ^ ((uint64_t)row_end << 20) ^ ((uint64_t)parts << 12) ^ ((uint64_t)part << 4) ^
+                             ((uint64_t)mode << 2) ^ (all ? 2u : 0u) ^ ((uint64_t)box_px << 52) ^ ((uint64_t)box_py << 58) ^ 1u;
+        const bool forced = c->force_cand_cap || c->force_pix_cap;              // tests exercise the overflow fallback
+        const bool verify = !forced && (repack || c->lists_key != key);
+        for (int attempt = 0;; ++attempt) {
+            SRT_CUDA(c, cudaMemsetAsync(c->d_cand_count, 0, 2 * sizeof(uint32_t), c->stream));
+            SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+            SRT_CUDA(c, srt::launch_lbuffer_filtered(a, c->stream));
+            SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+            SRT_CUDA(c, srt::launch_filtered_candidates(a, c->stream));
+            SRT_CUDA(c, cudaMemcpyAsync(c->h_cand_count, c->d_cand_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            if (!verify) break;
+            // First render of this launch geometry: wait for the counts.  A list that overflowed would make the resolve pass
+            // recompute every pixel with the exact sequence (correct, but hours on a large scene): grow and redo instead.
+            SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+            const uint64_t n_cand = c->h_cand_count[0], n_pix = c->h_cand_count[1];
+            if (n_cand <= a.cand_cap && n_pix <= a.pix_cap) {
+                c->lists_key = key;
+                // keep twice the need (other launch geometries of the same scene, e.g. shares of a multi-GPU frame, need less)
+                break;
+            }
+            if (attempt >= 4) break;                                   // give up growing: the resolve pass stays exact
+            // the pixel count of a truncated box list is a lower bound: grow it generously, the next attempt measures it
+            rc = ensure_lists(c, 2 * n_cand, std::max<uint64_t>(2 * n_pix, n_cand <= a.cand_cap ? 0 : 4 * n_pix));
+            if (rc) return rc;
+            // the exact-test stage has appended hits to the pixels' lists: empty them again before the next attempt
+            {
+                const size_t px = (size_t)(parts == 0 ? cam.height : a.n_blocks * 16) * cam.width;
+                SRT_CUDA(c, cudaMemsetAsync(c->d_hit_head, 0xff, px * sizeof(uint32_t), c->stream));
+            }
+            a.cand = c->d_cand; a.pix = c->d_pix; a.hit_next = c->d_hit_next; a.cand_cap = c->cand_cap; a.pix_cap = c->pix_cap;
+        }
         SRT_CUDA(c, srt::launch_resolve_hits(a, c->stream)); extra_launches = 3;          // + candidates, exact tests
-        SRT_CUDA(c, cudaMemcpyAsync(c->h_cand_count, c->d_cand_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     } else if (kernel == SRT_KERNEL_CULLED) {
         SRT_CUDA(c, srt::launch_lbuffer_bins(a, c->stream)); extra_launches = 1;
         SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
@@ -636,6 +678,53 @@ int srt_host_alloc(void** out, size_t bytes)
 }
 
 void srt_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- JPEG output (nvJPEG: the encoder runs on the GPU; replaces the libjpeg writers of src/Image.cxx:85-146 and
+// src/Image.bakk.cxx:170-226 -- quality 100, no chroma subsampling) ---------------------------------
+int srt_write_jpeg(srt_ctx* c, const char* path, const uint8_t* rgb, uint32_t width, uint32_t height, int quality)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (!path || !rgb || width == 0 || height == 0 || quality < 1 || quality > 100)
+        return fail(c, SRT_ERR_INVALID, "srt_write_jpeg: bad arguments");
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)width * height * 3;
+    if (bytes > c->rgb_cap) {
+        SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_rgb); c->d_rgb = nullptr; c->rgb_cap = 0;
+        SRT_CUDA(c, cudaMalloc(&c->d_rgb, bytes)); c->rgb_cap = bytes;
+    }
+    SRT_CUDA(c, cudaMemcpyAsync(c->d_rgb, rgb, bytes, cudaMemcpyHostToDevice, c->stream));
+    nvjpegHandle_t h = nullptr; nvjpegEncoderState_t st = nullptr; nvjpegEncoderParams_t ep = nullptr;
+    auto cleanup = [&]() {
+        if (ep) nvjpegEncoderParamsDestroy(ep);
+        if (st) nvjpegEncoderStateDestroy(st);
+        if (h) nvjpegDestroy(h);
+    };
+#define SRT_NVJPEG(call) do { const nvjpegStatus_t s__ = (call); if (s__ != NVJPEG_STATUS_SUCCESS) { cleanup(); \
+        return fail(c, SRT_ERR_CUDA, "%s: nvjpeg status %d", #call, (int)s__); } } while (0)
+    SRT_NVJPEG(nvjpegCreateSimple(&h));
+    SRT_NVJPEG(nvjpegEncoderStateCreate(h, &st, c->stream));
+    SRT_NVJPEG(nvjpegEncoderParamsCreate(h, &ep, c->stream));
+    SRT_NVJPEG(nvjpegEncoderParamsSetQuality(ep, quality, c->stream));
+    SRT_NVJPEG(nvjpegEncoderParamsSetSamplingFactors(ep, NVJPEG_CSS_444, c->stream));
+    nvjpegImage_t img{};
+    img.channel[0] = c->d_rgb; img.pitch[0] = (size_t)width * 3;
+    SRT_NVJPEG(nvjpegEncodeImage(h, st, ep, &img, NVJPEG_INPUT_RGBI, (int)width, (int)height, c->stream));
+    size_t len = 0;
+    SRT_NVJPEG(nvjpegEncodeRetrieveBitstream(h, st, nullptr, &len, c->stream));
+    std::vector<unsigned char> buf(len);
+    SRT_NVJPEG(nvjpegEncodeRetrieveBitstream(h, st, buf.data(), &len, c->stream));
+#undef SRT_NVJPEG
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(c, SRT_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
+    std::FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(c, SRT_ERR_INVALID, "Cannot create the file %s", path);
+    const size_t w = std::fwrite(buf.data(), 1, len, f);
+    std::fclose(f);
+    if (w != len) return fail(c, SRT_ERR_INVALID, "short write to %s", path);
+    return SRT_OK;
+}
 
 // ---- scene --------------------------------------------------------------------
 int srt_set_meshes(srt_ctx* c, int n_meshes, const srt_mesh_desc* meshes)
@@ -947,10 +1036,12 @@ int srt_last_timing(srt_ctx* c, srt_timing* out)
         SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
         SRT_CUDA(c, cudaEventElapsedTime(&c->timing.main_kernel_ms, c->ev[4], c->ev[5]));
         if (c->counters_pending && c->d_counters) {
-            unsigned long long cnts[2] = { 0, 0 };
+            unsigned long long cnts[3] = { 0, 0, 0 };
             SRT_CUDA(c, cudaMemcpyAsync(cnts, c->d_counters, sizeof cnts, cudaMemcpyDeviceToHost, c->stream));
             SRT_CUDA(c, cudaStreamSynchronize(c->stream));
             c->timing.exact_tests = cnts[0]; c->timing.filter_violations = cnts[1];
+            std::memcpy(&c->timing.min_strip_slack, &cnts[2], sizeof(float));
+            std::memcpy(&c->timing.min_box_slack, (const char*)&cnts[2] + sizeof(float), sizeof(float));
         }
         c->timing_pending = false; c->counters_pending = false;
     }

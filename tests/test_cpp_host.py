@@ -132,3 +132,29 @@ def test_shaded_render_loop_cpp(host_bins, tmp_path):
     want = np.load(GOLDEN / "shaded_dragon_logo_128.npz")["rgb_noise"]
     diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
     assert diff.max() <= 1 and (diff == 0).mean() >= 0.999
+
+
+@pytest.mark.gpu
+def test_jpeg_writer_matches_the_8bit_lut_image(tmp_path):
+    """srt_write_jpeg (nvJPEG on the GPU; replaces Image::saveJPEGFile, src/Image.cxx:85-146): the decoded file must be
+    the 8-bit LUT image up to JPEG quantisation at quality 100 / 4:4:4 (mean error < 1 level, no pixel off by more than 8)."""
+    from PIL import Image as PILImage
+    from simpleraytracing_b200 import Context, Library, scene
+    lib = Library(); ctx = Context(0, lib)
+    tri = scene.dragon()
+    lo, hi = lib.scene_bbox([(tri, 0.1037)])
+    ctx.set_meshes([(tri, 0.1037)]); ctx.set_camera(lib.camera_from_bbox(lo, hi, 320, 200))
+    img = ctx.render_xray(lib.default_params()).reshape(200, 320)
+    lut = np.round(255.0 * np.clip(np.nan_to_num(img, nan=0.0), 0, 80) / 80.0).astype(np.uint8)      # applyLUT(0, 80)
+    rgb = np.repeat(lut[:, :, None], 3, axis=2)
+    ctx.write_jpeg(tmp_path / "xray.jpg", rgb, quality=100)
+    back = np.asarray(PILImage.open(tmp_path / "xray.jpg").convert("RGB"))
+    assert back.shape == rgb.shape
+    d = np.abs(back.astype(np.int32) - rgb.astype(np.int32))
+    assert d.mean() < 1.0 and d.max() <= 8, (d.mean(), d.max())
+    # a colour image (the shaded variant's output format)
+    col = scene.noise_texture(64, 96)
+    ctx.write_jpeg(tmp_path / "c.jpg", col, quality=100)
+    back = np.asarray(PILImage.open(tmp_path / "c.jpg").convert("RGB"))
+    assert np.abs(back.astype(np.int32) - col.astype(np.int32)).mean() < 2.0
+    ctx.close()

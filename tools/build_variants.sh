@@ -12,7 +12,7 @@ while [ $# -ge 2 ]; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ftz=false -prec-div=true -prec-sqrt=true $flags -c $SRC/kernels.cu -o $tmp/kernels.o
   g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -I$ROOT/include -I/usr/local/cuda/include $flags -c $SRC/prepack.cpp -o $tmp/prepack.o
   g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -I$ROOT/include -I/usr/local/cuda/include $flags -c $SRC/srt_api.cpp -o $tmp/srt_api.o
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libsrt_b200_$name.so $tmp/kernels.o $tmp/prepack.o $tmp/srt_api.o -cudart static
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libsrt_b200_$name.so $tmp/kernels.o $tmp/prepack.o $tmp/srt_api.o -cudart static -L/usr/local/cuda/lib64 -lnvjpeg -Xlinker -rpath,/usr/local/cuda/lib64
   rm -rf $tmp
   echo built $name
 done
