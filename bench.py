@@ -25,7 +25,8 @@ Keys of the JSON line (see the task contract):
                SM clock sampled under load.  The FP32 figure SURVEY 8d asks for is kept as `fp32_equivalent`.
   cpu_baseline the reference's CPU implementation (oracle/_ref, else the oracle port) on a bounded sample of the same
                frame on the host cores (rank 0, N = 1 only)
-  accelerated  the same frame through SRT_KERNEL_CULLED (hierarchical conservative culling; identical results)
+  accelerated  the same frame through SRT_KERNEL_AUTO, the library's default (hierarchical conservative culling;
+               identical results)
 
 --impl reference times that CPU implementation as the bench arm itself.
 """
@@ -79,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
@@ -239,7 +240,7 @@ def load_counters(kernel_name, shape, W, world):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from simpleraytracing_b200 import Context, Library, PinnedArray, KERNEL_CULLED, KERNEL_FILTERED
+    from simpleraytracing_b200 import Context, Library, PinnedArray, KERNEL_AUTO, KERNEL_CULLED, KERNEL_FILTERED
     from simpleraytracing_b200.bands import BandLayout, InterleavedLayout, PeerFrames
     from simpleraytracing_b200.capi import Camera
 
@@ -273,7 +274,7 @@ def run_ours(args):
     ctx.set_meshes(meshes)
     ctx.set_camera(cam)
     params = lib.default_params(kernel=args.kernel, pixels_per_thread=args.box)
-    params_acc = lib.default_params(kernel=KERNEL_CULLED)
+    params_acc = lib.default_params(kernel=KERNEL_AUTO)           # the library's default: culled (exact for a handful of triangles)
 
     lay = BandLayout(H, W, world, rank)
     frame = lay.new_frame(torch.float32, dev)
@@ -453,7 +454,7 @@ def run_ours(args):
         acc_e2e_ms = timed(lambda: step_e2e_sharded(params_acc), e2e_steps, 2, sync_each=True)
         e2e_path = "per rank: srt_set_meshes + srt_set_camera + sharded render + assembly + repair; image to pinned host memory on rank 0"
 
-    # the accelerated path (not the headline): same frame, same step, SRT_KERNEL_CULLED
+    # the accelerated path (not the headline): same frame, same step, SRT_KERNEL_AUTO
     note("accelerated path")
     ctx.set_meshes(meshes); ctx.set_camera(cam)
     acc_ms = timed(lambda: step_device(params_acc), steps, 3, sync_each=False)
@@ -569,7 +570,8 @@ def run_ours(args):
             "clocks": clocks,
             "per_rank": None if world == 1 else {"render_pass_ms": per_rank_kernel,
                                                  "step_ms": [round(v, 4) for v in per_rank_ms[0]]},
-            "accelerated": {"kernel": acc_kernel_used, "kernel_name": "SRT_KERNEL_CULLED (bins + CTA tiles + pixel runs, identical results)",
+            "accelerated": {"kernel": acc_kernel_used,
+                            "kernel_name": "SRT_KERNEL_AUTO, the library default: 4 = culled (bins + CTA tiles + pixel runs), 1 = exact kernel for a handful of triangles; identical results",
                             "ms_per_step": acc_ms / steps, "value": tests_frame * steps / (acc_ms * 1e-3),
                             "unit": "tests/s (pairs resolved, most of them by a conservative box test)",
                             "e2e_ms_per_step": acc_e2e_ms / e2e_steps,
