@@ -460,6 +460,41 @@ def run_ours(args):
     acc_ms = timed(lambda: step_device(params_acc), steps, 3, sync_each=False)
     acc_kernel_used = ctx.timing().kernel_used
 
+    # the shaded variant of the same frame size (main-omp.cxx: dragon + textured quad, closest hit, Phong, shadow
+    # rays, texture), through the host-pointer call; N = 1, dragon configs only.  Not part of the headline.
+    shaded = None
+    if world == 1 and args.config in ("c2", "c3") and not args.no_shaded:
+        note("shaded variant")
+        from simpleraytracing_b200 import scene as scene_
+        sctx = Context(local, lib)
+        smeshes = scene_.shaded_scene(texture=scene_.noise_texture())
+        scam, slight = scene_.shaded_camera(lib, smeshes, W, H)
+        sctx.set_meshes(smeshes); sctx.set_camera(scam)
+        p_sh = lib.default_params()
+        sctx.render_shaded(p_sh, slight)
+        first = sctx.timing()
+        rows_ = []
+        for _ in range(5):
+            flush.fill_(1); torch.cuda.synchronize()
+            t0_ = time.perf_counter()
+            sctx.render_shaded(p_sh, slight)
+            wall = (time.perf_counter() - t0_) * 1e3
+            t_ = sctx.timing()
+            rows_.append((wall, t_.render_ms, t_.repair_ms))
+        brute = None
+        if W * H <= 1024 * 1024 or args.shaded_brute_force:
+            sctx.force_shadow_grid(-1)
+            sctx.render_shaded(p_sh, slight)
+            brute = sctx.timing().repair_ms
+        med = np.median(np.array(rows_), axis=0)
+        shaded = {"workload": f"shaded {W}x{H}: dragon + textured quad ({sum(len(m['tri']) for m in smeshes)} triangles), light of main-omp.cxx",
+                  "e2e_ms_per_frame": float(med[0]), "closest_hit_pass_ms": float(med[1]), "shade_pass_ms": float(med[2]),
+                  "shadow_grid": {"cells_per_side": int(first.shadow_grid_cells), "list_entries": int(first.shadow_grid_entries),
+                                  "build_ms_first_frame": float(first.shadow_grid_ms)},
+                  "shade_pass_ms_without_grid": brute,
+                  "d2h_bytes_per_frame": 3 * W * H}
+        sctx.close()
+
     # ---- correctness of the assembled frame (outside every timed region).  The frame a rank holds after a sharded
     # step must equal, bit for bit, the image of one unsharded render on this GPU.  The check alternates between two
     # cameras and poisons every rank's frame buffers with NaN before each sharded step, so a lost or late peer store
@@ -570,6 +605,7 @@ def run_ours(args):
             "clocks": clocks,
             "per_rank": None if world == 1 else {"render_pass_ms": per_rank_kernel,
                                                  "step_ms": [round(v, 4) for v in per_rank_ms[0]]},
+            "shaded": shaded,
             "accelerated": {"kernel": acc_kernel_used,
                             "kernel_name": "SRT_KERNEL_AUTO, the library default: 4 = culled (bins + CTA tiles + pixel runs), 1 = exact kernel for a handful of triangles; identical results",
                             "ms_per_step": acc_ms / steps, "value": tests_frame * steps / (acc_ms * 1e-3),
@@ -601,6 +637,9 @@ def main():
     ap.add_argument("--verify-iters", type=int, default=50, help="N > 1: sharded frames checked against unsharded renders")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-shaded", action="store_true", help="skip the shaded-variant block (N = 1, dragon configs)")
+    ap.add_argument("--shaded-brute-force", action="store_true",
+                    help="also time the shade pass without the shadow grid at sizes above 1024^2 (seconds per frame)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.config == "c5" and args.steps > 5 and "--steps" not in " ".join(sys.argv):

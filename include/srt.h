@@ -138,6 +138,11 @@ typedef struct {
     float    min_box_slack;     /* the same for the level-0 box bounds: (R - (|Y(c)| - |D(c)|)) / 2m; the box radii
                                    in R are exact geometry, so 0.5 is the geometric worst case (a hit on the
                                    strip's edge at a box corner)                                       */
+    float    shadow_grid_ms;    /* srt_render_shaded: device + host time spent (re)building the shadow rays' grid
+                                   (0 when the grid of the previous call was reused); repair_ms = the shade pass */
+    uint32_t shadow_grid_cells; /* cells per side of that grid; 0 = brute force (light inside the scene's box)  */
+    uint32_t shadow_grid_entries;
+    uint32_t shadow_grid_rebuilt;
 } srt_timing;
 
 /* ---- context ------------------------------------------------------------ */
@@ -267,7 +272,9 @@ int  srt_multi_last_timing(srt_multi* m, float* render_ms_per_device, float* ste
 /*
  * Closest hit over ALL meshes (z-buffer, strict `>`, ascending triangle order, negative t accepted), Phong
  * shading with the hit triangle's cached normal and its mesh's material, shadow ray against every other
- * triangle (t > 1e-7 => colour * 0.25), area-barycentric nearest-texel lookup for textured meshes, clamp +
+ * triangle (t > 1e-7 => colour * 0.25; "any blocker" does not depend on the order, so each ray only runs the
+ * reference's test on the triangles whose projection from the light can cover it -- a grid in light space, see
+ * kernels.h ShadowGrid), area-barycentric nearest-texel lookup for textured meshes, clamp +
  * int() truncation to 8 bits.  rgb_out: width*height*3 bytes, row-major; pixels without a hit get
  * background_rgb (the reference's Image(width, height, r, g, b) initial colour).  The camera's
  * pixel_spacing must be the one of the shaded drivers (from the bbox of all meshes, :594-607).
@@ -276,8 +283,12 @@ int  srt_render_shaded(srt_ctx* ctx, const srt_params* params, const srt_light* 
                        const uint8_t background_rgb[3], uint8_t* rgb_out);
 int  srt_render_shaded_device(srt_ctx* ctx, const srt_params* params, const srt_light* light,
                               const uint8_t background_rgb[3], uint8_t* d_rgb, uint8_t* d_shadow_or_null);
-/* Diagnostic: z-buffer and scene-wide triangle index per pixel of the last shaded render. */
-int  srt_debug_shaded_buffers(srt_ctx* ctx, float* z_out, int32_t* tri_id_out);
+/* Diagnostic: z-buffer, scene-wide triangle index and shadow flag (1 = shadow ray blocked) per pixel of the last shaded
+ * render; any pointer may be NULL.  The flags are only kept when the render was given no shadow buffer of its own. */
+int  srt_debug_shaded_buffers(srt_ctx* ctx, float* z_out, int32_t* tri_id_out, uint8_t* shadow_out);
+/* Diagnostic: cells per side of the light-space grid the shadow rays look their blockers up in (0 = heuristic,
+ * < 0 = no grid: every shadow ray tests every triangle like the reference's loop; identical images). */
+int  srt_debug_force_shadow_grid(srt_ctx* ctx, int cells_per_side);
 
 /* Last-call timings and counters (waits for the last render on the stream to finish). */
 int  srt_last_timing(srt_ctx* ctx, srt_timing* out);

@@ -51,7 +51,9 @@ class Timing(C.Structure):
     _fields_ = [("render_ms", C.c_float), ("repair_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("pair_tests", C.c_uint64), ("exact_tests", C.c_uint64), ("filter_violations", C.c_uint64),
                 ("kernel_used", C.c_uint32), ("launches", C.c_uint32), ("main_kernel_ms", C.c_float),
-                ("scan_cols", C.c_uint32), ("min_strip_slack", C.c_float), ("min_box_slack", C.c_float)]
+                ("scan_cols", C.c_uint32), ("min_strip_slack", C.c_float), ("min_box_slack", C.c_float),
+                ("shadow_grid_ms", C.c_float), ("shadow_grid_cells", C.c_uint32), ("shadow_grid_entries", C.c_uint32),
+                ("shadow_grid_rebuilt", C.c_uint32)]
 
 
 # every symbol include/srt.h declares (tests/test_abi.py checks the .so exports all of them)
@@ -61,7 +63,7 @@ EXPORTS = [
     "srt_set_meshes", "srt_set_camera", "srt_render_lbuffer", "srt_render_lbuffer_device", "srt_repair",
     "srt_repair_device", "srt_render_xray", "srt_interleave_slot_rows",
     "srt_render_lbuffer_interleaved_device", "srt_deinterleave_device", "srt_render_lbuffer_blocks_device", "srt_render_shaded",
-    "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_force_scan_cols", "srt_debug_force_list_caps", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_pack_info", "srt_debug_download_packed",
+    "srt_render_shaded_device", "srt_debug_shaded_buffers", "srt_last_timing", "srt_debug_count_exact", "srt_debug_force_scan_cols", "srt_debug_force_list_caps", "srt_debug_force_shadow_grid", "srt_debug_prepack", "srt_debug_ffma_peak", "srt_debug_pack_info", "srt_debug_download_packed",
     "srt_host_alloc", "srt_host_free", "srt_write_jpeg", "srt_render_xray_sorted", "srt_render_xray_sorted_device",
     "srt_multi_create", "srt_multi_destroy", "srt_multi_last_error", "srt_multi_device_count", "srt_multi_set_meshes",
     "srt_multi_set_camera", "srt_multi_render_xray_device", "srt_multi_synchronize", "srt_multi_frame",
@@ -114,7 +116,8 @@ class Library:
         L.srt_deinterleave_device.argtypes = [vp, u32, vp, vp]
         L.srt_render_shaded.argtypes = [vp, C.POINTER(Params), C.POINTER(Light), vp, vp]
         L.srt_render_shaded_device.argtypes = [vp, C.POINTER(Params), C.POINTER(Light), vp, vp, vp]
-        L.srt_debug_shaded_buffers.argtypes = [vp, vp, vp]
+        L.srt_debug_shaded_buffers.argtypes = [vp, vp, vp, vp]
+        L.srt_debug_force_shadow_grid.argtypes = [vp, C.c_int]
         L.srt_repair.argtypes = [vp, C.POINTER(Params), vp, vp]
         L.srt_repair_device.argtypes = [vp, C.POINTER(Params), vp, vp]
         L.srt_render_xray.argtypes = [vp, C.POINTER(Params), vp]
@@ -353,8 +356,17 @@ class Context:
     def shaded_buffers(self):
         n = self.cam.width * self.cam.height
         z = np.empty(n, np.float32); tid = np.empty(n, np.int32)
-        self._ck(self.lib.srt_debug_shaded_buffers(self.h, _ptr(z, np.float32), _ptr(tid, np.int32)))
+        self._ck(self.lib.srt_debug_shaded_buffers(self.h, _ptr(z, np.float32), _ptr(tid, np.int32), None))
         return z, tid
+
+    def shadow_flags(self):
+        """-> uint8 [H*W]: 1 where the shadow ray of the last shaded render was blocked"""
+        sh = np.empty(self.cam.width * self.cam.height, np.uint8)
+        self._ck(self.lib.srt_debug_shaded_buffers(self.h, None, None, _ptr(sh, np.uint8)))
+        return sh
+
+    def force_shadow_grid(self, cells_per_side):
+        self._ck(self.lib.srt_debug_force_shadow_grid(self.h, int(cells_per_side)))
 
     def repair(self, params, L):
         L = np.ascontiguousarray(L, np.float32).reshape(-1)

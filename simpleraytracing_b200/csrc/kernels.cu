@@ -21,7 +21,9 @@
 // shade_kernel, repair_kernel, deinterleave_kernel, prepack_kernel, offsets_kernel.
 #include "kernels.h"
 
+#include <algorithm>
 #include <cfloat>
+#include <cstring>
 
 #include "prepack_math.h"
 
@@ -1126,6 +1128,115 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
     if (a.counters && n_exact) atomicAdd(a.counters, n_exact);
 }
 
+// ------------------------------------------------------------------ shadow grid
+__device__ __forceinline__ uint32_t float_to_ordered_key(float f)
+{
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__device__ __forceinline__ int mesh_of(const ShadeMesh* meshes, int n_meshes, uint32_t g)
+{
+    int m = 0;
+    while (m + 1 < n_meshes && g >= meshes[m + 1].first) ++m;
+    return m;
+}
+
+__global__ void __launch_bounds__(256) scene_bbox_kernel(const ShadeMesh* meshes, int n_meshes, uint32_t total, uint32_t* out6)
+{
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+        const ShadeMesh M = meshes[mesh_of(meshes, n_meshes, g)];
+        const float* v = M.vertices + 9 * (size_t)(g - M.first);
+        for (int k = 0; k < 9; ++k) { const float x = __ldg(v + k); if (x == x) { lo[k % 3] = fminf(lo[k % 3], x); hi[k % 3] = fmaxf(hi[k % 3], x); } }
+    }
+    for (int k = 0; k < 3; ++k) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(out6 + k, float_to_ordered_key(lo[k]));
+            atomicMax(out6 + 3 + k, float_to_ordered_key(hi[k]));
+        }
+    }
+}
+
+// central projection of X from the light: (a, b) = (q.u, q.v) / q.w; false when X is too close to the plane through
+// the light perpendicular to w
+__device__ __forceinline__ bool light_project(const ShadowGrid& g, const float* L, float x, float y, float z, float& pa, float& pb, float& depth)
+{
+    const float qx = x - L[0], qy = y - L[1], qz = z - L[2];
+    depth = fmaf(qx, g.w[0], fmaf(qy, g.w[1], qz * g.w[2]));
+    const float qn = fabsf(qx) + fabsf(qy) + fabsf(qz);
+    if (!(fabsf(depth) > 1e-3f * qn)) return false;                      // also NaN
+    const float inv = 1.0f / depth;
+    pa = fmaf(qx, g.u[0], fmaf(qy, g.u[1], qz * g.u[2])) * inv;
+    pb = fmaf(qx, g.v[0], fmaf(qy, g.v[1], qz * g.v[2])) * inv;
+    return true;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) shadow_bin_kernel(const __grid_constant__ ShadeArgs a)
+{
+    const ShadowGrid& g = a.grid;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.total_tris) return;
+    const ShadeMesh M = a.meshes[mesh_of(a.meshes, a.n_meshes, t)];
+    const float* v = M.vertices + 9 * (size_t)(t - M.first);
+    float pa[3], pb[3], dp[3];
+    bool ok = true;
+    for (int k = 0; k < 3; ++k) ok = light_project(g, a.light_position, __ldg(v + 3 * k), __ldg(v + 3 * k + 1), __ldg(v + 3 * k + 2), pa[k], pb[k], dp[k]) && ok;
+    ok = ok && ((dp[0] > 0.0f) == (dp[1] > 0.0f)) && ((dp[0] > 0.0f) == (dp[2] > 0.0f));     // all on one side of the light
+    int ia0 = 0, ia1 = -1, ib0 = 0, ib1 = -1;
+    if (ok) {
+        const float amin = fminf(pa[0], fminf(pa[1], pa[2])), amax = fmaxf(pa[0], fmaxf(pa[1], pa[2]));
+        const float bmin = fminf(pb[0], fminf(pb[1], pb[2])), bmax = fmaxf(pb[0], fmaxf(pb[1], pb[2]));
+        // cell range widened by one cell on every side, clamped to the grid (queries outside the grid use brute force)
+        const float fa0 = floorf((amin - g.a0) * g.inv_da) - 1.0f, fa1 = floorf((amax - g.a0) * g.inv_da) + 1.0f;
+        const float fb0 = floorf((bmin - g.b0) * g.inv_db) - 1.0f, fb1 = floorf((bmax - g.b0) * g.inv_db) + 1.0f;
+        ok = fa0 == fa0 && fa1 == fa1 && fb0 == fb0 && fb1 == fb1;       // NaN: every ray tests it
+        if (ok) {
+            const float Gf = (float)g.G;
+            ia0 = (int)fminf(fmaxf(fa0, 0.0f), Gf); ia1 = (int)fminf(fmaxf(fa1, -1.0f), Gf - 1.0f);
+            ib0 = (int)fminf(fmaxf(fb0, 0.0f), Gf); ib1 = (int)fminf(fmaxf(fb1, -1.0f), Gf - 1.0f);
+        }
+    }
+    const long long cells = ok ? (long long)max(0, ia1 - ia0 + 1) * (long long)max(0, ib1 - ib0 + 1) : 0;
+    if (!ok || cells > (long long)kShadowMaxCells) {
+        if (FILL) g.global_tris[atomicAdd(g.n_global, 1u)] = t;
+        return;
+    }
+    for (int ib = ib0; ib <= ib1; ++ib)
+        for (int ia = ia0; ia <= ia1; ++ia) {
+            const uint32_t cell = (uint32_t)ib * g.G + (uint32_t)ia;
+            if (FILL) g.cell_tris[atomicAdd(g.cell_cursor + cell, 1u)] = t;
+            else atomicAdd(g.cell_off + cell, 1u);
+        }
+}
+
+// in-place exclusive scan of n values by one 1024-thread CTA (n ~ 2.6e5 cells: ~20 us)
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(uint32_t* data, uint32_t n)
+{
+    __shared__ uint32_t warp_sum[32];
+    const uint32_t per = (n + 1023) / 1024, lo = threadIdx.x * per, hi = min(n, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += data[i];
+    uint32_t incl = sum;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += u; }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = warp_sum[lane];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, v, o); if ((int)lane >= o) v += u; }
+        warp_sum[lane] = v;
+    }
+    __syncthreads();
+    uint32_t run = incl - sum + (warp ? warp_sum[warp - 1] : 0u);
+    for (uint32_t i = lo; i < hi; ++i) { const uint32_t c = data[i]; data[i] = run; run += c; }
+}
+
 // ------------------------------------------------------------------ shade kernel
 // Shaded variant, second pass (src/main-omp.cxx:668-794): Phong shading of the closest hit, shadow ray against
 // every other triangle, area-barycentric texture lookup, clamp + truncation to 8 bits.  One thread per pixel.
@@ -1221,15 +1332,34 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Shad
     V3 sdir = { 0.0f, 0.0f, 0.0f };
     if (sl != 0.0f) sdir = { __fdiv_rn(sdir0.x, sl), __fdiv_rn(sdir0.y, sl), __fdiv_rn(sdir0.z, sl) };   // Ray::Ray
     bool in_shadow = false;
-    for (int m = 0; m < a.n_meshes && !in_shadow; ++m) {
-        const ShadeMesh S = a.meshes[m];
-#pragma unroll 1
-        for (uint32_t k = 0; k < S.n; ++k) {
-            if (S.first + k == (uint32_t)id) continue;                                // &triangle != p_intersected_triangle
-            const float* v = S.vertices + 9 * (size_t)k;
-            float ts;
-            if (intersect_generic(P, sdir, ld_v3(v), ld_v3(v + 3), ld_v3(v + 6), ts) && (double)ts > 0.0000001) { in_shadow = true; break; }
+    // blockers: the triangles of the ray's cell of the light-space grid + the short list every ray tests; brute force
+    // over the scene when there is no grid or the hit point has no projection inside it
+    auto blocked_by = [&](uint32_t g) {
+        if (g == (uint32_t)id) return false;                                      // &triangle != p_intersected_triangle
+        const ShadeMesh S = a.meshes[mesh_of(a.meshes, a.n_meshes, g)];
+        const float* v = S.vertices + 9 * (size_t)(g - S.first);
+        float ts;
+        return intersect_generic(P, sdir, ld_v3(v), ld_v3(v + 3), ld_v3(v + 6), ts) && (double)ts > 0.0000001;
+    };
+    bool use_grid = false;
+    uint32_t cell = 0;
+    if (a.grid.enabled) {
+        float pa, pb, dp;
+        if (light_project(a.grid, a.light_position, P.x, P.y, P.z, pa, pb, dp)) {
+            const float fa = floorf((pa - a.grid.a0) * a.grid.inv_da), fb = floorf((pb - a.grid.b0) * a.grid.inv_db);
+            if (fa >= 0.0f && fb >= 0.0f && fa < (float)a.grid.G && fb < (float)a.grid.G) {
+                use_grid = true;
+                cell = (uint32_t)fb * a.grid.G + (uint32_t)fa;
+            }
         }
+    }
+    if (use_grid) {
+        const uint32_t e0 = a.grid.cell_off[cell], e1 = a.grid.cell_off[cell + 1];
+        for (uint32_t e = e0; e < e1 && !in_shadow; ++e) in_shadow = blocked_by(a.grid.cell_tris[e]);
+        const uint32_t ng = *a.grid.n_global;
+        for (uint32_t e = 0; e < ng && !in_shadow; ++e) in_shadow = blocked_by(a.grid.global_tris[e]);
+    } else {
+        for (uint32_t g = 0; g < a.grid.total_tris && !in_shadow; ++g) in_shadow = blocked_by(g);
     }
     if (a.shadow) a.shadow[pixel] = in_shadow ? 1 : 0;
     if (in_shadow) {                                                                   // colour *= 0.25 (double)
@@ -1510,6 +1640,37 @@ cudaError_t launch_resolve_hits(const RenderArgs& a, cudaStream_t s)
     if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0) return cudaSuccess;
     dim3 grid((a.cam.W + 255) / 256, a.n_blocks * 16);
     resolve_hits_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scene_bbox(const ShadeMesh* meshes, int n_meshes, uint32_t total_tris, uint32_t* out6, cudaStream_t s)
+{
+    if (total_tris == 0) return cudaSuccess;
+    scene_bbox_kernel<<<(unsigned)std::min<uint64_t>(1184, ((uint64_t)total_tris + 255) / 256), 256, 0, s>>>(meshes, n_meshes, total_tris, out6);
+    return cudaGetLastError();
+}
+
+float ordered_key_to_float(uint32_t k)
+{
+    const uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    float f;
+    memcpy(&f, &b, sizeof f);
+    return f;
+}
+
+cudaError_t launch_shadow_bin(const ShadeArgs& a, int fill, cudaStream_t s)
+{
+    if (a.grid.total_tris == 0) return cudaSuccess;
+    const unsigned blocks = (a.grid.total_tris + 255) / 256;
+    if (fill) shadow_bin_kernel<true><<<blocks, 256, 0, s>>>(a);
+    else shadow_bin_kernel<false><<<blocks, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exclusive_scan(uint32_t* data, uint32_t n, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    exclusive_scan_kernel<<<1, 1024, 0, s>>>(data, n);
     return cudaGetLastError();
 }
 

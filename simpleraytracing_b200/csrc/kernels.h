@@ -102,6 +102,27 @@ struct ShadeMesh {
     float ka[3], kd[3], ks[3], shininess;
 };
 
+// Light-space grid for the shadow rays of the shaded variant.  Every shadow ray lies on a line through the light, so a
+// triangle can only block the ray of hit point P if its central projection from the light onto a plane (basis u, v,
+// axis w) covers P's projection.  Triangles are binned by the bounding box of their projected vertices, widened by one
+// cell on every side (float rounding of the reference's test moves a ray by ~1e-7 of its length; a cell is ~2e-3 of the
+// scene's extent); triangles that cross the plane through the light (no finite projection) or cover more than
+// kShadowMaxCells cells go to a short list every ray tests.  Each ray then runs the reference's exact test only on the
+// triangles of its cell: the boolean "any blocker" does not depend on the order.
+struct ShadowGrid {
+    int enabled;               // 0: brute force over all triangles (light inside the scene's bounding box, ...)
+    float u[3], v[3], w[3];    // orthonormal light-space basis
+    float a0, b0, inv_da, inv_db;   // grid origin and 1 / cell size in projected coordinates
+    uint32_t G;                // cells per side
+    uint32_t* cell_off;        // [G*G + 1] exclusive prefix of the cell counts (count pass: the counts)
+    uint32_t* cell_cursor;     // [G*G] fill pass: next free slot of each cell
+    uint32_t* cell_tris;       // scene-wide triangle indices, cell by cell
+    uint32_t* global_tris;     // triangles every ray tests
+    uint32_t* n_global;
+    uint32_t total_tris;
+};
+constexpr uint32_t kShadowMaxCells = 1024;
+
 struct ShadeArgs {
     DevCamera cam;
     const ShadeMesh* meshes;   // device array
@@ -113,8 +134,17 @@ struct ShadeArgs {
     uint8_t* shadow;           // optional: 1 where the shadow ray is blocked
     uint32_t row_begin, row_end;
     uint8_t background[3];
+    ShadowGrid grid;
 };
 cudaError_t launch_shade(const ShadeArgs& a, cudaStream_t s);
+// bounding box of all vertices of the scene: out6 = {min x, y, z, max x, y, z} as order-preserving unsigned keys
+// (decode with ordered_key_to_float); out6 must be preset to {0xffffffff x 3, 0 x 3}
+cudaError_t launch_scene_bbox(const ShadeMesh* meshes, int n_meshes, uint32_t total_tris, uint32_t* out6, cudaStream_t s);
+float ordered_key_to_float(uint32_t k);
+// shadow grid: count pass (fill = 0: cell_off receives the counts), in-place exclusive scan of cell_off[0 .. G*G],
+// fill pass (fill = 1: cell_cursor preset to cell_off)
+cudaError_t launch_shadow_bin(const ShadeArgs& a, int fill, cudaStream_t s);
+cudaError_t launch_exclusive_scan(uint32_t* data, uint32_t n, cudaStream_t s);
 
 // Exact kernel: every pair runs the reference op sequence. audit != 0 additionally evaluates the
 // filters for every pair and counts (filter says reject) && (exact says hit) into counters[1].

@@ -73,7 +73,7 @@ struct srt_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // render begin / end, repair begin / end, main kernel begin / end
+    cudaEvent_t ev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // render begin / end, repair (shade) begin / end, main kernel begin / end, shadow grid begin
     std::string error;
 
     std::vector<MeshBuf> meshes;
@@ -88,6 +88,14 @@ struct srt_ctx {
     std::vector<srt::ShadeMesh> h_shade; // shaded variant: per-mesh descriptors
     srt::ShadeMesh* d_shade_meshes = nullptr; size_t shade_cap = 0;
     uint8_t* d_rgb = nullptr; size_t rgb_cap = 0;
+    // shadow rays: light-space grid of the scene (kernels.h ShadowGrid), rebuilt when the scene or the light changes
+    uint8_t* d_shadow = nullptr; size_t shadow_cap = 0;
+    srt::ShadowGrid grid{};
+    uint64_t scene_serial = 1, grid_scene = 0, bbox_scene = 0;
+    float grid_light[3] = { 0, 0, 0 }, scene_bbox[6] = { 0, 0, 0, 0, 0, 0 };
+    uint32_t* d_bbox = nullptr;
+    size_t grid_cells_cap = 0, grid_tris_cap = 0, grid_global_cap = 0;
+    int force_shadow_grid = 0;           // diagnostic: 0 = heuristic, > 0 = cells per side, < 0 = brute force
     std::vector<srt::DevMesh> h_desc;    // host copy of the descriptor arrays (default | all contribute)
     srt::DevMesh* d_meshes = nullptr;    // device array: [0, n) default semantics, [n, 2n) all meshes contribute
     size_t desc_cap = 0;
@@ -143,6 +151,11 @@ void free_scene(srt_ctx* c)
     for (auto& m : c->meshes) { free_mesh(m); cudaFree(m.d_texcoords); cudaFree(m.d_tex); }
     cudaFree(c->d_shade_meshes); c->d_shade_meshes = nullptr; c->shade_cap = 0;
     cudaFree(c->d_rgb); c->d_rgb = nullptr; c->rgb_cap = 0;
+    cudaFree(c->d_shadow); c->d_shadow = nullptr; c->shadow_cap = 0;
+    cudaFree(c->grid.cell_off); cudaFree(c->grid.cell_cursor); cudaFree(c->grid.cell_tris); cudaFree(c->grid.global_tris);
+    cudaFree(c->grid.n_global); cudaFree(c->d_bbox);
+    c->grid = srt::ShadowGrid{}; c->d_bbox = nullptr; c->grid_cells_cap = c->grid_tris_cap = c->grid_global_cap = 0;
+    c->grid_scene = c->bbox_scene = 0;
     c->meshes.clear(); c->n_meshes = 0;
     cudaFree(c->d_meshes); c->d_meshes = nullptr; c->desc_cap = 0;
     cudaFree(c->d_u_off); c->d_u_off = nullptr; c->off_cap_u = 0;
@@ -374,7 +387,9 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         a.counters = c->d_counters;
     }
 
-    if (kernel == SRT_KERNEL_AUTO) kernel = SRT_KERNEL_CULLED;          // falls back below when it does not apply
+    // AUTO: the hierarchically culled kernel; a handful of triangles (config C4: the 2-triangle logo quad) is fastest
+    // in the one-launch exact kernel -- the multi-kernel paths cost more in launches than such a frame in arithmetic
+    if (kernel == SRT_KERNEL_AUTO) kernel = (c->total_tris <= 64 && mode == 0) ? SRT_KERNEL_EXACT : SRT_KERNEL_CULLED;
     if (!c->filterable) kernel = SRT_KERNEL_EXACT;                        // camera outside the filter's preconditions
     if (mode == 2) {
         // the sort mode lives on the hit lists of the filtered path (an unfilterable camera lets every box through:
@@ -737,6 +752,7 @@ int srt_set_meshes(srt_ctx* c, int n_meshes, const srt_mesh_desc* meshes)
     SRT_CUDA(c, cudaSetDevice(c->device));
     if (c->meshes.size() < (size_t)n_meshes) c->meshes.resize((size_t)n_meshes);
     c->packed = false;
+    ++c->scene_serial;
     c->n_meshes = 0;
     for (int m = 0; m < n_meshes; ++m) {
         const srt_mesh_desc& d = meshes[m];
@@ -959,6 +975,111 @@ int srt_render_xray_sorted(srt_ctx* c, const srt_params* p, float* image_out)
 }
 
 // ---- shaded variant ------------------------------------------------------------------------
+namespace {
+
+// Build (or reuse) the light-space grid the shadow rays look their blockers up in: kernels.h ShadowGrid.
+// Synchronous the first time a (scene, light) pair is seen (two small read-backs: the scene's bounding box and the
+// number of list entries); cached afterwards.  Leaves grid.enabled = 0 (brute force) when the light is inside or
+// close to the scene's bounding box, where a central projection onto one plane does not cover the scene.
+int build_shadow_grid(srt_ctx* c, srt::ShadeArgs& a, uint32_t W, uint32_t H)
+{
+    srt::ShadowGrid& g = c->grid;
+    const bool same_light = std::memcmp(c->grid_light, a.light_position, sizeof c->grid_light) == 0;
+    if (c->grid_scene == c->scene_serial && same_light) { a.grid = g; return SRT_OK; }
+    c->timing.shadow_grid_rebuilt = 1;
+    const uint32_t total = (uint32_t)c->total_tris;
+    g.enabled = 0; g.total_tris = total;
+    a.grid = g;
+    std::memcpy(c->grid_light, a.light_position, sizeof c->grid_light);
+    c->grid_scene = c->scene_serial;
+    if (c->force_shadow_grid < 0 || total == 0) return SRT_OK;
+    if (!c->d_bbox) SRT_CUDA(c, cudaMalloc(&c->d_bbox, 6 * sizeof(uint32_t)));
+    if (!g.n_global) SRT_CUDA(c, cudaMalloc(&g.n_global, sizeof(uint32_t)));
+    if (c->bbox_scene != c->scene_serial) {
+        const uint32_t init[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
+        uint32_t keys[6];
+        SRT_CUDA(c, cudaMemcpyAsync(c->d_bbox, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+        SRT_CUDA(c, srt::launch_scene_bbox(c->d_shade_meshes, (int)c->n_meshes, total, c->d_bbox, c->stream));
+        SRT_CUDA(c, cudaMemcpyAsync(keys, c->d_bbox, sizeof keys, cudaMemcpyDeviceToHost, c->stream));
+        SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < 6; ++k) c->scene_bbox[k] = srt::ordered_key_to_float(keys[k]);
+        c->bbox_scene = c->scene_serial;
+        c->timing.launches += 1;
+    }
+    const float* bb = c->scene_bbox;
+    const float* L = a.light_position;
+    for (int k = 0; k < 3; ++k) if (!(bb[k] <= bb[3 + k])) return SRT_OK;          // empty or NaN box
+    // axis: from the light to the centre of the box
+    double w[3], len = 0.0;
+    for (int k = 0; k < 3; ++k) { w[k] = 0.5 * ((double)bb[k] + bb[3 + k]) - L[k]; len += w[k] * w[k]; }
+    len = std::sqrt(len);
+    if (!(len > 0.0) || !std::isfinite(len)) return SRT_OK;
+    for (int k = 0; k < 3; ++k) w[k] /= len;
+    int least = 0;
+    for (int k = 1; k < 3; ++k) if (std::fabs(w[k]) < std::fabs(w[least])) least = k;
+    double e[3] = { 0, 0, 0 }, u[3], v[3];
+    e[least] = 1.0;
+    u[0] = w[1] * e[2] - w[2] * e[1]; u[1] = w[2] * e[0] - w[0] * e[2]; u[2] = w[0] * e[1] - w[1] * e[0];
+    const double ul = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    for (int k = 0; k < 3; ++k) u[k] /= ul;
+    v[0] = w[1] * u[2] - w[2] * u[1]; v[1] = w[2] * u[0] - w[0] * u[2]; v[2] = w[0] * u[1] - w[1] * u[0];
+    // projected extent of the box: all 8 corners must lie well in front of the light
+    double amin = 1e300, amax = -1e300, bmin = 1e300, bmax = -1e300;
+    for (int corner = 0; corner < 8; ++corner) {
+        double q[3], qn = 0.0;
+        for (int k = 0; k < 3; ++k) { q[k] = (double)bb[(corner >> k & 1) ? 3 + k : k] - L[k]; qn += std::fabs(q[k]); }
+        const double depth = q[0] * w[0] + q[1] * w[1] + q[2] * w[2];
+        if (!(depth > 0.05 * qn)) return SRT_OK;                                  // light inside / beside the box: brute force
+        const double pa = (q[0] * u[0] + q[1] * u[1] + q[2] * u[2]) / depth, pb = (q[0] * v[0] + q[1] * v[1] + q[2] * v[2]) / depth;
+        amin = std::min(amin, pa); amax = std::max(amax, pa); bmin = std::min(bmin, pb); bmax = std::max(bmax, pb);
+    }
+    const double ra = std::max(amax - amin, 1e-30), rb = std::max(bmax - bmin, 1e-30);
+    uint32_t G = c->force_shadow_grid > 0 ? (uint32_t)c->force_shadow_grid
+                                          : (uint32_t)std::max(std::sqrt((double)W * H) / 4.0, std::sqrt((double)total));
+    G = std::min(std::max(G, 64u), 2048u);
+    for (int k = 0; k < 3; ++k) { g.u[k] = (float)u[k]; g.v[k] = (float)v[k]; g.w[k] = (float)w[k]; }
+    g.G = G;
+    g.a0 = (float)(amin - 0.01 * ra); g.b0 = (float)(bmin - 0.01 * rb);           // 1 % apron around the box's projection
+    g.inv_da = (float)(G / (1.02 * ra)); g.inv_db = (float)(G / (1.02 * rb));
+    const size_t cells = (size_t)G * G;
+    if (cells + 1 > c->grid_cells_cap) {
+        cudaFree(g.cell_off); cudaFree(g.cell_cursor); g.cell_off = g.cell_cursor = nullptr; c->grid_cells_cap = 0;
+        SRT_CUDA(c, cudaMalloc(&g.cell_off, (cells + 1) * sizeof(uint32_t)));
+        SRT_CUDA(c, cudaMalloc(&g.cell_cursor, (cells + 1) * sizeof(uint32_t)));
+        c->grid_cells_cap = cells + 1;
+    }
+    if (total > c->grid_global_cap) {
+        cudaFree(g.global_tris); g.global_tris = nullptr; c->grid_global_cap = 0;
+        SRT_CUDA(c, cudaMalloc(&g.global_tris, (size_t)total * sizeof(uint32_t)));
+        c->grid_global_cap = total;
+    }
+    a.grid = g;
+    SRT_CUDA(c, cudaMemsetAsync(g.cell_off, 0, (cells + 1) * sizeof(uint32_t), c->stream));
+    SRT_CUDA(c, srt::launch_shadow_bin(a, 0, c->stream));
+    SRT_CUDA(c, srt::launch_exclusive_scan(g.cell_off, (uint32_t)(cells + 1), c->stream));
+    uint32_t entries = 0;
+    SRT_CUDA(c, cudaMemcpyAsync(&entries, g.cell_off + cells, sizeof entries, cudaMemcpyDeviceToHost, c->stream));
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if ((size_t)entries > c->grid_tris_cap) {
+        cudaFree(g.cell_tris); g.cell_tris = nullptr; c->grid_tris_cap = 0;
+        const size_t cap = (size_t)entries + entries / 8 + 1024;
+        SRT_CUDA(c, cudaMalloc(&g.cell_tris, cap * sizeof(uint32_t)));
+        c->grid_tris_cap = cap;
+    }
+    a.grid = g;
+    SRT_CUDA(c, cudaMemcpyAsync(g.cell_cursor, g.cell_off, cells * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    SRT_CUDA(c, cudaMemsetAsync(g.n_global, 0, sizeof(uint32_t), c->stream));
+    SRT_CUDA(c, srt::launch_shadow_bin(a, 1, c->stream));
+    g.enabled = 1;
+    a.grid = g;
+    c->timing.launches += 3;
+    c->timing.shadow_grid_cells = G;
+    c->timing.shadow_grid_entries = entries;
+    return SRT_OK;
+}
+
+} // namespace
+
 int srt_render_shaded_device(srt_ctx* c, const srt_params* p, const srt_light* light, const uint8_t background_rgb[3],
                              uint8_t* d_rgb, uint8_t* d_shadow)
 {
@@ -984,8 +1105,21 @@ int srt_render_shaded_device(srt_ctx* c, const srt_params* p, const srt_light* l
     a.cam.W = W; a.cam.H = H;
     a.meshes = c->d_shade_meshes; a.n_meshes = (int)c->n_meshes;
     for (int k = 0; k < 3; ++k) { a.light_colour[k] = light->colour[k]; a.light_position[k] = light->position[k]; a.background[k] = background_rgb[k]; }
+    if (!d_shadow) {                                        // kept for srt_debug_shaded_buffers
+        if ((size_t)W * H > c->shadow_cap) {
+            SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_shadow); c->d_shadow = nullptr; c->shadow_cap = 0;
+            SRT_CUDA(c, cudaMalloc(&c->d_shadow, (size_t)W * H)); c->shadow_cap = (size_t)W * H;
+        }
+        d_shadow = c->d_shadow;
+    }
     a.z = c->d_dist; a.tri_id = c->d_ssum; a.rgb = d_rgb; a.shadow = d_shadow;
     a.row_begin = 0; a.row_end = H;
+    c->timing.shadow_grid_rebuilt = 0;
+    SRT_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
+    rc = build_shadow_grid(c, a, W, H);
+    if (rc) return rc;
+    c->timing.shadow_grid_cells = a.grid.enabled ? a.grid.G : 0;
     SRT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     SRT_CUDA(c, srt::launch_shade(a, c->stream));
     SRT_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
@@ -1011,12 +1145,13 @@ int srt_render_shaded(srt_ctx* c, const srt_params* p, const srt_light* light, c
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
     SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
     SRT_CUDA(c, cudaEventElapsedTime(&c->timing.repair_ms, c->ev[2], c->ev[3]));     // shade pass time
+    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.shadow_grid_ms, c->ev[6], c->ev[2]));
     c->timing_pending = false;
     return SRT_OK;
 }
 
 // diagnostic: z-buffer / triangle index / shadow flag of the last shaded render (host copies; any may be NULL)
-int srt_debug_shaded_buffers(srt_ctx* c, float* z_out, int32_t* tri_id_out)
+int srt_debug_shaded_buffers(srt_ctx* c, float* z_out, int32_t* tri_id_out, uint8_t* shadow_out)
 {
     if (!c || !c->have_camera) return SRT_ERR_INVALID;
     const size_t n = (size_t)c->camera.width * c->camera.height;
@@ -1024,6 +1159,10 @@ int srt_debug_shaded_buffers(srt_ctx* c, float* z_out, int32_t* tri_id_out)
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (z_out) SRT_CUDA(c, cudaMemcpy(z_out, c->d_dist, n * 4, cudaMemcpyDeviceToHost));
     if (tri_id_out) SRT_CUDA(c, cudaMemcpy(tri_id_out, c->d_ssum, n * 4, cudaMemcpyDeviceToHost));
+    if (shadow_out) {
+        if (n > c->shadow_cap) return fail(c, SRT_ERR_INVALID, "the last shaded render wrote its shadow flags to a caller's buffer");
+        SRT_CUDA(c, cudaMemcpy(shadow_out, c->d_shadow, n, cudaMemcpyDeviceToHost));
+    }
     return SRT_OK;
 }
 
@@ -1137,6 +1276,16 @@ int srt_debug_force_list_caps(srt_ctx* c, uint32_t bin_cap, uint32_t cand_cap, u
 {
     if (!c) return SRT_ERR_INVALID;
     c->force_bin_cap = bin_cap; c->force_cand_cap = cand_cap; c->force_pix_cap = pix_cap;
+    return SRT_OK;
+}
+
+// diagnostic: cells per side of the shadow rays' light-space grid (0 = heuristic, < 0 = no grid: every shadow ray
+// tests every triangle, the reference's loop)
+int srt_debug_force_shadow_grid(srt_ctx* c, int cells_per_side)
+{
+    if (!c) return SRT_ERR_INVALID;
+    c->force_shadow_grid = cells_per_side;
+    c->grid_scene = 0;
     return SRT_OK;
 }
 

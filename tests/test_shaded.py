@@ -66,6 +66,8 @@ def test_gpu_shaded_vs_reference_golden(gpu_ctx, srtlib, golden, kernel, name):
     want = golden[f"rgb_{name}"]
     d = np.abs(rgb.astype(np.int32) - want.astype(np.int32))
     assert d.max() <= 1 and (d == 0).mean() >= 0.999, (d.max(), (d == 0).mean())
+    assert (gpu_ctx.shadow_flags() == golden["shadow"].reshape(-1)).all(), "shadow mask differs from the reference's"
+    assert gpu_ctx.timing().shadow_grid_cells > 0, "the shadow rays of this scene should use the light-space grid"
 
 
 @pytest.mark.gpu
@@ -84,3 +86,58 @@ def test_gpu_shaded_other_size_and_background(gpu_ctx, srtlib, oracle):
     # the X-ray path still works on the same context afterwards (mode switch)
     r = gpu_ctx.render_lbuffer(srtlib.default_params())
     assert (r["hits"] > 0).any()
+
+
+@pytest.mark.gpu
+def test_gpu_shadow_grid_equals_brute_force_loop(gpu_ctx, srtlib):
+    """The light-space grid only prunes triangles that cannot block a shadow ray: the shadow mask and the image are
+    identical to the reference's loop over every triangle (grid switched off), for several grid resolutions and light
+    positions -- including lights inside / beside the scene's bounding box, where the library must fall back to the
+    loop by itself."""
+    meshes = scene.shaded_scene(texture=scene.noise_texture(40, 30, seed=7))
+    W, H = 192, 144
+    cam, light0 = scene.shaded_camera(srtlib, meshes, W, H)
+    gpu_ctx.set_meshes(meshes)
+    gpu_ctx.set_camera(cam)
+    allt = np.concatenate([np.asarray(m["tri"], np.float32).reshape(-1, 3) for m in meshes])
+    lo, hi = allt.min(0), allt.max(0)
+    centre, ext = (lo + hi) / 2, (hi - lo)
+    lights = [("reference", light0, True), ("inside the box", centre + ext * np.float32(0.1), False),
+              ("beside the box", np.array([hi[0] + ext[0] * 0.01, centre[1], centre[2]], np.float32), False),
+              ("far, oblique", centre + np.array([3, -2, 4], np.float32) * ext.max(), True),
+              ("behind the camera", cam.vec("origin") + (cam.vec("origin") - centre), True)]
+    p = srtlib.default_params()
+    shadowed = 0
+    for name, light, grid_expected in lights:
+        gpu_ctx.force_shadow_grid(-1)
+        want = gpu_ctx.render_shaded(p, light).copy()
+        want_shadow = gpu_ctx.shadow_flags().copy()
+        assert gpu_ctx.timing().shadow_grid_cells == 0
+        for cells in (0, 64, 333, 2048):
+            gpu_ctx.force_shadow_grid(cells)
+            got = gpu_ctx.render_shaded(p, light)
+            t = gpu_ctx.timing()
+            assert (t.shadow_grid_cells > 0) == grid_expected, (name, cells, t.shadow_grid_cells)
+            assert (gpu_ctx.shadow_flags() == want_shadow).all(), (name, cells)
+            assert (got == want).all(), (name, cells)
+        shadowed += int(want_shadow.sum())
+    gpu_ctx.force_shadow_grid(0)
+    assert shadowed > 1000
+
+
+@pytest.mark.gpu
+def test_gpu_shadow_grid_is_cached_per_scene_and_light(gpu_ctx, srtlib):
+    meshes = scene.shaded_scene()
+    cam, light = scene.shaded_camera(srtlib, meshes, 128, 128)
+    gpu_ctx.set_meshes(meshes)
+    gpu_ctx.set_camera(cam)
+    p = srtlib.default_params()
+    a = gpu_ctx.render_shaded(p, light).copy()
+    assert gpu_ctx.timing().shadow_grid_rebuilt == 1
+    b = gpu_ctx.render_shaded(p, light).copy()
+    assert gpu_ctx.timing().shadow_grid_rebuilt == 0 and (a == b).all()
+    gpu_ctx.render_shaded(p, light + np.float32(5.0))
+    assert gpu_ctx.timing().shadow_grid_rebuilt == 1
+    gpu_ctx.set_meshes(meshes)
+    c = gpu_ctx.render_shaded(p, light)
+    assert gpu_ctx.timing().shadow_grid_rebuilt == 1 and (a == c).all()
