@@ -238,10 +238,12 @@ def load_counters(kernel_name, shape, W, world):
 
 
 def run_ours(args):
+    # one hardware work queue per stream (the default of 8 would make the pipeline's lanes share queues and serialise)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import torch
     import torch.distributed as dist
     from simpleraytracing_b200 import Context, Library, PinnedArray, KERNEL_AUTO, KERNEL_CULLED, KERNEL_FILTERED
-    from simpleraytracing_b200.bands import BandLayout, InterleavedLayout, PeerFrames
+    from simpleraytracing_b200.bands import InterleavedLayout, PeerLanes
     from simpleraytracing_b200.capi import Camera
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -254,12 +256,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     lib = Library()
-    ctx = Context(local, lib)
-    # a dedicated non-default stream shared by torch (events, NCCL, copies) and the library's kernels
-    # (handle 0 would mean "the context's own stream" to srt_set_stream)
+    # the main stream: events, L2 flush, NCCL, copies.  Frames run on the lanes' streams, forked from / joined to it.
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
 
     wl = workload(args)
     meshes, W, H = wl["meshes"], wl["W"], wl["H"]
@@ -271,29 +270,29 @@ def run_ours(args):
     cam_b.detector[1] = cam.detector[1] + 7.5; cam_b.detector[2] = cam.detector[2] - 4.25
     cam_b.pixel_spacing[0] = cam.pixel_spacing[0] * 0.9; cam_b.pixel_spacing[1] = cam.pixel_spacing[1] * 0.9
     note("scene built")
-    ctx.set_meshes(meshes)
-    ctx.set_camera(cam)
     params = lib.default_params(kernel=args.kernel, pixels_per_thread=args.box)
     params_acc = lib.default_params(kernel=KERNEL_AUTO)           # the library's default: culled (exact for a handful of triangles)
 
-    lay = BandLayout(H, W, world, rank)
-    frame = lay.new_frame(torch.float32, dev)
-    # N > 1: block-cyclic 16-row blocks (contiguous bands are unbalanced: rows through the object cost more)
+    # ---- the pipeline: frames go round-robin to `n_lanes` lanes = one srt context + one stream + frame buffers each.
+    # Nothing is shared between the frames in flight, so the latency-bound tail of one frame (candidate stages,
+    # hit-list resolve, device barrier, repair) overlaps the scan of the next.
+    big = args.config == "c5"
+    n_lanes = max(1, args.lanes if args.lanes else (1 if big else 4))
+    B = max(1, args.frames_per_step if args.frames_per_step else (1 if big else 16))
+
+    # N > 1: block-cyclic 16-row blocks (contiguous bands are unbalanced: rows through the object cost more).
+    # Preferred assembly: the render kernels store their rows straight into every rank's frame over NVLink (multicast
+    # mapping when the switch offers one) + srt_peer_barrier_device; fallback: all_gather of slots + de-interleave.
     il = InterleavedLayout(H, W, world, rank)
-    slots = il.new_slots(torch.float32, dev) if world > 1 else None
-    my_slot_ptr = il.my_slot(slots).data_ptr() if world > 1 else 0
     my_rows = len(il.rows_of(rank)) if world > 1 else H
-    # N > 1, preferred: fused render + assembly -- the render kernels store their rows straight into every rank's frame
-    # over NVLink (multicast mapping when the switch offers one); falls back to all_gather + de-interleave
     peers, assembly = None, "single GPU"
     if world > 1:
         assembly = "all_gather of slots + de-interleave kernel"
         if args.assembly != "allgather":
             try:
-                # two frame sets used alternately: one barrier per step is enough (a rank can run at most one step ahead)
-                peers = [PeerFrames(H, W, use_multicast=(args.assembly != "p2p")) for _ in range(2)]
-                assembly = ("render kernels store (multimem.st) to the NVSwitch multicast mapping of all frames" if peers[0].multicast_ptr
-                            else "render kernels store to every peer's frame over NVLink") + " + one device barrier"
+                peers = PeerLanes(H, W, n_lanes, use_multicast=(args.assembly != "p2p"))
+                assembly = ("render kernels store (multimem.st) to the NVSwitch multicast mapping of all frames" if peers.multicast_ptr
+                            else "render kernels store to every peer's frame over NVLink") + " + one flag barrier kernel per frame"
             except Exception as exc:                      # no peer access on this box
                 peers = None
                 assembly += f" (symmetric memory unavailable: {type(exc).__name__})"
@@ -304,40 +303,88 @@ def run_ours(args):
             if int(ok.item()) == 0 and peers is not None:
                 peers = None
                 assembly = "all_gather of slots + de-interleave kernel (symmetric memory unavailable on another rank)"
-    image = torch.empty(H * W, dtype=torch.float32, device=dev)
+        if peers is None:
+            n_lanes = 1                                   # NCCL collectives stay on one stream
+
+    class Lane:
+        pass
+
+    lanes = []
+    for l in range(n_lanes):
+        ln = Lane()
+        ln.index = l
+        ln.ctx = Context(local, lib)
+        ln.stream = torch.cuda.Stream(device=dev) if n_lanes > 1 else stream
+        ln.ctx.set_stream(ln.stream.cuda_stream)
+        ln.ctx.set_meshes(meshes); ln.ctx.set_camera(cam)
+        ln.ctx.set_profiling(False)
+        if args.scan_ctas:
+            ln.ctx.set_scan_residency(args.scan_ctas)
+        ln.image = torch.empty(H * W, dtype=torch.float32, device=dev)
+        ln.done = torch.cuda.Event()
+        ln.epoch = 0
+        if world == 1:
+            ln.frame = torch.empty(H * W, dtype=torch.float32, device=dev)
+        elif peers is not None:
+            ln.calls = {}
+            for name, p_ in (("headline", params), ("acc", params_acc)):
+                ln.calls[name] = []
+                for s_ in (0, 1):
+                    ptrs, mc = peers.frame_ptrs(l, s_)
+                    ln.calls[name].append(Context.frame_call_args(p_, ptrs, peers.flag_ptrs(l), multicast=mc))
+            ln.own = [peers.own_frame_ptr(l, s_) for s_ in (0, 1)]
+        else:
+            ln.slots = il.new_slots(torch.float32, dev)
+            ln.frame = torch.empty(H * W, dtype=torch.float32, device=dev)
+        lanes.append(ln)
+    ctx = lanes[0].ctx
     host_image_t = torch.empty(H * W, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
-    step_no = [0]
-
-    def render_and_assemble(p):
+    def lane_frame(ln, which="headline"):
+        """enqueue ONE frame (render of this rank's blocks + assembly + repair) on the lane's stream"""
+        p = params if which == "headline" else params_acc
         if world == 1:
-            ctx.render_lbuffer_device(p, lay.rows, frame.data_ptr())
-            return frame
-        if peers is not None:
-            pf = peers[step_no[0] & 1]
-            step_no[0] += 1
-            ptrs, mc = pf.pointers()
-            ctx.render_lbuffer_blocks_device(p, world, rank, ptrs, multicast=mc)
-            pf.barrier()                                  # every rank's rows have landed in this rank's frame
-            return pf.frame
-        ctx.render_lbuffer_interleaved_device(p, world, rank, my_slot_ptr)
-        il.all_gather_(slots)
-        ctx.deinterleave_device(world, slots.data_ptr(), frame.data_ptr())
-        return frame
+            ln.ctx.render_lbuffer_device(p, (0, H), ln.frame.data_ptr())
+            ln.ctx.repair_device(p, ln.frame.data_ptr(), ln.image.data_ptr())
+        elif peers is not None:
+            ln.epoch += 1
+            s_ = ln.epoch & 1
+            ln.ctx.render_xray_blocks_device(ln.calls[which][s_], world, rank, ln.epoch, ln.own[s_], ln.image.data_ptr())
+        else:
+            ln.ctx.render_lbuffer_interleaved_device(p, world, rank, il.my_slot(ln.slots).data_ptr())
+            il.all_gather_(ln.slots)
+            ln.ctx.deinterleave_device(world, ln.slots.data_ptr(), ln.frame.data_ptr())
+            ln.ctx.repair_device(p, ln.frame.data_ptr(), ln.image.data_ptr())
 
-    def step_device(p=params):
-        full = render_and_assemble(p)
-        ctx.repair_device(p, full.data_ptr(), image.data_ptr())
+    fork = torch.cuda.Event()
 
-    def step_e2e_sharded(p=params):
+    def step_batch(which="headline", frames=None):
+        """one step = `frames` frames, round-robin over the lanes; forked from and joined to the main stream"""
+        frames = B if frames is None else frames
+        if n_lanes > 1:
+            fork.record(stream)
+            for ln in lanes[:min(frames, n_lanes)]:
+                ln.stream.wait_event(fork)
+        for f in range(frames):
+            lane_frame(lanes[f % n_lanes], which)
+        if n_lanes > 1:
+            for ln in lanes[:min(frames, n_lanes)]:
+                ln.done.record(ln.stream)
+                stream.wait_event(ln.done)
+
+    def step_e2e_sharded(which="headline"):
         # one process per GPU: host meshes + camera in, sharded render, assembly, repair, image to host memory
-        ctx.set_meshes(meshes)
-        ctx.set_camera(cam)
-        full = render_and_assemble(p)
-        ctx.repair_device(p, full.data_ptr(), image.data_ptr())
+        ln = lanes[0]
+        ln.ctx.set_meshes(meshes)
+        ln.ctx.set_camera(cam)
+        if n_lanes > 1:
+            fork.record(stream); ln.stream.wait_event(fork)
+        lane_frame(ln, which)
+        if n_lanes > 1:
+            ln.done.record(ln.stream); stream.wait_event(ln.done)
         if rank == 0:                           # the result is needed on the host once
-            host_image_t.copy_(image, non_blocking=True)
+            host_image_t.copy_(ln.image, non_blocking=True)
         stream.synchronize()
 
     def barrier():
@@ -350,10 +397,6 @@ def run_ours(args):
     def timed(fn, steps, warmup, sync_each):
         for i in range(warmup):
             fn()
-            if VERBOSE:
-                stream.synchronize()
-                tm_ = ctx.timing()
-                note(f"warm-up step {i}: pass {tm_.render_ms:.3f} ms, main kernel {tm_.main_kernel_ms:.3f} ms, kernel {tm_.kernel_used}")
         barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         wall = 0.0
@@ -395,29 +438,33 @@ def run_ours(args):
 
     peak_tf = ctx.ffma_peak_tflops(3)                     # FP32 FFMA peak of this GPU (secondary figure)
     steps = args.steps
+    # every lane renders once before anything is timed: the first render of a launch geometry verifies the list sizes
+    for which in ("headline", "acc"):
+        step_batch(which, frames=2 * n_lanes)
+    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     note("timing the device-resident steps")
-    total_ms = timed(step_device, steps, args.warmup, sync_each=False)
-    note(f"{total_ms / steps:.4f} ms per step")
+    total_ms = timed(step_batch, steps, args.warmup, sync_each=False)
+    note(f"{total_ms / steps:.4f} ms per step of {B} frames")
+    # one frame alone (no pipelining): the latency of a frame, and what a step was before frames were pipelined
+    single_ms = timed(lambda: step_batch("headline", frames=1), max(3, min(steps, 10)), 2, sync_each=False)
+    single_steps = max(3, min(steps, 10))
     # the dominant kernel alone: CUDA events around it on its stream (srt_timing.main_kernel_ms)
     barrier()
+    ctx.set_profiling(True)
     kern_ms, pass_ms = [], []
     for _ in range(max(3, min(steps, 10))):
         flush.fill_(1)
-        if world == 1:
-            ctx.render_lbuffer_device(params, lay.rows, frame.data_ptr())
-        elif peers is not None:
+        if world > 1:
             barrier()
-            ptrs, mc = peers[0].pointers()
-            ctx.render_lbuffer_blocks_device(params, world, rank, ptrs, multicast=mc)
-        else:
-            ctx.render_lbuffer_interleaved_device(params, world, rank, my_slot_ptr)
+        lane_frame(lanes[0])
         tm = ctx.timing()
         kern_ms.append(tm.main_kernel_ms); pass_ms.append(tm.render_ms)
-        render_launches = tm.launches              # dominant kernel + hit-list resolve (resp. bin pass)
+        render_launches = tm.launches              # dominant kernel + candidate stages + hit-list resolve (resp. bin pass)
         scan_cols = tm.scan_cols
+    ctx.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
     kernel_used = ctx.timing().kernel_used
     e2e_steps = max(1, min(steps, 10))
@@ -426,13 +473,14 @@ def run_ours(args):
     note("end to end")
     e2e = {}
     if world == 1:
+        ectx = Context(local, lib)                                     # the plugin call as a reference user makes it: own stream
         host_image = np.empty(H * W, np.float32)                      # an ordinary (pageable) host buffer
         host_meshes = [(np.array(m[0], np.float32, copy=True), m[1]) for m in meshes]
 
-        def plugin_call(img, ms_):
-            ctx.set_meshes(ms_)
-            ctx.set_camera(cam)
-            ctx.render_xray(params, out=img)                          # synchronous: returns with the image in host memory
+        def plugin_call(img, ms_, p_=params):
+            ectx.set_meshes(ms_)
+            ectx.set_camera(cam)
+            ectx.render_xray(p_, out=img)                             # synchronous: returns with the image in host memory
 
         e2e_ms = wall_timed(lambda: plugin_call(host_image, host_meshes), e2e_steps, 2)
         pin_img = PinnedArray(lib, (H * W,), np.float32)
@@ -442,23 +490,25 @@ def run_ours(args):
         pinned_meshes = [(pa.array, m[1]) for pa, m in zip(pin_tri, meshes)]
         e2e_pin_ms = wall_timed(lambda: plugin_call(pin_img.array, pinned_meshes), e2e_steps, 2)
         e2e_same = bool(np.array_equal(pin_img.array.view(np.uint32), host_image.view(np.uint32)))
-        acc_e2e_ms = wall_timed(lambda: (ctx.set_meshes(pinned_meshes), ctx.set_camera(cam),
-                                         ctx.render_xray(params_acc, out=pin_img.array)), e2e_steps, 2)
-        e2e_path = "srt_set_meshes + srt_set_camera + srt_render_xray, ordinary host buffers, wall clock"
+        acc_e2e_ms = wall_timed(lambda: plugin_call(pin_img.array, pinned_meshes, params_acc), e2e_steps, 2)
+        e2e_path = "srt_set_meshes + srt_set_camera + srt_render_xray, ordinary host buffers, wall clock, one frame per call"
         e2e.update({"pinned": {"ms_per_step": e2e_pin_ms / e2e_steps, "value": float(W) * H * ntri * e2e_steps / (e2e_pin_ms * 1e-3),
                                "note": "same calls with srt_host_alloc (page-locked) vertex and image buffers",
                                "image_equals_pageable_run": e2e_same}})
-        ctx.set_stream(stream.cuda_stream)
+        ectx.close()
     else:
         e2e_ms = timed(step_e2e_sharded, e2e_steps, max(1, min(args.warmup, 3)), sync_each=True)
-        acc_e2e_ms = timed(lambda: step_e2e_sharded(params_acc), e2e_steps, 2, sync_each=True)
-        e2e_path = "per rank: srt_set_meshes + srt_set_camera + sharded render + assembly + repair; image to pinned host memory on rank 0"
+        acc_e2e_ms = timed(lambda: step_e2e_sharded("acc"), e2e_steps, 2, sync_each=True)
+        e2e_path = "per rank: srt_set_meshes + srt_set_camera + sharded render + assembly + repair; image to pinned host memory on rank 0; one frame per step"
 
-    # the accelerated path (not the headline): same frame, same step, SRT_KERNEL_AUTO
+    # the accelerated path (not the headline): same frames, same step, SRT_KERNEL_AUTO
     note("accelerated path")
-    ctx.set_meshes(meshes); ctx.set_camera(cam)
-    acc_ms = timed(lambda: step_device(params_acc), steps, 3, sync_each=False)
-    acc_kernel_used = ctx.timing().kernel_used
+    for ln in lanes:
+        ln.ctx.set_meshes(meshes); ln.ctx.set_camera(cam)
+    step_batch("acc", frames=2 * n_lanes); step_batch("headline", frames=2 * n_lanes)
+    acc_ms = timed(lambda: step_batch("acc"), steps, 3, sync_each=False)
+    acc_single_ms = timed(lambda: step_batch("acc", frames=1), single_steps, 2, sync_each=False)
+    ctx.set_profiling(True); lane_frame(lanes[0], "acc"); acc_kernel_used = ctx.timing().kernel_used; ctx.set_profiling(False)
 
     # the shaded variant of the same frame size (main-omp.cxx: dragon + textured quad, closest hit, Phong, shadow
     # rays, texture), through the host-pointer call; N = 1, dragon configs only.  Not part of the headline.
@@ -495,45 +545,64 @@ def run_ours(args):
                   "d2h_bytes_per_frame": 3 * W * H}
         sctx.close()
 
-    # ---- correctness of the assembled frame (outside every timed region).  The frame a rank holds after a sharded
-    # step must equal, bit for bit, the image of one unsharded render on this GPU.  The check alternates between two
-    # cameras and poisons every rank's frame buffers with NaN before each sharded step, so a lost or late peer store
-    # (a missing barrier) cannot hide behind bytes left by an earlier step.
+    # ---- correctness of the assembled frames (outside every timed region).  The image a rank holds after a sharded
+    # frame must equal, bit for bit, the image of one unsharded render on this GPU.  Each round of the check gives the
+    # lanes alternating cameras, poisons every frame buffer of every rank with NaN, then runs a PIPELINED batch of
+    # 2 x lanes frames (both frame sets of every lane, all lanes in flight) -- a lost or late peer store, or a barrier
+    # that lets the repair pass start early, cannot hide behind bytes left by an earlier frame.
     verified, checks = True, 0
     if world > 1:
+        vctx = Context(local, lib)
+        vctx.set_stream(stream.cuda_stream)
+        vctx.set_meshes(meshes)
         ref_L = torch.empty(H * W, dtype=torch.float32, device=dev)
-        ref_img = torch.empty(H * W, dtype=torch.float32, device=dev)
-        nan = float("nan")
-        for it in range(args.verify_iters):
-            c_ = cam_b if (it & 1) else cam
-            p_ = params_acc if (it % 3 == 2) else params
-            ctx.set_camera(c_)
+        ref_img = {}
+        rounds = max(1, args.verify_iters // (2 * n_lanes))
+        for it in range(rounds):
+            which = "acc" if (it % 3 == 2) else "headline"
+            p_ = params_acc if which == "acc" else params
+            cams = [cam_b if ((ln.index + it) & 1) else cam for ln in lanes]
+            for ln, c_ in zip(lanes, cams):
+                ln.ctx.set_camera(c_)
+                ln.image.fill_(float("nan"))
+            for key, c_ in (("a", cam), ("b", cam_b)):
+                vctx.set_camera(c_)
+                vctx.render_lbuffer_device(p_, (0, H), ref_L.data_ptr())
+                ref_img[key] = torch.empty(H * W, dtype=torch.float32, device=dev)
+                vctx.repair_device(p_, ref_L.data_ptr(), ref_img[key].data_ptr())
             if peers is not None:
-                peers[step_no[0] & 1].frame.fill_(nan)
+                peers.poison()
             else:
-                slots.fill_(nan); frame.fill_(nan)
+                for ln in lanes:
+                    ln.slots.fill_(float("nan")); ln.frame.fill_(float("nan"))
             barrier()                                           # every rank has poisoned its buffers
-            step_device(p_)
-            ctx.render_lbuffer_device(p_, (0, H), ref_L.data_ptr())
-            ctx.repair_device(p_, ref_L.data_ptr(), ref_img.data_ptr())
-            stream.synchronize()
-            same = torch.equal(image.view(torch.int32), ref_img.view(torch.int32))
-            verified = verified and bool(same)
-            checks += 1
-        ctx.set_camera(cam)
+            step_batch(which, frames=2 * n_lanes)
+            torch.cuda.synchronize()
+            for ln, c_ in zip(lanes, cams):
+                same = torch.equal(ln.image.view(torch.int32), ref_img["b" if c_ is cam_b else "a"].view(torch.int32))
+                verified = verified and bool(same)
+                checks += 2
+            barrier()
+        for ln in lanes:
+            ln.ctx.set_camera(cam)
+        vctx.close()
         flag = torch.tensor([1 if verified else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         verified = bool(flag.item())
         if not verified:
-            raise SystemExit(f"bench.py: rank {rank}: the assembled frame differs from the unsharded render")
+            raise SystemExit(f"bench.py: rank {rank}: an assembled frame differs from the unsharded render")
+        step_batch("headline", frames=2 * n_lanes)              # back to the bench camera (list sizes re-verified)
+        barrier()
 
     note("exact-test counts")
     # actual work behind the "tests": pairs that reach the exact reference sequence (this rank's share), both kernels
     exact_counts = {}
     try:
         ctx.count_exact(True)
-        for name, p_ in (("headline", params), ("accelerated", params_acc)):
-            step_device(p_)
+        for name, which in (("headline", "headline"), ("accelerated", "acc")):
+            if world > 1:
+                barrier()
+            lane_frame(lanes[0], which)
             exact_counts[name] = int(ctx.timing().exact_tests)
     except Exception:
         exact_counts = {}
@@ -541,7 +610,7 @@ def run_ours(args):
         ctx.count_exact(False)
 
     tests_frame = float(W) * H * ntri
-    value = tests_frame * steps / (total_ms * 1e-3)
+    value = tests_frame * B * steps / (total_ms * 1e-3)
     e2e_value = tests_frame * e2e_steps / (e2e_ms * 1e-3)
     kt = float(np.mean(kern_ms)) * 1e-3
     per_rank_kernel = None
@@ -570,6 +639,7 @@ def run_ours(args):
         roof = {"bound": "issue", "unit": "Gwarp-inst/s", "peak": issue_peak,
                 "peak_source": f"4 issue slots x {sms} SMs x {sm_mhz:.0f} MHz (SM clock sampled under load)",
                 "kernel": kname, "kernel_ms": kt * 1e3, "pass_ms": float(np.mean(pass_ms)), "scan_cols": int(scan_cols),
+                "kernel_timing": "the kernel alone on an otherwise idle GPU (one frame, CUDA events around the launch)",
                 "tests_per_launch": band_tests, "exact_sequence_tests_per_launch": exact_counts.get("headline"),
                 "achieved": None, "frac": None, "traffic": None}
         if cnt:
@@ -586,20 +656,27 @@ def run_ours(args):
         roof["fp32_equivalent"] = {"flop_per_test": F_ALG, "equivalent_tflops": band_tests * F_ALG / kt / 1e12,
                                    "ffma_peak_tflops": peak_tf, "note": "equivalent rate / FFMA peak is NOT a utilisation"}
         h2d = int(sum(m[0].nbytes for m in meshes) + 4 * 16)
+        per_frame_launches = render_launches + (1 if world == 1 else 2)         # + repair (+ barrier kernel | de-interleave)
         line = {
             "metric": "ray-triangle tests/s (X-ray L-buffer)", "value": value, "unit": "tests/s",
             "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": total_ms / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "dragon mesh fixture (reference dragon.ply, 22866 triangles) / synthetic sphere; camera from the scene bbox",
+            "frames_per_step": B, "ms_per_frame": total_ms / steps / B,
+            "single_frame_ms": single_ms / single_steps,
             "config": {"workload": wl["name"], "triangles": ntri, "kernel": kernel_used,
                        "kernel_note": "2 = SRT_KERNEL_FILTERED: the brute-force path, every thread visits every triangle",
                        "l2": "256 MiB flush write between steps",
-                       "step": "render (16-row blocks, block-cyclic over ranks) + assembly + repair", "assembly": assembly,
+                       "step": f"a batch of {B} frames of the workload, each = render (16-row blocks, block-cyclic over ranks) + assembly + repair; "
+                               f"frames round-robin over {n_lanes} lanes (srt context + stream each) so that the tail of one frame overlaps the scan of the next; "
+                               "single_frame_ms = one frame alone",
+                       "lanes": n_lanes, "scan_ctas_per_sm_cap": args.scan_ctas,
+                       "assembly": assembly,
                        "assembled_frame_equals_unsharded_render": verified,
-                       "assembly_check": None if world == 1 else f"{checks} sharded frames, two cameras alternating, frames poisoned with NaN before each"},
+                       "assembly_check": None if world == 1 else f"{checks} sharded frames in pipelined batches, two cameras alternating over the lanes, frames poisoned with NaN before each batch"},
             "e2e": {"value": e2e_value, "unit": "tests/s", "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "path": e2e_path, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(H * W * 4), **e2e},
-            "gpu_launches": (render_launches + (1 if (world == 1 or peers is not None) else 2)) * steps,   # + repair (+ de-interleave)
+            "gpu_launches": per_frame_launches * B * steps,
             "roofline": roof,
             "cpu_baseline": cpu,
             "clocks": clocks,
@@ -608,7 +685,8 @@ def run_ours(args):
             "shaded": shaded,
             "accelerated": {"kernel": acc_kernel_used,
                             "kernel_name": "SRT_KERNEL_AUTO, the library default: 4 = culled (bins + CTA tiles + pixel runs), 1 = exact kernel for a handful of triangles; identical results",
-                            "ms_per_step": acc_ms / steps, "value": tests_frame * steps / (acc_ms * 1e-3),
+                            "ms_per_step": acc_ms / steps, "ms_per_frame": acc_ms / steps / B, "single_frame_ms": acc_single_ms / single_steps,
+                            "value": tests_frame * B * steps / (acc_ms * 1e-3),
                             "unit": "tests/s (pairs resolved, most of them by a conservative box test)",
                             "e2e_ms_per_step": acc_e2e_ms / e2e_steps,
                             "exact_sequence_tests_per_launch": exact_counts.get("accelerated")},
@@ -617,7 +695,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
+    for ln in lanes:
+        ln.ctx.close()
     return 0
 
 
@@ -634,7 +713,10 @@ def main():
                     help="box shape of the filtered kernel: width | height << 8 | boxes per thread << 16 (0 = default)")
     ap.add_argument("--assembly", default="auto", choices=["auto", "p2p", "allgather"],
                     help="N > 1: auto = fused stores (multicast if available, else per-peer), p2p = per-peer stores, allgather = NCCL")
-    ap.add_argument("--verify-iters", type=int, default=50, help="N > 1: sharded frames checked against unsharded renders")
+    ap.add_argument("--verify-iters", type=int, default=48, help="N > 1: sharded frames checked against unsharded renders")
+    ap.add_argument("--lanes", type=int, default=0, help="frames in flight (srt context + stream each); 0 = default (4; 1 for c5)")
+    ap.add_argument("--frames-per-step", type=int, default=0, help="frames per timed step; 0 = default (16; 1 for c5)")
+    ap.add_argument("--scan-ctas", type=int, default=0, help="cap on the scan kernel's resident CTAs per SM (0 = none, else >= 4)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-shaded", action="store_true", help="skip the shaded-variant block (N = 1, dragon configs)")

@@ -154,6 +154,14 @@ int  srt_version(void);
 int  srt_set_stream(srt_ctx* ctx, void* cuda_stream);
 int  srt_synchronize(srt_ctx* ctx);
 void srt_default_params(srt_params* p);
+/* Per-render CUDA timing events (srt_last_timing's render_ms / main_kernel_ms / repair_ms): on by default; a caller
+ * that pipelines frames on several contexts / streams switches them off (six event records per frame are a
+ * measurable share of a 0.1 ms frame).  With profiling off the timing fields read 0. */
+int  srt_set_profiling(srt_ctx* ctx, int enable);
+/* Cap the resident CTAs per SM of the brute-force scan kernel (0 = no cap, else >= 4): a scan that leaves part of the
+ * register file free lets the short, latency-bound kernels of another frame (another context on another stream) run
+ * beside it.  Tuning knob for frame pipelining; results never change. */
+int  srt_set_scan_residency(srt_ctx* ctx, uint32_t max_ctas_per_sm);
 
 /* ---- host-side helpers (pure CPU arithmetic, exact reference op order) --- */
 /* TriangleMesh::computeBoundingBox + getBBox (src/TriangleMesh.cxx:192-228, lbuffer.cxx:585-608). */
@@ -224,6 +232,23 @@ int  srt_deinterleave_device(srt_ctx* ctx, uint32_t n_parts, const float* d_slot
  */
 int  srt_render_lbuffer_blocks_device(srt_ctx* ctx, const srt_params* params, uint32_t n_parts, uint32_t part,
                                       uint32_t n_frames, float* const* d_frames);
+
+/*
+ * Device-side barrier over the n_ranks GPUs of one node (one process per GPU), on the context's stream: d_flags[j] is
+ * rank j's flag array (n_ranks 32-bit words in peer-mapped memory, zero before the first use) as mapped in THIS
+ * process; epoch starts at 1 and grows by one per barrier on a given set of flag arrays.  The kernels launched before
+ * it have stored their rows into the peers' frames; the kernels launched after it start when every rank's rows have
+ * landed in this rank's frame.  A one-CTA kernel: any number of barriers may be in flight on different streams.
+ * srt_render_xray_blocks_device = srt_render_lbuffer_blocks_device + this barrier + srt_repair_device(d_own_frame ->
+ * d_image) in one call: one frame of the sharded pipeline (the gather of src/main-mpi.cxx:854-881 fused into the
+ * render; every rank ends up with the repaired image).
+ */
+int  srt_peer_barrier_device(srt_ctx* ctx, uint32_t n_ranks, uint32_t rank, uint32_t* const* d_flags, uint32_t epoch,
+                             uint32_t phases /* 3 = signal + wait; 1 = signal only, 2 = wait only: a caller driving several
+                                                ranks from ONE thread enqueues every rank's signal before the first wait */);
+int  srt_render_xray_blocks_device(srt_ctx* ctx, const srt_params* params, uint32_t n_parts, uint32_t part,
+                                   uint32_t n_frames, float* const* d_frames, uint32_t* const* d_flags, uint32_t epoch,
+                                   const float* d_own_frame, float* d_image);
 
 /* Artefact repair + image fill over a full frame (lbuffer.cxx:329-404). L_in and image_out must not alias. */
 int  srt_repair(srt_ctx* ctx, const srt_params* params, const float* L_in, float* image_out);

@@ -133,3 +133,66 @@ class PeerFrames:
 
     def barrier(self):
         self.handle.barrier(channel=0)
+
+
+class PeerLanes:
+    """Frame buffers and barrier flags of a PIPELINE of sharded frames, in one symmetric allocation per rank.
+
+    Frames are rendered round-robin on `lanes` independent streams (one srt context each), so that the short,
+    latency-bound kernels of one frame (candidate stages, hit-list resolve, the device barrier, the repair pass)
+    overlap the scan of the next.  A lane owns two frame sets used alternately (a rank can run at most one frame
+    ahead of its peers per lane, so one barrier per frame suffices) and one flag array for
+    srt_peer_barrier_device (epoch = the lane's frame counter).  Layout per lane, in 4-byte words:
+    [frame set 0: H*W][frame set 1: H*W][flags: 64].
+    """
+    FLAG_WORDS = 64
+
+    def __init__(self, H, W, lanes, group=None, use_multicast=True):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.H, self.W, self.lanes = H, W, lanes
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.lane_words = 2 * H * W + self.FLAG_WORDS
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm_mem.empty(lanes * self.lane_words, dtype=torch.float32, device=dev)
+        self.buf.zero_()                                      # flags start at epoch 0
+        torch.cuda.synchronize()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        dist.barrier(group)                                   # every rank's flags are zero before anyone signals
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        mc = 0
+        if use_multicast:
+            try:
+                mc = int(self.handle.multicast_ptr)
+            except Exception:
+                mc = 0
+        self.multicast_ptr = mc
+
+    def _frame_off(self, lane, s):
+        return lane * self.lane_words + s * self.H * self.W              # words
+
+    def frame(self, lane, s):
+        """this rank's frame of set `s` of `lane` (a view of the symmetric buffer)"""
+        o = self._frame_off(lane, s)
+        return self.buf[o: o + self.H * self.W]
+
+    def frame_ptrs(self, lane, s):
+        """-> (frame pointers for srt_render_*_blocks_device, is_multicast): the multicast mapping when the fabric
+        offers one, else own frame first, then each peer's"""
+        o = 4 * self._frame_off(lane, s)
+        if self.multicast_ptr:
+            return [self.multicast_ptr + o], True
+        return [self.peer_ptrs[self.rank] + o] + [p + o for r, p in enumerate(self.peer_ptrs) if r != self.rank], False
+
+    def own_frame_ptr(self, lane, s):
+        return self.peer_ptrs[self.rank] + 4 * self._frame_off(lane, s)
+
+    def flag_ptrs(self, lane):
+        """flag array of every rank, in rank order, as mapped here"""
+        o = 4 * (lane * self.lane_words + 2 * self.H * self.W)
+        return [p + o for p in self.peer_ptrs]
+
+    def poison(self, value=float("nan")):
+        for lane in range(self.lanes):
+            for s in (0, 1):
+                self.frame(lane, s).fill_(value)

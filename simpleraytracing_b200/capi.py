@@ -68,6 +68,7 @@ EXPORTS = [
     "srt_multi_create", "srt_multi_destroy", "srt_multi_last_error", "srt_multi_device_count", "srt_multi_set_meshes",
     "srt_multi_set_camera", "srt_multi_render_xray_device", "srt_multi_synchronize", "srt_multi_frame",
     "srt_multi_render_xray", "srt_multi_last_timing",
+    "srt_set_profiling", "srt_set_scan_residency", "srt_peer_barrier_device", "srt_render_xray_blocks_device",
 ]
 
 
@@ -148,6 +149,11 @@ class Library:
         L.srt_multi_frame.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
         L.srt_multi_render_xray.argtypes = [vp, C.POINTER(Params), vp]
         L.srt_multi_last_timing.argtypes = [vp, vp, C.POINTER(C.c_float)]
+        L.srt_set_profiling.argtypes = [vp, i32]
+        L.srt_set_scan_residency.argtypes = [vp, u32]
+        L.srt_peer_barrier_device.argtypes = [vp, u32, u32, C.POINTER(C.c_void_p), u32, u32]
+        L.srt_render_xray_blocks_device.argtypes = [vp, C.POINTER(Params), u32, u32, u32, C.POINTER(C.c_void_p),
+                                                    C.POINTER(C.c_void_p), u32, vp, vp]
 
     # ---- host-only helpers ---------------------------------------------------
     def default_params(self, **kw):
@@ -335,6 +341,34 @@ class Context:
             q.flags |= FLAG_FRAME0_MULTICAST
             params = q
         self._ck(self.lib.srt_render_lbuffer_blocks_device(self.h, C.byref(params), n_parts, part, len(frame_ptrs), arr))
+
+    def set_profiling(self, on=True):
+        self._ck(self.lib.srt_set_profiling(self.h, int(on)))
+
+    def set_scan_residency(self, max_ctas_per_sm=0):
+        self._ck(self.lib.srt_set_scan_residency(self.h, int(max_ctas_per_sm)))
+
+    def peer_barrier_device(self, n_ranks, rank, flag_ptrs, epoch, phases=3):
+        arr = (C.c_void_p * len(flag_ptrs))(*[C.c_void_p(int(q)) for q in flag_ptrs])
+        self._ck(self.lib.srt_peer_barrier_device(self.h, n_ranks, rank, arr, epoch, phases))
+
+    @staticmethod
+    def frame_call_args(params, frame_ptrs, flag_ptrs, multicast=False):
+        """ctypes arguments of render_xray_blocks_device that do not change from frame to frame (build once per
+        frame set: the per-frame call is then one foreign call)."""
+        fr = (C.c_void_p * len(frame_ptrs))(*[C.c_void_p(int(q)) for q in frame_ptrs])
+        fl = (C.c_void_p * len(flag_ptrs))(*[C.c_void_p(int(q)) for q in flag_ptrs])
+        q = Params.from_buffer_copy(params)
+        if multicast:
+            q.flags |= FLAG_FRAME0_MULTICAST
+        return q, fr, len(frame_ptrs), fl
+
+    def render_xray_blocks_device(self, call_args, n_parts, part, epoch, d_own_frame, d_image):
+        """One frame of the sharded pipeline: this rank's 16-row blocks stored into every rank's frame, device barrier
+        over the ranks, repair of the assembled frame d_own_frame into d_image.  call_args: frame_call_args(...)."""
+        q, fr, nf, fl = call_args
+        self._ck(self.lib.srt_render_xray_blocks_device(self.h, C.byref(q), n_parts, part, nf, fr, fl, epoch,
+                                                        C.c_void_p(d_own_frame), C.c_void_p(d_image)))
 
     def render_lbuffer_interleaved_device(self, params, n_parts, part, d_slot, d_dist=0, d_ssum=0, d_hits=0):
         self._ck(self.lib.srt_render_lbuffer_interleaved_device(self.h, C.byref(params), n_parts, part, C.c_void_p(d_slot),

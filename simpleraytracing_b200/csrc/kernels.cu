@@ -332,6 +332,9 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
     const uint32_t n_cols = (W + PX - 1) / PX;                                               // box columns of the frame
     const uint32_t c_begin = cta.x * a.scan_cols, c_end = min(n_cols, c_begin + a.scan_cols);
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    // the list counters are double-buffered: this launch counts into cand_count, which the previous launch of the path
+    // left at zero, and leaves cand_count_next at zero for the next one (no memset between frames)
+    if (tid == 0 && a.cand_count_next && blockIdx.x + blockIdx.y + blockIdx.z == 0) { a.cand_count_next[0] = 0; a.cand_count_next[1] = 0; }
     __syncthreads();
     uint32_t phase = 0, n1 = 0;              // n1: survivors staged by this warp (warp-uniform)
     const float x_first = 0.5f * (float)(PX - 1) + a.cam.xc;                                 // centre of box column 0
@@ -1540,6 +1543,36 @@ cudaError_t launch_ffma_peak(float* scratch, int blocks, int iters, cudaStream_t
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ peer barrier (one process per GPU)
+// Device-side barrier over the ranks of one node, on flags in peer-mapped memory: thread j publishes this rank's epoch
+// in rank j's flag array and waits until rank j's epoch has arrived in this rank's.  The kernels launched before it on
+// the stream have completed, so their stores into the peers' frames (plain, peer or multimem) are ordered before the
+// flag by the system-scope fence; the kernels launched after it (the repair pass) start when every rank has signalled,
+// i.e. when every rank's rows have landed in this rank's frame.  One CTA: a waiting barrier never occupies more than
+// one CTA slot, so barriers of several frames in flight (one per stream) cannot starve the kernels they wait for.
+// phases: bit 0 = signal, bit 1 = wait (3 = the whole barrier in one launch).
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerFlags f, uint32_t n, uint32_t rank, uint32_t epoch, uint32_t phases)
+{
+    const uint32_t j = threadIdx.x;
+    if (j >= n || j == rank) return;
+    __threadfence_system();
+    if (phases & 1u) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[j] + rank), "r"(epoch) : "memory");
+    if (phases & 2u) {
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.p[rank] + j) : "memory");
+        } while ((int32_t)(v - epoch) < 0);                                // epochs only grow (wrap-safe comparison)
+        __threadfence_system();
+    }
+}
+
+cudaError_t launch_peer_barrier(const PeerFlags& f, uint32_t n, uint32_t rank, uint32_t epoch, uint32_t phases, cudaStream_t s)
+{
+    if (n <= 1) return cudaSuccess;
+    peer_barrier_kernel<<<1, 32, 0, s>>>(f, n, rank, epoch, phases);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ launchers
 cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
 {
@@ -1553,6 +1586,17 @@ cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
 // shapes the filtered kernel is built for: {box width, box height, triangles per thread}
 #define SRT_SCAN_SHAPES(X) X(16, 2, 4) X(16, 1, 4) X(32, 1, 4) X(8, 4, 4) X(8, 1, 4) X(32, 2, 4) X(16, 4, 4) X(8, 8, 4) X(16, 2, 2) X(16, 2, 6) X(32, 2, 6)
 
+// Dynamic shared memory of a scan CTA.  scan_max_ctas (0 = no cap) caps the CTAs resident per SM by padding the
+// request: with frames pipelined on several streams, a scan that leaves a quarter of the register file free lets the
+// latency-bound tail kernels of the previous frame run beside it instead of behind it.
+static size_t scan_smem_bytes(size_t need, uint32_t max_ctas)
+{
+    if (max_ctas == 0) return need;
+    const size_t per_sm = 228 * 1024, reserved = 1024;                    // sm_100: 228 KB per SM, 1 KB reserved per CTA
+    const size_t pad = per_sm / (max_ctas + 1) - reserved + 256;          // max_ctas + 1 CTAs of this size do not fit
+    return std::min<size_t>(std::max(need, pad), 48 * 1024);
+}
+
 template <int PX, int PY, int K>
 static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
 {
@@ -1560,7 +1604,7 @@ static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
     static_assert(G::kSmem <= 48 * 1024, "the chunk and the queues must fit the default dynamic shared-memory limit");
     const uint32_t n_cols = (a.cam.W + PX - 1) / PX;
     dim3 grid((n_cols + a.scan_cols - 1) / a.scan_cols, a.n_blocks, a.scan_chunks);
-    lbuffer_filtered_kernel<PX, PY, K><<<grid, 128, G::kSmem, s>>>(a);
+    lbuffer_filtered_kernel<PX, PY, K><<<grid, 128, scan_smem_bytes(G::kSmem, a.scan_max_ctas), s>>>(a);
     return cudaGetLastError();
 }
 
@@ -1570,10 +1614,15 @@ static cudaError_t launch_candidates_t(const RenderArgs& a, cudaStream_t s)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    candidates_kernel<PX, PY><<<sms * 32, 128, 0, s>>>(a);                // grid-stride over the box list
+    // grid-stride over the box list / the pixel list; when the host knows the list sizes of this launch geometry
+    // (verified on its first render) the grids are sized to them: a share of a multi-GPU frame has short lists
+    const unsigned full = (unsigned)sms * 32;
+    const unsigned g1 = a.cand_hint ? std::min(full, (a.cand_hint + 127) / 128 + 1) : full;
+    const unsigned g2 = a.pix_hint ? std::min(full, (a.pix_hint + 127) / 128 + 1) : full;
+    candidates_kernel<PX, PY><<<g1, 128, 0, s>>>(a);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    exact_tests_kernel<<<sms * 32, 128, 0, s>>>(a);                       // grid-stride over the pixel list
+    exact_tests_kernel<<<g2, 128, 0, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -1593,9 +1642,9 @@ static int filtered_occupancy_t()
     return n;
 }
 
-int filtered_resident_ctas(uint32_t px, uint32_t py, uint32_t k)
+int filtered_resident_ctas(uint32_t px, uint32_t py, uint32_t k, uint32_t max_ctas)
 {
-#define X(PX, PY, K) if (px == PX && py == PY && k == K) return filtered_occupancy_t<PX, PY, K>();
+#define X(PX, PY, K) if (px == PX && py == PY && k == K) { const int n = filtered_occupancy_t<PX, PY, K>(); return (max_ctas && n > (int)max_ctas) ? (int)max_ctas : n; }
     SRT_SCAN_SHAPES(X)
 #undef X
     return 0;

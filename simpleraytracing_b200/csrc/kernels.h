@@ -77,6 +77,9 @@ struct RenderArgs {
     // cand_count[0] / [1] count them: zero when the scan starts; they may exceed the capacities (entries beyond are
     // dropped and resolve_hits_kernel recomputes every pixel with the exact sequence).
     uint2* cand; uint2* pix; uint32_t* cand_count; uint32_t cand_cap, pix_cap;
+    uint32_t* cand_count_next;   // the other pair of the double-buffered counters: the scan leaves it at zero for the next launch (may be null)
+    uint32_t cand_hint, pix_hint;   // list sizes of this launch geometry when the host has verified them (0 = unknown): grid sizing only
+    uint32_t scan_max_ctas;      // cap on the scan's resident CTAs per SM (0 = none), see scan_smem_bytes
     uint32_t* hit_head;      // [pixel]: the pixel's hit list (index into pix / hit_next; 0xffffffff = empty, also between renders)
     uint32_t* hit_next;      // [pix_cap]: next node of the list; node e = candidate e of the pix list, which exact_tests_kernel
                              // overwrites in place with {scene-wide triangle index, value}
@@ -154,7 +157,7 @@ cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, cudaStream_t s);
 cudaError_t launch_filtered_candidates(const RenderArgs& a, cudaStream_t s);
 bool filtered_shape_supported(uint32_t box_px, uint32_t box_py, uint32_t scan_k);
-int filtered_resident_ctas(uint32_t box_px, uint32_t box_py, uint32_t scan_k);     // CTAs resident per SM on the current device
+int filtered_resident_ctas(uint32_t box_px, uint32_t box_py, uint32_t scan_k, uint32_t max_ctas = 0);     // CTAs resident per SM on the current device
 // Culled kernel: bin pass (every triangle against every bin of a.bins_x x a.bins_y), then the render pass.  Same results
 // as the other kernels: the bins and the per-CTA cull only ever drop pairs the conservative filter proves to miss.
 cudaError_t launch_lbuffer_bins(const RenderArgs& a, cudaStream_t s);
@@ -162,6 +165,12 @@ cudaError_t launch_lbuffer_culled(const RenderArgs& a, cudaStream_t s);
 // Scatter gathered slots [n_parts][slot_rows][W] (block-cyclic 16-row blocks) back to image order [H][W].
 cudaError_t launch_deinterleave(const float* slots, float* frame, uint32_t W, uint32_t H, uint32_t n_parts,
                                 uint32_t slot_rows, cudaStream_t s);
+// Device-side barrier over the n ranks of a node: p[j] = rank j's flag array (n words, zero before the first epoch) as
+// mapped in this process; epochs start at 1 and grow by one per barrier.
+struct PeerFlags { uint32_t* p[8]; };
+// phases: 1 = signal only, 2 = wait only, 3 = both (a caller that drives several ranks from one thread enqueues all the
+// signals before the first wait)
+cudaError_t launch_peer_barrier(const PeerFlags& f, uint32_t n, uint32_t rank, uint32_t epoch, uint32_t phases, cudaStream_t s);
 // Artefact repair + image fill (lbuffer.cxx:329-404).
 cudaError_t launch_repair(const float* L, float* image, uint32_t W, uint32_t H, uint32_t depth, cudaStream_t s);
 

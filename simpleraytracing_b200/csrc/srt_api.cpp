@@ -115,6 +115,10 @@ struct srt_ctx {
     uint2* d_cand = nullptr; uint2* d_pix = nullptr; uint32_t* d_cand_count = nullptr; uint32_t cand_cap = 0, pix_cap = 0;
     uint32_t* h_cand_count = nullptr;    // [0] box list, [1] pixel list
     uint64_t lists_key = 0;              // launch geometry whose list sizes have been verified (0 = none)
+    uint32_t verified_cand = 0, verified_pix = 0;   // ... and those sizes (they never change for a scene / camera / geometry)
+    int cnt_parity = 0;                  // which pair of the double-buffered list counters (d_cand_count[4]) is clean
+    uint32_t scan_max_ctas = 0;          // cap on the scan's resident CTAs per SM (0 = none; srt_set_scan_residency)
+    bool profiling = true;               // record the per-render timing events (srt_set_profiling)
     int force_scan_cols = 0;             // diagnostic override of the box columns per CTA: 0 = heuristic
     uint32_t force_bin_cap = 0, force_cand_cap = 0, force_pix_cap = 0;    // diagnostic: shrink the lists to exercise the overflow paths
     // per-bin triangle lists of the culled kernel
@@ -137,6 +141,15 @@ int fail(srt_ctx* c, int code, const char* fmt, ...)
 #define SRT_CUDA(c, call)                                                                        \
     do { cudaError_t e__ = (call);                                                               \
          if (e__ != cudaSuccess) return fail((c), SRT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); } while (0)
+
+// elapsed time between two of the context's events; 0 when the per-render events are switched off (srt_set_profiling)
+int elapsed_ms(srt_ctx* c, float* out, int from, int to)
+{
+    *out = 0.0f;
+    if (!c->profiling) return SRT_OK;
+    SRT_CUDA(c, cudaEventElapsedTime(out, c->ev[from], c->ev[to]));
+    return SRT_OK;
+}
 
 void free_mesh(MeshBuf& m)
 {
@@ -217,7 +230,11 @@ int ensure_lists(srt_ctx* c, uint64_t cand, uint64_t pix)
         SRT_CUDA(c, cudaHostAlloc(&c->h_cand_count, 2 * sizeof(uint32_t), cudaHostAllocDefault));
         c->h_cand_count[0] = c->h_cand_count[1] = 0;
     }
-    if (!c->d_cand_count) SRT_CUDA(c, cudaMalloc(&c->d_cand_count, 2 * sizeof(uint32_t)));
+    if (!c->d_cand_count) {
+        SRT_CUDA(c, cudaMalloc(&c->d_cand_count, 4 * sizeof(uint32_t)));
+        SRT_CUDA(c, cudaMemsetAsync(c->d_cand_count, 0, 4 * sizeof(uint32_t), c->stream));
+        c->cnt_parity = 0;
+    }
     if (cand > c->cand_cap) {
         SRT_CUDA(c, cudaStreamSynchronize(c->stream));
         cudaFree(c->d_cand); c->d_cand = nullptr; c->cand_cap = 0;
@@ -437,7 +454,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         // last wave and many tiny CTAs.
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-        int resident = srt::filtered_resident_ctas(box_px, box_py, scan_k);
+        int resident = srt::filtered_resident_ctas(box_px, box_py, scan_k, c->scan_max_ctas);
         if (resident <= 0) resident = SRT_RESIDENT_CTAS;
         uint32_t chunks = 0;
         for (size_t m = 0; m < c->n_meshes; ++m)
@@ -472,34 +489,41 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         // what that frame needed -- the counts of a scene / camera / launch geometry never change afterwards.
         rc = ensure_lists(c, std::max<uint64_t>(4ull << 20, 32ull * c->total_tris), std::max<uint64_t>(16ull << 20, 64ull * c->total_tris));
         if (rc) return rc;
-        a.cand = c->d_cand; a.pix = c->d_pix; a.hit_next = c->d_hit_next; a.cand_count = c->d_cand_count;
-        a.cand_cap = c->cand_cap; a.pix_cap = c->pix_cap;
+        a.cand = c->d_cand; a.pix = c->d_pix; a.hit_next = c->d_hit_next;
+        a.cand_count = c->d_cand_count + 2 * c->cnt_parity; a.cand_count_next = c->d_cand_count + 2 * (c->cnt_parity ^ 1);
+        a.cand_cap = c->cand_cap; a.pix_cap = c->pix_cap; a.scan_max_ctas = c->scan_max_ctas;
         if (c->force_cand_cap) a.cand_cap = std::min(a.cand_cap, c->force_cand_cap);
         if (c->force_pix_cap) a.pix_cap = std::min(a.pix_cap, c->force_pix_cap);
         if (c->n_meshes > 32 || c->total_tris >= (1ull << 27)) kernel = SRT_KERNEL_EXACT;     // candidate entries: 5-bit mesh, 27-bit triangle
     }
-    SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    const bool prof = c->profiling;
+    if (prof) SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     if (kernel == SRT_KERNEL_FILTERED) {
         // launch geometry the list sizes were verified for (scene / camera changes reset it through `packed`)
         const uint64_t key = ((uint64_t)row_begin << 40) ^ ((uint64_t)row_end << 20) ^ ((uint64_t)parts << 12) ^ ((uint64_t)part << 4) ^
                              ((uint64_t)mode << 2) ^ (all ? 2u : 0u) ^ ((uint64_t)box_px << 52) ^ ((uint64_t)box_py << 58) ^ 1u;
         const bool forced = c->force_cand_cap || c->force_pix_cap;              // tests exercise the overflow fallback
         const bool verify = !forced && (repack || c->lists_key != key);
+        // does launch_lbuffer_filtered launch anything?  (an empty launch touches no counter: the pairs keep their roles)
+        const bool launches = !(a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0 || a.scan_chunks == 0);
+        if (!verify && !forced) { a.cand_hint = c->verified_cand; a.pix_hint = c->verified_pix; }
         for (int attempt = 0;; ++attempt) {
-            SRT_CUDA(c, cudaMemsetAsync(c->d_cand_count, 0, 2 * sizeof(uint32_t), c->stream));
-            SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+            // the pair of counters this launch counts into was left at zero by the previous scan (or at allocation);
+            // a repeated attempt counts into the same pair again and clears it first
+            if (attempt > 0) SRT_CUDA(c, cudaMemsetAsync(a.cand_count, 0, 2 * sizeof(uint32_t), c->stream));
+            if (prof) SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
             SRT_CUDA(c, srt::launch_lbuffer_filtered(a, c->stream));
-            SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+            if (prof) SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
             SRT_CUDA(c, srt::launch_filtered_candidates(a, c->stream));
-            SRT_CUDA(c, cudaMemcpyAsync(c->h_cand_count, c->d_cand_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             if (!verify) break;
             // First render of this launch geometry: wait for the counts.  A list that overflowed would make the resolve pass
             // recompute every pixel with the exact sequence (correct, but hours on a large scene): grow and redo instead.
+            SRT_CUDA(c, cudaMemcpyAsync(c->h_cand_count, a.cand_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             SRT_CUDA(c, cudaStreamSynchronize(c->stream));
-            const uint64_t n_cand = c->h_cand_count[0], n_pix = c->h_cand_count[1];
+            const uint64_t n_cand = launches ? c->h_cand_count[0] : 0, n_pix = launches ? c->h_cand_count[1] : 0;
             if (n_cand <= a.cand_cap && n_pix <= a.pix_cap) {
                 c->lists_key = key;
-                // keep twice the need (other launch geometries of the same scene, e.g. shares of a multi-GPU frame, need less)
+                c->verified_cand = (uint32_t)std::max<uint64_t>(n_cand, 1); c->verified_pix = (uint32_t)std::max<uint64_t>(n_pix, 1);
                 break;
             }
             if (attempt >= 4) break;                                   // give up growing: the resolve pass stays exact
@@ -513,18 +537,19 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
             }
             a.cand = c->d_cand; a.pix = c->d_pix; a.hit_next = c->d_hit_next; a.cand_cap = c->cand_cap; a.pix_cap = c->pix_cap;
         }
+        if (launches) c->cnt_parity ^= 1;                              // the scan has cleared the other pair
         SRT_CUDA(c, srt::launch_resolve_hits(a, c->stream)); extra_launches = 3;          // + candidates, exact tests
     } else if (kernel == SRT_KERNEL_CULLED) {
         SRT_CUDA(c, srt::launch_lbuffer_bins(a, c->stream)); extra_launches = 1;
-        SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+        if (prof) SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
         SRT_CUDA(c, srt::launch_lbuffer_culled(a, c->stream));
-        SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+        if (prof) SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
     } else {
-        SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+        if (prof) SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
         SRT_CUDA(c, srt::launch_lbuffer_exact(a, audit, c->stream));
-        SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+        if (prof) SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
     }
-    SRT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    if (prof) SRT_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     c->timing.kernel_used = kernel;
     c->timing.scan_cols = a.scan_cols;
     c->timing.launches = ((band_rows > 0) ? 1 + extra_launches : 0) + (repack ? 1 + (uint32_t)c->n_meshes : 0);
@@ -532,7 +557,8 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     c->timing.pair_tests = (uint64_t)band_rows * cam.width * tris;
     c->timing.exact_tests = 0; c->timing.filter_violations = 0;
     c->counters_pending = a.counters != nullptr;
-    c->timing_pending = true;
+    c->timing_pending = prof || c->counters_pending;
+    if (!prof) { c->timing.render_ms = 0.0f; c->timing.main_kernel_ms = 0.0f; }
     return SRT_OK;
 }
 
@@ -608,6 +634,23 @@ int srt_synchronize(srt_ctx* c)
 {
     if (!c) return SRT_ERR_INVALID;
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SRT_OK;
+}
+
+int srt_set_profiling(srt_ctx* c, int enable)
+{
+    if (!c) return SRT_ERR_INVALID;
+    SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->profiling = enable != 0;
+    c->timing_pending = false;
+    return SRT_OK;
+}
+
+int srt_set_scan_residency(srt_ctx* c, uint32_t max_ctas_per_sm)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (max_ctas_per_sm != 0 && max_ctas_per_sm < 4) return fail(c, SRT_ERR_INVALID, "the scan can be capped at 4 or more CTAs per SM (0 = no cap)");
+    c->scan_max_ctas = max_ctas_per_sm;
     return SRT_OK;
 }
 
@@ -864,6 +907,36 @@ int srt_deinterleave_device(srt_ctx* c, uint32_t n_parts, const float* d_slots, 
     return SRT_OK;
 }
 
+int srt_peer_barrier_device(srt_ctx* c, uint32_t n_ranks, uint32_t rank, uint32_t* const* d_flags, uint32_t epoch, uint32_t phases)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (phases == 0 || phases > 3) return fail(c, SRT_ERR_INVALID, "phases: 1 = signal, 2 = wait, 3 = both");
+    if (n_ranks == 0 || n_ranks > 8 || rank >= n_ranks || !d_flags) return fail(c, SRT_ERR_INVALID, "rank %u of %u (1 to 8 ranks, flag arrays required)", rank, n_ranks);
+    srt::PeerFlags f{};
+    for (uint32_t j = 0; j < n_ranks; ++j) {
+        if (!d_flags[j]) return fail(c, SRT_ERR_INVALID, "flag array %u is NULL", j);
+        f.p[j] = d_flags[j];
+    }
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    SRT_CUDA(c, srt::launch_peer_barrier(f, n_ranks, rank, epoch, phases, c->stream));
+    return SRT_OK;
+}
+
+int srt_render_xray_blocks_device(srt_ctx* c, const srt_params* p, uint32_t n_parts, uint32_t part, uint32_t n_frames,
+                                  float* const* d_frames, uint32_t* const* d_flags, uint32_t epoch, const float* d_own_frame,
+                                  float* d_image)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (!d_own_frame || !d_image) return fail(c, SRT_ERR_INVALID, "own frame / image is NULL");
+    int rc = srt_render_lbuffer_blocks_device(c, p, n_parts, part, n_frames, d_frames);
+    if (rc) return rc;
+    if (n_parts > 1) {
+        rc = srt_peer_barrier_device(c, n_parts, part, d_flags, epoch, 3);
+        if (rc) return rc;
+    }
+    return srt_repair_device(c, p, d_own_frame, d_image);
+}
+
 int srt_render_lbuffer(srt_ctx* c, const srt_params* p, uint32_t rb, uint32_t re,
                        float* L_out, float* dist_out, int32_t* ssum_out, uint32_t* hits_out)
 {
@@ -884,10 +957,10 @@ int srt_render_lbuffer(srt_ctx* c, const srt_params* p, uint32_t rb, uint32_t re
         if (ssum_out) SRT_CUDA(c, cudaMemcpyAsync(ssum_out + off, c->d_ssum + off, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
         if (hits_out) SRT_CUDA(c, cudaMemcpyAsync(hits_out + off, c->d_hits + off, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
     }
-    SRT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    if (c->profiling) SRT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
-    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.d2h_ms, c->ev[1], c->ev[2]));
+    if (int erc = elapsed_ms(c, &c->timing.render_ms, 0, 1)) return erc;
+    if (int erc = elapsed_ms(c, &c->timing.d2h_ms, 1, 2)) return erc;
     c->timing.repair_ms = 0.0f; c->timing.h2d_ms = 0.0f;
     return SRT_OK;
 }
@@ -899,9 +972,9 @@ int srt_repair_device(srt_ctx* c, const srt_params* p, const float* dL, float* d
     if (!p || !dL || !dimg || dL == dimg) return fail(c, SRT_ERR_INVALID, "repair needs distinct non-NULL buffers");
     if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
     SRT_CUDA(c, cudaSetDevice(c->device));
-    SRT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    if (c->profiling) SRT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     SRT_CUDA(c, srt::launch_repair(dL, dimg, c->camera.width, c->camera.height, p->repair_depth, c->stream));
-    SRT_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    if (c->profiling) SRT_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     return SRT_OK;
 }
 
@@ -919,7 +992,7 @@ int srt_repair(srt_ctx* c, const srt_params* p, const float* L_in, float* image_
     if (rc) return rc;
     SRT_CUDA(c, cudaMemcpyAsync(image_out, c->d_img, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.repair_ms, c->ev[2], c->ev[3]));
+    if (int erc = elapsed_ms(c, &c->timing.repair_ms, 2, 3)) return erc;
     c->timing.launches = 1;
     return SRT_OK;
 }
@@ -940,8 +1013,8 @@ int srt_render_xray(srt_ctx* c, const srt_params* p, float* image_out)
     if (rc) return rc;
     SRT_CUDA(c, cudaMemcpyAsync(image_out, c->d_img, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
-    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.repair_ms, c->ev[2], c->ev[3]));
+    if (int erc = elapsed_ms(c, &c->timing.render_ms, 0, 1)) return erc;
+    if (int erc = elapsed_ms(c, &c->timing.repair_ms, 2, 3)) return erc;
     c->timing.launches = 2;
     return SRT_OK;
 }
@@ -969,7 +1042,7 @@ int srt_render_xray_sorted(srt_ctx* c, const srt_params* p, float* image_out)
     if (rc) return rc;
     SRT_CUDA(c, cudaMemcpyAsync(image_out, c->d_img, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
+    if (int erc = elapsed_ms(c, &c->timing.render_ms, 0, 1)) return erc;
     c->timing.repair_ms = 0.0f;
     return SRT_OK;
 }
@@ -1143,9 +1216,9 @@ int srt_render_shaded(srt_ctx* c, const srt_params* p, const srt_light* light, c
     if (rc) return rc;
     SRT_CUDA(c, cudaMemcpyAsync(rgb_out, c->d_rgb, bytes, cudaMemcpyDeviceToHost, c->stream));
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
-    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.repair_ms, c->ev[2], c->ev[3]));     // shade pass time
-    SRT_CUDA(c, cudaEventElapsedTime(&c->timing.shadow_grid_ms, c->ev[6], c->ev[2]));
+    if (int erc = elapsed_ms(c, &c->timing.render_ms, 0, 1)) return erc;
+    if (int erc = elapsed_ms(c, &c->timing.repair_ms, 2, 3)) return erc;     // shade pass time
+    if (int erc = elapsed_ms(c, &c->timing.shadow_grid_ms, 6, 2)) return erc;
     c->timing_pending = false;
     return SRT_OK;
 }
@@ -1171,9 +1244,9 @@ int srt_last_timing(srt_ctx* c, srt_timing* out)
     if (!c || !out) return SRT_ERR_INVALID;
     if (c->timing_pending) {
         SRT_CUDA(c, cudaSetDevice(c->device));
-        SRT_CUDA(c, cudaEventSynchronize(c->ev[1]));
-        SRT_CUDA(c, cudaEventElapsedTime(&c->timing.render_ms, c->ev[0], c->ev[1]));
-        SRT_CUDA(c, cudaEventElapsedTime(&c->timing.main_kernel_ms, c->ev[4], c->ev[5]));
+        if (c->profiling) SRT_CUDA(c, cudaEventSynchronize(c->ev[1]));
+        if (int erc = elapsed_ms(c, &c->timing.render_ms, 0, 1)) return erc;
+        if (int erc = elapsed_ms(c, &c->timing.main_kernel_ms, 4, 5)) return erc;
         if (c->counters_pending && c->d_counters) {
             unsigned long long cnts[3] = { 0, 0, 0 };
             SRT_CUDA(c, cudaMemcpyAsync(cnts, c->d_counters, sizeof cnts, cudaMemcpyDeviceToHost, c->stream));

@@ -1,0 +1,139 @@
+"""The sharded frame pipeline of bench.py (one process per GPU: srt_render_xray_blocks_device = render of the rank's
+blocks stored into every rank's frame + srt_peer_barrier_device + repair), exercised on ONE GPU: every "rank" is a
+context with its own stream in this process, the "peer-mapped" frames and flag arrays are plain buffers of the same
+device.  The kernels, the barrier protocol (flags, epochs, two frame sets per lane) and the concurrency of several
+lanes are exactly those of the multi-GPU run; only the transport differs.  Replaces the gather of
+src/main-mpi.cxx:854-881.  The image must equal the unsharded render bit for bit."""
+import numpy as np
+import pytest
+
+from conftest import bits
+from simpleraytracing_b200 import Context, KERNEL_CULLED, KERNEL_FILTERED, scene
+
+pytestmark = pytest.mark.gpu
+MU0 = float(scene.MU_MESH0)
+FLAG_WORDS = 64
+
+
+class FakeRanks:
+    """n_ranks x lanes contexts on cuda:0 with frames / flags laid out like bands.PeerLanes"""
+
+    def __init__(self, srtlib, meshes, cam, n_ranks, lanes, params):
+        import torch
+        self.torch = torch
+        self.n, self.lanes, self.W, self.H = n_ranks, lanes, cam.width, cam.height
+        px = self.W * self.H
+        dev = torch.device("cuda", 0)
+        # buf[rank][lane]: [frame set 0][frame set 1][flags]
+        self.buf = torch.zeros(n_ranks, lanes, 2 * px + FLAG_WORDS, dtype=torch.float32, device=dev)
+        self.img = torch.zeros(n_ranks, lanes, px, dtype=torch.float32, device=dev)
+        self.ctx = [[Context(0, srtlib) for _ in range(lanes)] for _ in range(n_ranks)]
+        self.streams = [[torch.cuda.Stream(device=dev) for _ in range(lanes)] for _ in range(n_ranks)]
+        self.epoch = [[0] * lanes for _ in range(n_ranks)]
+        self.args = {}
+        self.params = params
+        for r in range(n_ranks):
+            for l in range(lanes):
+                c = self.ctx[r][l]
+                c.set_stream(self.streams[r][l].cuda_stream)
+                c.set_meshes(meshes); c.set_camera(cam)
+                c.set_profiling(False)
+                flags = [self.buf[q, l, 2 * px:].data_ptr() for q in range(n_ranks)]
+                for s in (0, 1):
+                    own = self.buf[r, l, s * px:(s + 1) * px].data_ptr()
+                    frames = [own] + [self.buf[q, l, s * px:(s + 1) * px].data_ptr() for q in range(n_ranks) if q != r]
+                    self.args[r, l, s] = (frames, flags, own)
+
+    def frame(self, l, order):
+        """one frame of lane `l` on every rank.  All ranks are driven by this one thread, and streams may share a
+        hardware queue, so every rank's signal is enqueued before the first wait (a real rank uses phases = 3)."""
+        self.epoch[0][l] += 1
+        e = self.epoch[0][l]
+        for r in order:
+            frames, flags, own = self.args[r, l, e & 1]
+            self.ctx[r][l].render_lbuffer_blocks_device(self.params, self.n, r, frames)
+        for r in order:
+            self.ctx[r][l].peer_barrier_device(self.n, r, self.args[r, l, e & 1][1], e, phases=1)
+        for r in order:
+            frames, flags, own = self.args[r, l, e & 1]
+            self.ctx[r][l].peer_barrier_device(self.n, r, flags, e, phases=2)
+            self.ctx[r][l].repair_device(self.params, own, self.img[r, l].data_ptr())
+
+    def poison(self):
+        px = self.W * self.H
+        self.buf[:, :, :2 * px].fill_(float("nan"))
+        self.img.fill_(float("nan"))
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        for row in self.ctx:
+            for c in row:
+                c.close()
+
+
+@pytest.mark.parametrize("kernel,n_ranks,lanes", [(KERNEL_FILTERED, 2, 1), (KERNEL_FILTERED, 4, 3), (KERNEL_CULLED, 3, 2)])
+def test_sharded_pipeline_equals_the_unsharded_render(gpu_ctx, srtlib, dragon, kernel, n_ranks, lanes):
+    import torch
+    lo, hi = srtlib.scene_bbox([(dragon, MU0)])
+    cam = srtlib.camera_from_bbox(lo, hi, 600, 410)
+    p = srtlib.default_params(kernel=kernel)
+    gpu_ctx.set_meshes([(dragon, MU0)]); gpu_ctx.set_camera(cam)
+    want = torch.from_numpy(gpu_ctx.render_xray(p).view(np.int32)).cuda()
+    fr = FakeRanks(srtlib, [(dragon, MU0)], cam, n_ranks, lanes, p)
+    for rnd in range(3):
+        fr.poison()
+        torch.cuda.synchronize()
+        # 2 frames per lane (both frame sets), all lanes and all ranks in flight at once
+        order = list(range(n_ranks)) if rnd != 1 else list(reversed(range(n_ranks)))
+        for f in range(2):
+            for l in range(lanes):
+                fr.frame(l, order)
+        torch.cuda.synchronize()
+        for r in range(n_ranks):
+            for l in range(lanes):
+                assert torch.equal(fr.img[r, l].view(torch.int32), want), (rnd, r, l)
+    fr.close()
+
+
+def test_profiling_off_and_scan_residency_do_not_change_the_image(gpu_ctx, srtlib, dragon):
+    lo, hi = srtlib.scene_bbox([(dragon, MU0)])
+    cam = srtlib.camera_from_bbox(lo, hi, 512, 512)
+    p = srtlib.default_params(kernel=KERNEL_FILTERED)
+    gpu_ctx.set_meshes([(dragon, MU0)]); gpu_ctx.set_camera(cam)
+    want = gpu_ctx.render_xray(p)
+    c = Context(0, srtlib)
+    c.set_meshes([(dragon, MU0)]); c.set_camera(cam)
+    c.set_profiling(False)
+    for cap in (0, 4, 0):
+        c.set_scan_residency(cap)
+        for _ in range(3):                                   # the list counters alternate between their two pairs
+            got = c.render_xray(p)
+            assert (bits(got) == bits(want)).all(), cap
+    t = c.timing()
+    assert t.render_ms == 0.0 and t.main_kernel_ms == 0.0     # no events were recorded
+    c.set_profiling(True)
+    got = c.render_xray(p)
+    assert (bits(got) == bits(want)).all() and c.timing().render_ms > 0.0
+    from simpleraytracing_b200 import SrtError
+    with pytest.raises(SrtError):
+        c.set_scan_residency(2)
+    c.close()
+
+
+def test_fused_frame_call_with_one_rank_equals_render_xray(gpu_ctx, srtlib, dragon):
+    import torch
+    lo, hi = srtlib.scene_bbox([(dragon, MU0)])
+    cam = srtlib.camera_from_bbox(lo, hi, 300, 150)
+    p = srtlib.default_params(kernel=KERNEL_FILTERED)
+    gpu_ctx.set_meshes([(dragon, MU0)]); gpu_ctx.set_camera(cam)
+    want = torch.from_numpy(gpu_ctx.render_xray(p).view(np.int32)).cuda()
+    frame = torch.zeros(300 * 150, dtype=torch.float32, device="cuda"); img = torch.zeros_like(frame)
+    flags = torch.zeros(FLAG_WORDS, dtype=torch.int32, device="cuda")
+    args = Context.frame_call_args(p, [frame.data_ptr()], [flags.data_ptr()])
+    for e in (1, 2, 3):
+        gpu_ctx.render_xray_blocks_device(args, 1, 0, e, frame.data_ptr(), img.data_ptr())
+        gpu_ctx.synchronize()
+        assert torch.equal(img.view(torch.int32), want)
+    from simpleraytracing_b200 import SrtError
+    with pytest.raises(SrtError):
+        gpu_ctx.peer_barrier_device(2, 0, [flags.data_ptr(), flags.data_ptr()], 1, phases=0)
