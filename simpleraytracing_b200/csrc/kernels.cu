@@ -321,23 +321,43 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
 {
     using G = ScanGeom<PX, PY, K>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* recs = reinterpret_cast<float4*>(smem_raw);                        // [K][3][128]: the CTA's chunk, SoA
+    float4* recs = reinterpret_cast<float4*>(smem_raw);                        // [K][3][128]: the CTA's current chunk, SoA
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)K * 3 * 128 * sizeof(float4));
     uint2* stage = reinterpret_cast<uint2*>(bar + 2) + (threadIdx.x >> 5) * kStageCap;       // this warp's survivors
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
-    const CtaCoord cta = cta_coord();
     const uint32_t W = a.cam.W;
-    const uint32_t row0 = a.row_begin + (cta.y * a.blk_stride + a.blk_phase) * 16;          // the CTA's 16-row block
     const uint32_t n_cols = (W + PX - 1) / PX;                                               // box columns of the frame
-    const uint32_t c_begin = cta.x * a.scan_cols, c_end = min(n_cols, c_begin + a.scan_cols);
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     // the list counters are double-buffered: this launch counts into cand_count, which the previous launch of the path
     // left at zero, and leaves cand_count_next at zero for the next one (no memset between frames)
-    if (tid == 0 && a.cand_count_next && blockIdx.x + blockIdx.y + blockIdx.z == 0) { a.cand_count_next[0] = 0; a.cand_count_next[1] = 0; }
+    if (tid == 0 && a.cand_count_next && blockIdx.x == 0) { a.cand_count_next[0] = 0; a.cand_count_next[1] = 0; }
     __syncthreads();
     uint32_t phase = 0, n1 = 0;              // n1: survivors staged by this warp (warp-uniform)
     const float x_first = 0.5f * (float)(PX - 1) + a.cam.xc;                                 // centre of box column 0
+
+    // Persistent CTAs, static partition.  The work of the launch is the sequence of UNITS
+    //   (chunk, 16-row block, box row, range of scan_cols box columns),  chunk-major,
+    // every unit the same number of box tests (up to the frame's ragged edge); CTA g of G takes the contiguous range
+    // [g T / G, (g + 1) T / G) of the T units, so all CTAs finish together whatever the share of the frame and the number
+    // of resident CTAs (no partial last wave), and a CTA loads a new chunk at most twice.  Boxes over the object stage
+    // survivors and cost more than boxes over empty space, so the blocks of a chunk are visited in a strided order
+    // (block (t s) mod n, s coprime to n, ~0.62 n): the dozen blocks of a CTA's range sample the whole frame and every
+    // CTA gets the same mix (with contiguous bands the CTAs over the object's centre finished 20 % late).
+    const uint32_t parts_x = a.scan_parts_x;
+    const uint64_t per_chunk = (uint64_t)a.n_blocks * G::kBoxRows * parts_x;
+    const uint64_t total = per_chunk * a.scan_chunks;
+    const uint64_t u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
+    uint32_t gz = (uint32_t)(u0 / per_chunk);                                                // chunk, counted over the contributing meshes
+    uint32_t part, j, bt, blk;                                                              // bt: position in the block order, blk: the block
+    {
+        uint64_t r = u0 - (uint64_t)gz * per_chunk;
+        part = (uint32_t)(r % parts_x); r /= parts_x;
+        j = (uint32_t)(r % G::kBoxRows); bt = (uint32_t)(r / G::kBoxRows);
+        blk = (uint32_t)(((uint64_t)bt * a.scan_blk_stride) % a.n_blocks);
+    }
+    bool new_chunk = true, new_row = true, row_ok = false;
+    uint32_t m = 0, z = 0, n_chunks = 1;     // mesh / chunk within the mesh / chunks of that mesh
 
     // append the warp's staged survivors to the global candidate list: one atomic, coalesced 8-byte stores
     auto flush = [&]() {
@@ -351,64 +371,77 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
         n1 = 0;
     };
 
-    for (int m = 0; m < a.n_meshes; ++m) {
-        const DevMesh* Mp = a.meshes + m;
-        const uint32_t n_chunks = Mp->n_chunks;
-        if (!Mp->contributes || Mp->n == 0 || cta.z >= n_chunks) continue;                   // CTA-uniform
-        // the CTA's chunk of level-0 records: one bulk copy (TMA) into shared memory, then K records per thread into
-        // registers per box row (SoA in the chunk: consecutive lanes read consecutive float4)
-        __syncthreads();                                                                     // recs of the previous mesh are consumed
-        if (tid == 0) {
-            mbar_expect_tx(bar, (uint32_t)(K * 3 * 128 * sizeof(float4)));
-            bulk_g2s(recs, Mp->scan + (size_t)cta.z * K * 3 * 128, (uint32_t)(K * 3 * 128 * sizeof(float4)), bar);
+    // the thread's K triangles: x slopes and bounds, and the row parts of Y, Y2, D folded with the row's yc -- the inner
+    // loop lives on these 8 values per triangle (re-read from shared memory once per box row: 12 LDS per ~100 boxes)
+    float bx[K], bd[K], R[K], bx2[K], R2[K], by[K], dy[K], by2[K];
+    // level-0 test of the thread's K triangles against the box with centre xc: may any of them touch it?
+    auto scan = [&](float xc) {
+        bool surv = false;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float D = fabsf(fmaf(bd[k], xc, dy[k]));
+            const float Y = fmaf(bx[k], xc, by[k]), Y2 = fmaf(bx2[k], xc, by2[k]);
+            const bool r1 = fabsf(Y) - D > R[k], r2 = fabsf(Y2) - D > R2[k];          // NaN survives
+            surv |= !(r1 | r2);                                                      // bitwise: no short-circuit branches
         }
-        mbar_wait(bar, phase);
-        phase ^= 1u;
+        return surv;
+    };
+    // stage the survivors of box (j, i) -- rare: one ballot per k.  The tests are re-evaluated on an opaque copy
+    // of xc so that the compiler does not carry the K predicates of every box through the hot loop.
+    auto push = [&](uint32_t i, float xc) {
+        asm volatile("" : "+f"(xc));
+        if (n1 + 32 * K > kStageCap) flush();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float D = fabsf(fmaf(bd[k], xc, dy[k]));
+            const float Y = fmaf(bx[k], xc, by[k]), Y2 = fmaf(bx2[k], xc, by2[k]);
+            const bool sv = !((fabsf(Y) - D > R[k]) | (fabsf(Y2) - D > R2[k]));
+            const unsigned bal = __ballot_sync(0xffffffffu, sv);
+            if (sv) stage[n1 + __popc(bal & ((1u << lane) - 1u))] =
+                cand_pack(j, blk, i, ((uint32_t)k * 128 + tid) * n_chunks + z, m);
+            n1 += __popc(bal);
+        }
+        if (n1 >= kStageFlush) flush();
+    };
+
 #pragma unroll 1
-        for (uint32_t j = 0; j < G::kBoxRows; ++j) {
-            const uint32_t br0 = row0 + j * PY;
-            if (br0 >= a.row_end) break;
+    for (uint64_t u = u0; u < u1; ++u) {
+        if (new_chunk) {
+            // chunk gz of the launch -> (mesh, chunk of the mesh): meshes that add no path length hold no chunks
+            uint32_t rest = gz;
+            const DevMesh* Mp = a.meshes;
+            for (m = 0;; ++m, ++Mp) {
+                const uint32_t nc = (Mp->contributes && Mp->n) ? Mp->n_chunks : 0u;
+                if (rest < nc) { n_chunks = nc; break; }
+                rest -= nc;
+            }
+            z = rest;
+            // the chunk's level-0 records: one bulk copy (TMA) into shared memory (SoA in the chunk: consecutive lanes
+            // read consecutive float4)
+            __syncthreads();                                                                 // recs of the previous chunk are consumed
+            if (tid == 0) {
+                mbar_expect_tx(bar, (uint32_t)(K * 3 * 128 * sizeof(float4)));
+                bulk_g2s(recs, Mp->scan + (size_t)z * K * 3 * 128, (uint32_t)(K * 3 * 128 * sizeof(float4)), bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            new_chunk = false; new_row = true;
+        }
+        if (new_row) {
+            const uint32_t br0 = a.row_begin + (blk * a.blk_stride + a.blk_phase) * 16 + j * PY;   // first pixel row of the box row
+            row_ok = br0 < a.row_end;
             const uint32_t br1 = min(a.row_end, br0 + PY) - 1;                                // boxes are clamped to the frame
             const float yc = 0.5f * (float)(br0 + br1) + a.cam.yc;
-            // The thread's K records are re-read from shared memory at every box row (12 LDS per ~100 boxes) instead of
-            // being held across rows: the inner loop then lives on 8 values per triangle -- x slopes and bounds, and the
-            // row parts of Y, Y2, D folded with yc.
-            float bx[K], bd[K], R[K], bx2[K], R2[K], by[K], dy[K], by2[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const float4 fa = recs[(k * 3 + 0) * 128 + tid], fb = recs[(k * 3 + 1) * 128 + tid], fc = recs[(k * 3 + 2) * 128 + tid];
                 bx[k] = fa.x; bd[k] = fa.w; R[k] = fb.w; bx2[k] = fc.x; R2[k] = fc.w;
                 by[k] = fmaf(fa.y, yc, fa.z); dy[k] = fmaf(fb.x, yc, fb.y); by2[k] = fmaf(fc.y, yc, fc.z);
             }
-            // level-0 test of the thread's K triangles against the box with centre xc: may any of them touch it?
-            auto scan = [&](float xc) {
-                bool surv = false;
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float D = fabsf(fmaf(bd[k], xc, dy[k]));
-                    const float Y = fmaf(bx[k], xc, by[k]), Y2 = fmaf(bx2[k], xc, by2[k]);
-                    const bool r1 = fabsf(Y) - D > R[k], r2 = fabsf(Y2) - D > R2[k];          // NaN survives
-                    surv |= !(r1 | r2);                                                      // bitwise: no short-circuit branches
-                }
-                return surv;
-            };
-            // stage the survivors of box (j, i) -- rare: one ballot per k.  The tests are re-evaluated on an opaque copy
-            // of xc so that the compiler does not carry the K predicates of every box through the hot loop.
-            auto push = [&](uint32_t i, float xc) {
-                asm volatile("" : "+f"(xc));
-                if (n1 + 32 * K > kStageCap) flush();
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float D = fabsf(fmaf(bd[k], xc, dy[k]));
-                    const float Y = fmaf(bx[k], xc, by[k]), Y2 = fmaf(bx2[k], xc, by2[k]);
-                    const bool sv = !((fabsf(Y) - D > R[k]) | (fabsf(Y2) - D > R2[k]));
-                    const unsigned bal = __ballot_sync(0xffffffffu, sv);
-                    if (sv) stage[n1 + __popc(bal & ((1u << lane) - 1u))] =
-                        cand_pack(j, cta.y, i, ((uint32_t)k * 128 + tid) * n_chunks + cta.z, (uint32_t)m);
-                    n1 += __popc(bal);
-                }
-                if (n1 >= kStageFlush) flush();
-            };
+            new_row = false;
+        }
+        if (row_ok) {
+            const uint32_t c_begin = part * a.scan_cols, c_end = min(n_cols, c_begin + a.scan_cols);
             // full boxes: the centre advances by PX (exact in binary32: half-integers far below 2^23)
             const uint32_t c_full = min(c_end, W / PX);
             float xc = fmaf((float)c_begin, (float)PX, x_first);
@@ -427,6 +460,15 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
             if (c_full < c_end) {                               // the last box of the row is clamped to the frame
                 const float xl = 0.5f * (float)(c_full * PX + W - 1) + a.cam.xc;
                 if (__any_sync(0xffffffffu, scan(xl))) push(c_full, xl);
+            }
+        }
+        // next unit: column range, then box row, then block, then chunk
+        if (++part == parts_x) {
+            part = 0; new_row = true;
+            if (++j == G::kBoxRows) {
+                j = 0;
+                blk += a.scan_blk_stride; if (blk >= a.n_blocks) blk -= a.n_blocks;
+                if (++bt == a.n_blocks) { bt = 0; blk = 0; ++gz; new_chunk = true; }
             }
         }
     }
@@ -1602,18 +1644,14 @@ static cudaError_t launch_filtered_t(const RenderArgs& a, cudaStream_t s)
 {
     using G = ScanGeom<PX, PY, K>;
     static_assert(G::kSmem <= 48 * 1024, "the chunk and the queues must fit the default dynamic shared-memory limit");
-    const uint32_t n_cols = (a.cam.W + PX - 1) / PX;
-    dim3 grid((n_cols + a.scan_cols - 1) / a.scan_cols, a.n_blocks, a.scan_chunks);
-    lbuffer_filtered_kernel<PX, PY, K><<<grid, 128, scan_smem_bytes(G::kSmem, a.scan_max_ctas), s>>>(a);
+    lbuffer_filtered_kernel<PX, PY, K><<<a.scan_ctas, 128, scan_smem_bytes(G::kSmem, a.scan_max_ctas), s>>>(a);
     return cudaGetLastError();
 }
 
 template <int PX, int PY>
 static cudaError_t launch_candidates_t(const RenderArgs& a, cudaStream_t s)
 {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = a.sm_count ? (int)a.sm_count : 148;
     // grid-stride over the box list / the pixel list; when the host knows the list sizes of this launch geometry
     // (verified on its first render) the grids are sized to them: a share of a multi-GPU frame has short lists
     const unsigned full = (unsigned)sms * 32;
@@ -1662,7 +1700,8 @@ cudaError_t launch_filtered_candidates(const RenderArgs& a, cudaStream_t s)
 cudaError_t launch_lbuffer_filtered(const RenderArgs& a, cudaStream_t s)
 {
     if (a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0 || a.scan_chunks == 0) return cudaSuccess;
-    if (!a.hit_head || !a.hit_next || a.scan_cols == 0 || !a.cand || !a.cand_count || !a.pix || a.n_meshes > 32)
+    if (!a.hit_head || !a.hit_next || a.scan_cols == 0 || a.scan_parts_x == 0 || a.scan_ctas == 0 || !a.cand || !a.cand_count || !a.pix ||
+        a.n_meshes > 32)
         return cudaErrorInvalidValue;
 #define X(PX, PY, K) if (a.box_px == PX && a.box_py == PY && a.scan_k == K) return launch_filtered_t<PX, PY, K>(a, s);
     SRT_SCAN_SHAPES(X)

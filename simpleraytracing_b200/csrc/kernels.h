@@ -65,14 +65,19 @@ struct RenderArgs {
     // are sorted and exit - entry pairs summed; `L` receives 80 exp(-(mu0 d / 10)), `dist` the path length d, `hits` the count.
     int mode;
     // Filtered kernel.  A thread holds scan_k triangles and tests them against boxes of box_px x box_py pixels
-    // (FilterTri::R / R2 are packed for that box); a CTA covers the box rows of one 16-row block x scan_cols box columns
-    // x one chunk of 128 * scan_k triangles (grid.z = scan_chunks = the largest chunk count of a contributing mesh).
+    // (FilterTri::R / R2 are packed for that box); the unit of work is one box row of a 16-row block x scan_cols box
+    // columns x one chunk of 128 * scan_k triangles.
     // Accepted intersections are not accumulated in place (the reference's float sum is order dependent and the exact
     // tests of a warp run wherever a lane is free) but appended to the pixel's hit list {scene-wide triangle index,
     // value} -- value = sign * t (mode 0) or t (modes 1, 2) -- a linked list with an atomic head; resolve_hits_kernel
     // sorts each list by triangle index and replays lbuffer.cxx:788-809 (or the z-buffer update, main-omp.cxx:656-662) in the
     // reference's order.
     uint32_t box_px, box_py, scan_k, scan_cols, scan_chunks;
+    // the scan runs scan_ctas persistent CTAs over the units (chunk, block, box row, range of scan_cols box columns):
+    // scan_chunks = chunks of all contributing meshes together, scan_parts_x = column ranges per box row
+    uint32_t scan_parts_x, scan_ctas;
+    uint32_t scan_blk_stride;    // the t-th block a CTA visits within a chunk is block (t * scan_blk_stride) % n_blocks (coprime stride)
+    uint32_t sm_count;
     // survivors of the scan {box, triangle} (cand) and of the per-pixel strip tests {pixel, triangle} (pix).
     // cand_count[0] / [1] count them: zero when the scan starts; they may exceed the capacities (entries beyond are
     // dropped and resolve_hits_kernel recomputes every pixel with the exact sequence).

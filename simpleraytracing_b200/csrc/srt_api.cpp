@@ -116,6 +116,8 @@ struct srt_ctx {
     uint32_t* h_cand_count = nullptr;    // [0] box list, [1] pixel list
     uint64_t lists_key = 0;              // launch geometry whose list sizes have been verified (0 = none)
     uint32_t verified_cand = 0, verified_pix = 0;   // ... and those sizes (they never change for a scene / camera / geometry)
+    int sms = 148;                       // multiprocessors of the device (queried once)
+    uint64_t resident_key = ~0ull; int resident_val = 0;   // cached occupancy of the scan kernel for (shape, residency cap)
     int cnt_parity = 0;                  // which pair of the double-buffered list counters (d_cand_count[4]) is clean
     uint32_t scan_max_ctas = 0;          // cap on the scan's resident CTAs per SM (0 = none; srt_set_scan_residency)
     bool profiling = true;               // record the per-render timing events (srt_set_profiling)
@@ -448,30 +450,26 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     a.scan_cols = 0; a.scan_chunks = 0; a.hit_head = nullptr; a.hit_next = nullptr;
     uint32_t extra_launches = 0;
     if (kernel == SRT_KERNEL_FILTERED) {
-        // CTA = (one 16-row block) x (scan_cols box columns) x (one chunk of 128 K triangles).  The work of a CTA is
-        // uniform: a fixed prologue (chunk load: ~16 boxes' worth, measured) + its boxes, so the launch takes
-        // waves x (16 + boxes per CTA): the column range is the one that minimises that -- it avoids both a mostly empty
-        // last wave and many tiny CTAs.
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-        int resident = srt::filtered_resident_ctas(box_px, box_py, scan_k, c->scan_max_ctas);
-        if (resident <= 0) resident = SRT_RESIDENT_CTAS;
-        uint32_t chunks = 0;
-        for (size_t m = 0; m < c->n_meshes; ++m)
-            if (all || m == 0) chunks = std::max(chunks, c->meshes[m].n_chunks);
-        const uint32_t n_cols = (cam.width + box_px - 1) / box_px;
-        const uint64_t slots = (uint64_t)sms * (uint64_t)resident;
-        uint32_t cols = n_cols;
-        double best = 1e300;
-        for (uint32_t parts_x = 1; parts_x <= n_cols; ++parts_x) {
-            const uint32_t cw = (n_cols + parts_x - 1) / parts_x;
-            if (cw < 4 && parts_x > 1) break;
-            const uint64_t ctas = (uint64_t)((n_cols + cw - 1) / cw) * a.n_blocks * chunks;
-            const double cost = (double)((ctas + slots - 1) / slots) * (16.0 + (double)cw * (16 / box_py));
-            if (cost < best * 0.999) { best = cost; cols = cw; }
+        // The scan runs persistent CTAs -- as many as are resident at once -- over the units (chunk, 16-row block, box row,
+        // range of 32 box columns); every CTA takes an equal, contiguous share of the units (kernels.cu), so the launch has
+        // no partial last wave whatever the frame size, the share of a multi-GPU frame or the residency cap.
+        const int sms = c->sms;
+        const uint64_t rkey = ((uint64_t)box_px << 48) | ((uint64_t)box_py << 40) | ((uint64_t)scan_k << 32) | c->scan_max_ctas;
+        if (c->resident_key != rkey) {                                  // an occupancy query per frame costs microseconds
+            c->resident_val = srt::filtered_resident_ctas(box_px, box_py, scan_k, c->scan_max_ctas);
+            c->resident_key = rkey;
         }
+        int resident = c->resident_val;
+        if (resident <= 0) resident = SRT_RESIDENT_CTAS;
+        uint64_t chunks = 0;
+        for (size_t m = 0; m < c->n_meshes; ++m)
+            if ((all || m == 0) && c->meshes[m].n) chunks += c->meshes[m].n_chunks;
+        const uint32_t n_cols = (cam.width + box_px - 1) / box_px;
+        uint32_t cols = std::min<uint32_t>(32u, n_cols);
         if (c->force_scan_cols > 0) cols = std::min<uint32_t>((uint32_t)c->force_scan_cols, n_cols);
-        a.scan_cols = cols; a.scan_chunks = chunks;
+        a.scan_cols = cols; a.scan_parts_x = (n_cols + cols - 1) / cols; a.scan_chunks = (uint32_t)chunks;
+        const uint64_t units = chunks * a.n_blocks * (16 / box_py) * a.scan_parts_x;
+        a.scan_ctas = (uint32_t)std::min<uint64_t>((uint64_t)sms * (uint64_t)resident, std::max<uint64_t>(units, 1));
         // per-pixel hit lists: a 4-byte head per pixel of the launch's output index range (0xffffffff = empty; the
         // resolve pass leaves them empty again), nodes in the pix list below
         const size_t pixels = (size_t)(parts == 0 ? cam.height : a.n_blocks * 16) * cam.width;
@@ -491,7 +489,14 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         if (rc) return rc;
         a.cand = c->d_cand; a.pix = c->d_pix; a.hit_next = c->d_hit_next;
         a.cand_count = c->d_cand_count + 2 * c->cnt_parity; a.cand_count_next = c->d_cand_count + 2 * (c->cnt_parity ^ 1);
-        a.cand_cap = c->cand_cap; a.pix_cap = c->pix_cap; a.scan_max_ctas = c->scan_max_ctas;
+        a.cand_cap = c->cand_cap; a.pix_cap = c->pix_cap; a.scan_max_ctas = c->scan_max_ctas; a.sm_count = (uint32_t)sms;
+        // the blocks of a CTA's contiguous range of units are spread over the whole frame (kernels.cu): stride ~ 0.618 n, coprime to n
+        {
+            uint32_t st = std::max<uint32_t>(1u, (uint32_t)((double)a.n_blocks * 0.6180339887));
+            auto gcd = [](uint32_t x, uint32_t y) { while (y) { const uint32_t t = x % y; x = y; y = t; } return x; };
+            while (st > 1 && gcd(st, a.n_blocks) != 1) --st;
+            a.scan_blk_stride = a.n_blocks ? st : 1;
+        }
         if (c->force_cand_cap) a.cand_cap = std::min(a.cand_cap, c->force_cand_cap);
         if (c->force_pix_cap) a.pix_cap = std::min(a.pix_cap, c->force_pix_cap);
         if (c->n_meshes > 32 || c->total_tris >= (1ull << 27)) kernel = SRT_KERNEL_EXACT;     // candidate entries: 5-bit mesh, 27-bit triangle
@@ -600,6 +605,7 @@ int srt_create(srt_ctx** out, int device_id)
     srt_ctx* c = new (std::nothrow) srt_ctx();
     if (!c) return fail(nullptr, SRT_ERR_NOMEM, "out of host memory");
     c->device = device_id;
+    c->sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete c; return fail(nullptr, SRT_ERR_CUDA, "stream creation: %s", cudaGetErrorString(e));
     }

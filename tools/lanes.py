@@ -8,6 +8,7 @@ repair, i.e. the device work of a rank at N GPUs without the barrier).
 Output: one line per (share, lanes, scan residency cap); copy what matters into profiles/."""
 import os
 import sys
+import time
 from pathlib import Path
 
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
@@ -56,33 +57,36 @@ def main():
         for _ in range(2):
             batch(p, n_parts, lanes, max(nframes, 2 * lanes))
         torch.cuda.synchronize()
-        ms = []
+        ms, cpu = [], []
         for _ in range(reps):
             flush.fill_(1)
             a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
             a.record(main_s); batch(p, n_parts, lanes, nframes); b.record(main_s)
+            cpu.append((time.perf_counter() - t0) * 1e3)               # host time to enqueue the batch
             torch.cuda.synchronize()
             ms.append(a.elapsed_time(b))
-        return min(ms) / nframes, sorted(ms)[len(ms) // 2] / nframes
+        return min(ms) / nframes, sorted(ms)[len(ms) // 2] / nframes, min(cpu) / nframes
 
     for kern, kname in ((KERNEL_FILTERED, "filtered"), (KERNEL_AUTO, "auto")):
         p = lib.default_params(kernel=kern)
         base = {}
-        for n_parts in (1, 8, 4, 2):
+        for n_parts in (1, 8, 4):
             for cap in (0, 4):
                 for c in ctxs:
                     c.set_scan_residency(cap)
-                for lanes in (1, 2, 3, 4, 6):
+                for lanes in (1, 2, 4, 6):
                     if kern != KERNEL_FILTERED and cap:
                         continue
                     one = measure(p, n_parts, lanes, 1)[1] if lanes == 1 else None
-                    best, med = measure(p, n_parts, lanes, B)
+                    best, med, cpu = measure(p, n_parts, lanes, B)
                     if n_parts == 1 and lanes == 1 and cap == 0:
                         base[kname] = med
                     ideal = base.get(kname, med) / n_parts
                     print(f"{kname} {size}^2 share 1/{n_parts} lanes {lanes} scan cap {cap}: {med * 1e3:8.1f} us/frame (best {best * 1e3:8.1f})"
                           + (f" single frame {one * 1e3:8.1f}" if one is not None else "")
-                          + f" | vs 1-lane full frame / {n_parts}: {ideal / med:.3f}", flush=True)
+                          + f" | vs 1-lane full frame / {n_parts}: {ideal / med:.3f} | host enqueue {cpu * 1e3:.1f} us/frame", flush=True)
     for c in ctxs:
         c.close()
 
