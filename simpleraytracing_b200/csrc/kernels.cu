@@ -311,7 +311,10 @@ __device__ __forceinline__ uint2 cand_pack(uint32_t j, uint32_t block, uint32_t 
 
 template <int PX, int PY, int K>
 struct ScanGeom {
-    static_assert(16 % PY == 0 && PX * PY <= 64 && PX <= 32, "box rows tile a 16-row block; the per-entry pixel mask is 64 bits");
+    static_assert(16 % PY == 0 && PX <= 64, "box rows tile a 16-row block");
+    // boxes of more than 64 pixels are refined into 16 x 4 sub-boxes before the per-pixel stage (refine_kernel)
+    static constexpr bool kBig = PX * PY > 64;
+    static_assert(!kBig || (PX % 16 == 0 && PY % 4 == 0), "big boxes are whole 16 x 4 sub-boxes");
     static constexpr uint32_t kBoxRows = 16 / PY;
     static constexpr size_t kSmem = (size_t)K * 3 * 128 * sizeof(float4) + 16 + 4 * kStageCap * sizeof(uint2);
 };
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     // the list counters are double-buffered: this launch counts into cand_count, which the previous launch of the path
     // left at zero, and leaves cand_count_next at zero for the next one (no memset between frames)
-    if (tid == 0 && a.cand_count_next && blockIdx.x == 0) { a.cand_count_next[0] = 0; a.cand_count_next[1] = 0; }
+    if (tid < 4 && a.cand_count_next && blockIdx.x == 0) a.cand_count_next[tid] = 0;
     __syncthreads();
     uint32_t phase = 0, n1 = 0;              // n1: survivors staged by this warp (warp-uniform)
     const float x_first = 0.5f * (float)(PX - 1) + a.cam.xc;                                 // centre of box column 0
@@ -363,10 +366,12 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
     auto flush = [&]() {
         __syncwarp();
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(a.cand_count, n1);
+        uint2* const list = G::kBig ? a.big : a.cand;
+        const uint32_t cap = G::kBig ? a.big_cap : a.cand_cap;
+        if (lane == 0) base = atomicAdd(G::kBig ? a.big_count : a.cand_count, n1);
         base = __shfl_sync(0xffffffffu, base, 0);
         for (uint32_t e = lane; e < n1; e += 32)
-            if (base + e < a.cand_cap) a.cand[base + e] = stage[e];                         // overflow: resolve falls back to the exact sequence
+            if (base + e < cap) list[base + e] = stage[e];                                  // overflow: resolve falls back to the exact sequence
         __syncwarp();
         n1 = 0;
     };
@@ -473,6 +478,56 @@ __global__ void __launch_bounds__(128, SRT_MIN_CTAS) lbuffer_filtered_kernel(con
         }
     }
     if (n1) flush();
+}
+
+// ------------------------------------------------------------------ refine kernel (big-box shapes)
+// One {big box, triangle} survivor of the scan per thread (grid-stride): the three-strip box test (the triangle's
+// conservative footprint, DESIGN.md filter proof item 7) on each 16 x 4 sub-box of the big box; surviving
+// {sub-box, triangle} entries are appended to the box list of candidates_kernel<16, 4> (one atomic per warp and
+// sub-box position).  The scan's two-strip test on a big box lets ~10 x more area through than the triangle covers;
+// this stage cuts it back before the per-pixel tests.
+template <int PX, int PY>
+__global__ void __launch_bounds__(128) refine_kernel(const __grid_constant__ RenderArgs a)
+{
+    constexpr uint32_t SX = PX / 16, SY = PY / 4;                              // sub-boxes per big box
+    const uint32_t lane = threadIdx.x & 31u, W = a.cam.W;
+    const uint32_t n = min(*a.big_count, a.big_cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {      // warp-uniform trip count
+        const uint32_t e = base + lane;
+        const bool live = e < n;
+        uint32_t tm = 0, blk = 0, jb = 0, ib = 0, row0 = 0;
+        float4 fa = make_float4(0, 0, 0, 0), fb = fa, ga = fa, gb = fa;
+        if (live) {
+            const uint2 ent = a.big[e];
+            tm = ent.y;
+            const DevMesh* Mp = a.meshes + (tm >> 27);
+            const uint32_t tri = tm & 0x7ffffffu;
+            jb = ent.x & 15u; blk = (ent.x >> 4) & 0x3fffu; ib = ent.x >> 18;
+            row0 = a.row_begin + (blk * a.blk_stride + a.blk_phase) * 16 + jb * PY;
+            const float4* f0 = Mp->filt0 + 3 * (size_t)tri; const float4* f1 = Mp->filt1 + 2 * (size_t)tri;
+            fa = __ldg(f0); fb = __ldg(f0 + 1); ga = __ldg(f1); gb = __ldg(f1 + 1);
+        }
+#pragma unroll 1
+        for (uint32_t sy = 0; sy < SY; ++sy) {
+#pragma unroll 1
+            for (uint32_t sx = 0; sx < SX; ++sx) {
+                const uint32_t r0 = row0 + sy * 4, c0 = (ib * SX + sx) * 16;
+                bool keep = false;
+                if (live && r0 < a.row_end && c0 < W) {
+                    const uint32_t c1 = min(W, c0 + 16) - 1, r1 = min(a.row_end, r0 + 4) - 1;     // clamped to the frame
+                    keep = box_may_hit(fa, fb, ga, gb, 0.5f * (float)(c0 + c1) + a.cam.xc, 0.5f * (float)(r0 + r1) + a.cam.yc,
+                                       0.5f * (float)(c1 - c0), 0.5f * (float)(r1 - r0));
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (bal == 0) continue;
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(a.cand_count, (uint32_t)__popc(bal));
+                at = __shfl_sync(0xffffffffu, at, 0) + __popc(bal & ((1u << lane) - 1u));
+                if (keep && at < a.cand_cap) a.cand[at] = cand_pack(jb * SY + sy, blk, ib * SX + sx, tm & 0x7ffffffu, tm >> 27);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------ candidates kernel
@@ -670,7 +725,7 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
     float dist0 = 0.0f; int ssum0 = 0; uint32_t hits0 = 0;   // mode 1: z-buffer value / triangle index
     if (a.mode == 1) { dist0 = INFINITY; ssum0 = -1; }
     // a candidate list overflowed: no hit list can be trusted, every pixel is recomputed below
-    const bool overflow = a.cand_count[0] > a.cand_cap || a.cand_count[1] > a.pix_cap;
+    const bool overflow = a.cand_count[0] > a.cand_cap || a.cand_count[1] > a.pix_cap || (a.big_count && *a.big_count > a.big_cap);
     if (valid) {
         const uint32_t head = a.hit_head[p];
         if (head != kNoHit) a.hit_head[p] = kNoHit;         // ready for the next render
@@ -1626,7 +1681,8 @@ cudaError_t launch_lbuffer_exact(const RenderArgs& a, int audit, cudaStream_t s)
 }
 
 // shapes the filtered kernel is built for: {box width, box height, triangles per thread}
-#define SRT_SCAN_SHAPES(X) X(16, 2, 4) X(16, 1, 4) X(32, 1, 4) X(8, 4, 4) X(8, 1, 4) X(32, 2, 4) X(16, 4, 4) X(8, 8, 4) X(16, 2, 2) X(16, 2, 6) X(32, 2, 6)
+#define SRT_SCAN_SHAPES(X) X(16, 2, 4) X(16, 1, 4) X(32, 1, 4) X(8, 4, 4) X(8, 1, 4) X(32, 2, 4) X(16, 4, 4) X(8, 8, 4) X(16, 2, 2) X(16, 2, 6) X(32, 2, 6) \
+    X(32, 4, 4) X(32, 8, 4) X(32, 16, 4) X(64, 8, 4) X(64, 16, 4) X(16, 16, 4)
 
 // Dynamic shared memory of a scan CTA.  scan_max_ctas (0 = no cap) caps the CTAs resident per SM by padding the
 // request: with frames pipelined on several streams, a scan that leaves a quarter of the register file free lets the
@@ -1657,9 +1713,17 @@ static cudaError_t launch_candidates_t(const RenderArgs& a, cudaStream_t s)
     const unsigned full = (unsigned)sms * 32;
     const unsigned g1 = a.cand_hint ? std::min(full, (a.cand_hint + 127) / 128 + 1) : full;
     const unsigned g2 = a.pix_hint ? std::min(full, (a.pix_hint + 127) / 128 + 1) : full;
-    candidates_kernel<PX, PY><<<g1, 128, 0, s>>>(a);
-    const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
+    if constexpr (ScanGeom<PX, PY, 4>::kBig) {
+        if (!a.big || !a.big_count) return cudaErrorInvalidValue;
+        const unsigned g0 = a.big_hint ? std::min(full, (a.big_hint + 127) / 128 + 1) : full;
+        refine_kernel<PX, PY><<<g0, 128, 0, s>>>(a);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        candidates_kernel<16, 4><<<g1, 128, 0, s>>>(a);
+    } else {
+        candidates_kernel<PX, PY><<<g1, 128, 0, s>>>(a);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     exact_tests_kernel<<<g2, 128, 0, s>>>(a);
     return cudaGetLastError();
 }

@@ -82,7 +82,11 @@ struct RenderArgs {
     // cand_count[0] / [1] count them: zero when the scan starts; they may exceed the capacities (entries beyond are
     // dropped and resolve_hits_kernel recomputes every pixel with the exact sequence).
     uint2* cand; uint2* pix; uint32_t* cand_count; uint32_t cand_cap, pix_cap;
-    uint32_t* cand_count_next;   // the other pair of the double-buffered counters: the scan leaves it at zero for the next launch (may be null)
+    // Big-box shapes (box_px * box_py > 64 pixels): the scan's survivors {big box, triangle} go to `big` (counted in
+    // *big_count); refine_kernel tests the 16 x 4 sub-boxes of every entry with the three-strip box test and appends the
+    // surviving {sub-box, triangle} to `cand`, which candidates_kernel<16, 4> consumes as for the small shapes.
+    uint2* big; uint32_t* big_count; uint32_t big_cap, big_hint;
+    uint32_t* cand_count_next;   // the other set of the double-buffered counters (4 words: cand, pix, big, -): the scan leaves it at zero for the next launch (may be null)
     uint32_t cand_hint, pix_hint;   // list sizes of this launch geometry when the host has verified them (0 = unknown): grid sizing only
     uint32_t scan_max_ctas;      // cap on the scan's resident CTAs per SM (0 = none), see scan_smem_bytes
     uint32_t* hit_head;      // [pixel]: the pixel's hit list (index into pix / hit_next; 0xffffffff = empty, also between renders)

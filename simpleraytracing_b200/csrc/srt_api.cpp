@@ -113,9 +113,10 @@ struct srt_ctx {
     // candidate list of the filtered kernel: survivors of the scan.  h_cand_count (pinned) receives the count of every
     // render asynchronously; a later render grows the list when the last known count came close to the capacity.
     uint2* d_cand = nullptr; uint2* d_pix = nullptr; uint32_t* d_cand_count = nullptr; uint32_t cand_cap = 0, pix_cap = 0;
-    uint32_t* h_cand_count = nullptr;    // [0] box list, [1] pixel list
+    uint2* d_big = nullptr; uint32_t big_cap = 0;       // big-box shapes: survivors of the scan, refined into d_cand
+    uint32_t* h_cand_count = nullptr;    // [0] box list, [1] pixel list, [2] big-box list
     uint64_t lists_key = 0;              // launch geometry whose list sizes have been verified (0 = none)
-    uint32_t verified_cand = 0, verified_pix = 0;   // ... and those sizes (they never change for a scene / camera / geometry)
+    uint32_t verified_cand = 0, verified_pix = 0, verified_big = 0;   // ... and those sizes (they never change for a scene / camera / geometry)
     int sms = 148;                       // multiprocessors of the device (queried once)
     uint64_t resident_key = ~0ull; int resident_val = 0;   // cached occupancy of the scan kernel for (shape, residency cap)
     int cnt_parity = 0;                  // which pair of the double-buffered list counters (d_cand_count[4]) is clean
@@ -184,8 +185,9 @@ void free_frame(srt_ctx* c)
     c->d_L = c->d_img = c->d_dist = nullptr; c->d_ssum = nullptr; c->d_hits = nullptr; c->frame_cap = 0;
     cudaFree(c->d_hit_head); cudaFree(c->d_hit_next);
     c->d_hit_head = nullptr; c->d_hit_next = nullptr; c->hit_pixels_cap = 0;
-    cudaFree(c->d_cand); cudaFree(c->d_pix); cudaFree(c->d_cand_count); if (c->h_cand_count) cudaFreeHost(c->h_cand_count);
-    c->d_cand = nullptr; c->d_pix = nullptr; c->d_cand_count = nullptr; c->h_cand_count = nullptr; c->cand_cap = 0; c->pix_cap = 0;
+    cudaFree(c->d_cand); cudaFree(c->d_pix); cudaFree(c->d_big); cudaFree(c->d_cand_count); if (c->h_cand_count) cudaFreeHost(c->h_cand_count);
+    c->d_cand = nullptr; c->d_pix = nullptr; c->d_big = nullptr; c->d_cand_count = nullptr; c->h_cand_count = nullptr;
+    c->cand_cap = 0; c->pix_cap = 0; c->big_cap = 0;
     cudaFree(c->d_bin_entries); cudaFree(c->d_bin_counts);
     c->d_bin_entries = nullptr; c->d_bin_counts = nullptr; c->bin_entries_cap = 0; c->bin_counts_cap = 0;
 }
@@ -225,17 +227,23 @@ int ensure_mesh(srt_ctx* c, MeshBuf& m, size_t n, bool want_normals)
 }
 
 // Work lists of the filtered path: at least `cand` {box, triangle} and `pix` {pixel, triangle} entries (only ever grows).
-int ensure_lists(srt_ctx* c, uint64_t cand, uint64_t pix)
+int ensure_lists(srt_ctx* c, uint64_t cand, uint64_t pix, uint64_t big = 0)
 {
-    cand = std::min<uint64_t>(cand, 0xffffffffull); pix = std::min<uint64_t>(pix, 0xffffffffull);
+    cand = std::min<uint64_t>(cand, 0xffffffffull); pix = std::min<uint64_t>(pix, 0xffffffffull); big = std::min<uint64_t>(big, 0xffffffffull);
     if (!c->h_cand_count) {
-        SRT_CUDA(c, cudaHostAlloc(&c->h_cand_count, 2 * sizeof(uint32_t), cudaHostAllocDefault));
-        c->h_cand_count[0] = c->h_cand_count[1] = 0;
+        SRT_CUDA(c, cudaHostAlloc(&c->h_cand_count, 4 * sizeof(uint32_t), cudaHostAllocDefault));
+        c->h_cand_count[0] = c->h_cand_count[1] = c->h_cand_count[2] = c->h_cand_count[3] = 0;
     }
-    if (!c->d_cand_count) {
-        SRT_CUDA(c, cudaMalloc(&c->d_cand_count, 4 * sizeof(uint32_t)));
-        SRT_CUDA(c, cudaMemsetAsync(c->d_cand_count, 0, 4 * sizeof(uint32_t), c->stream));
+    if (!c->d_cand_count) {                                    // two sets of {cand, pix, big, -}
+        SRT_CUDA(c, cudaMalloc(&c->d_cand_count, 8 * sizeof(uint32_t)));
+        SRT_CUDA(c, cudaMemsetAsync(c->d_cand_count, 0, 8 * sizeof(uint32_t), c->stream));
         c->cnt_parity = 0;
+    }
+    if (big > c->big_cap) {
+        SRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_big); c->d_big = nullptr; c->big_cap = 0;
+        SRT_CUDA(c, cudaMalloc(&c->d_big, big * sizeof(uint2)));
+        c->big_cap = (uint32_t)big;
     }
     if (cand > c->cand_cap) {
         SRT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -448,6 +456,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
     }
 
     a.scan_cols = 0; a.scan_chunks = 0; a.hit_head = nullptr; a.hit_next = nullptr;
+    const bool big_boxes = box_px * box_py > 64;            // filtered path: the scan's survivors are refined into 16 x 4 sub-boxes
     uint32_t extra_launches = 0;
     if (kernel == SRT_KERNEL_FILTERED) {
         // The scan runs persistent CTAs -- as many as are resident at once -- over the units (chunk, 16-row block, box row,
@@ -465,7 +474,10 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         for (size_t m = 0; m < c->n_meshes; ++m)
             if ((all || m == 0) && c->meshes[m].n) chunks += c->meshes[m].n_chunks;
         const uint32_t n_cols = (cam.width + box_px - 1) / box_px;
+        // unit width: 32 box columns, narrower when the launch is small (big boxes, a share of a multi-GPU frame, a small
+        // frame) so that every CTA still gets a dozen units to balance
         uint32_t cols = std::min<uint32_t>(32u, n_cols);
+        while (cols > 4 && chunks * a.n_blocks * (16 / box_py) * ((n_cols + cols - 1) / cols) < 12ull * (uint64_t)sms * (uint64_t)resident) cols /= 2;
         if (c->force_scan_cols > 0) cols = std::min<uint32_t>((uint32_t)c->force_scan_cols, n_cols);
         a.scan_cols = cols; a.scan_parts_x = (n_cols + cols - 1) / cols; a.scan_chunks = (uint32_t)chunks;
         const uint64_t units = chunks * a.n_blocks * (16 / box_py) * a.scan_parts_x;
@@ -485,10 +497,12 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         // survivor of the per-pixel strip tests {pixel, triangle} (~ the hits).  First sized from the scene; the first
         // render of a launch geometry then CHECKS the counts (one synchronisation, below) and grows the lists to twice
         // what that frame needed -- the counts of a scene / camera / launch geometry never change afterwards.
-        rc = ensure_lists(c, std::max<uint64_t>(4ull << 20, 32ull * c->total_tris), std::max<uint64_t>(16ull << 20, 64ull * c->total_tris));
+        rc = ensure_lists(c, std::max<uint64_t>(4ull << 20, 32ull * c->total_tris), std::max<uint64_t>(16ull << 20, 64ull * c->total_tris),
+                          big_boxes ? std::max<uint64_t>(2ull << 20, 16ull * c->total_tris) : 0);
         if (rc) return rc;
         a.cand = c->d_cand; a.pix = c->d_pix; a.hit_next = c->d_hit_next;
-        a.cand_count = c->d_cand_count + 2 * c->cnt_parity; a.cand_count_next = c->d_cand_count + 2 * (c->cnt_parity ^ 1);
+        a.cand_count = c->d_cand_count + 4 * c->cnt_parity; a.cand_count_next = c->d_cand_count + 4 * (c->cnt_parity ^ 1);
+        if (big_boxes) { a.big = c->d_big; a.big_count = a.cand_count + 2; a.big_cap = c->big_cap; }
         a.cand_cap = c->cand_cap; a.pix_cap = c->pix_cap; a.scan_max_ctas = c->scan_max_ctas; a.sm_count = (uint32_t)sms;
         // the blocks of a CTA's contiguous range of units are spread over the whole frame (kernels.cu): stride ~ 0.618 n, coprime to n
         {
@@ -497,7 +511,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
             while (st > 1 && gcd(st, a.n_blocks) != 1) --st;
             a.scan_blk_stride = a.n_blocks ? st : 1;
         }
-        if (c->force_cand_cap) a.cand_cap = std::min(a.cand_cap, c->force_cand_cap);
+        if (c->force_cand_cap) { a.cand_cap = std::min(a.cand_cap, c->force_cand_cap); a.big_cap = std::min(a.big_cap, c->force_cand_cap); }
         if (c->force_pix_cap) a.pix_cap = std::min(a.pix_cap, c->force_pix_cap);
         if (c->n_meshes > 32 || c->total_tris >= (1ull << 27)) kernel = SRT_KERNEL_EXACT;     // candidate entries: 5-bit mesh, 27-bit triangle
     }
@@ -511,11 +525,11 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         const bool verify = !forced && (repack || c->lists_key != key);
         // does launch_lbuffer_filtered launch anything?  (an empty launch touches no counter: the pairs keep their roles)
         const bool launches = !(a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0 || a.scan_chunks == 0);
-        if (!verify && !forced) { a.cand_hint = c->verified_cand; a.pix_hint = c->verified_pix; }
+        if (!verify && !forced) { a.cand_hint = c->verified_cand; a.pix_hint = c->verified_pix; a.big_hint = c->verified_big; }
         for (int attempt = 0;; ++attempt) {
             // the pair of counters this launch counts into was left at zero by the previous scan (or at allocation);
             // a repeated attempt counts into the same pair again and clears it first
-            if (attempt > 0) SRT_CUDA(c, cudaMemsetAsync(a.cand_count, 0, 2 * sizeof(uint32_t), c->stream));
+            if (attempt > 0) SRT_CUDA(c, cudaMemsetAsync(a.cand_count, 0, 4 * sizeof(uint32_t), c->stream));
             if (prof) SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
             SRT_CUDA(c, srt::launch_lbuffer_filtered(a, c->stream));
             if (prof) SRT_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
@@ -523,17 +537,21 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
             if (!verify) break;
             // First render of this launch geometry: wait for the counts.  A list that overflowed would make the resolve pass
             // recompute every pixel with the exact sequence (correct, but hours on a large scene): grow and redo instead.
-            SRT_CUDA(c, cudaMemcpyAsync(c->h_cand_count, a.cand_count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            SRT_CUDA(c, cudaMemcpyAsync(c->h_cand_count, a.cand_count, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             SRT_CUDA(c, cudaStreamSynchronize(c->stream));
             const uint64_t n_cand = launches ? c->h_cand_count[0] : 0, n_pix = launches ? c->h_cand_count[1] : 0;
-            if (n_cand <= a.cand_cap && n_pix <= a.pix_cap) {
+            const uint64_t n_big = (launches && big_boxes) ? c->h_cand_count[2] : 0;
+            if (n_cand <= a.cand_cap && n_pix <= a.pix_cap && n_big <= a.big_cap) {
                 c->lists_key = key;
                 c->verified_cand = (uint32_t)std::max<uint64_t>(n_cand, 1); c->verified_pix = (uint32_t)std::max<uint64_t>(n_pix, 1);
+                c->verified_big = (uint32_t)std::max<uint64_t>(n_big, 1);
                 break;
             }
             if (attempt >= 4) break;                                   // give up growing: the resolve pass stays exact
-            // the pixel count of a truncated box list is a lower bound: grow it generously, the next attempt measures it
-            rc = ensure_lists(c, 2 * n_cand, std::max<uint64_t>(2 * n_pix, n_cand <= a.cand_cap ? 0 : 4 * n_pix));
+            // the counts behind a truncated list are lower bounds: grow generously, the next attempt measures them
+            const bool cut = n_big > a.big_cap;
+            rc = ensure_lists(c, cut ? std::max<uint64_t>(4 * n_cand, 2 * n_big) : 2 * n_cand,
+                              std::max<uint64_t>(2 * n_pix, (n_cand <= a.cand_cap && !cut) ? 0 : 4 * n_pix), big_boxes ? 2 * n_big : 0);
             if (rc) return rc;
             // the exact-test stage has appended hits to the pixels' lists: empty them again before the next attempt
             {
@@ -541,9 +559,10 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
                 SRT_CUDA(c, cudaMemsetAsync(c->d_hit_head, 0xff, px * sizeof(uint32_t), c->stream));
             }
             a.cand = c->d_cand; a.pix = c->d_pix; a.hit_next = c->d_hit_next; a.cand_cap = c->cand_cap; a.pix_cap = c->pix_cap;
+            if (big_boxes) { a.big = c->d_big; a.big_cap = c->big_cap; }
         }
         if (launches) c->cnt_parity ^= 1;                              // the scan has cleared the other pair
-        SRT_CUDA(c, srt::launch_resolve_hits(a, c->stream)); extra_launches = 3;          // + candidates, exact tests
+        SRT_CUDA(c, srt::launch_resolve_hits(a, c->stream)); extra_launches = big_boxes ? 4 : 3;   // + (refine,) candidates, exact tests
     } else if (kernel == SRT_KERNEL_CULLED) {
         SRT_CUDA(c, srt::launch_lbuffer_bins(a, c->stream)); extra_launches = 1;
         if (prof) SRT_CUDA(c, cudaEventRecord(c->ev[4], c->stream));

@@ -3,7 +3,7 @@
 each), for the whole frame and for ONE block-cyclic share of an N-GPU frame (no peers: the share's kernels + a full-frame
 repair, i.e. the device work of a rank at N GPUs without the barrier).
 
-  python tools/lanes.py [size] [frames per batch]
+  python tools/lanes.py [size] [frames per batch] [shape PXxPYxK ...]
 
 Output: one line per (share, lanes, scan residency cap); copy what matters into profiles/."""
 import os
@@ -17,6 +17,7 @@ import torch  # noqa: E402
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from simpleraytracing_b200 import Context, Library, scene, KERNEL_FILTERED, KERNEL_AUTO  # noqa: E402
+from simpleraytracing_b200.capi import box_shape  # noqa: E402
 
 
 def main():
@@ -69,10 +70,12 @@ def main():
             ms.append(a.elapsed_time(b))
         return min(ms) / nframes, sorted(ms)[len(ms) // 2] / nframes, min(cpu) / nframes
 
-    for kern, kname in ((KERNEL_FILTERED, "filtered"), (KERNEL_AUTO, "auto")):
-        p = lib.default_params(kernel=kern)
+    shapes = [tuple(int(v) for v in a.split("x")) for a in sys.argv[3:]] or [(0, 0, 0)]
+    runs = [(KERNEL_FILTERED, f"filtered {sh[0]}x{sh[1]}x{sh[2]}" if sh[0] else "filtered default", sh) for sh in shapes] + [(KERNEL_AUTO, "auto", (0, 0, 0))]
+    for kern, kname, sh in runs:
+        p = lib.default_params(kernel=kern, pixels_per_thread=box_shape(*sh) if sh[0] else 0)
         base = {}
-        for n_parts in (1, 8, 4):
+        for n_parts in (1, 8):
             for cap in (0, 4):
                 for c in ctxs:
                     c.set_scan_residency(cap)

@@ -19,7 +19,7 @@ sys.path.insert(0, str(ROOT))
 from simpleraytracing_b200 import Context, Library, scene, KERNEL_FILTERED, KERNEL_CULLED, KERNEL_EXACT  # noqa: E402
 from simpleraytracing_b200.capi import box_shape  # noqa: E402
 
-SHAPES = [(16, 2, 4), (16, 1, 4), (32, 1, 4), (8, 4, 4), (8, 1, 4), (32, 2, 4), (16, 4, 4), (8, 8, 4), (16, 2, 2), (16, 2, 6), (32, 2, 6)]
+SHAPES = [(16, 2, 4), (32, 2, 4), (16, 4, 4), (8, 8, 4), (32, 4, 4), (32, 8, 4), (16, 16, 4), (32, 16, 4), (64, 8, 4), (64, 16, 4)]
 
 
 def parse_shape(s):
