@@ -490,6 +490,7 @@ template <int PX, int PY>
 __global__ void __launch_bounds__(128) refine_kernel(const __grid_constant__ RenderArgs a)
 {
     constexpr uint32_t SX = PX / 16, SY = PY / 4;                              // sub-boxes per big box
+    static_assert(SX * SY <= 32, "one bit per sub-box");
     const uint32_t lane = threadIdx.x & 31u, W = a.cam.W;
     const uint32_t n = min(*a.big_count, a.big_cap);
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -508,24 +509,38 @@ __global__ void __launch_bounds__(128) refine_kernel(const __grid_constant__ Ren
             const float4* f0 = Mp->filt0 + 3 * (size_t)tri; const float4* f1 = Mp->filt1 + 2 * (size_t)tri;
             fa = __ldg(f0); fb = __ldg(f0 + 1); ga = __ldg(f1); gb = __ldg(f1 + 1);
         }
-#pragma unroll 1
-        for (uint32_t sy = 0; sy < SY; ++sy) {
-#pragma unroll 1
-            for (uint32_t sx = 0; sx < SX; ++sx) {
-                const uint32_t r0 = row0 + sy * 4, c0 = (ib * SX + sx) * 16;
-                bool keep = false;
-                if (live && r0 < a.row_end && c0 < W) {
-                    const uint32_t c1 = min(W, c0 + 16) - 1, r1 = min(a.row_end, r0 + 4) - 1;     // clamped to the frame
-                    keep = box_may_hit(fa, fb, ga, gb, 0.5f * (float)(c0 + c1) + a.cam.xc, 0.5f * (float)(r0 + r1) + a.cam.yc,
-                                       0.5f * (float)(c1 - c0), 0.5f * (float)(r1 - r0));
+        // which sub-boxes may the triangle touch?  (no atomics in this loop: one per warp below)
+        uint32_t mask = 0;
+        if (live) {
+#pragma unroll
+            for (uint32_t sy = 0; sy < SY; ++sy) {
+#pragma unroll
+                for (uint32_t sx = 0; sx < SX; ++sx) {
+                    const uint32_t r0 = row0 + sy * 4, c0 = (ib * SX + sx) * 16;
+                    if (r0 < a.row_end && c0 < W) {
+                        const uint32_t c1 = min(W, c0 + 16) - 1, r1 = min(a.row_end, r0 + 4) - 1;     // clamped to the frame
+                        if (box_may_hit(fa, fb, ga, gb, 0.5f * (float)(c0 + c1) + a.cam.xc, 0.5f * (float)(r0 + r1) + a.cam.yc,
+                                        0.5f * (float)(c1 - c0), 0.5f * (float)(r1 - r0)))
+                            mask |= 1u << (sy * SX + sx);
+                    }
                 }
-                const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (bal == 0) continue;
-                uint32_t at = 0;
-                if (lane == 0) at = atomicAdd(a.cand_count, (uint32_t)__popc(bal));
-                at = __shfl_sync(0xffffffffu, at, 0) + __popc(bal & ((1u << lane) - 1u));
-                if (keep && at < a.cand_cap) a.cand[at] = cand_pack(jb * SY + sy, blk, ib * SX + sx, tm & 0x7ffffffu, tm >> 27);
             }
+        }
+        // append the warp's sub-boxes: one atomic, each lane writes its own
+        const uint32_t mine = (uint32_t)__popc(mask);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += u; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        uint32_t at = 0;
+        if (lane == 31) at = atomicAdd(a.cand_count, total);
+        at = __shfl_sync(0xffffffffu, at, 31) + incl - mine;
+        while (mask) {
+            const uint32_t k = (uint32_t)__ffs((int)mask) - 1;
+            mask &= mask - 1;
+            if (at < a.cand_cap) a.cand[at] = cand_pack(jb * SY + k / SX, blk, ib * SX + k % SX, tm & 0x7ffffffu, tm >> 27);
+            ++at;
         }
     }
 }

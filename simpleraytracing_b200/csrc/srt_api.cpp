@@ -31,10 +31,10 @@
 #define SRT_RESIDENT_CTAS 4      // CTAs of the filtered kernel resident per SM if the occupancy query fails
 #endif
 #ifndef SRT_BOX_PX
-#define SRT_BOX_PX 16            // default box of the filtered kernel: SRT_BOX_PX x SRT_BOX_PY pixels, SRT_BOX_NB boxes per thread
+#define SRT_BOX_PX 64            // default box of the filtered kernel: SRT_BOX_PX x SRT_BOX_PY pixels, SRT_BOX_NB boxes per thread
 #endif
 #ifndef SRT_BOX_PY
-#define SRT_BOX_PY 4
+#define SRT_BOX_PY 16
 #endif
 #ifndef SRT_SCAN_K
 #define SRT_SCAN_K 4             // triangles a thread of the filtered kernel holds in registers
@@ -477,7 +477,18 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         // unit width: 32 box columns, narrower when the launch is small (big boxes, a share of a multi-GPU frame, a small
         // frame) so that every CTA still gets a dozen units to balance
         uint32_t cols = std::min<uint32_t>(32u, n_cols);
-        while (cols > 4 && chunks * a.n_blocks * (16 / box_py) * ((n_cols + cols - 1) / cols) < 12ull * (uint64_t)sms * (uint64_t)resident) cols /= 2;
+        {
+            // cost of the launch = units of the busiest CTA x (boxes of a unit + the unit's fixed overhead, ~3 boxes' worth)
+            const uint64_t slots = (uint64_t)sms * (uint64_t)resident;
+            double best = 1e300;
+            for (uint32_t cw = 64; cw >= 4; cw /= 2) {
+                if (cw > n_cols && cw != 4) continue;
+                const uint32_t w = std::min(cw, n_cols);
+                const uint64_t u = chunks * a.n_blocks * (16 / box_py) * ((n_cols + w - 1) / w);
+                const double cost = (double)((u + slots - 1) / slots) * ((double)w + 3.0);
+                if (cost < best * 0.995) { best = cost; cols = w; }
+            }
+        }
         if (c->force_scan_cols > 0) cols = std::min<uint32_t>((uint32_t)c->force_scan_cols, n_cols);
         a.scan_cols = cols; a.scan_parts_x = (n_cols + cols - 1) / cols; a.scan_chunks = (uint32_t)chunks;
         const uint64_t units = chunks * a.n_blocks * (16 / box_py) * a.scan_parts_x;
