@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 // If a candidate list overflows (adversarial scenes; the host grows it for the next frame), resolve recomputes every
 // pixel with the exact sequence: slow, never wrong.
 constexpr uint32_t kStageCap = 256, kStageFlush = 128;
+constexpr uint32_t kNoHit = 0xffffffffu;       // empty list head / end of a pixel's hit list
 
 // candidate entry: x = box row j (4 bits) | 16-row block of the launch (14) | box column i (14), y = triangle (27) | mesh (5)
 __device__ __forceinline__ uint2 cand_pack(uint32_t j, uint32_t block, uint32_t i, uint32_t tri, uint32_t mesh)
@@ -701,7 +702,6 @@ __device__ __forceinline__ float expf_glibc(float x)
     return (float)y;
 }
 
-constexpr uint32_t kNoHit = 0xffffffffu;       // empty list head / end of a pixel's hit list
 constexpr uint32_t kLocalHits = 32;            // hits of one pixel the resolve pass sorts in a local array
 constexpr uint32_t kSortOverflowCap = 256;     // sort mode: intersections of one ray the overflow path can order
 
@@ -726,6 +726,143 @@ __device__ float sorted_xray_value(float* t, uint32_t n, float incident, float m
     return __fmul_rn(incident, expf_glibc(-__fmul_rn(mu, distance)));                                  // :739
 }
 
+// One pixel's outputs from its hit list (head = first node, kNoHit = empty): L (modes 0, 2), path length / z value,
+// sign sum / triangle index, hit count.
+struct PixelOut { float L, dist; int ssum; uint32_t hits; };
+
+__device__ __forceinline__ PixelOut resolve_list(const RenderArgs& a, uint32_t head)
+{
+    float L = a.incident;
+    float dist0 = 0.0f; int ssum0 = 0; uint32_t hits0 = 0;   // mode 1: z-buffer value / triangle index
+    if (a.mode == 1) {
+        // closest hit: strict `z > t` in ascending triangle order == smallest t, lowest triangle index among equals
+        dist0 = INFINITY; ssum0 = -1;
+        for (uint32_t i = head; i != kNoHit; i = a.hit_next[i]) {
+            const uint2 e = a.pix[i];
+            const float t = __uint_as_float(e.y);
+            if (dist0 > t || (dist0 == t && (int)e.x < ssum0)) { dist0 = t; ssum0 = (int)e.x; }
+        }
+        return { L, dist0, ssum0, hits0 };
+    }
+    // The pixel's hits in the reference's order: ascending triangle index (mode 0: the float sum is order
+    // dependent) resp. ascending t (mode 2).
+    // Fast path, lists of up to 8 hits (nearly all): the nodes are sorted in REGISTERS by an unrolled insertion
+    // network -- no indexed local array, which costs a local-memory round trip per access.
+    {
+        uint2 r[8];
+        uint32_t n8 = 0, i = head;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            if (i != kNoHit) {
+                r[s] = a.pix[i]; i = a.hit_next[i]; n8 = s + 1;
+#pragma unroll
+                for (int j = s; j > 0; --j) {
+                    const bool sw = (a.mode == 2 ? r[j - 1].y : r[j - 1].x) > (a.mode == 2 ? r[j].y : r[j].x);
+                    const uint2 lo = sw ? r[j] : r[j - 1], hi = sw ? r[j - 1] : r[j];
+                    r[j - 1] = lo; r[j] = hi;
+                }
+            }
+        }
+        if (i == kNoHit && n8 > 0) {
+            if (a.mode == 2) {
+                // main.cxx:700-741 (sorted_xray_value): pairs (t[i], t[i + 1]) in ascending order
+                float distance = 0.0f;
+                if ((n8 & 1u) == 0) {
+#pragma unroll
+                    for (int s = 0; s < 8; s += 2)
+                        if ((uint32_t)s < n8) distance = __fadd_rn(distance, __fsub_rn(__uint_as_float(r[s + 1].y), __uint_as_float(r[s].y)));
+                }
+                dist0 = distance;
+                distance = (float)((double)distance * a.length_to_cm);
+                L = __fmul_rn(a.incident, expf_glibc(-__fmul_rn(a.meshes[0].mu, distance)));
+                return { L, dist0, 0, n8 };
+            }
+            for (int m = 0; m < a.n_meshes; ++m) {
+                const DevMesh M = a.meshes[m];
+                float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
+                if (M.contributes) {
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {                    // ascending triangle order; mesh ranges ascend with m
+                        if ((uint32_t)s < n8 && r[s].x >= M.first && r[s].x < M.first + M.n) {
+                            const float st = __uint_as_float(r[s].y);
+                            dist = __fadd_rn(dist, st);              // distance += sign * t
+                            ssum += (0.0f < st) - (st < 0.0f);
+                            ++hits;
+                        }
+                    }
+                }
+                L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
+                if (m == 0) { dist0 = dist; ssum0 = ssum; hits0 = hits; }
+            }
+            return { L, dist0, ssum0, hits0 };
+        }
+    }
+    // Longer lists: up to kLocalHits entries are insertion-sorted into a local array while the chain is walked; beyond
+    // that (rays grazing a bumpy silhouette) they are replayed by selection -- one walk of the chain per entry, no
+    // storage -- which is slow but rare and exact.
+    uint2 e[kLocalHits];
+    uint32_t n = 0;
+    for (uint32_t i = head; i != kNoHit; i = a.hit_next[i], ++n) {
+        if (n >= kLocalHits) continue;
+        const uint2 key = a.pix[i];
+        const uint32_t kk = a.mode == 2 ? key.y : key.x;            // positive floats order like their bits
+        uint32_t j = n;
+        while (j > 0 && (a.mode == 2 ? e[j - 1].y : e[j - 1].x) > kk) { e[j] = e[j - 1]; --j; }
+        e[j] = key;
+    }
+    // visit entry number `i` (0-based, in order): from the array, or by selection over the chain
+    unsigned long long last = 0;                                    // long lists: (key, node) + 1 of the last visited entry
+    auto entry = [&](uint32_t i) -> uint2 {
+        if (n <= kLocalHits) return e[i];
+        unsigned long long best = ~0ull; uint2 bv = make_uint2(0, 0);
+        for (uint32_t c = head; c != kNoHit; c = a.hit_next[c]) {
+            const uint2 v = a.pix[c];
+            const unsigned long long k = (((unsigned long long)(a.mode == 2 ? v.y : v.x)) << 32 | c) + 1;
+            if (k > last && k < best) { best = k; bv = v; }
+        }
+        last = best;
+        return bv;
+    };
+    if (a.mode == 2) {
+        // main.cxx:700-741 (sorted_xray_value), streamed: pairs (t[i], t[i + 1]) in ascending order
+        float distance = 0.0f;
+        if (n > 0 && (n & 1u) == 0)
+            for (uint32_t i = 0; i < n; i += 2) {
+                const float t0 = __uint_as_float(entry(i).y), t1 = __uint_as_float(entry(i + 1).y);
+                distance = __fadd_rn(distance, __fsub_rn(t1, t0));
+            }
+        dist0 = distance;
+        distance = (float)((double)distance * a.length_to_cm);
+        L = __fmul_rn(a.incident, expf_glibc(-__fmul_rn(a.meshes[0].mu, distance)));
+        ssum0 = 0; hits0 = n;
+    } else if (n == 0) {
+        // no hit in any mesh: L *= exp(-(mu * (0 * 0.1))) == L exactly, unless mu or the unit factor is not finite
+        for (int m = 0; m < a.n_meshes; ++m) {
+            const float mu = a.meshes[m].mu;
+            if (!(isfinite(mu) && isfinite(a.length_to_cm))) L = attenuate(L, mu, 0.0f, 0, a.length_to_cm);
+        }
+    } else {
+        uint32_t i = 0;
+        uint2 cur = entry(0);
+        for (int m = 0; m < a.n_meshes; ++m) {
+            const DevMesh M = a.meshes[m];
+            float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
+            if (M.contributes) {
+                while (i < n && cur.x < M.first + M.n) {
+                    const float st = __uint_as_float(cur.y);
+                    dist = __fadd_rn(dist, st);              // distance += sign * t, ascending triangle order
+                    ssum += (0.0f < st) - (st < 0.0f);
+                    ++hits; ++i;
+                    if (i < n) cur = entry(i);
+                }
+            }
+            L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
+            if (m == 0) { dist0 = dist; ssum0 = ssum; hits0 = hits; }
+        }
+    }
+    return { L, dist0, ssum0, hits0 };
+}
+
 __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant__ RenderArgs a)
 {
     __shared__ float s_sort[8][kSortOverflowCap];
@@ -744,79 +881,9 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
     if (valid) {
         const uint32_t head = a.hit_head[p];
         if (head != kNoHit) a.hit_head[p] = kNoHit;         // ready for the next render
-        if (overflow) { /* recomputed by the warp below */ }
-        else if (a.mode == 1) {
-            // closest hit: strict `z > t` in ascending triangle order == smallest t, lowest triangle index among equals
-            for (uint32_t i = head; i != kNoHit; i = a.hit_next[i]) {
-                const uint2 e = a.pix[i];
-                const float t = __uint_as_float(e.y);
-                if (dist0 > t || (dist0 == t && (int)e.x < ssum0)) { dist0 = t; ssum0 = (int)e.x; }
-            }
-        } else {
-            // The pixel's hits in the reference's order: ascending triangle index (mode 0: the float sum is order
-            // dependent) resp. ascending t (mode 2).  Lists of up to kLocalHits entries are insertion-sorted into a
-            // local array while the chain is walked; longer ones (rays grazing a bumpy silhouette) are replayed by
-            // selection -- one walk of the chain per entry, no storage -- which is slow but rare and exact.
-            uint2 e[kLocalHits];
-            uint32_t n = 0;
-            for (uint32_t i = head; i != kNoHit; i = a.hit_next[i], ++n) {
-                if (n >= kLocalHits) continue;
-                const uint2 key = a.pix[i];
-                const uint32_t kk = a.mode == 2 ? key.y : key.x;            // positive floats order like their bits
-                uint32_t j = n;
-                while (j > 0 && (a.mode == 2 ? e[j - 1].y : e[j - 1].x) > kk) { e[j] = e[j - 1]; --j; }
-                e[j] = key;
-            }
-            // visit entry number `i` (0-based, in order): from the array, or by selection over the chain
-            unsigned long long last = 0;                                    // long lists: (key, node) + 1 of the last visited entry
-            auto entry = [&](uint32_t i) -> uint2 {
-                if (n <= kLocalHits) return e[i];
-                unsigned long long best = ~0ull; uint2 bv = make_uint2(0, 0);
-                for (uint32_t c = head; c != kNoHit; c = a.hit_next[c]) {
-                    const uint2 v = a.pix[c];
-                    const unsigned long long k = (((unsigned long long)(a.mode == 2 ? v.y : v.x)) << 32 | c) + 1;
-                    if (k > last && k < best) { best = k; bv = v; }
-                }
-                last = best;
-                return bv;
-            };
-            if (a.mode == 2) {
-                // main.cxx:700-741 (sorted_xray_value), streamed: pairs (t[i], t[i + 1]) in ascending order
-                float distance = 0.0f;
-                if (n > 0 && (n & 1u) == 0)
-                    for (uint32_t i = 0; i < n; i += 2) {
-                        const float t0 = __uint_as_float(entry(i).y), t1 = __uint_as_float(entry(i + 1).y);
-                        distance = __fadd_rn(distance, __fsub_rn(t1, t0));
-                    }
-                dist0 = distance;
-                distance = (float)((double)distance * a.length_to_cm);
-                L = __fmul_rn(a.incident, expf_glibc(-__fmul_rn(a.meshes[0].mu, distance)));
-                ssum0 = 0; hits0 = n;
-            } else if (n == 0) {
-                // no hit in any mesh: L *= exp(-(mu * (0 * 0.1))) == L exactly, unless mu or the unit factor is not finite
-                for (int m = 0; m < a.n_meshes; ++m) {
-                    const float mu = a.meshes[m].mu;
-                    if (!(isfinite(mu) && isfinite(a.length_to_cm))) L = attenuate(L, mu, 0.0f, 0, a.length_to_cm);
-                }
-            } else {
-                uint32_t i = 0;
-                uint2 cur = entry(0);
-                for (int m = 0; m < a.n_meshes; ++m) {
-                    const DevMesh M = a.meshes[m];
-                    float dist = 0.0f; int ssum = 0; uint32_t hits = 0;
-                    if (M.contributes) {
-                        while (i < n && cur.x < M.first + M.n) {
-                            const float st = __uint_as_float(cur.y);
-                            dist = __fadd_rn(dist, st);              // distance += sign * t, ascending triangle order
-                            ssum += (0.0f < st) - (st < 0.0f);
-                            ++hits; ++i;
-                            if (i < n) cur = entry(i);
-                        }
-                    }
-                    L = attenuate(L, M.mu, dist, ssum, a.length_to_cm);
-                    if (m == 0) { dist0 = dist; ssum0 = ssum; hits0 = hits; }
-                }
-            }
+        if (!overflow) {
+            const PixelOut r = resolve_list(a, head);
+            L = r.L; dist0 = r.dist; ssum0 = r.ssum; hits0 = r.hits;
         }
     }
     // The candidate lists overflowed: the WARP recomputes each of its pixels from scratch with the exact sequence --
