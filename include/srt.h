@@ -95,7 +95,8 @@ typedef struct {
 } srt_light;
 
 typedef enum {
-    SRT_KERNEL_AUTO = 0,        /* fastest applicable: culled, else filtered, else exact (same results) */
+    SRT_KERNEL_AUTO = 0,        /* fastest for the scene: exact for a handful of triangles, filtered (brute force)
+                                   up to ~2e5 triangles, culled beyond (same results whichever runs)      */
     SRT_KERNEL_EXACT = 1,       /* every (ray, triangle) pair runs the reference op sequence          */
     SRT_KERNEL_FILTERED = 2,    /* conservative affine reject per pair + exact test for survivors     */
     SRT_KERNEL_AUDIT = 3,       /* diagnostic: exact kernel that also evaluates the filter for every
@@ -239,16 +240,26 @@ int  srt_render_lbuffer_blocks_device(srt_ctx* ctx, const srt_params* params, ui
  * process; epoch starts at 1 and grows by one per barrier on a given set of flag arrays.  The kernels launched before
  * it have stored their rows into the peers' frames; the kernels launched after it start when every rank's rows have
  * landed in this rank's frame.  A one-CTA kernel: any number of barriers may be in flight on different streams.
- * srt_render_xray_blocks_device = srt_render_lbuffer_blocks_device + this barrier + srt_repair_device(d_own_frame ->
- * d_image) in one call: one frame of the sharded pipeline (the gather of src/main-mpi.cxx:854-881 fused into the
- * render; every rank ends up with the repaired image).
+ *
+ * srt_repair_blocks_device: the sharded repair pass -- the rank repairs the pixels of ITS 16-row blocks (reading the
+ * assembled L frame d_L: the +-4-pixel stencil reaches into rows the neighbouring ranks rendered) and stores them into
+ * each of the n_images image buffers (own first, then the peers' mappings; or one multicast mapping with
+ * SRT_FLAG_FRAME0_MULTICAST), so that no rank spends time on pixels another rank repairs.
+ *
+ * srt_render_xray_blocks_device: one frame of the sharded pipeline in one call (the gather of
+ * src/main-mpi.cxx:854-881 fused into the kernels; every rank ends up with the complete repaired image):
+ *   srt_render_lbuffer_blocks_device -> barrier (epoch 2 e - 1) -> srt_repair_blocks_device(d_own_frame) -> barrier (2 e),
+ * e = `epoch` = 1, 2, ... counting the frames issued on this set of flag arrays.  When the call's work has completed on
+ * the stream, d_images (the rank's own one) holds the whole repaired image.
  */
 int  srt_peer_barrier_device(srt_ctx* ctx, uint32_t n_ranks, uint32_t rank, uint32_t* const* d_flags, uint32_t epoch,
                              uint32_t phases /* 3 = signal + wait; 1 = signal only, 2 = wait only: a caller driving several
                                                 ranks from ONE thread enqueues every rank's signal before the first wait */);
+int  srt_repair_blocks_device(srt_ctx* ctx, const srt_params* params, uint32_t n_parts, uint32_t part, const float* d_L,
+                              uint32_t n_images, float* const* d_images);
 int  srt_render_xray_blocks_device(srt_ctx* ctx, const srt_params* params, uint32_t n_parts, uint32_t part,
                                    uint32_t n_frames, float* const* d_frames, uint32_t* const* d_flags, uint32_t epoch,
-                                   const float* d_own_frame, float* d_image);
+                                   const float* d_own_frame, uint32_t n_images, float* const* d_images);
 
 /* Artefact repair + image fill over a full frame (lbuffer.cxx:329-404). L_in and image_out must not alias. */
 int  srt_repair(srt_ctx* ctx, const srt_params* params, const float* L_in, float* image_out);

@@ -139,11 +139,10 @@ class PeerLanes:
     """Frame buffers and barrier flags of a PIPELINE of sharded frames, in one symmetric allocation per rank.
 
     Frames are rendered round-robin on `lanes` independent streams (one srt context each), so that the short,
-    latency-bound kernels of one frame (candidate stages, hit-list resolve, the device barrier, the repair pass)
-    overlap the scan of the next.  A lane owns two frame sets used alternately (a rank can run at most one frame
-    ahead of its peers per lane, so one barrier per frame suffices) and one flag array for
-    srt_peer_barrier_device (epoch = the lane's frame counter).  Layout per lane, in 4-byte words:
-    [frame set 0: H*W][frame set 1: H*W][flags: 64].
+    latency-bound kernels of one frame (candidate stages, hit-list resolve, the device barriers, the repair pass)
+    overlap the scan of the next.  A lane owns two sets of {L frame, image} used alternately and one flag array for
+    srt_peer_barrier_device (two barriers per frame: after the L rows, after the repaired image rows).  Layout per
+    lane, in 4-byte words: [L frame 0: H*W][L frame 1][image 0][image 1][flags: 64].
     """
     FLAG_WORDS = 64
 
@@ -152,7 +151,7 @@ class PeerLanes:
         self.H, self.W, self.lanes = H, W, lanes
         group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.lane_words = 2 * H * W + self.FLAG_WORDS
+        self.lane_words = 4 * H * W + self.FLAG_WORDS
         dev = torch.device("cuda", torch.cuda.current_device())
         self.buf = symm_mem.empty(lanes * self.lane_words, dtype=torch.float32, device=dev)
         self.buf.zero_()                                      # flags start at epoch 0
@@ -187,12 +186,20 @@ class PeerLanes:
     def own_frame_ptr(self, lane, s):
         return self.peer_ptrs[self.rank] + 4 * self._frame_off(lane, s)
 
+    def image(self, lane, s):
+        """this rank's repaired image of set `s` of `lane`"""
+        return self.frame(lane, 2 + s)
+
+    def image_ptrs(self, lane, s):
+        return self.frame_ptrs(lane, 2 + s)
+
     def flag_ptrs(self, lane):
         """flag array of every rank, in rank order, as mapped here"""
-        o = 4 * (lane * self.lane_words + 2 * self.H * self.W)
+        o = 4 * (lane * self.lane_words + 4 * self.H * self.W)
         return [p + o for p in self.peer_ptrs]
 
     def poison(self, value=float("nan")):
+        """overwrite every L frame and image of this rank (not the flags)"""
         for lane in range(self.lanes):
-            for s in (0, 1):
+            for s in range(4):
                 self.frame(lane, s).fill_(value)

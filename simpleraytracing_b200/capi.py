@@ -69,6 +69,7 @@ EXPORTS = [
     "srt_multi_set_camera", "srt_multi_render_xray_device", "srt_multi_synchronize", "srt_multi_frame",
     "srt_multi_render_xray", "srt_multi_last_timing",
     "srt_set_profiling", "srt_set_scan_residency", "srt_peer_barrier_device", "srt_render_xray_blocks_device",
+    "srt_repair_blocks_device",
 ]
 
 
@@ -153,7 +154,8 @@ class Library:
         L.srt_set_scan_residency.argtypes = [vp, u32]
         L.srt_peer_barrier_device.argtypes = [vp, u32, u32, C.POINTER(C.c_void_p), u32, u32]
         L.srt_render_xray_blocks_device.argtypes = [vp, C.POINTER(Params), u32, u32, u32, C.POINTER(C.c_void_p),
-                                                    C.POINTER(C.c_void_p), u32, vp, vp]
+                                                    C.POINTER(C.c_void_p), u32, vp, u32, C.POINTER(C.c_void_p)]
+        L.srt_repair_blocks_device.argtypes = [vp, C.POINTER(Params), u32, u32, vp, u32, C.POINTER(C.c_void_p)]
 
     # ---- host-only helpers ---------------------------------------------------
     def default_params(self, **kw):
@@ -353,22 +355,33 @@ class Context:
         self._ck(self.lib.srt_peer_barrier_device(self.h, n_ranks, rank, arr, epoch, phases))
 
     @staticmethod
-    def frame_call_args(params, frame_ptrs, flag_ptrs, multicast=False):
+    def frame_call_args(params, frame_ptrs, flag_ptrs, image_ptrs, multicast=False):
         """ctypes arguments of render_xray_blocks_device that do not change from frame to frame (build once per
-        frame set: the per-frame call is then one foreign call)."""
+        frame set: the per-frame call is then one foreign call).  frame_ptrs / image_ptrs: own buffer first, then the
+        peers' mappings -- or the single multicast mapping with multicast=True."""
         fr = (C.c_void_p * len(frame_ptrs))(*[C.c_void_p(int(q)) for q in frame_ptrs])
         fl = (C.c_void_p * len(flag_ptrs))(*[C.c_void_p(int(q)) for q in flag_ptrs])
+        im = (C.c_void_p * len(image_ptrs))(*[C.c_void_p(int(q)) for q in image_ptrs])
         q = Params.from_buffer_copy(params)
         if multicast:
             q.flags |= FLAG_FRAME0_MULTICAST
-        return q, fr, len(frame_ptrs), fl
+        return q, fr, len(frame_ptrs), fl, im, len(image_ptrs)
 
-    def render_xray_blocks_device(self, call_args, n_parts, part, epoch, d_own_frame, d_image):
-        """One frame of the sharded pipeline: this rank's 16-row blocks stored into every rank's frame, device barrier
-        over the ranks, repair of the assembled frame d_own_frame into d_image.  call_args: frame_call_args(...)."""
-        q, fr, nf, fl = call_args
+    def render_xray_blocks_device(self, call_args, n_parts, part, epoch, d_own_frame):
+        """One frame of the sharded pipeline: this rank's 16-row blocks stored into every rank's L frame, device barrier,
+        repair of this rank's blocks (from the assembled frame d_own_frame) stored into every rank's image, device
+        barrier.  call_args: frame_call_args(...); epoch = 1, 2, ... per set of flag arrays."""
+        q, fr, nf, fl, im, ni = call_args
         self._ck(self.lib.srt_render_xray_blocks_device(self.h, C.byref(q), n_parts, part, nf, fr, fl, epoch,
-                                                        C.c_void_p(d_own_frame), C.c_void_p(d_image)))
+                                                        C.c_void_p(d_own_frame), ni, im))
+
+    def repair_blocks_device(self, params, n_parts, part, d_L, image_ptrs, multicast=False):
+        im = (C.c_void_p * len(image_ptrs))(*[C.c_void_p(int(q)) for q in image_ptrs])
+        if multicast:
+            q = Params.from_buffer_copy(params)
+            q.flags |= FLAG_FRAME0_MULTICAST
+            params = q
+        self._ck(self.lib.srt_repair_blocks_device(self.h, C.byref(params), n_parts, part, C.c_void_p(d_L), len(image_ptrs), im))
 
     def render_lbuffer_interleaved_device(self, params, n_parts, part, d_slot, d_dist=0, d_ssum=0, d_hits=0):
         self._ck(self.lib.srt_render_lbuffer_interleaved_device(self.h, C.byref(params), n_parts, part, C.c_void_p(d_slot),

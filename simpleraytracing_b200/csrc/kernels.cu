@@ -594,8 +594,12 @@ __global__ void __launch_bounds__(128) candidates_kernel(const __grid_constant__
                         const float x = x0 + (float)kx;                                 // exact: (half-)integers far below 2^23
                         const float Dd = fabsf(fmaf(fa.w, x, bd));
                         const float Y1 = fmaf(fa.x, x, b1), Y2 = fmaf(ga.x, x, b2), Y3 = fmaf(gb.x, x, b3);
-                        const bool rej = (fabsf(Y1) > Dd + fb.z) | (fabsf(Y2) > Dd + ga.w) | (fabsf(Y3) > Dd + gb.w);   // NaN survives
-                        rowmask |= rej ? 0u : (1u << kx);
+                        // reject iff |Y_i| > fl(Dd + m_i) for some strip  <=>  fl(fl(Dd + m_i) - |Y_i|) < 0 (the sign of a rounded
+                        // difference is the sign of the exact one); fminf drops NaN operands, and an all-NaN pixel survives as
+                        // with the comparisons.  Written this way the work sits on the FMA pipe (6 FADD) instead of the ALU
+                        // pipe the kernel was bound by (3 FSETP + 3 SEL per pixel).
+                        const float t = fminf(fminf((Dd + fb.z) - fabsf(Y1), (Dd + ga.w) - fabsf(Y2)), (Dd + gb.w) - fabsf(Y3));
+                        if (!(t < 0.0f)) rowmask |= 1u << kx;
                     }
                     if (col0 + PX > W) rowmask &= (1u << (W - col0)) - 1u;              // pixels beyond the last column
                     if (row0 + ky < a.row_end) mask |= (unsigned long long)rowmask << (ky * PX);
@@ -612,11 +616,18 @@ __global__ void __launch_bounds__(128) candidates_kernel(const __grid_constant__
         uint32_t at = 0;
         if (lane == 31) at = atomicAdd(a.cand_count + 1, total);
         at = __shfl_sync(0xffffffffu, at, 31) + incl - mine;
-        while (mask) {
-            const uint32_t k = (uint32_t)__ffsll((long long)mask) - 1;
-            mask &= mask - 1;
-            if (at < a.pix_cap) a.pix[at] = make_uint2((row0 + k / PX) * W + col0 + k % PX, tm);   // overflow: resolve falls back
-            ++at;
+        // (32-bit halves: the 64-bit find-first-set / clear-lowest pair costs three times the instructions, and this loop runs
+        // for as long as the lane with the most candidates)
+        const uint32_t pix0 = row0 * W + col0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t m = half ? (uint32_t)(mask >> 32) : (uint32_t)mask;
+            while (m) {
+                const uint32_t k = (uint32_t)__ffs((int)m) - 1 + 32u * half;
+                m &= m - 1;
+                if (at < a.pix_cap) a.pix[at] = make_uint2(pix0 + (k / PX) * W + k % PX, tm);   // overflow: resolve falls back
+                ++at;
+            }
         }
     }
 }
@@ -798,8 +809,7 @@ __device__ __forceinline__ PixelOut resolve_list(const RenderArgs& a, uint32_t h
         }
     }
     // Longer lists: up to kLocalHits entries are insertion-sorted into a local array while the chain is walked; beyond
-    // that (rays grazing a bumpy silhouette) they are replayed by selection -- one walk of the chain per entry, no
-    // storage -- which is slow but rare and exact.
+    // that they are replayed window by window (below).
     uint2 e[kLocalHits];
     uint32_t n = 0;
     for (uint32_t i = head; i != kNoHit; i = a.hit_next[i], ++n) {
@@ -810,18 +820,28 @@ __device__ __forceinline__ PixelOut resolve_list(const RenderArgs& a, uint32_t h
         while (j > 0 && (a.mode == 2 ? e[j - 1].y : e[j - 1].x) > kk) { e[j] = e[j - 1]; --j; }
         e[j] = key;
     }
-    // visit entry number `i` (0-based, in order): from the array, or by selection over the chain
-    unsigned long long last = 0;                                    // long lists: (key, node) + 1 of the last visited entry
+    // visit entry number `i` (0-based; the callers ask for 0, 1, 2, ... in order): from the array when the whole list
+    // fits, else from a WINDOW of the next kLocalHits entries in order, refilled by one walk of the chain that keeps the
+    // kLocalHits smallest (key, node) pairs above the last one visited -- n / kLocalHits walks per list instead of the n
+    // a plain selection takes (the poles of the 998 000-triangle sphere put ~1 400 hits on some rays).
+    unsigned long long last = 0;                                    // (key, node) + 1 of the last entry of the previous window
+    unsigned long long wk[kLocalHits];                              // the window's (key, node) + 1, ascending; values in e[]
+    uint32_t win_base = 0, win_n = 0;
     auto entry = [&](uint32_t i) -> uint2 {
         if (n <= kLocalHits) return e[i];
-        unsigned long long best = ~0ull; uint2 bv = make_uint2(0, 0);
-        for (uint32_t c = head; c != kNoHit; c = a.hit_next[c]) {
-            const uint2 v = a.pix[c];
-            const unsigned long long k = (((unsigned long long)(a.mode == 2 ? v.y : v.x)) << 32 | c) + 1;
-            if (k > last && k < best) { best = k; bv = v; }
+        if (i >= win_base + win_n) {
+            win_base += win_n; win_n = 0;
+            for (uint32_t c = head; c != kNoHit; c = a.hit_next[c]) {
+                const uint2 v = a.pix[c];
+                const unsigned long long k = (((unsigned long long)(a.mode == 2 ? v.y : v.x)) << 32 | c) + 1;
+                if (k <= last || (win_n == kLocalHits && k >= wk[kLocalHits - 1])) continue;
+                uint32_t j = win_n < kLocalHits ? win_n++ : kLocalHits - 1;      // full: the largest drops out
+                while (j > 0 && wk[j - 1] > k) { wk[j] = wk[j - 1]; e[j] = e[j - 1]; --j; }
+                wk[j] = k; e[j] = v;
+            }
+            last = wk[win_n - 1];
         }
-        last = best;
-        return bv;
+        return e[i - win_base];
     };
     if (a.mode == 2) {
         // main.cxx:700-741 (sorted_xray_value), streamed: pairs (t[i], t[i + 1]) in ascending order
@@ -866,6 +886,9 @@ __device__ __forceinline__ PixelOut resolve_list(const RenderArgs& a, uint32_t h
 __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant__ RenderArgs a)
 {
     __shared__ float s_sort[8][kSortOverflowCap];
+    __shared__ PixelOut s_none;                              // outputs of a pixel no triangle touches (~70 % of a frame): computed once
+    if (threadIdx.x == 0) s_none = resolve_list(a, kNoHit);
+    __syncthreads();
     const uint32_t W = a.cam.W;
     const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t by = blockIdx.y >> 4, lrow = blockIdx.y & 15u;
@@ -882,7 +905,7 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
         const uint32_t head = a.hit_head[p];
         if (head != kNoHit) a.hit_head[p] = kNoHit;         // ready for the next render
         if (!overflow) {
-            const PixelOut r = resolve_list(a, head);
+            const PixelOut r = head == kNoHit ? s_none : resolve_list(a, head);
             L = r.L; dist0 = r.dist; ssum0 = r.ssum; hits0 = r.hits;
         }
     }
@@ -1608,12 +1631,8 @@ __device__ __forceinline__ float repair_probe_dir(const float* __restrict__ L, u
     return value;
 }
 
-__global__ void __launch_bounds__(256) repair_kernel(const float* __restrict__ L, float* __restrict__ image,
-                                                     uint32_t W, uint32_t H, uint32_t depth)
+__device__ __forceinline__ float repair_value(const float* __restrict__ L, uint64_t pixel, uint32_t W, uint64_t size, uint32_t depth)
 {
-    const uint64_t size = (uint64_t)W * H;
-    const uint64_t pixel = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pixel >= size) return;
     float out = L[pixel];
     if (out == -1.0f) {
         const uint32_t row = (uint32_t)(pixel / W), col = (uint32_t)(pixel % W);
@@ -1626,7 +1645,47 @@ __global__ void __launch_bounds__(256) repair_kernel(const float* __restrict__ L
         v = repair_probe_dir(L, base, (int32_t)W, depth, size);      if (v != 0.0f) { sum = __fadd_rn(sum, v); ++n; }   // +row
         out = __fdiv_rn(sum, (float)n);                              // 0/0 -> NaN like the reference
     }
-    image[pixel] = out;
+    return out;
+}
+
+__global__ void __launch_bounds__(256) repair_kernel(const float* __restrict__ L, float* __restrict__ image,
+                                                     uint32_t W, uint32_t H, uint32_t depth)
+{
+    const uint64_t size = (uint64_t)W * H;
+    const uint64_t pixel = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel >= size) return;
+    image[pixel] = repair_value(L, pixel, W, size, depth);
+}
+
+// Sharded repair (multi-GPU): the rank repairs the pixels of ITS 16-row blocks only -- reading the assembled L frame, whose
+// rows around the blocks came from the neighbouring ranks -- and stores them into the image of every rank (peer
+// mappings, or one multimem.st into the NVSwitch multicast mapping).  4 pixels per thread, 128-bit stores.
+__global__ void __launch_bounds__(256) repair_blocks_kernel(const float* __restrict__ L, const RepairOut out, uint32_t W, uint32_t H,
+                                                            uint32_t depth, uint32_t n_parts, uint32_t part)
+{
+    const uint32_t by = blockIdx.y >> 4, lrow = blockIdx.y & 15u;
+    const uint32_t row = (by * n_parts + part) * 16 + lrow;
+    if (row >= H) return;
+    const uint64_t size = (uint64_t)W * H;
+    auto store1 = [&](uint64_t p, float v) {
+        if (out.multicast) asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(out.image + p), "f"(v) : "memory");
+        else out.image[p] = v;
+        for (uint32_t i = 0; i < out.n_extra; ++i) out.extra[i][p] = v;
+    };
+    if (out.vec4) {
+        const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (c >= W) return;
+        const uint64_t p = (uint64_t)row * W + c;
+        const float4 v = make_float4(repair_value(L, p, W, size, depth), repair_value(L, p + 1, W, size, depth),
+                                     repair_value(L, p + 2, W, size, depth), repair_value(L, p + 3, W, size, depth));
+        if (out.multicast)
+            asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out.image + p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        else *reinterpret_cast<float4*>(out.image + p) = v;
+        for (uint32_t i = 0; i < out.n_extra; ++i) *reinterpret_cast<float4*>(out.extra[i] + p) = v;
+    } else {
+        for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < W; c += gridDim.x * blockDim.x)
+            store1((uint64_t)row * W + c, repair_value(L, (uint64_t)row * W + c, W, size, depth));
+    }
 }
 
 // ------------------------------------------------------------------ scene pre-pack
@@ -1922,6 +1981,18 @@ cudaError_t launch_deinterleave(const float* slots, float* frame, uint32_t W, ui
     if (W == 0 || H == 0) return cudaSuccess;
     dim3 grid((W / 4 + 255) / 256 ? (W / 4 + 255) / 256 : 1, H);
     deinterleave_kernel<<<grid, 256, 0, s>>>(slots, frame, W, H, n_parts, slot_rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_repair_blocks(const float* L, const RepairOut& out, uint32_t W, uint32_t H, uint32_t depth, uint32_t n_parts,
+                                 uint32_t part, cudaStream_t s)
+{
+    if (W == 0 || H == 0 || n_parts == 0) return cudaSuccess;
+    const uint32_t blocks = (H + 15) / 16;
+    const uint32_t mine = blocks > part ? (blocks - part + n_parts - 1) / n_parts : 0;
+    if (mine == 0) return cudaSuccess;
+    dim3 grid(out.vec4 ? (W / 4 + 255) / 256 : std::min(8u, (W + 255) / 256), mine * 16);
+    repair_blocks_kernel<<<grid, 256, 0, s>>>(L, out, W, H, depth, n_parts, part);
     return cudaGetLastError();
 }
 

@@ -182,6 +182,11 @@ struct PeerFlags { uint32_t* p[8]; };
 cudaError_t launch_peer_barrier(const PeerFlags& f, uint32_t n, uint32_t rank, uint32_t epoch, uint32_t phases, cudaStream_t s);
 // Artefact repair + image fill (lbuffer.cxx:329-404).
 cudaError_t launch_repair(const float* L, float* image, uint32_t W, uint32_t H, uint32_t depth, cudaStream_t s);
+// Sharded repair: the pixels of the 16-row blocks part, part + n_parts, ... of the frame, stored into `image` (a multicast
+// mapping when multicast != 0) and the n_extra extra images; vec4: every image is 16-byte aligned and W % 4 == 0.
+struct RepairOut { float* image; int multicast, vec4; uint32_t n_extra; float* extra[7]; };
+cudaError_t launch_repair_blocks(const float* L, const RepairOut& out, uint32_t W, uint32_t H, uint32_t depth, uint32_t n_parts,
+                                 uint32_t part, cudaStream_t s);
 
 // Scene pre-pack on the GPU (prepack_math.h): raw vertices -> ExactTri / FilterTri / FilterTri2.
 struct FrameGeom;

@@ -414,9 +414,14 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         a.counters = c->d_counters;
     }
 
-    // AUTO: the hierarchically culled kernel; a handful of triangles (config C4: the 2-triangle logo quad) is fastest
-    // in the one-launch exact kernel -- the multi-kernel paths cost more in launches than such a frame in arithmetic
-    if (kernel == SRT_KERNEL_AUTO) kernel = (c->total_tris <= 64 && mode == 0) ? SRT_KERNEL_EXACT : SRT_KERNEL_CULLED;
+    // AUTO: the fastest kernel for the scene -- same results whichever runs.  A handful of triangles (config C4: the
+    // 2-triangle logo quad) is fastest in the one-launch exact kernel (the multi-kernel paths cost more in launches than
+    // such a frame in arithmetic); up to ~2e5 triangles the brute-force scan with 64 x 16 boxes wins (dragon, 2048^2:
+    // 0.17 ms against 0.22 ms culled); beyond, the bins of the culled kernel pay off (998 000-triangle sphere at 8192^2:
+    // 44 ms against 166 ms: every box still meets every triangle in the brute-force scan, and the bumpy silhouette's
+    // long hit lists cost the resolve pass more than the culled kernel's in-order accumulation).
+    if (kernel == SRT_KERNEL_AUTO)
+        kernel = (c->total_tris <= 64 && mode == 0) ? SRT_KERNEL_EXACT : (c->total_tris <= 200000 ? SRT_KERNEL_FILTERED : SRT_KERNEL_CULLED);
     if (!c->filterable) kernel = SRT_KERNEL_EXACT;                        // camera outside the filter's preconditions
     if (mode == 2) {
         // the sort mode lives on the hit lists of the filtered path (an unfilterable camera lets every box through:
@@ -958,19 +963,47 @@ int srt_peer_barrier_device(srt_ctx* c, uint32_t n_ranks, uint32_t rank, uint32_
     return SRT_OK;
 }
 
-int srt_render_xray_blocks_device(srt_ctx* c, const srt_params* p, uint32_t n_parts, uint32_t part, uint32_t n_frames,
-                                  float* const* d_frames, uint32_t* const* d_flags, uint32_t epoch, const float* d_own_frame,
-                                  float* d_image)
+int srt_repair_blocks_device(srt_ctx* c, const srt_params* p, uint32_t n_parts, uint32_t part, const float* d_L,
+                             uint32_t n_images, float* const* d_images)
 {
     if (!c) return SRT_ERR_INVALID;
-    if (!d_own_frame || !d_image) return fail(c, SRT_ERR_INVALID, "own frame / image is NULL");
+    if (!p || !d_L) return fail(c, SRT_ERR_INVALID, "params / L frame is NULL");
+    if (n_parts == 0 || part >= n_parts) return fail(c, SRT_ERR_INVALID, "part %u of %u", part, n_parts);
+    if (n_images == 0 || n_images > 8 || !d_images) return fail(c, SRT_ERR_INVALID, "1 to 8 image pointers expected");
+    if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
+    const bool multicast = (p->flags & SRT_FLAG_FRAME0_MULTICAST) != 0;
+    if (multicast && n_images != 1) return fail(c, SRT_ERR_INVALID, "a multicast mapping is the only image of the call");
+    srt::RepairOut out{};
+    bool aligned = (c->camera.width & 3u) == 0;
+    for (uint32_t i = 0; i < n_images; ++i) {
+        if (!d_images[i] || d_images[i] == d_L) return fail(c, SRT_ERR_INVALID, "image pointer %u is NULL or aliases the L frame", i);
+        aligned = aligned && ((uintptr_t)d_images[i] & 15u) == 0;
+        if (i == 0) out.image = d_images[0]; else out.extra[i - 1] = d_images[i];
+    }
+    out.n_extra = n_images - 1; out.multicast = multicast ? 1 : 0; out.vec4 = aligned ? 1 : 0;
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    if (c->profiling) SRT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    SRT_CUDA(c, srt::launch_repair_blocks(d_L, out, c->camera.width, c->camera.height, p->repair_depth, n_parts, part, c->stream));
+    if (c->profiling) SRT_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    return SRT_OK;
+}
+
+int srt_render_xray_blocks_device(srt_ctx* c, const srt_params* p, uint32_t n_parts, uint32_t part, uint32_t n_frames,
+                                  float* const* d_frames, uint32_t* const* d_flags, uint32_t epoch, const float* d_own_frame,
+                                  uint32_t n_images, float* const* d_images)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (!d_own_frame) return fail(c, SRT_ERR_INVALID, "own frame is NULL");
+    if (epoch == 0 || epoch >= 0x7fffffffu) return fail(c, SRT_ERR_INVALID, "epoch counts the frames of this flag set from 1");
     int rc = srt_render_lbuffer_blocks_device(c, p, n_parts, part, n_frames, d_frames);
     if (rc) return rc;
-    if (n_parts > 1) {
-        rc = srt_peer_barrier_device(c, n_parts, part, d_flags, epoch, 3);
-        if (rc) return rc;
-    }
-    return srt_repair_device(c, p, d_own_frame, d_image);
+    // barrier 1 (epoch 2 e - 1): every rank's rows have landed in this rank's L frame
+    if (n_parts > 1 && (rc = srt_peer_barrier_device(c, n_parts, part, d_flags, 2 * epoch - 1, 3)) != 0) return rc;
+    rc = srt_repair_blocks_device(c, p, n_parts, part, d_own_frame, n_images, d_images);
+    if (rc) return rc;
+    // barrier 2 (epoch 2 e): every rank's repaired rows have landed in this rank's image
+    if (n_parts > 1 && (rc = srt_peer_barrier_device(c, n_parts, part, d_flags, 2 * epoch, 3)) != 0) return rc;
+    return SRT_OK;
 }
 
 int srt_render_lbuffer(srt_ctx* c, const srt_params* p, uint32_t rb, uint32_t re,

@@ -16,21 +16,19 @@ FLAG_WORDS = 64
 
 
 class FakeRanks:
-    """n_ranks x lanes contexts on cuda:0 with frames / flags laid out like bands.PeerLanes"""
+    """n_ranks x lanes contexts on cuda:0 with frames / images / flags laid out like bands.PeerLanes"""
 
     def __init__(self, srtlib, meshes, cam, n_ranks, lanes, params):
         import torch
         self.torch = torch
         self.n, self.lanes, self.W, self.H = n_ranks, lanes, cam.width, cam.height
-        px = self.W * self.H
+        px = self.px = self.W * self.H
         dev = torch.device("cuda", 0)
-        # buf[rank][lane]: [frame set 0][frame set 1][flags]
-        self.buf = torch.zeros(n_ranks, lanes, 2 * px + FLAG_WORDS, dtype=torch.float32, device=dev)
-        self.img = torch.zeros(n_ranks, lanes, px, dtype=torch.float32, device=dev)
+        # buf[rank][lane]: [L frame 0][L frame 1][image 0][image 1][flags]
+        self.buf = torch.zeros(n_ranks, lanes, 4 * px + FLAG_WORDS, dtype=torch.float32, device=dev)
         self.ctx = [[Context(0, srtlib) for _ in range(lanes)] for _ in range(n_ranks)]
         self.streams = [[torch.cuda.Stream(device=dev) for _ in range(lanes)] for _ in range(n_ranks)]
-        self.epoch = [[0] * lanes for _ in range(n_ranks)]
-        self.args = {}
+        self.epoch = [0] * lanes
         self.params = params
         for r in range(n_ranks):
             for l in range(lanes):
@@ -38,31 +36,39 @@ class FakeRanks:
                 c.set_stream(self.streams[r][l].cuda_stream)
                 c.set_meshes(meshes); c.set_camera(cam)
                 c.set_profiling(False)
-                flags = [self.buf[q, l, 2 * px:].data_ptr() for q in range(n_ranks)]
-                for s in (0, 1):
-                    own = self.buf[r, l, s * px:(s + 1) * px].data_ptr()
-                    frames = [own] + [self.buf[q, l, s * px:(s + 1) * px].data_ptr() for q in range(n_ranks) if q != r]
-                    self.args[r, l, s] = (frames, flags, own)
+
+    def ptrs(self, r, l, which):
+        """buffer `which` (0, 1: L frames; 2, 3: images) of lane l: rank r's own first, then the other ranks'"""
+        px = self.px
+        own = self.buf[r, l, which * px:(which + 1) * px].data_ptr()
+        return [own] + [self.buf[q, l, which * px:(which + 1) * px].data_ptr() for q in range(self.n) if q != r]
+
+    def image(self, r, l):
+        s = self.epoch[l] & 1
+        return self.buf[r, l, (2 + s) * self.px:(3 + s) * self.px]
 
     def frame(self, l, order):
-        """one frame of lane `l` on every rank.  All ranks are driven by this one thread, and streams may share a
-        hardware queue, so every rank's signal is enqueued before the first wait (a real rank uses phases = 3)."""
-        self.epoch[0][l] += 1
-        e = self.epoch[0][l]
+        """one frame of lane `l` on every rank: srt_render_xray_blocks_device taken apart.  All ranks are driven by this
+        one thread, and streams may share a hardware queue, so at both barriers every rank's signal is enqueued
+        before the first wait (a real rank uses phases = 3)."""
+        self.epoch[l] += 1
+        e = self.epoch[l]
+        s = e & 1
+        flags = [self.buf[q, l, 4 * self.px:].data_ptr() for q in range(self.n)]
         for r in order:
-            frames, flags, own = self.args[r, l, e & 1]
-            self.ctx[r][l].render_lbuffer_blocks_device(self.params, self.n, r, frames)
+            self.ctx[r][l].render_lbuffer_blocks_device(self.params, self.n, r, self.ptrs(r, l, s))
         for r in order:
-            self.ctx[r][l].peer_barrier_device(self.n, r, self.args[r, l, e & 1][1], e, phases=1)
+            self.ctx[r][l].peer_barrier_device(self.n, r, flags, 2 * e - 1, phases=1)
         for r in order:
-            frames, flags, own = self.args[r, l, e & 1]
-            self.ctx[r][l].peer_barrier_device(self.n, r, flags, e, phases=2)
-            self.ctx[r][l].repair_device(self.params, own, self.img[r, l].data_ptr())
+            self.ctx[r][l].peer_barrier_device(self.n, r, flags, 2 * e - 1, phases=2)
+            self.ctx[r][l].repair_blocks_device(self.params, self.n, r, self.ptrs(r, l, s)[0], self.ptrs(r, l, 2 + s))
+        for r in order:
+            self.ctx[r][l].peer_barrier_device(self.n, r, flags, 2 * e, phases=1)
+        for r in order:
+            self.ctx[r][l].peer_barrier_device(self.n, r, flags, 2 * e, phases=2)
 
     def poison(self):
-        px = self.W * self.H
-        self.buf[:, :, :2 * px].fill_(float("nan"))
-        self.img.fill_(float("nan"))
+        self.buf[:, :, :4 * self.px].fill_(float("nan"))
 
     def close(self):
         self.torch.cuda.synchronize()
@@ -91,7 +97,7 @@ def test_sharded_pipeline_equals_the_unsharded_render(gpu_ctx, srtlib, dragon, k
         torch.cuda.synchronize()
         for r in range(n_ranks):
             for l in range(lanes):
-                assert torch.equal(fr.img[r, l].view(torch.int32), want), (rnd, r, l)
+                assert torch.equal(fr.image(r, l).view(torch.int32), want), (rnd, r, l)
     fr.close()
 
 
@@ -129,11 +135,21 @@ def test_fused_frame_call_with_one_rank_equals_render_xray(gpu_ctx, srtlib, drag
     want = torch.from_numpy(gpu_ctx.render_xray(p).view(np.int32)).cuda()
     frame = torch.zeros(300 * 150, dtype=torch.float32, device="cuda"); img = torch.zeros_like(frame)
     flags = torch.zeros(FLAG_WORDS, dtype=torch.int32, device="cuda")
-    args = Context.frame_call_args(p, [frame.data_ptr()], [flags.data_ptr()])
+    args = Context.frame_call_args(p, [frame.data_ptr()], [flags.data_ptr()], [img.data_ptr()])
     for e in (1, 2, 3):
-        gpu_ctx.render_xray_blocks_device(args, 1, 0, e, frame.data_ptr(), img.data_ptr())
+        img.fill_(float("nan"))
+        gpu_ctx.render_xray_blocks_device(args, 1, 0, e, frame.data_ptr())
         gpu_ctx.synchronize()
         assert torch.equal(img.view(torch.int32), want)
+    # the sharded repair pass alone: three shares of the frame into one image == the full-frame repair (300 is not a
+    # multiple of 4 x 256 threads, 150 rows leave a ragged last block)
+    img.fill_(float("nan"))
+    for part in range(3):
+        gpu_ctx.repair_blocks_device(p, 3, part, frame.data_ptr(), [img.data_ptr()])
+    gpu_ctx.synchronize()
+    assert torch.equal(img.view(torch.int32), want)
     from simpleraytracing_b200 import SrtError
     with pytest.raises(SrtError):
         gpu_ctx.peer_barrier_device(2, 0, [flags.data_ptr(), flags.data_ptr()], 1, phases=0)
+    with pytest.raises(SrtError):
+        gpu_ctx.repair_blocks_device(p, 3, 0, frame.data_ptr(), [frame.data_ptr()])           # image aliases the L frame
