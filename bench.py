@@ -279,8 +279,9 @@ def run_ours(args):
     # Nothing is shared between the frames in flight, so the latency-bound tail of one frame (candidate stages,
     # hit-list resolve, device barrier, repair) overlaps the scan of the next.
     big = args.config == "c5"
-    n_lanes = max(1, args.lanes if args.lanes else (1 if big else 4))
-    B = max(1, args.frames_per_step if args.frames_per_step else (1 if big else 16))
+    # (a share of a frame is short: more frames must be in flight to cover the fixed latencies of its ~8 launches)
+    n_lanes = max(1, args.lanes if args.lanes else (1 if big else (4 if world <= 2 else 8)))
+    B = max(1, args.frames_per_step if args.frames_per_step else (1 if big else 4 * n_lanes))
 
     # N > 1: block-cyclic 16-row blocks (contiguous bands are unbalanced: rows through the object cost more).
     # Preferred assembly: the render kernels store their rows straight into every rank's frame over NVLink (multicast
@@ -293,8 +294,11 @@ def run_ours(args):
         if args.assembly != "allgather":
             try:
                 peers = PeerLanes(H, W, n_lanes, use_multicast=(args.assembly != "p2p"))
-                assembly = ("render + sharded repair kernels store (multimem.st) to the NVSwitch multicast mapping of all frames / images" if peers.multicast_ptr
-                            else "render + sharded repair kernels store to every peer's frame / image over NVLink") + "; two flag-barrier kernels per frame"
+                assembly = ("L rows: " + ("own frame + the repair stencil's halo rows to the two neighbouring ranks (peer stores)" if args.l_exchange == "halo"
+                                          else "every row to every rank") +
+                            "; repaired image rows (sharded repair): " + ("multimem.st to the NVSwitch multicast mapping of all images" if peers.multicast_ptr
+                                                                          else "peer stores to every rank's image") +
+                            "; two flag-barrier kernels per frame")
             except Exception as exc:                      # no peer access on this box
                 peers = None
                 assembly += f" (symmetric memory unavailable: {type(exc).__name__})"
@@ -332,8 +336,12 @@ def run_ours(args):
             for name, p_ in (("headline", params), ("acc", params_acc)):
                 ln.calls[name] = []
                 for s_ in (0, 1):
-                    ptrs, mc = peers.frame_ptrs(l, s_)
-                    ln.calls[name].append(Context.frame_call_args(p_, ptrs, peers.flag_ptrs(l), peers.image_ptrs(l, s_)[0], multicast=mc))
+                    img_ptrs, mc = peers.image_ptrs(l, s_)
+                    if args.l_exchange == "halo":             # L rows: own frame + halo rows to the two neighbouring ranks
+                        ln.calls[name].append(Context.frame_call_args(p_, peers.unicast_ptrs(l, s_), peers.flag_ptrs(l), img_ptrs,
+                                                                      multicast=mc, halo=True))
+                    else:                                     # every L row to every rank
+                        ln.calls[name].append(Context.frame_call_args(p_, peers.frame_ptrs(l, s_)[0], peers.flag_ptrs(l), img_ptrs, multicast=mc))
             ln.own = [peers.own_frame_ptr(l, s_) for s_ in (0, 1)]
             ln.images = [peers.image(l, s_) for s_ in (0, 1)]
         else:
@@ -717,9 +725,11 @@ def main():
                     help="box shape of the filtered kernel: width | height << 8 | boxes per thread << 16 (0 = default)")
     ap.add_argument("--assembly", default="auto", choices=["auto", "p2p", "allgather"],
                     help="N > 1: auto = fused stores (multicast if available, else per-peer), p2p = per-peer stores, allgather = NCCL")
+    ap.add_argument("--l-exchange", default="halo", choices=["halo", "all"],
+                    help="N > 1: which L rows leave the rank: halo = only what the neighbours' repair stencils read, all = every row to every rank")
     ap.add_argument("--verify-iters", type=int, default=48, help="N > 1: sharded frames checked against unsharded renders")
-    ap.add_argument("--lanes", type=int, default=0, help="frames in flight (srt context + stream each); 0 = default (4; 1 for c5)")
-    ap.add_argument("--frames-per-step", type=int, default=0, help="frames per timed step; 0 = default (16; 1 for c5)")
+    ap.add_argument("--lanes", type=int, default=0, help="frames in flight (srt context + stream each); 0 = default (4, 8 at N > 2; 1 for c5)")
+    ap.add_argument("--frames-per-step", type=int, default=0, help="frames per timed step; 0 = default (4 x lanes; 1 for c5)")
     ap.add_argument("--scan-ctas", type=int, default=0, help="cap on the scan kernel's resident CTAs per SM (0 = none, else >= 4)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

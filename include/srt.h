@@ -107,8 +107,14 @@ typedef enum {
 } srt_kernel;
 
 #define SRT_FLAG_ALL_MESHES_CONTRIBUTE 1u  /* default off: only mesh 0 adds path length (lbuffer.cxx:788) */
-#define SRT_FLAG_FRAME0_MULTICAST 2u       /* srt_render_lbuffer_blocks_device: d_frames[0] is an NVSwitch multicast
-                                              mapping of every GPU's frame (written with multimem.st)             */
+#define SRT_FLAG_FRAME0_MULTICAST 2u       /* sharded entry points: a frame / image array of ONE pointer is an NVSwitch
+                                              multicast mapping of every GPU's buffer (written with multimem.st)   */
+#define SRT_FLAG_L_HALO_ONLY 4u            /* srt_render_lbuffer_blocks_device with n_frames == n_parts (own frame, then
+                                              every peer's in rank order): store each L row into the own frame and
+                                              only the first / last repair_depth rows of a 16-row block into the frame
+                                              of the rank that owns the block above / below -- all the sharded repair
+                                              pass (srt_repair_blocks_device) reads; 1/16 of the NVLink traffic of
+                                              replicating every row to every GPU                                   */
 
 typedef struct {
     float    incident;          /* initial L-buffer value, 80.0f (lbuffer.cxx:314)                    */

@@ -183,6 +183,11 @@ class PeerLanes:
             return [self.multicast_ptr + o], True
         return [self.peer_ptrs[self.rank] + o] + [p + o for r, p in enumerate(self.peer_ptrs) if r != self.rank], False
 
+    def unicast_ptrs(self, lane, s):
+        """own buffer first, then every peer's in rank order (what SRT_FLAG_L_HALO_ONLY expects)"""
+        o = 4 * self._frame_off(lane, s)
+        return [self.peer_ptrs[self.rank] + o] + [p + o for r, p in enumerate(self.peer_ptrs) if r != self.rank]
+
     def own_frame_ptr(self, lane, s):
         return self.peer_ptrs[self.rank] + 4 * self._frame_off(lane, s)
 

@@ -10,6 +10,7 @@ LIB_PATH = PKG / "lib" / "libsrt_b200.so"
 KERNEL_AUTO, KERNEL_EXACT, KERNEL_FILTERED, KERNEL_AUDIT, KERNEL_CULLED = 0, 1, 2, 3, 4
 FLAG_ALL_MESHES_CONTRIBUTE = 1
 FLAG_FRAME0_MULTICAST = 2
+FLAG_L_HALO_ONLY = 4
 
 
 class SrtError(RuntimeError):
@@ -333,14 +334,14 @@ class Context:
                                                     C.c_void_p(d_dist or None), C.c_void_p(d_ssum or None),
                                                     C.c_void_p(d_hits or None)))
 
-    def render_lbuffer_blocks_device(self, params, n_parts, part, frame_ptrs, multicast=False):
+    def render_lbuffer_blocks_device(self, params, n_parts, part, frame_ptrs, multicast=False, halo=False):
         """Fused render + assembly: this rank's 16-row blocks, stored at image positions into every frame in
         `frame_ptrs` (own frame first, then the peers' NVLink mappings) -- or, with multicast=True, into the single
         NVSwitch multicast mapping frame_ptrs[0]."""
         arr = (C.c_void_p * len(frame_ptrs))(*[C.c_void_p(int(q)) for q in frame_ptrs])
-        if multicast:
+        if multicast or halo:
             q = Params.from_buffer_copy(params)
-            q.flags |= FLAG_FRAME0_MULTICAST
+            q.flags |= (FLAG_FRAME0_MULTICAST if multicast else 0) | (FLAG_L_HALO_ONLY if halo else 0)
             params = q
         self._ck(self.lib.srt_render_lbuffer_blocks_device(self.h, C.byref(params), n_parts, part, len(frame_ptrs), arr))
 
@@ -355,7 +356,7 @@ class Context:
         self._ck(self.lib.srt_peer_barrier_device(self.h, n_ranks, rank, arr, epoch, phases))
 
     @staticmethod
-    def frame_call_args(params, frame_ptrs, flag_ptrs, image_ptrs, multicast=False):
+    def frame_call_args(params, frame_ptrs, flag_ptrs, image_ptrs, multicast=False, halo=False):
         """ctypes arguments of render_xray_blocks_device that do not change from frame to frame (build once per
         frame set: the per-frame call is then one foreign call).  frame_ptrs / image_ptrs: own buffer first, then the
         peers' mappings -- or the single multicast mapping with multicast=True."""
@@ -365,6 +366,8 @@ class Context:
         q = Params.from_buffer_copy(params)
         if multicast:
             q.flags |= FLAG_FRAME0_MULTICAST
+        if halo:
+            q.flags |= FLAG_L_HALO_ONLY
         return q, fr, len(frame_ptrs), fl, im, len(image_ptrs)
 
     def render_xray_blocks_device(self, call_args, n_parts, part, epoch, d_own_frame):

@@ -148,19 +148,38 @@ __device__ __forceinline__ CtaCoord cta_coord()
 }
 
 // L output: the launch's own frame plus the extra (peer) frames of a fused multi-GPU assembly.  When L is an NVSwitch
-// multicast mapping the store must be a multimem.st: the switch replicates it into every GPU's frame.
-__device__ __forceinline__ void store_L(const RenderArgs& a, size_t p, float v)
+// multicast mapping the store must be a multimem.st: the switch replicates it into every GPU's frame.  In halo mode
+// (L_halo = repair depth) only the rows the neighbouring ranks' repair stencils reach are sent, and only to those two
+// ranks: the first L_halo rows of a 16-row block to the owner of the block above, the last L_halo rows to the owner of
+// the block below (with all frames replicated to all GPUs, the NVLink receive side bounds an 8-GPU frame).
+__device__ __forceinline__ uint32_t halo_targets(const RenderArgs& a, uint32_t row)
+{
+    const uint32_t rel = row - a.row_begin, lrow = rel & 15u, blk = rel >> 4;
+    const uint32_t last = (a.row_end - a.row_begin - 1) >> 4;
+    return ((lrow < (uint32_t)a.L_halo && blk > 0) ? 1u : 0u) | ((lrow + (uint32_t)a.L_halo >= 16u && blk < last) ? 2u : 0u);
+}
+__device__ __forceinline__ void store_L(const RenderArgs& a, size_t p, uint32_t row, float v)
 {
     if (a.L_multicast) asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(a.L + p), "f"(v) : "memory");
     else a.L[p] = v;
-    for (uint32_t i = 0; i < a.n_L_extra; ++i) a.L_extra[i][p] = v;
+    if (a.L_halo) {
+        const uint32_t t = halo_targets(a, row);
+        if (t & 1u) a.L_extra[0][p] = v;
+        if (t & 2u) a.L_extra[1][p] = v;
+    } else
+        for (uint32_t i = 0; i < a.n_L_extra; ++i) a.L_extra[i][p] = v;
 }
-__device__ __forceinline__ void store_L4(const RenderArgs& a, size_t p, float4 v)      // p % 4 == 0, frames 16-byte aligned
+__device__ __forceinline__ void store_L4(const RenderArgs& a, size_t p, uint32_t row, float4 v)      // p % 4 == 0, frames 16-byte aligned
 {
     if (a.L_multicast)
         asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.L + p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
     else *reinterpret_cast<float4*>(a.L + p) = v;
-    for (uint32_t i = 0; i < a.n_L_extra; ++i) *reinterpret_cast<float4*>(a.L_extra[i] + p) = v;
+    if (a.L_halo) {
+        const uint32_t t = halo_targets(a, row);
+        if (t & 1u) *reinterpret_cast<float4*>(a.L_extra[0] + p) = v;
+        if (t & 2u) *reinterpret_cast<float4*>(a.L_extra[1] + p) = v;
+    } else
+        for (uint32_t i = 0; i < a.n_L_extra; ++i) *reinterpret_cast<float4*>(a.L_extra[i] + p) = v;
 }
 
 // Three-strip box test (filter proof item 7): may any pixel centre of the box hit the triangle?
@@ -255,7 +274,7 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
             if (a.hits) a.hits[p] = hits;
         }
     }
-    if (a.mode == 0) store_L(a, (size_t)(a.L_image ? row : orow) * W + col, L);
+    if (a.mode == 0) store_L(a, (size_t)(a.L_image ? row : orow) * W + col, row, L);
     else { a.dist[(size_t)orow * W + col] = zbuf; a.ssum[(size_t)orow * W + col] = zid; }
     if (AUDIT && a.counters) {
         if (n_viol) atomicAdd(a.counters + 1, n_viol);
@@ -972,7 +991,7 @@ __global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant
         if ((int)lane == src) { L = Lc; dist0 = d0; ssum0 = s0; hits0 = h0; }
     }
     if (!valid) return;
-    if (a.mode != 1) store_L(a, a.L_image ? (size_t)row * W + col : p, L);
+    if (a.mode != 1) store_L(a, a.L_image ? (size_t)row * W + col : p, row, L);
     if (a.dist) a.dist[p] = dist0;
     if (a.ssum) a.ssum[p] = ssum0;
     if (a.hits) a.hits[p] = hits0;
@@ -1323,11 +1342,11 @@ __global__ void __launch_bounds__(128, SRT_CULLED_MIN_CTAS) lbuffer_culled_kerne
         if (a.L_vec4 && col0 + P <= W) {
 #pragma unroll
             for (int k = 0; k < P; k += 4)
-                store_L4(a, out + k, make_float4(Lval[k], Lval[k + 1], Lval[k + 2], Lval[k + 3]));
+                store_L4(a, out + k, row, make_float4(Lval[k], Lval[k + 1], Lval[k + 2], Lval[k + 3]));
         } else {
 #pragma unroll
             for (int k = 0; k < P; ++k)
-                if (col0 + k < W) store_L(a, out + k, Lval[k]);
+                if (col0 + k < W) store_L(a, out + k, row, Lval[k]);
         }
     }
     if (a.counters && n_exact) atomicAdd(a.counters, n_exact);

@@ -53,6 +53,8 @@ struct RenderArgs {
     int L_multicast;         // L is an NVSwitch multicast mapping: stored with multimem.st (plain st to such an address is undefined)
     uint32_t n_L_extra;
     float* L_extra[7];
+    int L_halo;              // > 0: L_extra[0] / L_extra[1] are the frames of the ranks owning the blocks above / below this rank's;
+                             // only the first / last L_halo rows of each 16-row block are stored there (the repair stencil's reach)
     float* dist;             // optional
     int32_t* ssum;           // optional
     uint32_t* hits;          // optional

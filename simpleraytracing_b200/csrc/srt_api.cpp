@@ -349,7 +349,7 @@ bool decode_box(uint32_t v, uint32_t& px, uint32_t& py, uint32_t& k)
 int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint32_t row_end,
                   float* dL, float* d_dist, int32_t* d_ssum, uint32_t* d_hits, uint32_t parts = 0, uint32_t part = 0,
                   int mode = 0, float* const* extra_frames = nullptr, uint32_t n_extra = 0, bool image_positions = false,
-                  bool multicast = false)
+                  bool multicast = false, bool halo = false)
 {
     if (!params) return fail(c, SRT_ERR_INVALID, "params is NULL");
     if (mode != 1 && !dL) return fail(c, SRT_ERR_INVALID, "L buffer is NULL");
@@ -405,6 +405,13 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         aligned = aligned && ((uintptr_t)extra_frames[i] & 15u) == 0;
     }
     a.L_vec4 = aligned ? 1 : 0;                         // 128-bit stores only into 16-byte aligned frames
+    if (halo && parts > 1 && n_extra == parts - 1 && params->repair_depth >= 1 && params->repair_depth <= 16) {
+        // extra_frames lists the peers in rank order (own rank skipped): keep the owners of the blocks above / below only
+        const uint32_t prev = (part + parts - 1) % parts, next = (part + 1) % parts;
+        a.L_extra[0] = extra_frames[prev < part ? prev : prev - 1];
+        a.L_extra[1] = extra_frames[next < part ? next : next - 1];
+        a.n_L_extra = 2; a.L_halo = (int)params->repair_depth;
+    }
     a.box_px = box_px; a.box_py = box_py; a.scan_k = scan_k;
     a.counters = nullptr;
     if (c->count_exact || audit) {
@@ -930,10 +937,12 @@ int srt_render_lbuffer_blocks_device(srt_ctx* c, const srt_params* p, uint32_t n
         if (!d_frames[i]) return fail(c, SRT_ERR_INVALID, "frame pointer %u is NULL", i);
     if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
     SRT_CUDA(c, cudaSetDevice(c->device));
-    const bool multicast = (p && (p->flags & SRT_FLAG_FRAME0_MULTICAST) != 0);
-    if (multicast && n_frames != 1) return fail(c, SRT_ERR_INVALID, "a multicast mapping is the only frame of the call");
+    // a single pointer with SRT_FLAG_FRAME0_MULTICAST is a multicast mapping; n_parts pointers (own + every peer) with
+    // SRT_FLAG_L_HALO_ONLY send only the repair stencil's halo rows, and only to the two neighbouring ranks
+    const bool multicast = (p && (p->flags & SRT_FLAG_FRAME0_MULTICAST) != 0) && n_frames == 1;
+    const bool halo = (p && (p->flags & SRT_FLAG_L_HALO_ONLY) != 0) && n_frames == n_parts && n_parts > 1;
     return render_device(c, p, 0, c->camera.height, d_frames[0], nullptr, nullptr, nullptr, n_parts, part, 0,
-                         d_frames + 1, n_frames - 1, /*image_positions*/ true, multicast);
+                         d_frames + 1, n_frames - 1, /*image_positions*/ true, multicast, halo);
 }
 
 int srt_deinterleave_device(srt_ctx* c, uint32_t n_parts, const float* d_slots, float* d_frame)
@@ -971,8 +980,7 @@ int srt_repair_blocks_device(srt_ctx* c, const srt_params* p, uint32_t n_parts, 
     if (n_parts == 0 || part >= n_parts) return fail(c, SRT_ERR_INVALID, "part %u of %u", part, n_parts);
     if (n_images == 0 || n_images > 8 || !d_images) return fail(c, SRT_ERR_INVALID, "1 to 8 image pointers expected");
     if (!c->have_camera) return fail(c, SRT_ERR_INVALID, "srt_set_camera has not been called");
-    const bool multicast = (p->flags & SRT_FLAG_FRAME0_MULTICAST) != 0;
-    if (multicast && n_images != 1) return fail(c, SRT_ERR_INVALID, "a multicast mapping is the only image of the call");
+    const bool multicast = (p->flags & SRT_FLAG_FRAME0_MULTICAST) != 0 && n_images == 1;
     srt::RepairOut out{};
     bool aligned = (c->camera.width & 3u) == 0;
     for (uint32_t i = 0; i < n_images; ++i) {

@@ -18,7 +18,7 @@ FLAG_WORDS = 64
 class FakeRanks:
     """n_ranks x lanes contexts on cuda:0 with frames / images / flags laid out like bands.PeerLanes"""
 
-    def __init__(self, srtlib, meshes, cam, n_ranks, lanes, params):
+    def __init__(self, srtlib, meshes, cam, n_ranks, lanes, params, halo=False):
         import torch
         self.torch = torch
         self.n, self.lanes, self.W, self.H = n_ranks, lanes, cam.width, cam.height
@@ -30,6 +30,7 @@ class FakeRanks:
         self.streams = [[torch.cuda.Stream(device=dev) for _ in range(lanes)] for _ in range(n_ranks)]
         self.epoch = [0] * lanes
         self.params = params
+        self.halo = halo                                 # SRT_FLAG_L_HALO_ONLY: L rows go to the neighbouring ranks only
         for r in range(n_ranks):
             for l in range(lanes):
                 c = self.ctx[r][l]
@@ -56,7 +57,7 @@ class FakeRanks:
         s = e & 1
         flags = [self.buf[q, l, 4 * self.px:].data_ptr() for q in range(self.n)]
         for r in order:
-            self.ctx[r][l].render_lbuffer_blocks_device(self.params, self.n, r, self.ptrs(r, l, s))
+            self.ctx[r][l].render_lbuffer_blocks_device(self.params, self.n, r, self.ptrs(r, l, s), halo=self.halo)
         for r in order:
             self.ctx[r][l].peer_barrier_device(self.n, r, flags, 2 * e - 1, phases=1)
         for r in order:
@@ -77,15 +78,16 @@ class FakeRanks:
                 c.close()
 
 
-@pytest.mark.parametrize("kernel,n_ranks,lanes", [(KERNEL_FILTERED, 2, 1), (KERNEL_FILTERED, 4, 3), (KERNEL_CULLED, 3, 2)])
-def test_sharded_pipeline_equals_the_unsharded_render(gpu_ctx, srtlib, dragon, kernel, n_ranks, lanes):
+@pytest.mark.parametrize("kernel,n_ranks,lanes,halo", [(KERNEL_FILTERED, 2, 1, False), (KERNEL_FILTERED, 4, 3, True), (KERNEL_CULLED, 3, 2, True),
+                                                       (KERNEL_FILTERED, 2, 2, True), (KERNEL_CULLED, 8, 1, True)])
+def test_sharded_pipeline_equals_the_unsharded_render(gpu_ctx, srtlib, dragon, kernel, n_ranks, lanes, halo):
     import torch
     lo, hi = srtlib.scene_bbox([(dragon, MU0)])
     cam = srtlib.camera_from_bbox(lo, hi, 600, 410)
     p = srtlib.default_params(kernel=kernel)
     gpu_ctx.set_meshes([(dragon, MU0)]); gpu_ctx.set_camera(cam)
     want = torch.from_numpy(gpu_ctx.render_xray(p).view(np.int32)).cuda()
-    fr = FakeRanks(srtlib, [(dragon, MU0)], cam, n_ranks, lanes, p)
+    fr = FakeRanks(srtlib, [(dragon, MU0)], cam, n_ranks, lanes, p, halo=halo)
     for rnd in range(3):
         fr.poison()
         torch.cuda.synchronize()
