@@ -663,6 +663,22 @@ def run_ours(args):
             if cnt.get("width") == W and cnt.get("n_gpus", 1) == world:
                 roof["traffic"] = cnt.get("dram_bytes")              # dram__bytes_read.sum + dram__bytes_write.sum, this launch shape
             roof["algorithmic_bytes"] = 4.0 * my_rows * W             # the L-buffer rows this launch produces
+        # the whole frame: the six kernels of a frame together (warp instructions from the same ncu capture) over the measured,
+        # pipelined time per frame -- how much of the GPU's issue capacity the steady state uses
+        try:
+            caps = [c for c in json.loads(COUNTERS.read_text()).get("captures", [])
+                    if c.get("width") == W and c.get("n_gpus", 1) == 1 and c.get("box") == (cnt or {}).get("box")]
+            if world == 1 and kernel_used == KERNEL_FILTERED and caps:
+                frame_inst = float(sum(c["warp_inst"] for c in caps))
+                per_frame_s = total_ms / steps / B * 1e-3
+                roof["frame"] = {"kernels": {c["kernel"]: {"us_cold_serialised": round(c["duration_us"], 1), "warp_inst": c["warp_inst"],
+                                                           "ipc_per_sm": c["ipc_per_sm"]} for c in caps},
+                                 "warp_inst_per_frame": frame_inst, "achieved": frame_inst / per_frame_s / 1e9,
+                                 "frac": frame_inst / per_frame_s / 1e9 / issue_peak,
+                                 "note": "all kernels of a frame / measured pipelined time per frame; unit and peak as above"}
+                roof["kernel_share_of_frame"] = next((c["duration_us"] for c in caps if c["kernel"] == kname), 0.0) / sum(c["duration_us"] for c in caps)
+        except Exception:
+            pass
         # secondary: the reference's u-stage costed at 19 flop per test against the measured FFMA peak; the
         # kernel decides that stage with far fewer instructions, so this is an equivalence figure, not a fraction of peak
         roof["fp32_equivalent"] = {"flop_per_test": F_ALG, "equivalent_tflops": band_tests * F_ALG / kt / 1e12,
