@@ -318,6 +318,14 @@ __global__ void __launch_bounds__(128) lbuffer_exact_kernel(const __grid_constan
 //    so the result does not depend on which thread or chunk found a hit: bit-identical to the serial loop.
 // If a candidate list overflows (adversarial scenes; the host grows it for the next frame), resolve recomputes every
 // pixel with the exact sequence: slow, never wrong.
+// occupancy targets of the latency-bound exact-test and resolve kernels (CTAs per SM; the register cap follows: 40 registers,
+// a few spills, 3 / 2 us faster; the candidates kernel lost 2 us the same way and keeps its 56 registers)
+#ifndef SRT_RESOLVE_MIN_CTAS
+#define SRT_RESOLVE_MIN_CTAS 6
+#endif
+#ifndef SRT_EXACT_MIN_CTAS
+#define SRT_EXACT_MIN_CTAS 12
+#endif
 constexpr uint32_t kStageCap = 256, kStageFlush = 128;
 constexpr uint32_t kNoHit = 0xffffffffu;       // empty list head / end of a pixel's hit list
 
@@ -654,7 +662,7 @@ __global__ void __launch_bounds__(128) candidates_kernel(const __grid_constant__
 // Stage 3, one candidate {pixel, triangle} per thread (grid-stride): ray generation with both normalisations,
 // Ray::intersect's exact sequence, sign test; accepted intersections are appended to the pixel's hit list through an
 // atomic slot counter.
-__global__ void __launch_bounds__(128) exact_tests_kernel(const __grid_constant__ RenderArgs a)
+__global__ void __launch_bounds__(128, SRT_EXACT_MIN_CTAS) exact_tests_kernel(const __grid_constant__ RenderArgs a)
 {
     const uint32_t W = a.cam.W;
     const uint32_t n = min(a.cand_count[1], a.pix_cap);
@@ -902,7 +910,7 @@ __device__ __forceinline__ PixelOut resolve_list(const RenderArgs& a, uint32_t h
     return { L, dist0, ssum0, hits0 };
 }
 
-__global__ void __launch_bounds__(256) resolve_hits_kernel(const __grid_constant__ RenderArgs a)
+__global__ void __launch_bounds__(256, SRT_RESOLVE_MIN_CTAS) resolve_hits_kernel(const __grid_constant__ RenderArgs a)
 {
     __shared__ float s_sort[8][kSortOverflowCap];
     __shared__ PixelOut s_none;                              // outputs of a pixel no triangle touches (~70 % of a frame): computed once
