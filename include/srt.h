@@ -287,10 +287,12 @@ int  srt_render_xray_sorted_device(srt_ctx* ctx, const srt_params* params, float
 /* ---- one process, N GPUs (replaces the MPI driver, src/main-mpi.cxx:258-293 partition + :854-881 gather) ----
  *
  * srt_multi owns one context per device.  A frame is rendered in block-cyclic 16-row blocks (device i renders blocks
- * i, i + N, ...); every render kernel stores its L values straight into the frame of EVERY device over NVLink peer
- * mappings (cudaDeviceEnablePeerAccess), cross-device events order the renders before the repair passes, and each
- * device ends up with the complete, repaired image -- bit-identical to a single-GPU render.  Scene and camera are
- * replicated.  Requires peer access between all the devices (an NVLink / NVSwitch box); 1 <= n_devices <= 8.
+ * i, i + N, ...); every render kernel stores its L rows into its own frame and the rows the neighbours' repair stencils
+ * reach into the frames of the two neighbouring devices over NVLink peer mappings (cudaDeviceEnablePeerAccess);
+ * cross-device events order the renders before the sharded repair passes (each device repairs its own blocks and stores
+ * them into the image of EVERY device), and a second event barrier ends the frame: each device ends up with the
+ * complete, repaired image -- bit-identical to a single-GPU render.  Scene and camera are replicated.  Requires peer
+ * access between all the devices (an NVLink / NVSwitch box); 1 <= n_devices <= 8.
  */
 typedef struct srt_multi srt_multi;
 int  srt_multi_create(srt_multi** out, const int* device_ids, int n_devices);
@@ -300,7 +302,8 @@ int  srt_multi_device_count(const srt_multi* m);
 int  srt_multi_set_meshes(srt_multi* m, int n_meshes, const srt_mesh_desc* meshes);
 int  srt_multi_set_camera(srt_multi* m, const srt_camera* cam);
 /* Render + assemble + repair on all devices; asynchronous.  After srt_multi_synchronize the device pointers returned
- * by srt_multi_frame hold the pre-repair L-buffer and the repaired image of the LAST render on every device. */
+ * by srt_multi_frame hold, for the LAST render, the complete repaired image (d_image, on every device) and the device's
+ * part of the pre-repair L-buffer (d_L: its own blocks plus the neighbours' halo rows; complete only with one device). */
 int  srt_multi_render_xray_device(srt_multi* m, const srt_params* params);
 int  srt_multi_synchronize(srt_multi* m);
 int  srt_multi_frame(srt_multi* m, int index, float** d_L, float** d_image);

@@ -1457,7 +1457,7 @@ struct srt_multi {
     std::vector<srt_ctx*> ctx;
     std::vector<float*> L[2];            // two frame sets used alternately (one cross-device barrier per step suffices)
     std::vector<float*> img;
-    std::vector<cudaEvent_t> ev_start, ev_rendered, ev_end;
+    std::vector<cudaEvent_t> ev_start, ev_rendered, ev_repaired, ev_end;
     size_t frame_cap = 0;
     unsigned step = 0;
     bool have_camera = false; uint32_t W = 0, H = 0;
@@ -1546,12 +1546,14 @@ int srt_multi_create(srt_multi** out, const int* device_ids, int n_devices)
             cudaGetLastError();                                    // clear "already enabled"
         }
     }
-    m->ev_start.assign(n_devices, nullptr); m->ev_rendered.assign(n_devices, nullptr); m->ev_end.assign(n_devices, nullptr);
+    m->ev_start.assign(n_devices, nullptr); m->ev_rendered.assign(n_devices, nullptr); m->ev_repaired.assign(n_devices, nullptr);
+    m->ev_end.assign(n_devices, nullptr);
     m->L[0].assign(n_devices, nullptr); m->L[1].assign(n_devices, nullptr); m->img.assign(n_devices, nullptr);
     for (int i = 0; i < n_devices; ++i) {
         cudaSetDevice(device_ids[i]);
         if (cudaEventCreate(&m->ev_start[i]) != cudaSuccess || cudaEventCreate(&m->ev_end[i]) != cudaSuccess ||
-            cudaEventCreateWithFlags(&m->ev_rendered[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&m->ev_rendered[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_repaired[i], cudaEventDisableTiming) != cudaSuccess) {
             srt_multi_destroy(m);
             return mfail(nullptr, SRT_ERR_CUDA, "event creation failed on device %d", device_ids[i]);
         }
@@ -1569,6 +1571,7 @@ void srt_multi_destroy(srt_multi* m)
         cudaSetDevice(m->dev[i]);
         if (m->ev_start[i]) cudaEventDestroy(m->ev_start[i]);
         if (m->ev_rendered[i]) cudaEventDestroy(m->ev_rendered[i]);
+        if (i < m->ev_repaired.size() && m->ev_repaired[i]) cudaEventDestroy(m->ev_repaired[i]);
         if (m->ev_end[i]) cudaEventDestroy(m->ev_end[i]);
     }
     for (srt_ctx* c : m->ctx) srt_destroy(c);
@@ -1618,25 +1621,37 @@ int srt_multi_render_xray_device(srt_multi* m, const srt_params* params)
     int rc = multi_ensure_frames(m, (size_t)m->W * m->H);
     if (rc) return rc;
     const unsigned set = m->step & 1u;
-    // 1. every device renders its blocks into the frame of every device
+    // 1. every device renders its blocks: L rows into its own frame, the rows the neighbouring devices' repair stencils
+    //    reach (the first / last repair_depth rows of a block) also into those devices' frames over NVLink
     for (int i = 0; i < m->n; ++i) {
         srt_ctx* c = m->ctx[i];
         SRT_MCUDA(m, cudaSetDevice(m->dev[i]));
         SRT_MCUDA(m, cudaEventRecord(m->ev_start[i], c->stream));
         float* peers[7]; uint32_t np = 0;
-        for (int j = 0; j < m->n; ++j) if (j != i) peers[np++] = m->L[set][j];
+        for (int j = 0; j < m->n; ++j) if (j != i) peers[np++] = m->L[set][j];      // rank order, own skipped
         rc = render_device(c, params, 0, m->H, m->L[set][i], nullptr, nullptr, nullptr, (uint32_t)m->n, (uint32_t)i, 0,
-                           np ? peers : nullptr, np, /*image_positions*/ true, /*multicast*/ false);
+                           np ? peers : nullptr, np, /*image_positions*/ true, /*multicast*/ false, /*halo*/ np > 0);
         if (rc) return mfail(m, rc, "device %d: %s", m->dev[i], c->error.c_str());
         SRT_MCUDA(m, cudaEventRecord(m->ev_rendered[i], c->stream));
     }
-    // 2. cross-device barrier (events), then the repair pass on every device's own, now complete, frame
+    // 2. cross-device barrier (events), then the sharded repair pass: every device repairs the pixels of its own blocks and
+    //    stores them into the image of every device
     for (int i = 0; i < m->n; ++i) {
         srt_ctx* c = m->ctx[i];
         SRT_MCUDA(m, cudaSetDevice(m->dev[i]));
         for (int j = 0; j < m->n; ++j) if (j != i) SRT_MCUDA(m, cudaStreamWaitEvent(c->stream, m->ev_rendered[j], 0));
-        rc = srt_repair_device(c, params, m->L[set][i], m->img[i]);
+        float* images[8]; uint32_t ni = 0;
+        images[ni++] = m->img[i];
+        for (int j = 0; j < m->n; ++j) if (j != i) images[ni++] = m->img[j];
+        rc = srt_repair_blocks_device(c, params, (uint32_t)m->n, (uint32_t)i, m->L[set][i], ni, images);
         if (rc) return mfail(m, rc, "device %d: %s", m->dev[i], c->error.c_str());
+        SRT_MCUDA(m, cudaEventRecord(m->ev_repaired[i], c->stream));
+    }
+    // 3. second barrier: every device's image is complete when all repair passes have run
+    for (int i = 0; i < m->n; ++i) {
+        srt_ctx* c = m->ctx[i];
+        SRT_MCUDA(m, cudaSetDevice(m->dev[i]));
+        for (int j = 0; j < m->n; ++j) if (j != i) SRT_MCUDA(m, cudaStreamWaitEvent(c->stream, m->ev_repaired[j], 0));
         SRT_MCUDA(m, cudaEventRecord(m->ev_end[i], c->stream));
     }
     ++m->step;
