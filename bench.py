@@ -469,8 +469,7 @@ def run_ours(args):
     kern_ms, pass_ms = [], []
     for _ in range(max(3, min(steps, 10))):
         flush.fill_(1)
-        if world > 1:
-            barrier()
+        barrier()                                  # the flush has finished (it runs on the main stream, the frame on the lane's)
         lane_frame(lanes[0])
         tm = ctx.timing()
         kern_ms.append(tm.main_kernel_ms); pass_ms.append(tm.render_ms)
