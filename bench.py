@@ -2,31 +2,37 @@
 """bench.py -- headline benchmark of the X-ray L-buffer hot path.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5] [--impl ours|reference]
+                  [--lanes L] [--frames-per-step B] [--l-exchange halo|all] [--assembly auto|p2p|allgather]
 
 Workloads (BASELINE.json configs):
   c3 (default, the configuration the metric is quoted on): dragon (22 866 triangles), 2048 x 2048
   c2: dragon, 1024 x 1024       c4: logo quad only (2 triangles), 1512 x 1512 (latency / memory bound)
   c5: synthetic 998 000-triangle sphere, 8192 x 8192
-A step is ONE frame: L-buffer render + Beer-Lambert attenuation (block-cyclic 16-row blocks over the ranks at N > 1,
-each rank's kernels storing straight into every rank's frame over NVLink) -> artefact repair on the assembled frame.
-The frame is a fixed amount of work sharded over the ranks: scaling = "strong".
+A FRAME is: L-buffer render + Beer-Lambert attenuation (block-cyclic 16-row blocks over the ranks at N > 1: L halo rows
+to the neighbouring ranks by peer stores, device barrier, sharded artefact repair whose rows go to every rank's image
+over NVLink / NVSwitch multicast, device barrier) -> the repaired image on every rank.
+A STEP is a batch of B frames of the workload, issued round-robin on L lanes (an srt context + a stream + buffers each)
+so that the latency-bound tail of one frame overlaps the scan of the next; every frame does all of its work inside the
+timed region.  The frame is a fixed amount of work sharded over the ranks: scaling = "strong".
 
 Keys of the JSON line (see the task contract):
-  value        whole-job ray-triangle tests/s, scene + frame buffers resident in HBM, brute-force kernel
-               (SRT_KERNEL_FILTERED: every thread visits every triangle, every (ray, triangle) pair is decided
-               by a proven-conservative reject or the reference's exact sequence)
-  e2e          N = 1: the same frame through the host-pointer plugin call a reference user makes --
+  value        whole-job ray-triangle tests/s (tests of B x K frames / time of K steps), scene + frame buffers resident
+               in HBM, brute-force kernel (SRT_KERNEL_FILTERED: every box of pixels meets every triangle, every
+               (ray, triangle) pair is decided by a proven-conservative reject or the reference's exact sequence)
+  ms_per_frame = ms_per_step / frames_per_step;  single_frame_ms = one frame with no other frame in flight
+  e2e          N = 1: one frame through the host-pointer plugin call a reference user makes --
                srt_set_meshes(host vertices) + srt_set_camera + srt_render_xray(ordinary host image buffer) --
                timed by the wall clock around the synchronous calls; `pinned` repeats it with srt_host_alloc
                buffers.  N > 1 (one process per GPU): upload + sharded render + assembly + repair + image to host.
-  roofline     the dominant kernel is bound by the SM's instruction issue rate (no tensor-core or HBM roof applies:
-               0.3 % of the HBM roof): achieved = warp instructions / s (instructions per test from the committed
-               ncu capture x tests of the launch / kernel time by CUDA events), peak = 4 issue slots x SMs x the
-               SM clock sampled under load.  The FP32 figure SURVEY 8d asks for is kept as `fp32_equivalent`.
+  roofline     the kernels are bound by the SM's instruction issue rate (no tensor-core or HBM roof applies):
+               achieved = warp instructions / s of the scan kernel (instructions per test from the committed ncu
+               capture x tests of the launch / kernel time by CUDA events, the kernel alone), peak = 4 issue slots x
+               SMs x the SM clock sampled under load; `frame` = the same for all kernels of a frame over the measured
+               pipelined time per frame.  The FP32 figure SURVEY 8d asks for is kept as `fp32_equivalent`.
   cpu_baseline the reference's CPU implementation (oracle/_ref, else the oracle port) on a bounded sample of the same
                frame on the host cores (rank 0, N = 1 only)
-  accelerated  the same frame through SRT_KERNEL_AUTO, the library's default (hierarchical conservative culling;
-               identical results)
+  accelerated  the same frames through SRT_KERNEL_CULLED (hierarchical conservative culling; identical results; what
+               SRT_KERNEL_AUTO selects for meshes of more than ~2e5 triangles)
 
 --impl reference times that CPU implementation as the bench arm itself.
 """

@@ -18,11 +18,11 @@
  *   repair + Image::setPixel loop         ...lbuffer.cxx:329-404        srt_repair
  *   initialiseRayTracing / getBBox        ...lbuffer.cxx:585-667        srt_scene_bbox + srt_camera_from_bbox
  *   pthreadWorkLoadAllocation             ...lbuffer.cxx:694-725        srt_partition_rows
- *   MPI gather of pixel ranges            src/main-mpi.cxx:854-881      srt_multi_* (one process, N GPUs: the render
- *                                                                       kernels store into every GPU's frame over
- *                                                                       NVLink) or, one process per GPU,
- *                                                                       srt_render_lbuffer_blocks_device on
- *                                                                       peer-mapped frames
+ *   MPI gather of pixel ranges            src/main-mpi.cxx:854-881      srt_multi_* (one process, N GPUs) or, one
+ *                                                                       process per GPU, srt_render_xray_blocks_device
+ *                                                                       on peer-mapped buffers: the kernels store the
+ *                                                                       rows other GPUs need over NVLink, device-side
+ *                                                                       barriers in between
  *   renderLoop(Image&, meshes, detector, origin, up, right, Light)      srt_render_shaded
  *              src/main-omp.cxx:136-142,588-797
  *

@@ -1,16 +1,19 @@
-"""Row-band sharding of one frame over N ranks and its assembly with ONE all_gather.
+"""Sharding of one frame over N ranks (one process per GPU) and the buffers of its assembly.
 
-The reference's only communication step is a gather of contiguous pixel ranges to rank 0 with
-blocking MPI_Send/MPI_Recv (src/main-mpi.cxx:258-293, 854-881).  Here every rank renders the rows
-`rows` of its band straight into the full-frame buffer and a single in-place all_gather (NCCL over
-NVLink on the GPUs, gloo in the CPU tests) leaves the whole frame on every rank, so the +-4-pixel
-repair stencil (main-pthreads-lbuffer.cxx:329-404) can run after assembly and results do not
-depend on N.
+The reference's only communication step is a gather of contiguous pixel ranges to rank 0 with blocking
+MPI_Send/MPI_Recv (src/main-mpi.cxx:258-293, 854-881).  Here:
 
-Partition rule: H / N rows each, the first H % N ranks get one more
-(pthreadWorkLoadAllocation, main-pthreads-lbuffer.cxx:694-725; rows variant
-main-pthreads-rows.cxx:312-334).  all_gather needs equal counts, so when N does not divide H the
-frame buffer is padded: bands are gathered in slots of ceil(H/N) rows and compacted afterwards.
+* `PeerLanes` -- the product path: L frames, images and barrier flags of all ranks in peer-mapped (symmetric) memory;
+  the library's kernels store into them directly (srt_render_xray_blocks_device), nothing is gathered afterwards.
+* `BandLayout` / `InterleavedLayout` -- the fallback without peer mappings (and what the gloo CPU tests cover): every
+  rank renders its rows into a full-frame or slot buffer and a single in-place all_gather (NCCL over NVLink on the
+  GPUs, gloo in the CPU tests) leaves the whole frame on every rank, so the +-4-pixel repair stencil
+  (main-pthreads-lbuffer.cxx:329-404) can run after assembly and results do not depend on N.
+
+Band partition rule: H / N rows each, the first H % N ranks get one more (pthreadWorkLoadAllocation,
+main-pthreads-lbuffer.cxx:694-725; rows variant main-pthreads-rows.cxx:312-334).  all_gather needs equal counts, so
+when N does not divide H the frame buffer is padded: bands are gathered in slots of ceil(H/N) rows and compacted
+afterwards.
 """
 import torch
 import torch.distributed as dist
@@ -94,45 +97,6 @@ class InterleavedLayout:
             if rows:
                 out[torch.tensor(rows)] = s[r, : len(rows)]
         return out.view(-1)
-
-
-class PeerFrames:
-    """Full-frame buffers of all ranks of one node mapped into every rank's address space (NVLink peer memory,
-    `torch.distributed._symmetric_memory`), for the fused render + assembly of srt_render_lbuffer_blocks_device:
-    the render kernel stores each L value into every rank's frame, so the frame is complete on every GPU when the
-    kernels have finished -- no all_gather, no de-interleave pass.
-
-    `pointers()` is what the C ABI takes: [own frame] + [NVSwitch multicast mapping] when the fabric offers one
-    (a single store is replicated to every GPU by the switch), else [own frame] + [each peer's frame].
-    `barrier()` is a device-side barrier over the ranks on the current stream: after it, every rank's stores
-    have landed in this rank's frame.
-    """
-
-    def __init__(self, H, W, group=None, use_multicast=True):
-        import torch.distributed._symmetric_memory as symm_mem
-        self.H, self.W = H, W
-        group = group if group is not None else dist.group.WORLD
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.frame = symm_mem.empty(H * W, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
-        self.handle = symm_mem.rendezvous(self.frame, group)
-        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        mc = 0
-        if use_multicast:
-            try:
-                mc = int(self.handle.multicast_ptr)
-            except Exception:
-                mc = 0
-        self.multicast_ptr = mc
-
-    def pointers(self):
-        """-> (frame pointers for srt_render_lbuffer_blocks_device, is_multicast)"""
-        own = self.peer_ptrs[self.rank]
-        if self.multicast_ptr:
-            return [self.multicast_ptr], True    # the switch replicates the (multimem) store to every GPU, this one included
-        return [own] + [p for r, p in enumerate(self.peer_ptrs) if r != self.rank], False
-
-    def barrier(self):
-        self.handle.barrier(channel=0)
 
 
 class PeerLanes:
