@@ -1816,8 +1816,17 @@ cudaError_t launch_ffma_peak(float* scratch, int blocks, int iters, cudaStream_t
 // i.e. when every rank's rows have landed in this rank's frame.  One CTA: a waiting barrier never occupies more than
 // one CTA slot, so barriers of several frames in flight (one per stream) cannot starve the kernels they wait for.
 // phases: bit 0 = signal, bit 1 = wait (3 = the whole barrier in one launch).
-__global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerFlags f, uint32_t n, uint32_t rank, uint32_t epoch, uint32_t phases)
+// ctr != nullptr: the epoch is the next value of a counter in device memory (one barrier at a time uses it: barriers on a
+// set of flags are ordered by their stream), so that a captured CUDA graph of a frame can be replayed as it is.
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerFlags f, uint32_t n, uint32_t rank, uint32_t epoch, uint32_t phases,
+                                                          uint32_t* ctr)
 {
+    __shared__ uint32_t s_epoch;
+    if (ctr) {
+        if (threadIdx.x == 0) { s_epoch = *ctr + 1; *ctr = s_epoch; }
+        __syncthreads();
+        epoch = s_epoch;
+    }
     const uint32_t j = threadIdx.x;
     if (j >= n || j == rank) return;
     __threadfence_system();
@@ -1831,10 +1840,10 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerFlags f, uin
     }
 }
 
-cudaError_t launch_peer_barrier(const PeerFlags& f, uint32_t n, uint32_t rank, uint32_t epoch, uint32_t phases, cudaStream_t s)
+cudaError_t launch_peer_barrier(const PeerFlags& f, uint32_t n, uint32_t rank, uint32_t epoch, uint32_t phases, uint32_t* ctr, cudaStream_t s)
 {
     if (n <= 1) return cudaSuccess;
-    peer_barrier_kernel<<<1, 32, 0, s>>>(f, n, rank, epoch, phases);
+    peer_barrier_kernel<<<1, 32, 0, s>>>(f, n, rank, epoch, phases, ctr);
     return cudaGetLastError();
 }
 

@@ -181,7 +181,9 @@ cudaError_t launch_deinterleave(const float* slots, float* frame, uint32_t W, ui
 struct PeerFlags { uint32_t* p[8]; };
 // phases: 1 = signal only, 2 = wait only, 3 = both (a caller that drives several ranks from one thread enqueues all the
 // signals before the first wait)
-cudaError_t launch_peer_barrier(const PeerFlags& f, uint32_t n, uint32_t rank, uint32_t epoch, uint32_t phases, cudaStream_t s);
+// epoch_ctr != nullptr: the barrier's epoch is ++(*epoch_ctr) (device memory) instead of `epoch`
+cudaError_t launch_peer_barrier(const PeerFlags& f, uint32_t n, uint32_t rank, uint32_t epoch, uint32_t phases, uint32_t* epoch_ctr,
+                                cudaStream_t s);
 // Artefact repair + image fill (lbuffer.cxx:329-404).
 cudaError_t launch_repair(const float* L, float* image, uint32_t W, uint32_t H, uint32_t depth, cudaStream_t s);
 // Sharded repair: the pixels of the 16-row blocks part, part + n_parts, ... of the frame, stored into `image` (a multicast

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -122,6 +123,15 @@ struct srt_ctx {
     int cnt_parity = 0;                  // which pair of the double-buffered list counters (d_cand_count[4]) is clean
     uint32_t scan_max_ctas = 0;          // cap on the scan's resident CTAs per SM (0 = none; srt_set_scan_residency)
     bool profiling = true;               // record the per-render timing events (srt_set_profiling)
+    // one frame of the sharded pipeline (srt_render_xray_blocks_device) as a CUDA graph: the call's launches are captured the
+    // second time a call signature comes round in the steady state and replayed from then on (a rank's share of an 8-GPU frame
+    // is ~40 us of device work behind ~8 launches: the host's launch cost was the bound)
+    struct FrameGraph { std::vector<uint64_t> sig; uint32_t steady_runs = 0; uint64_t lists_key_after = 0; bool flips_parity = false; cudaGraphExec_t exec = nullptr; };
+    std::vector<FrameGraph> frame_graphs;
+    uint64_t pack_serial = 0;            // bumped whenever the packed arrays are rebuilt (new scene / camera / box shape)
+    bool verified_last_render = false;   // the last render_device call waited for list counts (first render of a launch geometry)
+    uint32_t* d_barrier_ctr = nullptr;   // epoch counter of the fused call's barriers (device memory), mirrored in barrier_epochs
+    uint64_t barrier_epochs = 0;
     int force_scan_cols = 0;             // diagnostic override of the box columns per CTA: 0 = heuristic
     uint32_t force_bin_cap = 0, force_cand_cap = 0, force_pix_cap = 0;    // diagnostic: shrink the lists to exercise the overflow paths
     // per-bin triangle lists of the culled kernel
@@ -326,7 +336,7 @@ int pack_scene(srt_ctx* c, uint32_t box_px = SRT_BOX_PX, uint32_t box_py = SRT_B
         SRT_CUDA(c, cudaMalloc(&c->d_shade_meshes, nm * sizeof(srt::ShadeMesh))); c->shade_cap = nm;
     }
     SRT_CUDA(c, cudaMemcpyAsync(c->d_shade_meshes, c->h_shade.data(), nm * sizeof(srt::ShadeMesh), cudaMemcpyHostToDevice, c->stream));
-    c->packed = true; c->box_px = box_px; c->box_py = box_py; c->scan_k = scan_k;
+    c->packed = true; c->box_px = box_px; c->box_py = box_py; c->scan_k = scan_k; ++c->pack_serial;
     c->lists_key = 0;                                       // new scene / camera: the work-list sizes are unverified again
     return SRT_OK;
 }
@@ -539,6 +549,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
         if (c->n_meshes > 32 || c->total_tris >= (1ull << 27)) kernel = SRT_KERNEL_EXACT;     // candidate entries: 5-bit mesh, 27-bit triangle
     }
     const bool prof = c->profiling;
+    c->verified_last_render = repack;
     if (prof) SRT_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     if (kernel == SRT_KERNEL_FILTERED) {
         // launch geometry the list sizes were verified for (scene / camera changes reset it through `packed`)
@@ -546,6 +557,7 @@ int render_device(srt_ctx* c, const srt_params* params, uint32_t row_begin, uint
                              ((uint64_t)mode << 2) ^ (all ? 2u : 0u) ^ ((uint64_t)box_px << 52) ^ ((uint64_t)box_py << 58) ^ 1u;
         const bool forced = c->force_cand_cap || c->force_pix_cap;              // tests exercise the overflow fallback
         const bool verify = !forced && (repack || c->lists_key != key);
+        c->verified_last_render = verify;
         // does launch_lbuffer_filtered launch anything?  (an empty launch touches no counter: the pairs keep their roles)
         const bool launches = !(a.row_end <= a.row_begin || a.cam.W == 0 || a.n_blocks == 0 || a.scan_chunks == 0);
         if (!verify && !forced) { a.cand_hint = c->verified_cand; a.pix_hint = c->verified_pix; a.big_hint = c->verified_big; }
@@ -664,6 +676,9 @@ void srt_destroy(srt_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_scene(c); free_frame(c);
+    for (auto& g : c->frame_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    c->frame_graphs.clear();
+    cudaFree(c->d_barrier_ctr);
     cudaFree(c->d_counters);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -968,7 +983,7 @@ int srt_peer_barrier_device(srt_ctx* c, uint32_t n_ranks, uint32_t rank, uint32_
         f.p[j] = d_flags[j];
     }
     SRT_CUDA(c, cudaSetDevice(c->device));
-    SRT_CUDA(c, srt::launch_peer_barrier(f, n_ranks, rank, epoch, phases, c->stream));
+    SRT_CUDA(c, srt::launch_peer_barrier(f, n_ranks, rank, epoch, phases, nullptr, c->stream));
     return SRT_OK;
 }
 
@@ -996,21 +1011,130 @@ int srt_repair_blocks_device(srt_ctx* c, const srt_params* p, uint32_t n_parts, 
     return SRT_OK;
 }
 
+} // extern "C"
+
+namespace {
+
+// The launches of one sharded frame: render of the rank's blocks -> barrier -> sharded repair -> barrier, the barriers taking
+// their epochs from the context's device counter.
+int frame_sequence(srt_ctx* c, const srt_params* p, uint32_t n_parts, uint32_t part, uint32_t n_frames, float* const* d_frames,
+                   uint32_t* const* d_flags, const float* d_own_frame, uint32_t n_images, float* const* d_images)
+{
+    int rc = srt_render_lbuffer_blocks_device(c, p, n_parts, part, n_frames, d_frames);
+    if (rc) return rc;
+    srt::PeerFlags f{};
+    for (uint32_t j = 0; j < n_parts && n_parts > 1; ++j) f.p[j] = d_flags[j];
+    // barrier 1: every rank's rows have landed in this rank's L frame
+    if (n_parts > 1) SRT_CUDA(c, srt::launch_peer_barrier(f, n_parts, part, 0, 3, c->d_barrier_ctr, c->stream));
+    rc = srt_repair_blocks_device(c, p, n_parts, part, d_own_frame, n_images, d_images);
+    if (rc) return rc;
+    // barrier 2: every rank's repaired rows have landed in this rank's image
+    if (n_parts > 1) SRT_CUDA(c, srt::launch_peer_barrier(f, n_parts, part, 0, 3, c->d_barrier_ctr, c->stream));
+    return SRT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
 int srt_render_xray_blocks_device(srt_ctx* c, const srt_params* p, uint32_t n_parts, uint32_t part, uint32_t n_frames,
                                   float* const* d_frames, uint32_t* const* d_flags, uint32_t epoch, const float* d_own_frame,
                                   uint32_t n_images, float* const* d_images)
 {
     if (!c) return SRT_ERR_INVALID;
-    if (!d_own_frame) return fail(c, SRT_ERR_INVALID, "own frame is NULL");
+    if (!p || !d_own_frame) return fail(c, SRT_ERR_INVALID, "params / own frame is NULL");
     if (epoch == 0 || epoch >= 0x7fffffffu) return fail(c, SRT_ERR_INVALID, "epoch counts the frames of this flag set from 1");
-    int rc = srt_render_lbuffer_blocks_device(c, p, n_parts, part, n_frames, d_frames);
+    if (n_parts == 0 || n_parts > 8 || part >= n_parts) return fail(c, SRT_ERR_INVALID, "part %u of %u (1 to 8 parts)", part, n_parts);
+    if (n_frames == 0 || n_frames > 8 || !d_frames || n_images == 0 || n_images > 8 || !d_images)
+        return fail(c, SRT_ERR_INVALID, "1 to 8 frame and image pointers expected");
+    if (n_parts > 1) {
+        if (!d_flags) return fail(c, SRT_ERR_INVALID, "flag arrays required");
+        for (uint32_t j = 0; j < n_parts; ++j) if (!d_flags[j]) return fail(c, SRT_ERR_INVALID, "flag array %u is NULL", j);
+    }
+    SRT_CUDA(c, cudaSetDevice(c->device));
+    // the barriers count their epochs (2 e - 1, 2 e) in device memory; the counter follows the caller's numbering
+    if (!c->d_barrier_ctr) {
+        SRT_CUDA(c, cudaMalloc(&c->d_barrier_ctr, sizeof(uint32_t)));
+        SRT_CUDA(c, cudaMemsetAsync(c->d_barrier_ctr, 0, sizeof(uint32_t), c->stream));
+        c->barrier_epochs = 0;
+    }
+    const uint32_t before = 2 * epoch - 2;
+    if (c->barrier_epochs != before) {                     // a new numbering (another set of flag arrays, a restart)
+        SRT_CUDA(c, cudaMemcpyAsync(c->d_barrier_ctr, &before, sizeof before, cudaMemcpyHostToDevice, c->stream));
+        c->barrier_epochs = before;
+    }
+
+    // ---- the call's signature: everything its launches depend on
+    std::vector<uint64_t> sig;
+    sig.reserve(40);
+    auto put = [&](uint64_t v) { sig.push_back(v); };
+    uint64_t bits = 0;
+    std::memcpy(&bits, &p->incident, sizeof(float)); put(bits);
+    std::memcpy(&bits, &p->length_to_cm, sizeof(double)); put(bits);
+    put(((uint64_t)p->repair_depth << 32) | p->kernel); put(((uint64_t)p->flags << 32) | p->pixels_per_thread);
+    put(((uint64_t)n_parts << 48) | ((uint64_t)part << 32) | ((uint64_t)n_frames << 16) | n_images);
+    for (uint32_t i = 0; i < n_frames; ++i) put((uint64_t)(uintptr_t)d_frames[i]);
+    for (uint32_t i = 0; i < n_images; ++i) put((uint64_t)(uintptr_t)d_images[i]);
+    for (uint32_t j = 0; j < n_parts && n_parts > 1; ++j) put((uint64_t)(uintptr_t)d_flags[j]);
+    put((uint64_t)(uintptr_t)d_own_frame); put((uint64_t)(uintptr_t)c->stream);
+    put(c->pack_serial); put(((uint64_t)c->cnt_parity << 32) | c->scan_max_ctas);
+    static const bool graphs_off = std::getenv("SRT_NO_GRAPH") != nullptr;
+    const bool forced = c->force_cand_cap || c->force_pix_cap || c->force_bin_cap || c->force_scan_cols;
+    const bool may_graph = !graphs_off && c->packed && !c->profiling && !c->count_exact && !forced;
+
+    srt_ctx::FrameGraph* g = nullptr;
+    for (auto& e : c->frame_graphs) if (e.sig == sig) { g = &e; break; }
+    if (may_graph && g && g->exec && g->lists_key_after == c->lists_key) {
+        // replay: the graph holds a scan that counts into this parity's counters and clears the other set
+        SRT_CUDA(c, cudaGraphLaunch(g->exec, c->stream));
+        if (g->flips_parity) c->cnt_parity ^= 1;
+        c->barrier_epochs += 2;
+        c->timing_pending = false;
+        return SRT_OK;
+    }
+    if (may_graph && g && !g->exec && g->steady_runs >= 1 && g->lists_key_after == c->lists_key) {
+        // the signature has run in the steady state before (no packing, no list verification, no allocation): capture it
+        const int parity0 = c->cnt_parity;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc_seq = frame_sequence(c, p, n_parts, part, n_frames, d_frames, d_flags, d_own_frame, n_images, d_images);
+            const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+            const bool clean = rc_seq == SRT_OK && ce == cudaSuccess && graph && !c->verified_last_render;
+            c->cnt_parity = parity0;                       // nothing has run yet
+            if (clean && cudaGraphInstantiate(&g->exec, graph, 0) != cudaSuccess) g->exec = nullptr;
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            if (clean && g->exec) {
+                SRT_CUDA(c, cudaGraphLaunch(g->exec, c->stream));
+                if (g->flips_parity) c->cnt_parity ^= 1;
+                c->barrier_epochs += 2;
+                c->timing_pending = false;
+                return SRT_OK;
+            }
+            g->steady_runs = 0;                            // not capturable as it is: run it normally below
+        }
+    }
+    // ---- plain launches
+    const uint64_t lists_before = c->lists_key;
+    const int parity_before = c->cnt_parity;
+    const int rc = frame_sequence(c, p, n_parts, part, n_frames, d_frames, d_flags, d_own_frame, n_images, d_images);
     if (rc) return rc;
-    // barrier 1 (epoch 2 e - 1): every rank's rows have landed in this rank's L frame
-    if (n_parts > 1 && (rc = srt_peer_barrier_device(c, n_parts, part, d_flags, 2 * epoch - 1, 3)) != 0) return rc;
-    rc = srt_repair_blocks_device(c, p, n_parts, part, d_own_frame, n_images, d_images);
-    if (rc) return rc;
-    // barrier 2 (epoch 2 e): every rank's repaired rows have landed in this rank's image
-    if (n_parts > 1 && (rc = srt_peer_barrier_device(c, n_parts, part, d_flags, 2 * epoch, 3)) != 0) return rc;
+    c->barrier_epochs += 2;
+    if (may_graph) {
+        if (!g) {
+            if (c->frame_graphs.size() >= 16) {            // bounded cache: drop the oldest entry
+                if (c->frame_graphs.front().exec) cudaGraphExecDestroy(c->frame_graphs.front().exec);
+                c->frame_graphs.erase(c->frame_graphs.begin());
+            }
+            c->frame_graphs.emplace_back();
+            g = &c->frame_graphs.back();
+            g->sig = sig;
+        }
+        const bool steady = !c->verified_last_render && lists_before == c->lists_key;
+        g->lists_key_after = c->lists_key;                 // a replay is valid while no other launch geometry has been verified since
+        g->flips_parity = parity_before != c->cnt_parity;  // the filtered path ran: its scan alternates between the two counter sets
+        g->steady_runs = steady ? g->steady_runs + 1 : 0;
+    }
     return SRT_OK;
 }
 

@@ -138,18 +138,35 @@ def test_fused_frame_call_with_one_rank_equals_render_xray(gpu_ctx, srtlib, drag
     frame = torch.zeros(300 * 150, dtype=torch.float32, device="cuda"); img = torch.zeros_like(frame)
     flags = torch.zeros(FLAG_WORDS, dtype=torch.int32, device="cuda")
     args = Context.frame_call_args(p, [frame.data_ptr()], [flags.data_ptr()], [img.data_ptr()])
-    for e in (1, 2, 3):
+    gpu_ctx.set_profiling(False)                             # steady-state calls are captured into a CUDA graph and replayed
+    try:
+        for e in range(1, 13):
+            img.fill_(float("nan")); frame.fill_(float("nan"))
+            gpu_ctx.synchronize(); torch.cuda.synchronize()
+            gpu_ctx.render_xray_blocks_device(args, 1, 0, e, frame.data_ptr())
+            gpu_ctx.synchronize()
+            assert torch.equal(img.view(torch.int32), want), e
+        # the sharded repair pass alone: three shares of the frame into one image == the full-frame repair (300 is not a
+        # multiple of 4 x 256 threads, 150 rows leave a ragged last block)
         img.fill_(float("nan"))
-        gpu_ctx.render_xray_blocks_device(args, 1, 0, e, frame.data_ptr())
+        for part in range(3):
+            gpu_ctx.repair_blocks_device(p, 3, part, frame.data_ptr(), [img.data_ptr()])
         gpu_ctx.synchronize()
         assert torch.equal(img.view(torch.int32), want)
-    # the sharded repair pass alone: three shares of the frame into one image == the full-frame repair (300 is not a
-    # multiple of 4 x 256 threads, 150 rows leave a ragged last block)
-    img.fill_(float("nan"))
-    for part in range(3):
-        gpu_ctx.repair_blocks_device(p, 3, part, frame.data_ptr(), [img.data_ptr()])
-    gpu_ctx.synchronize()
-    assert torch.equal(img.view(torch.int32), want)
+        # a new camera: the graphs of the old one must not be replayed
+        cam2 = srtlib.camera_from_bbox(lo, hi, 300, 150); cam2.pixel_spacing[0] *= 0.8; cam2.pixel_spacing[1] *= 0.8
+        gpu_ctx.set_camera(cam2)
+        want2 = torch.from_numpy(gpu_ctx.render_xray(p).view(np.int32)).cuda()
+        assert not torch.equal(want2, want)
+        for e in range(13, 21):
+            img.fill_(float("nan"))
+            torch.cuda.synchronize()
+            gpu_ctx.render_xray_blocks_device(args, 1, 0, e, frame.data_ptr())
+            gpu_ctx.synchronize()
+            assert torch.equal(img.view(torch.int32), want2), e
+        gpu_ctx.set_camera(cam)
+    finally:
+        gpu_ctx.set_profiling(True)
     from simpleraytracing_b200 import SrtError
     with pytest.raises(SrtError):
         gpu_ctx.peer_barrier_device(2, 0, [flags.data_ptr(), flags.data_ptr()], 1, phases=0)
