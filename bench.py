@@ -503,6 +503,15 @@ def run_ours(args):
             ectx.render_xray(p_, out=img)                             # synchronous: returns with the image in host memory
 
         e2e_ms = wall_timed(lambda: plugin_call(host_image, host_meshes), e2e_steps, 2)
+        # the frame reaches a pageable buffer through a pinned staging area + copy threads (srt_set_host_copy_threads,
+        # default = from the core count); the same call with the driver's own pageable copy (0) and other thread counts
+        copy_sweep = {}
+        for threads in (0, 1, 2, 4, 7):
+            ectx.set_host_copy_threads(threads)
+            copy_sweep[str(threads)] = wall_timed(lambda: plugin_call(host_image, host_meshes), e2e_steps, 2) / e2e_steps
+        ectx.set_host_copy_threads(-1)
+        e2e["pageable_copy"] = {"ms_per_step_by_helper_threads": copy_sweep, "default_threads": "half of the host cores - 1, at most 7",
+                                "note": "0 = cudaMemcpyAsync into the pageable buffer (the driver stages it on one thread)"}
         pin_img = PinnedArray(lib, (H * W,), np.float32)
         pin_tri = [PinnedArray(lib, m[0].shape, np.float32) for m in meshes]
         for pa, m in zip(pin_tri, meshes):

@@ -169,6 +169,14 @@ int  srt_set_profiling(srt_ctx* ctx, int enable);
  * register file free lets the short, latency-bound kernels of another frame (another context on another stream) run
  * beside it.  Tuning knob for frame pipelining; results never change. */
 int  srt_set_scan_residency(srt_ctx* ctx, uint32_t max_ctas_per_sm);
+/* Host threads (besides the caller's) that move a frame into a PAGEABLE buffer the caller passed to a host-pointer entry
+ * point (srt_render_xray, srt_render_xray_sorted, srt_render_lbuffer, srt_repair, srt_render_shaded,
+ * srt_multi_render_xray): frames of 2 MiB or more land chunk by chunk in a pinned staging area of the context and these
+ * threads copy every chunk that has arrived while the next ones are in flight (the driver's own pageable copy runs on
+ * one thread: 1.0 ms for a 2048^2 frame).  -1 = default (half of the host's cores, at most 7; environment variable
+ * SRT_COPY_THREADS overrides), 0 = off (plain cudaMemcpyAsync), at most 32.  Page-locked buffers (srt_host_alloc) are
+ * always written by the DMA engine directly.  The bytes returned never depend on this setting. */
+int  srt_set_host_copy_threads(srt_ctx* ctx, int threads);
 
 /* ---- host-side helpers (pure CPU arithmetic, exact reference op order) --- */
 /* TriangleMesh::computeBoundingBox + getBBox (src/TriangleMesh.cxx:192-228, lbuffer.cxx:585-608). */
@@ -353,6 +361,11 @@ int  srt_debug_pack_info(uint32_t* pad_to, uint32_t* box_w, uint32_t* box_h);
  * of the two level-0 strips for a box of box_w x box_h pixels, 0 = default box).  Any output may be NULL. */
 int  srt_debug_prepack(const float* vertices, uint32_t n_triangles, const srt_camera* cam, uint32_t box_w, uint32_t box_h,
                        float* exact16, float* filt12, float* filt2_8, uint32_t* n_padded, uint32_t* n_unfilterable);
+/* Diagnostic, host only (no GPU needed): the thread pool behind srt_set_host_copy_threads copies `bytes` from src to dst
+ * in chunks of chunk_bytes with `threads` helper threads (0 = the calling thread alone). */
+int  srt_debug_host_copy(void* dst, const void* src, size_t bytes, size_t chunk_bytes, int threads);
+/* Diagnostic: number of device-to-host copies of the context that went through the pinned staging area so far. */
+int  srt_debug_host_copy_stats(srt_ctx* ctx, uint64_t* staged_copies);
 /* Diagnostic: the same arrays as computed ON THE GPU for mesh `mesh` of the context's scene. */
 int  srt_debug_download_packed(srt_ctx* ctx, int mesh, float* exact16, float* filt12, float* filt2_8);
 

@@ -70,7 +70,7 @@ EXPORTS = [
     "srt_multi_set_camera", "srt_multi_render_xray_device", "srt_multi_synchronize", "srt_multi_frame",
     "srt_multi_render_xray", "srt_multi_last_timing",
     "srt_set_profiling", "srt_set_scan_residency", "srt_peer_barrier_device", "srt_render_xray_blocks_device",
-    "srt_repair_blocks_device",
+    "srt_repair_blocks_device", "srt_set_host_copy_threads", "srt_debug_host_copy", "srt_debug_host_copy_stats",
 ]
 
 
@@ -153,6 +153,9 @@ class Library:
         L.srt_multi_last_timing.argtypes = [vp, vp, C.POINTER(C.c_float)]
         L.srt_set_profiling.argtypes = [vp, i32]
         L.srt_set_scan_residency.argtypes = [vp, u32]
+        L.srt_set_host_copy_threads.argtypes = [vp, i32]
+        L.srt_debug_host_copy.argtypes = [vp, vp, C.c_size_t, C.c_size_t, i32]
+        L.srt_debug_host_copy_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.srt_peer_barrier_device.argtypes = [vp, u32, u32, C.POINTER(C.c_void_p), u32, u32]
         L.srt_render_xray_blocks_device.argtypes = [vp, C.POINTER(Params), u32, u32, u32, C.POINTER(C.c_void_p),
                                                     C.POINTER(C.c_void_p), u32, vp, u32, C.POINTER(C.c_void_p)]
@@ -350,6 +353,15 @@ class Context:
 
     def set_scan_residency(self, max_ctas_per_sm=0):
         self._ck(self.lib.srt_set_scan_residency(self.h, int(max_ctas_per_sm)))
+
+    def set_host_copy_threads(self, threads=-1):
+        """Helper threads for frames returned into pageable host buffers (-1 = default, 0 = the driver's own copy)."""
+        self._ck(self.lib.srt_set_host_copy_threads(self.h, int(threads)))
+
+    def staged_copies(self):
+        n = C.c_uint64(0)
+        self._ck(self.lib.srt_debug_host_copy_stats(self.h, C.byref(n)))
+        return int(n.value)
 
     def peer_barrier_device(self, n_ranks, rank, flag_ptrs, epoch, phases=3):
         arr = (C.c_void_p * len(flag_ptrs))(*[C.c_void_p(int(q)) for q in flag_ptrs])

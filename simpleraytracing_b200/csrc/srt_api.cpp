@@ -15,12 +15,15 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
 #include <nvjpeg.h>
 
+#include "host_copy.h"
 #include "kernels.h"
 #include "prepack.h"
 
@@ -137,6 +140,13 @@ struct srt_ctx {
     // per-bin triangle lists of the culled kernel
     uint32_t* d_bin_entries = nullptr; uint32_t* d_bin_counts = nullptr; size_t bin_entries_cap = 0, bin_counts_cap = 0;
     bool counters_pending = false, timing_pending = false;
+    // frames returned into PAGEABLE host buffers (copy_to_host): a pinned staging area the DMA engine fills chunk by chunk,
+    // one event per chunk, and a few threads that move the chunks that have landed into the caller's buffer (host_copy.h)
+    void* h_stage = nullptr; size_t stage_cap = 0;
+    std::vector<cudaEvent_t> stage_ev;
+    std::unique_ptr<srt::HostCopyPool> copy_pool;
+    int copy_threads = -1;               // threads besides the caller's: -1 = from the core count, 0 = leave pageable copies to the driver
+    uint64_t staged_copies = 0;          // copies that went through the staging area (srt_debug_host_copy_stats)
 
     srt_timing timing{};
 };
@@ -213,6 +223,100 @@ int ensure_frame(srt_ctx* c, size_t pixels)
     SRT_CUDA(c, cudaMalloc(&c->d_ssum, pixels * 4));
     SRT_CUDA(c, cudaMalloc(&c->d_hits, pixels * 4));
     c->frame_cap = pixels;
+    return SRT_OK;
+}
+
+// ---- device -> caller's host buffer ---------------------------------------------------------------------------------
+constexpr size_t kStageChunk = 1u << 20;        // bytes per DMA chunk (one event each)
+constexpr size_t kStageBytes = 32u << 20;       // pinned staging area of a context; larger frames go through it in rounds
+constexpr size_t kStageMin = 2u << 20;          // smaller copies are left to the driver
+
+int default_copy_threads()
+{
+    static const int n = [] {
+        if (const char* e = std::getenv("SRT_COPY_THREADS")) return std::max(0, std::min(32, std::atoi(e)));
+        const unsigned hw = std::thread::hardware_concurrency();      // 0 = unknown
+        return (int)std::min(7u, hw / 2 > 0 ? hw / 2 - 1 : 0u);      // with the caller's thread: half of the cores, at most 8
+    }();
+    return n;
+}
+
+void free_stage(srt_ctx* c)
+{
+    c->copy_pool.reset();
+    for (auto& ev : c->stage_ev) if (ev) cudaEventDestroy(ev);
+    c->stage_ev.clear();
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->stage_cap = 0;
+}
+
+// Staging area, events and threads for `threads` helpers; false = not available (the caller falls back to the driver's copy).
+bool ensure_stage(srt_ctx* c, int threads)
+{
+    if (!c->h_stage) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, kStageBytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
+        c->h_stage = p; c->stage_cap = kStageBytes;
+    }
+    const size_t n_ev = c->stage_cap / kStageChunk;
+    while (c->stage_ev.size() < n_ev) {
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+        c->stage_ev.push_back(ev);
+    }
+    if (!c->copy_pool || c->copy_pool->workers() != threads) {
+        c->copy_pool.reset();
+        c->copy_pool.reset(new (std::nothrow) srt::HostCopyPool(threads));
+        if (!c->copy_pool) return false;
+    }
+    return true;
+}
+
+// Copy `bytes` from device memory to the caller's host buffer behind the work already on the context's stream.
+//   * page-locked destination (srt_host_alloc / cudaHostAlloc / registered), small copies, copy threads switched off:
+//     one cudaMemcpyAsync; the caller synchronises the stream afterwards, as before;
+//   * pageable destination of kStageMin bytes or more: DMA chunks into the pinned staging area, and the copy threads move
+//     every chunk that has landed while the next ones are in flight.  Returns with the bytes in place.
+// The bytes that arrive are the same either way (tests/test_gpu_parity.py compares the two).
+int copy_to_host(srt_ctx* c, void* dst, const void* d_src, size_t bytes)
+{
+    if (!bytes) return SRT_OK;
+    const int threads = c->copy_threads >= 0 ? c->copy_threads : default_copy_threads();
+    bool staged = false;
+    if (bytes >= kStageMin && threads > 0) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, dst) == cudaSuccess) staged = at.type == cudaMemoryTypeUnregistered;
+        else cudaGetLastError();
+    }
+    if (staged && !ensure_stage(c, threads)) staged = false;
+    if (!staged) {
+        SRT_CUDA(c, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        return SRT_OK;
+    }
+    const char* src = (const char*)d_src;
+    char* out = (char*)dst;
+    char* stage = (char*)c->h_stage;
+    cudaError_t err = cudaSuccess;
+    for (size_t done = 0; done < bytes && err == cudaSuccess; ) {
+        const size_t round = std::min(bytes - done, c->stage_cap);
+        const size_t n_chunks = (round + kStageChunk - 1) / kStageChunk;
+        size_t issued = 0;
+        for (; issued < n_chunks && err == cudaSuccess; ++issued) {
+            const size_t off = issued * kStageChunk, n = std::min(kStageChunk, round - off);
+            err = cudaMemcpyAsync(stage + off, src + done + off, n, cudaMemcpyDeviceToHost, c->stream);
+            if (err == cudaSuccess) err = cudaEventRecord(c->stage_ev[issued], c->stream);
+            if (err != cudaSuccess) break;
+        }
+        for (size_t i = 0; i < issued && err == cudaSuccess; ++i) {
+            const size_t off = i * kStageChunk, n = std::min(kStageChunk, round - off);
+            err = cudaEventSynchronize(c->stage_ev[i]);
+            if (err == cudaSuccess) c->copy_pool->submit(out + done + off, stage + off, n);
+        }
+        c->copy_pool->drain();                              // also on errors: no copy may outlive this call
+        done += round;
+    }
+    if (err != cudaSuccess) return fail(c, SRT_ERR_CUDA, "staged device-to-host copy: %s", cudaGetErrorString(err));
+    ++c->staged_copies;
     return SRT_OK;
 }
 
@@ -675,7 +779,7 @@ void srt_destroy(srt_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    free_scene(c); free_frame(c);
+    free_scene(c); free_frame(c); free_stage(c);
     for (auto& g : c->frame_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     c->frame_graphs.clear();
     cudaFree(c->d_barrier_ctr);
@@ -714,6 +818,32 @@ int srt_set_scan_residency(srt_ctx* c, uint32_t max_ctas_per_sm)
     if (!c) return SRT_ERR_INVALID;
     if (max_ctas_per_sm != 0 && max_ctas_per_sm < 4) return fail(c, SRT_ERR_INVALID, "the scan can be capped at 4 or more CTAs per SM (0 = no cap)");
     c->scan_max_ctas = max_ctas_per_sm;
+    return SRT_OK;
+}
+
+int srt_set_host_copy_threads(srt_ctx* c, int threads)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (threads < -1 || threads > 32) return fail(c, SRT_ERR_INVALID, "copy threads: -1 (default), 0 (off) ... 32");
+    c->copy_threads = threads;
+    return SRT_OK;
+}
+
+int srt_debug_host_copy(void* dst, const void* src, size_t bytes, size_t chunk_bytes, int threads)
+{
+    if ((!dst || !src) && bytes) return SRT_ERR_INVALID;
+    if (chunk_bytes == 0 || threads < 0 || threads > 32) return SRT_ERR_INVALID;
+    srt::HostCopyPool pool(threads);
+    for (size_t off = 0; off < bytes; off += chunk_bytes)
+        pool.submit((char*)dst + off, (const char*)src + off, std::min(chunk_bytes, bytes - off));
+    pool.drain();
+    return SRT_OK;
+}
+
+int srt_debug_host_copy_stats(srt_ctx* c, uint64_t* staged_copies)
+{
+    if (!c || !staged_copies) return SRT_ERR_INVALID;
+    *staged_copies = c->staged_copies;
     return SRT_OK;
 }
 
@@ -1153,10 +1283,10 @@ int srt_render_lbuffer(srt_ctx* c, const srt_params* p, uint32_t rb, uint32_t re
     if (rc) return rc;
     const size_t off = (size_t)rb * W, cnt = (size_t)(re - rb) * W;
     if (cnt) {
-        SRT_CUDA(c, cudaMemcpyAsync(L_out + off, c->d_L + off, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
-        if (dist_out) SRT_CUDA(c, cudaMemcpyAsync(dist_out + off, c->d_dist + off, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
-        if (ssum_out) SRT_CUDA(c, cudaMemcpyAsync(ssum_out + off, c->d_ssum + off, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
-        if (hits_out) SRT_CUDA(c, cudaMemcpyAsync(hits_out + off, c->d_hits + off, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+        if ((rc = copy_to_host(c, L_out + off, c->d_L + off, cnt * 4)) != 0) return rc;
+        if (dist_out && (rc = copy_to_host(c, dist_out + off, c->d_dist + off, cnt * 4)) != 0) return rc;
+        if (ssum_out && (rc = copy_to_host(c, ssum_out + off, c->d_ssum + off, cnt * 4)) != 0) return rc;
+        if (hits_out && (rc = copy_to_host(c, hits_out + off, c->d_hits + off, cnt * 4)) != 0) return rc;
     }
     if (c->profiling) SRT_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1191,7 +1321,7 @@ int srt_repair(srt_ctx* c, const srt_params* p, const float* L_in, float* image_
     SRT_CUDA(c, cudaMemcpyAsync(c->d_L, L_in, pixels * 4, cudaMemcpyHostToDevice, c->stream));
     rc = srt_repair_device(c, p, c->d_L, c->d_img);
     if (rc) return rc;
-    SRT_CUDA(c, cudaMemcpyAsync(image_out, c->d_img, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = copy_to_host(c, image_out, c->d_img, pixels * 4)) != 0) return rc;
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (int erc = elapsed_ms(c, &c->timing.repair_ms, 2, 3)) return erc;
     c->timing.launches = 1;
@@ -1212,7 +1342,7 @@ int srt_render_xray(srt_ctx* c, const srt_params* p, float* image_out)
     if (rc) return rc;
     rc = srt_repair_device(c, p, c->d_L, c->d_img);
     if (rc) return rc;
-    SRT_CUDA(c, cudaMemcpyAsync(image_out, c->d_img, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = copy_to_host(c, image_out, c->d_img, pixels * 4)) != 0) return rc;
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (int erc = elapsed_ms(c, &c->timing.render_ms, 0, 1)) return erc;
     if (int erc = elapsed_ms(c, &c->timing.repair_ms, 2, 3)) return erc;
@@ -1241,7 +1371,7 @@ int srt_render_xray_sorted(srt_ctx* c, const srt_params* p, float* image_out)
     if (rc) return rc;
     rc = render_device(c, p, 0, c->camera.height, c->d_img, nullptr, nullptr, nullptr, 0, 0, /*mode*/ 2);
     if (rc) return rc;
-    SRT_CUDA(c, cudaMemcpyAsync(image_out, c->d_img, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = copy_to_host(c, image_out, c->d_img, pixels * 4)) != 0) return rc;
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (int erc = elapsed_ms(c, &c->timing.render_ms, 0, 1)) return erc;
     c->timing.repair_ms = 0.0f;
@@ -1415,7 +1545,7 @@ int srt_render_shaded(srt_ctx* c, const srt_params* p, const srt_light* light, c
     }
     int rc = srt_render_shaded_device(c, p, light, background_rgb, c->d_rgb, nullptr);
     if (rc) return rc;
-    SRT_CUDA(c, cudaMemcpyAsync(rgb_out, c->d_rgb, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = copy_to_host(c, rgb_out, c->d_rgb, bytes)) != 0) return rc;
     SRT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (int erc = elapsed_ms(c, &c->timing.render_ms, 0, 1)) return erc;
     if (int erc = elapsed_ms(c, &c->timing.repair_ms, 2, 3)) return erc;     // shade pass time
@@ -1799,7 +1929,8 @@ int srt_multi_render_xray(srt_multi* m, const srt_params* params, float* image_o
     int rc = srt_multi_render_xray_device(m, params);
     if (rc) return rc;
     SRT_MCUDA(m, cudaSetDevice(m->dev[0]));
-    SRT_MCUDA(m, cudaMemcpyAsync(image_out, m->img[0], (size_t)m->W * m->H * sizeof(float), cudaMemcpyDeviceToHost, m->ctx[0]->stream));
+    if ((rc = copy_to_host(m->ctx[0], image_out, m->img[0], (size_t)m->W * m->H * sizeof(float))) != 0)
+        return mfail(m, rc, "%s", m->ctx[0]->error.c_str());
     return srt_multi_synchronize(m);
 }
 

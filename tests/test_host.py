@@ -174,3 +174,21 @@ def test_unfilterable_triangles_always_survive(srtlib, oracle, dragon):
     assert pk["unfilterable"] == 3
     for k in (1, 3, 4):
         assert (pk["filt"][k] == 0).all() and (pk["filt2"][k] == 0).all()
+
+
+def test_host_copy_pool_moves_every_byte(srtlib):
+    """The thread pool behind srt_set_host_copy_threads (csrc/host_copy.h; frames returned into pageable buffers):
+    every byte arrives, nothing outside the destination is touched, for any chunk size and thread count."""
+    lib = srtlib.lib
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 255, 3_000_017, dtype=np.uint8)
+    for it in range(200):
+        n = int(rng.integers(0, src.size)) if it % 4 else int(rng.integers(0, 5000))
+        chunk = int(rng.integers(1, 400_000)) if it % 4 else int(rng.integers(1, 64))
+        threads = int(rng.integers(0, 9))
+        dst = np.full(n + 16, 7, np.uint8)
+        assert lib.srt_debug_host_copy(dst.ctypes.data + 8, src.ctypes.data, n, chunk, threads) == 0
+        assert (dst[8:8 + n] == src[:n]).all() and (dst[:8] == 7).all() and (dst[8 + n:] == 7).all()
+    assert lib.srt_debug_host_copy(None, None, 0, 1, 0) == 0
+    assert lib.srt_debug_host_copy(dst.ctypes.data, src.ctypes.data, 8, 0, 1) != 0          # chunk size 0
+    assert lib.srt_debug_host_copy(dst.ctypes.data, src.ctypes.data, 8, 8, 33) != 0         # too many threads
