@@ -510,7 +510,7 @@ def run_ours(args):
             ectx.set_host_copy_threads(threads)
             copy_sweep[str(threads)] = wall_timed(lambda: plugin_call(host_image, host_meshes), e2e_steps, 2) / e2e_steps
         ectx.set_host_copy_threads(-1)
-        e2e["pageable_copy"] = {"ms_per_step_by_helper_threads": copy_sweep, "default_threads": "half of the host cores - 1, at most 7",
+        e2e["pageable_copy"] = {"ms_per_step_by_helper_threads": copy_sweep, "default_threads": "a quarter of the host cores, at most 4",
                                 "note": "0 = cudaMemcpyAsync into the pageable buffer (the driver stages it on one thread)"}
         pin_img = PinnedArray(lib, (H * W,), np.float32)
         pin_tri = [PinnedArray(lib, m[0].shape, np.float32) for m in meshes]

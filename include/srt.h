@@ -173,7 +173,7 @@ int  srt_set_scan_residency(srt_ctx* ctx, uint32_t max_ctas_per_sm);
  * point (srt_render_xray, srt_render_xray_sorted, srt_render_lbuffer, srt_repair, srt_render_shaded,
  * srt_multi_render_xray): frames of 2 MiB or more land chunk by chunk in a pinned staging area of the context and these
  * threads copy every chunk that has arrived while the next ones are in flight (the driver's own pageable copy runs on
- * one thread: 1.0 ms for a 2048^2 frame).  -1 = default (half of the host's cores, at most 7; environment variable
+ * one thread: 1.0 ms for a 2048^2 frame).  -1 = default (a quarter of the host's cores, at most 4; environment variable
  * SRT_COPY_THREADS overrides), 0 = off (plain cudaMemcpyAsync), at most 32.  Page-locked buffers (srt_host_alloc) are
  * always written by the DMA engine directly.  The bytes returned never depend on this setting. */
 int  srt_set_host_copy_threads(srt_ctx* ctx, int threads);
@@ -362,8 +362,12 @@ int  srt_debug_pack_info(uint32_t* pad_to, uint32_t* box_w, uint32_t* box_h);
 int  srt_debug_prepack(const float* vertices, uint32_t n_triangles, const srt_camera* cam, uint32_t box_w, uint32_t box_h,
                        float* exact16, float* filt12, float* filt2_8, uint32_t* n_padded, uint32_t* n_unfilterable);
 /* Diagnostic, host only (no GPU needed): the thread pool behind srt_set_host_copy_threads copies `bytes` from src to dst
- * in chunks of chunk_bytes with `threads` helper threads (0 = the calling thread alone). */
-int  srt_debug_host_copy(void* dst, const void* src, size_t bytes, size_t chunk_bytes, int threads);
+ * in chunks of chunk_bytes with `threads` helper threads (0 = the calling thread alone) that poll for work for spin_us
+ * microseconds before they sleep (0 = sleep at once). */
+int  srt_debug_host_copy(void* dst, const void* src, size_t bytes, size_t chunk_bytes, int threads, int spin_us);
+/* Diagnostic: bytes per DMA chunk of that path (0 = default 1 MiB; a power of two from 64 KiB to 32 MiB) and the time an
+ * idle copy thread polls for the next chunk of a frame before it goes back to sleep (-1 = default 2000 us, 0 = never). */
+int  srt_debug_tune_host_copy(srt_ctx* ctx, size_t chunk_bytes, int spin_us);
 /* Diagnostic: number of device-to-host copies of the context that went through the pinned staging area so far. */
 int  srt_debug_host_copy_stats(srt_ctx* ctx, uint64_t* staged_copies);
 /* Diagnostic: the same arrays as computed ON THE GPU for mesh `mesh` of the context's scene. */

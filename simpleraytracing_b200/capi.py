@@ -71,6 +71,7 @@ EXPORTS = [
     "srt_multi_render_xray", "srt_multi_last_timing",
     "srt_set_profiling", "srt_set_scan_residency", "srt_peer_barrier_device", "srt_render_xray_blocks_device",
     "srt_repair_blocks_device", "srt_set_host_copy_threads", "srt_debug_host_copy", "srt_debug_host_copy_stats",
+    "srt_debug_tune_host_copy",
 ]
 
 
@@ -154,8 +155,9 @@ class Library:
         L.srt_set_profiling.argtypes = [vp, i32]
         L.srt_set_scan_residency.argtypes = [vp, u32]
         L.srt_set_host_copy_threads.argtypes = [vp, i32]
-        L.srt_debug_host_copy.argtypes = [vp, vp, C.c_size_t, C.c_size_t, i32]
+        L.srt_debug_host_copy.argtypes = [vp, vp, C.c_size_t, C.c_size_t, i32, i32]
         L.srt_debug_host_copy_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.srt_debug_tune_host_copy.argtypes = [vp, C.c_size_t, i32]
         L.srt_peer_barrier_device.argtypes = [vp, u32, u32, C.POINTER(C.c_void_p), u32, u32]
         L.srt_render_xray_blocks_device.argtypes = [vp, C.POINTER(Params), u32, u32, u32, C.POINTER(C.c_void_p),
                                                     C.POINTER(C.c_void_p), u32, vp, u32, C.POINTER(C.c_void_p)]
@@ -357,6 +359,9 @@ class Context:
     def set_host_copy_threads(self, threads=-1):
         """Helper threads for frames returned into pageable host buffers (-1 = default, 0 = the driver's own copy)."""
         self._ck(self.lib.srt_set_host_copy_threads(self.h, int(threads)))
+
+    def tune_host_copy(self, chunk_bytes=0, spin_us=-1):
+        self._ck(self.lib.srt_debug_tune_host_copy(self.h, int(chunk_bytes), int(spin_us)))
 
     def staged_copies(self):
         n = C.c_uint64(0)

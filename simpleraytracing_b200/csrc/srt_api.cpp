@@ -146,6 +146,8 @@ struct srt_ctx {
     std::vector<cudaEvent_t> stage_ev;
     std::unique_ptr<srt::HostCopyPool> copy_pool;
     int copy_threads = -1;               // threads besides the caller's: -1 = from the core count, 0 = leave pageable copies to the driver
+    size_t copy_chunk = 0;               // bytes per DMA chunk; 0 = kStageChunk (srt_debug_tune_host_copy)
+    int copy_spin_us = -1;               // how long an idle copy thread polls for the next chunk; -1 = kCopySpinUs
     uint64_t staged_copies = 0;          // copies that went through the staging area (srt_debug_host_copy_stats)
 
     srt_timing timing{};
@@ -230,13 +232,16 @@ int ensure_frame(srt_ctx* c, size_t pixels)
 constexpr size_t kStageChunk = 1u << 20;        // bytes per DMA chunk (one event each)
 constexpr size_t kStageBytes = 32u << 20;       // pinned staging area of a context; larger frames go through it in rounds
 constexpr size_t kStageMin = 2u << 20;          // smaller copies are left to the driver
+constexpr int kCopySpinUs = 2000;               // copy threads poll this long for a frame's chunks before they sleep again
 
 int default_copy_threads()
 {
     static const int n = [] {
         if (const char* e = std::getenv("SRT_COPY_THREADS")) return std::max(0, std::min(32, std::atoi(e)));
+        // measured on the B200 boxes (16 cores): 16 MiB move at 17 / 32 / 44 / 56 / 59 / 43 GB/s with 0 / 1 / 2 / 4 / 7 / 12
+        // helpers, and the whole srt_render_xray call is shortest with 4 (gpurun_out/r02e_*): a quarter of the cores, at most 4
         const unsigned hw = std::thread::hardware_concurrency();      // 0 = unknown
-        return (int)std::min(7u, hw / 2 > 0 ? hw / 2 - 1 : 0u);      // with the caller's thread: half of the cores, at most 8
+        return (int)std::min(4u, hw / 4);
     }();
     return n;
 }
@@ -258,15 +263,17 @@ bool ensure_stage(srt_ctx* c, int threads)
         if (cudaHostAlloc(&p, kStageBytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
         c->h_stage = p; c->stage_cap = kStageBytes;
     }
-    const size_t n_ev = c->stage_cap / kStageChunk;
+    const size_t chunk = c->copy_chunk ? c->copy_chunk : kStageChunk;
+    const size_t n_ev = (c->stage_cap + chunk - 1) / chunk;
     while (c->stage_ev.size() < n_ev) {
         cudaEvent_t ev = nullptr;
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
         c->stage_ev.push_back(ev);
     }
-    if (!c->copy_pool || c->copy_pool->workers() != threads) {
+    const unsigned spin = (unsigned)(c->copy_spin_us >= 0 ? c->copy_spin_us : kCopySpinUs);
+    if (!c->copy_pool || c->copy_pool->workers() != threads || c->copy_pool->spin_us() != spin) {
         c->copy_pool.reset();
-        c->copy_pool.reset(new (std::nothrow) srt::HostCopyPool(threads));
+        c->copy_pool.reset(new (std::nothrow) srt::HostCopyPool(threads, spin));
         if (!c->copy_pool) return false;
     }
     return true;
@@ -296,19 +303,21 @@ int copy_to_host(srt_ctx* c, void* dst, const void* d_src, size_t bytes)
     const char* src = (const char*)d_src;
     char* out = (char*)dst;
     char* stage = (char*)c->h_stage;
+    const size_t chunk = c->copy_chunk ? c->copy_chunk : kStageChunk;
     cudaError_t err = cudaSuccess;
     for (size_t done = 0; done < bytes && err == cudaSuccess; ) {
         const size_t round = std::min(bytes - done, c->stage_cap);
-        const size_t n_chunks = (round + kStageChunk - 1) / kStageChunk;
+        const size_t n_chunks = (round + chunk - 1) / chunk;
         size_t issued = 0;
+        c->copy_pool->activate();                           // the threads wake up while the stream is still busy
         for (; issued < n_chunks && err == cudaSuccess; ++issued) {
-            const size_t off = issued * kStageChunk, n = std::min(kStageChunk, round - off);
+            const size_t off = issued * chunk, n = std::min(chunk, round - off);
             err = cudaMemcpyAsync(stage + off, src + done + off, n, cudaMemcpyDeviceToHost, c->stream);
             if (err == cudaSuccess) err = cudaEventRecord(c->stage_ev[issued], c->stream);
             if (err != cudaSuccess) break;
         }
         for (size_t i = 0; i < issued && err == cudaSuccess; ++i) {
-            const size_t off = i * kStageChunk, n = std::min(kStageChunk, round - off);
+            const size_t off = i * chunk, n = std::min(chunk, round - off);
             err = cudaEventSynchronize(c->stage_ev[i]);
             if (err == cudaSuccess) c->copy_pool->submit(out + done + off, stage + off, n);
         }
@@ -829,11 +838,23 @@ int srt_set_host_copy_threads(srt_ctx* c, int threads)
     return SRT_OK;
 }
 
-int srt_debug_host_copy(void* dst, const void* src, size_t bytes, size_t chunk_bytes, int threads)
+int srt_debug_tune_host_copy(srt_ctx* c, size_t chunk_bytes, int spin_us)
+{
+    if (!c) return SRT_ERR_INVALID;
+    if (chunk_bytes != 0 && (chunk_bytes < (64u << 10) || chunk_bytes > kStageBytes || (chunk_bytes & (chunk_bytes - 1)) != 0))
+        return fail(c, SRT_ERR_INVALID, "copy chunk: 0 (default) or a power of two from 64 KiB to 32 MiB");
+    if (spin_us < -1 || spin_us > 1000000) return fail(c, SRT_ERR_INVALID, "spin time: -1 (default), 0 ... 1000000 us");
+    c->copy_chunk = chunk_bytes;
+    c->copy_spin_us = spin_us;
+    return SRT_OK;
+}
+
+int srt_debug_host_copy(void* dst, const void* src, size_t bytes, size_t chunk_bytes, int threads, int spin_us)
 {
     if ((!dst || !src) && bytes) return SRT_ERR_INVALID;
-    if (chunk_bytes == 0 || threads < 0 || threads > 32) return SRT_ERR_INVALID;
-    srt::HostCopyPool pool(threads);
+    if (chunk_bytes == 0 || threads < 0 || threads > 32 || spin_us < 0 || spin_us > 1000000) return SRT_ERR_INVALID;
+    srt::HostCopyPool pool(threads, spin_us > 0 ? (unsigned)spin_us : 0u);
+    pool.activate();
     for (size_t off = 0; off < bytes; off += chunk_bytes)
         pool.submit((char*)dst + off, (const char*)src + off, std::min(chunk_bytes, bytes - off));
     pool.drain();

@@ -186,9 +186,10 @@ def test_host_copy_pool_moves_every_byte(srtlib):
         n = int(rng.integers(0, src.size)) if it % 4 else int(rng.integers(0, 5000))
         chunk = int(rng.integers(1, 400_000)) if it % 4 else int(rng.integers(1, 64))
         threads = int(rng.integers(0, 9))
+        spin_us = int(rng.choice([0, 1, 50, 2000]))
         dst = np.full(n + 16, 7, np.uint8)
-        assert lib.srt_debug_host_copy(dst.ctypes.data + 8, src.ctypes.data, n, chunk, threads) == 0
+        assert lib.srt_debug_host_copy(dst.ctypes.data + 8, src.ctypes.data, n, chunk, threads, spin_us) == 0
         assert (dst[8:8 + n] == src[:n]).all() and (dst[:8] == 7).all() and (dst[8 + n:] == 7).all()
-    assert lib.srt_debug_host_copy(None, None, 0, 1, 0) == 0
-    assert lib.srt_debug_host_copy(dst.ctypes.data, src.ctypes.data, 8, 0, 1) != 0          # chunk size 0
-    assert lib.srt_debug_host_copy(dst.ctypes.data, src.ctypes.data, 8, 8, 33) != 0         # too many threads
+    assert lib.srt_debug_host_copy(None, None, 0, 1, 0, 0) == 0
+    assert lib.srt_debug_host_copy(dst.ctypes.data, src.ctypes.data, 8, 0, 1, 0) != 0       # chunk size 0
+    assert lib.srt_debug_host_copy(dst.ctypes.data, src.ctypes.data, 8, 8, 33, 0) != 0      # too many threads
