@@ -110,9 +110,36 @@ static int cpu_tests()
     return failures ? 1 : 0;
 }
 
+// `parity <in.bin> <out.bin>`: records of 15 floats (ray origin, direction, triangle) -> 9 floats each: the Ray's stored
+// direction, hit flag, t, the Triangle's cached normal and its area.  tests/test_cpp_host.py compares them bit for bit with
+// the reference's own Ray / Triangle classes (oracle/_ref) and with the C oracle.
+static int parity_dump(const char* in_path, const char* out_path)
+{
+    using namespace srt;
+    std::FILE* in = std::fopen(in_path, "rb");
+    std::FILE* out = std::fopen(out_path, "wb");
+    if (!in || !out) { std::printf("ERROR: cannot open files\n"); return 1; }
+    float r[15];
+    size_t n = 0;
+    while (std::fread(r, sizeof(float), 15, in) == 15) {
+        const Ray ray(Vec3(r[0], r[1], r[2]), Vec3(r[3], r[4], r[5]));
+        const Triangle tri(Vec3(r[6], r[7], r[8]), Vec3(r[9], r[10], r[11]), Vec3(r[12], r[13], r[14]));
+        float t = 0.0f;
+        const bool hit = ray.intersect(tri, t);
+        const float o[9] = { ray.getDirection().getX(), ray.getDirection().getY(), ray.getDirection().getZ(), hit ? 1.0f : 0.0f,
+                             hit ? t : 0.0f, tri.getNormal().getX(), tri.getNormal().getY(), tri.getNormal().getZ(), tri.getArea() };
+        std::fwrite(o, sizeof(float), 9, out);
+        ++n;
+    }
+    std::fclose(in); std::fclose(out);
+    std::printf("OK %zu records\n", n);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc >= 2 && std::strcmp(argv[1], "cpu") == 0) return cpu_tests();
+    if (argc >= 4 && std::strcmp(argv[1], "parity") == 0) return parity_dump(argv[2], argv[3]);
     if (argc >= 6 && std::strcmp(argv[1], "gpu") == 0) {
         try {
             std::vector<srt::TriangleMesh> meshes;
@@ -189,6 +216,6 @@ int main(int argc, char** argv)
             return 0;
         } catch (const std::exception& e) { std::printf("ERROR: %s\n", e.what()); return 1; }
     }
-    std::printf("usage: %s cpu | ply <file> | gpu <ply> <W> <H> <out.txt> | shaded <ply> <W> <H> <tex.ppm> <out.ppm>\n", argv[0]);
+    std::printf("usage: %s cpu | parity <in.bin> <out.bin> | ply <file> | gpu <ply> <W> <H> <out.txt> | shaded <ply> <W> <H> <tex.ppm> <out.ppm>\n", argv[0]);
     return 2;
 }

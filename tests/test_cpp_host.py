@@ -47,6 +47,71 @@ def test_host_classes(host_bins):
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
 
 
+def test_host_classes_equal_the_reference_classes_bit_for_bit(host_bins, tmp_path, oracle, reference, dragon):
+    """srt::Ray (constructor + intersect) and srt::Triangle (cached normal, area) of include/srt/*.h against the
+    reference's own classes compiled from /root/reference (oracle/_ref) and the C oracle, on dragon triangles under
+    camera rays, random soups and the degenerate inputs the reference's code paths distinguish."""
+    rng = np.random.default_rng(17)
+    recs = []
+    cam = oracle.camera(dragon)
+    W = H = 256
+    for _ in range(1500):                                   # rays of the 256^2 camera against dragon triangles near them
+        row, col = int(rng.integers(0, H)), int(rng.integers(0, W))
+        _, d = oracle.make_ray(cam, W, H, row, col)
+        tri = dragon[int(rng.integers(0, len(dragon)))]
+        # aim half of the rays at the triangle so that hits, edge cases and misses all occur
+        o = cam.vec("origin")
+        if rng.random() < 0.5:
+            w = rng.dirichlet([1, 1, 1]).astype(np.float32)
+            if rng.random() < 0.3:
+                w = np.array([[1, 0, 0], [0, 1, 0], [0.5, 0.5, 0], [0, 0.5, 0.5]][int(rng.integers(0, 4))], np.float32)
+            d = (tri.reshape(3, 3) * w[:, None]).sum(0).astype(np.float32) - o
+        recs.append(np.concatenate([o, d, tri.reshape(-1)]))
+    for _ in range(1500):                                   # random soups over many scales, rays from anywhere
+        s = np.float32(10.0 ** rng.uniform(-6, 6))
+        tri = (rng.standard_normal(9) * s).astype(np.float32)
+        o = (rng.standard_normal(3) * s * 3).astype(np.float32)
+        d = (tri.reshape(3, 3).mean(0) + rng.standard_normal(3) * s * 0.3 - o).astype(np.float32)
+        if rng.random() < 0.3:
+            d = -d                                          # the triangle lies behind the origin: negative t is accepted
+        recs.append(np.concatenate([o, d, tri]))
+    z = np.zeros(3, np.float32)
+    t0 = np.array([0, 0, 0, 2, 0, 0, 0, 2, 0], np.float32)
+    recs += [np.concatenate([[0.5, 0.5, -1], z, t0]),                            # zero direction stays zero
+             np.concatenate([[0.5, 0.5, -1], [0, 0, 1e-30], t0]),                # tiny direction: length underflows
+             np.concatenate([[0.5, 0.5, 0], [1, 0, 0], t0]),                     # ray in the triangle's plane: det == 0
+             np.concatenate([[0, 0, -1], [0, 0, 1], t0]),                        # through a vertex
+             np.concatenate([[1, 0, -1], [0, 0, 1], t0]),                        # through an edge midpoint
+             np.concatenate([[1, 1, -1], [0, 0, 1], t0]),                        # on the hypotenuse: u + v == 1
+             np.concatenate([[0.5, 0.5, -1], [0, 0, 1], np.array([0, 0, 0, 1, 1, 1, 2, 2, 2], np.float32)]),   # zero-area triangle
+             np.concatenate([[0.5, 0.5, -1], [0, 0, 1], np.zeros(9, np.float32)])]
+    recs = np.asarray(recs, np.float32)
+    (tmp_path / "in.bin").write_bytes(recs.tobytes())
+    r = subprocess.run([str(host_bins / "test_host_api"), "parity", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and f"OK {len(recs)} records" in r.stdout, r.stdout + r.stderr
+    got = np.frombuffer((tmp_path / "out.bin").read_bytes(), np.float32).reshape(len(recs), 9)
+
+    def same(a, b):                                         # bit for bit; NaN (0 / 0 of a degenerate normal) equals NaN
+        a = np.asarray(a, np.float32).reshape(-1); b = np.asarray(b, np.float32).reshape(-1)
+        return bool(((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all())
+
+    hits = 0
+    for rec, g in zip(recs, got):
+        o, d, tri = rec[0:3], rec[3:6], rec[6:15]
+        for impl in (reference, oracle):
+            assert same(g[0:3], impl.ray_direction(d)), ("direction", rec)
+            # the reference's Ray constructor renormalises d itself; the C oracle's intersect takes the stored direction
+            res = impl.intersect(o, d if impl is reference else impl.ray_direction(d), tri)
+            assert bool(g[3]) == res[0], ("hit flag", rec)
+            if res[0]:
+                assert same(g[4], res[1]), ("t", rec)
+            assert same(g[5:8], impl.triangle_normal(tri)), ("normal", rec)
+            assert same(g[8], impl.triangle_area(tri)), ("area", rec)
+        hits += int(g[3])
+    assert 300 < hits < len(recs) - 300                     # both outcomes are well represented
+
+
 @pytest.mark.parametrize("binary", [True, False])
 def test_ply_loader_matches_fixture(host_bins, tmp_path, binary):
     d = np.load(GOLDEN / "dragon_mesh.npz")
