@@ -170,21 +170,24 @@ def cpu_reference_engine():
     return "port", Oracle()
 
 
-def cpu_sample_rate(engine, kind, wl, seconds, threads):
+def cpu_sample_rate(engine, kind, wl, seconds, threads, n_pix=None):
     """Time the CPU L-buffer path on a contiguous pixel range through the frame centre.
-    Brute-force cost is uniform per pixel, so tests/s of the sample is tests/s of the frame."""
+    Brute-force cost is uniform per pixel, so tests/s of the sample is tests/s of the frame.
+    n_pix = None: grow the sample until it takes about `seconds`; else time exactly that many pixels once."""
     tri = wl["meshes"][0][0]
     W, H = wl["W"], wl["H"]
     ntri = len(tri)
     cam = engine.camera(wl["cam_tri"], [len(wl["cam_tri"])]) if kind == "reference" else engine.camera(wl["cam_tri"])
     start = (H // 2) * W
-    n_pix = max(threads * 16, 256)
-    while True:                                   # grow the sample until it takes about `seconds`
+    calibrate = n_pix is None
+    if calibrate:
+        n_pix = max(threads * 16, 256)
+    while True:
         n_pix = int(min(W * H - start, n_pix))
         t0 = time.perf_counter()
         engine.render_lbuffer(tri, [ntri], cam, W, H, pixel_range=(start, start + n_pix - 1), threads=threads)
         dt = max(time.perf_counter() - t0, 1e-4)
-        if dt >= 0.6 * seconds or n_pix >= W * H - start:
+        if not calibrate or dt >= 0.6 * seconds or n_pix >= W * H - start:
             return n_pix * ntri / dt, n_pix, dt
         n_pix = int(n_pix * min(8.0, max(1.5, 1.1 * seconds / dt)))
 
@@ -198,23 +201,29 @@ def run_reference_arm(args):
     W, H = wl["W"], wl["H"]
     kind, eng = cpu_reference_engine()
     threads = os.cpu_count() or 1
+    # a step = one bounded sample of the frame: the sample size is calibrated once (about per_step seconds of work on all
+    # host threads), every warm-up and timed step then renders exactly that pixel range
     per_step = max(0.5, min(8.0, 150.0 / max(1, args.steps + args.warmup)))
+    _, n_pix, _ = cpu_sample_rate(eng, kind, wl, per_step, threads)
     for _ in range(args.warmup):
-        cpu_sample_rate(eng, kind, wl, per_step, threads)
+        cpu_sample_rate(eng, kind, wl, per_step, threads, n_pix)
     pix, secs = 0, 0.0
     for _ in range(args.steps):
-        r, n_pix, dt = cpu_sample_rate(eng, kind, wl, per_step, threads)
-        pix += n_pix; secs += dt
+        r, n, dt = cpu_sample_rate(eng, kind, wl, per_step, threads, n_pix)
+        pix += n; secs += dt
     value = pix * len(tri) / secs
     frame_ms = W * H * len(tri) / value * 1e3
-    sample = f"{pix // max(1, args.steps)} contiguous pixels of the {W}x{H} frame per step, all {len(tri)} triangles"
+    sample = f"{n_pix} contiguous pixels of the {W}x{H} frame per step, all {len(tri)} triangles"
     line = {
         "impl": "reference", "metric": "ray-triangle tests/s (X-ray L-buffer)", "value": value,
         "unit": "tests/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": secs * 1e3 / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "dragon mesh fixture (tests/golden/dragon_mesh.npz) / synthetic; CPU, no GPU used",
+        "ms_per_frame": frame_ms,
         "config": {"workload": wl["name"], "triangles": len(tri),
-                   "ms_per_step_note": "full-frame time extrapolated from the sample (uniform cost per pixel)"},
+                   "step": f"one bounded sample of the frame ({n_pix} of {W * H} pixels x all triangles) on {threads} host threads; "
+                           "ms_per_step is the measured time of a sample, ms_per_frame the full frame extrapolated from it "
+                           "(brute-force cost is uniform per pixel)"},
         "cpu_baseline": {"value": value, "unit": "tests/s", "cores": threads, "cpu_model": cpu_model(), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
