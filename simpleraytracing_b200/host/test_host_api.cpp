@@ -112,7 +112,7 @@ static int cpu_tests()
 
 // `parity <in.bin> <out.bin>`: records of 15 floats (ray origin, direction, triangle) -> 9 floats each: the Ray's stored
 // direction, hit flag, t, the Triangle's cached normal and its area.  tests/test_cpp_host.py compares them bit for bit with
-// the reference's own Ray / Triangle classes (oracle/_ref) and with the C oracle.
+// what the reference's own Ray / Triangle classes compute for the same records.
 static int parity_dump(const char* in_path, const char* out_path)
 {
     using namespace srt;
