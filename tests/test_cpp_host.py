@@ -127,6 +127,119 @@ def test_ply_loader_matches_fixture(host_bins, tmp_path, binary):
     assert int(n) == en and float(s) == pytest.approx(es, rel=1e-12) and float(ws) == pytest.approx(ews, rel=1e-12)
 
 
+def _write_general_ply(path, v, f, fmt, vertex_dtype="f4", index_type=("uchar", "int"), extras=True):
+    """A PLY as scanners / modelling tools write them: normals and colours next to x, y, z, a confidence value BEFORE the
+    coordinates, per-face flags and texture-coordinate lists, an `edge` element between vertices and faces, quads among the
+    triangles; fmt: ascii | binary_little_endian | binary_big_endian."""
+    e = {"ascii": "", "binary_little_endian": "<", "binary_big_endian": ">"}[fmt]
+    np_of = {"char": "i1", "uchar": "u1", "short": "i2", "ushort": "u2", "int": "i4", "uint": "u4", "float": "f4", "double": "f8"}
+    vt = "double" if vertex_dtype == "f8" else "float"
+    hdr = ["ply", f"format {fmt} 1.0", "comment written by the tests", f"element vertex {len(v)}"]
+    if extras:
+        hdr += ["property float confidence"]
+    hdr += [f"property {vt} x", f"property {vt} y", f"property {vt} z"]
+    if extras:
+        hdr += ["property float nx", "property float ny", "property float nz", "property uchar red", "property uchar green",
+                "property uchar blue", "property short tag", f"element edge 2", "property int vertex1", "property int vertex2",
+                "property list uchar ushort marks"]
+    hdr += [f"element face {len(f)}"]
+    if extras:
+        hdr += ["property uchar flags"]
+    hdr += [f"property list {index_type[0]} {index_type[1]} vertex_indices"]
+    if extras:
+        hdr += ["property list uchar float texcoord"]
+    hdr += ["end_header"]
+    rng = np.random.default_rng(0)
+    with open(path, "wb") as fh:
+        fh.write(("\n".join(hdr) + "\n").encode())
+
+        def put(kind, value):
+            if fmt == "ascii":
+                fh.write((("%.17g" if kind in ("float", "double") else "%d") % value + " ").encode())
+            else:
+                fh.write(np.array(value, dtype=e + np_of[kind]).tobytes())
+
+        for p in v:
+            if extras:
+                put("float", float(np.float32(rng.random())))
+            for c in p:
+                put(vt, float(c))
+            if extras:
+                for c in rng.normal(size=3):
+                    put("float", float(np.float32(c)))
+                for c in rng.integers(0, 256, 3):
+                    put("uchar", int(c))
+                put("short", int(rng.integers(-30000, 30000)))
+            if fmt == "ascii":
+                fh.write(b"\n")
+        if extras:
+            for k in range(2):
+                put("int", k); put("int", k + 1); put("uchar", 3)
+                for m in range(3):
+                    put("ushort", 1000 * m + k)
+                if fmt == "ascii":
+                    fh.write(b"\n")
+        for t in f:
+            if extras:
+                put("uchar", int(rng.integers(0, 256)))
+            put(index_type[0], len(t))
+            for i in t:
+                put(index_type[1], int(i))
+            if extras:
+                put("uchar", 2 * len(t))
+                for c in rng.random(2 * len(t)):
+                    put("float", float(np.float32(c)))
+            if fmt == "ascii":
+                fh.write(b"\n")
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "binary_little_endian", "binary_big_endian"])
+@pytest.mark.parametrize("vertex_dtype,index_type,extras", [("f4", ("uchar", "int"), True), ("f8", ("ushort", "uint"), True),
+                                                            ("f4", ("uint", "ushort"), False), ("f4", ("uchar", "uchar"), True)])
+def test_ply_loader_general_layouts(host_bins, tmp_path, fmt, vertex_dtype, index_type, extras):
+    """The loader stands in for Assimp (lbuffer.cxx:518-582): any PLY encoding, property set and element order; only x, y, z
+    and the triangles' vertex_indices are kept, float coordinates bit for bit, in file order."""
+    d = np.load(GOLDEN / "dragon_mesh.npz")
+    nv = 200 if index_type[1] == "uchar" else 2500
+    v = d["vertices"][:nv]
+    f = d["faces"]
+    f = f[(f < nv).all(1)][:3000]
+    faces = [list(t) for t in f]
+    faces.insert(5, [0, 1, 2, 3]); faces.insert(40, [4, 5, 6, 7, 8]); faces.append([0, 1])       # skipped: not triangles
+    p = tmp_path / "mesh.ply"
+    _write_general_ply(p, v.astype(np.float64) if vertex_dtype == "f8" else v, faces, fmt, vertex_dtype, index_type, extras)
+    r = subprocess.run([str(host_bins / "test_host_api"), "ply", str(p)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    n, s_, ws = r.stdout.split()
+    en, es, ews = expected_sums(v, f)
+    assert int(n) == en and len(f) > 100
+    assert float(s_) == pytest.approx(es, rel=1e-12) and float(ws) == pytest.approx(ews, rel=1e-12)
+
+
+def test_ply_loader_reports_truncated_and_inconsistent_files(host_bins, tmp_path):
+    d = np.load(GOLDEN / "dragon_mesh.npz")
+    v, f = d["vertices"][:300], d["faces"]
+    f = [list(t) for t in f[(f < 300).all(1)][:200]]
+    good = tmp_path / "good.ply"
+    _write_general_ply(good, v, f, "binary_little_endian")
+    raw = good.read_bytes()
+    for cut in (len(raw) - 5, len(raw) // 2, raw.index(b"end_header") + 20):
+        bad = tmp_path / "cut.ply"; bad.write_bytes(raw[:cut])
+        r = subprocess.run([str(host_bins / "test_host_api"), "ply", str(bad)], capture_output=True, text=True)
+        assert r.returncode == 1 and "truncated" in r.stdout, (cut, r.stdout)
+    bad = tmp_path / "range.ply"
+    _write_general_ply(bad, v, f + [[0, 1, 300]], "ascii", extras=False)                       # index == number of vertices
+    r = subprocess.run([str(host_bins / "test_host_api"), "ply", str(bad)], capture_output=True, text=True)
+    assert r.returncode == 1 and "out of range" in r.stdout
+    for text in ("ply\nformat ascii 1.0\nelement vertex 1\nproperty float x\nproperty float y\nend_header\n0 0\n",      # no z
+                 "ply\nformat ascii 1.0\nelement vertex 1\nproperty quaternion x\nend_header\n",                         # unknown type
+                 "ply\nformat binary_middle_endian 1.0\nelement vertex 0\nproperty float x\nproperty float y\nproperty float z\nend_header\n",
+                 "ply\nformat ascii 1.0\nelement vertex 0\nproperty float x\n"):                                          # no end_header
+        bad = tmp_path / "hdr.ply"; bad.write_text(text)
+        r = subprocess.run([str(host_bins / "test_host_api"), "ply", str(bad)], capture_output=True, text=True)
+        assert r.returncode == 1 and "ERROR" in r.stdout, text
+
+
 def test_ply_loader_skips_non_triangles_and_rejects_garbage(host_bins, tmp_path):
     p = tmp_path / "quad.ply"
     p.write_text("ply\nformat ascii 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\n"
