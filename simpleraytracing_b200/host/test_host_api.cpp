@@ -14,6 +14,7 @@
 
 #include "srt/PlyLoader.h"
 #include "srt/RenderLoop.h"
+#include "../csrc/host_copy.h"
 
 static int failures = 0;
 #define CHECK(cond) do { if (!(cond)) { std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); ++failures; } } while (0)
@@ -136,9 +137,46 @@ static int parity_dump(const char* in_path, const char* out_path)
     return 0;
 }
 
+// `pool`: one HostCopyPool reused for many frames like a context reuses its pool (activate -> chunks trickle in -> drain,
+// several rounds per frame), for every thread count and polling time; every byte must arrive and none beyond.
+static int pool_tests()
+{
+    uint32_t state = 12345u;
+    auto rnd = [&state] { state = state * 1664525u + 1013904223u; return state >> 8; };
+    const size_t N = 3u << 20;
+    std::vector<unsigned char> src(N), dst(N);
+    for (auto& v : src) v = (unsigned char)rnd();
+    for (unsigned spin : { 0u, 20u, 2000u })
+        for (int threads : { 0, 1, 3, 7 }) {
+            srt::HostCopyPool pool(threads, spin);
+            for (int it = 0; it < 120; ++it) {
+                const size_t n = rnd() % N, chunk = 1 + rnd() % (1u << 18);
+                std::fill(dst.begin(), dst.end(), 0);
+                const int rounds = 1 + (int)(rnd() % 3);
+                size_t done = 0;
+                for (int r = 0; r < rounds; ++r) {
+                    const size_t part = (r == rounds - 1) ? n - done : (n - done) / 2;
+                    pool.activate();
+                    if (it % 7 == 0) std::this_thread::sleep_for(std::chrono::microseconds(rnd() % 300));
+                    for (size_t off = 0; off < part; off += chunk)
+                        pool.submit(dst.data() + done + off, src.data() + done + off, std::min(chunk, part - off));
+                    pool.drain();
+                    done += part;
+                }
+                CHECK(std::memcmp(dst.data(), src.data(), n) == 0);
+                bool clean = true;
+                for (size_t i = n; i < std::min(N, n + 64); ++i) clean = clean && dst[i] == 0;
+                CHECK(clean);
+            }
+        }
+    std::printf(failures ? "%d FAILURES\n" : "OK\n", failures);
+    return failures ? 1 : 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc >= 2 && std::strcmp(argv[1], "cpu") == 0) return cpu_tests();
+    if (argc >= 2 && std::strcmp(argv[1], "pool") == 0) return pool_tests();
     if (argc >= 4 && std::strcmp(argv[1], "parity") == 0) return parity_dump(argv[2], argv[3]);
     if (argc >= 6 && std::strcmp(argv[1], "gpu") == 0) {
         try {
@@ -216,6 +254,6 @@ int main(int argc, char** argv)
             return 0;
         } catch (const std::exception& e) { std::printf("ERROR: %s\n", e.what()); return 1; }
     }
-    std::printf("usage: %s cpu | parity <in.bin> <out.bin> | ply <file> | gpu <ply> <W> <H> <out.txt> | shaded <ply> <W> <H> <tex.ppm> <out.ppm>\n", argv[0]);
+    std::printf("usage: %s cpu | pool | parity <in.bin> <out.bin> | ply <file> | gpu <ply> <W> <H> <out.txt> | shaded <ply> <W> <H> <tex.ppm> <out.ppm>\n", argv[0]);
     return 2;
 }

@@ -47,6 +47,13 @@ def test_host_classes(host_bins):
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
 
 
+def test_host_copy_pool_reused_across_frames(host_bins):
+    """csrc/host_copy.h as a context uses it: one pool, many frames of activate -> submit ... -> drain (several rounds),
+    for 0 - 7 helper threads and polling times 0 / 20 / 2000 us."""
+    r = subprocess.run([str(host_bins / "test_host_api"), "pool"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
+
+
 def test_host_classes_equal_the_reference_classes_bit_for_bit(host_bins, tmp_path, oracle, reference, dragon):
     """srt::Ray (constructor + intersect) and srt::Triangle (cached normal, area) of include/srt/*.h against the
     reference's own classes compiled from /root/reference (oracle/_ref) and the C oracle, on dragon triangles under
